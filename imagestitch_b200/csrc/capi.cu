@@ -1,0 +1,281 @@
+// capi.cu -- extern "C" surface of libvfsms.so (see include/vfsms.h for the contract and reference citations).
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+
+static thread_local char g_err[1024] = "";
+
+void vfsms_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// phase.cu / blend.cu / orb.cu
+void phase_state_destroy(vfsms_ctx *ctx);
+void blend_state_destroy(vfsms_ctx *ctx);
+
+extern "C" {
+
+int vfsms_version(void) { return VFSMS_VERSION; }
+const char *vfsms_last_error(void) { return g_err; }
+
+int vfsms_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int vfsms_create(int device, vfsms_ctx **out)
+{
+    if (!out) { vfsms_set_error("vfsms_create: out is NULL"); return VFSMS_E_ARG; }
+    *out = nullptr;
+    int n = vfsms_device_count();
+    if (n <= 0) { vfsms_set_error("no CUDA device visible: libvfsms has no CPU fallback"); return VFSMS_E_NODEVICE; }
+    if (device < 0 || device >= n) { vfsms_set_error("device %d out of range (0..%d)", device, n - 1); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { vfsms_set_error("device %d is sm_%d%d; libvfsms is built for sm_100a only", device, prop.major, prop.minor); return VFSMS_E_NODEVICE; }
+    vfsms_ctx *ctx = new vfsms_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    int rc = surf_init_tables();
+    if (rc) { delete ctx; return rc; }
+    *out = ctx;
+    return 0;
+}
+
+void vfsms_destroy(vfsms_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    phase_state_destroy(ctx);
+    blend_state_destroy(ctx);
+    SurfWorkspace &w = ctx->surf;
+    DevBuf *bufs[] = { &w.integral, &w.band_tot, &w.cand, &w.sorted, &w.kp, &w.desc, &w.descT, &w.counters, &w.prefix,
+                       &ctx->match.best_idx, &ctx->match.best_dist, &ctx->match.matches, &ctx->match.n_matches,
+                       &ctx->match.table_keys, &ctx->match.table_cnt, &ctx->match.table_first, &ctx->match.bf16_a,
+                       &ctx->match.bf16_b, &ctx->match.cand_topk, &ctx->img_a, &ctx->img_b, &ctx->results,
+                       &ctx->scratch0, &ctx->scratch1, &ctx->scratch2, &ctx->scratch3 };
+    for (DevBuf *b : bufs) b->release();
+    ctx->pinned_in.release(); ctx->pinned_out.release();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int vfsms_synchronize(vfsms_ctx *ctx)
+{
+    if (!ctx) return VFSMS_E_ARG;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+void *vfsms_stream(vfsms_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int64_t vfsms_launch_count(vfsms_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------- SURF, host in / host out
+int vfsms_surf_detect_and_describe(vfsms_ctx *ctx, const uint8_t *image, int rows, int cols, int stride,
+                                   const vfsms_surf_params *params, float *kp_out, float *desc_out, int cap, int *n_out)
+{
+    if (!ctx || !image || !params || !n_out || rows < 1 || cols < 1 || stride < cols) { vfsms_set_error("surf: bad arguments"); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if ((rc = ctx->img_a.reserve((size_t)rows * cols))) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(ctx->img_a.p, cols, image, stride, cols, rows, cudaMemcpyHostToDevice, st));
+    if ((rc = surf_reserve(ctx, 1, rows, cols, params))) return rc;
+    int32_t cnt[4];
+    for (int attempt = 0; attempt < 6; attempt++) {
+        if ((rc = surf_run_batch(ctx, ctx->img_a.as<uint8_t>(), nullptr, 1, 1, rows, cols, cols, 0, params, st))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(cnt, ctx->surf.counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (!(cnt[3] & 3)) break;
+        if ((rc = surf_grow(ctx, cnt[3] & 1, cnt[3] & 2))) return rc;
+        if (attempt == 5) { vfsms_set_error("surf: candidate buffer overflow after regrow"); return VFSMS_E_OVERFLOW; }
+    }
+    const int n = cnt[2];
+    *n_out = n;
+    if (n > cap) { vfsms_set_error("surf: %d keypoints but capacity %d", n, cap); return VFSMS_E_CAPACITY; }
+    const int dim = ctx->surf.dim;
+    if (n > 0) {
+        if (kp_out) CUDA_TRY(cudaMemcpyAsync(kp_out, ctx->surf.kp.p, (size_t)n * KP_STRIDE * 4, cudaMemcpyDeviceToHost, st));
+        if (desc_out) CUDA_TRY(cudaMemcpyAsync(desc_out, ctx->surf.desc.p, (size_t)n * dim * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- matcher, host in / host out
+int vfsms_match_descriptors(vfsms_ctx *ctx, const float *desc_a, int n_a, const float *desc_b, int n_b, int dim,
+                            int feature_type, float param, int32_t *matches_out, int *m_out)
+{
+    if (!ctx || !m_out || n_a < 0 || n_b < 0 || dim < 1) { vfsms_set_error("match: bad arguments"); return VFSMS_E_ARG; }
+    if (feature_type != 1 && feature_type != 2 && feature_type != 3) { vfsms_set_error("match: featureType %d", feature_type); return VFSMS_E_ARG; }
+    *m_out = 0;
+    if (n_a == 0 || n_b == 0) return 0;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int cap = (((n_a > n_b ? n_a : n_b) + 63) / 64) * 64;
+    int rc;
+    if ((rc = ctx->scratch0.reserve((size_t)cap * dim * 4))) return rc;   // A row-major
+    if ((rc = ctx->scratch1.reserve((size_t)cap * dim * 4))) return rc;   // B row-major
+    if ((rc = ctx->scratch2.reserve((size_t)cap * dim * 4 * 2))) return rc;   // A^T, B^T
+    if ((rc = ctx->scratch3.reserve(64))) return rc;                      // counts
+    if ((rc = match_reserve(ctx, 1, cap))) return rc;
+    int32_t counts[2] = { n_a, n_b };
+    CUDA_TRY(cudaMemcpyAsync(ctx->scratch3.p, counts, sizeof(counts), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->scratch0.p, desc_a, (size_t)n_a * dim * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->scratch1.p, desc_b, (size_t)n_b * dim * 4, cudaMemcpyHostToDevice, st));
+    const int32_t *cn = ctx->scratch3.as<int32_t>();
+    MatchWorkspace &mw = ctx->match;
+    if (feature_type == 3) {
+        if ((rc = match_hamming_batch(ctx, ctx->scratch0.as<float>(), cn, 0, ctx->scratch1.as<float>(), cn + 1, 0, 1, cap, dim, 0, 0,
+                                      mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(), st))) return rc;
+    } else {
+        float *AT = ctx->scratch2.as<float>(), *BT = AT + (size_t)cap * dim;
+        CUDA_TRY(cudaMemsetAsync(AT, 0, (size_t)cap * dim * 4 * 2, st));
+        if ((rc = transpose_desc_batch(ctx, ctx->scratch0.as<float>(), cn, 0, AT, 1, cap, dim, 0, 0, st))) return rc;
+        if ((rc = transpose_desc_batch(ctx, ctx->scratch1.as<float>(), cn + 1, 0, BT, 1, cap, dim, 0, 0, st))) return rc;
+        if ((rc = match_l2_knn2_batch(ctx, AT, cn, 0, BT, cn + 1, 0, 1, cap, dim, 0, 0, mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(), st))) return rc;
+    }
+    if ((rc = ratio_vote_batch(ctx, nullptr, nullptr, 0, 0, KP_STRIDE, cn, 0, cn + 1, 0, mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(),
+                               1, cap, feature_type == 3 ? 1 : 0, (double)param, 0, nullptr, nullptr, 0, 0, nullptr, st))) return rc;
+    int32_t m = 0;
+    CUDA_TRY(cudaMemcpyAsync(&m, mw.n_matches.p, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *m_out = m;
+    if (m > 0 && matches_out) {
+        CUDA_TRY(cudaMemcpyAsync(matches_out, mw.matches.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- getOffsetByMode
+int vfsms_offset_by_mode(vfsms_ctx *ctx, const float *kps_a, int n_a, const float *kps_b, int n_b, int kp_stride,
+                         const int32_t *matches, int m, int offset_evaluate, vfsms_pair_result *result)
+{
+    if (!ctx || !result || m < 0 || kp_stride < 2) { vfsms_set_error("offset_by_mode: bad arguments"); return VFSMS_E_ARG; }
+    memset(result, 0, sizeof(*result));
+    result->n_a = n_a; result->n_b = n_b; result->n_matches = m;
+    if (m == 0) return 0;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if ((rc = ctx->scratch0.reserve((size_t)n_a * kp_stride * 4))) return rc;
+    if ((rc = ctx->scratch1.reserve((size_t)n_b * kp_stride * 4))) return rc;
+    if ((rc = ctx->scratch2.reserve((size_t)m * 8))) return rc;
+    if ((rc = ctx->results.reserve(sizeof(vfsms_pair_result)))) return rc;
+    if ((rc = match_reserve(ctx, 1, m))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ctx->scratch0.p, kps_a, (size_t)n_a * kp_stride * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->scratch1.p, kps_b, (size_t)n_b * kp_stride * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->scratch2.p, matches, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = vote_matches_batch(ctx, ctx->scratch0.as<float>(), ctx->scratch1.as<float>(), kp_stride, ctx->scratch2.as<int32_t>(), m,
+                                 n_a, n_b, offset_evaluate, ctx->results.as<vfsms_pair_result>(), st))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(result, ctx->results.p, sizeof(*result), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    result->n_a = n_a; result->n_b = n_b;
+    return 0;
+}
+
+// ---------------------------------------------------------------- fused batch alignment
+static int align_batch_launch(vfsms_ctx *ctx, const uint8_t *a_dev, const uint8_t *b_dev, int n_pairs, int rows, int cols,
+                              int stride, int64_t pair_stride, const vfsms_surf_params *params, double ratio,
+                              int offset_evaluate, vfsms_pair_result *results_dev, cudaStream_t st)
+{
+    int rc;
+    SurfWorkspace &ws = ctx->surf;
+    if ((rc = surf_run_batch(ctx, a_dev, b_dev, n_pairs, 2 * n_pairs, rows, cols, stride, pair_stride, params, st))) return rc;
+    const int cap = ws.kp_cap, dim = ws.dim;
+    const int32_t *nfin = ws.counters.as<int32_t>() + 2;     // n_final of image b at [b*4]
+    const int32_t *flags = ws.counters.as<int32_t>() + 3;
+    CUDA_TRY(cudaMemsetAsync(ws.descT.p, 0, (size_t)2 * n_pairs * cap * dim * 4, st));
+    if ((rc = transpose_desc_batch(ctx, ws.desc.as<float>(), nfin, 4, ws.descT.as<float>(), 2 * n_pairs, cap, dim,
+                                   (int64_t)cap * dim, (int64_t)cap * dim, st))) return rc;
+    MatchWorkspace &mw = ctx->match;
+    const float *AT = ws.descT.as<float>(), *BT = AT + (size_t)n_pairs * cap * dim;
+    if ((rc = match_l2_knn2_batch(ctx, AT, nfin, 4, BT, nfin + 4 * n_pairs, 4, n_pairs, cap, dim, (int64_t)cap * dim, (int64_t)cap * dim,
+                                  mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(), st))) return rc;
+    const float *KA = ws.kp.as<float>(), *KB = KA + (size_t)n_pairs * cap * KP_STRIDE;
+    if ((rc = ratio_vote_batch(ctx, KA, KB, (int64_t)cap * KP_STRIDE, (int64_t)cap * KP_STRIDE, KP_STRIDE, nfin, 4, nfin + 4 * n_pairs, 4,
+                               mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(), n_pairs, cap, 0, ratio, offset_evaluate,
+                               flags, flags + 4 * n_pairs, 4, 1, results_dev, st))) return rc;
+    return 0;
+}
+
+int vfsms_align_batch_dev(vfsms_ctx *ctx, const uint8_t *rois_a_dev, const uint8_t *rois_b_dev, int n_pairs,
+                          int rows, int cols, int stride, int64_t pair_stride, const vfsms_surf_params *params,
+                          float ratio, int offset_evaluate, vfsms_pair_result *results_dev, void *stream)
+{
+    if (!ctx || !rois_a_dev || !rois_b_dev || !params || !results_dev || n_pairs < 1) { vfsms_set_error("align_batch_dev: bad arguments"); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    int rc;
+    if ((rc = surf_reserve(ctx, 2 * n_pairs, rows, cols, params))) return rc;
+    if ((rc = match_reserve(ctx, n_pairs, ctx->surf.kp_cap))) return rc;
+    return align_batch_launch(ctx, rois_a_dev, rois_b_dev, n_pairs, rows, cols, stride, pair_stride, params, (double)ratio,
+                              offset_evaluate, results_dev, st);
+}
+
+int vfsms_align_batch_host(vfsms_ctx *ctx, const uint8_t *rois_a, const uint8_t *rois_b, int n_pairs,
+                           int rows, int cols, int stride, int64_t pair_stride, const vfsms_surf_params *params,
+                           float ratio, int offset_evaluate, vfsms_pair_result *results)
+{
+    if (!ctx || !rois_a || !rois_b || !params || !results || n_pairs < 1 || rows < 1 || cols < 1) { vfsms_set_error("align_batch_host: bad arguments"); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc;
+    const size_t img_bytes = (size_t)rows * cols;
+    if ((rc = ctx->img_a.reserve(img_bytes * n_pairs))) return rc;
+    if ((rc = ctx->img_b.reserve(img_bytes * n_pairs))) return rc;
+    if ((rc = ctx->results.reserve(sizeof(vfsms_pair_result) * (size_t)n_pairs))) return rc;
+    for (int p = 0; p < n_pairs; p++) {
+        CUDA_TRY(cudaMemcpy2DAsync(ctx->img_a.as<uint8_t>() + p * img_bytes, cols, rois_a + p * pair_stride, stride, cols, rows, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpy2DAsync(ctx->img_b.as<uint8_t>() + p * img_bytes, cols, rois_b + p * pair_stride, stride, cols, rows, cudaMemcpyHostToDevice, st));
+    }
+    if ((rc = surf_reserve(ctx, 2 * n_pairs, rows, cols, params))) return rc;
+    for (int attempt = 0; attempt < 6; attempt++) {
+        if ((rc = match_reserve(ctx, n_pairs, ctx->surf.kp_cap))) return rc;
+        if ((rc = align_batch_launch(ctx, ctx->img_a.as<uint8_t>(), ctx->img_b.as<uint8_t>(), n_pairs, rows, cols, cols, (int64_t)img_bytes,
+                                     params, (double)ratio, offset_evaluate, ctx->results.as<vfsms_pair_result>(), st))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(results, ctx->results.p, sizeof(vfsms_pair_result) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        bool overflow = false;
+        for (int p = 0; p < n_pairs; p++) overflow |= (results[p].flags & 1) != 0;
+        if (!overflow) return 0;
+        std::vector<int32_t> cnt((size_t)8 * n_pairs);
+        CUDA_TRY(cudaMemcpy(cnt.data(), ctx->surf.counters.p, cnt.size() * 4, cudaMemcpyDeviceToHost));
+        int gc = 0, gk = 0;
+        for (int b = 0; b < 2 * n_pairs; b++) { gc |= cnt[b * 4 + 3] & 1; gk |= cnt[b * 4 + 3] & 2; }
+        if ((rc = surf_grow(ctx, gc, gk))) return rc;
+    }
+    vfsms_set_error("align_batch_host: candidate buffer overflow after regrow");
+    return VFSMS_E_OVERFLOW;
+}
+
+int vfsms_match_batch_dev(vfsms_ctx *ctx, const float *desc_a_dev, const int32_t *n_a_dev, const float *desc_b_dev,
+                          const int32_t *n_b_dev, int n_pairs, int cap, int dim, float ratio,
+                          int32_t *best_idx_dev, float *best_dist_dev, void *stream)
+{
+    (void)ratio;
+    if (!ctx || cap % 64) { vfsms_set_error("match_batch_dev: cap must be a multiple of 64"); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    int rc;
+    if ((rc = ctx->scratch2.reserve((size_t)2 * n_pairs * cap * dim * 4))) return rc;
+    float *AT = ctx->scratch2.as<float>(), *BT = AT + (size_t)n_pairs * cap * dim;
+    CUDA_TRY(cudaMemsetAsync(AT, 0, (size_t)2 * n_pairs * cap * dim * 4, st));
+    if ((rc = transpose_desc_batch(ctx, desc_a_dev, n_a_dev, 1, AT, n_pairs, cap, dim, (int64_t)cap * dim, (int64_t)cap * dim, st))) return rc;
+    if ((rc = transpose_desc_batch(ctx, desc_b_dev, n_b_dev, 1, BT, n_pairs, cap, dim, (int64_t)cap * dim, (int64_t)cap * dim, st))) return rc;
+    return match_l2_knn2_batch(ctx, AT, n_a_dev, 1, BT, n_b_dev, 1, n_pairs, cap, dim, (int64_t)cap * dim, (int64_t)cap * dim,
+                               best_idx_dev, best_dist_dev, st);
+}
+
+}  // extern "C"

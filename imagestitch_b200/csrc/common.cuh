@@ -1,0 +1,167 @@
+// common.cuh -- shared declarations of libvfsms.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/vfsms.h"
+
+#define KP_X 0
+#define KP_Y 1
+#define KP_SIZE 2
+#define KP_ANGLE 3
+#define KP_RESPONSE 4
+#define KP_OCTAVE 5
+#define KP_LAPLACIAN 6
+#define KP_STRIDE VFSMS_KP_STRIDE
+
+#define VFSMS_MAX_OCTAVES 5
+#define VFSMS_MAX_LAYERS_PER_OCTAVE 8   // nOctaveLayers + 2
+#define VFSMS_NUM_SMS 148
+
+void vfsms_set_error(const char *fmt, ...);
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            vfsms_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return VFSMS_E_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                                       \
+    do {                                                                                        \
+        (ctx)->launches++;                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess) {                                                                \
+            vfsms_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e));  \
+            return VFSMS_E_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+// A grow-only device buffer.
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t n) {
+        if (n <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        size_t want = n + n / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { vfsms_set_error("cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e)); return VFSMS_E_CUDA; }
+        bytes = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+struct HostBuf {   // pinned staging
+    void *p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t n) {
+        if (n <= bytes) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMallocHost(&p, n + n / 8);
+        if (e != cudaSuccess) { vfsms_set_error("cudaMallocHost(%zu) -> %s", n, cudaGetErrorString(e)); return VFSMS_E_CUDA; }
+        bytes = n + n / 8;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+// ---------------------------------------------------------------- SURF plan (host-built, passed by value to kernels)
+struct HaarBox { short x1, y1, x2, y2; float w; };   // offsets in integral pixels relative to the sample origin
+
+struct SurfLayer {
+    int size;            // filter size in pixels
+    int margin;          // (size/2)/step : where sample 0 lands in the layer grid
+    int samples_i;       // 1 + (rows - size)/step  (0 when the layer is skipped)
+    int samples_j;
+    HaarBox dx[3], dy[3], dxy[4];
+};
+
+struct SurfPlan {
+    int rows, cols;              // image size
+    int n_octaves, n_layers;     // n_layers = nOctaveLayers + 2
+    float threshold;
+    int tile_begin[VFSMS_MAX_OCTAVES + 1];   // prefix of CTA tiles per octave
+    int tiles_x[VFSMS_MAX_OCTAVES];
+    SurfLayer layer[VFSMS_MAX_OCTAVES][VFSMS_MAX_LAYERS_PER_OCTAVE];
+};
+
+// Workspace of the SURF pipeline for a batch of equally-sized images.
+struct SurfWorkspace {
+    int batch = 0, rows = 0, cols = 0;
+    int cand_cap = 0;        // candidate slots per image
+    int kp_cap = 0;          // final keypoint slots per image
+    int dim = 0;
+    int max_features = 0;    // > 0: GPU-plugin semantics (keep the strongest max_features), 0: unlimited
+    DevBuf integral;         // [batch][(rows+1)*(cols+1)] int32
+    DevBuf band_tot;         // [batch][bands][cols] int32
+    DevBuf cand;             // [batch][cand_cap][8] float
+    DevBuf sorted;           // [batch][cand_cap][8] float
+    DevBuf kp;               // [batch][kp_cap][8] float
+    DevBuf desc;             // [batch][kp_cap][dim] float
+    DevBuf descT;            // [batch][dim][kp_cap] float, k-major copy for the matcher
+    DevBuf counters;         // [batch][4] int32 : n_cand, n_sorted, n_final, flags
+    DevBuf prefix;           // [batch+1] int32 prefix of n_final
+};
+
+struct MatchWorkspace {
+    DevBuf best_idx, best_dist;   // [pairs][cap][2]
+    DevBuf matches;               // [pairs][cap][2] int32
+    DevBuf n_matches;             // [pairs]
+    DevBuf table_keys, table_cnt, table_first;   // vote hash tables [pairs][table_size]
+    DevBuf bf16_a, bf16_b;        // tensor-core candidates path
+    DevBuf cand_topk;
+    int table_size = 0;
+};
+
+struct vfsms_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    int num_sms = VFSMS_NUM_SMS;
+    SurfWorkspace surf;
+    MatchWorkspace match;
+    DevBuf img_a, img_b;      // staged ROIs (host variants)
+    DevBuf results;           // vfsms_pair_result[pairs]
+    DevBuf scratch0, scratch1, scratch2, scratch3;
+    HostBuf pinned_in, pinned_out;
+    void *phase_state = nullptr;   // cuFFT plans etc. (phase.cu)
+    void *blend_state = nullptr;
+};
+
+// ---------------------------------------------------------------- internal entry points (defined in the .cu files)
+int surf_build_plan(SurfPlan *plan, int rows, int cols, const vfsms_surf_params *p);
+int surf_reserve(vfsms_ctx *ctx, int batch, int rows, int cols, const vfsms_surf_params *p);
+// images: batch images, image b at base_a + b*img_stride for b < split, else base_b + (b-split)*img_stride
+int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b, int split, int batch, int rows,
+                   int cols, int stride, int64_t img_stride, const vfsms_surf_params *p, cudaStream_t st);
+
+int surf_grow(vfsms_ctx *ctx, int grow_cand, int grow_kp);
+int surf_init_tables();
+
+int match_reserve(vfsms_ctx *ctx, int n_pairs, int cap);
+int transpose_desc_batch(vfsms_ctx *ctx, const float *src, const int32_t *n_ptr, int n_stride, float *dst, int n_pairs, int cap,
+                         int dim, int64_t src_pair_stride, int64_t dst_pair_stride, cudaStream_t st);
+int match_l2_knn2_batch(vfsms_ctx *ctx, const float *descT_a, const int32_t *n_a, int n_a_stride,
+                        const float *descT_b, const int32_t *n_b, int n_b_stride, int n_pairs, int cap, int dim,
+                        int64_t pair_stride_a, int64_t pair_stride_b, int32_t *best_idx, float *best_dist, cudaStream_t st);
+int match_hamming_batch(vfsms_ctx *ctx, const float *desc_a, const int32_t *n_a, int n_a_stride,
+                        const float *desc_b, const int32_t *n_b, int n_b_stride, int n_pairs, int cap, int dim,
+                        int64_t pair_stride_a, int64_t pair_stride_b, int32_t *best_idx, float *best_dist, cudaStream_t st);
+int ratio_vote_batch(vfsms_ctx *ctx, const float *kp_a, const float *kp_b, int64_t kp_pair_stride_a, int64_t kp_pair_stride_b,
+                     int kp_elems, const int32_t *n_a, int n_a_stride, const int32_t *n_b, int n_b_stride,
+                     const int32_t *best_idx, const float *best_dist, int n_pairs, int cap, int mode, double param,
+                     int offset_evaluate, const int32_t *flags_a, const int32_t *flags_b, int flags_stride, int do_vote,
+                     vfsms_pair_result *results, cudaStream_t st);
+int vote_matches_batch(vfsms_ctx *ctx, const float *kp_a, const float *kp_b, int kp_elems, const int32_t *matches, int m,
+                       int n_a, int n_b, int offset_evaluate, vfsms_pair_result *result_dev, cudaStream_t st);
+
+__host__ __device__ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

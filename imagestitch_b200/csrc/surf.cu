@@ -1,0 +1,901 @@
+// surf.cu -- SURF detect + describe for a batch of equally-sized u8 images, sm_100a.
+//
+// Replaces what the reference reaches through cv2.xfeatures2d.SURF_create().detectAndCompute
+// (ImageUtility.py:258,262) and myGpuFeatures.detectAndDescribeBySurf (appendix/myGpuFeatures.cpp:67-104):
+// integral image -> Hessian box-filter layers -> 3x3x3 NMS -> interpolation -> response order ->
+// orientation -> rotated 20s window -> INTER_AREA 21x21 patch -> 4x4x(4|8) descriptor.
+// Arithmetic follows the CPU algorithm restated in oracle/surf_oracle.c operation by operation (this file is
+// compiled with -fmad=false so float expressions round exactly like the scalar CPU code); the structure does not:
+//   * det/trace layers are never materialised in HBM: one CTA computes the (nOctaveLayers+2) det layers of a
+//     64x16 sample tile (+1 halo) into shared memory and runs NMS + interpolation straight from there;
+//   * no host synchronisation anywhere: counters stay on the device, later kernels size themselves from them;
+//   * the response ordering (OpenCV's KeypointGreater) is a rank-by-counting pass, deterministic under any
+//     atomic arrival order of the candidates;
+//   * everything is batched over images (grid.y / flattened work lists) so one launch serves a whole batch of ROIs.
+#include "common.cuh"
+#include <math.h>
+#include <float.h>
+
+#define ORI_RADIUS 6
+#define ORI_WIN 60
+#define PATCH_SZ 20
+#define ORI_SAMPLES 113
+#define MAX_WIN 2048
+
+#define HT_X 64          // Hessian tile (samples)
+#define HT_Y 16
+#define HT_THREADS 256
+#define INT_BAND 32      // integral band height
+#define INT_SUB 8        // rows staged per sub-step (one warp per row)
+
+__constant__ int c_apt_x[ORI_SAMPLES];
+__constant__ int c_apt_y[ORI_SAMPLES];
+__constant__ float c_aptw[ORI_SAMPLES];
+__constant__ float c_DW[PATCH_SZ * PATCH_SZ];
+
+// ---------------------------------------------------------------- host: constant tables (same formulas as the oracle)
+static void gaussian_kernel_f32(int n, double sigma, float *out)
+{
+    double sum = 0, scale2X = -0.5 / (sigma * sigma), tmp[64];
+    for (int i = 0; i < n; i++) {
+        double x = i - (n - 1) * 0.5;
+        tmp[i] = (double)(float)exp(scale2X * x * x);
+        sum += tmp[i];
+    }
+    sum = 1. / sum;
+    for (int i = 0; i < n; i++) out[i] = (float)(tmp[i] * sum);
+}
+
+int surf_init_tables()
+{
+    static bool done = false;   // per process & device; tables are immutable
+    if (done) return 0;
+    float G[13], Gd[PATCH_SZ], aptw[ORI_SAMPLES], DW[PATCH_SZ * PATCH_SZ];
+    int ax[ORI_SAMPLES], ay[ORI_SAMPLES], n = 0;
+    gaussian_kernel_f32(13, 2.5, G);
+    for (int i = -ORI_RADIUS; i <= ORI_RADIUS; i++)
+        for (int j = -ORI_RADIUS; j <= ORI_RADIUS; j++)
+            if (i * i + j * j <= ORI_RADIUS * ORI_RADIUS) { ax[n] = i; ay[n] = j; aptw[n++] = G[i + ORI_RADIUS] * G[j + ORI_RADIUS]; }
+    gaussian_kernel_f32(PATCH_SZ, 3.3, Gd);
+    for (int i = 0; i < PATCH_SZ; i++)
+        for (int j = 0; j < PATCH_SZ; j++) DW[i * PATCH_SZ + j] = Gd[i] * Gd[j];
+    CUDA_TRY(cudaMemcpyToSymbol(c_apt_x, ax, sizeof(ax)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_apt_y, ay, sizeof(ay)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_aptw, aptw, sizeof(aptw)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_DW, DW, sizeof(DW)));
+    done = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------- host: plan
+static void resize_haar_host(const int src[][5], HaarBox *dst, int n, int oldSize, int newSize)
+{
+    float ratio = (float)newSize / oldSize;
+    for (int k = 0; k < n; k++) {
+        int dx1 = (int)lrint(ratio * src[k][0]), dy1 = (int)lrint(ratio * src[k][1]);
+        int dx2 = (int)lrint(ratio * src[k][2]), dy2 = (int)lrint(ratio * src[k][3]);
+        dst[k].x1 = (short)dx1; dst[k].y1 = (short)dy1; dst[k].x2 = (short)dx2; dst[k].y2 = (short)dy2;
+        dst[k].w = src[k][4] / ((float)(dx2 - dx1) * (dy2 - dy1));
+    }
+}
+
+int surf_build_plan(SurfPlan *plan, int rows, int cols, const vfsms_surf_params *p)
+{
+    static const int dx_s[3][5] = { {0, 2, 3, 7, 1}, {3, 2, 6, 7, -2}, {6, 2, 9, 7, 1} };
+    static const int dy_s[3][5] = { {2, 0, 7, 3, 1}, {2, 3, 7, 6, -2}, {2, 6, 7, 9, 1} };
+    static const int dxy_s[4][5] = { {1, 1, 4, 4, 1}, {5, 1, 8, 4, -1}, {1, 5, 4, 8, -1}, {5, 5, 8, 8, 1} };
+    if (p->n_octaves < 1 || p->n_octaves > VFSMS_MAX_OCTAVES || p->n_octave_layers < 1 ||
+        p->n_octave_layers + 2 > VFSMS_MAX_LAYERS_PER_OCTAVE || rows < 1 || cols < 1) {
+        vfsms_set_error("surf: unsupported parameters (octaves %d, layers %d, %dx%d)", p->n_octaves, p->n_octave_layers, rows, cols);
+        return VFSMS_E_ARG;
+    }
+    memset(plan, 0, sizeof(*plan));
+    plan->rows = rows; plan->cols = cols;
+    plan->n_octaves = p->n_octaves; plan->n_layers = p->n_octave_layers + 2;
+    plan->threshold = p->hessian_threshold;
+    int tiles = 0;
+    for (int o = 0; o < plan->n_octaves; o++) {
+        int step = 1 << o;
+        int lrows = rows / step, lcols = cols / step;
+        for (int l = 0; l < plan->n_layers; l++) {
+            SurfLayer &L = plan->layer[o][l];
+            L.size = (9 + 6 * l) << o;
+            L.margin = (L.size / 2) / step;
+            if (L.size > rows || L.size > cols) { L.samples_i = L.samples_j = 0; }
+            else { L.samples_i = 1 + (rows - L.size) / step; L.samples_j = 1 + (cols - L.size) / step; }
+            resize_haar_host(dx_s, L.dx, 3, 9, L.size);
+            resize_haar_host(dy_s, L.dy, 3, 9, L.size);
+            resize_haar_host(dxy_s, L.dxy, 4, 9, L.size);
+        }
+        // NMS positions exist only inside [margin_min, l - margin_min): skip tiles that cannot hold a maximum
+        int tx = ceil_div(lcols > 0 ? lcols : 1, HT_X), ty = ceil_div(lrows > 0 ? lrows : 1, HT_Y);
+        if (lrows < 3 || lcols < 3) { tx = 0; ty = 0; }
+        plan->tiles_x[o] = tx;
+        plan->tile_begin[o] = tiles;
+        tiles += tx * ty;
+    }
+    plan->tile_begin[plan->n_octaves] = tiles;
+    return 0;
+}
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ const uint8_t *image_ptr(const uint8_t *base_a, const uint8_t *base_b, int split, int b, int64_t img_stride)
+{
+    return b < split ? base_a + (int64_t)b * img_stride : base_b + (int64_t)(b - split) * img_stride;
+}
+
+// ---------------------------------------------------------------- K1a: band-local integral
+// grid (bands, batch), 256 threads = 8 warps, one warp per staged row.  Output: integral rows of the band hold
+// sums over the band's own rows only; the band's column totals go to band_tot[b][band][cols].
+__global__ void __launch_bounds__(256) integral_band_kernel(const uint8_t *base_a, const uint8_t *base_b, int split,
+                                                            int64_t img_stride, int rows, int cols, int stride,
+                                                            int32_t *integral, int32_t *band_tot, int n_bands)
+{
+    extern __shared__ int32_t s_rows[];   // [INT_SUB][cols_pad]
+    const int band = blockIdx.x, b = blockIdx.y;
+    const int W = cols + 1;
+    const int cols_pad = (min(cols, 4096) + 3) & ~3;
+    const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
+    int32_t *I = integral + (size_t)b * (rows + 1) * W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = band * INT_BAND;
+    const int r1 = min(rows, r0 + INT_BAND);
+    if (band == 0) for (int c = threadIdx.x; c < W; c += blockDim.x) I[c] = 0;   // integral row 0
+    // running column sums: thread owns columns threadIdx.x + k*256
+    int32_t run[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) run[k] = 0;
+    const bool aligned4 = ((((uintptr_t)img) | (uintptr_t)stride) & 3) == 0;
+    for (int cbase = 0; cbase < cols; cbase += 4096) {          // column super-chunks (cols <= 4096: one pass)
+        const int ccount = min(4096, cols - cbase);
+#pragma unroll
+        for (int k = 0; k < 16; k++) run[k] = 0;
+        for (int rs = r0; rs < r1; rs += INT_SUB) {
+            const int r = rs + warp;
+            if (r < r1) {
+                // horizontal inclusive prefix of row r over [0, cbase+ccount), keeping only [cbase, ...) in smem
+                const uint8_t *src = img + (size_t)r * stride;
+                int32_t carry = 0;
+                // prefix of the columns before cbase (only when cols > 4096)
+                for (int c = lane * 4; c < cbase; c += 128) {
+                    int32_t s = 0;
+                    for (int q = 0; q < 4; q++) s += src[c + q];
+                    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    carry += s;
+                }
+                int32_t *dst = s_rows + (size_t)warp * cols_pad;
+                for (int c0 = 0; c0 < ccount; c0 += 128) {
+                    const int c = c0 + lane * 4;
+                    uint32_t px = 0;
+                    if (c + 3 < ccount && aligned4) px = *(const uint32_t *)(src + cbase + c);
+                    else {
+                        for (int q = 0; q < 4; q++) if (c + q < ccount) px |= (uint32_t)src[cbase + c + q] << (8 * q);
+                    }
+                    int32_t p0 = px & 255, p1 = p0 + ((px >> 8) & 255), p2 = p1 + ((px >> 16) & 255), p3 = p2 + (px >> 24);
+                    int32_t incl = p3;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    const int32_t excl = incl - p3 + carry;
+                    if (c < ccount) {
+                        int4 v = make_int4(excl + p0, excl + p1, excl + p2, excl + p3);
+                        *(int4 *)(dst + c) = v;
+                    }
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                }
+            }
+            __syncthreads();
+            // vertical accumulation over the staged rows
+            const int nsub = min(INT_SUB, r1 - rs);
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int c = threadIdx.x + k * 256;
+                if (c < ccount) {
+                    int32_t acc = run[k];
+                    for (int q = 0; q < nsub; q++) {
+                        acc += s_rows[(size_t)q * cols_pad + c];
+                        I[(size_t)(rs + q + 1) * W + cbase + c + 1] = acc;
+                    }
+                    run[k] = acc;
+                }
+            }
+            if (threadIdx.x == 0 && cbase == 0) for (int q = 0; q < nsub; q++) I[(size_t)(rs + q + 1) * W] = 0;
+            __syncthreads();
+        }
+        int32_t *bt = band_tot + ((size_t)b * n_bands + band) * cols + cbase;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int c = threadIdx.x + k * 256;
+            if (c < ccount) bt[c] = run[k];
+        }
+    }
+}
+
+// K1b: add the totals of all previous bands.  grid (bands-1, batch): band index = blockIdx.x + 1.
+__global__ void __launch_bounds__(256) integral_fix_kernel(int rows, int cols, int32_t *integral,
+                                                           const int32_t *band_tot, int n_bands)
+{
+    const int band = blockIdx.x + 1, b = blockIdx.y;
+    const int W = cols + 1;
+    int32_t *I = integral + (size_t)b * (rows + 1) * W;
+    const int32_t *bt = band_tot + (size_t)b * n_bands * cols;
+    const int r0 = band * INT_BAND, r1 = min(rows, r0 + INT_BAND);
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        int32_t off = 0;
+        for (int q = 0; q < band; q++) off += bt[(size_t)q * cols + c];
+        for (int r = r0; r < r1; r++) I[(size_t)(r + 1) * W + c + 1] += off;
+    }
+}
+
+// ---------------------------------------------------------------- K2: Hessian layers + NMS + interpolation
+__device__ __forceinline__ float haar_response(const int32_t *__restrict__ o, int W, const HaarBox *f, int n)
+{
+    double d = 0;
+    for (int k = 0; k < n; k++) {
+        const int32_t v = __ldg(o + f[k].y1 * W + f[k].x1) + __ldg(o + f[k].y2 * W + f[k].x2)
+                        - __ldg(o + f[k].y2 * W + f[k].x1) - __ldg(o + f[k].y1 * W + f[k].x2);
+        d += (double)v * (double)f[k].w;
+    }
+    return (float)d;
+}
+
+__device__ __forceinline__ bool solve3(const float a[3][3], const float b[3], float x[3])
+{
+    float d = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1])
+            - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0])
+            + a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+    if (d == 0) { x[0] = x[1] = x[2] = 0; return false; }
+    d = 1 / d;
+    x[0] = d * (b[0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1])
+              - a[0][1] * (b[1] * a[2][2] - a[1][2] * b[2])
+              + a[0][2] * (b[1] * a[2][1] - a[1][1] * b[2]));
+    x[1] = d * (a[0][0] * (b[1] * a[2][2] - a[1][2] * b[2])
+              - b[0] * (a[1][0] * a[2][2] - a[1][2] * a[2][0])
+              + a[0][2] * (a[1][0] * b[2] - b[1] * a[2][0]));
+    x[2] = d * (a[0][0] * (a[1][1] * b[2] - b[1] * a[2][1])
+              - a[0][1] * (a[1][0] * b[2] - b[1] * a[2][0])
+              + b[0] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]));
+    return true;
+}
+
+__global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_constant__ SurfPlan plan,
+                                                                 const int32_t *__restrict__ integral,
+                                                                 float *cand, int32_t *counters, int cand_cap)
+{
+    extern __shared__ float s_det[];     // [n_layers][HT_Y+2][HT_X+2]
+    const int b = blockIdx.y;
+    int o = 0;
+    while (o + 1 < plan.n_octaves && (int)blockIdx.x >= plan.tile_begin[o + 1]) o++;
+    const int t = blockIdx.x - plan.tile_begin[o];
+    const int tile_x = t % plan.tiles_x[o], tile_y = t / plan.tiles_x[o];
+    const int step = 1 << o;
+    const int lrows = plan.rows / step, lcols = plan.cols / step;
+    const int W = plan.cols + 1;
+    const int32_t *I = integral + (size_t)b * (plan.rows + 1) * W;
+    const int nl = plan.n_layers;
+    constexpr int SW = HT_X + 2, SH = HT_Y + 2;
+    const int i0 = tile_y * HT_Y - 1, j0 = tile_x * HT_X - 1;   // layer coords of the smem origin
+
+    // phase 1: det for every layer over the haloed tile
+    for (int idx = threadIdx.x; idx < SW * SH; idx += HT_THREADS) {
+        const int ly = idx / SW, lx = idx - ly * SW;
+        const int li = i0 + ly, lj = j0 + lx;
+        for (int l = 0; l < nl; l++) {
+            const SurfLayer &L = plan.layer[o][l];
+            const int si = li - L.margin, sj = lj - L.margin;
+            float det = 0.f;
+            if (si >= 0 && si < L.samples_i && sj >= 0 && sj < L.samples_j) {
+                const int32_t *org = I + (size_t)(si * step) * W + sj * step;
+                const float dx = haar_response(org, W, L.dx, 3);
+                const float dy = haar_response(org, W, L.dy, 3);
+                const float dxy = haar_response(org, W, L.dxy, 4);
+                float tt = 0.81f * dxy;
+                tt = tt * dxy;
+                det = dx * dy - tt;
+            }
+            s_det[(l * SH + ly) * SW + lx] = det;
+        }
+    }
+    __syncthreads();
+
+    // phase 2: 3x3x3 non-maximum suppression on the middle layers, interpolation, candidate push
+    for (int idx = threadIdx.x; idx < HT_X * HT_Y; idx += HT_THREADS) {
+        const int ty = idx / HT_X, tx = idx - ty * HT_X;
+        const int li = tile_y * HT_Y + ty, lj = tile_x * HT_X + tx;
+        if (li >= lrows || lj >= lcols) continue;
+        for (int l = 1; l < nl - 1; l++) {
+            const SurfLayer &L = plan.layer[o][l];
+            const int margin = (plan.layer[o][l + 1].size / 2) / step + 1;
+            if (li < margin || li >= lrows - margin || lj < margin || lj >= lcols - margin) continue;
+            const float *c1 = s_det + (l * SH + ty + 1) * SW + tx + 1;
+            const float val0 = c1[0];
+            if (!(val0 > plan.threshold)) continue;
+            const float *c0 = c1 - SH * SW, *c2 = c1 + SH * SW;
+            float N9[3][9];
+            const float *cs[3] = { c0, c1, c2 };
+            bool is_max = true;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const float *c = cs[q];
+                N9[q][0] = c[-SW - 1]; N9[q][1] = c[-SW]; N9[q][2] = c[-SW + 1];
+                N9[q][3] = c[-1];      N9[q][4] = c[0];   N9[q][5] = c[1];
+                N9[q][6] = c[SW - 1];  N9[q][7] = c[SW];  N9[q][8] = c[SW + 1];
+            }
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+#pragma unroll
+                for (int k = 0; k < 9; k++)
+                    if (!(q == 1 && k == 4)) is_max = is_max && (val0 > N9[q][k]);
+            if (!is_max) continue;
+            const int size = L.size;
+            const int sum_i = step * (li - (size / 2) / step), sum_j = step * (lj - (size / 2) / step);
+            float py = sum_i + (size - 1) * 0.5f, px = sum_j + (size - 1) * 0.5f, psz = (float)size;
+            const int ds = size - plan.layer[o][l - 1].size;
+            float bb[3] = { -(N9[1][5] - N9[1][3]) / 2, -(N9[1][7] - N9[1][1]) / 2, -(N9[2][4] - N9[0][4]) / 2 };
+            float A[3][3];
+            A[0][0] = N9[1][3] - 2 * N9[1][4] + N9[1][5];
+            A[0][1] = (N9[1][8] - N9[1][6] - N9[1][2] + N9[1][0]) / 4;
+            A[0][2] = (N9[2][5] - N9[2][3] - N9[0][5] + N9[0][3]) / 4;
+            A[1][0] = A[0][1];
+            A[1][1] = N9[1][1] - 2 * N9[1][4] + N9[1][7];
+            A[1][2] = (N9[2][7] - N9[2][1] - N9[0][7] + N9[0][1]) / 4;
+            A[2][0] = A[0][2]; A[2][1] = A[1][2];
+            A[2][2] = N9[0][4] - 2 * N9[1][4] + N9[2][4];
+            float x[3];
+            solve3(A, bb, x);
+            const bool ok = (x[0] != 0 || x[1] != 0 || x[2] != 0) && fabsf(x[0]) <= 1 && fabsf(x[1]) <= 1 && fabsf(x[2]) <= 1;
+            if (!ok) continue;
+            px += x[0] * step;
+            py += x[1] * step;
+            psz = (float)__float2int_rn(psz + x[2] * ds);
+            // laplacian sign: recompute trace at the maximum (rare path)
+            const int32_t *org = I + (size_t)((li - L.margin) * step) * W + (lj - L.margin) * step;
+            const float trace = haar_response(org, W, L.dx, 3) + haar_response(org, W, L.dy, 3);
+            const int slot = atomicAdd(&counters[b * 4 + 0], 1);
+            if (slot < cand_cap) {
+                float4 *dst = (float4 *)(cand + ((size_t)b * cand_cap + slot) * KP_STRIDE);
+                dst[0] = make_float4(px, py, psz, -1.f);
+                dst[1] = make_float4(val0, (float)o, (float)((trace > 0) - (trace < 0)), 0.f);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- K3: response ordering by rank counting
+// OpenCV's KeypointGreater: response desc, size desc, octave desc, y desc, x asc.
+struct SortKey { unsigned long long k1, k2; };
+
+__device__ __forceinline__ unsigned f2ord(float f)   // order-preserving float -> uint
+{
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ SortKey make_key(const float *kp)
+{
+    SortKey k;
+    // size is integral (< 2^24) and octave < 256: both exact in the low word
+    const unsigned sz = (unsigned)kp[KP_SIZE], oc = (unsigned)kp[KP_OCTAVE];
+    k.k1 = ((unsigned long long)f2ord(kp[KP_RESPONSE]) << 32) | ((unsigned long long)(sz & 0xffffffu) << 8) | (oc & 0xffu);
+    k.k2 = ((unsigned long long)f2ord(kp[KP_Y]) << 32) | (unsigned long long)(~f2ord(kp[KP_X]));
+    return k;
+}
+
+// a sorts before b ?
+__device__ __forceinline__ bool key_before(const SortKey &a, const SortKey &b)
+{
+    return a.k1 > b.k1 || (a.k1 == b.k1 && a.k2 > b.k2);
+}
+
+// grid: flattened (image, chunk) work items, grid-strided.  n per image read from counters.
+__global__ void __launch_bounds__(256) rank_sort_kernel(const float *__restrict__ cand, float *sorted, int32_t *counters,
+                                                        int cand_cap, int batch, int max_features)
+{
+    __shared__ SortKey s_keys[1024];
+    const int chunks_per_img = ceil_div(cand_cap, 256);
+    for (int item = blockIdx.x; item < batch * chunks_per_img; item += gridDim.x) {
+        const int b = item / chunks_per_img, chunk = item - b * chunks_per_img;
+        const int n_raw = counters[b * 4 + 0];
+        const int n = min(n_raw, cand_cap);
+        if (chunk * 256 >= n) continue;             // uniform per CTA
+        const float *C = cand + (size_t)b * cand_cap * KP_STRIDE;
+        const int i = chunk * 256 + threadIdx.x;
+        SortKey mine; mine.k1 = 0; mine.k2 = 0;
+        if (i < n) mine = make_key(C + (size_t)i * KP_STRIDE);
+        int rank = 0;
+        for (int base = 0; base < n; base += 1024) {
+            __syncthreads();
+            for (int q = threadIdx.x; q < 1024; q += 256) {
+                const int j = base + q;
+                SortKey k; k.k1 = 0; k.k2 = 0;
+                if (j < n) k = make_key(C + (size_t)j * KP_STRIDE);
+                s_keys[q] = k;
+            }
+            __syncthreads();
+            const int m = min(1024, n - base);
+            if (i < n) {
+                for (int q = 0; q < m; q++) {
+                    const SortKey k = s_keys[q];
+                    const int j = base + q;
+                    rank += (key_before(k, mine) || (k.k1 == mine.k1 && k.k2 == mine.k2 && j < i)) ? 1 : 0;
+                }
+            }
+        }
+        const int n_keep = (max_features > 0) ? min(n, max_features) : n;
+        if (i < n && rank < n_keep) {
+            const float4 *src = (const float4 *)(C + (size_t)i * KP_STRIDE);
+            float4 *dst = (float4 *)(sorted + ((size_t)b * cand_cap + rank) * KP_STRIDE);
+            dst[0] = src[0]; dst[1] = src[1];
+        }
+        if (chunk == 0 && threadIdx.x == 0) {
+            counters[b * 4 + 1] = n_keep;
+            if (n_raw > cand_cap) counters[b * 4 + 3] |= 1;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- K3b: drop keypoints that cannot be oriented, keep order
+__device__ __forceinline__ bool keypoint_valid(const float *kp, int rows, int cols, int upright)
+{
+    const int srows = rows + 1, scols = cols + 1;
+    const float size = kp[KP_SIZE];
+    const float s = size * 1.2f / 9.0f;
+    const int gws = 2 * __float2int_rn(2 * s);
+    if (srows < gws || scols < gws) return false;
+    if (upright) return true;
+    const float cx = kp[KP_X], cy = kp[KP_Y];
+    const float half = (float)(gws - 1) / 2;
+    for (int kk = 0; kk < ORI_SAMPLES; kk++) {
+        const int x = __float2int_rn(cx + c_apt_x[kk] * s - half);
+        const int y = __float2int_rn(cy + c_apt_y[kk] * s - half);
+        if (y < 0 || y >= srows - gws || x < 0 || x >= scols - gws) continue;
+        return true;
+    }
+    return false;
+}
+
+// one CTA (1024 threads) per image
+__global__ void __launch_bounds__(1024) validate_compact_kernel(const float *__restrict__ sorted, float *kp_out,
+                                                                int32_t *counters, int cand_cap, int kp_cap,
+                                                                int rows, int cols, int upright)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_base, s_total;
+    const int b = blockIdx.x;
+    const int n = counters[b * 4 + 1];
+    const float *S = sorted + (size_t)b * cand_cap * KP_STRIDE;
+    float *K = kp_out + (size_t)b * kp_cap * KP_STRIDE;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const bool v = (i < n) && keypoint_valid(S + (size_t)i * KP_STRIDE, rows, cols, upright);
+        const unsigned bal = __ballot_sync(0xffffffffu, v);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        if (warp == 0) {
+            const int c = s_warp[lane];
+            int incl = c;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            s_warp[lane] = incl - c;
+            if (lane == 31) s_total = incl;
+        }
+        __syncthreads();
+        const int pos = s_base + s_warp[warp] + __popc(bal & ((1u << lane) - 1));
+        if (v && pos < kp_cap) {
+            const float4 *src = (const float4 *)(S + (size_t)i * KP_STRIDE);
+            float4 *dst = (float4 *)(K + (size_t)pos * KP_STRIDE);
+            dst[0] = src[0]; dst[1] = src[1];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += s_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int m = s_base;
+        if (m > kp_cap) { counters[b * 4 + 3] |= 2; m = kp_cap; }
+        counters[b * 4 + 2] = m;
+    }
+}
+
+// prefix over images of n_final -> work list for the describe kernel
+__global__ void prefix_kernel(const int32_t *counters, int32_t *prefix, int batch)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < batch; b++) { prefix[b] = acc; acc += counters[b * 4 + 2]; }
+        prefix[batch] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- K4: orientation + descriptor, one CTA per keypoint
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    const float p1 = 0.9997878412794807f * (float)(180 / M_PI);
+    const float p3 = -0.3258083974640975f * (float)(180 / M_PI);
+    const float p5 = 0.1555786518463281f * (float)(180 / M_PI);
+    const float p7 = -0.04432655554792128f * (float)(180 / M_PI);
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+__device__ __forceinline__ int box_sum(const int32_t *__restrict__ o, int W, int x1, int y1, int x2, int y2)
+{
+    return __ldg(o + y1 * W + x1) + __ldg(o + y2 * W + x2) - __ldg(o + y2 * W + x1) - __ldg(o + y1 * W + x2);
+}
+
+// bilinear / clamped sample of the rotated window, rounded to u8 exactly like the CPU loop
+__device__ __forceinline__ int window_pixel(const uint8_t *__restrict__ img, int stride, int ncols1, int nrows1,
+                                            double pixel_x, double pixel_y)
+{
+    const int ix = __double2int_rd(pixel_x), iy = __double2int_rd(pixel_y);
+    if ((unsigned)ix < (unsigned)ncols1 && (unsigned)iy < (unsigned)nrows1) {
+        const float a = (float)(pixel_x - ix), bq = (float)(pixel_y - iy);
+        const uint8_t *p = img + (size_t)iy * stride + ix;
+        const float p00 = p[0], p01 = p[1], p10 = p[stride], p11 = p[stride + 1];
+        const float v = p00 * (1.f - a) * (1.f - bq) + p01 * a * (1.f - bq) + p10 * (1.f - a) * bq + p11 * a * bq;
+        return __float2int_rn(v) & 255;
+    }
+    int x = __double2int_rn(pixel_x), y = __double2int_rn(pixel_y);
+    x = min(max(x, 0), ncols1); y = min(max(y, 0), nrows1);
+    return img[(size_t)y * stride + x];
+}
+
+#define DESC_THREADS 256
+
+__global__ void __launch_bounds__(DESC_THREADS) orient_describe_kernel(
+    const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
+    const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
+    int batch, int kp_cap, int extended, int upright)
+{
+    __shared__ float s_X[ORI_SAMPLES], s_Y[ORI_SAMPLES], s_ang[ORI_SAMPLES];
+    __shared__ int s_flag_cnt[4];
+    __shared__ float s_sumx[72], s_sumy[72];
+    __shared__ float s_startx[MAX_WIN], s_starty[MAX_WIN];
+    __shared__ uint8_t s_patch[(PATCH_SZ + 1) * (PATCH_SZ + 1) + 3];
+    __shared__ float s_DX[PATCH_SZ * PATCH_SZ], s_DY[PATCH_SZ * PATCH_SZ];
+    __shared__ float s_vec[128];
+    __shared__ float s_dir, s_scale;
+    __shared__ int s_nangle;
+
+    const int total = prefix[batch];
+    const int W = cols + 1, srows = rows + 1, scols = cols + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int dsize = extended ? 128 : 64;
+
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        // (image, keypoint) from the flattened index
+        int lo = 0, hi = batch;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (prefix[mid] <= item) lo = mid; else hi = mid; }
+        const int b = lo, k = item - prefix[lo];
+        float *kp = kp_all + ((size_t)b * kp_cap + k) * KP_STRIDE;
+        const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
+        const int32_t *I = integral + (size_t)b * srows * W;
+        const float size = kp[KP_SIZE], cx = kp[KP_X], cy = kp[KP_Y];
+        const float s = size * 1.2f / 9.0f;
+        const int gws = 2 * __float2int_rn(2 * s);
+
+        float descriptor_dir = 360.f - 90.f;
+        if (!upright) {
+            // --- 113 Haar samples on a disc of radius 6s, compacted in table order
+            const int h2 = __float2int_rn(((float)gws / 4) * 2);   // cvRound(ratio*2), ratio = gws/4
+            const int h4 = __float2int_rn(((float)gws / 4) * 4);
+            const float wgt = 1.f / ((float)(h2) * (float)(h4));    // |w| of both half boxes: 1/((dx2-dx1)*(dy2-dy1))
+            bool have = false; float vX = 0, vY = 0;
+            if (tid < ORI_SAMPLES) {
+                const float half = (float)(gws - 1) / 2;
+                const int x = __float2int_rn(cx + c_apt_x[tid] * s - half);
+                const int y = __float2int_rn(cy + c_apt_y[tid] * s - half);
+                if (!(y < 0 || y >= srows - gws || x < 0 || x >= scols - gws)) {
+                    const int32_t *o = I + (size_t)y * W + x;
+                    // dx pattern {0,0,2,4,-1},{2,0,4,4,+1}; dy pattern {0,0,4,2,+1},{0,2,4,4,-1}
+                    const int bl = box_sum(o, W, 0, 0, h2, h4), br = box_sum(o, W, h2, 0, h4, h4);
+                    const int bt = box_sum(o, W, 0, 0, h4, h2), bb = box_sum(o, W, 0, h2, h4, h4);
+                    double d = 0; d += (double)bl * (double)(-wgt); d += (double)br * (double)wgt;
+                    const float vx = (float)d;
+                    d = 0; d += (double)bt * (double)wgt; d += (double)bb * (double)(-wgt);
+                    const float vy = (float)d;
+                    vX = vx * c_aptw[tid]; vY = vy * c_aptw[tid];
+                    have = true;
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, have);
+            if (lane == 0 && warp < 4) s_flag_cnt[warp] = __popc(bal);
+            __syncthreads();
+            if (tid < 128) {
+                int off = 0;
+                for (int q = 0; q < warp; q++) off += s_flag_cnt[q];
+                if (have) {
+                    const int pos = off + __popc(bal & ((1u << lane) - 1));
+                    s_X[pos] = vX; s_Y[pos] = vY; s_ang[pos] = fast_atan2_deg(vY, vX);
+                }
+            }
+            if (tid == 0) s_nangle = s_flag_cnt[0] + s_flag_cnt[1] + s_flag_cnt[2] + s_flag_cnt[3];
+            __syncthreads();
+            const int nangle = s_nangle;
+            // --- 72 sliding windows of 60 degrees, each summed serially in sample order (CPU summation order)
+            if (tid < 72) {
+                const int i = tid * 5;
+                float sumx = 0, sumy = 0;
+                for (int j = 0; j < nangle; j++) {
+                    const int d = abs(__float2int_rn(s_ang[j]) - i);
+                    if (d < ORI_WIN / 2 || d > 360 - ORI_WIN / 2) { sumx += s_X[j]; sumy += s_Y[j]; }
+                }
+                s_sumx[tid] = sumx; s_sumy[tid] = sumy;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float bestx = 0, besty = 0, best = 0;
+                for (int q = 0; q < 72; q++) {
+                    const float m = s_sumx[q] * s_sumx[q] + s_sumy[q] * s_sumy[q];
+                    if (m > best) { best = m; bestx = s_sumx[q]; besty = s_sumy[q]; }
+                }
+                s_dir = fast_atan2_deg(-besty, bestx);
+            }
+            __syncthreads();
+            descriptor_dir = s_dir;
+        }
+        if (tid == 0) kp[KP_ANGLE] = descriptor_dir;
+
+        // --- 20s window -> 21x21 patch (INTER_AREA), sampled on the fly
+        const int win = (int)((PATCH_SZ + 1) * s);
+        const int ncols1 = cols - 1, nrows1 = rows - 1;
+        float sin_dir = 0, cos_dir = 0;
+        int ustart_x = 0, ustart_y = 0;
+        if (!upright) {
+            const float dir_rad = descriptor_dir * (float)(M_PI / 180);
+            sin_dir = -(float)sin((double)dir_rad);
+            cos_dir = (float)cos((double)dir_rad);
+            const float win_offset = -(float)(win - 1) / 2;
+            if (tid == 0) {
+                float sx = cx + win_offset * cos_dir + win_offset * sin_dir;
+                for (int i = 0; i < win && i < MAX_WIN; i++) { s_startx[i] = sx; sx += sin_dir; }
+            } else if (tid == 32) {
+                float sy = cy - win_offset * sin_dir + win_offset * cos_dir;
+                for (int i = 0; i < win && i < MAX_WIN; i++) { s_starty[i] = sy; sy += cos_dir; }
+            }
+        } else {
+            const float win_offset = -(float)(win - 1) / 2;
+            ustart_x = __float2int_rn(cx + win_offset);
+            ustart_y = __float2int_rn(cy - win_offset);
+        }
+        __syncthreads();
+
+        // WIN(i, j): row i, column j of the window
+        auto WINPIX = [&](int i, int j) -> int {
+            if (!upright) {
+                const double px = (double)s_startx[i] + (double)j * (double)cos_dir;
+                const double py = (double)s_starty[i] - (double)j * (double)sin_dir;
+                return window_pixel(img, stride, ncols1, nrows1, px, py);
+            }
+            int x = ustart_x + i, y = ustart_y - j;
+            x = min(max(x, 0), cols - 1); y = min(max(y, 0), rows - 1);
+            return img[(size_t)y * stride + x];
+        };
+
+        constexpr int PD = PATCH_SZ + 1;
+        const double inv_scale = (double)PD / win;
+        const double scale = 1. / inv_scale;
+        const int iscale = __double2int_rn(scale);
+        const bool area_fast = fabs(scale - iscale) < DBL_EPSILON;
+        for (int p = tid; p < PD * PD; p += DESC_THREADS) {
+            const int dy = p / PD, dx = p - dy * PD;
+            int out;
+            if (win == PD) out = WINPIX(dy, dx);
+            else if (area_fast) {
+                int sum = 0;
+                for (int yy = 0; yy < iscale; yy++)
+                    for (int xx = 0; xx < iscale; xx++) sum += WINPIX(dy * iscale + yy, dx * iscale + xx);
+                if (iscale == 2) out = (sum + 2) >> 2;
+                else { const float fs = 1.f / (float)(iscale * iscale); out = min(max(__float2int_rn(sum * fs), 0), 255); }
+            } else {
+                // decimation tables of this output pixel, generated in table order
+                double fsx1 = dx * scale, fsx2 = fsx1 + scale, cwx = fmin(scale, win - fsx1);
+                int sx1 = __double2int_ru(fsx1), sx2 = __double2int_rd(fsx2);
+                sx2 = min(sx2, win - 1); sx1 = min(sx1, sx2);
+                double fsy1 = dy * scale, fsy2 = fsy1 + scale, cwy = fmin(scale, win - fsy1);
+                int sy1 = __double2int_ru(fsy1), sy2 = __double2int_rd(fsy2);
+                sy2 = min(sy2, win - 1); sy1 = min(sy1, sy2);
+                const bool xl = (sx1 - fsx1 > 1e-3), xr = (fsx2 - sx2 > 1e-3);
+                const bool yl = (sy1 - fsy1 > 1e-3), yr = (fsy2 - sy2 > 1e-3);
+                const float axl = (float)((sx1 - fsx1) / cwx), axm = (float)(1.0 / cwx),
+                            axr = (float)(fmin(fmin(fsx2 - sx2, 1.), cwx) / cwx);
+                const float ayl = (float)((sy1 - fsy1) / cwy), aym = (float)(1.0 / cwy),
+                            ayr = (float)(fmin(fmin(fsy2 - sy2, 1.), cwy) / cwy);
+                float sum = 0; bool first = true;
+                const int ya = yl ? sy1 - 1 : sy1, yb = yr ? sy2 : sy2 - 1;     // inclusive source row range
+                for (int sy = ya; sy <= yb; sy++) {
+                    const float beta = (yl && sy == sy1 - 1) ? ayl : ((yr && sy == sy2) ? ayr : aym);
+                    float buf = 0;
+                    if (xl) buf += (float)WINPIX(sy, sx1 - 1) * axl;
+                    for (int sx = sx1; sx < sx2; sx++) buf += (float)WINPIX(sy, sx) * axm;
+                    if (xr) buf += (float)WINPIX(sy, sx2) * axr;
+                    if (first) { sum = beta * buf; first = false; } else sum += beta * buf;
+                }
+                out = min(max(__float2int_rn(sum), 0), 255);
+            }
+            s_patch[p] = (uint8_t)out;
+        }
+        __syncthreads();
+
+        // --- gradients with wavelets of size 2s, Gaussian weighted
+        for (int p = tid; p < PATCH_SZ * PATCH_SZ; p += DESC_THREADS) {
+            const int i = p / PATCH_SZ, j = p - i * PATCH_SZ;
+            const float dw = c_DW[p];
+            const int p00 = s_patch[i * PD + j], p01 = s_patch[i * PD + j + 1];
+            const int p10 = s_patch[(i + 1) * PD + j], p11 = s_patch[(i + 1) * PD + j + 1];
+            s_DX[p] = (float)(p01 - p00 + p11 - p10) * dw;
+            s_DY[p] = (float)(p10 - p00 + p11 - p01) * dw;
+        }
+        __syncthreads();
+
+        // --- 4x4 cells x (4|8) bins, each bin summed serially in the CPU order
+        if (tid < dsize) {
+            const int nb = extended ? 8 : 4;
+            const int cell = tid / nb, bin = tid - cell * nb;
+            const int ci = cell >> 2, cj = cell & 3;
+            float acc = 0;
+            for (int y = ci * 5; y < ci * 5 + 5; y++)
+                for (int x = cj * 5; x < cj * 5 + 5; x++) {
+                    const float tx = s_DX[y * PATCH_SZ + x], ty = s_DY[y * PATCH_SZ + x];
+                    if (extended) {
+                        switch (bin) {
+                        case 0: if (ty >= 0) acc += tx; break;
+                        case 1: if (ty >= 0) acc += fabsf(tx); break;
+                        case 2: if (!(ty >= 0)) acc += tx; break;
+                        case 3: if (!(ty >= 0)) acc += fabsf(tx); break;
+                        case 4: if (tx >= 0) acc += ty; break;
+                        case 5: if (tx >= 0) acc += fabsf(ty); break;
+                        case 6: if (!(tx >= 0)) acc += ty; break;
+                        default: if (!(tx >= 0)) acc += fabsf(ty); break;
+                        }
+                    } else {
+                        switch (bin) {
+                        case 0: acc += tx; break;
+                        case 1: acc += ty; break;
+                        case 2: acc += fabsf(tx); break;
+                        default: acc += fabsf(ty); break;
+                        }
+                    }
+                }
+            s_vec[tid] = acc;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double sq = 0;
+            for (int q = 0; q < dsize; q++) sq += (double)(s_vec[q] * s_vec[q]);
+            s_scale = (float)(1. / (sqrt(sq) + (double)FLT_EPSILON));
+        }
+        __syncthreads();
+        if (tid < dsize) desc_all[((size_t)b * kp_cap + k) * dsize + tid] = s_vec[tid] * s_scale;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- host driver
+int surf_reserve(vfsms_ctx *ctx, int batch, int rows, int cols, const vfsms_surf_params *p)
+{
+    SurfWorkspace &ws = ctx->surf;
+    const int dim = p->extended ? 128 : 64;
+    const long long px = (long long)rows * cols;
+    int kp_cap, cand_cap, max_features = 0;
+    if (p->keypoints_ratio > 0) {
+        long long mf = (long long)(p->keypoints_ratio * (float)px);
+        if (mf > 65535) mf = 65535;
+        if (mf < 1) mf = 1;
+        max_features = (int)mf;
+        kp_cap = max_features;
+    } else {
+        kp_cap = (int)(px / 24 > 4096 ? px / 24 : 4096);
+    }
+    cand_cap = (int)(px / 24 > 8192 ? px / 24 : 8192);
+    if (cand_cap < kp_cap) cand_cap = kp_cap;
+    if (ws.rows == rows && ws.cols == cols) {          // keep sizes that were regrown for this shape
+        if (ws.cand_cap > cand_cap) cand_cap = ws.cand_cap;
+        if (max_features == 0 && ws.kp_cap > kp_cap) kp_cap = ws.kp_cap;
+    }
+    cand_cap = (cand_cap + 255) & ~255;
+    kp_cap = (kp_cap + 63) & ~63;                       // matcher tiles are 64 wide
+    const int n_bands = ceil_div(rows, INT_BAND);
+    int rc;
+    if ((rc = ws.integral.reserve((size_t)batch * (rows + 1) * (cols + 1) * 4))) return rc;
+    if ((rc = ws.band_tot.reserve((size_t)batch * n_bands * cols * 4))) return rc;
+    if ((rc = ws.cand.reserve((size_t)batch * cand_cap * KP_STRIDE * 4))) return rc;
+    if ((rc = ws.sorted.reserve((size_t)batch * cand_cap * KP_STRIDE * 4))) return rc;
+    if ((rc = ws.kp.reserve((size_t)batch * kp_cap * KP_STRIDE * 4))) return rc;
+    if ((rc = ws.desc.reserve((size_t)batch * kp_cap * dim * 4))) return rc;
+    if ((rc = ws.counters.reserve((size_t)batch * 16))) return rc;
+    if ((rc = ws.prefix.reserve((size_t)(batch + 1) * 4))) return rc;
+    if ((rc = ws.descT.reserve((size_t)batch * kp_cap * dim * 4))) return rc;
+    ws.max_features = max_features;
+    ws.batch = batch; ws.rows = rows; ws.cols = cols; ws.cand_cap = cand_cap; ws.kp_cap = kp_cap; ws.dim = dim;
+    return 0;
+}
+
+int surf_grow(vfsms_ctx *ctx, int grow_cand, int grow_kp)
+{
+    SurfWorkspace &ws = ctx->surf;
+    if (grow_cand) ws.cand_cap *= 2;
+    int rc;
+    if (grow_kp && ws.max_features == 0) {
+        ws.kp_cap *= 2;
+        if (ws.cand_cap < ws.kp_cap) ws.cand_cap = ws.kp_cap;
+        if ((rc = ws.kp.reserve((size_t)ws.batch * ws.kp_cap * KP_STRIDE * 4))) return rc;
+        if ((rc = ws.desc.reserve((size_t)ws.batch * ws.kp_cap * ws.dim * 4))) return rc;
+        if ((rc = ws.descT.reserve((size_t)ws.batch * ws.kp_cap * ws.dim * 4))) return rc;
+    }
+    if ((rc = ws.cand.reserve((size_t)ws.batch * ws.cand_cap * KP_STRIDE * 4))) return rc;
+    if ((rc = ws.sorted.reserve((size_t)ws.batch * ws.cand_cap * KP_STRIDE * 4))) return rc;
+    return 0;
+}
+
+int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b, int split, int batch, int rows,
+                   int cols, int stride, int64_t img_stride, const vfsms_surf_params *p, cudaStream_t st)
+{
+    SurfWorkspace &ws = ctx->surf;
+    int rc;
+    if ((rc = surf_init_tables())) return rc;
+    if (ws.batch < batch || ws.rows != rows || ws.cols != cols || ws.dim != (p->extended ? 128 : 64)) {
+        vfsms_set_error("surf_run_batch: workspace not reserved for this shape");
+        return VFSMS_E_ARG;
+    }
+    SurfPlan plan;
+    if ((rc = surf_build_plan(&plan, rows, cols, p))) return rc;
+    const int n_bands = ceil_div(rows, INT_BAND);
+    const int cols_pad = (min(cols, 4096) + 3) & ~3;
+    const size_t smem_int = (size_t)INT_SUB * cols_pad * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(integral_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_done = true;
+    }
+    CUDA_TRY(cudaMemsetAsync(ws.counters.p, 0, (size_t)batch * 16, st));
+    integral_band_kernel<<<dim3(n_bands, batch), 256, smem_int, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
+                                                                      ws.integral.as<int32_t>(), ws.band_tot.as<int32_t>(), n_bands);
+    LAUNCH_CHECK(ctx);
+    if (n_bands > 1) {
+        integral_fix_kernel<<<dim3(n_bands - 1, batch), 256, 0, st>>>(rows, cols, ws.integral.as<int32_t>(),
+                                                                      ws.band_tot.as<int32_t>(), n_bands);
+        LAUNCH_CHECK(ctx);
+    }
+    const int total_tiles = plan.tile_begin[plan.n_octaves];
+    if (total_tiles > 0) {
+        const size_t smem_h = (size_t)plan.n_layers * (HT_X + 2) * (HT_Y + 2) * 4;
+        hessian_nms_kernel<<<dim3(total_tiles, batch), HT_THREADS, smem_h, st>>>(plan, ws.integral.as<int32_t>(),
+                                                                                 ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap);
+        LAUNCH_CHECK(ctx);
+    }
+    const int max_features = ws.max_features;
+    {
+        const int chunks = ceil_div(ws.cand_cap, 256) * batch;
+        const int grid = min(chunks, ctx->num_sms * 8);
+        rank_sort_kernel<<<grid, 256, 0, st>>>(ws.cand.as<float>(), ws.sorted.as<float>(), ws.counters.as<int32_t>(),
+                                              ws.cand_cap, batch, max_features);
+        LAUNCH_CHECK(ctx);
+    }
+    validate_compact_kernel<<<batch, 1024, 0, st>>>(ws.sorted.as<float>(), ws.kp.as<float>(), ws.counters.as<int32_t>(),
+                                                    ws.cand_cap, ws.kp_cap, rows, cols, p->upright);
+    LAUNCH_CHECK(ctx);
+    prefix_kernel<<<1, 32, 0, st>>>(ws.counters.as<int32_t>(), ws.prefix.as<int32_t>(), batch);
+    LAUNCH_CHECK(ctx);
+    orient_describe_kernel<<<ctx->num_sms * 6, DESC_THREADS, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
+                                                                       ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(),
+                                                                       ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, p->upright);
+    LAUNCH_CHECK(ctx);
+    return 0;
+}

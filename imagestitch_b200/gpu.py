@@ -1,0 +1,152 @@
+"""Array-level host API over libvfsms.so (numpy in / numpy out, plus torch-tensor device variants).
+
+This is the layer the reference-surface modules (ImageUtility.Method, Stitcher, ImageFusion, myGpuFeatures) call.
+Nothing here computes on the CPU: every function ends in a C-ABI call and raises VfsmsError when the library or
+the device is missing.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import KP_STRIDE, PAIR_RESULT_DTYPE, PairResult, SurfParams, VfsmsError, check
+
+# reference defaults: ImageUtility.py:23-28 (GPU-SURF) and cv2.xfeatures2d.SURF_create() (ImageUtility.py:258)
+SURF_GPU_DEFAULTS = dict(hessian_threshold=100.0, n_octaves=4, n_octave_layers=3, extended=True, keypoints_ratio=0.01,
+                         upright=False)
+SURF_CPU_DEFAULTS = dict(hessian_threshold=100.0, n_octaves=4, n_octave_layers=3, extended=False, keypoints_ratio=0.0,
+                         upright=False)
+
+
+def surf_params(hessian_threshold=100.0, n_octaves=4, n_octave_layers=3, extended=True, keypoints_ratio=0.01,
+                upright=False):
+    return SurfParams(float(hessian_threshold), int(n_octaves), int(n_octave_layers), int(bool(extended)),
+                      float(keypoints_ratio), int(bool(upright)))
+
+
+def _vp(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _as_u8_image(image):
+    img = np.asarray(image)
+    if img.dtype != np.uint8 or img.ndim != 2:
+        raise TypeError("expected a 2-D uint8 image, got %s %s" % (img.dtype, img.shape))
+    if img.strides[1] != 1 or img.strides[0] < img.shape[1]:
+        img = np.ascontiguousarray(img)     # Fortran-ordered / negative-stride views (conversion.cpp:197-202)
+    return img
+
+
+def surf_detect_and_describe(image, params=None, device=0, **kw):
+    """-> (kp [N, 8] float32 (x, y, size, angle, response, octave, laplacian, 0), desc [N, 64|128] float32)."""
+    L = _lib.load()
+    ctx = _lib.context(device)
+    img = _as_u8_image(image)
+    p = params if params is not None else surf_params(**kw)
+    h, w = img.shape
+    dim = 128 if p.extended else 64
+    if p.keypoints_ratio > 0:
+        cap = int(min(max(p.keypoints_ratio * h * w, 1), 65535)) + 64
+    else:
+        cap = max(4096, h * w // 24) + 64
+    n = ctypes.c_int(0)
+    while True:
+        kp = np.empty((cap, KP_STRIDE), np.float32)
+        desc = np.empty((cap, dim), np.float32)
+        rc = L.vfsms_surf_detect_and_describe(ctx, _vp(img), h, w, img.strides[0], ctypes.byref(p), _vp(kp), _vp(desc), cap,
+                                              ctypes.byref(n))
+        if rc == _lib.VFSMS_E_CAPACITY:
+            cap = n.value + 64
+            continue
+        check(rc, "vfsms_surf_detect_and_describe")
+        return kp[:n.value].copy(), desc[:n.value].copy()
+
+
+def match_descriptors(desc_a, desc_b, feature_type=2, param=0.75, device=0):
+    """-> int32 [M, 2] rows (trainIdx, queryIdx), ascending queryIdx (appendix/myGpuFeatures.cpp:53-65)."""
+    L = _lib.load()
+    ctx = _lib.context(device)
+    A = np.ascontiguousarray(desc_a, np.float32)
+    B = np.ascontiguousarray(desc_b, np.float32)
+    if A.ndim != 2 or B.ndim != 2 or (A.shape[0] and B.shape[0] and A.shape[1] != B.shape[1]):
+        raise ValueError("descriptor arrays must be [n, D] with equal D")
+    nA, nB = A.shape[0], B.shape[0]
+    out = np.empty((max(nA, 1), 2), np.int32)
+    m = ctypes.c_int(0)
+    dim = A.shape[1] if nA else (B.shape[1] if nB else 1)
+    check(L.vfsms_match_descriptors(ctx, _vp(A), nA, _vp(B), nB, dim, int(feature_type), float(param), _vp(out),
+                                    ctypes.byref(m)), "vfsms_match_descriptors")
+    return out[:m.value].copy()
+
+
+def offset_by_mode(kps_a, kps_b, matches, offset_evaluate=3, device=0):
+    """-> (status, [dRow, dCol], votes) with the reference's truncation / first-seen tie rule."""
+    L = _lib.load()
+    ctx = _lib.context(device)
+    A = np.ascontiguousarray(kps_a, np.float32).reshape(len(kps_a), -1) if len(kps_a) else np.zeros((0, 2), np.float32)
+    B = np.ascontiguousarray(kps_b, np.float32).reshape(len(kps_b), -1) if len(kps_b) else np.zeros((0, 2), np.float32)
+    m = np.ascontiguousarray(matches, np.int32).reshape(-1, 2)
+    if A.shape[1] != B.shape[1]:
+        raise ValueError("keypoint arrays must share their row length")
+    if len(m) and (m[:, 1].max() >= len(A) or m[:, 0].max() >= len(B) or m.min() < 0):
+        raise IndexError("match index out of range")
+    r = PairResult()
+    check(L.vfsms_offset_by_mode(ctx, _vp(A), len(A), _vp(B), len(B), A.shape[1], _vp(m), len(m), int(offset_evaluate),
+                                 ctypes.byref(r)), "vfsms_offset_by_mode")
+    return bool(r.status), [int(r.d_row), int(r.d_col)], int(r.votes)
+
+
+def align_batch(rois_a, rois_b, params=None, ratio=0.75, offset_evaluate=3, device=0, **kw):
+    """Fused detect x2 -> match -> vote for P ROI pairs of equal shape (host arrays).  -> structured array [P]."""
+    L = _lib.load()
+    ctx = _lib.context(device)
+    A = np.asarray(rois_a)
+    B = np.asarray(rois_b)
+    if A.ndim == 2:
+        A = A[None]; B = B[None]
+    if A.dtype != np.uint8 or B.dtype != np.uint8 or A.shape != B.shape or A.ndim != 3:
+        raise TypeError("rois must be uint8 arrays of identical shape [P, h, w]")
+    if A.strides[2] != 1 or A.strides[1] < A.shape[2] or A.strides[0] < 0:
+        A = np.ascontiguousarray(A)
+    if B.strides != A.strides:
+        A = np.ascontiguousarray(A); B = np.ascontiguousarray(B)
+    P, h, w = A.shape
+    p = params if params is not None else surf_params(**kw)
+    res = np.zeros(P, PAIR_RESULT_DTYPE)
+    check(L.vfsms_align_batch_host(ctx, _vp(A), _vp(B), P, h, w, A.strides[1], A.strides[0] if P > 1 else h * A.strides[1],
+                                   ctypes.byref(p), float(ratio), int(offset_evaluate), _vp(res)), "vfsms_align_batch_host")
+    return res
+
+
+def align_batch_dev(rois_a, rois_b, results, params=None, ratio=0.75, offset_evaluate=3, stream=None):
+    """Device-resident variant: rois_* are contiguous torch uint8 CUDA tensors [P, h, w]; results is a torch int32
+    CUDA tensor [P, 8].  Asynchronous on `stream` (a torch.cuda.Stream) or the current torch stream."""
+    import torch
+    L = _lib.load()
+    dev = rois_a.device.index or 0
+    ctx = _lib.context(dev)
+    assert rois_a.is_cuda and rois_b.is_cuda and results.is_cuda and rois_a.dtype == torch.uint8
+    assert rois_a.is_contiguous() and rois_b.is_contiguous() and results.is_contiguous() and rois_a.shape == rois_b.shape
+    P, h, w = rois_a.shape
+    assert results.dtype == torch.int32 and results.numel() >= 8 * P
+    p = params if params is not None else surf_params()
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    check(L.vfsms_align_batch_dev(ctx, ctypes.c_void_p(rois_a.data_ptr()), ctypes.c_void_p(rois_b.data_ptr()), P, h, w, w, h * w,
+                                  ctypes.byref(p), float(ratio), int(offset_evaluate), ctypes.c_void_p(results.data_ptr()),
+                                  ctypes.c_void_p(st.cuda_stream)), "vfsms_align_batch_dev")
+
+
+def launch_count(device=0):
+    return int(_lib.load().vfsms_launch_count(_lib.context(device)))
+
+
+def synchronize(device=0):
+    check(_lib.load().vfsms_synchronize(_lib.context(device)), "vfsms_synchronize")
+
+
+def device_count():
+    return int(_lib.load().vfsms_device_count())
+
+
+__all__ = ["surf_params", "surf_detect_and_describe", "match_descriptors", "offset_by_mode", "align_batch",
+           "align_batch_dev", "launch_count", "synchronize", "device_count", "VfsmsError"]

@@ -1,0 +1,172 @@
+/*
+ * vfsms.h -- C ABI of libvfsms.so: the B200-native replacement for the pairwise-alignment hot path of
+ * Keep-Passion/ImageStitch (VFSMS).  Plain pointers and sizes only; no torch / numpy / OpenCV types.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the reference tree).
+ * The reference's own native boundary is the Boost.Python module `myGpuFeatures`
+ * (appendix/myGpuFeatures.cpp:203-209) with three functions; the first block below is that boundary,
+ * the second block is the fused / batched path the Python host (imagestitch_b200/) drives.
+ *
+ * Conventions
+ *   - all functions return 0 on success or a negative VFSMS_E_* code; vfsms_last_error() gives the text
+ *     (thread-local).  Nothing here falls back to a CPU implementation: without a CUDA device
+ *     vfsms_create() fails with VFSMS_E_NODEVICE.
+ *   - "host" pointers are ordinary (preferably pinned) host memory; "dev" pointers are device memory on the
+ *     context's device.  `stream` is a cudaStream_t passed as void* (NULL = the context's own stream).
+ *   - keypoint records are 8 float32: x, y, size, angle, response, octave, laplacian, 0   (VFSMS_KP_STRIDE).
+ *   - row = first image axis (the reference calls it "dx"), col = second axis ("dy"), ImageUtility.py:154-161.
+ */
+#ifndef VFSMS_H
+#define VFSMS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFSMS_VERSION 100
+#define VFSMS_KP_STRIDE 8
+
+enum {
+    VFSMS_OK = 0,
+    VFSMS_E_NODEVICE = -1,   /* no CUDA device / driver */
+    VFSMS_E_CUDA = -2,       /* CUDA runtime error (text in vfsms_last_error) */
+    VFSMS_E_ARG = -3,        /* invalid argument */
+    VFSMS_E_CAPACITY = -4,   /* caller-provided output capacity too small (needed size reported) */
+    VFSMS_E_OVERFLOW = -5,   /* internal candidate buffer overflow even after regrow */
+    VFSMS_E_UNSUPPORTED = -6
+};
+
+typedef struct vfsms_ctx vfsms_ctx;
+
+/* SURF parameters: the argument list of myGpuFeatures.detectAndDescribeBySurf (appendix/myGpuFeatures.cpp:67,
+ * defaults ImageUtility.py:23-28) / cv2.xfeatures2d.SURF_create (ImageUtility.py:258). */
+typedef struct {
+    float hessian_threshold;   /* 100 */
+    int n_octaves;             /* 4 */
+    int n_octave_layers;       /* 3 */
+    int extended;              /* 1 -> 128-d, 0 -> 64-d */
+    float keypoints_ratio;     /* GPU semantics: keep at most min(ratio*rows*cols, 65535) strongest; <= 0: unlimited */
+    int upright;               /* 0 */
+} vfsms_surf_params;
+
+/* Per-pair result of the fused alignment (one evaluation of the body of the search loop,
+ * Stitcher.py:319-346: detect x2 -> match -> getOffsetByMode). */
+typedef struct {
+    int32_t status;     /* 1 when votes >= offset_evaluate (ImageUtility.py:175) */
+    int32_t d_row;      /* ROI-relative mode offset, before the ROI origin is added back (Stitcher.py:353-360) */
+    int32_t d_col;
+    int32_t votes;
+    int32_t n_a;        /* keypoints in ROI A */
+    int32_t n_b;        /* keypoints in ROI B */
+    int32_t n_matches;  /* ratio-test survivors */
+    int32_t flags;      /* bit0: candidate overflow (result invalid) */
+} vfsms_pair_result;
+
+/* ---------------------------------------------------------------- library / context */
+int vfsms_version(void);
+const char *vfsms_last_error(void);
+int vfsms_device_count(void);                 /* 0 when no usable CUDA device */
+/* One context per (process, device): owns a stream, workspaces and cuFFT plans. */
+int vfsms_create(int device, vfsms_ctx **out);
+void vfsms_destroy(vfsms_ctx *ctx);
+int vfsms_synchronize(vfsms_ctx *ctx);
+void *vfsms_stream(vfsms_ctx *ctx);           /* the context's cudaStream_t */
+/* number of kernel launches this context has issued since creation (bench.py's gpu_launches) */
+int64_t vfsms_launch_count(vfsms_ctx *ctx);
+
+/* ---------------------------------------------------------------- legacy plugin boundary (host in, host out) */
+
+/* Replaces myGpuFeatures.detectAndDescribeBySurf (appendix/myGpuFeatures.cpp:67-104; caller ImageUtility.py:272).
+ * image: rows x cols u8, row stride `stride` bytes (strided ROI views are accepted like NDArrayConverter::toMat,
+ * appendix/conversion.cpp:145-243).  kp_out: cap x 8 float32, desc_out: cap x (64|128) float32.
+ * *n_out = keypoints found; VFSMS_E_CAPACITY (and *n_out = needed) when cap is too small. */
+int vfsms_surf_detect_and_describe(vfsms_ctx *ctx, const uint8_t *image, int rows, int cols, int stride,
+                                   const vfsms_surf_params *params, float *kp_out, float *desc_out, int cap,
+                                   int *n_out);
+
+/* Replaces myGpuFeatures.matchDescriptors (appendix/myGpuFeatures.cpp:148-195; callers ImageUtility.py:306,308).
+ * feature_type 1|2: L2 kNN(2) + `d0 < param * d1` (cpp:160-173); 3: Hamming best-1 + `d < param` (cpp:174-187,
+ * descriptors are byte values stored as float32, cpp:118).  matches_out: n_a x 2 int32 rows (trainIdx, queryIdx)
+ * in ascending queryIdx (cpp:53-65). */
+int vfsms_match_descriptors(vfsms_ctx *ctx, const float *desc_a, int n_a, const float *desc_b, int n_b, int dim,
+                            int feature_type, float param, int32_t *matches_out, int *m_out);
+
+/* Replaces myGpuFeatures.detectAndDescribeByOrb (appendix/myGpuFeatures.cpp:106-146; caller ImageUtility.py:274).
+ * desc_out: cap x 32 float32 holding byte values 0..255 (cpp:118). */
+int vfsms_orb_detect_and_describe(vfsms_ctx *ctx, const uint8_t *image, int rows, int cols, int stride,
+                                  int n_features, float scale_factor, int n_levels, int edge_threshold,
+                                  int first_level, int wta_k, int patch_size, int fast_threshold,
+                                  float *kp_out, float *desc_out, int cap, int *n_out);
+
+/* ---------------------------------------------------------------- fused alignment path */
+
+/* Replaces Method.getOffsetByMode (ImageUtility.py:139-178).  kps_*: n x kp_stride float32 with (x, y) first;
+ * matches: m x 2 int32 (trainIdx, queryIdx).  result: status, d_row, d_col, votes filled. */
+int vfsms_offset_by_mode(vfsms_ctx *ctx, const float *kps_a, int n_a, const float *kps_b, int n_b, int kp_stride,
+                         const int32_t *matches, int m, int offset_evaluate, vfsms_pair_result *result);
+
+/* One body of the incremental search loop for a batch of ROI pairs (Stitcher.py:323-346 with
+ * featureMethod="surf", offsetCaculate="mode"):  results[p] = vote(match(surf(roi_a[p]), surf(roi_b[p]))).
+ * All ROIs of a batch share rows x cols; roi_*[p] starts at base + p * pair_stride bytes, row stride `stride`.
+ * Host variant: H2D of the ROIs and D2H of the results are inside the call (what the reference boundary includes,
+ * appendix/myGpuFeatures.cpp:74,84).  Dev variant: inputs already in HBM, results written to device memory,
+ * asynchronous on `stream`. */
+int vfsms_align_batch_host(vfsms_ctx *ctx, const uint8_t *rois_a, const uint8_t *rois_b, int n_pairs,
+                           int rows, int cols, int stride, int64_t pair_stride,
+                           const vfsms_surf_params *params, float ratio, int offset_evaluate,
+                           vfsms_pair_result *results);
+int vfsms_align_batch_dev(vfsms_ctx *ctx, const uint8_t *rois_a_dev, const uint8_t *rois_b_dev, int n_pairs,
+                          int rows, int cols, int stride, int64_t pair_stride,
+                          const vfsms_surf_params *params, float ratio, int offset_evaluate,
+                          vfsms_pair_result *results_dev, void *stream);
+
+/* Matcher on device-resident descriptors (bench / profiling hook for the BF matcher, ImageUtility.py:278-309):
+ * exact fp32 kNN(2)+ratio for n_pairs descriptor sets laid out [pair][cap][dim], counts per pair on device. */
+int vfsms_match_batch_dev(vfsms_ctx *ctx, const float *desc_a_dev, const int32_t *n_a_dev, const float *desc_b_dev,
+                          const int32_t *n_b_dev, int n_pairs, int cap, int dim, float ratio,
+                          int32_t *best_idx_dev /* [pair][cap][2] */, float *best_dist_dev /* [pair][cap][2] */,
+                          void *stream);
+
+/* ---------------------------------------------------------------- phase correlation */
+
+/* Replaces cv2.phaseCorrelate(np.float64(roiA), np.float64(roiB)) as called at Stitcher.py:230 (no window):
+ * pads to the optimal DFT size, cross-power spectrum, inverse transform, 5x5 weighted centroid.
+ * out: shift_x, shift_y, response (float64, cv2's sign convention). */
+int vfsms_phase_correlate_host(vfsms_ctx *ctx, const uint8_t *roi_a, const uint8_t *roi_b, int rows, int cols,
+                               int stride, double out[3]);
+int vfsms_phase_correlate_dev(vfsms_ctx *ctx, const uint8_t *roi_a_dev, const uint8_t *roi_b_dev, int rows, int cols,
+                              int stride, double *out_dev, void *stream);
+
+/* ---------------------------------------------------------------- overlap blending */
+
+enum {
+    VFSMS_FUSE_NONE = 0,        /* "notFuse"            Stitcher.py:507 */
+    VFSMS_FUSE_AVERAGE = 1,     /* fuseByAverage        ImageFusion.py:12-21 */
+    VFSMS_FUSE_MAXIMUM = 2,     /* fuseByMaximum        ImageFusion.py:23-31 */
+    VFSMS_FUSE_MINIMUM = 3,     /* fuseByMinimum        ImageFusion.py:33-41 */
+    VFSMS_FUSE_FADE = 4,        /* fuseByFadeInAndFadeOut ImageFusion.py:192-244 */
+    VFSMS_FUSE_TRIG = 5,        /* fuseByTrigonometric  ImageFusion.py:246-293 */
+    VFSMS_FUSE_MULTIBAND = 6    /* fuseByMultiBandBlending ImageFusion.py:296-367 */
+};
+
+/* Replaces Stitcher.fuseImage (Stitcher.py:488-525) for one overlap ROI.  a, b: rows x cols x channels int16 with
+ * -1 = empty (the reference's int64 canvas sentinel, Stitcher.py:434-436); out: rows x cols x channels u8.
+ * d_row / d_col: the ORIGINAL pair offset whose sign selects the ramp direction (Stitcher.py:478,483). */
+int vfsms_fuse_roi_host(vfsms_ctx *ctx, const int16_t *a, const int16_t *b, int rows, int cols, int channels,
+                        int method, int d_row, int d_col, uint8_t *out);
+
+/* Replaces Stitcher.getStitchByOffset's paste/blend loop (Stitcher.py:433-486) on a device-resident canvas.
+ * tiles: n_tiles images of tile_rows x tile_cols x channels u8 (host), placed at rectified offsets (row, col);
+ * occupied-bbox bookkeeping (rangeX / rangeY) is computed by the host mirror and passed as roi rects.
+ * canvas_out: canvas_rows x canvas_cols x channels u8 (host). */
+int vfsms_mosaic_host(vfsms_ctx *ctx, const uint8_t *tiles, int n_tiles, int tile_rows, int tile_cols, int channels,
+                      const int32_t *tile_origin /* n x 2 */, const int32_t *roi_rect /* n x 4: r0,c0,r1,c1 */,
+                      const int32_t *pair_offset /* n x 2 original offsets */, int method,
+                      int canvas_rows, int canvas_cols, uint8_t *canvas_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFSMS_H */

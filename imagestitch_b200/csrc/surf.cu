@@ -235,7 +235,7 @@ __device__ __forceinline__ float haar_response(const int32_t *__restrict__ o, in
     for (int k = 0; k < n; k++) {
         const int32_t v = __ldg(o + f[k].y1 * W + f[k].x1) + __ldg(o + f[k].y2 * W + f[k].x2)
                         - __ldg(o + f[k].y2 * W + f[k].x1) - __ldg(o + f[k].y1 * W + f[k].x2);
-        d += (double)v * (double)f[k].w;
+        d += (double)((float)v * f[k].w);      // int * float rounds to float first, like the CPU expression
     }
     return (float)d;
 }
@@ -606,9 +606,9 @@ __global__ void __launch_bounds__(DESC_THREADS) orient_describe_kernel(
                     // dx pattern {0,0,2,4,-1},{2,0,4,4,+1}; dy pattern {0,0,4,2,+1},{0,2,4,4,-1}
                     const int bl = box_sum(o, W, 0, 0, h2, h4), br = box_sum(o, W, h2, 0, h4, h4);
                     const int bt = box_sum(o, W, 0, 0, h4, h2), bb = box_sum(o, W, 0, h2, h4, h4);
-                    double d = 0; d += (double)bl * (double)(-wgt); d += (double)br * (double)wgt;
+                    double d = 0; d += (double)((float)bl * (-wgt)); d += (double)((float)br * wgt);
                     const float vx = (float)d;
-                    d = 0; d += (double)bt * (double)wgt; d += (double)bb * (double)(-wgt);
+                    d = 0; d += (double)((float)bt * wgt); d += (double)((float)bb * (-wgt));
                     const float vy = (float)d;
                     vX = vx * c_aptw[tid]; vY = vy * c_aptw[tid];
                     have = true;

@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- pairwise alignments/s on 2048^2 tiles (BASELINE.json metric), one process per GPU.
+
+A "step" = one pass of the hot path (2 x ROI SURF detect+describe -> kNN(2) match + ratio -> offset vote, i.e. one
+body of Stitcher.calculateOffsetForFeatureSearchIncre succeeding at i=1 in the starting direction, roiRatio 0.2,
+GPU-SURF parameters of ImageUtility.py:23-28) over a batch of synthetic tile pairs.
+  value : whole-job pairs/s with tiles resident in HBM (device timing, max over ranks)
+  e2e   : same metric through the public host API (gpu.align_batch: pinned host ROIs -> H2D -> kernels -> D2H)
+  --impl reference : the CPU port of the same path (oracle SURF on all host cores + cv2 BFMatcher + vote port)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROI_RATIO = 0.2
+TILE = 2048
+OVERLAP = 205
+METRIC = "pairwise_alignments_per_s_2048sq_surf"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index; self.rows = []; self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_pipeline_pair(roiA, roiB, mf):
+    """CPU port of one alignment: oracle SURF (OpenMP) + cv2 BFMatcher kNN(2) (the call the reference makes,
+    ImageUtility.py:288-289) + ratio test + vote port."""
+    import cv2
+    from oracle import surf
+    kA, dA = surf.detect_and_compute(roiA, 100.0, 4, 3, True, False, mf)
+    kB, dB = surf.detect_and_compute(roiB, 100.0, 4, 3, True, False, mf)
+    matcher = cv2.DescriptorMatcher_create("BruteForce")
+    raw = matcher.knnMatch(dA, dB, 2)
+    m = np.array([(r[0].trainIdx, r[0].queryIdx) for r in raw if len(r) == 2 and r[0].distance < r[1].distance * 0.75], np.int32).reshape(-1, 2)
+    return surf.offset_by_mode(kA, kB, m, 3)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import cv2
+    from imagestitch_b200 import synth
+    from oracle import surf
+    L = int(np.floor(TILE * ROI_RATIO))
+    mf = int(0.01 * L * TILE)
+    n_sample = 2
+    tiles, offs = [], []
+    for p in range(n_sample):
+        A, B, off = synth.pair(seed=1234 + p, size=TILE, overlap=OVERLAP, direction=1)
+        tiles.append((np.ascontiguousarray(A[TILE - L:]), np.ascontiguousarray(B[:L]))); offs.append(off)
+    for _ in range(args.warmup):
+        cpu_pipeline_pair(tiles[0][0], tiles[0][1], mf)
+    t0 = time.perf_counter()
+    ok = 0
+    for _ in range(args.steps):
+        for (a, b), off in zip(tiles, offs):
+            st, o, v = cpu_pipeline_pair(a, b, mf)
+            ok += int(st and abs(o[0] + TILE - L - off[0]) <= 1 and abs(o[1] - off[1]) <= 1)
+    dt = time.perf_counter() - t0
+    val = args.steps * n_sample / dt
+    cores = surf.num_threads()
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "synthetic 2048x2048 grayscale pair, SURF detect+describe+match+vote (ROI 409x2048, GPU-SURF params)",
+                      "pairs_per_step": n_sample, "correct_pairs": ok, "cv2_threads": cv2.getNumThreads(), "host_cpus": os.cpu_count()},
+           "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
+                            "sample": "%d pairs/step x %d steps: oracle C SURF (OpenMP %d thr) + cv2 BFMatcher knnMatch + ratio + vote port" % (n_sample, args.steps, cores)},
+           "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--pairs", type=int, default=32, help="tile pairs per GPU per step")
+    ap.add_argument("--batches", type=int, default=3, help="distinct input batches rotated through (L2 hygiene)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from imagestitch_b200 import gpu, synth
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P, NB = args.pairs, args.batches
+    L = int(np.floor(TILE * ROI_RATIO))
+    params = gpu.surf_params()          # GPU-SURF defaults, ImageUtility.py:23-28
+
+    # ---- synthetic input, resident in HBM: NB distinct batches of P tile pairs (2 x NB x P x 4 MiB)
+    batches = []
+    for nb in range(NB):
+        A, B, offs = synth.pair_batch_torch(seed=2025 + 97 * rank + nb, n_pairs=P, size=TILE, overlap=OVERLAP, device=dev)
+        batches.append((A, B, offs))
+    results = [torch.zeros((P, 8), dtype=torch.int32, device=dev) for _ in range(NB)]
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i):
+        A, B, _ = batches[i % NB]
+        gpu.align_strips_dev(A, B, results[i % NB], L, params=params, stream=stream)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize(dev)
+    gpu.profile_read(reset=True, device=local)
+    gpu.profile_enable(True, device=local)
+    clocks = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    clocks.start()
+    l0 = gpu.launch_count(local)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    if world > 1:       # the only collective of the path: gather of the per-pair result table
+        gathered = [torch.empty_like(results[0]) for _ in range(world)]
+        dist.all_gather(gathered, results[(args.steps - 1) % NB])
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = gpu.launch_count(local) - l0
+    clk = clocks.stop()
+    gpu.profile_enable(False, device=local)
+    stages = gpu.profile_read(reset=True, device=local)
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+
+    # ---- correctness of what was timed
+    ok = 0; tot = 0; nkp = []; nmatch = []
+    for nb in range(min(NB, args.steps)):
+        r = results[nb].cpu().numpy(); offs = batches[nb][2]
+        for p in range(P):
+            tot += 1
+            ok += int(r[p, 0] == 1 and abs(r[p, 1] + TILE - L - offs[p, 0]) <= 1 and abs(r[p, 2] - offs[p, 1]) <= 1 and r[p, 7] == 0)
+            nkp.append((r[p, 4], r[p, 5])); nmatch.append(r[p, 6])
+    nkp = np.array(nkp, np.float64); mean_na, mean_nb = nkp[:, 0].mean(), nkp[:, 1].mean()
+
+    # ---- e2e: public host API with pinned host ROIs (H2D + kernels + D2H inside the timed region)
+    A0, B0, offs0 = batches[0]
+    hostA = torch.empty((P, L, TILE), dtype=torch.uint8).pin_memory(); hostB = torch.empty_like(hostA).pin_memory()
+    hostA.copy_(A0[:, TILE - L:, :]); hostB.copy_(B0[:, :L, :])
+    nA, nB_ = hostA.numpy(), hostB.numpy()
+    for _ in range(2):
+        gpu.align_batch(nA, nB_, params=params, device=local)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(e2e_steps):
+        res_host = gpu.align_batch(nA, nB_, params=params, device=local)
+    torch.cuda.synchronize(dev)
+    dt_e2e = time.perf_counter() - t0
+    te = torch.tensor([dt_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * P * e2e_steps / float(te.item())
+    e2e_ok = int(sum(int(r["status"] == 1 and abs(r["d_row"] + TILE - L - offs0[p, 0]) <= 1) for p, r in enumerate(res_host)))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant stage (CUDA-event time inside the timed region)
+    peaks = load_peaks()
+    stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in stages.items() if v[1] > 0}
+    dom = max(stage_ms, key=stage_ms.get)
+    D = 128
+    px = L * TILE
+    imgs = 2 * P
+    alg = {
+        # B_det ~ 88.7 B/px (u8 in + integral w/r + det/trace w + det r) over all 2P ROI images
+        "integral": ("hbm", (1 + 4) * px * imgs),
+        "hessian_nms": ("hbm", (4 + 2 * 4 * 5 * 1.328 + 4 * 5 * 1.328) * px * imgs),
+        "orient_describe": ("hbm", sum((113 * 16 * 4 + 60 * 60 + 4 * D + 28) * n for n in (mean_na, mean_nb)) * P),
+        "match_knn2": ("tensor", 2.0 * mean_na * mean_nb * D * P),
+        "match_tc": ("tensor", 2.0 * mean_na * mean_nb * D * P),
+    }
+    roof = None
+    if dom in alg:
+        bound, work = alg[dom]
+        t = stage_ms[dom] * 1e-3
+        if bound == "hbm":
+            ach = work / t / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                    "traffic": None, "peak_source": peaks["source"], "algorithmic_bytes_per_launch": work}
+        else:
+            ach = work / t / 1e12
+            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+                    "algorithmic_flops_per_launch": work,
+                    "matcher_gbs": (4 * D * (mean_na + mean_nb) + 16 * mean_na) * P / t / 1e9}
+    else:
+        roof = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None}
+
+    # ---- CPU baseline on a bounded sample of the same workload (rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import surf
+        mf = int(0.01 * L * TILE)
+        sample = 3
+        cpu_pipeline_pair(nA[0], nB_[0], mf)
+        t0 = time.perf_counter()
+        for p in range(sample):
+            cpu_pipeline_pair(nA[p], nB_[p], mf)
+        dtc = time.perf_counter() - t0
+        cpu = {"value": sample / dtc, "unit": "pairs/s", "cores": surf.num_threads(), "kind": "port",
+               "sample": "%d ROI pairs (409x2048) of this workload: oracle C SURF (OpenMP) + cv2 BFMatcher knnMatch + ratio + vote port" % sample}
+
+    value = world * P * args.steps / (ms_max * 1e-3)
+    out = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": "synthetic 2048x2048 grayscale pair, SURF detect+describe+match+vote (configs[1]); ROI 409x2048 read in place from HBM-resident tiles",
+                      "pairs_per_gpu_per_step": P, "global_pairs_per_step": P * world, "roi": [L, TILE], "surf": "thr100 oct4 layers3 128-d ratio0.01",
+                      "l2": "%d distinct input batches rotated; per-step intermediate traffic > L2" % NB,
+                      "mean_keypoints": [mean_na, mean_nb], "mean_matches": float(np.mean(nmatch)), "correct_pairs": "%d/%d" % (ok, tot),
+                      "e2e_correct_pairs": "%d/%d" % (e2e_ok, P)},
+           "clocks": clk, "gpu_launches": int(launches),
+           "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * P * L * TILE), "d2h_bytes_per_step": int(P * 32),
+                   "steps": e2e_steps},
+           "roofline": roof, "stages_ms_per_step": stage_ms}
+    if cpu:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -18,7 +18,38 @@ void vfsms_set_error(const char *fmt, ...)
 void phase_state_destroy(vfsms_ctx *ctx);
 void blend_state_destroy(vfsms_ctx *ctx);
 
+cudaEvent_t prof_event(vfsms_ctx *ctx)
+{
+    if (!ctx->prof_free.empty()) { cudaEvent_t e = ctx->prof_free.back(); ctx->prof_free.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+
+static const char *k_stage_names[VFSMS_STAGE_COUNT] = { "integral", "hessian_nms", "rank_sort", "validate_compact", "orient_describe",
+                                                        "transpose", "match_knn2", "ratio_vote", "phase_fft", "phase_peak", "blend",
+                                                        "match_tc" };
+
 extern "C" {
+
+int vfsms_profile_enable(vfsms_ctx *ctx, int on) { if (!ctx) return VFSMS_E_ARG; ctx->prof = on != 0; return 0; }
+const char *vfsms_stage_name(int stage) { return (stage >= 0 && stage < VFSMS_STAGE_COUNT) ? k_stage_names[stage] : ""; }
+int vfsms_profile_read(vfsms_ctx *ctx, float *ms_out, int32_t *calls_out, int reset)
+{
+    if (!ctx) return VFSMS_E_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (auto &pp : ctx->prof_pending) {
+        float ms = 0; cudaEventElapsedTime(&ms, pp.a, pp.b);
+        ctx->prof_ms[pp.stage] += ms; ctx->prof_calls[pp.stage]++;
+        ctx->prof_free.push_back(pp.a); ctx->prof_free.push_back(pp.b);
+    }
+    ctx->prof_pending.clear();
+    for (int i = 0; i < VFSMS_STAGE_COUNT; i++) {
+        if (ms_out) ms_out[i] = ctx->prof_ms[i];
+        if (calls_out) calls_out[i] = ctx->prof_calls[i];
+        if (reset) { ctx->prof_ms[i] = 0; ctx->prof_calls[i] = 0; }
+    }
+    return 0;
+}
 
 int vfsms_version(void) { return VFSMS_VERSION; }
 const char *vfsms_last_error(void) { return g_err; }
@@ -56,6 +87,8 @@ void vfsms_destroy(vfsms_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (auto &pp : ctx->prof_pending) { cudaEventDestroy(pp.a); cudaEventDestroy(pp.b); }
+    for (auto e : ctx->prof_free) cudaEventDestroy(e);
     phase_state_destroy(ctx);
     blend_state_destroy(ctx);
     SurfWorkspace &w = ctx->surf;
@@ -196,14 +229,21 @@ static int align_batch_launch(vfsms_ctx *ctx, const uint8_t *a_dev, const uint8_
     const int cap = ws.kp_cap, dim = ws.dim;
     const int32_t *nfin = ws.counters.as<int32_t>() + 2;     // n_final of image b at [b*4]
     const int32_t *flags = ws.counters.as<int32_t>() + 3;
-    CUDA_TRY(cudaMemsetAsync(ws.descT.p, 0, (size_t)2 * n_pairs * cap * dim * 4, st));
-    if ((rc = transpose_desc_batch(ctx, ws.desc.as<float>(), nfin, 4, ws.descT.as<float>(), 2 * n_pairs, cap, dim,
-                                   (int64_t)cap * dim, (int64_t)cap * dim, st))) return rc;
+    {
+        StageTimer t(ctx, st, VFSMS_STAGE_TRANSPOSE);
+        CUDA_TRY(cudaMemsetAsync(ws.descT.p, 0, (size_t)2 * n_pairs * cap * dim * 4, st));
+        if ((rc = transpose_desc_batch(ctx, ws.desc.as<float>(), nfin, 4, ws.descT.as<float>(), 2 * n_pairs, cap, dim,
+                                       (int64_t)cap * dim, (int64_t)cap * dim, st))) return rc;
+    }
     MatchWorkspace &mw = ctx->match;
     const float *AT = ws.descT.as<float>(), *BT = AT + (size_t)n_pairs * cap * dim;
-    if ((rc = match_l2_knn2_batch(ctx, AT, nfin, 4, BT, nfin + 4 * n_pairs, 4, n_pairs, cap, dim, (int64_t)cap * dim, (int64_t)cap * dim,
-                                  mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(), st))) return rc;
+    {
+        StageTimer t(ctx, st, VFSMS_STAGE_MATCH);
+        if ((rc = match_l2_knn2_batch(ctx, AT, nfin, 4, BT, nfin + 4 * n_pairs, 4, n_pairs, cap, dim, (int64_t)cap * dim, (int64_t)cap * dim,
+                                      mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(), st))) return rc;
+    }
     const float *KA = ws.kp.as<float>(), *KB = KA + (size_t)n_pairs * cap * KP_STRIDE;
+    StageTimer tv(ctx, st, VFSMS_STAGE_VOTE);
     if ((rc = ratio_vote_batch(ctx, KA, KB, (int64_t)cap * KP_STRIDE, (int64_t)cap * KP_STRIDE, KP_STRIDE, nfin, 4, nfin + 4 * n_pairs, 4,
                                mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(), n_pairs, cap, 0, ratio, offset_evaluate,
                                flags, flags + 4 * n_pairs, 4, 1, results_dev, st))) return rc;

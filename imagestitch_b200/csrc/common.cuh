@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 #include "../../include/vfsms.h"
 
 #define KP_X 0
@@ -122,7 +123,14 @@ struct MatchWorkspace {
     int table_size = 0;
 };
 
+struct ProfPending { int stage; cudaEvent_t a, b; };
+
 struct vfsms_ctx {
+    bool prof = false;
+    std::vector<ProfPending> prof_pending;
+    std::vector<cudaEvent_t> prof_free;
+    float prof_ms[VFSMS_STAGE_COUNT] = {0};
+    int32_t prof_calls[VFSMS_STAGE_COUNT] = {0};
     int device = 0;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
@@ -135,6 +143,18 @@ struct vfsms_ctx {
     HostBuf pinned_in, pinned_out;
     void *phase_state = nullptr;   // cuFFT plans etc. (phase.cu)
     void *blend_state = nullptr;
+};
+
+// stage timing: events on the launching stream; no-ops unless vfsms_profile_enable(ctx, 1)
+cudaEvent_t prof_event(vfsms_ctx *ctx);
+struct StageTimer {
+    vfsms_ctx *ctx; cudaStream_t st; int stage; cudaEvent_t a = nullptr;
+    StageTimer(vfsms_ctx *c, cudaStream_t s, int stg) : ctx(c), st(s), stage(stg) {
+        if (ctx->prof) { a = prof_event(ctx); cudaEventRecord(a, st); }
+    }
+    ~StageTimer() {
+        if (a) { cudaEvent_t b = prof_event(ctx); cudaEventRecord(b, st); ctx->prof_pending.push_back({stage, a, b}); }
+    }
 };
 
 // ---------------------------------------------------------------- internal entry points (defined in the .cu files)

@@ -865,6 +865,8 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         attr_done = true;
     }
     CUDA_TRY(cudaMemsetAsync(ws.counters.p, 0, (size_t)batch * 16, st));
+    {
+    StageTimer t_int(ctx, st, VFSMS_STAGE_INTEGRAL);
     integral_band_kernel<<<dim3(n_bands, batch), 256, smem_int, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
                                                                       ws.integral.as<int32_t>(), ws.band_tot.as<int32_t>(), n_bands);
     LAUNCH_CHECK(ctx);
@@ -873,8 +875,10 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
                                                                       ws.band_tot.as<int32_t>(), n_bands);
         LAUNCH_CHECK(ctx);
     }
+    }
     const int total_tiles = plan.tile_begin[plan.n_octaves];
     if (total_tiles > 0) {
+        StageTimer t_h(ctx, st, VFSMS_STAGE_HESSIAN);
         const size_t smem_h = (size_t)plan.n_layers * (HT_X + 2) * (HT_Y + 2) * 4;
         hessian_nms_kernel<<<dim3(total_tiles, batch), HT_THREADS, smem_h, st>>>(plan, ws.integral.as<int32_t>(),
                                                                                  ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap);
@@ -882,17 +886,22 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
     }
     const int max_features = ws.max_features;
     {
+        StageTimer t_s(ctx, st, VFSMS_STAGE_SORT);
         const int chunks = ceil_div(ws.cand_cap, 256) * batch;
         const int grid = min(chunks, ctx->num_sms * 8);
         rank_sort_kernel<<<grid, 256, 0, st>>>(ws.cand.as<float>(), ws.sorted.as<float>(), ws.counters.as<int32_t>(),
                                               ws.cand_cap, batch, max_features);
         LAUNCH_CHECK(ctx);
     }
+    {
+    StageTimer t_c(ctx, st, VFSMS_STAGE_COMPACT);
     validate_compact_kernel<<<batch, 1024, 0, st>>>(ws.sorted.as<float>(), ws.kp.as<float>(), ws.counters.as<int32_t>(),
                                                     ws.cand_cap, ws.kp_cap, rows, cols, p->upright);
     LAUNCH_CHECK(ctx);
     prefix_kernel<<<1, 32, 0, st>>>(ws.counters.as<int32_t>(), ws.prefix.as<int32_t>(), batch);
     LAUNCH_CHECK(ctx);
+    }
+    StageTimer t_d(ctx, st, VFSMS_STAGE_DESCRIBE);
     orient_describe_kernel<<<ctx->num_sms * 6, DESC_THREADS, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
                                                                        ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(),
                                                                        ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, p->upright);

@@ -136,6 +136,37 @@ def align_batch_dev(rois_a, rois_b, results, params=None, ratio=0.75, offset_eva
                                   ctypes.c_void_p(st.cuda_stream)), "vfsms_align_batch_dev")
 
 
+def align_strips_dev(tiles_a, tiles_b, results, roi_rows, params=None, ratio=0.75, offset_evaluate=3, stream=None):
+    """Direction-1 incremental-search body on device-resident FULL tiles [P, H, W] (torch uint8 CUDA): ROI A = bottom
+    `roi_rows` rows of tiles_a[p], ROI B = top rows of tiles_b[p] (ImageUtility.py:77-82), read in place by stride."""
+    import torch
+    L = _lib.load()
+    dev = tiles_a.device.index or 0
+    ctx = _lib.context(dev)
+    assert tiles_a.is_cuda and tiles_a.dtype == torch.uint8 and tiles_a.is_contiguous() and tiles_b.is_contiguous()
+    P, H, W = tiles_a.shape
+    assert results.dtype == torch.int32 and results.numel() >= 8 * P and results.is_contiguous()
+    p = params if params is not None else surf_params()
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    a_ptr = tiles_a.data_ptr() + (H - roi_rows) * W
+    check(L.vfsms_align_batch_dev(ctx, ctypes.c_void_p(a_ptr), ctypes.c_void_p(tiles_b.data_ptr()), P, roi_rows, W, W, H * W,
+                                  ctypes.byref(p), float(ratio), int(offset_evaluate), ctypes.c_void_p(results.data_ptr()),
+                                  ctypes.c_void_p(st.cuda_stream)), "vfsms_align_batch_dev")
+
+
+def profile_enable(on=True, device=0):
+    check(_lib.load().vfsms_profile_enable(_lib.context(device), int(on)), "vfsms_profile_enable")
+
+
+def profile_read(reset=True, device=0):
+    """-> {stage_name: (total_ms, calls)} measured with CUDA events on the launching stream."""
+    L = _lib.load()
+    ms = np.zeros(_lib.STAGE_COUNT, np.float32)
+    calls = np.zeros(_lib.STAGE_COUNT, np.int32)
+    check(L.vfsms_profile_read(_lib.context(device), _vp(ms), _vp(calls), int(reset)), "vfsms_profile_read")
+    return {L.vfsms_stage_name(i).decode(): (float(ms[i]), int(calls[i])) for i in range(_lib.STAGE_COUNT)}
+
+
 def launch_count(device=0):
     return int(_lib.load().vfsms_launch_count(_lib.context(device)))
 

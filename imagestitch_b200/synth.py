@@ -80,3 +80,60 @@ def pair(seed=1234, size=2048, overlap=205, direction=1):
     else:
         tiles, off = tile_sequence(seed, 1, 2, size, overlap)
     return tiles[0], tiles[1], (int(off[0][0]), int(off[0][1]))
+
+
+# ---------------------------------------------------------------- torch (device) variant of the same recipe, for bench.py
+def canvas_torch(seed, H, W, device):
+    """Same recipe as canvas() evaluated with torch on `device` (different RNG stream, same statistics)."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator(device=device)
+    acc = torch.zeros((H, W), dtype=torch.float32, device=device)
+    for k, (sigma, wgt) in enumerate(zip((1.5, 3.0, 6.0, 12.0), (1.0, 0.8, 0.6, 0.4))):
+        g.manual_seed(seed + k)
+        f = torch.randn((1, 1, H, W), generator=g, device=device, dtype=torch.float32)
+        r = int(3 * sigma + 0.5)
+        x = torch.arange(-r, r + 1, device=device, dtype=torch.float32)
+        kern = torch.exp(-0.5 * (x / sigma) ** 2)
+        kern = kern / kern.sum()
+        f = F.conv2d(F.pad(f, (r, r, 0, 0), mode="reflect"), kern.view(1, 1, 1, -1))
+        f = F.conv2d(F.pad(f, (0, 0, r, r), mode="reflect"), kern.view(1, 1, -1, 1))
+        f = f[0, 0]
+        acc += wgt * f / f.std().clamp_min(1e-6)
+    rng = np.random.default_rng(seed + 100)
+    n_disc = int(round(20 * H * W / 1e6))
+    ys = rng.integers(16, H - 16, n_disc); xs = rng.integers(16, W - 16, n_disc)
+    rs = rng.uniform(3, 12, n_disc); depth = rng.uniform(0.8, 2.0, n_disc)
+    yy, xx = torch.meshgrid(torch.arange(-13, 14, device=device), torch.arange(-13, 14, device=device), indexing="ij")
+    d2 = (yy * yy + xx * xx).float()
+    for y, x, r, d in zip(ys, xs, rs, depth):
+        patch = acc[y - 13:y + 14, x - 13:x + 14]
+        patch -= float(d) * (d2 <= float(r * r)).float()
+    acc = (acc - acc.mean()) / acc.std().clamp_min(1e-6)
+    return (acc * 40.0 + 124.0).clamp(0, 255)
+
+
+def pair_batch_torch(seed, n_pairs, size, overlap, device, noise=2.0, canvas_hw=None):
+    """n_pairs vertically overlapping tile pairs (direction 1) cropped from one synthetic canvas.
+    Returns (tiles_a [P,size,size] u8, tiles_b, true_offsets [P,2] int64 numpy)."""
+    import torch
+    step = size - overlap
+    H, W = canvas_hw if canvas_hw else (size + step + 64, size * 3)
+    base = canvas_torch(seed, H, W, device)
+    rng = np.random.default_rng(seed + 7)
+    vig = torch.from_numpy(_vignette(size, size)).to(device)
+    g = torch.Generator(device=device)
+    A = torch.empty((n_pairs, size, size), dtype=torch.uint8, device=device)
+    B = torch.empty_like(A)
+    offs = np.zeros((n_pairs, 2), np.int64)
+    for p in range(n_pairs):
+        dr = step + int(rng.integers(-24, 25)); dc = int(rng.integers(-4, 5))
+        r0 = int(rng.integers(0, H - size - dr)); c0 = int(rng.integers(4, W - size - 4))
+        offs[p] = (dr, dc)
+        for dst, (r, c), sd in ((A, (r0, c0), 2 * p), (B, (r0 + dr, c0 + dc), 2 * p + 1)):
+            t = base[r:r + size, c:c + size] * vig
+            if noise > 0:
+                g.manual_seed(seed + 1000 + sd)
+                t = t + noise * torch.randn(t.shape, generator=g, device=device)
+            dst[p] = (t + 0.5).clamp(0, 255).to(torch.uint8)
+    return A, B, offs

@@ -76,6 +76,18 @@ void *vfsms_stream(vfsms_ctx *ctx);           /* the context's cudaStream_t */
 /* number of kernel launches this context has issued since creation (bench.py's gpu_launches) */
 int64_t vfsms_launch_count(vfsms_ctx *ctx);
 
+/* Per-stage device timing with CUDA events recorded on the launching stream (bench.py's roofline numbers).
+ * Off by default.  vfsms_profile_read synchronises the stream, then returns accumulated milliseconds and call
+ * counts per stage (arrays of VFSMS_STAGE_COUNT) and optionally resets them. */
+enum {
+    VFSMS_STAGE_INTEGRAL = 0, VFSMS_STAGE_HESSIAN, VFSMS_STAGE_SORT, VFSMS_STAGE_COMPACT, VFSMS_STAGE_DESCRIBE,
+    VFSMS_STAGE_TRANSPOSE, VFSMS_STAGE_MATCH, VFSMS_STAGE_VOTE, VFSMS_STAGE_PHASE_FFT, VFSMS_STAGE_PHASE_PEAK,
+    VFSMS_STAGE_BLEND, VFSMS_STAGE_MATCH_TC, VFSMS_STAGE_COUNT
+};
+int vfsms_profile_enable(vfsms_ctx *ctx, int on);
+int vfsms_profile_read(vfsms_ctx *ctx, float *ms_out, int32_t *calls_out, int reset);
+const char *vfsms_stage_name(int stage);
+
 /* ---------------------------------------------------------------- legacy plugin boundary (host in, host out) */
 
 /* Replaces myGpuFeatures.detectAndDescribeBySurf (appendix/myGpuFeatures.cpp:67-104; caller ImageUtility.py:272).

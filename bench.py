@@ -157,12 +157,14 @@ def main():
         A, B, offs = synth.pair_batch_torch(seed=2025 + 97 * rank + nb, n_pairs=P, size=TILE, overlap=OVERLAP, device=dev)
         batches.append((A, B, offs))
     results = [torch.zeros((P, 8), dtype=torch.int32, device=dev) for _ in range(NB)]
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)          # explicit non-NULL stream: kernels and timing events share it
+    torch.cuda.synchronize(dev)
 
     def step(i):
         A, B, _ = batches[i % NB]
         gpu.align_strips_dev(A, B, results[i % NB], L, params=params, stream=stream)
 
+    torch.cuda.set_stream(stream)
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize(dev)

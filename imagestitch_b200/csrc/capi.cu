@@ -91,6 +91,8 @@ void vfsms_destroy(vfsms_ctx *ctx)
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
     phase_state_destroy(ctx);
     blend_state_destroy(ctx);
+    surf_tex_destroy(ctx);
+    ctx->tex_dev.release();
     SurfWorkspace &w = ctx->surf;
     DevBuf *bufs[] = { &w.integral, &w.band_tot, &w.cand, &w.sorted, &w.kp, &w.desc, &w.descT, &w.counters, &w.prefix,
                        &ctx->match.best_idx, &ctx->match.best_dist, &ctx->match.matches, &ctx->match.n_matches,

@@ -141,6 +141,8 @@ struct vfsms_ctx {
     DevBuf results;           // vfsms_pair_result[pairs]
     DevBuf scratch0, scratch1, scratch2, scratch3;
     HostBuf pinned_in, pinned_out;
+    void *tex_cache = nullptr;     // texture objects over caller images (surf.cu)
+    DevBuf tex_dev;
     void *phase_state = nullptr;   // cuFFT plans etc. (phase.cu)
     void *blend_state = nullptr;
 };
@@ -166,6 +168,7 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
 
 int surf_grow(vfsms_ctx *ctx, int grow_cand, int grow_kp);
 int surf_init_tables();
+void surf_tex_destroy(vfsms_ctx *ctx);
 
 int match_reserve(vfsms_ctx *ctx, int n_pairs, int cap);
 int transpose_desc_batch(vfsms_ctx *ctx, const float *src, const int32_t *n_ptr, int n_stride, float *dst, int n_pairs, int cap,

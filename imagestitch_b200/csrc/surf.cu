@@ -15,6 +15,9 @@
 #include "common.cuh"
 #include <math.h>
 #include <float.h>
+#include <map>
+#include <tuple>
+#include <vector>
 
 #define ORI_RADIUS 6
 #define ORI_WIN 60
@@ -556,7 +559,287 @@ __device__ __forceinline__ int window_pixel(const uint8_t *__restrict__ img, int
     return img[(size_t)y * stride + x];
 }
 
+// TEX variant: one tex2Dgather returns the whole 2x2 footprint (exact integer texels, no filtering arithmetic).
+__device__ __forceinline__ int window_pixel_tex(cudaTextureObject_t tex, const uint8_t *__restrict__ img, int stride,
+                                                int ncols1, int nrows1, double pixel_x, double pixel_y)
+{
+    const int ix = __double2int_rd(pixel_x), iy = __double2int_rd(pixel_y);
+    if ((unsigned)ix < (unsigned)ncols1 && (unsigned)iy < (unsigned)nrows1) {
+        const float a = (float)(pixel_x - ix), bq = (float)(pixel_y - iy);
+        const uchar4 g = tex2Dgather<uchar4>(tex, (float)ix + 1.0f, (float)iy + 1.0f, 0);
+        const float p00 = g.w, p01 = g.z, p10 = g.x, p11 = g.y;
+        const float v = p00 * (1.f - a) * (1.f - bq) + p01 * a * (1.f - bq) + p10 * (1.f - a) * bq + p11 * a * bq;
+        return __float2int_rn(v) & 255;
+    }
+    int x = __double2int_rn(pixel_x), y = __double2int_rn(pixel_y);
+    x = min(max(x, 0), ncols1); y = min(max(y, 0), nrows1);
+    return img[(size_t)y * stride + x];
+}
+
 #define DESC_THREADS 256
+#define WK_MAX_WIN 768       // windows up to this size are described by one warp (n_octaves <= 4 never exceeds 739)
+#define WK_WARPS 8
+
+// ---------------------------------------------------------------- K4a: orientation + descriptor, one WARP per keypoint
+// Same arithmetic and summation orders as the scalar CPU code, different schedule:
+//   * no block-level barriers: 8 keypoints in flight per CTA, up to 32 per SM, so the order-preserving serial
+//     sections of one keypoint overlap with other keypoints;
+//   * the 20s window is never materialised: its rows are sampled ONCE each, in order (the start_x += sin / start_y += cos
+//     chain advances exactly like the CPU loop), into a per-warp row buffer, and folded straight into the INTER_AREA
+//     accumulators of the 21 patch columns (lane dx owns column dx);
+//   * descriptor bins: lane = (cell, half) accumulates its 4 bins with predicated adds in raster order.
+struct __align__(16) WarpScratch {
+    float buf[800];              // orientation: X[0..127] Y[128..255] A[256..383] (int) ; descriptor: DX[0..399] DY[400..799]
+    float vec[128];
+    uint8_t row[WK_MAX_WIN];     // one sampled window row
+    uint8_t patch[448];
+};
+
+template <bool TEX>
+__global__ void __launch_bounds__(WK_WARPS * 32, 3) orient_describe_warp_kernel(
+    const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
+    const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
+    int batch, int kp_cap, int extended, int upright, const cudaTextureObject_t *__restrict__ texs, int *work_counter)
+{
+    __shared__ WarpScratch s_ws[WK_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpScratch &S = s_ws[warp];
+    const int total = prefix[batch];
+    const int W = cols + 1, srows = rows + 1, scols = cols + 1;
+    const int dsize = extended ? 128 : 64;
+    const unsigned lt_mask = (1u << lane) - 1;
+    constexpr int PD = PATCH_SZ + 1;
+
+    while (true) {
+        // dynamic work distribution: window sizes have a heavy tail, a static split leaves warps idle behind giants
+        int item = 0;
+        if (lane == 0) item = atomicAdd(work_counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total) break;
+        int lo = 0, hi = batch;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(prefix + mid) <= item) lo = mid; else hi = mid; }
+        const int b = lo, k = item - __ldg(prefix + lo);
+        float *kp = kp_all + ((size_t)b * kp_cap + k) * KP_STRIDE;
+        const float size = kp[KP_SIZE], cx = kp[KP_X], cy = kp[KP_Y];
+        const float s = size * 1.2f / 9.0f;
+        const int win = (int)((PATCH_SZ + 1) * s);
+        if (win > WK_MAX_WIN) continue;                       // warp-uniform: the CTA kernel takes it
+        const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
+        const int32_t *I = integral + (size_t)b * srows * W;
+        const int gws = 2 * __float2int_rn(2 * s);
+        cudaTextureObject_t tex = 0;
+        if (TEX) tex = texs[b];
+
+        float descriptor_dir = 360.f - 90.f;
+        if (!upright) {
+            float *sX = S.buf, *sY = S.buf + 128; int *sA = (int *)(S.buf + 256);
+            const int h2 = __float2int_rn(((float)gws / 4) * 2);
+            const int h4 = __float2int_rn(((float)gws / 4) * 4);
+            const float wgt = 1.f / ((float)(h2) * (float)(h4));
+            const float half = (float)(gws - 1) / 2;
+            int nangle = 0;
+#pragma unroll 1
+            for (int r = 0; r < 4; r++) {
+                const int kk = r * 32 + lane;
+                bool have = false; float vX = 0, vY = 0;
+                if (kk < ORI_SAMPLES) {
+                    const int x = __float2int_rn(cx + c_apt_x[kk] * s - half);
+                    const int y = __float2int_rn(cy + c_apt_y[kk] * s - half);
+                    if (!(y < 0 || y >= srows - gws || x < 0 || x >= scols - gws)) {
+                        const int32_t *o = I + (size_t)y * W + x;
+                        // 3x3 grid of integral corners shared by the four half boxes
+                        const int a00 = __ldg(o), a01 = __ldg(o + h2), a02 = __ldg(o + h4);
+                        const int32_t *o1 = o + (size_t)h2 * W, *o2 = o + (size_t)h4 * W;
+                        const int a10 = __ldg(o1), a12 = __ldg(o1 + h4);
+                        const int a20 = __ldg(o2), a21 = __ldg(o2 + h2), a22 = __ldg(o2 + h4);
+                        const int bl = a00 + a21 - a20 - a01;          // x in [0,h2), y in [0,h4)
+                        const int br = a01 + a22 - a21 - a02;          // x in [h2,h4)
+                        const int bt = a00 + a12 - a10 - a02;          // y in [0,h2)
+                        const int bb = a10 + a22 - a20 - a12;          // y in [h2,h4)
+                        double d = 0; d += (double)((float)bl * (-wgt)); d += (double)((float)br * wgt);
+                        const float vx = (float)d;
+                        d = 0; d += (double)((float)bt * wgt); d += (double)((float)bb * (-wgt));
+                        const float vy = (float)d;
+                        vX = vx * c_aptw[kk]; vY = vy * c_aptw[kk];
+                        have = true;
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, have);
+                if (have) {
+                    const int pos = nangle + __popc(bal & lt_mask);
+                    sX[pos] = vX; sY[pos] = vY; sA[pos] = __float2int_rn(fast_atan2_deg(vY, vX));
+                }
+                nangle += __popc(bal);
+            }
+            __syncwarp();
+            float bmod = 0, bx = 0, by = 0; int bw = 1 << 30;
+#pragma unroll 1
+            for (int w = lane; w < 72; w += 32) {
+                const int i = w * 5;
+                float sumx = 0, sumy = 0;
+                for (int j = 0; j < nangle; j++) {
+                    const int d = abs(sA[j] - i);
+                    if (d < ORI_WIN / 2 || d > 360 - ORI_WIN / 2) { sumx += sX[j]; sumy += sY[j]; }
+                }
+                const float m = sumx * sumx + sumy * sumy;
+                if (m > bmod) { bmod = m; bx = sumx; by = sumy; bw = w; }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const float om = __shfl_xor_sync(0xffffffffu, bmod, o), ox = __shfl_xor_sync(0xffffffffu, bx, o),
+                            oy = __shfl_xor_sync(0xffffffffu, by, o);
+                const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
+                if (om > bmod || (om == bmod && ow < bw)) { bmod = om; bx = ox; by = oy; bw = ow; }
+            }
+            descriptor_dir = fast_atan2_deg(-by, bx);
+            __syncwarp();
+        }
+        if (lane == 0) kp[KP_ANGLE] = descriptor_dir;
+
+        // ---- window rows -> INTER_AREA patch
+        const int ncols1 = cols - 1, nrows1 = rows - 1;
+        float sin_dir = 0, cos_dir = 0, chain_x = 0, chain_y = 0;     // chain_*: start_x / start_y of row `cur_row + 1`
+        int ustart_x = 0, ustart_y = 0;
+        if (!upright) {
+            const float dir_rad = descriptor_dir * (float)(M_PI / 180);
+            sin_dir = -(float)sin((double)dir_rad);
+            cos_dir = (float)cos((double)dir_rad);
+            const float win_offset = -(float)(win - 1) / 2;
+            chain_x = cx + win_offset * cos_dir + win_offset * sin_dir;
+            chain_y = cy - win_offset * sin_dir + win_offset * cos_dir;
+        } else {
+            const float win_offset = -(float)(win - 1) / 2;
+            ustart_x = __float2int_rn(cx + win_offset);
+            ustart_y = __float2int_rn(cy - win_offset);
+        }
+        int cur_row = -1;                 // row currently held in S.row
+        // sample window row `r` (>= cur_row) into S.row; rows are requested in nondecreasing order
+        auto fetch_row = [&](int r) {
+            if (r == cur_row) return;
+            __syncwarp();
+            if (!upright) {
+                while (cur_row < r - 1) { chain_x += sin_dir; chain_y += cos_dir; cur_row++; }   // skipped rows still advance the chain
+                const double rx = (double)chain_x, ry = (double)chain_y;
+#pragma unroll 2
+                for (int j = lane; j < win; j += 32) {
+                    const double px = rx + (double)j * (double)cos_dir;
+                    const double py = ry - (double)j * (double)sin_dir;
+                    S.row[j] = (uint8_t)(TEX ? window_pixel_tex(tex, img, stride, ncols1, nrows1, px, py)
+                                             : window_pixel(img, stride, ncols1, nrows1, px, py));
+                }
+                chain_x += sin_dir; chain_y += cos_dir;
+            } else {
+                const int x = min(max(ustart_x + r, 0), cols - 1);
+                for (int j = lane; j < win; j += 32) {
+                    const int y = min(max(ustart_y - j, 0), rows - 1);
+                    S.row[j] = img[(size_t)y * stride + x];
+                }
+            }
+            cur_row = r;
+            __syncwarp();
+        };
+
+        const double inv_scale = (double)PD / win;
+        const double scale = 1. / inv_scale;
+        const int iscale = __double2int_rn(scale);
+        const bool area_fast = fabs(scale - iscale) < DBL_EPSILON;
+        const int dx = lane < PD ? lane : PD - 1;           // lanes >= 21 shadow column 20 (results discarded)
+        if (win == PD) {
+            for (int dy = 0; dy < PD; dy++) { fetch_row(dy); if (lane < PD) S.patch[dy * PD + lane] = S.row[lane]; }
+        } else if (area_fast) {
+            const float fs = 1.f / (float)(iscale * iscale);
+            for (int dy = 0; dy < PD; dy++) {
+                int sum = 0;
+                for (int yy = 0; yy < iscale; yy++) {
+                    fetch_row(dy * iscale + yy);
+                    for (int xx = 0; xx < iscale; xx++) sum += S.row[dx * iscale + xx];
+                }
+                int out;
+                if (iscale == 2) out = (sum + 2) >> 2;
+                else out = min(max(__float2int_rn(sum * fs), 0), 255);
+                if (lane < PD) S.patch[dy * PD + lane] = (uint8_t)out;
+            }
+        } else {
+            // column taps of this lane (decimation table entries of output column dx, in table order)
+            const double fsx1 = dx * scale, fsx2 = fsx1 + scale, cwx = fmin(scale, win - fsx1);
+            int sx1 = __double2int_ru(fsx1), sx2 = __double2int_rd(fsx2);
+            sx2 = min(sx2, win - 1); sx1 = min(sx1, sx2);
+            const bool xl = (sx1 - fsx1 > 1e-3), xr = (fsx2 - sx2 > 1e-3);
+            const float axl = (float)((sx1 - fsx1) / cwx), axm = (float)(1.0 / cwx),
+                        axr = (float)(fmin(fmin(fsx2 - sx2, 1.), cwx) / cwx);
+            for (int dy = 0; dy < PD; dy++) {
+                const double fsy1 = dy * scale, fsy2 = fsy1 + scale, cwy = fmin(scale, win - fsy1);
+                int sy1 = __double2int_ru(fsy1), sy2 = __double2int_rd(fsy2);
+                sy2 = min(sy2, win - 1); sy1 = min(sy1, sy2);
+                const bool yl = (sy1 - fsy1 > 1e-3), yr = (fsy2 - sy2 > 1e-3);
+                const float ayl = (float)((sy1 - fsy1) / cwy), aym = (float)(1.0 / cwy),
+                            ayr = (float)(fmin(fmin(fsy2 - sy2, 1.), cwy) / cwy);
+                const int ya = yl ? sy1 - 1 : sy1, yb = yr ? sy2 : sy2 - 1;
+                float sum = 0; bool first = true;
+                for (int sy = ya; sy <= yb; sy++) {
+                    fetch_row(sy);
+                    const float beta = (yl && sy == sy1 - 1) ? ayl : ((yr && sy == sy2) ? ayr : aym);
+                    float bufv = 0;
+                    if (xl) bufv += (float)S.row[sx1 - 1] * axl;
+                    for (int sx = sx1; sx < sx2; sx++) bufv += (float)S.row[sx] * axm;
+                    if (xr) bufv += (float)S.row[sx2] * axr;
+                    if (first) { sum = beta * bufv; first = false; } else sum += beta * bufv;
+                }
+                if (lane < PD) S.patch[dy * PD + lane] = (uint8_t)min(max(__float2int_rn(sum), 0), 255);
+            }
+        }
+        __syncwarp();
+
+        float *sDX = S.buf, *sDY = S.buf + 400;
+        for (int p = lane; p < PATCH_SZ * PATCH_SZ; p += 32) {
+            const int i = p / PATCH_SZ, j = p - i * PATCH_SZ;
+            const float dw = c_DW[p];
+            const int p00 = S.patch[i * PD + j], p01 = S.patch[i * PD + j + 1];
+            const int p10 = S.patch[(i + 1) * PD + j], p11 = S.patch[(i + 1) * PD + j + 1];
+            sDX[p] = (float)(p01 - p00 + p11 - p10) * dw;
+            sDY[p] = (float)(p10 - p00 + p11 - p01) * dw;
+        }
+        __syncwarp();
+
+        {   // lane = (cell, half): 4 running sums each, raster order inside the 5x5 cell
+            const int cell = lane >> 1, half = lane & 1;
+            const int ci = cell >> 2, cj = cell & 3;
+            float v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+            for (int y = ci * 5; y < ci * 5 + 5; y++)
+#pragma unroll
+                for (int x5 = 0; x5 < 5; x5++) {
+                    const int x = cj * 5 + x5;
+                    const float tx = sDX[y * PATCH_SZ + x], ty = sDY[y * PATCH_SZ + x];
+                    if (extended) {
+                        // half 0: tx sums split by sign(ty); half 1: ty sums split by sign(tx)
+                        const float u = half ? ty : tx, g = half ? tx : ty;
+                        if (g >= 0) { v0 += u; v1 += fabsf(u); } else { v2 += u; v3 += fabsf(u); }
+                    } else {
+                        // 64-d: (sum tx, sum ty, sum |tx|, sum |ty|); half 0 -> (v0, v2) from tx, half 1 -> from ty
+                        const float u = half ? ty : tx;
+                        v0 += u; v1 += fabsf(u);
+                    }
+                }
+            if (extended) {
+                float *d = S.vec + cell * 8 + half * 4;
+                d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v3;
+            } else {
+                float *d = S.vec + cell * 4;
+                d[half] = v0; d[2 + half] = v1;
+            }
+        }
+        __syncwarp();
+        // sum of squares: float products accumulated in double (order differences are far below float resolution)
+        double sq = 0;
+        for (int t = lane; t < dsize; t += 32) sq += (double)(S.vec[t] * S.vec[t]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float nscale = (float)(1. / (sqrt(sq) + (double)FLT_EPSILON));
+        float *dst = desc_all + ((size_t)b * kp_cap + k) * dsize;
+        for (int t = lane; t < dsize; t += 32) dst[t] = S.vec[t] * nscale;
+        __syncwarp();
+    }
+}
 
 __global__ void __launch_bounds__(DESC_THREADS) orient_describe_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
@@ -589,6 +872,7 @@ __global__ void __launch_bounds__(DESC_THREADS) orient_describe_kernel(
         const float size = kp[KP_SIZE], cx = kp[KP_X], cy = kp[KP_Y];
         const float s = size * 1.2f / 9.0f;
         const int gws = 2 * __float2int_rn(2 * s);
+        if ((int)((PATCH_SZ + 1) * s) <= WK_MAX_WIN) continue;   // small windows: orient_describe_warp_kernel (CTA-uniform)
 
         float descriptor_dir = 360.f - 90.f;
         if (!upright) {
@@ -787,6 +1071,67 @@ __global__ void __launch_bounds__(DESC_THREADS) orient_describe_kernel(
     }
 }
 
+// ---------------------------------------------------------------- host: texture objects over the caller's images
+// One pitch-2D u8 texture per image (point sampled, used only through tex2Dgather).  Cached by (ptr, shape, pitch).
+struct TexKey { const void *p; int rows, cols, stride; bool operator<(const TexKey &o) const {
+    return std::tie(p, rows, cols, stride) < std::tie(o.p, o.rows, o.cols, o.stride); } };
+struct TexCache { std::map<TexKey, cudaTextureObject_t> m; int align = 512, pitch_align = 32; bool init = false; };
+
+void surf_tex_destroy(vfsms_ctx *ctx)
+{
+    TexCache *tc = (TexCache *)ctx->tex_cache;
+    if (!tc) return;
+    for (auto &kv : tc->m) cudaDestroyTextureObject(kv.second);
+    delete tc;
+    ctx->tex_cache = nullptr;
+}
+
+// returns false when some image cannot be bound (alignment): caller uses the LDG sampler
+static bool surf_textures(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b, int split, int batch, int rows, int cols,
+                          int stride, int64_t img_stride, cudaStream_t st, cudaTextureObject_t **dev_out)
+{
+    if (!ctx->tex_cache) ctx->tex_cache = new TexCache();
+    TexCache *tc = (TexCache *)ctx->tex_cache;
+    if (!tc->init) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) { tc->align = (int)prop.textureAlignment; tc->pitch_align = (int)prop.texturePitchAlignment; }
+        tc->init = true;
+    }
+    if (stride % tc->pitch_align) return false;
+    if (tc->m.size() > 8192) {           // bound the cache: drop everything once idle
+        cudaStreamSynchronize(st);
+        for (auto &kv : tc->m) cudaDestroyTextureObject(kv.second);
+        tc->m.clear();
+    }
+    std::vector<cudaTextureObject_t> h((size_t)batch);
+    for (int b = 0; b < batch; b++) {
+        const uint8_t *p = b < split ? base_a + (int64_t)b * img_stride : base_b + (int64_t)(b - split) * img_stride;
+        if (((uintptr_t)p) % tc->align) return false;
+        TexKey key{p, rows, cols, stride};
+        auto it = tc->m.find(key);
+        if (it == tc->m.end()) {
+            cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+            rd.resType = cudaResourceTypePitch2D;
+            rd.res.pitch2D.devPtr = (void *)p;
+            rd.res.pitch2D.desc = cudaCreateChannelDesc<unsigned char>();
+            rd.res.pitch2D.width = cols; rd.res.pitch2D.height = rows; rd.res.pitch2D.pitchInBytes = stride;
+            cudaTextureDesc td; memset(&td, 0, sizeof(td));
+            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+            cudaTextureObject_t t = 0;
+            if (cudaCreateTextureObject(&t, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); return false; }
+            it = tc->m.emplace(key, t).first;
+        }
+        h[b] = it->second;
+    }
+    if (ctx->tex_dev.reserve((size_t)batch * sizeof(cudaTextureObject_t))) return false;
+    if (cudaMemcpyAsync(ctx->tex_dev.p, h.data(), (size_t)batch * sizeof(cudaTextureObject_t), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        cudaGetLastError(); return false;
+    }
+    *dev_out = ctx->tex_dev.as<cudaTextureObject_t>();
+    return true;
+}
+
 // ---------------------------------------------------------------- host driver
 int surf_reserve(vfsms_ctx *ctx, int batch, int rows, int cols, const vfsms_surf_params *p)
 {
@@ -819,7 +1164,7 @@ int surf_reserve(vfsms_ctx *ctx, int batch, int rows, int cols, const vfsms_surf
     if ((rc = ws.sorted.reserve((size_t)batch * cand_cap * KP_STRIDE * 4))) return rc;
     if ((rc = ws.kp.reserve((size_t)batch * kp_cap * KP_STRIDE * 4))) return rc;
     if ((rc = ws.desc.reserve((size_t)batch * kp_cap * dim * 4))) return rc;
-    if ((rc = ws.counters.reserve((size_t)batch * 16))) return rc;
+    if ((rc = ws.counters.reserve((size_t)batch * 16 + 16))) return rc;
     if ((rc = ws.prefix.reserve((size_t)(batch + 1) * 4))) return rc;
     if ((rc = ws.descT.reserve((size_t)batch * kp_cap * dim * 4))) return rc;
     ws.max_features = max_features;
@@ -864,7 +1209,7 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         CUDA_TRY(cudaFuncSetAttribute(integral_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_done = true;
     }
-    CUDA_TRY(cudaMemsetAsync(ws.counters.p, 0, (size_t)batch * 16, st));
+    CUDA_TRY(cudaMemsetAsync(ws.counters.p, 0, (size_t)batch * 16 + 16, st));
     {
     StageTimer t_int(ctx, st, VFSMS_STAGE_INTEGRAL);
     integral_band_kernel<<<dim3(n_bands, batch), 256, smem_int, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
@@ -902,7 +1247,19 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
     LAUNCH_CHECK(ctx);
     }
     StageTimer t_d(ctx, st, VFSMS_STAGE_DESCRIBE);
-    orient_describe_kernel<<<ctx->num_sms * 6, DESC_THREADS, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
+    cudaTextureObject_t *texs = nullptr;
+    const bool use_tex = surf_textures(ctx, base_a, base_b, split, batch, rows, cols, stride, img_stride, st, &texs);
+    int *work_counter = ws.counters.as<int32_t>() + (size_t)batch * 4;      // one extra slot after the per-image counters
+    if (use_tex)
+        orient_describe_warp_kernel<true><<<ctx->num_sms * 3, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
+            ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap,
+            p->extended, p->upright, texs, work_counter);
+    else
+        orient_describe_warp_kernel<false><<<ctx->num_sms * 3, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
+            ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap,
+            p->extended, p->upright, nullptr, work_counter);
+    LAUNCH_CHECK(ctx);
+    orient_describe_kernel<<<ctx->num_sms * 2, DESC_THREADS, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
                                                                        ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(),
                                                                        ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, p->upright);
     LAUNCH_CHECK(ctx);

@@ -13,7 +13,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", "/u
 UNITS = {
     "surf.cu": ["-fmad=false"],
     "match.cu": ["-fmad=false"],
-    "match_tc.cu": [],
+    "match_tc.cu": ["-fmad=false"],
     "phase.cu": ["-fmad=false"],
     "blend.cu": ["-fmad=false"],
     "orb.cu": ["-fmad=false"],

@@ -51,6 +51,23 @@ int vfsms_profile_read(vfsms_ctx *ctx, float *ms_out, int32_t *calls_out, int re
     return 0;
 }
 
+int vfsms_set_matcher(vfsms_ctx *ctx, int mode)
+{
+    if (!ctx || mode < 0 || mode > 1) { vfsms_set_error("vfsms_set_matcher: bad arguments"); return VFSMS_E_ARG; }
+    ctx->matcher_mode = mode;
+    return 0;
+}
+int vfsms_last_match_fallbacks(vfsms_ctx *ctx, int *count_out)
+{
+    if (!ctx || !count_out) return VFSMS_E_ARG;
+    *count_out = 0;
+    if (!ctx->last_fallback_count_dev) return 0;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(count_out, ctx->last_fallback_count_dev, 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int vfsms_version(void) { return VFSMS_VERSION; }
 const char *vfsms_last_error(void) { return g_err; }
 
@@ -157,7 +174,7 @@ int vfsms_match_descriptors(vfsms_ctx *ctx, const float *desc_a, int n_a, const 
     if (n_a == 0 || n_b == 0) return 0;
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const int cap = (((n_a > n_b ? n_a : n_b) + 63) / 64) * 64;
+    const int cap = (((n_a > n_b ? n_a : n_b) + 127) / 128) * 128;
     int rc;
     if ((rc = ctx->scratch0.reserve((size_t)cap * dim * 4))) return rc;   // A row-major
     if ((rc = ctx->scratch1.reserve((size_t)cap * dim * 4))) return rc;   // B row-major
@@ -173,6 +190,9 @@ int vfsms_match_descriptors(vfsms_ctx *ctx, const float *desc_a, int n_a, const 
     if (feature_type == 3) {
         if ((rc = match_hamming_batch(ctx, ctx->scratch0.as<float>(), cn, 0, ctx->scratch1.as<float>(), cn + 1, 0, 1, cap, dim, 0, 0,
                                       mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(), st))) return rc;
+    } else if (ctx->matcher_mode == 0 && dim % 32 == 0 && dim <= 128) {
+        if ((rc = match_tc_batch(ctx, ctx->scratch0.as<float>(), cn, 0, ctx->scratch1.as<float>(), cn + 1, 0, 1, cap, dim,
+                                 mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(), st))) return rc;
     } else {
         float *AT = ctx->scratch2.as<float>(), *BT = AT + (size_t)cap * dim;
         CUDA_TRY(cudaMemsetAsync(AT, 0, (size_t)cap * dim * 4 * 2, st));
@@ -231,15 +251,20 @@ static int align_batch_launch(vfsms_ctx *ctx, const uint8_t *a_dev, const uint8_
     const int cap = ws.kp_cap, dim = ws.dim;
     const int32_t *nfin = ws.counters.as<int32_t>() + 2;     // n_final of image b at [b*4]
     const int32_t *flags = ws.counters.as<int32_t>() + 3;
-    {
-        StageTimer t(ctx, st, VFSMS_STAGE_TRANSPOSE);
-        CUDA_TRY(cudaMemsetAsync(ws.descT.p, 0, (size_t)2 * n_pairs * cap * dim * 4, st));
-        if ((rc = transpose_desc_batch(ctx, ws.desc.as<float>(), nfin, 4, ws.descT.as<float>(), 2 * n_pairs, cap, dim,
-                                       (int64_t)cap * dim, (int64_t)cap * dim, st))) return rc;
-    }
     MatchWorkspace &mw = ctx->match;
-    const float *AT = ws.descT.as<float>(), *BT = AT + (size_t)n_pairs * cap * dim;
-    {
+    const bool use_tc = ctx->matcher_mode == 0 && cap % 128 == 0 && dim % 32 == 0 && dim <= 128;
+    if (use_tc) {
+        const float *DA = ws.desc.as<float>(), *DB = DA + (size_t)n_pairs * cap * dim;
+        if ((rc = match_tc_batch(ctx, DA, nfin, 4, DB, nfin + 4 * n_pairs, 4, n_pairs, cap, dim, mw.best_idx.as<int32_t>(),
+                                 mw.best_dist.as<float>(), st))) return rc;
+    } else {
+        {
+            StageTimer t(ctx, st, VFSMS_STAGE_TRANSPOSE);
+            CUDA_TRY(cudaMemsetAsync(ws.descT.p, 0, (size_t)2 * n_pairs * cap * dim * 4, st));
+            if ((rc = transpose_desc_batch(ctx, ws.desc.as<float>(), nfin, 4, ws.descT.as<float>(), 2 * n_pairs, cap, dim,
+                                           (int64_t)cap * dim, (int64_t)cap * dim, st))) return rc;
+        }
+        const float *AT = ws.descT.as<float>(), *BT = AT + (size_t)n_pairs * cap * dim;
         StageTimer t(ctx, st, VFSMS_STAGE_MATCH);
         if ((rc = match_l2_knn2_batch(ctx, AT, nfin, 4, BT, nfin + 4 * n_pairs, 4, n_pairs, cap, dim, (int64_t)cap * dim, (int64_t)cap * dim,
                                       mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(), st))) return rc;

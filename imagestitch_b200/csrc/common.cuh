@@ -132,6 +132,8 @@ struct vfsms_ctx {
     float prof_ms[VFSMS_STAGE_COUNT] = {0};
     int32_t prof_calls[VFSMS_STAGE_COUNT] = {0};
     int device = 0;
+    int matcher_mode = 0;          // 0: tcgen05 candidates + exact rescoring, 1: exact SIMT kernel
+    int32_t *last_fallback_count_dev = nullptr;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
     int num_sms = VFSMS_NUM_SMS;
@@ -171,6 +173,8 @@ int surf_init_tables();
 void surf_tex_destroy(vfsms_ctx *ctx);
 
 int match_reserve(vfsms_ctx *ctx, int n_pairs, int cap);
+int match_tc_batch(vfsms_ctx *ctx, const float *desc_a, const int32_t *n_a, int n_a_stride, const float *desc_b, const int32_t *n_b,
+                   int n_b_stride, int n_pairs, int cap, int dim, int32_t *best_idx, float *best_dist, cudaStream_t st);
 int transpose_desc_batch(vfsms_ctx *ctx, const float *src, const int32_t *n_ptr, int n_stride, float *dst, int n_pairs, int cap,
                          int dim, int64_t src_pair_stride, int64_t dst_pair_stride, cudaStream_t st);
 int match_l2_knn2_batch(vfsms_ctx *ctx, const float *descT_a, const int32_t *n_a, int n_a_stride,

@@ -1,0 +1,521 @@
+// match_tc.cu -- tensor-core brute-force matcher (tcgen05 / TMEM / TMA), exact results.  sm_100a only.
+//
+// Replaces the O(nA*nB*D) part of Method.matchDescriptors (ImageUtility.py:278-309, BF L2 kNN(2)).
+//
+//   1. prep_split_kernel      fp32 descriptors -> bf16 rows of K' = 3D + 64 columns:
+//                               query  row: [ a_hi | a_hi | a_lo | 1, 1, 0 ... ]
+//                               train  row: [-2b_hi|-2b_lo|-2b_hi| nb_hi, nb_lo, 0 ... ]     (nb = ||b||^2)
+//                             so that  <query row, train row> = ||b||^2 - 2 a.b  up to ~2^-17 relative error
+//                             (3-term split-bf16 product; the hi*hi + hi*lo + lo*hi terms of (a_hi+a_lo).(b_hi+b_lo)).
+//   2. match_tc_kernel        persistent warp-specialised GEMM: TMA (SWIZZLE_128B) -> smem -> tcgen05.mma (M128 N128 K16,
+//                             kind::f16, bf16 in / fp32 accumulate in TMEM, two accumulator buffers) -> epilogue warpgroup
+//                             reads TMEM with tcgen05.ld and keeps a running top-4 (score, train index) per query row.
+//                             The query tile (128 x K') stays resident in shared memory while train tiles stream through a
+//                             4-stage mbarrier ring.  Nothing but the 4 candidates per query is written to HBM.
+//   3. rescore_kernel         exact fp32 distances (serial k order, no FMA: the CPU value) of the candidates, best two by
+//                             (distance, index), plus a guard: if the second best exact score is not separated from the
+//                             worst kept candidate by more than the split-bf16 error bound, the query is flagged ...
+//   4. fallback_exact_kernel  ... and rescanned exactly against every train row.  Results are therefore identical to the
+//                             exact SIMT kernel (match.cu) by construction, not by luck.
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <float.h>
+
+#define TC_M 128
+#define TC_N 128
+#define TC_KB 64                 // bf16 elements per k-block = 128 bytes = one swizzle row
+#define TC_STAGES 4
+#define TC_TOPK 4
+#define TC_MAX_KBLOCKS 7         // K' <= 448  (D <= 128)
+#define TC_THREADS 256           // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: epilogue
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) { }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)     // arrives on `bar` when all prior MMAs of this thread finished
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
+//   start address >> 4 | LBO (ignored for swizzled K-major; 1) | SBO = 8 rows * 128 B = 1024 B | layout type 2 (128B swizzle)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor: D = f32, A = B = bf16, both K-major, N = 128, M = 128
+__device__ __forceinline__ uint32_t make_idesc()
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- 1. split-bf16 operand rows
+// grid (ceil(cap/8), images), 256 threads: one warp per row.  side 0 = query layout, 1 = train layout.
+__global__ void __launch_bounds__(256) prep_split_kernel(const float *__restrict__ desc, const int32_t *n_ptr, int n_stride,
+                                                         int cap, int dim, int kprime, int side, int img0,
+                                                         __nv_bfloat16 *out, float *norms)
+{
+    const int b = blockIdx.y;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= cap) return;
+    const int n = n_ptr[(size_t)(img0 + b) * n_stride];
+    const float *src = desc + ((size_t)(img0 + b) * cap + row) * dim;
+    __nv_bfloat16 *dst = out + ((size_t)b * cap + row) * kprime;
+    const bool valid = row < n;
+    float nrm = 0.f;
+    for (int k = lane; k < dim; k += 32) {
+        const float v = valid ? src[k] : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        nrm += v * v;
+        if (side == 0) { dst[k] = hi; dst[dim + k] = hi; dst[2 * dim + k] = lo; }
+        else {
+            const __nv_bfloat16 mhi = __float2bfloat16_rn(-2.f * __bfloat162float(hi)), mlo = __float2bfloat16_rn(-2.f * __bfloat162float(lo));
+            dst[k] = mhi; dst[dim + k] = mlo; dst[2 * dim + k] = mhi;
+        }
+    }
+    for (int o = 16; o; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    for (int k = 3 * dim + lane; k < kprime; k += 32) {
+        float v = 0.f;
+        const int e = k - 3 * dim;
+        if (side == 0) v = (e < 2) ? 1.f : 0.f;
+        else {
+            const float nb = valid ? nrm : 1e30f;       // padding train rows can never be selected
+            const float hi = __bfloat162float(__float2bfloat16_rn(nb));
+            v = e == 0 ? hi : (e == 1 ? (valid ? nb - hi : 0.f) : 0.f);
+        }
+        dst[k] = __float2bfloat16_rn(v);
+    }
+    if (lane == 0) norms[(size_t)b * cap + row] = valid ? nrm : 0.f;
+}
+
+// ---------------------------------------------------------------- 2. the GEMM + running top-K
+struct TcShared {
+    uint64_t a_full, a_empty;
+    uint64_t b_full[TC_STAGES], b_empty[TC_STAGES];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void topk_insert(float s, int idx, float (&ts)[TC_TOPK], int (&ti)[TC_TOPK])
+{
+    // ts ascending; strict '<' keeps the earlier (lower) train index on ties
+    if (s < ts[1]) {
+        if (s < ts[0]) { ts[3] = ts[2]; ti[3] = ti[2]; ts[2] = ts[1]; ti[2] = ti[1]; ts[1] = ts[0]; ti[1] = ti[0]; ts[0] = s; ti[0] = idx; }
+        else { ts[3] = ts[2]; ti[3] = ti[2]; ts[2] = ts[1]; ti[2] = ti[1]; ts[1] = s; ti[1] = idx; }
+    } else {
+        if (s < ts[2]) { ts[3] = ts[2]; ti[3] = ti[2]; ts[2] = s; ti[2] = idx; }
+        else { ts[3] = s; ti[3] = idx; }
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                 const __grid_constant__ CUtensorMap tmap_b,
+                                                                 const int32_t *__restrict__ n_a_ptr, int n_a_stride,
+                                                                 const int32_t *__restrict__ n_b_ptr, int n_b_stride,
+                                                                 int n_pairs, int cap, int kblocks, int n_splits,
+                                                                 float *cand_score, int32_t *cand_idx)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // SWIZZLE_128B needs 1024-B alignment
+    uint8_t *sA = smem;                                                 // kblocks x [128 rows x 128 B]
+    uint8_t *sB = smem + (size_t)TC_MAX_KBLOCKS * TC_M * 128;           // TC_STAGES x [128 rows x 128 B]
+    TcShared *sh = (TcShared *)(sB + (size_t)TC_STAGES * TC_N * 128);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = cap / TC_M;
+    const int items = n_pairs * m_tiles * n_splits;
+
+    if (warp == 1 && lane == 0) {
+        mbar_init(&sh->a_full, 1); mbar_init(&sh->a_empty, 1);
+        for (int i = 0; i < TC_STAGES; i++) { mbar_init(&sh->b_full[i], 1); mbar_init(&sh->b_empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&sh->acc_full[i], 1); mbar_init(&sh->acc_empty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(&sh->tmem_base, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    // per-item geometry shared by all roles
+    auto item_geom = [&](int item, int &p, int &mt, int &nt0, int &nt1) -> bool {
+        const int s = item % n_splits;
+        const int r = item / n_splits;
+        mt = r % m_tiles; p = r / m_tiles;
+        const int nA = n_a_ptr[(size_t)p * n_a_stride], nB = n_b_ptr[(size_t)p * n_b_stride];
+        if (mt * TC_M >= nA) return false;
+        const int n_tiles = (nB + TC_N - 1) / TC_N;
+        const int per = (n_tiles + n_splits - 1) / n_splits;
+        nt0 = s * per; nt1 = min(n_tiles, nt0 + per);
+        return true;                       // nt0 >= nt1 is allowed: the epilogue still writes an empty candidate list
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, sphase = 0, a_phase = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                int p, mt, nt0, nt1;
+                if (!item_geom(item, p, mt, nt0, nt1) || nt0 >= nt1) continue;
+                mbar_wait(&sh->a_empty, a_phase ^ 1); a_phase ^= 1;
+                mbar_expect_tx(&sh->a_full, (uint32_t)kblocks * TC_M * 128);
+                for (int kb = 0; kb < kblocks; kb++)
+                    tma_load_2d(sA + (size_t)kb * TC_M * 128, &tmap_a, &sh->a_full, kb * TC_KB, p * cap + mt * TC_M);
+                for (int nt = nt0; nt < nt1; nt++)
+                    for (int kb = 0; kb < kblocks; kb++) {
+                        mbar_wait(&sh->b_empty[stage], sphase ^ 1);
+                        mbar_expect_tx(&sh->b_full[stage], TC_N * 128);
+                        tma_load_2d(sB + (size_t)stage * TC_N * 128, &tmap_b, &sh->b_full[stage], kb * TC_KB, p * cap + nt * TC_N);
+                        if (++stage == TC_STAGES) { stage = 0; sphase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc();
+            uint32_t stage = 0, sphase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                int p, mt, nt0, nt1;
+                if (!item_geom(item, p, mt, nt0, nt1) || nt0 >= nt1) continue;
+                mbar_wait(&sh->a_full, a_phase); a_phase ^= 1;
+                tc_fence_after();
+                for (int nt = nt0; nt < nt1; nt++) {
+                    mbar_wait(&sh->acc_empty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * TC_N;
+                    for (int kb = 0; kb < kblocks; kb++) {
+                        mbar_wait(&sh->b_full[stage], sphase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(sA + (size_t)kb * TC_M * 128);
+                        const uint32_t b_addr = smem_u32(sB + (size_t)stage * TC_N * 128);
+#pragma unroll
+                        for (int k = 0; k < TC_KB / 16; k++)
+                            umma_bf16(d_tmem, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
+                        umma_commit(&sh->b_empty[stage]);            // frees the smem stage when these MMAs are done
+                        if (++stage == TC_STAGES) { stage = 0; sphase ^= 1; }
+                    }
+                    umma_commit(&sh->acc_full[acc]);                 // accumulator ready for the epilogue
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+                umma_commit(&sh->a_empty);                           // query tile may be overwritten
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue warpgroup: TMEM -> registers -> running top-K =====================
+        const int q4 = warp & 3;                                     // TMEM lane quarter this warp may access
+        const int row = q4 * 32 + lane;
+        uint32_t acc = 0, acc_phase = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            int p, mt, nt0, nt1;
+            if (!item_geom(item, p, mt, nt0, nt1)) continue;
+            float ts[TC_TOPK]; int ti[TC_TOPK];
+#pragma unroll
+            for (int i = 0; i < TC_TOPK; i++) { ts[i] = FLT_MAX; ti[i] = -1; }
+            for (int nt = nt0; nt < nt1; nt++) {
+                mbar_wait(&sh->acc_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * TC_N;
+#pragma unroll 1
+                for (int c = 0; c < TC_N / 32; c++) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    const int col0 = nt * TC_N + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float s = __uint_as_float(v[j]);
+                        if (s < ts[TC_TOPK - 1]) topk_insert(s, col0 + j, ts, ti);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh->acc_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            const int q = mt * TC_M + row;
+            const int s_id = item % n_splits;
+            const size_t o = (((size_t)p * cap + q) * n_splits + s_id) * TC_TOPK;
+#pragma unroll
+            for (int i = 0; i < TC_TOPK; i++) { cand_score[o + i] = ts[i]; cand_idx[o + i] = ti[i]; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+// ---------------------------------------------------------------- 3. exact rescoring + guard
+// one warp per query.  desc_*: fp32 row-major [img][cap][dim] (the original descriptors).
+__global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ desc_a, const float *__restrict__ desc_b,
+                                                      int64_t pair_stride_a, int64_t pair_stride_b,
+                                                      const int32_t *__restrict__ n_a_ptr, int n_a_stride,
+                                                      const int32_t *__restrict__ n_b_ptr, int n_b_stride,
+                                                      const float *__restrict__ norm_a, const float *__restrict__ norm_b_max,
+                                                      const float *__restrict__ cand_score, const int32_t *__restrict__ cand_idx,
+                                                      int cap, int dim, int n_splits, int32_t *best_idx, float *best_dist,
+                                                      int32_t *fallback_list, int32_t *fallback_count)
+{
+    const int p = blockIdx.y;
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int nA = n_a_ptr[(size_t)p * n_a_stride], nB = n_b_ptr[(size_t)p * n_b_stride];
+    if (q >= nA) return;
+    const float *a = desc_a + p * pair_stride_a + (size_t)q * dim;
+    const float *B = desc_b + p * pair_stride_b;
+    const int nc = n_splits * TC_TOPK;                 // <= 32 candidates: one per lane
+    float d = FLT_MAX; int t = -1; float approx = FLT_MAX;
+    if (lane < nc) {
+        const size_t o = ((size_t)p * cap + q) * nc + lane;
+        t = cand_idx[o]; approx = cand_score[o];
+        if (t >= nB || approx > 1e29f) t = -1;
+        if (t >= 0) {
+            const float *b = B + (size_t)t * dim;
+            float s = 0.f;
+            for (int k = 0; k < dim; k++) { const float df = a[k] - b[k]; s += df * df; }      // -fmad=false: CPU rounding
+            d = s;
+        }
+    }
+    // cmin: the smallest "worst kept" approximate score over splits that filled their list
+    float worst = FLT_MAX;
+    if (lane < nc && (lane % TC_TOPK) == TC_TOPK - 1 && t >= 0) worst = approx;
+    // a split whose list is not full saw every train row of its range: it cannot hide a better one
+    for (int o = 16; o; o >>= 1) worst = fminf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    // best two by (d, t)
+    float d0 = d; int t0 = t;
+    for (int o = 16; o; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, d0, o); const int ot = __shfl_xor_sync(0xffffffffu, t0, o);
+        if (ot >= 0 && (t0 < 0 || od < d0 || (od == d0 && ot < t0))) { d0 = od; t0 = ot; }
+    }
+    float d1 = (t == t0) ? FLT_MAX : d; int t1 = (t == t0) ? -1 : t;
+    for (int o = 16; o; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, d1, o); const int ot = __shfl_xor_sync(0xffffffffu, t1, o);
+        if (ot >= 0 && (t1 < 0 || od < d1 || (od == d1 && ot < t1))) { d1 = od; t1 = ot; }
+    }
+    if (lane == 0) {
+        const float na = norm_a[(size_t)p * cap + q];
+        const float bmax = norm_b_max[p];
+        // |approx score - exact score| <= E  (3-term split-bf16 + fp32 tensor accumulation + fp32 rescoring), generous
+        const float E = 1e-3f * (sqrtf(na) * sqrtf(bmax) + bmax) + 1e-6f;
+        bool ok = true;
+        if (nB >= 2) {
+            if (t1 < 0) ok = false;
+            else if (worst < FLT_MAX && !((d1 - na) < worst - E)) ok = false;
+        } else if (nB == 1 && t0 < 0) ok = false;
+        const size_t o = ((size_t)p * cap + q) * 2;
+        best_idx[o] = t0; best_idx[o + 1] = t1;
+        best_dist[o] = t0 >= 0 ? sqrtf(d0) : FLT_MAX; best_dist[o + 1] = t1 >= 0 ? sqrtf(d1) : FLT_MAX;
+        if (!ok) { const int slot = atomicAdd(fallback_count, 1); fallback_list[slot] = p * cap + q; }
+    }
+}
+
+// per pair: max ||b||^2
+__global__ void norm_max_kernel(const float *__restrict__ norms_b, const int32_t *n_b_ptr, int n_b_stride, int cap, float *out)
+{
+    __shared__ float s[32];
+    const int p = blockIdx.x;
+    const int n = n_b_ptr[(size_t)p * n_b_stride];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, norms_b[(size_t)p * cap + i]);
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, s[w]); out[p] = m; }
+}
+
+// ---------------------------------------------------------------- 4. exact fallback for flagged queries (one warp each)
+__global__ void __launch_bounds__(256) fallback_exact_kernel(const float *__restrict__ desc_a, const float *__restrict__ desc_b,
+                                                             int64_t pair_stride_a, int64_t pair_stride_b,
+                                                             const int32_t *__restrict__ n_b_ptr, int n_b_stride, int cap, int dim,
+                                                             const int32_t *__restrict__ fallback_list, const int32_t *__restrict__ fallback_count,
+                                                             int32_t *best_idx, float *best_dist)
+{
+    const int lane = threadIdx.x & 31;
+    const int total = *fallback_count;
+    for (int w = blockIdx.x * 8 + (threadIdx.x >> 5); w < total; w += gridDim.x * 8) {
+        const int pq = fallback_list[w];
+        const int p = pq / cap, q = pq - p * cap;
+        const int nB = n_b_ptr[(size_t)p * n_b_stride];
+        const float *a = desc_a + p * pair_stride_a + (size_t)q * dim;
+        const float *B = desc_b + p * pair_stride_b;
+        float d0 = FLT_MAX, d1 = FLT_MAX; int t0 = -1, t1 = -1;
+        for (int t = lane; t < nB; t += 32) {
+            const float *b = B + (size_t)t * dim;
+            float s = 0.f;
+            for (int k = 0; k < dim; k++) { const float df = a[k] - b[k]; s += df * df; }
+            if (s < d0) { d1 = d0; t1 = t0; d0 = s; t0 = t; }
+            else if (s < d1) { d1 = s; t1 = t; }
+        }
+        // merge 32 sorted pairs: lexicographic (d, t)
+        for (int o = 16; o; o >>= 1) {
+            const float e0 = __shfl_xor_sync(0xffffffffu, d0, o), e1 = __shfl_xor_sync(0xffffffffu, d1, o);
+            const int u0 = __shfl_xor_sync(0xffffffffu, t0, o), u1 = __shfl_xor_sync(0xffffffffu, t1, o);
+            float c[4] = { d0, d1, e0, e1 }; int ci[4] = { t0, t1, u0, u1 };
+            float b0 = FLT_MAX, b1 = FLT_MAX; int i0 = -1, i1 = -1;
+#pragma unroll
+            for (int z = 0; z < 4; z++) {
+                if (ci[z] < 0) continue;
+                if (i0 < 0 || c[z] < b0 || (c[z] == b0 && ci[z] < i0)) { b1 = b0; i1 = i0; b0 = c[z]; i0 = ci[z]; }
+                else if (i1 < 0 || c[z] < b1 || (c[z] == b1 && ci[z] < i1)) { b1 = c[z]; i1 = ci[z]; }
+            }
+            d0 = b0; t0 = i0; d1 = b1; t1 = i1;
+        }
+        if (lane == 0) {
+            const size_t o = ((size_t)p * cap + q) * 2;
+            best_idx[o] = t0; best_idx[o + 1] = t1;
+            best_dist[o] = t0 >= 0 ? sqrtf(d0) : FLT_MAX; best_dist[o + 1] = t1 >= 0 ? sqrtf(d1) : FLT_MAX;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- host driver
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+        fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+static int make_tmap(CUtensorMap *map, void *base, int kprime, long long rows)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { vfsms_set_error("cuTensorMapEncodeTiled not available"); return VFSMS_E_CUDA; }
+    cuuint64_t dims[2] = { (cuuint64_t)kprime, (cuuint64_t)rows };
+    cuuint64_t strides[1] = { (cuuint64_t)kprime * 2 };
+    cuuint32_t box[2] = { TC_KB, TC_M };
+    cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { vfsms_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return VFSMS_E_CUDA; }
+    return 0;
+}
+
+// desc_a / desc_b: fp32 row-major [pair][cap][dim] (pair stride in floats); counts on device.  Writes best_idx / best_dist
+// in the format of match_l2_knn2_batch.
+int match_tc_batch(vfsms_ctx *ctx, const float *desc_a, const int32_t *n_a, int n_a_stride, const float *desc_b, const int32_t *n_b,
+                   int n_b_stride, int n_pairs, int cap, int dim, int32_t *best_idx, float *best_dist, cudaStream_t st)
+{
+    if (cap % TC_M || dim % 32 || dim > 128) { vfsms_set_error("match_tc: cap %% 128 == 0 and dim in {32,64,96,128} required"); return VFSMS_E_ARG; }
+    MatchWorkspace &mw = ctx->match;
+    const int kprime = 3 * dim + 64, kblocks = kprime / TC_KB;
+    const int m_tiles = cap / TC_M;
+    int n_splits = 1;
+    while (n_pairs * m_tiles * n_splits < 2 * ctx->num_sms && n_splits < 8) n_splits *= 2;
+    int rc;
+    const size_t rows = (size_t)n_pairs * cap;
+    if ((rc = mw.bf16_a.reserve(rows * kprime * 2))) return rc;
+    if ((rc = mw.bf16_b.reserve(rows * kprime * 2))) return rc;
+    // cand buffer: scores | idx | norms_a | norms_b | bmax | fallback_count | fallback_list
+    const size_t n_cand = rows * n_splits * TC_TOPK;
+    const size_t bytes = n_cand * 8 + rows * 8 + (size_t)n_pairs * 4 + 16 + rows * 4;
+    if ((rc = mw.cand_topk.reserve(bytes))) return rc;
+    float *cand_score = mw.cand_topk.as<float>();
+    int32_t *cand_idx = (int32_t *)(cand_score + n_cand);
+    float *norm_a = (float *)(cand_idx + n_cand), *norm_b = norm_a + rows, *bmax = norm_b + rows;
+    int32_t *fb_count = (int32_t *)(bmax + n_pairs), *fb_list = fb_count + 4;
+
+    StageTimer tt(ctx, st, VFSMS_STAGE_MATCH_TC);
+    prep_split_kernel<<<dim3(ceil_div(cap, 8), n_pairs), 256, 0, st>>>(desc_a, n_a, n_a_stride, cap, dim, kprime, 0, 0, mw.bf16_a.as<__nv_bfloat16>(), norm_a);
+    LAUNCH_CHECK(ctx);
+    prep_split_kernel<<<dim3(ceil_div(cap, 8), n_pairs), 256, 0, st>>>(desc_b, n_b, n_b_stride, cap, dim, kprime, 1, 0, mw.bf16_b.as<__nv_bfloat16>(), norm_b);
+    LAUNCH_CHECK(ctx);
+    norm_max_kernel<<<n_pairs, 256, 0, st>>>(norm_b, n_b, n_b_stride, cap, bmax);
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(cudaMemsetAsync(fb_count, 0, 16, st));
+
+    CUtensorMap ta, tb;
+    if ((rc = make_tmap(&ta, mw.bf16_a.p, kprime, (long long)rows))) return rc;
+    if ((rc = make_tmap(&tb, mw.bf16_b.p, kprime, (long long)rows))) return rc;
+    const size_t smem = (size_t)(TC_MAX_KBLOCKS * TC_M + TC_STAGES * TC_N) * 128 + sizeof(TcShared) + 1024;
+    static bool attr = false;
+    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    const int items = n_pairs * m_tiles * n_splits;
+    const int grid = items < ctx->num_sms ? items : ctx->num_sms;
+    match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(ta, tb, n_a, n_a_stride, n_b, n_b_stride, n_pairs, cap, kblocks, n_splits, cand_score, cand_idx);
+    LAUNCH_CHECK(ctx);
+    rescore_kernel<<<dim3(ceil_div(cap, 8), n_pairs), 256, 0, st>>>(desc_a, desc_b, (int64_t)cap * dim, (int64_t)cap * dim, n_a, n_a_stride, n_b, n_b_stride,
+                                                                    norm_a, bmax, cand_score, cand_idx, cap, dim, n_splits, best_idx, best_dist, fb_list, fb_count);
+    LAUNCH_CHECK(ctx);
+    fallback_exact_kernel<<<ctx->num_sms * 2, 256, 0, st>>>(desc_a, desc_b, (int64_t)cap * dim, (int64_t)cap * dim, n_b, n_b_stride, cap, dim,
+                                                            fb_list, fb_count, best_idx, best_dist);
+    LAUNCH_CHECK(ctx);
+    ctx->last_fallback_count_dev = fb_count;
+    return 0;
+}

@@ -154,6 +154,17 @@ def align_strips_dev(tiles_a, tiles_b, results, roi_rows, params=None, ratio=0.7
                                   ctypes.c_void_p(st.cuda_stream)), "vfsms_align_batch_dev")
 
 
+def set_matcher(mode, device=0):
+    """'tc' (default): tcgen05 candidates + exact rescoring; 'simt': exact fp32 SIMT kernel.  Identical results."""
+    check(_lib.load().vfsms_set_matcher(_lib.context(device), {"tc": 0, "simt": 1}[mode]), "vfsms_set_matcher")
+
+
+def last_match_fallbacks(device=0):
+    n = ctypes.c_int(0)
+    check(_lib.load().vfsms_last_match_fallbacks(_lib.context(device), ctypes.byref(n)), "vfsms_last_match_fallbacks")
+    return n.value
+
+
 def profile_enable(on=True, device=0):
     check(_lib.load().vfsms_profile_enable(_lib.context(device), int(on)), "vfsms_profile_enable")
 

@@ -76,6 +76,12 @@ void *vfsms_stream(vfsms_ctx *ctx);           /* the context's cudaStream_t */
 /* number of kernel launches this context has issued since creation (bench.py's gpu_launches) */
 int64_t vfsms_launch_count(vfsms_ctx *ctx);
 
+/* Matcher selection: 0 (default) = tcgen05 split-bf16 GEMM candidates + exact fp32 rescoring (+ exact fallback),
+ * 1 = exact fp32 SIMT kernel.  Both produce identical results; 1 exists for verification. */
+int vfsms_set_matcher(vfsms_ctx *ctx, int mode);
+/* Number of queries of the last tensor-core match that needed the exact fallback scan (synchronises the stream). */
+int vfsms_last_match_fallbacks(vfsms_ctx *ctx, int *count_out);
+
 /* Per-stage device timing with CUDA events recorded on the launching stream (bench.py's roofline numbers).
  * Off by default.  vfsms_profile_read synchronises the stream, then returns accumulated milliseconds and call
  * counts per stage (arrays of VFSMS_STAGE_COUNT) and optionally resets them. */

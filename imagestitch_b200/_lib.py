@@ -75,7 +75,7 @@ def load():
     L.vfsms_match_batch_dev.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp]
     L.vfsms_phase_correlate_host.argtypes = [vp, vp, vp, i32, i32, i32, ctypes.POINTER(ctypes.c_double)]
     L.vfsms_phase_correlate_dev.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
-    L.vfsms_fuse_roi_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    L.vfsms_fuse_roi_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     L.vfsms_mosaic_host.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp]
     L.vfsms_set_matcher.argtypes = [vp, i32]
     L.vfsms_last_match_fallbacks.argtypes = [vp, ctypes.POINTER(i32)]

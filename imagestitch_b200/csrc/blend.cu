@@ -1,0 +1,401 @@
+// blend.cu -- overlap blending and mosaic assembly on a device-resident canvas, sm_100a.
+//
+// Replaces Stitcher.fuseImage (Stitcher.py:488-525), ImageFusion.fuseByAverage / Maximum / Minimum / FadeInAndFadeOut /
+// Trigonometric and getWeightsMatrix (ImageFusion.py:12-293), and the paste/blend loop of Stitcher.getStitchByOffset
+// (Stitcher.py:433-486).  Data model: the canvas holds -1 for "empty"; the reference uses int64,
+// here int16 (values are -1..255) -- 4x less HBM traffic, identical results.
+//
+// Per overlap ROI, three launches and no host synchronisation:
+//   blend_stats_kernel   count(A > -1), the four quadrant counts of (A > 0), first/last non-empty row of every column
+//   blend_plan_kernel    "normal" vs "corner" decision (ImageFusion.py:209), and for corners a literal transcription of
+//                        the data-dependent scans of getWeightsMatrix (ImageFusion.py:62-187, including its early-exit and
+//                        index-wrap quirks) producing the two 1-D ramps weightMatB_1 / weightMatB_2
+//   blend_apply_kernel   A[A<0] = B, w_A*A + w_B*B in float64, clip, truncate (ImageFusion.py:240-243, 289-291)
+// All HBM-bound: ~ (2+2) B/px read for stats, (2+2) B/px read + 1-2 B/px written for apply.
+#include "common.cuh"
+#include <math.h>
+
+struct BlendPlan {
+    int corner;            // 0: 1-D ramp, 1: corner weights
+    int index;             // quadrant case 0..3 (ImageFusion.py:62)
+    int row_index, col_index;
+    long long count_valid; // elements with A > -1
+    long long quad[4];     // elements with A > 0 per quadrant: TL, BL, BR, TR (ImageFusion.py:57-60)
+};
+
+struct BlendState {
+    DevBuf a16, b16, out8, plan, col_top, col_bot, w1, w2, wa_out, wb_out, canvas, tile, tiles_all;
+};
+
+static BlendState *bstate(vfsms_ctx *ctx)
+{
+    if (!ctx->blend_state) ctx->blend_state = new BlendState();
+    return (BlendState *)ctx->blend_state;
+}
+
+void blend_state_destroy(vfsms_ctx *ctx)
+{
+    BlendState *s = (BlendState *)ctx->blend_state;
+    if (!s) return;
+    DevBuf *b[] = { &s->a16, &s->b16, &s->out8, &s->plan, &s->col_top, &s->col_bot, &s->w1, &s->w2, &s->wa_out, &s->wb_out,
+                    &s->canvas, &s->tile, &s->tiles_all };
+    for (DevBuf *x : b) x->release();
+    delete s;
+    ctx->blend_state = nullptr;
+}
+
+// pixel "non-empty" test of getWeightsMatrix: gray: != -1; colour: channel sum != -3 (ImageFusion.py:72,93,...)
+__device__ __forceinline__ bool px_nonempty(const int16_t *p, int ch)
+{
+    if (ch == 1) return p[0] != -1;
+    return (int)p[0] + (int)p[1] + (int)p[2] != -3;
+}
+
+// A: rows x cols x ch int16 with row stride a_rs (elements).
+__global__ void __launch_bounds__(256) blend_stats_kernel(const int16_t *__restrict__ A, int64_t a_rs, int rows, int cols, int ch,
+                                                          BlendPlan *plan, int *col_top, int *col_bot)
+{
+    long long cv = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+    const int64_t total = (int64_t)rows * cols;
+    const int hr = rows / 2, hc = cols / 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+        const int16_t *p = A + r * a_rs + (int64_t)c * ch;
+        int pos = 0, valid = 0;
+        for (int k = 0; k < ch; k++) { pos += p[k] > 0; valid += p[k] > -1; }
+        cv += valid;
+        if (r < hr) { if (c < hc) q0 += pos; else q3 += pos; }
+        else { if (c < hc) q1 += pos; else q2 += pos; }
+        if (px_nonempty(p, ch)) { atomicMin(&col_top[c], r); atomicMax(&col_bot[c], r); }
+    }
+    for (int o = 16; o; o >>= 1) {
+        cv += __shfl_xor_sync(0xffffffffu, cv, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+        q1 += __shfl_xor_sync(0xffffffffu, q1, o); q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+        q3 += __shfl_xor_sync(0xffffffffu, q3, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd((unsigned long long *)&plan->count_valid, (unsigned long long)cv);
+        atomicAdd((unsigned long long *)&plan->quad[0], (unsigned long long)q0);
+        atomicAdd((unsigned long long *)&plan->quad[1], (unsigned long long)q1);
+        atomicAdd((unsigned long long *)&plan->quad[2], (unsigned long long)q2);
+        atomicAdd((unsigned long long *)&plan->quad[3], (unsigned long long)q3);
+    }
+}
+
+// python-style index into a length-n axis (negative wraps once, like numpy); clamps what numpy would reject
+__device__ __forceinline__ int py_index(int i, int n)
+{
+    if (i < 0) i += n;
+    return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+
+__global__ void __launch_bounds__(256) blend_plan_kernel(const int16_t *__restrict__ A, int64_t a_rs, int rows, int cols, int ch,
+                                                         BlendPlan *plan, const int *__restrict__ col_top, const int *__restrict__ col_bot,
+                                                         float *w1, float *w2, int force_corner)
+{
+    __shared__ int s_ri_start, s_ri, s_ci_start, s_ci, s_index, s_corner;
+    const int row = rows, col = cols;
+    if (threadIdx.x == 0) {
+        const double ratio = (double)plan->count_valid / ((double)rows * cols * ch);
+        int corner = force_corner || !(ratio > 0.65);
+        int index = 0;
+        { long long best = plan->quad[0]; for (int k = 1; k < 4; k++) if (plan->quad[k] < best) { best = plan->quad[k]; index = k; } }
+        int rowIndex = 0, colIndex = 0;
+        if (corner) {
+            if (index == 2) {                                         // ImageFusion.py:63-90
+                for (int j = 1; j < col; j++) {
+                    const int c = col - j;
+                    if (col_bot[c] >= 0) rowIndex = col_bot[c] + 1;
+                    if (rowIndex != 0) break;
+                }
+                const int16_t *rp = A + py_index(rowIndex, row) * a_rs;
+                for (int i = col - 1; i >= 0; i--) if (px_nonempty(rp + (int64_t)i * ch, ch)) { colIndex = i + 1; break; }
+            } else if (index == 3) {                                  // ImageFusion.py:92-120
+                for (int j = 1; j < col; j++) {
+                    const int c = col - j;
+                    if (col_top[c] < row) rowIndex = col_top[c] - 1;
+                    if (rowIndex != 0) break;
+                }
+                const int16_t *rp = A + py_index(rowIndex, row) * a_rs;
+                for (int i = col - 1; i >= 0; i--) if (px_nonempty(rp + (int64_t)i * ch, ch)) { colIndex = i + 1; break; }
+            } else if (index == 0) {                                  // ImageFusion.py:122-152
+                for (int j = 0; j < col; j++) {
+                    if (col_top[j] < row) rowIndex = col_top[j] - 1;
+                    if (rowIndex != 0) break;
+                }
+                const int16_t *rp = A + py_index(rowIndex, row) * a_rs;
+                for (int i = 0; i < col; i++) if (px_nonempty(rp + (int64_t)i * ch, ch)) { colIndex = i - 1; break; }
+            } else {                                                  // index == 1, ImageFusion.py:154-186
+                for (int j = 0; j < col; j++) {
+                    if (col_bot[j] >= 0) rowIndex = col_bot[j] + 1;
+                    if (rowIndex != 0) break;
+                }
+                const int16_t *rp = A + py_index(rowIndex, row) * a_rs;
+                for (int i = 0; i < col; i++) if (px_nonempty(rp + (int64_t)i * ch, ch)) { colIndex = i - 1; break; }
+            }
+        }
+        plan->corner = corner; plan->index = index; plan->row_index = rowIndex; plan->col_index = colIndex;
+        s_corner = corner; s_index = index;
+        s_ri_start = rowIndex; s_ci_start = colIndex;
+        // "if rowIndex == 0: rowIndex = 1" happens inside the assignment loops (first iteration), ImageFusion.py:85-90 etc.
+        s_ri = rowIndex == 0 ? 1 : rowIndex;
+        s_ci = colIndex == 0 ? 1 : colIndex;
+    }
+    __syncthreads();
+    if (!s_corner) return;
+    const int index = s_index, ri0 = s_ri_start, ri = s_ri, ci0 = s_ci_start, ci = s_ci;
+    for (int r = threadIdx.x; r < row; r += blockDim.x) w1[r] = 1.f;
+    for (int c = threadIdx.x; c < col; c += blockDim.x) w2[c] = 1.f;
+    __syncthreads();
+    // row ramp weightMatB_1
+    if (index == 2 || index == 1) {
+        // for i in range(rowIndex + 1): w[rowIndex - i] = (rowIndex - i) / rowIndex   (rowIndex bumped 0 -> 1 first)
+        // loop bound uses the ORIGINAL rowIndex, targets use the bumped one
+        for (int i = threadIdx.x; i <= ri0; i += blockDim.x) {
+            const int t = ri - i;
+            if (ri0 < 0) break;
+            const int tt = t < 0 ? t + row : t;
+            if (tt >= 0 && tt < row) w1[tt] = (float)((double)(ri - i) / (double)ri);
+        }
+    } else {
+        // for i in range(rowIndex, row): w[i] = (row - i - 1) / (row - rowIndex - 1)
+        // (a negative start index wraps to the last rows in numpy, which later iterations overwrite: skipping i < 0 is equivalent)
+        for (int i = (ri0 < 0 ? 0 : ri0) + (int)threadIdx.x; i < row; i += blockDim.x) {
+            const int den = row - ri - 1;
+            w1[i] = den != 0 ? (float)((double)(row - i - 1) / (double)den) : 1.f;
+        }
+    }
+    // column ramp weightMatB_2
+    if (index == 2 || index == 3) {
+        for (int i = threadIdx.x; i <= ci0; i += blockDim.x) {
+            if (ci0 < 0) break;
+            const int t = ci - i;
+            const int tt = t < 0 ? t + col : t;
+            if (tt >= 0 && tt < col) w2[tt] = (float)((double)(ci - i) / (double)ci);
+        }
+    } else {
+        for (int i = (ci0 < 0 ? 0 : ci0) + (int)threadIdx.x; i < col; i += blockDim.x) {
+            const int den = col - ci - 1;
+            w2[i] = den != 0 ? (float)((double)(col - i - 1) / (double)den) : 1.f;
+        }
+    }
+}
+
+// method: VFSMS_FUSE_*.  out may alias nothing; wa_out / wb_out optional (per pixel, float32).
+__global__ void __launch_bounds__(256) blend_apply_kernel(const int16_t *__restrict__ A, int64_t a_rs, const int16_t *__restrict__ B, int64_t b_rs,
+                                                          int rows, int cols, int ch, int method, int d_row, int d_col,
+                                                          const BlendPlan *__restrict__ plan, const float *__restrict__ w1, const float *__restrict__ w2,
+                                                          uint8_t *out8, int64_t o_rs, int16_t *out16, int64_t o16_rs,
+                                                          float *wa_out, float *wb_out)
+{
+    const int64_t total = (int64_t)rows * cols;
+    const int corner = (method == VFSMS_FUSE_FADE || method == VFSMS_FUSE_TRIG) ? plan->corner : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+        const int16_t *pa = A + r * a_rs + (int64_t)c * ch, *pb = B + r * b_rs + (int64_t)c * ch;
+        double wa = 1.0, wb = 1.0;
+        if (method == VFSMS_FUSE_FADE) {
+            float fa = 1.f, fb = 1.f;
+            if (corner) { fb = w1[r] * w2[c]; fa = 1.f - fb; }
+            else if (cols <= rows) {                                       // horizontal ramp, ImageFusion.py:213-225
+                const float fc = (float)cols;
+                if (d_col >= 0) { fa = (float)(cols - 1 - c) / fc; fb = (float)c / fc; }
+                else { fa = (float)(c + 1) / fc; fb = (float)(cols - c) / fc; }
+            } else {                                                       // vertical ramp, ImageFusion.py:227-235
+                const float fr = (float)rows;
+                if (d_row <= 0) { fa = (float)r / fr; fb = (float)(rows - 1 - r) / fr; }
+                else { fa = (float)(rows - r) / fr; fb = (float)(r + 1) / fr; }
+            }
+            wa = (double)fa; wb = (double)fb;
+        } else if (method == VFSMS_FUSE_TRIG) {
+            if (corner) {
+                // getWeightsMatrix returns float32, so sin / square / 1-x stay in float32 (numpy keeps the array dtype)
+                const float fb = w1[r] * w2[c];
+                const float x = ((1.f - fb) * (float)M_PI) / 2.f;
+                const float sv = sinf(x);
+                const float fwa = sv * sv;
+                wa = (double)fwa; wb = (double)(1.f - fwa);
+            } else {
+                double ta;
+                if (cols <= rows) {                                        // ImageFusion.py:263-271 (orientation differs from fade)
+                    if (d_col >= 0) ta = (double)c / (double)cols; else ta = (double)(cols - c) / (double)cols;
+                } else {
+                    if (d_row <= 0) ta = (double)r / (double)rows; else ta = (double)(rows - r) / (double)rows;
+                }
+                const double sv = sin(ta * M_PI / 2);
+                wa = sv * sv; wb = 1.0 - wa;                               // ImageFusion.py:286-287
+            }
+        }
+        if (wa_out) { wa_out[i] = (float)wa; wb_out[i] = (float)wb; }
+        for (int k = 0; k < ch; k++) {
+            int a = pa[k], b = pb[k];
+            int res;
+            if (method == VFSMS_FUSE_FADE || method == VFSMS_FUSE_TRIG) {
+                if (a < 0) a = b;                                          // imageA[imageA < 0] = imageB[imageA < 0]
+                double v = wa * (double)a + wb * (double)b;
+                v = v < 0 ? 0 : (v > 255 ? 255 : v);
+                res = (int)v;                                              // np.uint8 truncation
+            } else {
+                // Stitcher.py:498-504: -1 -> 0, then mutual zero fill
+                if (a == -1) a = 0;
+                if (b == -1) b = 0;
+                if (a == 0) a = b;
+                if (b == 0) b = a;
+                if (method == VFSMS_FUSE_AVERAGE) res = (a + b) / 2;      // uint8((A + B) / 2): truncation of a non-negative value
+                else if (method == VFSMS_FUSE_MAXIMUM) res = a > b ? a : b;
+                else if (method == VFSMS_FUSE_MINIMUM) res = a < b ? a : b;
+                else res = b;                                              // notFuse
+            }
+            if (out8) out8[r * o_rs + (int64_t)c * ch + k] = (uint8_t)res;
+            if (out16) out16[r * o16_rs + (int64_t)c * ch + k] = (int16_t)(res & 255);
+        }
+    }
+}
+
+__global__ void fill_i32_kernel(int *p, int n, int v) { for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v; }
+__global__ void fill_i16_kernel(int16_t *p, int64_t n, int16_t v)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+// tile (u8) -> int16 buffer, rectangular copy
+__global__ void u8_to_i16_kernel(const uint8_t *__restrict__ src, int64_t s_rs, int16_t *dst, int64_t d_rs, int rows, int row_elems)
+{
+    const int64_t total = (int64_t)rows * row_elems;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / row_elems), e = (int)(i - (int64_t)r * row_elems);
+        dst[r * d_rs + e] = src[r * s_rs + e];
+    }
+}
+__global__ void canvas_to_u8_kernel(const int16_t *__restrict__ src, uint8_t *dst, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = src[i];
+        dst[i] = (uint8_t)(v < 0 ? 0 : v);                                // stitchResult[stitchResult == -1] = 0 (Stitcher.py:485)
+    }
+}
+
+static int grid_for(vfsms_ctx *ctx, int64_t n) { int64_t g = (n + 255) / 256; int64_t m = (int64_t)ctx->num_sms * 8; return (int)(g < m ? (g < 1 ? 1 : g) : m); }
+
+// Core: fuse ROI (A, B int16 on device) -> out8 and/or out16 (may alias A's memory: every pixel is read before written by
+// the same thread).  Asynchronous on st.
+static int fuse_roi_dev(vfsms_ctx *ctx, const int16_t *A, int64_t a_rs, const int16_t *B, int64_t b_rs, int rows, int cols, int ch,
+                        int method, int d_row, int d_col, uint8_t *out8, int64_t o_rs, int16_t *out16, int64_t o16_rs,
+                        float *wa_out, float *wb_out, cudaStream_t st)
+{
+    const int force_corner = (method & 0x100) != 0;      // getWeightsMatrix parity hook: always take the corner path
+    method &= 0xff;
+    BlendState *bs = bstate(ctx);
+    int rc;
+    if ((rc = bs->plan.reserve(sizeof(BlendPlan)))) return rc;
+    if ((rc = bs->col_top.reserve((size_t)cols * 4))) return rc;
+    if ((rc = bs->col_bot.reserve((size_t)cols * 4))) return rc;
+    if ((rc = bs->w1.reserve((size_t)rows * 4))) return rc;
+    if ((rc = bs->w2.reserve((size_t)cols * 4))) return rc;
+    StageTimer t(ctx, st, VFSMS_STAGE_BLEND);
+    const int64_t n = (int64_t)rows * cols;
+    if (method == VFSMS_FUSE_FADE || method == VFSMS_FUSE_TRIG) {
+        CUDA_TRY(cudaMemsetAsync(bs->plan.p, 0, sizeof(BlendPlan), st));
+        fill_i32_kernel<<<grid_for(ctx, cols), 256, 0, st>>>(bs->col_top.as<int>(), cols, rows);     // "none" = rows
+        LAUNCH_CHECK(ctx);
+        CUDA_TRY(cudaMemsetAsync(bs->col_bot.p, 0xff, (size_t)cols * 4, st));                        // "none" = -1
+        blend_stats_kernel<<<grid_for(ctx, n), 256, 0, st>>>(A, a_rs, rows, cols, ch, bs->plan.as<BlendPlan>(), bs->col_top.as<int>(), bs->col_bot.as<int>());
+        LAUNCH_CHECK(ctx);
+        blend_plan_kernel<<<1, 256, 0, st>>>(A, a_rs, rows, cols, ch, bs->plan.as<BlendPlan>(), bs->col_top.as<int>(), bs->col_bot.as<int>(),
+                                             bs->w1.as<float>(), bs->w2.as<float>(), force_corner);
+        LAUNCH_CHECK(ctx);
+    }
+    blend_apply_kernel<<<grid_for(ctx, n), 256, 0, st>>>(A, a_rs, B, b_rs, rows, cols, ch, method, d_row, d_col, bs->plan.as<BlendPlan>(),
+                                                         bs->w1.as<float>(), bs->w2.as<float>(), out8, o_rs, out16, o16_rs, wa_out, wb_out);
+    LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" {
+
+int vfsms_fuse_roi_host(vfsms_ctx *ctx, const int16_t *a, const int16_t *b, int rows, int cols, int channels, int method,
+                        int d_row, int d_col, uint8_t *out, float *wa_out, float *wb_out)
+{
+    if (!ctx || !a || !b || !out || rows < 1 || cols < 1 || (channels != 1 && channels != 3)) { vfsms_set_error("fuse_roi: bad arguments"); return VFSMS_E_ARG; }
+    if ((method & 0xff) < VFSMS_FUSE_NONE || (method & 0xff) > VFSMS_FUSE_TRIG) {
+        vfsms_set_error("fuse_roi: method %d is not available through this entry point", method); return VFSMS_E_UNSUPPORTED;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    BlendState *bs = bstate(ctx);
+    const size_t n = (size_t)rows * cols * channels;
+    int rc;
+    if ((rc = bs->a16.reserve(n * 2))) return rc;
+    if ((rc = bs->b16.reserve(n * 2))) return rc;
+    if ((rc = bs->out8.reserve(n))) return rc;
+    float *dwa = nullptr, *dwb = nullptr;
+    if (wa_out && wb_out) {
+        if ((rc = bs->wa_out.reserve((size_t)rows * cols * 4))) return rc;
+        if ((rc = bs->wb_out.reserve((size_t)rows * cols * 4))) return rc;
+        dwa = bs->wa_out.as<float>(); dwb = bs->wb_out.as<float>();
+    }
+    CUDA_TRY(cudaMemcpyAsync(bs->a16.p, a, n * 2, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(bs->b16.p, b, n * 2, cudaMemcpyHostToDevice, st));
+    const int64_t rs = (int64_t)cols * channels;
+    if ((rc = fuse_roi_dev(ctx, bs->a16.as<int16_t>(), rs, bs->b16.as<int16_t>(), rs, rows, cols, channels, method, d_row, d_col,
+                           bs->out8.as<uint8_t>(), rs, nullptr, 0, dwa, dwb, st))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, bs->out8.p, n, cudaMemcpyDeviceToHost, st));
+    if (dwa) {
+        CUDA_TRY(cudaMemcpyAsync(wa_out, dwa, (size_t)rows * cols * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(wb_out, dwb, (size_t)rows * cols * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vfsms_mosaic_host(vfsms_ctx *ctx, const uint8_t *tiles, int n_tiles, int tile_rows, int tile_cols, int channels,
+                      const int32_t *tile_origin, const int32_t *roi_rect, const int32_t *pair_offset, int method,
+                      int canvas_rows, int canvas_cols, uint8_t *canvas_out)
+{
+    if (!ctx || !tiles || !tile_origin || !roi_rect || !pair_offset || !canvas_out || n_tiles < 1 || (channels != 1 && channels != 3)) {
+        vfsms_set_error("mosaic: bad arguments"); return VFSMS_E_ARG;
+    }
+    if (method < VFSMS_FUSE_NONE || method > VFSMS_FUSE_TRIG) { vfsms_set_error("mosaic: method %d not available", method); return VFSMS_E_UNSUPPORTED; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    BlendState *bs = bstate(ctx);
+    const int64_t crs = (int64_t)canvas_cols * channels;
+    const int64_t cn = (int64_t)canvas_rows * crs;
+    const size_t tile_bytes = (size_t)tile_rows * tile_cols * channels;
+    int rc;
+    if ((rc = bs->canvas.reserve((size_t)cn * 2))) return rc;
+    if ((rc = bs->tile.reserve(tile_bytes * 2))) return rc;          // int16 copy of the current tile
+    if ((rc = bs->tiles_all.reserve(tile_bytes))) return rc;          // u8 staging of the current tile
+    if ((rc = bs->out8.reserve((size_t)cn))) return rc;
+    int16_t *canvas = bs->canvas.as<int16_t>();
+    fill_i16_kernel<<<grid_for(ctx, cn), 256, 0, st>>>(canvas, cn, (int16_t)-1);
+    LAUNCH_CHECK(ctx);
+    const int64_t trs = (int64_t)tile_cols * channels;
+    for (int i = 0; i < n_tiles; i++) {
+        const int r0 = tile_origin[2 * i], c0 = tile_origin[2 * i + 1];
+        if (r0 < 0 || c0 < 0 || r0 + tile_rows > canvas_rows || c0 + tile_cols > canvas_cols) { vfsms_set_error("mosaic: tile %d outside the canvas", i); return VFSMS_E_ARG; }
+        CUDA_TRY(cudaMemcpyAsync(bs->tiles_all.p, tiles + (size_t)i * tile_bytes, tile_bytes, cudaMemcpyHostToDevice, st));
+        int16_t *t16 = bs->tile.as<int16_t>();
+        u8_to_i16_kernel<<<grid_for(ctx, (int64_t)tile_rows * trs), 256, 0, st>>>(bs->tiles_all.as<uint8_t>(), trs, t16, trs, tile_rows, (int)trs);
+        LAUNCH_CHECK(ctx);
+        int16_t *dst = canvas + r0 * crs + (int64_t)c0 * channels;
+        const int rr0 = roi_rect[4 * i], rc0 = roi_rect[4 * i + 1], rr1 = roi_rect[4 * i + 2], rc1 = roi_rect[4 * i + 3];
+        const bool fuse = i > 0 && method != VFSMS_FUSE_NONE && rr1 > rr0 && rc1 > rc0;
+        if (fuse) {
+            // ROI: A = canvas before the paste, B = the tile there; result written over the canvas ROI (Stitcher.py:466-483)
+            if (rr0 < r0 || rc0 < c0 || rr1 > r0 + tile_rows || rc1 > c0 + tile_cols) { vfsms_set_error("mosaic: ROI %d outside its tile", i); return VFSMS_E_ARG; }
+            int16_t *Aroi = canvas + rr0 * crs + (int64_t)rc0 * channels;
+            const int16_t *Broi = t16 + (rr0 - r0) * trs + (int64_t)(rc0 - c0) * channels;
+            // the fused values go to a scratch copy of the tile ROI (so that the plain paste below finishes the job)
+            if ((rc = fuse_roi_dev(ctx, Aroi, crs, Broi, trs, rr1 - rr0, rc1 - rc0, channels, method, pair_offset[2 * i], pair_offset[2 * i + 1],
+                                   nullptr, 0, (int16_t *)Broi, trs, nullptr, nullptr, st))) return rc;
+        }
+        CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)crs * 2, t16, (size_t)trs * 2, (size_t)trs * 2, tile_rows, cudaMemcpyDeviceToDevice, st));
+    }
+    canvas_to_u8_kernel<<<grid_for(ctx, cn), 256, 0, st>>>(canvas, bs->out8.as<uint8_t>(), cn);
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(cudaMemcpyAsync(canvas_out, bs->out8.p, (size_t)cn, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

@@ -27,8 +27,9 @@
 #define TC_KB 64                 // bf16 elements per k-block = 128 bytes = one swizzle row
 #define TC_STAGES 4
 #define TC_TOPK 4
+#define TC_EPI_GROUPS 2          // epilogue warpgroups; group g scans columns [g*64, g*64+64) of every tile
 #define TC_MAX_KBLOCKS 7         // K' <= 448  (D <= 128)
-#define TC_THREADS 256           // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: epilogue
+#define TC_THREADS (128 + 128 * TC_EPI_GROUPS)   // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4..: epilogue
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -168,13 +169,15 @@ struct TcShared {
 
 __device__ __forceinline__ void topk_insert(float s, int idx, float (&ts)[TC_TOPK], int (&ti)[TC_TOPK])
 {
-    // ts ascending; strict '<' keeps the earlier (lower) train index on ties
-    if (s < ts[1]) {
-        if (s < ts[0]) { ts[3] = ts[2]; ti[3] = ti[2]; ts[2] = ts[1]; ti[2] = ti[1]; ts[1] = ts[0]; ti[1] = ti[0]; ts[0] = s; ti[0] = idx; }
-        else { ts[3] = ts[2]; ti[3] = ti[2]; ts[2] = ts[1]; ti[2] = ti[1]; ts[1] = s; ti[1] = idx; }
-    } else {
-        if (s < ts[2]) { ts[3] = ts[2]; ti[3] = ti[2]; ts[2] = s; ti[2] = idx; }
-        else { ts[3] = s; ti[3] = idx; }
+    // ts ascending.  The new element replaces the worst and bubbles up; strict '<' keeps the earlier (lower) train
+    // index ahead on ties.
+    ts[TC_TOPK - 1] = s; ti[TC_TOPK - 1] = idx;
+#pragma unroll
+    for (int i = TC_TOPK - 1; i > 0; i--) {
+        if (ts[i] < ts[i - 1]) {
+            const float f = ts[i]; ts[i] = ts[i - 1]; ts[i - 1] = f;
+            const int t = ti[i]; ti[i] = ti[i - 1]; ti[i - 1] = t;
+        }
     }
 }
 
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const __grid_co
     if (warp == 1 && lane == 0) {
         mbar_init(&sh->a_full, 1); mbar_init(&sh->a_empty, 1);
         for (int i = 0; i < TC_STAGES; i++) { mbar_init(&sh->b_full[i], 1); mbar_init(&sh->b_empty[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&sh->acc_full[i], 1); mbar_init(&sh->acc_empty[i], 4); }
+        for (int i = 0; i < 2; i++) { mbar_init(&sh->acc_full[i], 1); mbar_init(&sh->acc_empty[i], 4 * TC_EPI_GROUPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(&sh->tmem_base, 256);
@@ -272,9 +275,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const __grid_co
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue warpgroup: TMEM -> registers -> running top-K =====================
+        // ===================== epilogue warpgroups: TMEM -> registers -> running top-K =====================
+        // Two warps per TMEM lane quarter (one per column half) so every scheduler has two epilogue warps to interleave:
+        // the insert path is a dependent chain and a lone warp per scheduler cannot hide its latency.
         const int q4 = warp & 3;                                     // TMEM lane quarter this warp may access
+        const int grp = (warp - 4) >> 2;                             // column group
         const int row = q4 * 32 + lane;
+        constexpr int GCOLS = TC_N / TC_EPI_GROUPS;
         uint32_t acc = 0, acc_phase = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             int p, mt, nt0, nt1;
@@ -285,16 +292,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const __grid_co
             for (int nt = nt0; nt < nt1; nt++) {
                 mbar_wait(&sh->acc_full[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * TC_N;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * TC_N + grp * GCOLS;
 #pragma unroll 1
-                for (int c = 0; c < TC_N / 32; c++) {
+                for (int c = 0; c < GCOLS / 32; c++) {
                     uint32_t v[32];
                     tmem_ld32(taddr + c * 32, v);
-                    const int col0 = nt * TC_N + c * 32;
+                    const int col0 = nt * TC_N + grp * GCOLS + c * 32;
+                    // inserts are rare once the list has warmed up: one min-tree per 32 values, then the slow path
+                    float m0 = fminf(__uint_as_float(v[0]), __uint_as_float(v[1])), m1 = fminf(__uint_as_float(v[2]), __uint_as_float(v[3]));
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float s = __uint_as_float(v[j]);
-                        if (s < ts[TC_TOPK - 1]) topk_insert(s, col0 + j, ts, ti);
+                    for (int j = 4; j < 32; j += 2) { m0 = fminf(m0, __uint_as_float(v[j])); m1 = fminf(m1, __uint_as_float(v[j + 1])); }
+                    if (fminf(m0, m1) < ts[TC_TOPK - 1]) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float s = __uint_as_float(v[j]);
+                            if (s < ts[TC_TOPK - 1]) topk_insert(s, col0 + j, ts, ti);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -304,7 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const __grid_co
             }
             const int q = mt * TC_M + row;
             const int s_id = item % n_splits;
-            const size_t o = (((size_t)p * cap + q) * n_splits + s_id) * TC_TOPK;
+            const size_t o = ((((size_t)p * cap + q) * n_splits + s_id) * TC_EPI_GROUPS + grp) * TC_TOPK;
 #pragma unroll
             for (int i = 0; i < TC_TOPK; i++) { cand_score[o + i] = ts[i]; cand_idx[o + i] = ti[i]; }
         }
@@ -331,7 +344,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
     if (q >= nA) return;
     const float *a = desc_a + p * pair_stride_a + (size_t)q * dim;
     const float *B = desc_b + p * pair_stride_b;
-    const int nc = n_splits * TC_TOPK;                 // <= 32 candidates: one per lane
+    const int nc = n_splits * TC_EPI_GROUPS * TC_TOPK;     // <= 32 candidates: one per lane, lists of TC_TOPK
     float d = FLT_MAX; int t = -1; float approx = FLT_MAX;
     if (lane < nc) {
         const size_t o = ((size_t)p * cap + q) * nc + lane;
@@ -363,8 +376,11 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
     if (lane == 0) {
         const float na = norm_a[(size_t)p * cap + q];
         const float bmax = norm_b_max[p];
-        // |approx score - exact score| <= E  (3-term split-bf16 + fp32 tensor accumulation + fp32 rescoring), generous
-        const float E = 1e-3f * (sqrtf(na) * sqrtf(bmax) + bmax) + 1e-6f;
+        // |approx score - exact score| <= E.  Terms (DESIGN.md "matcher error bound"): dropped lo*lo and second-order split
+        // errors 3*2^-18 |a||b| (x2 for the -2 scale), fp32 accumulation of K' = 448 exact bf16 products, worst case
+        // truncating adder 448*2^-23 (2|a||b| + |b|^2), norm split 2^-17 |b|^2, fp32 rescoring 128*2^-24 d^2.
+        const float ab = sqrtf(na) * sqrtf(bmax);
+        const float E = 1.4e-4f * ab + 7e-5f * bmax + 1e-5f * (na + bmax + 2.f * ab) + 1e-7f;
         bool ok = true;
         if (nB >= 2) {
             if (t1 < 0) ok = false;
@@ -391,44 +407,64 @@ __global__ void norm_max_kernel(const float *__restrict__ norms_b, const int32_t
     if (threadIdx.x == 0) { for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, s[w]); out[p] = m; }
 }
 
-// ---------------------------------------------------------------- 4. exact fallback for flagged queries (one warp each)
+// ---------------------------------------------------------------- 4. exact fallback for flagged queries (one CTA each)
+__device__ __forceinline__ void top2_merge(float &d0, int &t0, float &d1, int &t1, float e0, int u0, float e1, int u1)
+{
+    float c[4] = { d0, d1, e0, e1 }; int ci[4] = { t0, t1, u0, u1 };
+    float b0 = FLT_MAX, b1 = FLT_MAX; int i0 = -1, i1 = -1;
+#pragma unroll
+    for (int z = 0; z < 4; z++) {
+        if (ci[z] < 0) continue;
+        if (i0 < 0 || c[z] < b0 || (c[z] == b0 && ci[z] < i0)) { b1 = b0; i1 = i0; b0 = c[z]; i0 = ci[z]; }
+        else if (i1 < 0 || c[z] < b1 || (c[z] == b1 && ci[z] < i1)) { b1 = c[z]; i1 = ci[z]; }
+    }
+    d0 = b0; t0 = i0; d1 = b1; t1 = i1;
+}
+
 __global__ void __launch_bounds__(256) fallback_exact_kernel(const float *__restrict__ desc_a, const float *__restrict__ desc_b,
                                                              int64_t pair_stride_a, int64_t pair_stride_b,
                                                              const int32_t *__restrict__ n_b_ptr, int n_b_stride, int cap, int dim,
                                                              const int32_t *__restrict__ fallback_list, const int32_t *__restrict__ fallback_count,
                                                              int32_t *best_idx, float *best_dist)
 {
-    const int lane = threadIdx.x & 31;
+    __shared__ float s_a[128];
+    __shared__ float s_d[8][2];
+    __shared__ int s_t[8][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int total = *fallback_count;
-    for (int w = blockIdx.x * 8 + (threadIdx.x >> 5); w < total; w += gridDim.x * 8) {
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int pq = fallback_list[w];
         const int p = pq / cap, q = pq - p * cap;
         const int nB = n_b_ptr[(size_t)p * n_b_stride];
         const float *a = desc_a + p * pair_stride_a + (size_t)q * dim;
         const float *B = desc_b + p * pair_stride_b;
+        __syncthreads();
+        for (int k = threadIdx.x; k < dim; k += blockDim.x) s_a[k] = a[k];
+        __syncthreads();
         float d0 = FLT_MAX, d1 = FLT_MAX; int t0 = -1, t1 = -1;
-        for (int t = lane; t < nB; t += 32) {
-            const float *b = B + (size_t)t * dim;
+        for (int t = threadIdx.x; t < nB; t += blockDim.x) {
+            const float4 *b4 = (const float4 *)(B + (size_t)t * dim);       // dim % 4 == 0, rows 16-byte aligned
             float s = 0.f;
-            for (int k = 0; k < dim; k++) { const float df = a[k] - b[k]; s += df * df; }
+#pragma unroll 4
+            for (int k4 = 0; k4 < dim / 4; k4++) {
+                const float4 bv = __ldg(b4 + k4);
+                float df = s_a[4 * k4] - bv.x; s += df * df;
+                df = s_a[4 * k4 + 1] - bv.y; s += df * df;
+                df = s_a[4 * k4 + 2] - bv.z; s += df * df;
+                df = s_a[4 * k4 + 3] - bv.w; s += df * df;
+            }
             if (s < d0) { d1 = d0; t1 = t0; d0 = s; t0 = t; }
             else if (s < d1) { d1 = s; t1 = t; }
         }
-        // merge 32 sorted pairs: lexicographic (d, t)
         for (int o = 16; o; o >>= 1) {
             const float e0 = __shfl_xor_sync(0xffffffffu, d0, o), e1 = __shfl_xor_sync(0xffffffffu, d1, o);
             const int u0 = __shfl_xor_sync(0xffffffffu, t0, o), u1 = __shfl_xor_sync(0xffffffffu, t1, o);
-            float c[4] = { d0, d1, e0, e1 }; int ci[4] = { t0, t1, u0, u1 };
-            float b0 = FLT_MAX, b1 = FLT_MAX; int i0 = -1, i1 = -1;
-#pragma unroll
-            for (int z = 0; z < 4; z++) {
-                if (ci[z] < 0) continue;
-                if (i0 < 0 || c[z] < b0 || (c[z] == b0 && ci[z] < i0)) { b1 = b0; i1 = i0; b0 = c[z]; i0 = ci[z]; }
-                else if (i1 < 0 || c[z] < b1 || (c[z] == b1 && ci[z] < i1)) { b1 = c[z]; i1 = ci[z]; }
-            }
-            d0 = b0; t0 = i0; d1 = b1; t1 = i1;
+            top2_merge(d0, t0, d1, t1, e0, u0, e1, u1);
         }
-        if (lane == 0) {
+        if (lane == 0) { s_d[warp][0] = d0; s_d[warp][1] = d1; s_t[warp][0] = t0; s_t[warp][1] = t1; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int z = 1; z < 8; z++) top2_merge(d0, t0, d1, t1, s_d[z][0], s_t[z][0], s_d[z][1], s_t[z][1]);
             const size_t o = ((size_t)p * cap + q) * 2;
             best_idx[o] = t0; best_idx[o + 1] = t1;
             best_dist[o] = t0 >= 0 ? sqrtf(d0) : FLT_MAX; best_dist[o + 1] = t1 >= 0 ? sqrtf(d1) : FLT_MAX;
@@ -477,13 +513,13 @@ int match_tc_batch(vfsms_ctx *ctx, const float *desc_a, const int32_t *n_a, int 
     const int kprime = 3 * dim + 64, kblocks = kprime / TC_KB;
     const int m_tiles = cap / TC_M;
     int n_splits = 1;
-    while (n_pairs * m_tiles * n_splits < 2 * ctx->num_sms && n_splits < 8) n_splits *= 2;
+    while (n_pairs * m_tiles * n_splits < 2 * ctx->num_sms && n_splits * TC_EPI_GROUPS * TC_TOPK < 32) n_splits *= 2;
     int rc;
     const size_t rows = (size_t)n_pairs * cap;
     if ((rc = mw.bf16_a.reserve(rows * kprime * 2))) return rc;
     if ((rc = mw.bf16_b.reserve(rows * kprime * 2))) return rc;
     // cand buffer: scores | idx | norms_a | norms_b | bmax | fallback_count | fallback_list
-    const size_t n_cand = rows * n_splits * TC_TOPK;
+    const size_t n_cand = rows * n_splits * TC_EPI_GROUPS * TC_TOPK;
     const size_t bytes = n_cand * 8 + rows * 8 + (size_t)n_pairs * 4 + 16 + rows * 4;
     if ((rc = mw.cand_topk.reserve(bytes))) return rc;
     float *cand_score = mw.cand_topk.as<float>();
@@ -513,7 +549,7 @@ int match_tc_batch(vfsms_ctx *ctx, const float *desc_a, const int32_t *n_a, int 
     rescore_kernel<<<dim3(ceil_div(cap, 8), n_pairs), 256, 0, st>>>(desc_a, desc_b, (int64_t)cap * dim, (int64_t)cap * dim, n_a, n_a_stride, n_b, n_b_stride,
                                                                     norm_a, bmax, cand_score, cand_idx, cap, dim, n_splits, best_idx, best_dist, fb_list, fb_count);
     LAUNCH_CHECK(ctx);
-    fallback_exact_kernel<<<ctx->num_sms * 2, 256, 0, st>>>(desc_a, desc_b, (int64_t)cap * dim, (int64_t)cap * dim, n_b, n_b_stride, cap, dim,
+    fallback_exact_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(desc_a, desc_b, (int64_t)cap * dim, (int64_t)cap * dim, n_b, n_b_stride, cap, dim,
                                                             fb_list, fb_count, best_idx, best_dist);
     LAUNCH_CHECK(ctx);
     ctx->last_fallback_count_dev = fb_count;

@@ -2,7 +2,6 @@
 #include "common.cuh"
 
 void phase_state_destroy(vfsms_ctx *) {}
-void blend_state_destroy(vfsms_ctx *) {}
 
 extern "C" {
 int vfsms_orb_detect_and_describe(vfsms_ctx *, const uint8_t *, int, int, int, int, float, int, int, int, int, int, int,
@@ -12,9 +11,4 @@ int vfsms_phase_correlate_host(vfsms_ctx *, const uint8_t *, const uint8_t *, in
 { vfsms_set_error("vfsms_phase_correlate_host: not implemented yet"); return VFSMS_E_UNSUPPORTED; }
 int vfsms_phase_correlate_dev(vfsms_ctx *, const uint8_t *, const uint8_t *, int, int, int, double *, void *)
 { vfsms_set_error("vfsms_phase_correlate_dev: not implemented yet"); return VFSMS_E_UNSUPPORTED; }
-int vfsms_fuse_roi_host(vfsms_ctx *, const int16_t *, const int16_t *, int, int, int, int, int, int, uint8_t *)
-{ vfsms_set_error("vfsms_fuse_roi_host: not implemented yet"); return VFSMS_E_UNSUPPORTED; }
-int vfsms_mosaic_host(vfsms_ctx *, const uint8_t *, int, int, int, int, const int32_t *, const int32_t *, const int32_t *, int,
-                      int, int, uint8_t *)
-{ vfsms_set_error("vfsms_mosaic_host: not implemented yet"); return VFSMS_E_UNSUPPORTED; }
 }

@@ -154,6 +154,58 @@ def align_strips_dev(tiles_a, tiles_b, results, roi_rows, params=None, ratio=0.7
                                   ctypes.c_void_p(st.cuda_stream)), "vfsms_align_batch_dev")
 
 
+FUSE_METHODS = {"notFuse": 0, "average": 1, "maximum": 2, "minimum": 3, "fadeInAndFadeOut": 4, "trigonometric": 5,
+                "multiBandBlending": 6}
+
+
+def _as_i16(a):
+    a = np.asarray(a)
+    if a.size and (a.min() < -1 or a.max() > 255):
+        raise ValueError("canvas values must lie in [-1, 255]")
+    return np.ascontiguousarray(a, np.int16)
+
+
+def fuse_roi(image_a, image_b, method, d_row=0, d_col=0, want_weights=False, force_corner=False, device=0):
+    """Stitcher.fuseImage for one overlap ROI.  image_*: [r, c] or [r, c, 3] integer arrays with -1 = empty.
+    -> uint8 array (and the float32 weight matrices when want_weights)."""
+    L = _lib.load()
+    ctx = _lib.context(device)
+    A, B = _as_i16(image_a), _as_i16(image_b)
+    if A.shape != B.shape or A.ndim not in (2, 3):
+        raise ValueError("ROI arrays must have identical 2-D or 3-D shape")
+    rows, cols = A.shape[:2]
+    ch = 1 if A.ndim == 2 else A.shape[2]
+    m = FUSE_METHODS[method] if isinstance(method, str) else int(method)
+    if force_corner:
+        m |= 0x100
+    out = np.empty(A.shape, np.uint8)
+    wa = wb = None
+    if want_weights:
+        wa = np.empty((rows, cols), np.float32); wb = np.empty((rows, cols), np.float32)
+    check(L.vfsms_fuse_roi_host(ctx, _vp(A), _vp(B), rows, cols, ch, m, int(d_row), int(d_col), _vp(out),
+                                _vp(wa) if want_weights else None, _vp(wb) if want_weights else None), "vfsms_fuse_roi_host")
+    return (out, wa, wb) if want_weights else out
+
+
+def mosaic(tiles, tile_origin, roi_rect, pair_offset, method, canvas_shape, device=0):
+    """Paste/blend loop of Stitcher.getStitchByOffset on a device-resident canvas.
+    tiles [n, h, w] or [n, h, w, 3] uint8; tile_origin [n, 2]; roi_rect [n, 4] (r0, c0, r1, c1 in canvas coordinates);
+    pair_offset [n, 2] original offsets; canvas_shape (rows, cols)."""
+    L = _lib.load()
+    ctx = _lib.context(device)
+    T = np.ascontiguousarray(tiles, np.uint8)
+    n, h, w = T.shape[:3]
+    ch = 1 if T.ndim == 3 else T.shape[3]
+    org = np.ascontiguousarray(tile_origin, np.int32).reshape(n, 2)
+    roi = np.ascontiguousarray(roi_rect, np.int32).reshape(n, 4)
+    off = np.ascontiguousarray(pair_offset, np.int32).reshape(n, 2)
+    m = FUSE_METHODS[method] if isinstance(method, str) else int(method)
+    R, C = int(canvas_shape[0]), int(canvas_shape[1])
+    out = np.empty((R, C) if ch == 1 else (R, C, ch), np.uint8)
+    check(L.vfsms_mosaic_host(ctx, _vp(T), n, h, w, ch, _vp(org), _vp(roi), _vp(off), m, R, C, _vp(out)), "vfsms_mosaic_host")
+    return out
+
+
 def set_matcher(mode, device=0):
     """'tc' (default): tcgen05 candidates + exact rescoring; 'simt': exact fp32 SIMT kernel.  Identical results."""
     check(_lib.load().vfsms_set_matcher(_lib.context(device), {"tc": 0, "simt": 1}[mode]), "vfsms_set_matcher")

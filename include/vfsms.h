@@ -171,9 +171,12 @@ enum {
 
 /* Replaces Stitcher.fuseImage (Stitcher.py:488-525) for one overlap ROI.  a, b: rows x cols x channels int16 with
  * -1 = empty (the reference's int64 canvas sentinel, Stitcher.py:434-436); out: rows x cols x channels u8.
- * d_row / d_col: the ORIGINAL pair offset whose sign selects the ramp direction (Stitcher.py:478,483). */
+ * d_row / d_col: the ORIGINAL pair offset whose sign selects the ramp direction (Stitcher.py:478,483).
+ * method | 0x100 forces the corner-weight path of getWeightsMatrix regardless of the fill ratio (parity hook). */
 int vfsms_fuse_roi_host(vfsms_ctx *ctx, const int16_t *a, const int16_t *b, int rows, int cols, int channels,
-                        int method, int d_row, int d_col, uint8_t *out);
+                        int method, int d_row, int d_col, uint8_t *out,
+                        float *weight_a_out /* rows x cols float32 or NULL: ImageFusion.getWeightsMatrix parity hook */,
+                        float *weight_b_out);
 
 /* Replaces Stitcher.getStitchByOffset's paste/blend loop (Stitcher.py:433-486) on a device-resident canvas.
  * tiles: n_tiles images of tile_rows x tile_cols x channels u8 (host), placed at rectified offsets (row, col);

@@ -158,6 +158,9 @@ FUSE_METHODS = {"notFuse": 0, "average": 1, "maximum": 2, "minimum": 3, "fadeInA
                 "multiBandBlending": 6}
 
 
+DEVICE_MOSAIC_METHODS = ("notFuse", "average", "maximum", "minimum", "fadeInAndFadeOut", "trigonometric")
+
+
 def _as_i16(a):
     a = np.asarray(a)
     if a.size and (a.min() < -1 or a.max() > 255):
@@ -204,6 +207,38 @@ def mosaic(tiles, tile_origin, roi_rect, pair_offset, method, canvas_shape, devi
     out = np.empty((R, C) if ch == 1 else (R, C, ch), np.uint8)
     check(L.vfsms_mosaic_host(ctx, _vp(T), n, h, w, ch, _vp(org), _vp(roi), _vp(off), m, R, C, _vp(out)), "vfsms_mosaic_host")
     return out
+
+
+def phase_correlate(roi_a, roi_b, device=0):
+    """cv2.phaseCorrelate(np.float64(a), np.float64(b)) as called at Stitcher.py:230 -> ((shift_x, shift_y), response)."""
+    L = _lib.load()
+    ctx = _lib.context(device)
+    A = _as_u8_image(roi_a)
+    B = _as_u8_image(roi_b)
+    if A.shape != B.shape:
+        raise ValueError("phase correlation needs equally sized ROIs")
+    if A.strides != B.strides:
+        A = np.ascontiguousarray(A); B = np.ascontiguousarray(B)
+    out = (ctypes.c_double * 3)()
+    check(L.vfsms_phase_correlate_host(ctx, _vp(A), _vp(B), A.shape[0], A.shape[1], A.strides[0], out), "vfsms_phase_correlate_host")
+    return (float(out[0]), float(out[1])), float(out[2])
+
+
+def orb_detect_and_describe(image, n_features=5000, scale_factor=1.2, n_levels=8, edge_threshold=31, first_level=0, wta_k=2,
+                            patch_size=31, fast_threshold=20, device=0):
+    """-> (kp [N, 8] float32, desc [N, 32] float32 holding byte values) -- appendix/myGpuFeatures.cpp:106-146."""
+    L = _lib.load()
+    ctx = _lib.context(device)
+    img = _as_u8_image(image)
+    h, w = img.shape
+    cap = int(n_features) + 64
+    kp = np.empty((cap, KP_STRIDE), np.float32)
+    desc = np.empty((cap, 32), np.float32)
+    n = ctypes.c_int(0)
+    check(L.vfsms_orb_detect_and_describe(ctx, _vp(img), h, w, img.strides[0], int(n_features), float(scale_factor), int(n_levels),
+                                          int(edge_threshold), int(first_level), int(wta_k), int(patch_size), int(fast_threshold),
+                                          _vp(kp), _vp(desc), cap, ctypes.byref(n)), "vfsms_orb_detect_and_describe")
+    return kp[:n.value].copy(), desc[:n.value].copy()
 
 
 def set_matcher(mode, device=0):

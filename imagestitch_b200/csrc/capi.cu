@@ -17,6 +17,7 @@ void vfsms_set_error(const char *fmt, ...)
 // phase.cu / blend.cu / orb.cu
 void phase_state_destroy(vfsms_ctx *ctx);
 void blend_state_destroy(vfsms_ctx *ctx);
+void orb_state_destroy(vfsms_ctx *ctx);
 
 cudaEvent_t prof_event(vfsms_ctx *ctx)
 {
@@ -108,6 +109,7 @@ void vfsms_destroy(vfsms_ctx *ctx)
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
     phase_state_destroy(ctx);
     blend_state_destroy(ctx);
+    orb_state_destroy(ctx);
     surf_tex_destroy(ctx);
     ctx->tex_dev.release();
     SurfWorkspace &w = ctx->surf;

@@ -147,6 +147,7 @@ struct vfsms_ctx {
     DevBuf tex_dev;
     void *phase_state = nullptr;   // cuFFT plans etc. (phase.cu)
     void *blend_state = nullptr;
+    void *orb_state = nullptr;
 };
 
 // stage timing: events on the launching stream; no-ops unless vfsms_profile_enable(ctx, 1)

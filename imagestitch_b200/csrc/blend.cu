@@ -24,7 +24,7 @@ struct BlendPlan {
 };
 
 struct BlendState {
-    DevBuf a16, b16, out8, plan, col_top, col_bot, w1, w2, wa_out, wb_out, canvas, tile, tiles_all;
+    DevBuf a16, b16, out8, plan, col_top, col_bot, w1, w2, wa_out, wb_out, canvas, tile, tiles_all, pyr;
 };
 
 static BlendState *bstate(vfsms_ctx *ctx)
@@ -38,11 +38,13 @@ void blend_state_destroy(vfsms_ctx *ctx)
     BlendState *s = (BlendState *)ctx->blend_state;
     if (!s) return;
     DevBuf *b[] = { &s->a16, &s->b16, &s->out8, &s->plan, &s->col_top, &s->col_bot, &s->w1, &s->w2, &s->wa_out, &s->wb_out,
-                    &s->canvas, &s->tile, &s->tiles_all };
+                    &s->canvas, &s->tile, &s->tiles_all, &s->pyr };
     for (DevBuf *x : b) x->release();
     delete s;
     ctx->blend_state = nullptr;
 }
+
+static int grid_for(vfsms_ctx *ctx, int64_t n) { int64_t g = (n + 255) / 256; int64_t m = (int64_t)ctx->num_sms * 8; return (int)(g < m ? (g < 1 ? 1 : g) : m); }
 
 // pixel "non-empty" test of getWeightsMatrix: gray: != -1; colour: channel sum != -3 (ImageFusion.py:72,93,...)
 __device__ __forceinline__ bool px_nonempty(const int16_t *p, int ch)
@@ -274,7 +276,6 @@ __global__ void canvas_to_u8_kernel(const int16_t *__restrict__ src, uint8_t *ds
     }
 }
 
-static int grid_for(vfsms_ctx *ctx, int64_t n) { int64_t g = (n + 255) / 256; int64_t m = (int64_t)ctx->num_sms * 8; return (int)(g < m ? (g < 1 ? 1 : g) : m); }
 
 // Core: fuse ROI (A, B int16 on device) -> out8 and/or out16 (may alias A's memory: every pixel is read before written by
 // the same thread).  Asynchronous on st.
@@ -310,14 +311,187 @@ static int fuse_roi_dev(vfsms_ctx *ctx, const int16_t *A, int64_t a_rs, const in
     return 0;
 }
 
+// ---------------------------------------------------------------- multi-band blending (ImageFusion.py:296-367)
+// BlendArbitrary2(A, B, 4): Gaussian pyramids (cv2.pyrDown, float64), Laplacian levels through cv2.pyrUp + resize(INTER_CUBIC)
+// to the finer level's size, constant 0.5 / 0.5 level weights, reconstruction, np.uint8 truncation.  Border rules pinned
+// against cv2 here: pyrDown BORDER_REFLECT_101; pyrUp reflects at the left / top and clamps at the right / bottom.
+__device__ __forceinline__ int refl101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) { if (i < 0) i = -i; else i = 2 * n - 2 - i; }
+    return i;
+}
+
+__global__ void __launch_bounds__(256) pyr_down_kernel(const double *__restrict__ src, int h, int w, double *dst)
+{
+    const int H = (h + 1) / 2, W = (w + 1) / 2;
+    const double k[5] = { 1, 4, 6, 4, 1 };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+        const int y = i / W, x = i - y * W;
+        double acc = 0;
+        for (int ty = 0; ty < 5; ty++) {
+            const double *row = src + (size_t)refl101(2 * y + ty - 2, h) * w;
+            double r = 0;
+            for (int tx = 0; tx < 5; tx++) r += k[tx] * row[refl101(2 * x + tx - 2, w)];
+            acc += k[ty] * r;
+        }
+        dst[i] = acc / 256.0;
+    }
+}
+
+__device__ __forceinline__ int up_idx(int i, int n) { return i < 0 ? refl101(i, n) : (i > n - 1 ? n - 1 : i); }
+
+// cv2.pyrUp: (h, w) -> (2h, 2w)
+__global__ void __launch_bounds__(256) pyr_up_kernel(const double *__restrict__ src, int h, int w, double *dst)
+{
+    const int H = 2 * h, W = 2 * w;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+        const int Y = i / W, X = i - Y * W;
+        const int y = Y >> 1, x = X >> 1;
+        // horizontal pass value at source row r, output column X
+        auto hval = [&](int r) -> double {
+            const double *row = src + (size_t)r * w;
+            if (X & 1) return 4.0 * (row[x] + row[up_idx(x + 1, w)]);
+            return row[up_idx(x - 1, w)] + 6.0 * row[x] + row[up_idx(x + 1, w)];
+        };
+        double v;
+        if (Y & 1) v = 4.0 * (hval(y) + hval(up_idx(y + 1, h)));
+        else v = hval(up_idx(y - 1, h)) + 6.0 * hval(y) + hval(up_idx(y + 1, h));
+        dst[i] = v / 64.0;
+    }
+}
+
+__device__ __forceinline__ void cubic_coeffs(float t, float c[4])
+{
+    const float A = -0.75f;
+    c[0] = ((A * (t + 1) - 5 * A) * (t + 1) + 8 * A) * (t + 1) - 4 * A;
+    c[1] = ((A + 2) * t - (A + 3)) * t * t + 1;
+    c[2] = ((A + 2) * (1 - t) - (A + 3)) * (1 - t) * (1 - t) + 1;
+    c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+// cv2.resize(src, (W, H), INTER_CUBIC) for float64 (identity when the size is unchanged is handled by the caller)
+__global__ void __launch_bounds__(256) resize_cubic_kernel(const double *__restrict__ src, int h, int w, double *dst, int H, int W)
+{
+    const double sx = (double)w / W, sy = (double)h / H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+        const int Y = i / W, X = i - Y * W;
+        float fx = (float)((X + 0.5) * sx - 0.5), fy = (float)((Y + 0.5) * sy - 0.5);
+        const int x0 = (int)floorf(fx), y0 = (int)floorf(fy);
+        float cx[4], cy[4];
+        cubic_coeffs(fx - x0, cx); cubic_coeffs(fy - y0, cy);
+        double acc = 0;
+        for (int ky = 0; ky < 4; ky++) {
+            const double *row = src + (size_t)min(max(y0 - 1 + ky, 0), h - 1) * w;
+            double r = 0;
+            for (int kx = 0; kx < 4; kx++) r += (double)cx[kx] * row[min(max(x0 - 1 + kx, 0), w - 1)];
+            acc += (double)cy[ky] * r;
+        }
+        dst[i] = acc;
+    }
+}
+
+// dst = alpha * a + beta * b   (b may be null)
+__global__ void __launch_bounds__(256) axpby_kernel(double *dst, const double *a, double alpha, const double *b, double beta, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = alpha * a[i] + (b ? beta * b[i] : 0.0);
+}
+
+// Stitcher.fuseImage pre-processing (-1 -> 0, mutual zero fill, Stitcher.py:498-504) + conversion to float64
+__global__ void __launch_bounds__(256) multiband_prepare_kernel(const int16_t *__restrict__ A, int64_t a_rs, const int16_t *__restrict__ B, int64_t b_rs,
+                                                                int rows, int cols, double *da, double *db)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols; i += gridDim.x * blockDim.x) {
+        const int r = i / cols, c = i - r * cols;
+        int a = A[r * a_rs + c], b = B[r * b_rs + c];
+        if (a == -1) a = 0;
+        if (b == -1) b = 0;
+        if (a == 0) a = b;
+        if (b == 0) b = a;
+        da[i] = a; db[i] = b;
+    }
+}
+
+__global__ void __launch_bounds__(256) multiband_store_kernel(const double *__restrict__ src, int rows, int cols, uint8_t *out8, int64_t o_rs,
+                                                              int16_t *out16, int64_t o16_rs)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols; i += gridDim.x * blockDim.x) {
+        const int r = i / cols, c = i - r * cols;
+        const uint8_t v = (uint8_t)(long long)src[i];          // np.uint8(float64): truncation toward zero, wraps like the C cast
+        if (out8) out8[r * o_rs + c] = v;
+        if (out16) out16[r * o16_rs + c] = v;
+    }
+}
+
+static int multiband_dev(vfsms_ctx *ctx, const int16_t *A, int64_t a_rs, const int16_t *B, int64_t b_rs, int rows, int cols,
+                         uint8_t *out8, int64_t o_rs, int16_t *out16, int64_t o16_rs, cudaStream_t st)
+{
+    BlendState *bs = bstate(ctx);
+    const int LEVELS = 4;
+    int hs[LEVELS], wsz[LEVELS];
+    size_t off[LEVELS], tot = 0;
+    hs[0] = rows; wsz[0] = cols;
+    for (int l = 0; l < LEVELS; l++) {
+        if (l) { hs[l] = (hs[l - 1] + 1) / 2; wsz[l] = (wsz[l - 1] + 1) / 2; }
+        off[l] = tot; tot += (size_t)hs[l] * wsz[l];
+    }
+    const size_t big = (size_t)rows * cols * 4 + 64;        // room for a pyrUp of the finest level
+    // layout: gpA | gpB | LC | tmp1 | tmp2
+    int rc;
+    if ((rc = bs->pyr.reserve((tot * 3 + big * 2) * 8))) return rc;
+    double *gA = bs->pyr.as<double>(), *gB = gA + tot, *LC = gB + tot, *t1 = LC + tot, *t2 = t1 + big;
+    StageTimer t(ctx, st, VFSMS_STAGE_BLEND);
+    auto G = [&](int n) { return grid_for(ctx, n); };
+    multiband_prepare_kernel<<<G(rows * cols), 256, 0, st>>>(A, a_rs, B, b_rs, rows, cols, gA, gB);
+    LAUNCH_CHECK(ctx);
+    for (int l = 1; l < LEVELS; l++) {
+        pyr_down_kernel<<<G(hs[l] * wsz[l]), 256, 0, st>>>(gA + off[l - 1], hs[l - 1], wsz[l - 1], gA + off[l]); LAUNCH_CHECK(ctx);
+        pyr_down_kernel<<<G(hs[l] * wsz[l]), 256, 0, st>>>(gB + off[l - 1], hs[l - 1], wsz[l - 1], gB + off[l]); LAUNCH_CHECK(ctx);
+    }
+    // expand(src at level l+1) -> size of level l, into `dst`
+    auto expand = [&](const double *src, int l, double *dst) -> int {
+        const int h = hs[l + 1], w = wsz[l + 1];
+        if (2 * h == hs[l] && 2 * w == wsz[l]) { pyr_up_kernel<<<G(4 * h * w), 256, 0, st>>>(src, h, w, dst); LAUNCH_CHECK(ctx); }
+        else {
+            pyr_up_kernel<<<G(4 * h * w), 256, 0, st>>>(src, h, w, t2); LAUNCH_CHECK(ctx);
+            resize_cubic_kernel<<<G(hs[l] * wsz[l]), 256, 0, st>>>(t2, 2 * h, 2 * w, dst, hs[l], wsz[l]); LAUNCH_CHECK(ctx);
+        }
+        return 0;
+    };
+    // LC[coarsest] = 0.5 gA[3] + 0.5 gB[3];  LC[l] = 0.5 (gA[l] - E(gA[l+1])) + 0.5 (gB[l] - E(gB[l+1]))
+    axpby_kernel<<<G(hs[LEVELS - 1] * wsz[LEVELS - 1]), 256, 0, st>>>(LC + off[LEVELS - 1], gA + off[LEVELS - 1], 0.5, gB + off[LEVELS - 1], 0.5, hs[LEVELS - 1] * wsz[LEVELS - 1]);
+    LAUNCH_CHECK(ctx);
+    for (int l = LEVELS - 2; l >= 0; l--) {
+        const int n = hs[l] * wsz[l];
+        if ((rc = expand(gA + off[l + 1], l, t1))) return rc;
+        axpby_kernel<<<G(n), 256, 0, st>>>(t1, gA + off[l], 1.0, t1, -1.0, n); LAUNCH_CHECK(ctx);             // LA[l]
+        axpby_kernel<<<G(n), 256, 0, st>>>(LC + off[l], t1, 0.5, nullptr, 0.0, n); LAUNCH_CHECK(ctx);
+        if ((rc = expand(gB + off[l + 1], l, t1))) return rc;
+        axpby_kernel<<<G(n), 256, 0, st>>>(t1, gB + off[l], 1.0, t1, -1.0, n); LAUNCH_CHECK(ctx);             // LB[l]
+        axpby_kernel<<<G(n), 256, 0, st>>>(LC + off[l], LC + off[l], 1.0, t1, 0.5, n); LAUNCH_CHECK(ctx);
+    }
+    // reconstruct: out = LC[3]; out = E(out) + LC[l]
+    double *cur = gA;      // reuse gA storage level by level
+    CUDA_TRY(cudaMemcpyAsync(cur + off[LEVELS - 1], LC + off[LEVELS - 1], (size_t)hs[LEVELS - 1] * wsz[LEVELS - 1] * 8, cudaMemcpyDeviceToDevice, st));
+    for (int l = LEVELS - 2; l >= 0; l--) {
+        const int n = hs[l] * wsz[l];
+        if ((rc = expand(cur + off[l + 1], l, t1))) return rc;
+        axpby_kernel<<<G(n), 256, 0, st>>>(cur + off[l], t1, 1.0, LC + off[l], 1.0, n); LAUNCH_CHECK(ctx);
+    }
+    multiband_store_kernel<<<G(rows * cols), 256, 0, st>>>(cur, rows, cols, out8, o_rs, out16, o16_rs);
+    LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 extern "C" {
 
 int vfsms_fuse_roi_host(vfsms_ctx *ctx, const int16_t *a, const int16_t *b, int rows, int cols, int channels, int method,
                         int d_row, int d_col, uint8_t *out, float *wa_out, float *wb_out)
 {
     if (!ctx || !a || !b || !out || rows < 1 || cols < 1 || (channels != 1 && channels != 3)) { vfsms_set_error("fuse_roi: bad arguments"); return VFSMS_E_ARG; }
-    if ((method & 0xff) < VFSMS_FUSE_NONE || (method & 0xff) > VFSMS_FUSE_TRIG) {
-        vfsms_set_error("fuse_roi: method %d is not available through this entry point", method); return VFSMS_E_UNSUPPORTED;
+    if ((method & 0xff) < VFSMS_FUSE_NONE || (method & 0xff) > VFSMS_FUSE_MULTIBAND) { vfsms_set_error("fuse_roi: unknown method %d", method); return VFSMS_E_ARG; }
+    if ((method & 0xff) == VFSMS_FUSE_MULTIBAND && channels != 1) {
+        vfsms_set_error("fuse_roi: multi-band blending is gray only (Stitcher.py:520)"); return VFSMS_E_UNSUPPORTED;
     }
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -336,8 +510,10 @@ int vfsms_fuse_roi_host(vfsms_ctx *ctx, const int16_t *a, const int16_t *b, int 
     CUDA_TRY(cudaMemcpyAsync(bs->a16.p, a, n * 2, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(bs->b16.p, b, n * 2, cudaMemcpyHostToDevice, st));
     const int64_t rs = (int64_t)cols * channels;
-    if ((rc = fuse_roi_dev(ctx, bs->a16.as<int16_t>(), rs, bs->b16.as<int16_t>(), rs, rows, cols, channels, method, d_row, d_col,
-                           bs->out8.as<uint8_t>(), rs, nullptr, 0, dwa, dwb, st))) return rc;
+    if ((method & 0xff) == VFSMS_FUSE_MULTIBAND) {
+        if ((rc = multiband_dev(ctx, bs->a16.as<int16_t>(), rs, bs->b16.as<int16_t>(), rs, rows, cols, bs->out8.as<uint8_t>(), rs, nullptr, 0, st))) return rc;
+    } else if ((rc = fuse_roi_dev(ctx, bs->a16.as<int16_t>(), rs, bs->b16.as<int16_t>(), rs, rows, cols, channels, method, d_row, d_col,
+                                  bs->out8.as<uint8_t>(), rs, nullptr, 0, dwa, dwb, st))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, bs->out8.p, n, cudaMemcpyDeviceToHost, st));
     if (dwa) {
         CUDA_TRY(cudaMemcpyAsync(wa_out, dwa, (size_t)rows * cols * 4, cudaMemcpyDeviceToHost, st));

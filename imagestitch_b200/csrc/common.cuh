@@ -92,6 +92,7 @@ struct SurfPlan {
     float threshold;
     int tile_begin[VFSMS_MAX_OCTAVES + 1];   // prefix of CTA tiles per octave
     int tiles_x[VFSMS_MAX_OCTAVES];
+    int stage_off_min[VFSMS_MAX_OCTAVES], stage_rows[VFSMS_MAX_OCTAVES], stage_cols[VFSMS_MAX_OCTAVES];   // smem footprint of a tile
     SurfLayer layer[VFSMS_MAX_OCTAVES][VFSMS_MAX_LAYERS_PER_OCTAVE];
 };
 
@@ -111,6 +112,7 @@ struct SurfWorkspace {
     DevBuf descT;            // [batch][dim][kp_cap] float, k-major copy for the matcher
     DevBuf counters;         // [batch][4] int32 : n_cand, n_sorted, n_final, flags
     DevBuf prefix;           // [batch+1] int32 prefix of n_final
+    DevBuf hist;             // [batch][2048] response histogram + [batch] thresholds
 };
 
 struct MatchWorkspace {

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <float.h>
+#include <algorithm>
 #include <map>
 #include <tuple>
 #include <vector>
@@ -109,6 +110,17 @@ int surf_build_plan(SurfPlan *plan, int rows, int cols, const vfsms_surf_params 
             resize_haar_host(dx_s, L.dx, 3, 9, L.size);
             resize_haar_host(dy_s, L.dy, 3, 9, L.size);
             resize_haar_host(dxy_s, L.dxy, 4, 9, L.size);
+        }
+        {   // integral footprint of one tile (haloed) over all layers: offsets relative to (tile origin - 1) * step
+            int off_min = 0, off_max = 0;
+            for (int l = 0; l < plan->n_layers; l++) {
+                const SurfLayer &L = plan->layer[o][l];
+                off_min = std::min(off_min, -L.margin * step);
+                off_max = std::max(off_max, -L.margin * step + L.size);
+            }
+            plan->stage_off_min[o] = off_min;
+            plan->stage_rows[o] = (HT_Y + 1) * step + (off_max - off_min) + 1;
+            plan->stage_cols[o] = (HT_X + 1) * step + (off_max - off_min) + 1;
         }
         // NMS positions exist only inside [margin_min, l - margin_min): skip tiles that cannot hold a maximum
         int tx = ceil_div(lcols > 0 ? lcols : 1, HT_X), ty = ceil_div(lrows > 0 ? lrows : 1, HT_Y);
@@ -232,17 +244,6 @@ __global__ void __launch_bounds__(256) integral_fix_kernel(int rows, int cols, i
 }
 
 // ---------------------------------------------------------------- K2: Hessian layers + NMS + interpolation
-__device__ __forceinline__ float haar_response(const int32_t *__restrict__ o, int W, const HaarBox *f, int n)
-{
-    double d = 0;
-    for (int k = 0; k < n; k++) {
-        const int32_t v = __ldg(o + f[k].y1 * W + f[k].x1) + __ldg(o + f[k].y2 * W + f[k].x2)
-                        - __ldg(o + f[k].y2 * W + f[k].x1) - __ldg(o + f[k].y1 * W + f[k].x2);
-        d += (double)((float)v * f[k].w);      // int * float rounds to float first, like the CPU expression
-    }
-    return (float)d;
-}
-
 __device__ __forceinline__ bool solve3(const float a[3][3], const float b[3], float x[3])
 {
     float d = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1])
@@ -258,19 +259,67 @@ __device__ __forceinline__ bool solve3(const float a[3][3], const float b[3], fl
               + a[0][2] * (a[1][0] * b[2] - b[1] * a[2][0]));
     x[2] = d * (a[0][0] * (a[1][1] * b[2] - b[1] * a[2][1])
               - a[0][1] * (a[1][0] * b[2] - b[1] * a[2][0])
-              + b[0] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]));
+              + b[0] * (a[1][0] * a[2][1] - a[1][1] * b[2]));
     return true;
 }
 
+// Box responses of one sample from 32 integral reads (the 10 boxes share their corners: Dxx 2x4, Dyy 4x2, Dxy 4x4 grid).
+// `o` points at the sample origin inside an int32 array of row pitch P (global integral or its shared-memory copy).
+// Each box sum is an exact integer; products and the double accumulation keep the CPU expression's rounding.
+template <typename Ptr>
+__device__ __forceinline__ void hessian_responses(Ptr o, int P, const SurfLayer &L, float &dx, float &dy, float &dxy)
+{
+    {   // Dxx: rows y1, y2; column edges x0 < x1 < x2 < x3
+        const int y1 = L.dx[0].y1 * P, y2 = L.dx[0].y2 * P;
+        const int x0 = L.dx[0].x1, x1 = L.dx[1].x1, x2 = L.dx[2].x1, x3 = L.dx[2].x2;
+        const int t0 = o[y1 + x0], t1 = o[y1 + x1], t2 = o[y1 + x2], t3 = o[y1 + x3];
+        const int b0 = o[y2 + x0], b1 = o[y2 + x1], b2 = o[y2 + x2], b3 = o[y2 + x3];
+        double d = 0;
+        d += (double)((float)(t0 + b1 - b0 - t1) * L.dx[0].w);
+        d += (double)((float)(t1 + b2 - b1 - t2) * L.dx[1].w);
+        d += (double)((float)(t2 + b3 - b2 - t3) * L.dx[2].w);
+        dx = (float)d;
+    }
+    {   // Dyy: columns x1, x2; row edges y0 < y1 < y2 < y3
+        const int x1 = L.dy[0].x1, x2 = L.dy[0].x2;
+        const int y0 = L.dy[0].y1 * P, y1 = L.dy[1].y1 * P, y2 = L.dy[2].y1 * P, y3 = L.dy[2].y2 * P;
+        const int l0 = o[y0 + x1], l1 = o[y1 + x1], l2 = o[y2 + x1], l3 = o[y3 + x1];
+        const int r0 = o[y0 + x2], r1 = o[y1 + x2], r2 = o[y2 + x2], r3 = o[y3 + x2];
+        double d = 0;
+        d += (double)((float)(l0 + r1 - l1 - r0) * L.dy[0].w);
+        d += (double)((float)(l1 + r2 - l2 - r1) * L.dy[1].w);
+        d += (double)((float)(l2 + r3 - l3 - r2) * L.dy[2].w);
+        dy = (float)d;
+    }
+    {   // Dxy: 4x4 corner grid, boxes (x01,y01) (x23,y01) (x01,y23) (x23,y23)
+        const int xa = L.dxy[0].x1, xb = L.dxy[0].x2, xc = L.dxy[1].x1, xd = L.dxy[1].x2;
+        const int ya = L.dxy[0].y1 * P, yb = L.dxy[0].y2 * P, yc = L.dxy[2].y1 * P, yd = L.dxy[2].y2 * P;
+        const int aa = o[ya + xa], ab = o[ya + xb], ac = o[ya + xc], ad = o[ya + xd];
+        const int ba = o[yb + xa], bb = o[yb + xb], bc = o[yb + xc], bd = o[yb + xd];
+        const int ca = o[yc + xa], cb = o[yc + xb], cc = o[yc + xc], cd = o[yc + xd];
+        const int da = o[yd + xa], db = o[yd + xb], dc = o[yd + xc], dd = o[yd + xd];
+        double d = 0;
+        d += (double)((float)(aa + bb - ba - ab) * L.dxy[0].w);
+        d += (double)((float)(ac + bd - bc - ad) * L.dxy[1].w);
+        d += (double)((float)(ca + db - da - cb) * L.dxy[2].w);
+        d += (double)((float)(cc + dd - dc - cd) * L.dxy[3].w);
+        dxy = (float)d;
+    }
+}
+
+// STAGE = true: the integral footprint of the tile (all layers of the octave) is copied to shared memory once and the
+// 32 corner reads per sample-layer become LDS (octaves whose footprint fits: 0 and 1); false: reads go to L1/L2.
+template <bool STAGE>
 __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_constant__ SurfPlan plan,
                                                                  const int32_t *__restrict__ integral,
-                                                                 float *cand, int32_t *counters, int cand_cap)
+                                                                 float *cand, int32_t *counters, int cand_cap, int tile_offset)
 {
-    extern __shared__ float s_det[];     // [n_layers][HT_Y+2][HT_X+2]
+    extern __shared__ float s_dyn[];
     const int b = blockIdx.y;
+    const int tile_id = blockIdx.x + tile_offset;
     int o = 0;
-    while (o + 1 < plan.n_octaves && (int)blockIdx.x >= plan.tile_begin[o + 1]) o++;
-    const int t = blockIdx.x - plan.tile_begin[o];
+    while (o + 1 < plan.n_octaves && tile_id >= plan.tile_begin[o + 1]) o++;
+    const int t = tile_id - plan.tile_begin[o];
     const int tile_x = t % plan.tiles_x[o], tile_y = t / plan.tiles_x[o];
     const int step = 1 << o;
     const int lrows = plan.rows / step, lcols = plan.cols / step;
@@ -278,7 +327,21 @@ __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_co
     const int32_t *I = integral + (size_t)b * (plan.rows + 1) * W;
     const int nl = plan.n_layers;
     constexpr int SW = HT_X + 2, SH = HT_Y + 2;
+    float *s_det = s_dyn;                                   // [n_layers][HT_Y+2][HT_X+2]
+    int32_t *s_int = (int32_t *)(s_dyn + nl * SW * SH);     // [stage_rows][stage_cols] (STAGE only)
     const int i0 = tile_y * HT_Y - 1, j0 = tile_x * HT_X - 1;   // layer coords of the smem origin
+    const int RW = plan.stage_cols[o];
+    const int r_base = i0 * step + plan.stage_off_min[o], c_base = j0 * step + plan.stage_off_min[o];
+
+    if (STAGE) {
+        const int RH = plan.stage_rows[o];
+        for (int idx = threadIdx.x; idx < RH * RW; idx += HT_THREADS) {
+            const int rr = idx / RW, cc = idx - rr * RW;
+            const int r = min(max(r_base + rr, 0), plan.rows), c = min(max(c_base + cc, 0), plan.cols);
+            s_int[idx] = __ldg(I + (size_t)r * W + c);
+        }
+        __syncthreads();
+    }
 
     // phase 1: det for every layer over the haloed tile
     for (int idx = threadIdx.x; idx < SW * SH; idx += HT_THREADS) {
@@ -289,10 +352,9 @@ __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_co
             const int si = li - L.margin, sj = lj - L.margin;
             float det = 0.f;
             if (si >= 0 && si < L.samples_i && sj >= 0 && sj < L.samples_j) {
-                const int32_t *org = I + (size_t)(si * step) * W + sj * step;
-                const float dx = haar_response(org, W, L.dx, 3);
-                const float dy = haar_response(org, W, L.dy, 3);
-                const float dxy = haar_response(org, W, L.dxy, 4);
+                float dx, dy, dxy;
+                if (STAGE) hessian_responses(s_int + (si * step - r_base) * RW + (sj * step - c_base), RW, L, dx, dy, dxy);
+                else hessian_responses(I + (size_t)(si * step) * W + sj * step, W, L, dx, dy, dxy);
                 float tt = 0.81f * dxy;
                 tt = tt * dxy;
                 det = dx * dy - tt;
@@ -353,8 +415,9 @@ __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_co
             py += x[1] * step;
             psz = (float)__float2int_rn(psz + x[2] * ds);
             // laplacian sign: recompute trace at the maximum (rare path)
-            const int32_t *org = I + (size_t)((li - L.margin) * step) * W + (lj - L.margin) * step;
-            const float trace = haar_response(org, W, L.dx, 3) + haar_response(org, W, L.dy, 3);
+            float tdx, tdy, tdxy;
+            hessian_responses(I + (size_t)((li - L.margin) * step) * W + (lj - L.margin) * step, W, L, tdx, tdy, tdxy);
+            const float trace = tdx + tdy;
             const int slot = atomicAdd(&counters[b * 4 + 0], 1);
             if (slot < cand_cap) {
                 float4 *dst = (float4 *)(cand + ((size_t)b * cand_cap + slot) * KP_STRIDE);
@@ -391,52 +454,119 @@ __device__ __forceinline__ bool key_before(const SortKey &a, const SortKey &b)
     return a.k1 > b.k1 || (a.k1 == b.k1 && a.k2 > b.k2);
 }
 
-// grid: flattened (image, chunk) work items, grid-strided.  n per image read from counters.
-__global__ void __launch_bounds__(256) rank_sort_kernel(const float *__restrict__ cand, float *sorted, int32_t *counters,
+// K3a: when only the strongest max_features survive, most candidates never need a rank.  Histogram the responses on
+// their top 11 bits (positive floats order like their bit patterns), pick the bin holding the max_features-th
+// largest, and copy everything at or above that bin (K + at most one bin) into the staging buffer.
+#define RH_BINS 2048
+__global__ void __launch_bounds__(256) response_hist_kernel(const float *__restrict__ cand, const int32_t *__restrict__ counters, int cand_cap,
+                                                            int *hist)
+{
+    const int b = blockIdx.y;
+    const int n = min(counters[b * 4 + 0], cand_cap);
+    const float *C = cand + (size_t)b * cand_cap * KP_STRIDE;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&hist[b * RH_BINS + (__float_as_uint(C[(size_t)i * KP_STRIDE + KP_RESPONSE]) >> 20)], 1);
+}
+
+// one warp per image: smallest bin index whose suffix count reaches max_features (0 = keep everything)
+__global__ void response_threshold_kernel(const int *__restrict__ hist, int32_t *counters, int cand_cap, int max_features, int batch, unsigned *thr_bits)
+{
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= batch) return;
+    const int n = min(counters[b * 4 + 0], cand_cap);
+    unsigned thr = 0;
+    if (max_features > 0 && n > max_features) {
+        int cum = 0, found = -1;
+        for (int base = RH_BINS - 32; base >= 0 && found < 0; base -= 32) {
+            const int v = hist[b * RH_BINS + base + lane];
+            // suffix sums within the 32-bin group, high bins first
+            int suf = v;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += t; }
+            const unsigned hit = __ballot_sync(0xffffffffu, cum + suf >= max_features);
+            if (hit) found = base + 31 - __clz(hit);          // highest bin of the group that already reaches the target
+            cum += __shfl_sync(0xffffffffu, suf, 0);
+        }
+        thr = found < 0 ? 0u : ((unsigned)found << 20);
+    }
+    if (lane == 0) thr_bits[b] = thr;
+}
+
+__global__ void __launch_bounds__(256) response_filter_kernel(const float *__restrict__ cand, float *staged, int32_t *counters, int cand_cap,
+                                                              const unsigned *__restrict__ thr_bits)
+{
+    const int b = blockIdx.y;
+    const int n = min(counters[b * 4 + 0], cand_cap);
+    const unsigned thr = thr_bits[b];
+    const float *C = cand + (size_t)b * cand_cap * KP_STRIDE;
+    float *S = staged + (size_t)b * cand_cap * KP_STRIDE;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (__float_as_uint(C[(size_t)i * KP_STRIDE + KP_RESPONSE]) < thr) continue;
+        const int slot = atomicAdd(&counters[b * 4 + 1], 1);
+        const float4 *src = (const float4 *)(C + (size_t)i * KP_STRIDE);
+        float4 *dst = (float4 *)(S + (size_t)slot * KP_STRIDE);
+        dst[0] = src[0]; dst[1] = src[1];
+    }
+}
+
+// K3: rank of every staged candidate under KeypointGreater (any arrival order in -> the same order out).
+// src = staged [n_staged = counters[1]], dst = ordered; n_keep written back to counters[1].
+__global__ void __launch_bounds__(256) rank_sort_kernel(const float *__restrict__ src, float *dst, int32_t *counters,
                                                         int cand_cap, int batch, int max_features)
 {
-    __shared__ SortKey s_keys[1024];
+    __shared__ unsigned long long s_k1[1024];
     const int chunks_per_img = ceil_div(cand_cap, 256);
     for (int item = blockIdx.x; item < batch * chunks_per_img; item += gridDim.x) {
         const int b = item / chunks_per_img, chunk = item - b * chunks_per_img;
         const int n_raw = counters[b * 4 + 0];
-        const int n = min(n_raw, cand_cap);
+        const int n = counters[b * 4 + 1];
         if (chunk * 256 >= n) continue;             // uniform per CTA
-        const float *C = cand + (size_t)b * cand_cap * KP_STRIDE;
+        const float *C = src + (size_t)b * cand_cap * KP_STRIDE;
         const int i = chunk * 256 + threadIdx.x;
         SortKey mine; mine.k1 = 0; mine.k2 = 0;
         if (i < n) mine = make_key(C + (size_t)i * KP_STRIDE);
-        int rank = 0;
+        int rank = 0, ties = 0;
         for (int base = 0; base < n; base += 1024) {
             __syncthreads();
             for (int q = threadIdx.x; q < 1024; q += 256) {
                 const int j = base + q;
-                SortKey k; k.k1 = 0; k.k2 = 0;
-                if (j < n) k = make_key(C + (size_t)j * KP_STRIDE);
-                s_keys[q] = k;
+                s_k1[q] = j < n ? make_key(C + (size_t)j * KP_STRIDE).k1 : 0ull;
             }
             __syncthreads();
             const int m = min(1024, n - base);
             if (i < n) {
+#pragma unroll 4
                 for (int q = 0; q < m; q++) {
-                    const SortKey k = s_keys[q];
-                    const int j = base + q;
-                    rank += (key_before(k, mine) || (k.k1 == mine.k1 && k.k2 == mine.k2 && j < i)) ? 1 : 0;
+                    const unsigned long long k = s_k1[q];
+                    rank += k > mine.k1 ? 1 : 0;
+                    ties += k == mine.k1 ? 1 : 0;
                 }
+            }
+        }
+        if (i < n && ties > 1) {
+            // equal (response, size, octave): order by (y desc, x asc), then arrival index -- rare, resolved from global memory
+            for (int j = 0; j < n; j++) {
+                const SortKey k = make_key(C + (size_t)j * KP_STRIDE);
+                if (k.k1 == mine.k1 && (k.k2 > mine.k2 || (k.k2 == mine.k2 && j < i))) rank++;
             }
         }
         const int n_keep = (max_features > 0) ? min(n, max_features) : n;
         if (i < n && rank < n_keep) {
-            const float4 *src = (const float4 *)(C + (size_t)i * KP_STRIDE);
-            float4 *dst = (float4 *)(sorted + ((size_t)b * cand_cap + rank) * KP_STRIDE);
-            dst[0] = src[0]; dst[1] = src[1];
-        }
-        if (chunk == 0 && threadIdx.x == 0) {
-            counters[b * 4 + 1] = n_keep;
-            if (n_raw > cand_cap) counters[b * 4 + 3] |= 1;
+            const float4 *s4 = (const float4 *)(C + (size_t)i * KP_STRIDE);
+            float4 *d4 = (float4 *)(dst + ((size_t)b * cand_cap + rank) * KP_STRIDE);
+            d4[0] = s4[0]; d4[1] = s4[1];
         }
         __syncthreads();
+        if (chunk == 0 && threadIdx.x == 0 && n_raw > cand_cap) counters[b * 4 + 3] |= 1;
     }
+}
+
+// after every chunk of an image has ranked: publish n_keep (separate tiny kernel: chunks of one image run in different CTAs)
+__global__ void rank_finalize_kernel(int32_t *counters, int batch, int max_features)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const int n = counters[b * 4 + 1];
+    counters[b * 4 + 1] = (max_features > 0) ? min(n, max_features) : n;
 }
 
 // ---------------------------------------------------------------- K3b: drop keypoints that cannot be oriented, keep order
@@ -1191,6 +1321,7 @@ int surf_reserve(vfsms_ctx *ctx, int batch, int rows, int cols, const vfsms_surf
     if ((rc = ws.counters.reserve((size_t)batch * 16 + 16))) return rc;
     if ((rc = ws.prefix.reserve((size_t)(batch + 1) * 4))) return rc;
     if ((rc = ws.descT.reserve((size_t)batch * kp_cap * dim * 4))) return rc;
+    if ((rc = ws.hist.reserve((size_t)batch * (RH_BINS + 1) * 4))) return rc;
     ws.max_features = max_features;
     ws.batch = batch; ws.rows = rows; ws.cols = cols; ws.cand_cap = cand_cap; ws.kp_cap = kp_cap; ws.dim = dim;
     return 0;
@@ -1248,23 +1379,55 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
     const int total_tiles = plan.tile_begin[plan.n_octaves];
     if (total_tiles > 0) {
         StageTimer t_h(ctx, st, VFSMS_STAGE_HESSIAN);
-        const size_t smem_h = (size_t)plan.n_layers * (HT_X + 2) * (HT_Y + 2) * 4;
-        hessian_nms_kernel<<<dim3(total_tiles, batch), HT_THREADS, smem_h, st>>>(plan, ws.integral.as<int32_t>(),
-                                                                                 ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap);
-        LAUNCH_CHECK(ctx);
+        const size_t smem_det = (size_t)plan.n_layers * (HT_X + 2) * (HT_Y + 2) * 4;
+        // octaves whose integral footprint fits in shared memory next to the det tile (two CTAs per SM)
+        int o_split = 0; size_t smem_stage = 0;
+        while (o_split < plan.n_octaves && smem_det + (size_t)plan.stage_rows[o_split] * plan.stage_cols[o_split] * 4 <= 110 * 1024) {
+            smem_stage = std::max(smem_stage, (size_t)plan.stage_rows[o_split] * plan.stage_cols[o_split] * 4);
+            o_split++;
+        }
+        static bool attr_h = false;
+        if (!attr_h) {
+            CUDA_TRY(cudaFuncSetAttribute(hessian_nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+            attr_h = true;
+        }
+        const int tiles_staged = plan.tile_begin[o_split];
+        if (tiles_staged > 0) {
+            hessian_nms_kernel<true><<<dim3(tiles_staged, batch), HT_THREADS, smem_det + smem_stage, st>>>(plan, ws.integral.as<int32_t>(),
+                ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap, 0);
+            LAUNCH_CHECK(ctx);
+        }
+        if (total_tiles > tiles_staged) {
+            hessian_nms_kernel<false><<<dim3(total_tiles - tiles_staged, batch), HT_THREADS, smem_det, st>>>(plan, ws.integral.as<int32_t>(),
+                ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap, tiles_staged);
+            LAUNCH_CHECK(ctx);
+        }
     }
     const int max_features = ws.max_features;
     {
         StageTimer t_s(ctx, st, VFSMS_STAGE_SORT);
+        int *hist = ws.hist.as<int>();
+        unsigned *thr_bits = (unsigned *)(hist + (size_t)batch * RH_BINS);
+        CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)batch * RH_BINS * 4, st));
+        const int gx = min(ceil_div(ws.cand_cap, 256), 64);
+        response_hist_kernel<<<dim3(gx, batch), 256, 0, st>>>(ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap, hist);
+        LAUNCH_CHECK(ctx);
+        response_threshold_kernel<<<ceil_div(batch, 8), 256, 0, st>>>(hist, ws.counters.as<int32_t>(), ws.cand_cap, max_features, batch, thr_bits);
+        LAUNCH_CHECK(ctx);
+        response_filter_kernel<<<dim3(gx, batch), 256, 0, st>>>(ws.cand.as<float>(), ws.sorted.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap, thr_bits);
+        LAUNCH_CHECK(ctx);
+        // staged (ws.sorted) -> ordered (ws.cand, whose raw content is no longer needed)
         const int chunks = ceil_div(ws.cand_cap, 256) * batch;
         const int grid = min(chunks, ctx->num_sms * 8);
-        rank_sort_kernel<<<grid, 256, 0, st>>>(ws.cand.as<float>(), ws.sorted.as<float>(), ws.counters.as<int32_t>(),
+        rank_sort_kernel<<<grid, 256, 0, st>>>(ws.sorted.as<float>(), ws.cand.as<float>(), ws.counters.as<int32_t>(),
                                               ws.cand_cap, batch, max_features);
+        LAUNCH_CHECK(ctx);
+        rank_finalize_kernel<<<ceil_div(batch, 256), 256, 0, st>>>(ws.counters.as<int32_t>(), batch, max_features);
         LAUNCH_CHECK(ctx);
     }
     {
     StageTimer t_c(ctx, st, VFSMS_STAGE_COMPACT);
-    validate_compact_kernel<<<batch, 1024, 0, st>>>(ws.sorted.as<float>(), ws.kp.as<float>(), ws.counters.as<int32_t>(),
+    validate_compact_kernel<<<batch, 1024, 0, st>>>(ws.cand.as<float>(), ws.kp.as<float>(), ws.counters.as<int32_t>(),
                                                     ws.cand_cap, ws.kp_cap, rows, cols, p->upright);
     LAUNCH_CHECK(ctx);
     prefix_kernel<<<1, 32, 0, st>>>(ws.counters.as<int32_t>(), ws.prefix.as<int32_t>(), batch);

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <float.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <map>
 #include <tuple>
@@ -259,7 +260,7 @@ __device__ __forceinline__ bool solve3(const float a[3][3], const float b[3], fl
               + a[0][2] * (a[1][0] * b[2] - b[1] * a[2][0]));
     x[2] = d * (a[0][0] * (a[1][1] * b[2] - b[1] * a[2][1])
               - a[0][1] * (a[1][0] * b[2] - b[1] * a[2][0])
-              + b[0] * (a[1][0] * a[2][1] - a[1][1] * b[2]));
+              + b[0] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]));
     return true;
 }
 
@@ -1382,7 +1383,8 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         const size_t smem_det = (size_t)plan.n_layers * (HT_X + 2) * (HT_Y + 2) * 4;
         // octaves whose integral footprint fits in shared memory next to the det tile (two CTAs per SM)
         int o_split = 0; size_t smem_stage = 0;
-        while (o_split < plan.n_octaves && smem_det + (size_t)plan.stage_rows[o_split] * plan.stage_cols[o_split] * 4 <= 110 * 1024) {
+        static const bool no_stage = getenv("VFSMS_HESSIAN_UNSTAGED") != nullptr;     // debugging aid
+        while (!no_stage && o_split < plan.n_octaves && smem_det + (size_t)plan.stage_rows[o_split] * plan.stage_cols[o_split] * 4 <= 110 * 1024) {
             smem_stage = std::max(smem_stage, (size_t)plan.stage_rows[o_split] * plan.stage_cols[o_split] * 4);
             o_split++;
         }

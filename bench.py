@@ -235,6 +235,14 @@ def main():
 
     # ---- roofline of the dominant stage (CUDA-event time inside the timed region)
     peaks = load_peaks()
+    # mean window area of the descriptor stage (win = floor(21 * 1.2 * size / 9)), from the keypoints of one ROI of this workload
+    kp_probe, _ = gpu.surf_detect_and_describe(nA[0], params=params, device=local)
+    win = np.floor(np.float32(21) * (kp_probe[:, 2] * np.float32(1.2) / np.float32(9.0))).astype(np.int64)
+    mean_win2 = float((win * win).mean()) if len(win) else 0.0
+    traffic_db = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic_ncu.json")
+    if os.path.exists(tpath):
+        traffic_db = json.load(open(tpath))
     stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in stages.items() if v[1] > 0}
     dom = max(stage_ms, key=stage_ms.get)
     D = 128
@@ -244,7 +252,8 @@ def main():
         # B_det ~ 88.7 B/px (u8 in + integral w/r + det/trace w + det r) over all 2P ROI images
         "integral": ("hbm", (1 + 4) * px * imgs),
         "hessian_nms": ("hbm", (4 + 2 * 4 * 5 * 1.328 + 4 * 5 * 1.328) * px * imgs),
-        "orient_describe": ("hbm", sum((113 * 16 * 4 + 60 * 60 + 4 * D + 28) * n for n in (mean_na, mean_nb)) * P),
+        # B_kp = 113*16*4 (orientation Haar gathers) + win^2 (u8 window) + 4*D + 28 per keypoint
+        "orient_describe": ("hbm", sum((113 * 16 * 4 + mean_win2 + 4 * D + 28) * n for n in (mean_na, mean_nb)) * P),
         "match_knn2": ("tensor", 2.0 * mean_na * mean_nb * D * P),
         "match_tc": ("tensor", 2.0 * mean_na * mean_nb * D * P),
     }
@@ -255,15 +264,28 @@ def main():
         if bound == "hbm":
             ach = work / t / 1e9
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                    "traffic": None, "peak_source": peaks["source"], "algorithmic_bytes_per_launch": work}
+                    "traffic": traffic_db.get(dom, {}).get("dram_bytes_per_launch_P%d" % P), "peak_source": peaks["source"],
+                    "algorithmic_bytes_per_launch": work, "mean_window_area_px": mean_win2,
+                    "note": "issue-bound, not HBM-bound: exact CPU-order arithmetic costs ~70 instructions per window sample (profiles/)"}
         else:
             ach = work / t / 1e12
             roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic_db.get(dom, {}).get("dram_bytes_per_launch_P%d" % P),
+                    "peak_source": peaks["source"] + " (sustained)",
                     "algorithmic_flops_per_launch": work,
                     "matcher_gbs": (4 * D * (mean_na + mean_nb) + 16 * mean_na) * P / t / 1e9}
     else:
         roof = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None}
+
+    # the matcher's own roofline (tensor pipe), reported beside the dominant stage
+    matcher = None
+    if "match_tc" in stage_ms:
+        tm = stage_ms["match_tc"] * 1e-3
+        fl = 2.0 * mean_na * mean_nb * D * P
+        matcher = {"stage_ms": stage_ms["match_tc"], "algorithmic_tflops": fl / tm / 1e12, "frac_of_bf16_sustained": fl / tm / 1e12 / peaks["bf16_tflops_sustained"],
+                   "gbs": (4 * D * (mean_na + mean_nb) + 16 * mean_na) * P / tm / 1e9,
+                   "note": "stage = split + tcgen05 GEMM + exact rescoring + fallback; the GEMM executes 3.5x the algorithmic FLOPs (3-term split-bf16 + norm columns)"}
+    surf_kps = (mean_na + mean_nb) * P * world / (sum(stage_ms.get(k, 0) for k in ("integral", "hessian_nms", "rank_sort", "validate_compact", "orient_describe")) * 1e-3)
 
     # ---- CPU baseline on a bounded sample of the same workload (rank 0, N = 1 only)
     cpu = None
@@ -291,7 +313,7 @@ def main():
            "clocks": clk, "gpu_launches": int(launches),
            "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * P * L * TILE), "d2h_bytes_per_step": int(P * 32),
                    "steps": e2e_steps},
-           "roofline": roof, "stages_ms_per_step": stage_ms}
+           "roofline": roof, "stages_ms_per_step": stage_ms, "matcher": matcher, "surf_keypoints_per_s": surf_kps}
     if cpu:
         out["cpu_baseline"] = cpu
     print(json.dumps(out), flush=True)

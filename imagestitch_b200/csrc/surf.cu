@@ -336,10 +336,11 @@ __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_co
 
     if (STAGE) {
         const int RH = plan.stage_rows[o];
-        for (int idx = threadIdx.x; idx < RH * RW; idx += HT_THREADS) {
-            const int rr = idx / RW, cc = idx - rr * RW;
-            const int r = min(max(r_base + rr, 0), plan.rows), c = min(max(c_base + cc, 0), plan.cols);
-            s_int[idx] = __ldg(I + (size_t)r * W + c);
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int rr = warp; rr < RH; rr += HT_THREADS / 32) {           // one warp per footprint row: no index division
+            const int32_t *src = I + (size_t)min(max(r_base + rr, 0), plan.rows) * W;
+            int32_t *dst = s_int + rr * RW;
+            for (int cc = lane; cc < RW; cc += 32) dst[cc] = __ldg(src + min(max(c_base + cc, 0), plan.cols));
         }
         __syncthreads();
     }
@@ -371,12 +372,12 @@ __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_co
         const int li = tile_y * HT_Y + ty, lj = tile_x * HT_X + tx;
         if (li >= lrows || lj >= lcols) continue;
         for (int l = 1; l < nl - 1; l++) {
+            const float *c1 = s_det + (l * SH + ty + 1) * SW + tx + 1;
+            const float val0 = c1[0];
+            if (!(val0 > plan.threshold)) continue;                      // cheapest test first: most samples stop here
             const SurfLayer &L = plan.layer[o][l];
             const int margin = (plan.layer[o][l + 1].size / 2) / step + 1;
             if (li < margin || li >= lrows - margin || lj < margin || lj >= lcols - margin) continue;
-            const float *c1 = s_det + (l * SH + ty + 1) * SW + tx + 1;
-            const float val0 = c1[0];
-            if (!(val0 > plan.threshold)) continue;
             const float *c0 = c1 - SH * SW, *c2 = c1 + SH * SW;
             float N9[3][9];
             const float *cs[3] = { c0, c1, c2 };
@@ -462,11 +463,16 @@ __device__ __forceinline__ bool key_before(const SortKey &a, const SortKey &b)
 __global__ void __launch_bounds__(256) response_hist_kernel(const float *__restrict__ cand, const int32_t *__restrict__ counters, int cand_cap,
                                                             int *hist)
 {
+    __shared__ int s_h[RH_BINS];          // responses of one image crowd into a few exponent bins: privatise per CTA
     const int b = blockIdx.y;
     const int n = min(counters[b * 4 + 0], cand_cap);
     const float *C = cand + (size_t)b * cand_cap * KP_STRIDE;
+    for (int i = threadIdx.x; i < RH_BINS; i += blockDim.x) s_h[i] = 0;
+    __syncthreads();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        atomicAdd(&hist[b * RH_BINS + (__float_as_uint(C[(size_t)i * KP_STRIDE + KP_RESPONSE]) >> 20)], 1);
+        atomicAdd(&s_h[__float_as_uint(C[(size_t)i * KP_STRIDE + KP_RESPONSE]) >> 20], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < RH_BINS; i += blockDim.x) if (s_h[i]) atomicAdd(&hist[b * RH_BINS + i], s_h[i]);
 }
 
 // one warp per image: smallest bin index whose suffix count reaches max_features (0 = keep everything)
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__(256) response_filter_kernel(const float *__res
 __global__ void __launch_bounds__(256) rank_sort_kernel(const float *__restrict__ src, float *dst, int32_t *counters,
                                                         int cand_cap, int batch, int max_features)
 {
-    __shared__ unsigned long long s_k1[1024];
+    __shared__ unsigned s_r[2048];                 // order-preserving response bits: the hot loop compares 32-bit words only
     const int chunks_per_img = ceil_div(cand_cap, 256);
     for (int item = blockIdx.x; item < batch * chunks_per_img; item += gridDim.x) {
         const int b = item / chunks_per_img, chunk = item - b * chunks_per_img;
@@ -525,29 +531,28 @@ __global__ void __launch_bounds__(256) rank_sort_kernel(const float *__restrict_
         const int i = chunk * 256 + threadIdx.x;
         SortKey mine; mine.k1 = 0; mine.k2 = 0;
         if (i < n) mine = make_key(C + (size_t)i * KP_STRIDE);
-        int rank = 0, ties = 0;
-        for (int base = 0; base < n; base += 1024) {
+        int rank = 0;
+        const unsigned my_r = (unsigned)(mine.k1 >> 32);
+        for (int base = 0; base < n; base += 2048) {
             __syncthreads();
-            for (int q = threadIdx.x; q < 1024; q += 256) {
+            for (int q = threadIdx.x; q < 2048; q += 256) {
                 const int j = base + q;
-                s_k1[q] = j < n ? make_key(C + (size_t)j * KP_STRIDE).k1 : 0ull;
+                s_r[q] = j < n ? f2ord(C[(size_t)j * KP_STRIDE + KP_RESPONSE]) : 0u;
             }
             __syncthreads();
-            const int m = min(1024, n - base);
+            const int m = min(2048, n - base);
             if (i < n) {
-#pragma unroll 4
+#pragma unroll 8
                 for (int q = 0; q < m; q++) {
-                    const unsigned long long k = s_k1[q];
-                    rank += k > mine.k1 ? 1 : 0;
-                    ties += k == mine.k1 ? 1 : 0;
+                    const unsigned k = s_r[q];
+                    rank += k > my_r ? 1 : 0;
+                    if (k == my_r && base + q != i) {
+                        // equal response (rare): the full KeypointGreater order -- size, octave, y desc, x asc -- then arrival index
+                        const int j = base + q;
+                        const SortKey kj = make_key(C + (size_t)j * KP_STRIDE);
+                        if (kj.k1 > mine.k1 || (kj.k1 == mine.k1 && (kj.k2 > mine.k2 || (kj.k2 == mine.k2 && j < i)))) rank++;
+                    }
                 }
-            }
-        }
-        if (i < n && ties > 1) {
-            // equal (response, size, octave): order by (y desc, x asc), then arrival index -- rare, resolved from global memory
-            for (int j = 0; j < n; j++) {
-                const SortKey k = make_key(C + (size_t)j * KP_STRIDE);
-                if (k.k1 == mine.k1 && (k.k2 > mine.k2 || (k.k2 == mine.k2 && j < i))) rank++;
             }
         }
         const int n_keep = (max_features > 0) ? min(n, max_features) : n;
@@ -749,7 +754,7 @@ struct __align__(16) WarpScratch {
 };
 
 template <bool TEX>
-__global__ void __launch_bounds__(WK_WARPS * 32, 3) orient_describe_warp_kernel(
+__global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
     const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
     int batch, int kp_cap, int extended, int upright, const cudaTextureObject_t *__restrict__ texs, int *work_counter)
@@ -923,12 +928,12 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 3) orient_describe_warp_kernel(
             const float axl = (float)((sx1 - fsx1) / cwx), axm = (float)(1.0 / cwx),
                         axr = (float)(fmin(fmin(fsx2 - sx2, 1.), cwx) / cwx);
             for (int dy = 0; dy < PD; dy++) {
-                const double fsy1 = dy * scale, fsy2 = fsy1 + scale, cwy = fmin(scale, win - fsy1);
-                int sy1 = __double2int_ru(fsy1), sy2 = __double2int_rd(fsy2);
-                sy2 = min(sy2, win - 1); sy1 = min(sy1, sy2);
-                const bool yl = (sy1 - fsy1 > 1e-3), yr = (fsy2 - sy2 > 1e-3);
-                const float ayl = (float)((sy1 - fsy1) / cwy), aym = (float)(1.0 / cwy),
-                            ayr = (float)(fmin(fmin(fsy2 - sy2, 1.), cwy) / cwy);
+                // the row table of output row dy equals the column table of output column dy (square window, same scale):
+                // take lane dy's parameters instead of redoing the double-precision divisions
+                const int sy1 = __shfl_sync(0xffffffffu, sx1, dy), sy2 = __shfl_sync(0xffffffffu, sx2, dy);
+                const bool yl = __shfl_sync(0xffffffffu, (int)xl, dy) != 0, yr = __shfl_sync(0xffffffffu, (int)xr, dy) != 0;
+                const float ayl = __shfl_sync(0xffffffffu, axl, dy), aym = __shfl_sync(0xffffffffu, axm, dy),
+                            ayr = __shfl_sync(0xffffffffu, axr, dy);
                 const int ya = yl ? sy1 - 1 : sy1, yb = yr ? sy2 : sy2 - 1;
                 float sum = 0; bool first = true;
                 for (int sy = ya; sy <= yb; sy++) {
@@ -1394,11 +1399,15 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
             attr_h = true;
         }
         const int tiles_staged = plan.tile_begin[o_split];
-        if (tiles_staged > 0) {
-            hessian_nms_kernel<true><<<dim3(tiles_staged, batch), HT_THREADS, smem_det + smem_stage, st>>>(plan, ws.integral.as<int32_t>(),
-                ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap, 0);
+        for (int o = 0; o < o_split; o++) {          // one launch per staged octave: each gets exactly its own footprint of smem
+            const int nt = plan.tile_begin[o + 1] - plan.tile_begin[o];
+            if (nt <= 0) continue;
+            const size_t sm = smem_det + (size_t)plan.stage_rows[o] * plan.stage_cols[o] * 4;
+            hessian_nms_kernel<true><<<dim3(nt, batch), HT_THREADS, sm, st>>>(plan, ws.integral.as<int32_t>(),
+                ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap, plan.tile_begin[o]);
             LAUNCH_CHECK(ctx);
         }
+        (void)smem_stage;
         if (total_tiles > tiles_staged) {
             hessian_nms_kernel<false><<<dim3(total_tiles - tiles_staged, batch), HT_THREADS, smem_det, st>>>(plan, ws.integral.as<int32_t>(),
                 ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap, tiles_staged);
@@ -1411,7 +1420,7 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         int *hist = ws.hist.as<int>();
         unsigned *thr_bits = (unsigned *)(hist + (size_t)batch * RH_BINS);
         CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)batch * RH_BINS * 4, st));
-        const int gx = min(ceil_div(ws.cand_cap, 256), 64);
+        const int gx = min(ceil_div(ws.cand_cap, 256), 16);
         response_hist_kernel<<<dim3(gx, batch), 256, 0, st>>>(ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap, hist);
         LAUNCH_CHECK(ctx);
         response_threshold_kernel<<<ceil_div(batch, 8), 256, 0, st>>>(hist, ws.counters.as<int32_t>(), ws.cand_cap, max_features, batch, thr_bits);
@@ -1440,11 +1449,11 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
     const bool use_tex = surf_textures(ctx, base_a, base_b, split, batch, rows, cols, stride, img_stride, st, &texs);
     int *work_counter = ws.counters.as<int32_t>() + (size_t)batch * 4;      // one extra slot after the per-image counters
     if (use_tex)
-        orient_describe_warp_kernel<true><<<ctx->num_sms * 3, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
+        orient_describe_warp_kernel<true><<<ctx->num_sms * 4, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
             ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap,
             p->extended, p->upright, texs, work_counter);
     else
-        orient_describe_warp_kernel<false><<<ctx->num_sms * 3, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
+        orient_describe_warp_kernel<false><<<ctx->num_sms * 4, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
             ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap,
             p->extended, p->upright, nullptr, work_counter);
     LAUNCH_CHECK(ctx);

@@ -753,8 +753,8 @@ struct __align__(16) WarpScratch {
     uint8_t patch[448];
 };
 
-template <bool TEX>
-__global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
+template <bool TEX, int VAR>      // VAR 0: 64 registers / 4 CTAs per SM, sampler unrolled x2;  1: 80 registers / 3 CTAs, x4;  2: 64 / 4 CTAs, x4
+__global__ void __launch_bounds__(WK_WARPS * 32, VAR == 1 ? 3 : 4) orient_describe_warp_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
     const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
     int batch, int kp_cap, int extended, int upright, const cudaTextureObject_t *__restrict__ texs, int *work_counter)
@@ -781,7 +781,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
         const float size = kp[KP_SIZE], cx = kp[KP_X], cy = kp[KP_Y];
         const float s = size * 1.2f / 9.0f;
         const int win = (int)((PATCH_SZ + 1) * s);
-        if (win > WK_MAX_WIN) continue;                       // warp-uniform: the CTA kernel takes it
+        if (win > WK_MAX_WIN) { if (lane == 0) work_counter[1] = 1; continue; }     // warp-uniform: flag work for the CTA kernel
         const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
         const int32_t *I = integral + (size_t)b * srows * W;
         const int gws = 2 * __float2int_rn(2 * s);
@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
                 // |x| < 2^13), so the running sum equals the CPU's column-by-column accumulation
                 double px = rx + (double)lane * (double)cos_dir, py = ry - (double)lane * (double)sin_dir;
                 const double dpx = 32.0 * (double)cos_dir, dpy = 32.0 * (double)sin_dir;
-#pragma unroll 2
+#pragma unroll (VAR == 0 ? 2 : 4)
                 for (int j = lane; j < win; j += 32, px += dpx, py -= dpy) {
                     S.row[j] = (uint8_t)(TEX ? window_pixel_tex(tex, img, stride, ncols1, nrows1, px, py)
                                              : window_pixel(img, stride, ncols1, nrows1, px, py));
@@ -1004,8 +1004,9 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
 __global__ void __launch_bounds__(DESC_THREADS) orient_describe_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
     const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
-    int batch, int kp_cap, int extended, int upright)
+    int batch, int kp_cap, int extended, int upright, const int *big_flag)
 {
+    if (*big_flag == 0) return;        // no window exceeded WK_MAX_WIN (always the case for n_octaves <= 4)
     __shared__ float s_X[ORI_SAMPLES], s_Y[ORI_SAMPLES], s_ang[ORI_SAMPLES];
     __shared__ int s_flag_cnt[4];
     __shared__ float s_sumx[72], s_sumy[72];
@@ -1448,18 +1449,22 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
     cudaTextureObject_t *texs = nullptr;
     const bool use_tex = surf_textures(ctx, base_a, base_b, split, batch, rows, cols, stride, img_stride, st, &texs);
     int *work_counter = ws.counters.as<int32_t>() + (size_t)batch * 4;      // one extra slot after the per-image counters
-    if (use_tex)
-        orient_describe_warp_kernel<true><<<ctx->num_sms * 4, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
-            ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap,
-            p->extended, p->upright, texs, work_counter);
-    else
-        orient_describe_warp_kernel<false><<<ctx->num_sms * 4, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
-            ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap,
-            p->extended, p->upright, nullptr, work_counter);
+    static const int var = getenv("VFSMS_DESCRIBE_VARIANT") ? atoi(getenv("VFSMS_DESCRIBE_VARIANT")) : 0;
+#define LAUNCH_WK(T, V, NB)                                                                                                        \
+    orient_describe_warp_kernel<T, V><<<ctx->num_sms * NB, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride, \
+        ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap,                    \
+        p->extended, p->upright, texs, work_counter)
+    if (use_tex) {
+        if (var == 1) LAUNCH_WK(true, 1, 3); else if (var == 2) LAUNCH_WK(true, 2, 4); else LAUNCH_WK(true, 0, 4);
+    } else {
+        texs = nullptr;
+        LAUNCH_WK(false, 0, 4);
+    }
+#undef LAUNCH_WK
     LAUNCH_CHECK(ctx);
     orient_describe_kernel<<<ctx->num_sms * 2, DESC_THREADS, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
                                                                        ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(),
-                                                                       ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, p->upright);
+                                                                       ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, p->upright, work_counter + 1);
     LAUNCH_CHECK(ctx);
     return 0;
 }

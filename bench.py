@@ -20,6 +20,12 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# torchrun exports OMP_NUM_THREADS=1; the CPU arms (reference / cpu_baseline) must see every host core, and NCCL's
+# version banner must not precede the single JSON line on stdout.
+if "--impl" in sys.argv and "reference" in sys.argv or int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 ROI_RATIO = 0.2
 TILE = 2048
@@ -96,6 +102,7 @@ def run_reference(args, rank, world):
     import cv2
     from imagestitch_b200 import synth
     from oracle import surf
+    cv2.setNumThreads(os.cpu_count() or 1)
     L = int(np.floor(TILE * ROI_RATIO))
     mf = int(0.01 * L * TILE)
     n_sample = 2

@@ -218,10 +218,8 @@ class Stitcher(Utility.Method):
         return self._incre_search(images, evaluate)
 
     def _enhance(self, image):
-        """Optional pre-processing (Stitcher.py:269-276, 327-334) -- cv2 passthrough, off by default."""
-        if self.isClahe:
-            return cv2.createCLAHE(clipLimit=self.clipLimit, tileGridSize=(self.tileSize, self.tileSize)).apply(np.ascontiguousarray(image))
-        return cv2.equalizeHist(np.ascontiguousarray(image))
+        """Optional pre-processing (Stitcher.py:269-276, 327-334): CLAHE(clipLimit, tileSize) or equalizeHist, on the device."""
+        return gpu.enhance(image, clahe=bool(self.isClahe), clip_limit=self.clipLimit, tile_size=self.tileSize)
 
     def calculateOffsetForFeatureSearch(self, images):
         """Full-frame features with the B-feature cache (Stitcher.py:260-304)."""

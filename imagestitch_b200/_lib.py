@@ -32,7 +32,7 @@ EXPORTS = [
     "vfsms_orb_detect_and_describe", "vfsms_offset_by_mode", "vfsms_align_batch_host", "vfsms_align_batch_dev",
     "vfsms_match_batch_dev", "vfsms_phase_correlate_host", "vfsms_phase_correlate_dev", "vfsms_fuse_roi_host",
     "vfsms_mosaic_host", "vfsms_profile_enable", "vfsms_profile_read", "vfsms_stage_name",
-    "vfsms_set_matcher", "vfsms_last_match_fallbacks",
+    "vfsms_set_matcher", "vfsms_last_match_fallbacks", "vfsms_enhance_host",
 ]
 STAGE_COUNT = 12
 
@@ -79,6 +79,7 @@ def load():
     L.vfsms_mosaic_host.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp]
     L.vfsms_set_matcher.argtypes = [vp, i32]
     L.vfsms_last_match_fallbacks.argtypes = [vp, ctypes.POINTER(i32)]
+    L.vfsms_enhance_host.argtypes = [vp, vp, i32, i32, i32, i32, ctypes.c_double, i32, vp]
     L.vfsms_profile_enable.argtypes = [vp, i32]
     L.vfsms_profile_read.argtypes = [vp, vp, vp, i32]
     L.vfsms_stage_name.argtypes = [i32]

@@ -17,6 +17,7 @@ UNITS = {
     "phase.cu": ["-fmad=false"],
     "blend.cu": ["-fmad=false"],
     "orb.cu": ["-fmad=false"],
+    "enhance.cu": ["-fmad=false"],
     "capi.cu": [],
     "stubs.cu": [],
 }

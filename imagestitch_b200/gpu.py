@@ -241,6 +241,17 @@ def orb_detect_and_describe(image, n_features=5000, scale_factor=1.2, n_levels=8
     return kp[:n.value].copy(), desc[:n.value].copy()
 
 
+def enhance(image, clahe=False, clip_limit=20, tile_size=5, device=0):
+    """cv2.equalizeHist / cv2.createCLAHE(clip_limit, (tile_size, tile_size)).apply on the device (Stitcher.py:269-276)."""
+    L = _lib.load()
+    ctx = _lib.context(device)
+    img = _as_u8_image(image)
+    out = np.empty(img.shape, np.uint8)
+    check(L.vfsms_enhance_host(ctx, _vp(img), img.shape[0], img.shape[1], img.strides[0], 1 if clahe else 0, float(clip_limit),
+                               int(tile_size), _vp(out)), "vfsms_enhance_host")
+    return out
+
+
 def set_matcher(mode, device=0):
     """'tc' (default): tcgen05 candidates + exact rescoring; 'simt': exact fp32 SIMT kernel.  Identical results."""
     check(_lib.load().vfsms_set_matcher(_lib.context(device), {"tc": 0, "simt": 1}[mode]), "vfsms_set_matcher")

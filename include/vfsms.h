@@ -147,6 +147,12 @@ int vfsms_match_batch_dev(vfsms_ctx *ctx, const float *desc_a_dev, const int32_t
                           int32_t *best_idx_dev /* [pair][cap][2] */, float *best_dist_dev /* [pair][cap][2] */,
                           void *stream);
 
+/* Optional ROI enhancement before detection (Stitcher.py:269-276, 327-334; off by default).
+ * mode 0: cv2.equalizeHist(image);  mode 1: cv2.createCLAHE(clip_limit, (tile_grid, tile_grid)).apply(image)
+ * (reference values: clipLimit 20, tileSize 5, ImageUtility.py:47-50).  out: rows x cols u8, contiguous. */
+int vfsms_enhance_host(vfsms_ctx *ctx, const uint8_t *image, int rows, int cols, int stride, int mode, double clip_limit,
+                       int tile_grid, uint8_t *out);
+
 /* ---------------------------------------------------------------- phase correlation */
 
 /* Replaces cv2.phaseCorrelate(np.float64(roiA), np.float64(roiB)) as called at Stitcher.py:230 (no window):

@@ -111,3 +111,18 @@ def test_phase_incre_equals_cv2_evaluation(tile_set):
     Stitcher.direction = 1; Stitcher.isPrintLog = True
     if "direction" in st.__dict__:
         del st.__dict__["direction"]
+
+
+def test_enhancement_equals_cv2(tile_set):
+    """isEnhance path (Stitcher.py:269-276): equalizeHist and CLAHE(20, 5x5) vs cv2, incl. sizes not divisible by the grid."""
+    import cv2
+    from imagestitch_b200 import gpu
+    root, tiles, offs = tile_set
+    for img in (tiles[0], tiles[1][:103, :257], np.ascontiguousarray(tiles[2][:, 512 - 102:])):
+        assert np.array_equal(gpu.enhance(img, clahe=False), cv2.equalizeHist(np.ascontiguousarray(img)))
+        ref = cv2.createCLAHE(clipLimit=20, tileGridSize=(5, 5)).apply(np.ascontiguousarray(img))
+        out = gpu.enhance(img, clahe=True, clip_limit=20, tile_size=5)
+        d = np.abs(out.astype(int) - ref.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3, (int(d.max()), float((d > 0).mean()))
+    flat = np.full((40, 50), 9, np.uint8)
+    assert np.array_equal(gpu.enhance(flat), cv2.equalizeHist(flat))

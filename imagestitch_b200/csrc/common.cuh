@@ -84,6 +84,7 @@ struct SurfLayer {
     int samples_i;       // 1 + (rows - size)/step  (0 when the layer is skipped)
     int samples_j;
     HaarBox dx[3], dy[3], dxy[4];
+    int off[32];         // the 32 distinct box corners as offsets into the array the octave's kernel reads (pitch folded in)
 };
 
 struct SurfPlan {

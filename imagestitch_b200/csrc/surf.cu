@@ -265,40 +265,36 @@ __device__ __forceinline__ bool solve3(const float a[3][3], const float b[3], fl
 }
 
 // Box responses of one sample from 32 integral reads (the 10 boxes share their corners: Dxx 2x4, Dyy 4x2, Dxy 4x4 grid).
-// `o` points at the sample origin inside an int32 array of row pitch P (global integral or its shared-memory copy).
+// `o` points at the sample origin inside an int32 array (global integral or its shared-memory copy); L.off[] holds the 32
+// corner offsets already combined with that array's row pitch.  With the octave a template parameter and the layer loop
+// unrolled, every L.field is a compile-time address in the kernel-parameter constant bank, i.e. a free instruction operand.
 // Each box sum is an exact integer; products and the double accumulation keep the CPU expression's rounding.
 template <typename Ptr>
-__device__ __forceinline__ void hessian_responses(Ptr o, int P, const SurfLayer &L, float &dx, float &dy, float &dxy)
+__device__ __forceinline__ void hessian_responses(Ptr o, const SurfLayer &L, float &dx, float &dy, float &dxy)
 {
-    {   // Dxx: rows y1, y2; column edges x0 < x1 < x2 < x3
-        const int y1 = L.dx[0].y1 * P, y2 = L.dx[0].y2 * P;
-        const int x0 = L.dx[0].x1, x1 = L.dx[1].x1, x2 = L.dx[2].x1, x3 = L.dx[2].x2;
-        const int t0 = o[y1 + x0], t1 = o[y1 + x1], t2 = o[y1 + x2], t3 = o[y1 + x3];
-        const int b0 = o[y2 + x0], b1 = o[y2 + x1], b2 = o[y2 + x2], b3 = o[y2 + x3];
+    {   // Dxx: rows y1, y2 x column edges x0..x3          off[0..3] = (y1, x0..x3), off[4..7] = (y2, x0..x3)
+        const int t0 = o[L.off[0]], t1 = o[L.off[1]], t2 = o[L.off[2]], t3 = o[L.off[3]];
+        const int b0 = o[L.off[4]], b1 = o[L.off[5]], b2 = o[L.off[6]], b3 = o[L.off[7]];
         double d = 0;
         d += (double)((float)(t0 + b1 - b0 - t1) * L.dx[0].w);
         d += (double)((float)(t1 + b2 - b1 - t2) * L.dx[1].w);
         d += (double)((float)(t2 + b3 - b2 - t3) * L.dx[2].w);
         dx = (float)d;
     }
-    {   // Dyy: columns x1, x2; row edges y0 < y1 < y2 < y3
-        const int x1 = L.dy[0].x1, x2 = L.dy[0].x2;
-        const int y0 = L.dy[0].y1 * P, y1 = L.dy[1].y1 * P, y2 = L.dy[2].y1 * P, y3 = L.dy[2].y2 * P;
-        const int l0 = o[y0 + x1], l1 = o[y1 + x1], l2 = o[y2 + x1], l3 = o[y3 + x1];
-        const int r0 = o[y0 + x2], r1 = o[y1 + x2], r2 = o[y2 + x2], r3 = o[y3 + x2];
+    {   // Dyy: row edges y0..y3 x columns x1, x2            off[8..11] = (y0..y3, x1), off[12..15] = (y0..y3, x2)
+        const int l0 = o[L.off[8]], l1 = o[L.off[9]], l2 = o[L.off[10]], l3 = o[L.off[11]];
+        const int r0 = o[L.off[12]], r1 = o[L.off[13]], r2 = o[L.off[14]], r3 = o[L.off[15]];
         double d = 0;
         d += (double)((float)(l0 + r1 - l1 - r0) * L.dy[0].w);
         d += (double)((float)(l1 + r2 - l2 - r1) * L.dy[1].w);
         d += (double)((float)(l2 + r3 - l3 - r2) * L.dy[2].w);
         dy = (float)d;
     }
-    {   // Dxy: 4x4 corner grid, boxes (x01,y01) (x23,y01) (x01,y23) (x23,y23)
-        const int xa = L.dxy[0].x1, xb = L.dxy[0].x2, xc = L.dxy[1].x1, xd = L.dxy[1].x2;
-        const int ya = L.dxy[0].y1 * P, yb = L.dxy[0].y2 * P, yc = L.dxy[2].y1 * P, yd = L.dxy[2].y2 * P;
-        const int aa = o[ya + xa], ab = o[ya + xb], ac = o[ya + xc], ad = o[ya + xd];
-        const int ba = o[yb + xa], bb = o[yb + xb], bc = o[yb + xc], bd = o[yb + xd];
-        const int ca = o[yc + xa], cb = o[yc + xb], cc = o[yc + xc], cd = o[yc + xd];
-        const int da = o[yd + xa], db = o[yd + xb], dc = o[yd + xc], dd = o[yd + xd];
+    {   // Dxy: 4x4 corner grid, row-major                    off[16 + 4*row + col], rows ya..yd, cols xa..xd
+        const int aa = o[L.off[16]], ab = o[L.off[17]], ac = o[L.off[18]], ad = o[L.off[19]];
+        const int ba = o[L.off[20]], bb = o[L.off[21]], bc = o[L.off[22]], bd = o[L.off[23]];
+        const int ca = o[L.off[24]], cb = o[L.off[25]], cc = o[L.off[26]], cd = o[L.off[27]];
+        const int da = o[L.off[28]], db = o[L.off[29]], dc = o[L.off[30]], dd = o[L.off[31]];
         double d = 0;
         d += (double)((float)(aa + bb - ba - ab) * L.dxy[0].w);
         d += (double)((float)(ac + bd - bc - ad) * L.dxy[1].w);
@@ -308,21 +304,83 @@ __device__ __forceinline__ void hessian_responses(Ptr o, int P, const SurfLayer 
     }
 }
 
+#include "hessian_tables.inc"
+
+// det of one sample for the default layer structure: every corner offset and weight is an immediate
+template <int OCT, int L>
+__device__ __forceinline__ float det_fixed(const int32_t *o)
+{
+    using T = HessFixed<OCT, L>;
+    float dx, dy, dxy;
+    {
+        const int t0 = o[T::off(0)], t1 = o[T::off(1)], t2 = o[T::off(2)], t3 = o[T::off(3)];
+        const int b0 = o[T::off(4)], b1 = o[T::off(5)], b2 = o[T::off(6)], b3 = o[T::off(7)];
+        double d = 0;
+        d += (double)((float)(t0 + b1 - b0 - t1) * T::w(0));
+        d += (double)((float)(t1 + b2 - b1 - t2) * T::w(1));
+        d += (double)((float)(t2 + b3 - b2 - t3) * T::w(2));
+        dx = (float)d;
+    }
+    {
+        const int l0 = o[T::off(8)], l1 = o[T::off(9)], l2 = o[T::off(10)], l3 = o[T::off(11)];
+        const int r0 = o[T::off(12)], r1 = o[T::off(13)], r2 = o[T::off(14)], r3 = o[T::off(15)];
+        double d = 0;
+        d += (double)((float)(l0 + r1 - l1 - r0) * T::w(3));
+        d += (double)((float)(l1 + r2 - l2 - r1) * T::w(4));
+        d += (double)((float)(l2 + r3 - l3 - r2) * T::w(5));
+        dy = (float)d;
+    }
+    {
+        const int aa = o[T::off(16)], ab = o[T::off(17)], ac = o[T::off(18)], ad = o[T::off(19)];
+        const int ba = o[T::off(20)], bb = o[T::off(21)], bc = o[T::off(22)], bd = o[T::off(23)];
+        const int ca = o[T::off(24)], cb = o[T::off(25)], cc = o[T::off(26)], cd = o[T::off(27)];
+        const int da = o[T::off(28)], db = o[T::off(29)], dc = o[T::off(30)], dd = o[T::off(31)];
+        double d = 0;
+        d += (double)((float)(aa + bb - ba - ab) * T::w(6));
+        d += (double)((float)(ac + bd - bc - ad) * T::w(7));
+        d += (double)((float)(ca + db - da - cb) * T::w(8));
+        d += (double)((float)(cc + dd - dc - cd) * T::w(9));
+        dxy = (float)d;
+    }
+    float tt = 0.81f * dxy;
+    tt = tt * dxy;
+    return dx * dy - tt;
+}
+
+template <int OCT, int L>
+__device__ __forceinline__ void det_layer_fixed(const SurfPlan &plan, const int32_t *s_int, float *s_det, int i0, int j0, int r_base, int c_base)
+{
+    using T = HessFixed<OCT, L>;
+    constexpr int step = 1 << OCT, SW = HT_X + 2, SH = HT_Y + 2, RW = T::pitch;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ni = plan.layer[OCT][L].samples_i, nj = plan.layer[OCT][L].samples_j;
+    for (int ly = warp; ly < SH; ly += HT_THREADS / 32) {
+        const int si = i0 + ly - T::margin;
+        const bool row_ok = si >= 0 && si < ni;
+        const int32_t *row = s_int + (si * step - r_base) * RW - c_base;
+        for (int lx = lane; lx < SW; lx += 32) {
+            const int sj = j0 + lx - T::margin;
+            float det = 0.f;
+            if (row_ok && sj >= 0 && sj < nj) det = det_fixed<OCT, L>(row + sj * step);
+            s_det[(L * SH + ly) * SW + lx] = det;
+        }
+    }
+}
+
 // STAGE = true: the integral footprint of the tile (all layers of the octave) is copied to shared memory once and the
 // 32 corner reads per sample-layer become LDS (octaves whose footprint fits: 0 and 1); false: reads go to L1/L2.
-template <bool STAGE>
+// One launch per octave (OCT is a template parameter, see hessian_responses).
+template <bool STAGE, int OCT, bool FIXED = false>
 __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_constant__ SurfPlan plan,
                                                                  const int32_t *__restrict__ integral,
-                                                                 float *cand, int32_t *counters, int cand_cap, int tile_offset)
+                                                                 float *cand, int32_t *counters, int cand_cap)
 {
     extern __shared__ float s_dyn[];
     const int b = blockIdx.y;
-    const int tile_id = blockIdx.x + tile_offset;
-    int o = 0;
-    while (o + 1 < plan.n_octaves && tile_id >= plan.tile_begin[o + 1]) o++;
-    const int t = tile_id - plan.tile_begin[o];
+    constexpr int o = OCT;
+    const int t = blockIdx.x;
     const int tile_x = t % plan.tiles_x[o], tile_y = t / plan.tiles_x[o];
-    const int step = 1 << o;
+    constexpr int step = 1 << OCT;
     const int lrows = plan.rows / step, lcols = plan.cols / step;
     const int W = plan.cols + 1;
     const int32_t *I = integral + (size_t)b * (plan.rows + 1) * W;
@@ -333,10 +391,10 @@ __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_co
     const int i0 = tile_y * HT_Y - 1, j0 = tile_x * HT_X - 1;   // layer coords of the smem origin
     const int RW = plan.stage_cols[o];
     const int r_base = i0 * step + plan.stage_off_min[o], c_base = j0 * step + plan.stage_off_min[o];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (STAGE) {
         const int RH = plan.stage_rows[o];
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         for (int rr = warp; rr < RH; rr += HT_THREADS / 32) {           // one warp per footprint row: no index division
             const int32_t *src = I + (size_t)min(max(r_base + rr, 0), plan.rows) * W;
             int32_t *dst = s_int + rr * RW;
@@ -345,23 +403,36 @@ __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_co
         __syncthreads();
     }
 
-    // phase 1: det for every layer over the haloed tile
-    for (int idx = threadIdx.x; idx < SW * SH; idx += HT_THREADS) {
-        const int ly = idx / SW, lx = idx - ly * SW;
-        const int li = i0 + ly, lj = j0 + lx;
-        for (int l = 0; l < nl; l++) {
-            const SurfLayer &L = plan.layer[o][l];
-            const int si = li - L.margin, sj = lj - L.margin;
-            float det = 0.f;
-            if (si >= 0 && si < L.samples_i && sj >= 0 && sj < L.samples_j) {
-                float dx, dy, dxy;
-                if (STAGE) hessian_responses(s_int + (si * step - r_base) * RW + (sj * step - c_base), RW, L, dx, dy, dxy);
-                else hessian_responses(I + (size_t)(si * step) * W + sj * step, W, L, dx, dy, dxy);
-                float tt = 0.81f * dxy;
-                tt = tt * dxy;
-                det = dx * dy - tt;
+    // phase 1: det for every layer over the haloed tile; warp w takes rows w, w+8, ..., lanes take columns
+    if constexpr (FIXED) {
+        // default layer structure: geometry from compile-time tables (verified against the plan by the host)
+        det_layer_fixed<OCT < 2 ? OCT : 0, 0>(plan, s_int, s_det, i0, j0, r_base, c_base);
+        det_layer_fixed<OCT < 2 ? OCT : 0, 1>(plan, s_int, s_det, i0, j0, r_base, c_base);
+        det_layer_fixed<OCT < 2 ? OCT : 0, 2>(plan, s_int, s_det, i0, j0, r_base, c_base);
+        det_layer_fixed<OCT < 2 ? OCT : 0, 3>(plan, s_int, s_det, i0, j0, r_base, c_base);
+        det_layer_fixed<OCT < 2 ? OCT : 0, 4>(plan, s_int, s_det, i0, j0, r_base, c_base);
+    } else
+    for (int ly = warp; ly < SH; ly += HT_THREADS / 32) {
+        const int li = i0 + ly;
+        for (int lx = lane; lx < SW; lx += 32) {
+            const int lj = j0 + lx;
+#pragma unroll
+            for (int l = 0; l < VFSMS_MAX_LAYERS_PER_OCTAVE; l++) {
+                if (l < nl) {
+                    const SurfLayer &L = plan.layer[OCT][l];
+                    const int si = li - L.margin, sj = lj - L.margin;
+                    float det = 0.f;
+                    if (si >= 0 && si < L.samples_i && sj >= 0 && sj < L.samples_j) {
+                        float dx, dy, dxy;
+                        if (STAGE) hessian_responses(s_int + (si * step - r_base) * RW + (sj * step - c_base), L, dx, dy, dxy);
+                        else hessian_responses(I + (size_t)(si * step) * W + sj * step, L, dx, dy, dxy);
+                        float tt = 0.81f * dxy;
+                        tt = tt * dxy;
+                        det = dx * dy - tt;
+                    }
+                    s_det[(l * SH + ly) * SW + lx] = det;
+                }
             }
-            s_det[(l * SH + ly) * SW + lx] = det;
         }
     }
     __syncthreads();
@@ -417,9 +488,17 @@ __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_co
             py += x[1] * step;
             psz = (float)__float2int_rn(psz + x[2] * ds);
             // laplacian sign: recompute trace at the maximum (rare path)
-            float tdx, tdy, tdxy;
-            hessian_responses(I + (size_t)((li - L.margin) * step) * W + (lj - L.margin) * step, W, L, tdx, tdy, tdxy);
-            const float trace = tdx + tdy;
+            // laplacian sign from trace = dxx + dyy, recomputed box by box from the global integral
+            const int32_t *org = I + (size_t)((li - L.margin) * step) * W + (lj - L.margin) * step;
+            double tdx = 0, tdy = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const HaarBox &fx = L.dx[k], &fy = L.dy[k];
+                const int vx = __ldg(org + fx.y1 * W + fx.x1) + __ldg(org + fx.y2 * W + fx.x2) - __ldg(org + fx.y2 * W + fx.x1) - __ldg(org + fx.y1 * W + fx.x2);
+                const int vy = __ldg(org + fy.y1 * W + fy.x1) + __ldg(org + fy.y2 * W + fy.x2) - __ldg(org + fy.y2 * W + fy.x1) - __ldg(org + fy.y1 * W + fy.x2);
+                tdx += (double)((float)vx * fx.w); tdy += (double)((float)vy * fy.w);
+            }
+            const float trace = (float)tdx + (float)tdy;
             const int slot = atomicAdd(&counters[b * 4 + 0], 1);
             if (slot < cand_cap) {
                 float4 *dst = (float4 *)(cand + ((size_t)b * cand_cap + slot) * KP_STRIDE);
@@ -1388,30 +1467,66 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         StageTimer t_h(ctx, st, VFSMS_STAGE_HESSIAN);
         const size_t smem_det = (size_t)plan.n_layers * (HT_X + 2) * (HT_Y + 2) * 4;
         // octaves whose integral footprint fits in shared memory next to the det tile (two CTAs per SM)
-        int o_split = 0; size_t smem_stage = 0;
+        int o_split = 0;
         static const bool no_stage = getenv("VFSMS_HESSIAN_UNSTAGED") != nullptr;     // debugging aid
-        while (!no_stage && o_split < plan.n_octaves && smem_det + (size_t)plan.stage_rows[o_split] * plan.stage_cols[o_split] * 4 <= 110 * 1024) {
-            smem_stage = std::max(smem_stage, (size_t)plan.stage_rows[o_split] * plan.stage_cols[o_split] * 4);
-            o_split++;
+        while (!no_stage && o_split < plan.n_octaves &&
+               smem_det + (size_t)plan.stage_rows[o_split] * plan.stage_cols[o_split] * 4 <= 110 * 1024) o_split++;
+        if (o_split > 2) o_split = 2;                  // staged kernels are instantiated for octaves 0 and 1
+        // corner offsets combined with the pitch each octave's kernel reads from
+        for (int o = 0; o < plan.n_octaves; o++) {
+            const int P = o < o_split ? plan.stage_cols[o] : cols + 1;
+            for (int l = 0; l < plan.n_layers; l++) {
+                SurfLayer &L = plan.layer[o][l];
+                const int xs[4] = { L.dx[0].x1, L.dx[1].x1, L.dx[2].x1, L.dx[2].x2 };
+                for (int k = 0; k < 4; k++) { L.off[k] = L.dx[0].y1 * P + xs[k]; L.off[4 + k] = L.dx[0].y2 * P + xs[k]; }
+                const int ys[4] = { L.dy[0].y1, L.dy[1].y1, L.dy[2].y1, L.dy[2].y2 };
+                for (int k = 0; k < 4; k++) { L.off[8 + k] = ys[k] * P + L.dy[0].x1; L.off[12 + k] = ys[k] * P + L.dy[0].x2; }
+                const int gx[4] = { L.dxy[0].x1, L.dxy[0].x2, L.dxy[1].x1, L.dxy[1].x2 };
+                const int gy[4] = { L.dxy[0].y1, L.dxy[0].y2, L.dxy[2].y1, L.dxy[2].y2 };
+                for (int r = 0; r < 4; r++) for (int k = 0; k < 4; k++) L.off[16 + 4 * r + k] = gy[r] * P + gx[k];
+            }
         }
         static bool attr_h = false;
         if (!attr_h) {
-            CUDA_TRY(cudaFuncSetAttribute(hessian_nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(hessian_nms_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(hessian_nms_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(hessian_nms_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(hessian_nms_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
             attr_h = true;
         }
-        const int tiles_staged = plan.tile_begin[o_split];
-        for (int o = 0; o < o_split; o++) {          // one launch per staged octave: each gets exactly its own footprint of smem
+        // the compile-time tables apply when they reproduce this plan exactly (default nOctaveLayers = 3)
+        bool fixed_ok[2] = { plan.n_layers == 5 && o_split > 0, plan.n_layers == 5 && o_split > 1 };
+        static const bool no_fixed = getenv("VFSMS_HESSIAN_GENERIC") != nullptr;           // debugging aid
+        auto check_fixed = [&](int o, int l, int size, int margin, int pitch, int (*off)(int), float (*w)(int)) {
+            const SurfLayer &L = plan.layer[o][l];
+            bool ok = L.size == size && L.margin == margin && plan.stage_cols[o] == pitch;
+            for (int k = 0; ok && k < 32; k++) ok = L.off[k] == off(k);
+            const float pw[10] = { L.dx[0].w, L.dx[1].w, L.dx[2].w, L.dy[0].w, L.dy[1].w, L.dy[2].w, L.dxy[0].w, L.dxy[1].w, L.dxy[2].w, L.dxy[3].w };
+            for (int k = 0; ok && k < 10; k++) { const float wk = w(k); ok = memcmp(&pw[k], &wk, 4) == 0; }
+            if (!ok) fixed_ok[o] = false;
+        };
+#define CHK(O, LL) if (fixed_ok[O]) check_fixed(O, LL, HessFixed<O, LL>::size, HessFixed<O, LL>::margin, HessFixed<O, LL>::pitch, \
+                                                [](int k) { return HessFixed<O, LL>::off(k); }, [](int k) { return HessFixed<O, LL>::w(k); })
+        CHK(0, 0); CHK(0, 1); CHK(0, 2); CHK(0, 3); CHK(0, 4); CHK(1, 0); CHK(1, 1); CHK(1, 2); CHK(1, 3); CHK(1, 4);
+#undef CHK
+        if (no_fixed) fixed_ok[0] = fixed_ok[1] = false;
+        for (int o = 0; o < plan.n_octaves; o++) {          // one launch per octave: its own smem footprint, octave as template parameter
             const int nt = plan.tile_begin[o + 1] - plan.tile_begin[o];
             if (nt <= 0) continue;
-            const size_t sm = smem_det + (size_t)plan.stage_rows[o] * plan.stage_cols[o] * 4;
-            hessian_nms_kernel<true><<<dim3(nt, batch), HT_THREADS, sm, st>>>(plan, ws.integral.as<int32_t>(),
-                ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap, plan.tile_begin[o]);
-            LAUNCH_CHECK(ctx);
-        }
-        (void)smem_stage;
-        if (total_tiles > tiles_staged) {
-            hessian_nms_kernel<false><<<dim3(total_tiles - tiles_staged, batch), HT_THREADS, smem_det, st>>>(plan, ws.integral.as<int32_t>(),
-                ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap, tiles_staged);
+            const bool staged = o < o_split;
+            const size_t sm = smem_det + (staged ? (size_t)plan.stage_rows[o] * plan.stage_cols[o] * 4 : 0);
+            const dim3 grid(nt, batch);
+#define HL(S, O) hessian_nms_kernel<S, O><<<grid, HT_THREADS, sm, st>>>(plan, ws.integral.as<int32_t>(), ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap)
+            switch (o) {
+#define HLF(O) hessian_nms_kernel<true, O, true><<<grid, HT_THREADS, sm, st>>>(plan, ws.integral.as<int32_t>(), ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap)
+            case 0: if (staged && fixed_ok[0]) HLF(0); else if (staged) HL(true, 0); else HL(false, 0); break;
+            case 1: if (staged && fixed_ok[1]) HLF(1); else if (staged) HL(true, 1); else HL(false, 1); break;
+#undef HLF
+            case 2: HL(false, 2); break;
+            case 3: HL(false, 3); break;
+            default: HL(false, 4); break;
+            }
+#undef HL
             LAUNCH_CHECK(ctx);
         }
     }

@@ -22,8 +22,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # torchrun exports OMP_NUM_THREADS=1; the CPU arms (reference / cpu_baseline) must see every host core, and NCCL's
 # version banner must not precede the single JSON line on stdout.
+def host_cores():
+    """CPUs this process may run on (cgroup / affinity aware; os.cpu_count() over-reports inside a cpuset)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 if "--impl" in sys.argv and "reference" in sys.argv or int(os.environ.get("WORLD_SIZE", "1")) == 1:
-    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(host_cores())
 if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
     os.environ["NCCL_DEBUG"] = "WARN"
 
@@ -102,7 +110,7 @@ def run_reference(args, rank, world):
     import cv2
     from imagestitch_b200 import synth
     from oracle import surf
-    cv2.setNumThreads(os.cpu_count() or 1)
+    cv2.setNumThreads(host_cores())
     L = int(np.floor(TILE * ROI_RATIO))
     mf = int(0.01 * L * TILE)
     n_sample = 2
@@ -125,7 +133,7 @@ def run_reference(args, rank, world):
            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "synthetic 2048x2048 grayscale pair, SURF detect+describe+match+vote (ROI 409x2048, GPU-SURF params)",
-                      "pairs_per_step": n_sample, "correct_pairs": ok, "cv2_threads": cv2.getNumThreads(), "host_cpus": os.cpu_count()},
+                      "pairs_per_step": n_sample, "correct_pairs": ok, "cv2_threads": cv2.getNumThreads(), "host_cpus": host_cores()},
            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
                             "sample": "%d pairs/step x %d steps: oracle C SURF (OpenMP %d thr) + cv2 BFMatcher knnMatch + ratio + vote port" % (n_sample, args.steps, cores)},
            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -113,7 +113,7 @@ void vfsms_destroy(vfsms_ctx *ctx)
     surf_tex_destroy(ctx);
     ctx->tex_dev.release();
     SurfWorkspace &w = ctx->surf;
-    DevBuf *bufs[] = { &w.integral, &w.band_tot, &w.cand, &w.sorted, &w.kp, &w.desc, &w.descT, &w.counters, &w.prefix, &w.hist,
+    DevBuf *bufs[] = { &w.integral, &w.band_tot, &w.cand, &w.sorted, &w.kp, &w.desc, &w.descT, &w.counters, &w.prefix, &w.hist, &w.img_f32,
                        &ctx->match.best_idx, &ctx->match.best_dist, &ctx->match.matches, &ctx->match.n_matches,
                        &ctx->match.table_keys, &ctx->match.table_cnt, &ctx->match.table_first, &ctx->match.bf16_a,
                        &ctx->match.bf16_b, &ctx->match.cand_topk, &ctx->img_a, &ctx->img_b, &ctx->results,

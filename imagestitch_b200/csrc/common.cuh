@@ -114,6 +114,8 @@ struct SurfWorkspace {
     DevBuf counters;         // [batch][4] int32 : n_cand, n_sorted, n_final, flags
     DevBuf prefix;           // [batch+1] int32 prefix of n_final
     DevBuf hist;             // [batch][2048] response histogram + [batch] thresholds
+    DevBuf img_f32;          // [batch][rows][pitch_f] float copy of the images (texture source of the descriptor stage)
+    int pitch_f = 0;
 };
 
 struct MatchWorkspace {

@@ -781,36 +781,50 @@ __device__ __forceinline__ int round_half_even_u8(float v)      // cvRound for 0
 {
     return __float_as_int(v + 12582912.0f) - 0x4B400000;
 }
-// floor(x) for |x| < 2^31: returns the integer and writes floor(x) as a double
-__device__ __forceinline__ int floor_magic(double x, double &fl)
+// floor-like split of x (|x| < 2^31) into an integer i and f = x - i with 0 <= f <= 1:  i = rn(x - 0.5).  It equals
+// floor(x) except when x is an exact integer n and the tie rounds down (i = n - 1, f = 1); the bilinear expression then
+// yields the same value (weights 0 / 1 move to the neighbouring texel: p[n-1]*0 + p[n]*1), and so does the border path,
+// so the result is identical to the CPU's floor-based code while saving the compare / select / fix-up sequence.
+__device__ __forceinline__ int floor_split(double x, double &fl)
 {
-    const double M = 6755399441055744.0;     // 1.5 * 2^52: x + M rounds x to the nearest integer (ties to even)
-    const double t = x + M;
-    int i = __double2loint(t);
-    double r = t - M;
-    if (r > x) { i -= 1; r -= 1.0; }
-    fl = r;
-    return i;
+    const double M = 6755399441055744.0;     // 1.5 * 2^52: adding it rounds to the nearest integer (ties to even)
+    const double t = (x - 0.5) + M;
+    fl = t - M;
+    return __double2loint(t);
 }
 
-// TEX variant: one tex2Dgather returns the whole 2x2 footprint (exact integer texels, no filtering arithmetic).
+// TEX variant: one tex2Dgather on a float copy of the image returns the whole 2x2 footprint as exact floats.
 __device__ __forceinline__ int window_pixel_tex(cudaTextureObject_t tex, const uint8_t *__restrict__ img, int stride,
                                                 int ncols1, int nrows1, double pixel_x, double pixel_y)
 {
     double fx, fy;
-    const int ix = floor_magic(pixel_x, fx), iy = floor_magic(pixel_y, fy);
+    const int ix = floor_split(pixel_x, fx), iy = floor_split(pixel_y, fy);
     if ((unsigned)ix < (unsigned)ncols1 && (unsigned)iy < (unsigned)nrows1) {
         const float a = (float)(pixel_x - fx), bq = (float)(pixel_y - fy);
         const float tx = __uint_as_float(0x4B000000u | (unsigned)ix) - 8388607.0f;      // ix + 1.0f, exact
         const float ty = __uint_as_float(0x4B000000u | (unsigned)iy) - 8388607.0f;
-        const uchar4 g = tex2Dgather<uchar4>(tex, tx, ty, 0);
-        const float p00 = u8_to_float(g.w), p01 = u8_to_float(g.z), p10 = u8_to_float(g.x), p11 = u8_to_float(g.y);
+        const float4 g = tex2Dgather<float4>(tex, tx, ty, 0);
+        const float p00 = g.w, p01 = g.z, p10 = g.x, p11 = g.y;
         const float v = p00 * (1.f - a) * (1.f - bq) + p01 * a * (1.f - bq) + p10 * (1.f - a) * bq + p11 * a * bq;
         return round_half_even_u8(v) & 255;
     }
     int x = __double2int_rn(pixel_x), y = __double2int_rn(pixel_y);
     x = min(max(x, 0), ncols1); y = min(max(y, 0), nrows1);
     return img[(size_t)y * stride + x];
+}
+
+// float copy of the batch's images for the texture path (pitch in floats)
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride,
+                                                        int rows, int cols, int stride, float *dst, int pitch_f)
+{
+    const int b = blockIdx.y;
+    const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
+    float *D = dst + (size_t)b * rows * pitch_f;
+    const int total = rows * cols;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int y = i / cols, x = i - y * cols;
+        D[(size_t)y * pitch_f + x] = (float)img[(size_t)y * stride + x];
+    }
 }
 
 #define DESC_THREADS 256
@@ -1314,7 +1328,7 @@ __global__ void __launch_bounds__(DESC_THREADS) orient_describe_kernel(
 // ---------------------------------------------------------------- host: texture objects over the caller's images
 // One pitch-2D u8 texture per image (point sampled, used only through tex2Dgather).  Cached by (ptr, shape, pitch).
 struct TexKey { const void *p; int rows, cols, stride; bool operator<(const TexKey &o) const {
-    return std::tie(p, rows, cols, stride) < std::tie(o.p, o.rows, o.cols, o.stride); } };
+    return std::tie(p, rows, cols, stride) < std::tie(o.p, o.rows, o.cols, o.stride); } };   // stride: pitch in floats
 struct TexCache { std::map<TexKey, cudaTextureObject_t> m; int align = 512, pitch_align = 32; bool init = false; };
 
 void surf_tex_destroy(vfsms_ctx *ctx)
@@ -1326,35 +1340,29 @@ void surf_tex_destroy(vfsms_ctx *ctx)
     ctx->tex_cache = nullptr;
 }
 
-// returns false when some image cannot be bound (alignment): caller uses the LDG sampler
-static bool surf_textures(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b, int split, int batch, int rows, int cols,
-                          int stride, int64_t img_stride, cudaStream_t st, cudaTextureObject_t **dev_out)
+// Textures over the workspace's float copy of the images (our own allocation: always aligned).  Returns false only when
+// texture creation fails; the caller then uses the LDG sampler.
+static bool surf_textures(vfsms_ctx *ctx, int batch, int rows, int cols, int pitch_f, cudaStream_t st, cudaTextureObject_t **dev_out)
 {
     if (!ctx->tex_cache) ctx->tex_cache = new TexCache();
     TexCache *tc = (TexCache *)ctx->tex_cache;
-    if (!tc->init) {
-        cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) { tc->align = (int)prop.textureAlignment; tc->pitch_align = (int)prop.texturePitchAlignment; }
-        tc->init = true;
-    }
-    if (stride % tc->pitch_align) return false;
     if (tc->m.size() > 8192) {           // bound the cache: drop everything once idle
         cudaStreamSynchronize(st);
         for (auto &kv : tc->m) cudaDestroyTextureObject(kv.second);
         tc->m.clear();
     }
     std::vector<cudaTextureObject_t> h((size_t)batch);
+    const float *base = ctx->surf.img_f32.as<float>();
     for (int b = 0; b < batch; b++) {
-        const uint8_t *p = b < split ? base_a + (int64_t)b * img_stride : base_b + (int64_t)(b - split) * img_stride;
-        if (((uintptr_t)p) % tc->align) return false;
-        TexKey key{p, rows, cols, stride};
+        const float *p = base + (size_t)b * rows * pitch_f;
+        TexKey key{p, rows, cols, pitch_f};
         auto it = tc->m.find(key);
         if (it == tc->m.end()) {
             cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
             rd.resType = cudaResourceTypePitch2D;
             rd.res.pitch2D.devPtr = (void *)p;
-            rd.res.pitch2D.desc = cudaCreateChannelDesc<unsigned char>();
-            rd.res.pitch2D.width = cols; rd.res.pitch2D.height = rows; rd.res.pitch2D.pitchInBytes = stride;
+            rd.res.pitch2D.desc = cudaCreateChannelDesc<float>();
+            rd.res.pitch2D.width = cols; rd.res.pitch2D.height = rows; rd.res.pitch2D.pitchInBytes = (size_t)pitch_f * 4;
             cudaTextureDesc td; memset(&td, 0, sizeof(td));
             td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
             td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
@@ -1408,6 +1416,8 @@ int surf_reserve(vfsms_ctx *ctx, int batch, int rows, int cols, const vfsms_surf
     if ((rc = ws.prefix.reserve((size_t)(batch + 1) * 4))) return rc;
     if ((rc = ws.descT.reserve((size_t)batch * kp_cap * dim * 4))) return rc;
     if ((rc = ws.hist.reserve((size_t)batch * (RH_BINS + 1) * 4))) return rc;
+    ws.pitch_f = (cols + 31) & ~31;
+    if (!p->upright && (rc = ws.img_f32.reserve((size_t)batch * rows * ws.pitch_f * 4))) return rc;
     ws.max_features = max_features;
     ws.batch = batch; ws.rows = rows; ws.cols = cols; ws.cand_cap = cand_cap; ws.kp_cap = kp_cap; ws.dim = dim;
     return 0;
@@ -1562,7 +1572,14 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
     }
     StageTimer t_d(ctx, st, VFSMS_STAGE_DESCRIBE);
     cudaTextureObject_t *texs = nullptr;
-    const bool use_tex = surf_textures(ctx, base_a, base_b, split, batch, rows, cols, stride, img_stride, st, &texs);
+    bool use_tex = false;
+    if (!p->upright) {        // the rotated-window sampler reads a float copy of the images through the texture unit
+        if ((rc = ws.img_f32.reserve((size_t)batch * rows * ws.pitch_f * 4))) return rc;
+        u8_to_f32_kernel<<<dim3(std::min(ceil_div(rows * cols, 256), ctx->num_sms * 4), batch), 256, 0, st>>>(base_a, base_b, split, img_stride, rows, cols,
+                                                                                                            stride, ws.img_f32.as<float>(), ws.pitch_f);
+        LAUNCH_CHECK(ctx);
+        use_tex = surf_textures(ctx, batch, rows, cols, ws.pitch_f, st, &texs);
+    }
     int *work_counter = ws.counters.as<int32_t>() + (size_t)batch * 4;      // one extra slot after the per-image counters
     static const int var = getenv("VFSMS_DESCRIBE_VARIANT") ? atoi(getenv("VFSMS_DESCRIBE_VARIANT")) : 0;
 #define LAUNCH_WK(T, V, NB)                                                                                                        \

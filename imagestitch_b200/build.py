@@ -19,7 +19,6 @@ UNITS = {
     "orb.cu": ["-fmad=false"],
     "enhance.cu": ["-fmad=false"],
     "capi.cu": [],
-    "stubs.cu": [],
 }
 LIBS = ["-lcufft"]
 

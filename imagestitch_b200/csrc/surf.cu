@@ -794,8 +794,10 @@ __device__ __forceinline__ int floor_split(double x, double &fl)
 }
 
 // TEX variant: one tex2Dgather on a float copy of the image returns the whole 2x2 footprint as exact floats.
-__device__ __forceinline__ int window_pixel_tex(cudaTextureObject_t tex, const uint8_t *__restrict__ img, int stride,
-                                                int ncols1, int nrows1, double pixel_x, double pixel_y)
+// Returns the window pixel (cvRound of the bilinear value, 0..255) as an exact float: v + 1.5*2^23 - 1.5*2^23 rounds half to
+// even without leaving the FP32 pipe.
+__device__ __forceinline__ float window_pixel_tex(cudaTextureObject_t tex, const uint8_t *__restrict__ img, int stride,
+                                                  int ncols1, int nrows1, double pixel_x, double pixel_y)
 {
     double fx, fy;
     const int ix = floor_split(pixel_x, fx), iy = floor_split(pixel_y, fy);
@@ -806,11 +808,11 @@ __device__ __forceinline__ int window_pixel_tex(cudaTextureObject_t tex, const u
         const float4 g = tex2Dgather<float4>(tex, tx, ty, 0);
         const float p00 = g.w, p01 = g.z, p10 = g.x, p11 = g.y;
         const float v = p00 * (1.f - a) * (1.f - bq) + p01 * a * (1.f - bq) + p10 * (1.f - a) * bq + p11 * a * bq;
-        return round_half_even_u8(v) & 255;
+        return (v + 12582912.0f) - 12582912.0f;
     }
     int x = __double2int_rn(pixel_x), y = __double2int_rn(pixel_y);
     x = min(max(x, 0), ncols1); y = min(max(y, 0), nrows1);
-    return img[(size_t)y * stride + x];
+    return (float)img[(size_t)y * stride + x];
 }
 
 // float copy of the batch's images for the texture path (pitch in floats)
@@ -840,14 +842,15 @@ __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t *base_a, c
 //     accumulators of the 21 patch columns (lane dx owns column dx);
 //   * descriptor bins: lane = (cell, half) accumulates its 4 bins with predicated adds in raster order.
 struct __align__(16) WarpScratch {
-    float buf[800];              // orientation: X[0..127] Y[128..255] A[256..383] (int) ; descriptor: DX[0..399] DY[400..799]
+    float buf[800];              // orientation: X[0..127] Y[128..255] A[256..383] (int) ; window phase: one sampled row as exact
+                                 // floats (<= WK_MAX_WIN = 768 entries) ; descriptor: DX[0..399] DY[400..799]
     float vec[128];
-    uint8_t row[WK_MAX_WIN];     // one sampled window row
     uint8_t patch[448];
 };
 
-template <bool TEX, int VAR>      // VAR 0: 64 registers / 4 CTAs per SM, sampler unrolled x2;  1: 80 registers / 3 CTAs, x4;  2: 64 / 4 CTAs, x4
-__global__ void __launch_bounds__(WK_WARPS * 32, VAR == 1 ? 3 : 4) orient_describe_warp_kernel(
+// 64 registers / 4 CTAs per SM with the sampler unrolled x2 measured best on B200 (80 registers / 3 CTAs / x4: +20 % time).
+template <bool TEX>
+__global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
     const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
     int batch, int kp_cap, int extended, int upright, const cudaTextureObject_t *__restrict__ texs, int *work_counter)
@@ -963,8 +966,9 @@ __global__ void __launch_bounds__(WK_WARPS * 32, VAR == 1 ? 3 : 4) orient_descri
             ustart_x = __float2int_rn(cx + win_offset);
             ustart_y = __float2int_rn(cy - win_offset);
         }
-        int cur_row = -1;                 // row currently held in S.row
-        // sample window row `r` (>= cur_row) into S.row; rows are requested in nondecreasing order
+        float *rowf = S.buf;              // the orientation scratch is free now: one window row as exact float pixel values
+        int cur_row = -1;                 // row currently held in rowf
+        // sample window row `r` (>= cur_row) into rowf; rows are requested in nondecreasing order
         auto fetch_row = [&](int r) {
             if (r == cur_row) return;
             __syncwarp();
@@ -975,17 +979,17 @@ __global__ void __launch_bounds__(WK_WARPS * 32, VAR == 1 ? 3 : 4) orient_descri
                 // |x| < 2^13), so the running sum equals the CPU's column-by-column accumulation
                 double px = rx + (double)lane * (double)cos_dir, py = ry - (double)lane * (double)sin_dir;
                 const double dpx = 32.0 * (double)cos_dir, dpy = 32.0 * (double)sin_dir;
-#pragma unroll (VAR == 0 ? 2 : 4)
+#pragma unroll 2
                 for (int j = lane; j < win; j += 32, px += dpx, py -= dpy) {
-                    S.row[j] = (uint8_t)(TEX ? window_pixel_tex(tex, img, stride, ncols1, nrows1, px, py)
-                                             : window_pixel(img, stride, ncols1, nrows1, px, py));
+                    rowf[j] = TEX ? window_pixel_tex(tex, img, stride, ncols1, nrows1, px, py)
+                                  : (float)window_pixel(img, stride, ncols1, nrows1, px, py);
                 }
                 chain_x += sin_dir; chain_y += cos_dir;
             } else {
                 const int x = min(max(ustart_x + r, 0), cols - 1);
                 for (int j = lane; j < win; j += 32) {
                     const int y = min(max(ustart_y - j, 0), rows - 1);
-                    S.row[j] = img[(size_t)y * stride + x];
+                    rowf[j] = (float)img[(size_t)y * stride + x];
                 }
             }
             cur_row = r;
@@ -998,18 +1002,18 @@ __global__ void __launch_bounds__(WK_WARPS * 32, VAR == 1 ? 3 : 4) orient_descri
         const bool area_fast = fabs(scale - iscale) < DBL_EPSILON;
         const int dx = lane < PD ? lane : PD - 1;           // lanes >= 21 shadow column 20 (results discarded)
         if (win == PD) {
-            for (int dy = 0; dy < PD; dy++) { fetch_row(dy); if (lane < PD) S.patch[dy * PD + lane] = S.row[lane]; }
+            for (int dy = 0; dy < PD; dy++) { fetch_row(dy); if (lane < PD) S.patch[dy * PD + lane] = (uint8_t)(int)rowf[lane]; }
         } else if (area_fast) {
             const float fs = 1.f / (float)(iscale * iscale);
             for (int dy = 0; dy < PD; dy++) {
-                int sum = 0;
+                float sumf = 0;            // integer box sum (<= 35^2 * 255): exact in float
                 for (int yy = 0; yy < iscale; yy++) {
                     fetch_row(dy * iscale + yy);
-                    for (int xx = 0; xx < iscale; xx++) sum += S.row[dx * iscale + xx];
+                    for (int xx = 0; xx < iscale; xx++) sumf += rowf[dx * iscale + xx];
                 }
                 int out;
-                if (iscale == 2) out = (sum + 2) >> 2;
-                else out = min(max(__float2int_rn(sum * fs), 0), 255);
+                if (iscale == 2) out = (int)((sumf + 2.f) * 0.25f);          // (sum + 2) >> 2
+                else out = min(max(__float2int_rn(sumf * fs), 0), 255);
                 if (lane < PD) S.patch[dy * PD + lane] = (uint8_t)out;
             }
         } else {
@@ -1033,9 +1037,9 @@ __global__ void __launch_bounds__(WK_WARPS * 32, VAR == 1 ? 3 : 4) orient_descri
                     fetch_row(sy);
                     const float beta = (yl && sy == sy1 - 1) ? ayl : ((yr && sy == sy2) ? ayr : aym);
                     float bufv = 0;
-                    if (xl) bufv += u8_to_float(S.row[sx1 - 1]) * axl;
-                    for (int sx = sx1; sx < sx2; sx++) bufv += u8_to_float(S.row[sx]) * axm;
-                    if (xr) bufv += u8_to_float(S.row[sx2]) * axr;
+                    if (xl) bufv += rowf[sx1 - 1] * axl;
+                    for (int sx = sx1; sx < sx2; sx++) bufv += rowf[sx] * axm;
+                    if (xr) bufv += rowf[sx2] * axr;
                     if (first) { sum = beta * bufv; first = false; } else sum += beta * bufv;
                 }
                 if (lane < PD) S.patch[dy * PD + lane] = (uint8_t)min(max(round_half_even_u8(sum), 0), 255);
@@ -1581,17 +1585,11 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         use_tex = surf_textures(ctx, batch, rows, cols, ws.pitch_f, st, &texs);
     }
     int *work_counter = ws.counters.as<int32_t>() + (size_t)batch * 4;      // one extra slot after the per-image counters
-    static const int var = getenv("VFSMS_DESCRIBE_VARIANT") ? atoi(getenv("VFSMS_DESCRIBE_VARIANT")) : 0;
-#define LAUNCH_WK(T, V, NB)                                                                                                        \
-    orient_describe_warp_kernel<T, V><<<ctx->num_sms * NB, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride, \
-        ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap,                    \
+#define LAUNCH_WK(T)                                                                                                               \
+    orient_describe_warp_kernel<T><<<ctx->num_sms * 4, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,  \
+        ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap,              \
         p->extended, p->upright, texs, work_counter)
-    if (use_tex) {
-        if (var == 1) LAUNCH_WK(true, 1, 3); else if (var == 2) LAUNCH_WK(true, 2, 4); else LAUNCH_WK(true, 0, 4);
-    } else {
-        texs = nullptr;
-        LAUNCH_WK(false, 0, 4);
-    }
+    if (use_tex) LAUNCH_WK(true); else { texs = nullptr; LAUNCH_WK(false); }
 #undef LAUNCH_WK
     LAUNCH_CHECK(ctx);
     orient_describe_kernel<<<ctx->num_sms * 2, DESC_THREADS, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,

@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=32, help="tile pairs per GPU per step")
     ap.add_argument("--batches", type=int, default=3, help="distinct input batches rotated through (L2 hygiene)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--matcher", default=None, choices=["tc", "tc_1sm", "simt"], help="override the descriptor matcher kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -165,6 +166,8 @@ def main():
     P, NB = args.pairs, args.batches
     L = int(np.floor(TILE * ROI_RATIO))
     params = gpu.surf_params()          # GPU-SURF defaults, ImageUtility.py:23-28
+    if args.matcher:
+        gpu.set_matcher(args.matcher, device=local)
 
     # ---- synthetic input, resident in HBM: NB distinct batches of P tile pairs (2 x NB x P x 4 MiB)
     batches = []
@@ -299,6 +302,7 @@ def main():
         fl = 2.0 * mean_na * mean_nb * D * P
         matcher = {"stage_ms": stage_ms["match_tc"], "algorithmic_tflops": fl / tm / 1e12, "frac_of_bf16_sustained": fl / tm / 1e12 / peaks["bf16_tflops_sustained"],
                    "gbs": (4 * D * (mean_na + mean_nb) + 16 * mean_na) * P / tm / 1e9,
+                   "kernel": args.matcher or "tc", "exact_rescans_last_step": gpu.last_match_fallbacks(local), "queries_per_step": int(mean_na * P),
                    "note": "stage = split + tcgen05 GEMM + exact rescoring + fallback; the GEMM executes 3.5x the algorithmic FLOPs (3-term split-bf16 + norm columns)"}
     surf_kps = (mean_na + mean_nb) * P * world / (sum(stage_ms.get(k, 0) for k in ("integral", "hessian_nms", "rank_sort", "validate_compact", "orient_describe")) * 1e-3)
 

@@ -54,7 +54,7 @@ int vfsms_profile_read(vfsms_ctx *ctx, float *ms_out, int32_t *calls_out, int re
 
 int vfsms_set_matcher(vfsms_ctx *ctx, int mode)
 {
-    if (!ctx || mode < 0 || mode > 1) { vfsms_set_error("vfsms_set_matcher: bad arguments"); return VFSMS_E_ARG; }
+    if (!ctx || mode < 0 || mode > 2) { vfsms_set_error("vfsms_set_matcher: bad arguments"); return VFSMS_E_ARG; }
     ctx->matcher_mode = mode;
     return 0;
 }
@@ -176,7 +176,7 @@ int vfsms_match_descriptors(vfsms_ctx *ctx, const float *desc_a, int n_a, const 
     if (n_a == 0 || n_b == 0) return 0;
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const int cap = (((n_a > n_b ? n_a : n_b) + 127) / 128) * 128;
+    const int cap = (((n_a > n_b ? n_a : n_b) + 255) / 256) * 256;
     int rc;
     if ((rc = ctx->scratch0.reserve((size_t)cap * dim * 4))) return rc;   // A row-major
     if ((rc = ctx->scratch1.reserve((size_t)cap * dim * 4))) return rc;   // B row-major
@@ -192,7 +192,7 @@ int vfsms_match_descriptors(vfsms_ctx *ctx, const float *desc_a, int n_a, const 
     if (feature_type == 3) {
         if ((rc = match_hamming_batch(ctx, ctx->scratch0.as<float>(), cn, 0, ctx->scratch1.as<float>(), cn + 1, 0, 1, cap, dim, 0, 0,
                                       mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(), st))) return rc;
-    } else if (ctx->matcher_mode == 0 && dim % 32 == 0 && dim <= 128) {
+    } else if (ctx->matcher_mode != 1 && dim % 32 == 0 && dim <= 128) {
         if ((rc = match_tc_batch(ctx, ctx->scratch0.as<float>(), cn, 0, ctx->scratch1.as<float>(), cn + 1, 0, 1, cap, dim,
                                  mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(), st))) return rc;
     } else {
@@ -254,7 +254,7 @@ static int align_batch_launch(vfsms_ctx *ctx, const uint8_t *a_dev, const uint8_
     const int32_t *nfin = ws.counters.as<int32_t>() + 2;     // n_final of image b at [b*4]
     const int32_t *flags = ws.counters.as<int32_t>() + 3;
     MatchWorkspace &mw = ctx->match;
-    const bool use_tc = ctx->matcher_mode == 0 && cap % 128 == 0 && dim % 32 == 0 && dim <= 128;
+    const bool use_tc = ctx->matcher_mode != 1 && cap % 128 == 0 && dim % 32 == 0 && dim <= 128;
     if (use_tc) {
         const float *DA = ws.desc.as<float>(), *DB = DA + (size_t)n_pairs * cap * dim;
         if ((rc = match_tc_batch(ctx, DA, nfin, 4, DB, nfin + 4 * n_pairs, 4, n_pairs, cap, dim, mw.best_idx.as<int32_t>(),

@@ -1407,7 +1407,7 @@ int surf_reserve(vfsms_ctx *ctx, int batch, int rows, int cols, const vfsms_surf
         if (max_features == 0 && ws.kp_cap > kp_cap) kp_cap = ws.kp_cap;
     }
     cand_cap = (cand_cap + 255) & ~255;
-    kp_cap = (kp_cap + 127) & ~127;                     // matcher tiles are 128 (tcgen05) / 64 (SIMT) wide
+    kp_cap = (kp_cap + 255) & ~255;                     // matcher tiles: 256 train rows per CTA pair (tcgen05), 64 (SIMT)
     const int n_bands = ceil_div(rows, INT_BAND);
     int rc;
     if ((rc = ws.integral.reserve((size_t)batch * (rows + 1) * (cols + 1) * 4))) return rc;

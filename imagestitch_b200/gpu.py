@@ -253,8 +253,9 @@ def enhance(image, clahe=False, clip_limit=20, tile_size=5, device=0):
 
 
 def set_matcher(mode, device=0):
-    """'tc' (default): tcgen05 candidates + exact rescoring; 'simt': exact fp32 SIMT kernel.  Identical results."""
-    check(_lib.load().vfsms_set_matcher(_lib.context(device), {"tc": 0, "simt": 1}[mode]), "vfsms_set_matcher")
+    """'tc' (default): tcgen05 candidates (CTA pairs) + exact rescoring; 'tc_1sm': the same on single CTAs;
+    'simt': exact fp32 SIMT kernel.  Identical results."""
+    check(_lib.load().vfsms_set_matcher(_lib.context(device), {"tc": 0, "simt": 1, "tc_1sm": 2}[mode]), "vfsms_set_matcher")
 
 
 def last_match_fallbacks(device=0):

@@ -77,7 +77,8 @@ void *vfsms_stream(vfsms_ctx *ctx);           /* the context's cudaStream_t */
 int64_t vfsms_launch_count(vfsms_ctx *ctx);
 
 /* Matcher selection: 0 (default) = tcgen05 split-bf16 GEMM candidates + exact fp32 rescoring (+ exact fallback),
- * 1 = exact fp32 SIMT kernel.  Both produce identical results; 1 exists for verification. */
+ * 1 = exact fp32 SIMT kernel, 2 = like 0 with the GEMM on single CTAs (128 x 128 tiles, cta_group::1) instead of CTA pairs.
+ * All produce identical results; 1 and 2 exist for verification. */
 int vfsms_set_matcher(vfsms_ctx *ctx, int mode);
 /* Number of queries of the last tensor-core match that needed the exact fallback scan (synchronises the stream). */
 int vfsms_last_match_fallbacks(vfsms_ctx *ctx, int *count_out);

@@ -30,8 +30,13 @@ def test_tc_equals_simt_and_oracle(gpu, na, nb, d):
         gpu.set_matcher("tc")
         m_tc = gpu.match_descriptors(A, B, 2, ratio)
         fb = gpu.last_match_fallbacks()
+        gpu.set_matcher("tc_1sm")
+        m_cl = gpu.match_descriptors(A, B, 2, ratio)
+        fb_cl = gpu.last_match_fallbacks()
         gpu.set_matcher("simt")
         m_simt = gpu.match_descriptors(A, B, 2, ratio)
+        assert np.array_equal(m_cl, m_simt)
+        assert fb_cl <= max(2, na // 50)
         m_or = surf.match_l2_ratio(A, B, ratio)
         assert np.array_equal(m_tc, m_simt)
         assert np.array_equal(m_tc, m_or)

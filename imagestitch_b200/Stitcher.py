@@ -50,6 +50,33 @@ def _imread(path, flag):
     return cv2.imdecode(np.fromfile(path, dtype=np.uint8), flag)
 
 
+def _imread_gray_many(paths, decoder="b200"):
+    """Grayscale decode of a tile sequence (Stitcher.py:68-69 decodes them one by one, twice).  JPEG files go through the
+    library in batches -- host cores do the entropy decoding of many files at once, the device the IDCT; the pixels are
+    bit-identical to cv2.imdecode(..., 0) -- anything the library does not support (progressive JPEG, PNG, ...) through cv2."""
+    datas = [np.fromfile(p, dtype=np.uint8) for p in paths]
+    images = [None] * len(paths)
+    if decoder == "b200":
+        groups = {}
+        for k, d in enumerate(datas):
+            if d.size > 3 and d[0] == 0xFF and d[1] == 0xD8:
+                try:
+                    groups.setdefault(gpu.jpeg_info(d)[:2], []).append(k)
+                except gpu.JpegUnsupported:
+                    pass
+        for idx in groups.values():
+            try:
+                out = gpu.jpeg_decode_gray([datas[k] for k in idx])
+            except gpu.JpegUnsupported:
+                continue
+            for j, k in enumerate(idx):
+                images[k] = out[j]
+    for k, d in enumerate(datas):
+        if images[k] is None:
+            images[k] = cv2.imdecode(d, cv2.IMREAD_GRAYSCALE)
+    return images
+
+
 class Stitcher(Utility.Method):
     isColorMode = True
     direction = 1           # 1: B below A, 2: B right of A, 3: B above A, 4: B left of A
@@ -59,6 +86,7 @@ class Stitcher(Utility.Method):
     tempImageFeature = ImageFeature()
     imageFusion = ImageFusion.ImageFusion()
     batchPairs = 16         # pairs evaluated per fused device call in flowStitch
+    decoder = "b200"        # "b200": JPEG tiles decoded by the library (bit-identical to cv2); "cv2": cv2.imdecode
 
     # ------------------------------------------------------------------ direction bookkeeping
     def directionIncrease(self, direction):
@@ -80,7 +108,7 @@ class Stitcher(Utility.Method):
         startTime = time.time()
         status = True
         endfileIndex = 0
-        images = [_imread(f, cv2.IMREAD_GRAYSCALE) for f in fileList]      # decoded once (the reference decodes every tile twice)
+        images = _imread_gray_many(fileList, self.decoder)                   # decoded once (the reference decodes every tile twice)
         batched = self._is_incre_feature_method(caculateOffsetMethod) and self.featureMethod == "surf" \
             and self.offsetCaculate == "mode" and not self.isEnhance
         table = {}
@@ -102,7 +130,11 @@ class Stitcher(Utility.Method):
 
         self.printAndWrite("start stitching")
         startTime = time.time()
-        stitchImage = self.getStitchByOffset(fileList, offsetList)
+        self._gray_cache = dict(zip(fileList, images))      # gray mosaics reuse the decoded tiles (the reference decodes them again)
+        try:
+            stitchImage = self.getStitchByOffset(fileList, offsetList)
+        finally:
+            self._gray_cache = {}
         endTime = time.time()
         self.printAndWrite("The time of fusing is " + str(endTime - startTime) + "s")
         if status == False:
@@ -319,6 +351,10 @@ class Stitcher(Utility.Method):
         """Global offset rectification on the host (Stitcher.py:378-431, integer bookkeeping kept verbatim in behaviour),
         paste + blend on a device canvas (Stitcher.py:433-486)."""
         flag = cv2.IMREAD_COLOR if self.isColorMode else cv2.IMREAD_GRAYSCALE
+        cache = {} if self.isColorMode else getattr(self, "_gray_cache", {})
+
+        def _imread(path, flag):
+            return cache[path] if path in cache else globals()["_imread"](path, flag)
         imageList = [_imread(fileList[0], flag)]
         resultRow, resultCol = imageList[0].shape[0], imageList[0].shape[1]
         originOffsetList.insert(0, [0, 0])          # the reference mutates its argument the same way

@@ -33,6 +33,7 @@ EXPORTS = [
     "vfsms_match_batch_dev", "vfsms_phase_correlate_host", "vfsms_phase_correlate_dev", "vfsms_fuse_roi_host",
     "vfsms_mosaic_host", "vfsms_profile_enable", "vfsms_profile_read", "vfsms_stage_name",
     "vfsms_set_matcher", "vfsms_last_match_fallbacks", "vfsms_enhance_host",
+    "vfsms_jpeg_info", "vfsms_jpeg_luma_coefficients", "vfsms_jpeg_decode_gray_dev", "vfsms_jpeg_decode_gray_host",
 ]
 STAGE_COUNT = 12
 

@@ -18,6 +18,7 @@ UNITS = {
     "blend.cu": ["-fmad=false"],
     "orb.cu": ["-fmad=false"],
     "enhance.cu": ["-fmad=false"],
+    "jpeg.cu": [],
     "capi.cu": [],
 }
 LIBS = ["-lcufft"]

@@ -148,6 +148,8 @@ struct vfsms_ctx {
     DevBuf results;           // vfsms_pair_result[pairs]
     DevBuf scratch0, scratch1, scratch2, scratch3;
     HostBuf pinned_in, pinned_out;
+    HostBuf jpeg_pinned;       // entropy-decoded luma coefficients of one chunk of files (jpeg.cu)
+    DevBuf jpeg_coef, jpeg_out;
     void *tex_cache = nullptr;     // texture objects over caller images (surf.cu)
     DevBuf tex_dev;
     void *phase_state = nullptr;   // cuFFT plans etc. (phase.cu)

@@ -291,3 +291,73 @@ def device_count():
 
 __all__ = ["surf_params", "surf_detect_and_describe", "match_descriptors", "offset_by_mode", "align_batch",
            "align_batch_dev", "launch_count", "synchronize", "device_count", "VfsmsError"]
+
+
+# ---------------------------------------------------------------- JPEG tile decode
+class JpegUnsupported(_lib.VfsmsError):
+    """The file is not a sequential-Huffman 8-bit grayscale / YCbCr JPEG; callers fall back to their own decoder."""
+
+
+def _jpeg_check(rc, what):
+    if rc == -6:
+        raise JpegUnsupported("%s: %s" % (what, _lib.load().vfsms_last_error().decode()))
+    check(rc, what)
+
+
+def jpeg_info(data):
+    """(rows, cols, components) of a JPEG byte string; host-only."""
+    buf = np.frombuffer(data, np.uint8)
+    r, c, n = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _jpeg_check(_lib.load().vfsms_jpeg_info(buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(buf.size), ctypes.byref(r), ctypes.byref(c),
+                                           ctypes.byref(n)), "vfsms_jpeg_info")
+    return r.value, c.value, n.value
+
+
+def jpeg_luma_coefficients(data):
+    """Host-only entropy stage: (coef int16 [blocks_h, blocks_w, 64] natural order, quant uint16[64])."""
+    L = _lib.load()
+    buf = np.frombuffer(data, np.uint8)
+    bh, bw = ctypes.c_int(), ctypes.c_int()
+    quant = np.zeros(64, np.uint16)
+    p = buf.ctypes.data_as(ctypes.c_void_p)
+    _jpeg_check(L.vfsms_jpeg_luma_coefficients(p, ctypes.c_size_t(buf.size), None, ctypes.c_size_t(0), ctypes.byref(bh), ctypes.byref(bw),
+                                               quant.ctypes.data_as(ctypes.c_void_p)), "vfsms_jpeg_luma_coefficients")
+    coef = np.empty((bh.value, bw.value, 64), np.int16)
+    _jpeg_check(L.vfsms_jpeg_luma_coefficients(p, ctypes.c_size_t(buf.size), coef.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(coef.size),
+                                               ctypes.byref(bh), ctypes.byref(bw), quant.ctypes.data_as(ctypes.c_void_p)),
+                "vfsms_jpeg_luma_coefficients")
+    return coef, quant
+
+
+def _jpeg_args(datas):
+    bufs = [np.frombuffer(d, np.uint8) for d in datas]
+    n = len(bufs)
+    ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
+    sizes = (ctypes.c_size_t * n)(*[b.size for b in bufs])
+    return bufs, ptrs, sizes
+
+
+def jpeg_decode_gray(datas, device=0):
+    """cv2.imdecode(data, cv2.IMREAD_GRAYSCALE) for a list of JPEG byte strings of identical geometry -> u8 [n, rows, cols]
+    (bit-identical to cv2).  Entropy decoding on the host cores, IDCT on the device."""
+    single = isinstance(datas, (bytes, bytearray, memoryview, np.ndarray))
+    if single:
+        datas = [datas]
+    rows, cols, _ = jpeg_info(datas[0])
+    bufs, ptrs, sizes = _jpeg_args(datas)
+    out = np.empty((len(bufs), rows, cols), np.uint8)
+    _jpeg_check(_lib.load().vfsms_jpeg_decode_gray_host(_lib.context(device), len(bufs), ptrs, sizes, out.ctypes.data_as(ctypes.c_void_p), rows, cols),
+                "vfsms_jpeg_decode_gray_host")
+    return out[0] if single else out
+
+
+def jpeg_decode_gray_dev(datas, out, device=0, stream=None):
+    """Decode into a device-resident tile stack: `out` is a torch.uint8 CUDA tensor [n, rows, cols] (any row / image stride)."""
+    rows, cols, _ = jpeg_info(datas[0])
+    assert out.is_cuda and out.dim() == 3 and out.shape[0] == len(datas) and out.shape[1] == rows and out.shape[2] == cols and out.stride(2) == 1
+    bufs, ptrs, sizes = _jpeg_args(datas)
+    _jpeg_check(_lib.load().vfsms_jpeg_decode_gray_dev(_lib.context(device), len(bufs), ptrs, sizes, ctypes.c_void_p(out.data_ptr()), rows, cols,
+                                                       ctypes.c_int64(out.stride(1)), ctypes.c_int64(out.stride(0)),
+                                                       ctypes.c_void_p(stream.cuda_stream if stream is not None else 0)),
+                "vfsms_jpeg_decode_gray_dev")
+    return out

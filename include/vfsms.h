@@ -194,6 +194,27 @@ int vfsms_mosaic_host(vfsms_ctx *ctx, const uint8_t *tiles, int n_tiles, int til
                       const int32_t *pair_offset /* n x 2 original offsets */, int method,
                       int canvas_rows, int canvas_cols, uint8_t *canvas_out);
 
+/* ---------------------------------------------------------------- JPEG tile decode */
+
+/* Replace `cv2.imdecode(np.fromfile(f, dtype=np.uint8), 0)` (Stitcher.py:68-69; the same files are decoded again at
+ * :382 and :401): grayscale decode = luma component only (libjpeg JCS_GRAYSCALE), entropy decoding on the host cores
+ * (files in parallel), dequantisation + accurate integer IDCT (jidctint.c islow) + range limit on the device.
+ * Output is bit-identical to cv2.imdecode(..., 0).  Supported: SOF0 / SOF1 (sequential Huffman), 8-bit, one interleaved
+ * scan or a single component, restart intervals; anything else -> VFSMS_E_UNSUPPORTED (callers fall back to cv2).
+ * vfsms_jpeg_info and vfsms_jpeg_luma_coefficients are host-only (no context, no GPU). */
+int vfsms_jpeg_info(const uint8_t *data, size_t size, int *rows, int *cols, int *components);
+/* Entropy stage alone: quantised luma coefficients, int16, natural (row-major) order, blocks_h x blocks_w x 64, and the
+ * luma quantisation table (natural order).  coef == NULL only reports the geometry. */
+int vfsms_jpeg_luma_coefficients(const uint8_t *data, size_t size, int16_t *coef, size_t coef_capacity, int *blocks_h,
+                                 int *blocks_w, uint16_t *quant /* 64 */);
+/* n_images files of identical geometry (rows x cols, checked).  _dev: image i lands at
+ * out_dev + i * image_stride + y * row_stride + x in HBM (the device-resident tile stack the align / mosaic entry points
+ * read in place).  _host: out = n_images x rows x cols u8, contiguous, host memory. */
+int vfsms_jpeg_decode_gray_dev(vfsms_ctx *ctx, int n_images, const uint8_t *const *data, const size_t *sizes,
+                               uint8_t *out_dev, int rows, int cols, int64_t row_stride, int64_t image_stride, void *stream);
+int vfsms_jpeg_decode_gray_host(vfsms_ctx *ctx, int n_images, const uint8_t *const *data, const size_t *sizes,
+                                uint8_t *out, int rows, int cols);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,97 @@
+"""JPEG tile decode, CPU side: the oracle restatement is pinned against cv2.imdecode (the reference's decoder call,
+Stitcher.py:68-69), and the library's host entropy stage is checked against the oracle.  No GPU needed."""
+import hashlib
+import json
+import os
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import jpeg_oracle as jo
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+SAMPLINGS = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420,
+             cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411]
+
+
+def _image(rows, cols, seed, channels=3):
+    rng = np.random.default_rng(seed)
+    img = cv2.GaussianBlur(rng.standard_normal((rows + 8, cols + 8, channels)).astype(np.float32), (0, 0), 2.0) * 300 + 128
+    img = img.reshape(rows + 8, cols + 8, channels)
+    img += rng.standard_normal(img.shape).astype(np.float32) * 6
+    img = img[:rows, :cols].clip(0, 255).astype(np.uint8)
+    return np.ascontiguousarray(img[:, :, 0] if channels == 1 else img)
+
+
+def _encode(img, quality=90, sampling=None, restart=0):
+    p = [cv2.IMWRITE_JPEG_QUALITY, quality, cv2.IMWRITE_JPEG_RST_INTERVAL, restart]
+    if sampling is not None:
+        p += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sampling]
+    ok, buf = cv2.imencode(".jpg", img, p)
+    assert ok
+    return buf.tobytes()
+
+
+@pytest.mark.parametrize("sampling", SAMPLINGS)
+@pytest.mark.parametrize("quality,restart", [(35, 0), (92, 5), (100, 1)])
+def test_oracle_equals_cv2(sampling, quality, restart):
+    data = _encode(_image(75, 131, quality + restart), quality, sampling, restart)
+    ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_GRAYSCALE)
+    assert np.array_equal(jo.decode_gray(data), ref)
+
+
+def test_oracle_grayscale_file_and_tiny_sizes():
+    for rows, cols in [(1, 1), (7, 9), (8, 8), (16, 16), (17, 33)]:
+        data = _encode(_image(rows, cols, rows * 100 + cols, channels=1), 80)
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_GRAYSCALE)
+        assert np.array_equal(jo.decode_gray(data), ref)
+
+
+def test_range_limit_wraps_like_libjpeg():
+    x = np.arange(-2048, 2048)
+    idx = x & 1023
+    table = np.concatenate([np.arange(128, 256), np.full(384, 255), np.zeros(384, np.int64), np.arange(0, 128)])   # jdmaster.c prepare_range_limit_table
+    assert np.array_equal(jo.range_limit(x), table[idx].astype(np.uint8))
+
+
+@pytest.mark.parametrize("sampling", SAMPLINGS)
+def test_host_entropy_stage_equals_oracle(sampling):
+    from imagestitch_b200 import gpu
+    data = _encode(_image(203, 157, 11), 88, sampling, restart=3)
+    info, coef_o = jo.luma_coefficients(data)
+    coef, quant = gpu.jpeg_luma_coefficients(data)
+    assert coef.shape == coef_o.shape and np.array_equal(coef, coef_o)
+    assert np.array_equal(quant.astype(np.int32), info["quant"][info["comps"][0][3]])
+    assert gpu.jpeg_info(data) == (203, 157, 3)
+
+
+def test_golden_files_through_host_stage_and_oracle_idct():
+    """The reference's own tiles (custom Huffman / quantisation tables of the microscope software)."""
+    from imagestitch_b200 import gpu
+    cases = json.load(open(os.path.join(GOLDEN, "jpeg_cases.json")))
+    assert cases["_demo_sweep"]["files"] == cases["_demo_sweep"]["bit_exact_vs_cv2"] == 140
+    for name, c in cases.items():
+        if name.startswith("_"):
+            continue
+        data = np.fromfile(os.path.join(GOLDEN, name), np.uint8).tobytes()
+        coef, quant = gpu.jpeg_luma_coefficients(data)
+        img = jo.idct_islow(coef, quant.astype(np.int32))[:c["rows"], :c["cols"]]
+        assert hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest() == c["sha256_of_cv2_imdecode_gray"]
+        assert np.array_equal(img, cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_GRAYSCALE))
+
+
+def test_unsupported_and_damaged_input():
+    from imagestitch_b200 import gpu
+    img = _image(64, 64, 3)
+    ok, prog = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    with pytest.raises(gpu.JpegUnsupported):
+        gpu.jpeg_info(prog.tobytes())
+    with pytest.raises(gpu.JpegUnsupported):
+        gpu.jpeg_info(b"\x89PNG\r\n\x1a\n" + bytes(64))
+    data = _encode(img, 90)
+    # a truncated entropy segment decodes to *something* of the right geometry without reading out of bounds (libjpeg warns and pads)
+    coef, _ = gpu.jpeg_luma_coefficients(data[: len(data) // 2])
+    assert coef.shape == (8, 8, 64)
+    with pytest.raises(gpu.JpegUnsupported):
+        gpu.jpeg_info(data[:30])

@@ -77,6 +77,42 @@ def _imread_gray_many(paths, decoder="b200"):
     return images
 
 
+def _load_sequence(paths, decoder="b200", keep_on_device=True):
+    """Decode a tile sequence ONCE.  -> (host gray images, on_device).  With decoder "b200" and equally sized tiles the
+    tiles also stay in the library's device-resident stack (slot k = paths[k]): JPEG files are decoded straight into it,
+    the rest is decoded by cv2 and uploaded; the host copies are then a download of the stack."""
+    if decoder != "b200" or not keep_on_device:
+        return _imread_gray_many(paths, decoder), False
+    datas = [np.fromfile(p, dtype=np.uint8) for p in paths]
+    shapes, jpeg_ok = [], []
+    for d in datas:
+        try:
+            r, c, _ = gpu.jpeg_info(d)
+            shapes.append((r, c)); jpeg_ok.append(True)
+        except gpu.VfsmsError:
+            shapes.append(None); jpeg_ok.append(False)
+    others = {k: cv2.imdecode(datas[k], cv2.IMREAD_GRAYSCALE) for k in range(len(paths)) if not jpeg_ok[k]}
+    for k, im in others.items():
+        shapes[k] = None if im is None else im.shape[:2]
+    if any(sh is None for sh in shapes) or len(set(shapes)) != 1:
+        return _imread_gray_many(paths, decoder), False
+    rows, cols = shapes[0]
+    n = len(paths)
+    gpu.tiles_reserve(n, rows, cols)
+    k = 0
+    while k < n:                                     # runs of JPEG files are decoded with one call each
+        e = k
+        while e < n and jpeg_ok[e] == jpeg_ok[k]:
+            e += 1
+        if jpeg_ok[k]:
+            gpu.tiles_decode_jpeg(k, [datas[j] for j in range(k, e)])
+        else:
+            gpu.tiles_upload(k, np.stack([others[j] for j in range(k, e)]))
+        k = e
+    host = gpu.tiles_download(0, n, rows, cols)
+    return [host[j] for j in range(n)], True
+
+
 class Stitcher(Utility.Method):
     isColorMode = True
     direction = 1           # 1: B below A, 2: B right of A, 3: B above A, 4: B left of A
@@ -108,9 +144,10 @@ class Stitcher(Utility.Method):
         startTime = time.time()
         status = True
         endfileIndex = 0
-        images = _imread_gray_many(fileList, self.decoder)                   # decoded once (the reference decodes every tile twice)
         batched = self._is_incre_feature_method(caculateOffsetMethod) and self.featureMethod == "surf" \
             and self.offsetCaculate == "mode" and not self.isEnhance
+        # decoded once (the reference decodes every tile twice, and a third time for the mosaic)
+        images, self._on_device = _load_sequence(fileList, self.decoder, keep_on_device=batched or not self.isColorMode)
         table = {}
         for fileIndex in range(0, fileNum - 1):
             self.printAndWrite("stitching " + str(fileList[fileIndex]) + " and " + str(fileList[fileIndex + 1]))
@@ -131,10 +168,13 @@ class Stitcher(Utility.Method):
         self.printAndWrite("start stitching")
         startTime = time.time()
         self._gray_cache = dict(zip(fileList, images))      # gray mosaics reuse the decoded tiles (the reference decodes them again)
+        self._stack_files = list(fileList) if self._on_device else None
         try:
             stitchImage = self.getStitchByOffset(fileList, offsetList)
         finally:
             self._gray_cache = {}
+            self._stack_files = None
+            self._on_device = False
         endTime = time.time()
         self.printAndWrite("The time of fusing is " + str(endTime - startTime) + "s")
         if status == False:
@@ -327,6 +367,12 @@ class Stitcher(Utility.Method):
                 break
         if not idx:
             return
+        if getattr(self, "_on_device", False):
+            L = int(np.floor((images[start].shape[0] if d in (1, 3) else images[start].shape[1]) * self.roiRatio))
+            res = gpu.tiles_align(idx[0], len(idx), d, L, params=self._surf_params(), ratio=self.searchRatio, offset_evaluate=self.offsetEvaluate)
+            for k, r in zip(idx, res):
+                table[(k, 1, d)] = (bool(r["status"]), [int(r["d_row"]), int(r["d_col"])])
+            return
         roisA = np.stack([np.ascontiguousarray(self.getROIRegionForIncreMethod(images[k], d, "first", self.roiRatio)) for k in idx])
         roisB = np.stack([np.ascontiguousarray(self.getROIRegionForIncreMethod(images[k + 1], d, "second", self.roiRatio)) for k in idx])
         res = gpu.align_batch(roisA, roisB, params=self._surf_params(), ratio=self.searchRatio, offset_evaluate=self.offsetEvaluate)
@@ -336,6 +382,11 @@ class Stitcher(Utility.Method):
     def _surf_evaluator(self, k, table):
         def evaluate(i, d):
             key = (k, i, d)
+            if key not in table and getattr(self, "_on_device", False):
+                shape = self._cur_images[0].shape
+                L = int(np.floor((shape[0] if d in (1, 3) else shape[1]) * (i * self.roiRatio)))
+                r = gpu.tiles_align(k, 1, d, L, params=self._surf_params(), ratio=self.searchRatio, offset_evaluate=self.offsetEvaluate)[0]
+                table[key] = (bool(r["status"]), [int(r["d_row"]), int(r["d_col"])])
             if key not in table:
                 roiA = self.getROIRegionForIncreMethod(self._cur_images[0], direction=d, order="first", searchRatio=i * self.roiRatio)
                 roiB = self.getROIRegionForIncreMethod(self._cur_images[1], direction=d, order="second", searchRatio=i * self.roiRatio)
@@ -404,6 +455,10 @@ class Stitcher(Utility.Method):
             rois[i] = (max(offsetList[i][0], rangeX[i - 1][0]), max(offsetList[i][1], rangeY[i - 1][0]),
                        min(offsetList[i][0] + imageList[i].shape[0], rangeX[i - 1][1]),
                        min(offsetList[i][1] + imageList[i].shape[1], rangeY[i - 1][1]))
+        if same_shape and self.fuseMethod in gpu.DEVICE_MOSAIC_METHODS and not self.isColorMode \
+                and getattr(self, "_stack_files", None) is not None and self._stack_files[:n] == list(fileList[:n]):
+            return gpu.tiles_mosaic(0, n, np.asarray(offsetList, np.int32), rois, np.asarray(originOffsetList, np.int32),
+                                    self.fuseMethod, (resultRow, resultCol))
         if same_shape and self.fuseMethod in gpu.DEVICE_MOSAIC_METHODS:
             return gpu.mosaic(np.stack(imageList), np.asarray(offsetList, np.int32), rois, np.asarray(originOffsetList, np.int32),
                               self.fuseMethod, (resultRow, resultCol))

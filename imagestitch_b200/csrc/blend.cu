@@ -523,10 +523,12 @@ int vfsms_fuse_roi_host(vfsms_ctx *ctx, const int16_t *a, const int16_t *b, int 
     return 0;
 }
 
-int vfsms_mosaic_host(vfsms_ctx *ctx, const uint8_t *tiles, int n_tiles, int tile_rows, int tile_cols, int channels,
+// tiles_host: n_tiles x (tile_rows x tile_cols x channels) in host memory, or nullptr with tiles_dev pointing at the same layout in HBM
+static int mosaic_run(vfsms_ctx *ctx, const uint8_t *tiles_host, const uint8_t *tiles_dev, int n_tiles, int tile_rows, int tile_cols, int channels,
                       const int32_t *tile_origin, const int32_t *roi_rect, const int32_t *pair_offset, int method,
                       int canvas_rows, int canvas_cols, uint8_t *canvas_out)
 {
+    const uint8_t *tiles = tiles_host ? tiles_host : tiles_dev;
     if (!ctx || !tiles || !tile_origin || !roi_rect || !pair_offset || !canvas_out || n_tiles < 1 || (channels != 1 && channels != 3)) {
         vfsms_set_error("mosaic: bad arguments"); return VFSMS_E_ARG;
     }
@@ -549,9 +551,10 @@ int vfsms_mosaic_host(vfsms_ctx *ctx, const uint8_t *tiles, int n_tiles, int til
     for (int i = 0; i < n_tiles; i++) {
         const int r0 = tile_origin[2 * i], c0 = tile_origin[2 * i + 1];
         if (r0 < 0 || c0 < 0 || r0 + tile_rows > canvas_rows || c0 + tile_cols > canvas_cols) { vfsms_set_error("mosaic: tile %d outside the canvas", i); return VFSMS_E_ARG; }
-        CUDA_TRY(cudaMemcpyAsync(bs->tiles_all.p, tiles + (size_t)i * tile_bytes, tile_bytes, cudaMemcpyHostToDevice, st));
+        const uint8_t *t8 = tiles_dev ? tiles_dev + (size_t)i * tile_bytes : bs->tiles_all.as<uint8_t>();
+        if (tiles_host) CUDA_TRY(cudaMemcpyAsync(bs->tiles_all.p, tiles_host + (size_t)i * tile_bytes, tile_bytes, cudaMemcpyHostToDevice, st));
         int16_t *t16 = bs->tile.as<int16_t>();
-        u8_to_i16_kernel<<<grid_for(ctx, (int64_t)tile_rows * trs), 256, 0, st>>>(bs->tiles_all.as<uint8_t>(), trs, t16, trs, tile_rows, (int)trs);
+        u8_to_i16_kernel<<<grid_for(ctx, (int64_t)tile_rows * trs), 256, 0, st>>>(t8, trs, t16, trs, tile_rows, (int)trs);
         LAUNCH_CHECK(ctx);
         int16_t *dst = canvas + r0 * crs + (int64_t)c0 * channels;
         const int rr0 = roi_rect[4 * i], rc0 = roi_rect[4 * i + 1], rr1 = roi_rect[4 * i + 2], rc1 = roi_rect[4 * i + 3];
@@ -572,6 +575,26 @@ int vfsms_mosaic_host(vfsms_ctx *ctx, const uint8_t *tiles, int n_tiles, int til
     CUDA_TRY(cudaMemcpyAsync(canvas_out, bs->out8.p, (size_t)cn, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
+}
+
+int vfsms_mosaic_host(vfsms_ctx *ctx, const uint8_t *tiles, int n_tiles, int tile_rows, int tile_cols, int channels,
+                      const int32_t *tile_origin, const int32_t *roi_rect, const int32_t *pair_offset, int method,
+                      int canvas_rows, int canvas_cols, uint8_t *canvas_out)
+{
+    if (!tiles) { vfsms_set_error("mosaic: bad arguments"); return VFSMS_E_ARG; }
+    return mosaic_run(ctx, tiles, nullptr, n_tiles, tile_rows, tile_cols, channels, tile_origin, roi_rect, pair_offset, method, canvas_rows,
+                      canvas_cols, canvas_out);
+}
+
+int vfsms_tiles_mosaic(vfsms_ctx *ctx, int first, int n_tiles, const int32_t *tile_origin, const int32_t *roi_rect, const int32_t *pair_offset,
+                       int method, int canvas_rows, int canvas_cols, uint8_t *canvas_out)
+{
+    if (!ctx || !ctx->tiles.p || first < 0 || n_tiles < 1 || first + n_tiles > ctx->tiles_n) {
+        vfsms_set_error("tiles_mosaic: tiles [%d, %d) outside the reserved stack", first, first + n_tiles); return VFSMS_E_ARG;
+    }
+    const size_t img = (size_t)ctx->tiles_rows * ctx->tiles_cols;
+    return mosaic_run(ctx, nullptr, ctx->tiles.as<uint8_t>() + first * img, n_tiles, ctx->tiles_rows, ctx->tiles_cols, 1, tile_origin, roi_rect,
+                      pair_offset, method, canvas_rows, canvas_cols, canvas_out);
 }
 
 }  // extern "C"

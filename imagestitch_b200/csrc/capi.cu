@@ -120,7 +120,7 @@ void vfsms_destroy(vfsms_ctx *ctx)
                        &ctx->scratch0, &ctx->scratch1, &ctx->scratch2, &ctx->scratch3 };
     for (DevBuf *b : bufs) b->release();
     ctx->pinned_in.release(); ctx->pinned_out.release();
-    ctx->jpeg_pinned.release(); ctx->jpeg_coef.release(); ctx->jpeg_out.release();
+    ctx->jpeg_pinned.release(); ctx->jpeg_coef.release(); ctx->jpeg_out.release(); ctx->tiles.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -294,26 +294,18 @@ int vfsms_align_batch_dev(vfsms_ctx *ctx, const uint8_t *rois_a_dev, const uint8
                               offset_evaluate, results_dev, st);
 }
 
-int vfsms_align_batch_host(vfsms_ctx *ctx, const uint8_t *rois_a, const uint8_t *rois_b, int n_pairs,
-                           int rows, int cols, int stride, int64_t pair_stride, const vfsms_surf_params *params,
-                           float ratio, int offset_evaluate, vfsms_pair_result *results)
+// detect + describe + match + vote on device-resident ROIs, results to the host; regrows the candidate / keypoint buffers
+// and repeats when a pair reports overflow
+static int align_dev_regrow(vfsms_ctx *ctx, const uint8_t *a_dev, const uint8_t *b_dev, int n_pairs, int rows, int cols, int stride,
+                            int64_t pair_stride, const vfsms_surf_params *params, float ratio, int offset_evaluate,
+                            vfsms_pair_result *results, cudaStream_t st)
 {
-    if (!ctx || !rois_a || !rois_b || !params || !results || n_pairs < 1 || rows < 1 || cols < 1) { vfsms_set_error("align_batch_host: bad arguments"); return VFSMS_E_ARG; }
-    CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
     int rc;
-    const size_t img_bytes = (size_t)rows * cols;
-    if ((rc = ctx->img_a.reserve(img_bytes * n_pairs))) return rc;
-    if ((rc = ctx->img_b.reserve(img_bytes * n_pairs))) return rc;
     if ((rc = ctx->results.reserve(sizeof(vfsms_pair_result) * (size_t)n_pairs))) return rc;
-    for (int p = 0; p < n_pairs; p++) {
-        CUDA_TRY(cudaMemcpy2DAsync(ctx->img_a.as<uint8_t>() + p * img_bytes, cols, rois_a + p * pair_stride, stride, cols, rows, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpy2DAsync(ctx->img_b.as<uint8_t>() + p * img_bytes, cols, rois_b + p * pair_stride, stride, cols, rows, cudaMemcpyHostToDevice, st));
-    }
     if ((rc = surf_reserve(ctx, 2 * n_pairs, rows, cols, params))) return rc;
     for (int attempt = 0; attempt < 6; attempt++) {
         if ((rc = match_reserve(ctx, n_pairs, ctx->surf.kp_cap))) return rc;
-        if ((rc = align_batch_launch(ctx, ctx->img_a.as<uint8_t>(), ctx->img_b.as<uint8_t>(), n_pairs, rows, cols, cols, (int64_t)img_bytes,
+        if ((rc = align_batch_launch(ctx, a_dev, b_dev, n_pairs, rows, cols, stride, pair_stride,
                                      params, (double)ratio, offset_evaluate, ctx->results.as<vfsms_pair_result>(), st))) return rc;
         CUDA_TRY(cudaMemcpyAsync(results, ctx->results.p, sizeof(vfsms_pair_result) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -326,8 +318,103 @@ int vfsms_align_batch_host(vfsms_ctx *ctx, const uint8_t *rois_a, const uint8_t 
         for (int b = 0; b < 2 * n_pairs; b++) { gc |= cnt[b * 4 + 3] & 1; gk |= cnt[b * 4 + 3] & 2; }
         if ((rc = surf_grow(ctx, gc, gk))) return rc;
     }
-    vfsms_set_error("align_batch_host: candidate buffer overflow after regrow");
+    vfsms_set_error("align: candidate buffer overflow after regrow");
     return VFSMS_E_OVERFLOW;
+}
+
+int vfsms_align_batch_host(vfsms_ctx *ctx, const uint8_t *rois_a, const uint8_t *rois_b, int n_pairs,
+                           int rows, int cols, int stride, int64_t pair_stride, const vfsms_surf_params *params,
+                           float ratio, int offset_evaluate, vfsms_pair_result *results)
+{
+    if (!ctx || !rois_a || !rois_b || !params || !results || n_pairs < 1 || rows < 1 || cols < 1) { vfsms_set_error("align_batch_host: bad arguments"); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc;
+    const size_t img_bytes = (size_t)rows * cols;
+    if ((rc = ctx->img_a.reserve(img_bytes * n_pairs))) return rc;
+    if ((rc = ctx->img_b.reserve(img_bytes * n_pairs))) return rc;
+    for (int p = 0; p < n_pairs; p++) {
+        CUDA_TRY(cudaMemcpy2DAsync(ctx->img_a.as<uint8_t>() + p * img_bytes, cols, rois_a + p * pair_stride, stride, cols, rows, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpy2DAsync(ctx->img_b.as<uint8_t>() + p * img_bytes, cols, rois_b + p * pair_stride, stride, cols, rows, cudaMemcpyHostToDevice, st));
+    }
+    return align_dev_regrow(ctx, ctx->img_a.as<uint8_t>(), ctx->img_b.as<uint8_t>(), n_pairs, rows, cols, cols, (int64_t)img_bytes, params, ratio,
+                            offset_evaluate, results, st);
+}
+
+/* ---------------------------------------------------------------- device-resident tile stack */
+int vfsms_tiles_reserve(vfsms_ctx *ctx, int n_tiles, int rows, int cols)
+{
+    if (!ctx || n_tiles < 1 || rows < 1 || cols < 1) { vfsms_set_error("tiles_reserve: bad arguments"); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ctx->tiles.reserve((size_t)n_tiles * rows * cols))) return rc;
+    ctx->tiles_n = n_tiles; ctx->tiles_rows = rows; ctx->tiles_cols = cols;
+    return 0;
+}
+
+static int tiles_range_ok(vfsms_ctx *ctx, int first, int n, const char *who)
+{
+    if (!ctx || !ctx->tiles.p || first < 0 || n < 0 || first + n > ctx->tiles_n) {
+        vfsms_set_error("%s: tiles [%d, %d) outside the reserved stack of %d", who, first, first + n, ctx ? ctx->tiles_n : 0); return VFSMS_E_ARG;
+    }
+    return 0;
+}
+
+int vfsms_tiles_decode_jpeg(vfsms_ctx *ctx, int first, int n, const uint8_t *const *data, const size_t *sizes)
+{
+    int rc;
+    if ((rc = tiles_range_ok(ctx, first, n, "tiles_decode_jpeg"))) return rc;
+    const int64_t img = (int64_t)ctx->tiles_rows * ctx->tiles_cols;
+    return vfsms_jpeg_decode_gray_dev(ctx, n, data, sizes, ctx->tiles.as<uint8_t>() + first * img, ctx->tiles_rows, ctx->tiles_cols,
+                                      ctx->tiles_cols, img, nullptr);
+}
+
+int vfsms_tiles_upload(vfsms_ctx *ctx, int first, int n, const uint8_t *tiles)
+{
+    int rc;
+    if ((rc = tiles_range_ok(ctx, first, n, "tiles_upload"))) return rc;
+    if (!tiles) { vfsms_set_error("tiles_upload: bad arguments"); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t img = (size_t)ctx->tiles_rows * ctx->tiles_cols;
+    CUDA_TRY(cudaMemcpyAsync(ctx->tiles.as<uint8_t>() + first * img, tiles, img * n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int vfsms_tiles_download(vfsms_ctx *ctx, int first, int n, uint8_t *out)
+{
+    int rc;
+    if ((rc = tiles_range_ok(ctx, first, n, "tiles_download"))) return rc;
+    if (!out) { vfsms_set_error("tiles_download: bad arguments"); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t img = (size_t)ctx->tiles_rows * ctx->tiles_cols;
+    CUDA_TRY(cudaMemcpyAsync(out, ctx->tiles.as<uint8_t>() + first * img, img * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+const uint8_t *vfsms_tiles_ptr(vfsms_ctx *ctx) { return ctx ? ctx->tiles.as<uint8_t>() : nullptr; }
+
+int vfsms_tiles_align(vfsms_ctx *ctx, int first, int n_pairs, int direction, int roi_len, const vfsms_surf_params *params, float ratio,
+                      int offset_evaluate, vfsms_pair_result *results)
+{
+    int rc;
+    if ((rc = tiles_range_ok(ctx, first, n_pairs + 1, "tiles_align"))) return rc;
+    const int H = ctx->tiles_rows, W = ctx->tiles_cols;
+    const int edge = (direction == 1 || direction == 3) ? H : W;
+    if (!params || !results || n_pairs < 1 || direction < 1 || direction > 4 || roi_len < 1 || roi_len > edge) {
+        vfsms_set_error("tiles_align: bad arguments"); return VFSMS_E_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    // ROI of the first image / of the second image (ImageUtility.py:66-101), read in place from the stack
+    const int64_t img = (int64_t)H * W;
+    const uint8_t *A = ctx->tiles.as<uint8_t>() + first * img, *B = A + img;
+    int rows, cols;
+    if (direction == 1) { rows = roi_len; cols = W; A += (int64_t)(H - roi_len) * W; }            // A bottom strip, B top strip
+    else if (direction == 2) { rows = H; cols = roi_len; A += W - roi_len; }                      // A right strip, B left strip
+    else if (direction == 3) { rows = roi_len; cols = W; B += (int64_t)(H - roi_len) * W; }       // A top strip, B bottom strip
+    else { rows = H; cols = roi_len; B += W - roi_len; }                                          // A left strip, B right strip
+    return align_dev_regrow(ctx, A, B, n_pairs, rows, cols, W, img, params, ratio, offset_evaluate, results, ctx->stream);
 }
 
 int vfsms_match_batch_dev(vfsms_ctx *ctx, const float *desc_a_dev, const int32_t *n_a_dev, const float *desc_b_dev,

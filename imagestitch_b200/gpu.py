@@ -361,3 +361,46 @@ def jpeg_decode_gray_dev(datas, out, device=0, stream=None):
                                                        ctypes.c_void_p(stream.cuda_stream if stream is not None else 0)),
                 "vfsms_jpeg_decode_gray_dev")
     return out
+
+
+# ---------------------------------------------------------------- device-resident tile stack
+def tiles_reserve(n_tiles, rows, cols, device=0):
+    check(_lib.load().vfsms_tiles_reserve(_lib.context(device), int(n_tiles), int(rows), int(cols)), "vfsms_tiles_reserve")
+
+
+def tiles_decode_jpeg(first, datas, device=0):
+    """Decode JPEG byte strings into stack slots first .. first + len(datas) - 1 (geometry = the reserved one)."""
+    bufs, ptrs, sizes = _jpeg_args(datas)
+    _jpeg_check(_lib.load().vfsms_tiles_decode_jpeg(_lib.context(device), int(first), len(bufs), ptrs, sizes), "vfsms_tiles_decode_jpeg")
+
+
+def tiles_upload(first, tiles, device=0):
+    t = np.ascontiguousarray(tiles, np.uint8)
+    if t.ndim == 2:
+        t = t[None]
+    check(_lib.load().vfsms_tiles_upload(_lib.context(device), int(first), t.shape[0], t.ctypes.data_as(ctypes.c_void_p)), "vfsms_tiles_upload")
+
+
+def tiles_download(first, n, rows, cols, device=0):
+    out = np.empty((n, rows, cols), np.uint8)
+    check(_lib.load().vfsms_tiles_download(_lib.context(device), int(first), int(n), out.ctypes.data_as(ctypes.c_void_p)), "vfsms_tiles_download")
+    return out
+
+
+def tiles_align(first, n_pairs, direction, roi_len, params=None, ratio=0.75, offset_evaluate=3, device=0):
+    """Candidate (direction, ROI length) of the incremental search for pairs (first+p, first+p+1), ROIs read in place
+    from the tile stack.  -> structured array like align_batch."""
+    p = params if params is not None else surf_params()
+    res = np.zeros(n_pairs, PAIR_RESULT_DTYPE)
+    check(_lib.load().vfsms_tiles_align(_lib.context(device), int(first), int(n_pairs), int(direction), int(roi_len), ctypes.byref(p),
+                                        ctypes.c_float(ratio), int(offset_evaluate), res.ctypes.data_as(ctypes.c_void_p)), "vfsms_tiles_align")
+    return res
+
+
+def tiles_mosaic(first, n_tiles, origins, rois, pair_offsets, method, canvas_shape, device=0):
+    o = np.ascontiguousarray(origins, np.int32); r = np.ascontiguousarray(rois, np.int32); po = np.ascontiguousarray(pair_offsets, np.int32)
+    out = np.empty((int(canvas_shape[0]), int(canvas_shape[1])), np.uint8)
+    check(_lib.load().vfsms_tiles_mosaic(_lib.context(device), int(first), int(n_tiles), o.ctypes.data_as(ctypes.c_void_p),
+                                         r.ctypes.data_as(ctypes.c_void_p), po.ctypes.data_as(ctypes.c_void_p), FUSE_METHODS[method],
+                                         out.shape[0], out.shape[1], out.ctypes.data_as(ctypes.c_void_p)), "vfsms_tiles_mosaic")
+    return out

@@ -215,6 +215,24 @@ int vfsms_jpeg_decode_gray_dev(vfsms_ctx *ctx, int n_images, const uint8_t *cons
 int vfsms_jpeg_decode_gray_host(vfsms_ctx *ctx, int n_images, const uint8_t *const *data, const size_t *sizes,
                                 uint8_t *out, int rows, int cols);
 
+/* ---------------------------------------------------------------- device-resident tile stack
+ * The reference decodes every tile two or three times and ships ROIs to the plugin per call (Stitcher.py:68-69, 382, 401;
+ * appendix/myGpuFeatures.cpp:70).  Here the gray tiles of a sequence (all rows x cols) are decoded / uploaded ONCE into a
+ * context-owned stack in HBM; alignment reads its ROI strips in place and the gray mosaic pastes from it. */
+int vfsms_tiles_reserve(vfsms_ctx *ctx, int n_tiles, int rows, int cols);
+int vfsms_tiles_decode_jpeg(vfsms_ctx *ctx, int first, int n, const uint8_t *const *data, const size_t *sizes);   /* as vfsms_jpeg_decode_gray_dev */
+int vfsms_tiles_upload(vfsms_ctx *ctx, int first, int n, const uint8_t *tiles /* n x rows x cols, host */);
+int vfsms_tiles_download(vfsms_ctx *ctx, int first, int n, uint8_t *out /* n x rows x cols, host */);
+const uint8_t *vfsms_tiles_ptr(vfsms_ctx *ctx);                      /* device address of tile 0 */
+/* One search candidate (ROI length roi_len = floor(edge * i * roiRatio), direction 1..4) of calculateOffsetForFeatureSearchIncre
+ * (Stitcher.py:319-351) for the n_pairs consecutive pairs (first + p, first + p + 1): ROIs as getROIRegionForIncreMethod
+ * cuts them (ImageUtility.py:66-101), read in place; results as vfsms_align_batch_host (ROI coordinates, host memory). */
+int vfsms_tiles_align(vfsms_ctx *ctx, int first, int n_pairs, int direction, int roi_len, const vfsms_surf_params *params,
+                      float ratio, int offset_evaluate, vfsms_pair_result *results);
+/* vfsms_mosaic_host with tiles first .. first + n_tiles - 1 of the stack (gray). */
+int vfsms_tiles_mosaic(vfsms_ctx *ctx, int first, int n_tiles, const int32_t *tile_origin, const int32_t *roi_rect,
+                       const int32_t *pair_offset, int method, int canvas_rows, int canvas_cols, uint8_t *canvas_out);
+
 #ifdef __cplusplus
 }
 #endif

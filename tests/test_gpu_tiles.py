@@ -1,0 +1,95 @@
+"""Device-resident tile stack: decode once, align ROI strips in place, mosaic from the stack -- results identical to the
+host-array entry points (and therefore to the reference path they are tested against)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tiles():
+    from imagestitch_b200 import synth
+    t, offs = synth.tile_sequence(seed=321, n_rows=2, n_cols=3, size=640, overlap=150, noise=1.5)
+    return np.stack(t), np.asarray(offs)
+
+
+@pytest.mark.parametrize("direction", [1, 2, 3, 4])
+@pytest.mark.parametrize("i", [1, 2])
+def test_tiles_align_equals_host_rois(tiles, direction, i):
+    from imagestitch_b200 import gpu
+    from imagestitch_b200.ImageUtility import Method
+    T, _ = tiles
+    m = Method()
+    n, H, W = T.shape
+    gpu.tiles_reserve(n, H, W)
+    gpu.tiles_upload(0, T)
+    assert np.array_equal(gpu.tiles_download(0, n, H, W), T)
+    ratio = 0.2 * i
+    L = int(np.floor((H if direction in (1, 3) else W) * ratio))
+    params = gpu.surf_params()
+    got = gpu.tiles_align(0, n - 1, direction, L, params=params)
+    A = np.stack([np.ascontiguousarray(m.getROIRegionForIncreMethod(T[k], direction, "first", ratio)) for k in range(n - 1)])
+    B = np.stack([np.ascontiguousarray(m.getROIRegionForIncreMethod(T[k + 1], direction, "second", ratio)) for k in range(n - 1)])
+    ref = gpu.align_batch(A, B, params=params)
+    for name in ("status", "d_row", "d_col", "votes", "n_a", "n_b", "n_matches"):
+        if name in ref.dtype.names:
+            assert np.array_equal(got[name], ref[name]), name
+    # a sub-range of the stack
+    sub = gpu.tiles_align(2, 2, direction, L, params=params)
+    assert np.array_equal(sub["d_row"], ref["d_row"][2:4]) and np.array_equal(sub["status"], ref["status"][2:4])
+
+
+def test_tiles_mosaic_equals_host_mosaic(tiles):
+    from imagestitch_b200 import gpu
+    T, _ = tiles
+    n, H, W = 3, T.shape[1], T.shape[2]
+    gpu.tiles_reserve(n, H, W)
+    gpu.tiles_upload(0, T[:n])
+    origins = np.array([[0, 0], [5, W - 150], [2, 2 * (W - 150) + 7]], np.int32)
+    pair = np.array([[0, 0], [5, W - 150], [-3, W - 143]], np.int32)
+    rois = np.zeros((n, 4), np.int32)
+    for k in range(1, n):
+        rois[k] = (max(origins[k, 0], 0), origins[k, 1], min(origins[k, 0] + H, H + 5), origins[k - 1, 1] + W)
+    shape = (H + 8, int(origins[-1, 1]) + W)
+    for method in ("notFuse", "average", "fadeInAndFadeOut", "trigonometric"):
+        a = gpu.tiles_mosaic(0, n, origins, rois, pair, method, shape)
+        b = gpu.mosaic(T[:n], origins, rois, pair, method, shape)
+        assert np.array_equal(a, b), method
+
+
+def test_stitcher_on_jpeg_tiles_device_stack_equals_cv2_decode(tiles, tmp_path):
+    """What Main.py does on a directory of JPEG tiles: library decode + tile stack vs cv2 decode + host ROIs -- same
+    offsets, same mosaic bytes."""
+    import cv2
+    from Stitcher import Stitcher
+    T, offs = tiles
+    d = tmp_path / "set" / "1"
+    d.mkdir(parents=True)
+    for k, t in enumerate(T):
+        cv2.imwrite(str(d / ("tile-%02d.jpg" % k)), t, [cv2.IMWRITE_JPEG_QUALITY, 95])
+    results = {}
+    for decoder in ("b200", "cv2"):
+        Stitcher.featureMethod = "surf"; Stitcher.isColorMode = False; Stitcher.isGPUAvailable = False; Stitcher.isEnhance = False
+        Stitcher.searchRatio = 0.75; Stitcher.offsetCaculate = "mode"; Stitcher.offsetEvaluate = 3; Stitcher.roiRatio = 0.2
+        Stitcher.fuseMethod = "fadeInAndFadeOut"; Stitcher.direction = 1; Stitcher.directIncre = 1; Stitcher.isPrintLog = False
+        Stitcher.decoder = decoder
+        st = Stitcher()
+        seen = {}
+        orig = st.getStitchByOffset
+
+        def spy(fileList, offsetList, _orig=orig, _seen=seen):
+            _seen["offsets"] = [list(o) for o in offsetList]
+            return _orig(fileList, offsetList)
+        st.getStitchByOffset = spy
+        out = tmp_path / ("out_" + decoder)
+        st.imageSetStitchWithMutiple(str(tmp_path / "set"), str(out), 1, st.calculateOffsetForFeatureSearchIncre, fileExtension="jpg",
+                                     outputfileExtension="png")
+        results[decoder] = (seen["offsets"], cv2.imread(os.path.join(str(out), "stitching_result_1.png"), 0))
+    Stitcher.decoder = "b200"; Stitcher.isPrintLog = True; Stitcher.isColorMode = True; Stitcher.fuseMethod = "notFuse"; Stitcher.direction = 1
+    assert results["b200"][0] == results["cv2"][0]
+    assert len(results["b200"][0]) == len(offs)
+    for got, true in zip(results["b200"][0], offs):
+        assert abs(got[0] - true[0]) <= 1 and abs(got[1] - true[1]) <= 1
+    assert results["b200"][1] is not None and np.array_equal(results["b200"][1], results["cv2"][1])

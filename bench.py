@@ -22,16 +22,64 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # torchrun exports OMP_NUM_THREADS=1; the CPU arms (reference / cpu_baseline) must see every host core, and NCCL's
 # version banner must not precede the single JSON line on stdout.
-def host_cores():
-    """CPUs this process may run on (cgroup / affinity aware; os.cpu_count() over-reports inside a cpuset)."""
+def _cgroup_cpu_quota():
+    """CPUs' worth of CFS quota of this container (cgroup v2 cpu.max / v1 cfs_quota_us), or None when unlimited."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            return float(q) / float(per)
+    except (OSError, ValueError):
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0:
+            return q / per
+    except (OSError, ValueError):
+        pass
+    return None
+
+
+def _physical_cores(allowed):
+    """Distinct (socket, core) pairs among the allowed logical CPUs (hyper-thread siblings counted once)."""
+    cores, cur = set(), {}
+    try:
+        for line in open("/proc/cpuinfo"):
+            if ":" in line:
+                k, v = [t.strip() for t in line.split(":", 1)]
+                cur[k] = v
+            elif cur:
+                if int(cur.get("processor", -1)) in allowed:
+                    cores.add((cur.get("physical id", "0"), cur.get("core id", cur.get("processor"))))
+                cur = {}
+        if cur and int(cur.get("processor", -1)) in allowed:
+            cores.add((cur.get("physical id", "0"), cur.get("core id", cur.get("processor"))))
+    except (OSError, ValueError):
+        return None
+    return len(cores) or None
+
+
+def host_cores():
+    """Threads the CPU arms use: the physical cores this process may run on, capped by the container's CPU quota.
+    (os.cpu_count() over-reports inside a cpuset; one busy-waiting OpenMP thread per hyper-thread or beyond the quota
+    made the reference arm 12x slower than the same code with one thread per core.)"""
+    try:
+        allowed = set(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        allowed = set(range(os.cpu_count() or 1))
+    n = len(allowed)
+    phys = _physical_cores(allowed)
+    if phys:
+        n = min(n, phys)
+    quota = _cgroup_cpu_quota()
+    if quota:
+        n = min(n, max(1, int(quota)))
+    return max(1, n)
 
 
 if "--impl" in sys.argv and "reference" in sys.argv or int(os.environ.get("WORLD_SIZE", "1")) == 1:
     os.environ["OMP_NUM_THREADS"] = str(host_cores())
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")       # idle OpenMP workers must not spin while cv2's own pool runs the matcher
 if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
     os.environ["NCCL_DEBUG"] = "WARN"
 
@@ -339,7 +387,7 @@ def main():
         dt_c = (time.perf_counter() - t0) / 8
         exact = all(np.array_equal(stack[k].cpu().numpy(), ref[k]) for k in range(8))
         ingest = {"tiles_per_s": n_t / dt_b, "mpix_per_s": n_t * TILE * TILE / dt_b / 1e6, "bit_exact_vs_cv2": bool(exact),
-                  "jpeg_bytes_per_tile": int(np.mean([len(f) for f in files])), "host_threads": min(host_cores(), 32, n_t),
+                  "jpeg_bytes_per_tile": int(np.mean([len(f) for f in files])), "host_threads": min(len(os.sched_getaffinity(0)), int(_cgroup_cpu_quota() or 1 << 30), 32, n_t),
                   "cv2_imdecode_tiles_per_s_1_thread": 1.0 / dt_c,
                   "what": "%d synthetic 2048x2048 JPEG tiles (q92, single component) from host bytes to HBM-resident u8 tiles: host Huffman threads + H2D of int16 coefficients + IDCT kernel; wall clock" % n_t}
 

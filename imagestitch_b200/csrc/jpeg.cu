@@ -13,6 +13,7 @@
 // caller keeps its own decoder.
 #include "common.cuh"
 #include <sched.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include <thread>
@@ -341,11 +342,24 @@ __global__ void __launch_bounds__(JPEG_BLOCKS_PER_CTA * 8) jpeg_idct_luma_kernel
 }
 
 // ---------------------------------------------------------------- C ABI
+// worker threads for the entropy stage: CPUs this process may run on, capped by the container's CFS quota
+// (cgroup v2 cpu.max / v1 cfs_quota_us) and by 32
 static int host_threads()
 {
     cpu_set_t set;
     int n = 1;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+    long long quota = -1, period = 100000;
+    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char q[32] = { 0 };
+        if (fscanf(f, "%31s %lld", q, &period) == 2 && strcmp(q, "max") != 0) quota = atoll(q);
+        fclose(f);
+    } else if (FILE *g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {
+        if (fscanf(g, "%lld", &quota) != 1) quota = -1;
+        fclose(g);
+        if (FILE *h = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (fscanf(h, "%lld", &period) != 1) period = 100000; fclose(h); }
+    }
+    if (quota > 0 && period > 0 && quota / period < n) n = (int)(quota / period);
     if (n > 32) n = 32;
     return n < 1 ? 1 : n;
 }

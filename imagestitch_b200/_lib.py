@@ -34,6 +34,7 @@ EXPORTS = [
     "vfsms_mosaic_host", "vfsms_profile_enable", "vfsms_profile_read", "vfsms_stage_name",
     "vfsms_set_matcher", "vfsms_last_match_fallbacks", "vfsms_enhance_host",
     "vfsms_jpeg_info", "vfsms_jpeg_luma_coefficients", "vfsms_jpeg_decode_gray_dev", "vfsms_jpeg_decode_gray_host",
+    "vfsms_jpeg_component_coefficients", "vfsms_jpeg_decode_bgr_dev", "vfsms_jpeg_decode_bgr_host",
     "vfsms_tiles_reserve", "vfsms_tiles_decode_jpeg", "vfsms_tiles_upload", "vfsms_tiles_download", "vfsms_tiles_ptr",
     "vfsms_tiles_align", "vfsms_tiles_mosaic",
 ]

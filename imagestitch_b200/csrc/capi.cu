@@ -120,7 +120,7 @@ void vfsms_destroy(vfsms_ctx *ctx)
                        &ctx->scratch0, &ctx->scratch1, &ctx->scratch2, &ctx->scratch3 };
     for (DevBuf *b : bufs) b->release();
     ctx->pinned_in.release(); ctx->pinned_out.release();
-    ctx->jpeg_pinned.release(); ctx->jpeg_coef.release(); ctx->jpeg_out.release(); ctx->tiles.release();
+    ctx->jpeg_pinned.release(); ctx->jpeg_coef.release(); ctx->jpeg_out.release(); ctx->jpeg_planes.release(); ctx->tiles.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -149,7 +149,7 @@ struct vfsms_ctx {
     DevBuf scratch0, scratch1, scratch2, scratch3;
     HostBuf pinned_in, pinned_out;
     HostBuf jpeg_pinned;       // entropy-decoded luma coefficients of one chunk of files (jpeg.cu)
-    DevBuf jpeg_coef, jpeg_out;
+    DevBuf jpeg_coef, jpeg_out, jpeg_planes;
     DevBuf tiles;              // device-resident tile stack [tiles_n][tiles_rows][tiles_cols] u8 (vfsms_tiles_*)
     int tiles_n = 0, tiles_rows = 0, tiles_cols = 0;
     void *tex_cache = nullptr;     // texture objects over caller images (surf.cu)

@@ -204,8 +204,9 @@ struct BitReader {
     }
 };
 
-// Entropy-decode one file; luma coefficients (quantised, natural order) -> coef[blocks_h][blocks_w][64].
-static void jpeg_entropy_decode(const uint8_t *d, size_t n, const JpegHeader &H, int16_t *coef)
+// Entropy-decode one file.  coef[c] = destination of component c (quantised, natural order,
+// [mcuy * v_c][mcux * h_c][64]) or nullptr to parse and drop that component (the grayscale path drops chroma).
+static void jpeg_entropy_decode(const uint8_t *d, size_t n, const JpegHeader &H, int16_t *const coef[4])
 {
     BitReader br{ d, H.scan_begin, n };
     int pred[4] = { 0, 0, 0, 0 };
@@ -216,14 +217,15 @@ static void jpeg_entropy_decode(const uint8_t *d, size_t n, const JpegHeader &H,
             for (int c = 0; c < H.ncomp; c++) {
                 const JpegComp &C = H.comp[c];
                 const HuffTable &dc = H.dc[C.td], &ac = H.ac[C.ta];
+                const int comp_bw = H.mcux * C.h;
                 for (int v = 0; v < C.v; v++)
                     for (int h = 0; h < C.h; h++) {
                         const int s = br.symbol(dc) & 15;
                         pred[c] += br.receive_extend(s);
-                        if (c == 0) {
-                            int16_t *blk = coef + ((size_t)(my * C.v + v) * H.blocks_w + (mx * C.h + h)) * 64;
+                        if (coef[c]) {
+                            int16_t *blk = coef[c] + ((size_t)(my * C.v + v) * comp_bw + (mx * C.h + h)) * 64;
                             memset(blk, 0, 128);
-                            blk[0] = (int16_t)pred[0];
+                            blk[0] = (int16_t)pred[c];
                             for (int k = 1; k < 64;) {
                                 const int rs = br.symbol(ac), r = rs >> 4, sz = rs & 15;
                                 if (sz == 0) { if (r == 15) { k += 16; continue; } break; }
@@ -233,7 +235,7 @@ static void jpeg_entropy_decode(const uint8_t *d, size_t n, const JpegHeader &H,
                                 k++;
                             }
                         } else {
-                            for (int k = 1; k < 64;) {                  // chroma: parse and drop
+                            for (int k = 1; k < 64;) {                  // parse and drop
                                 const int rs = br.symbol(ac), r = rs >> 4, sz = rs & 15;
                                 if (sz == 0) { if (r == 15) { k += 16; continue; } break; }
                                 k += r + 1;
@@ -341,6 +343,58 @@ __global__ void __launch_bounds__(JPEG_BLOCKS_PER_CTA * 8) jpeg_idct_luma_kernel
     }
 }
 
+// ---------------------------------------------------------------- device: chroma upsampling + YCbCr -> BGR
+// libjpeg defaults for cv2.imdecode(data, IMREAD_COLOR) (Stitcher.py:382,401): do_fancy_upsampling (jdsample.c triangle
+// filters for 2h1v, 2h2v -- only when the downsampled width exceeds 2 -- and 1h2v; box replication otherwise) and the
+// 16-bit fixed-point tables of jdcolor.c, evaluated here directly.  One thread per output pixel.
+struct JpegPlanes {
+    const uint8_t *y, *cb, *cr;      // IDCT output planes, pitches in bytes
+    int pitch_y, pitch_c;
+    int hf, vf;                      // chroma upsampling factors (max sampling / chroma sampling)
+    int ds_rows, ds_cols;            // true downsampled chroma size (compptr->downsampled_height / _width)
+    int gray;                        // single-component file: B = G = R = Y
+};
+
+__device__ __forceinline__ int chroma_sample(const uint8_t *__restrict__ p, int pitch, int x, int y, const JpegPlanes &P)
+{
+    const int hf = P.hf, vf = P.vf, dr = P.ds_rows, dc = P.ds_cols;
+    if (hf == 1 && vf == 1) return p[(size_t)y * pitch + x];
+    const bool fancy_h = hf == 2 && dc > 2 && (vf == 1 || vf == 2);
+    if (vf == 2 && (fancy_h || hf == 1)) {
+        // vertical triangle: 3 * nearer row + farther row (edge rows replicated)
+        const int r = y >> 1, rf = (y & 1) ? min(r + 1, dr - 1) : max(r - 1, 0);
+        const uint8_t *near = p + (size_t)r * pitch, *far = p + (size_t)rf * pitch;
+        if (hf == 1) return (3 * near[x] + far[x] + ((y & 1) ? 2 : 1)) >> 2;                    // h1v2_fancy_upsample
+        const int i = x >> 1;
+        const int cs = 3 * near[i] + far[i];
+        if (x & 1) { if (i == dc - 1) return (cs * 4 + 7) >> 4; return (3 * cs + 3 * near[i + 1] + far[i + 1] + 7) >> 4; }
+        if (i == 0) return (cs * 4 + 8) >> 4;
+        return (3 * cs + 3 * near[i - 1] + far[i - 1] + 8) >> 4;                                // h2v2_fancy_upsample
+    }
+    if (fancy_h && vf == 1) {                                                                   // h2v1_fancy_upsample
+        const uint8_t *row = p + (size_t)y * pitch;
+        const int i = x >> 1;
+        if (x & 1) return i == dc - 1 ? row[i] : (3 * row[i] + row[i + 1] + 2) >> 2;
+        return i == 0 ? row[0] : (3 * row[i] + row[i - 1] + 1) >> 2;
+    }
+    return p[(size_t)(y / vf) * pitch + x / hf];                                                // int_upsample / h2v1 / h2v2 box
+}
+
+__global__ void __launch_bounds__(256) jpeg_upsample_bgr_kernel(JpegPlanes P, uint8_t *__restrict__ out, int rows, int cols, int64_t row_stride)
+{
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= cols || y >= rows) return;
+    const int Y = P.y[(size_t)y * P.pitch_y + x];
+    uint8_t *dst = out + (size_t)y * row_stride + 3 * x;
+    if (P.gray) { dst[0] = dst[1] = dst[2] = (uint8_t)Y; return; }
+    const int cb = chroma_sample(P.cb, P.pitch_c, x, y, P) - 128, cr = chroma_sample(P.cr, P.pitch_c, x, y, P) - 128;
+    // FIX(x) = (int)(x * 65536 + 0.5): 1.40200 -> 91881, 1.77200 -> 116130, 0.71414 -> 46802, 0.34414 -> 22554
+    const int r = Y + ((91881 * cr + 32768) >> 16);
+    const int g = Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+    const int b = Y + ((116130 * cb + 32768) >> 16);
+    dst[0] = (uint8_t)min(max(b, 0), 255); dst[1] = (uint8_t)min(max(g, 0), 255); dst[2] = (uint8_t)min(max(r, 0), 255);
+}
+
 // ---------------------------------------------------------------- C ABI
 // worker threads for the entropy stage: CPUs this process may run on, capped by the container's CFS quota
 // (cgroup v2 cpu.max / v1 cfs_quota_us) and by 32
@@ -376,50 +430,94 @@ extern "C" int vfsms_jpeg_info(const uint8_t *data, size_t size, int *rows, int 
     return 0;
 }
 
-extern "C" int vfsms_jpeg_luma_coefficients(const uint8_t *data, size_t size, int16_t *coef, size_t coef_capacity, int *blocks_h,
-                                            int *blocks_w, uint16_t *quant)
+extern "C" int vfsms_jpeg_component_coefficients(const uint8_t *data, size_t size, int component, int16_t *coef, size_t coef_capacity,
+                                                 int *blocks_h, int *blocks_w, uint16_t *quant, int *h_samp, int *v_samp)
 {
-    if (!data) { vfsms_set_error("vfsms_jpeg_luma_coefficients: bad arguments"); return VFSMS_E_ARG; }
+    if (!data || component < 0 || component > 3) { vfsms_set_error("vfsms_jpeg_component_coefficients: bad arguments"); return VFSMS_E_ARG; }
     JpegHeader H;
     int rc = jpeg_parse(data, size, H);
     if (rc) return rc;
-    if (blocks_h) *blocks_h = H.blocks_h;
-    if (blocks_w) *blocks_w = H.blocks_w;
-    if (quant) memcpy(quant, H.quant[H.comp[0].tq], 128);
-    const size_t need = (size_t)H.blocks_h * H.blocks_w * 64;
+    if (component >= H.ncomp) { vfsms_set_error("vfsms_jpeg_component_coefficients: the file has %d components", H.ncomp); return VFSMS_E_ARG; }
+    const JpegComp &C = H.comp[component];
+    if (!H.quant_present[C.tq]) { vfsms_set_error("jpeg: missing quantisation table"); return VFSMS_E_UNSUPPORTED; }
+    const int bh = H.mcuy * C.v, bw = H.mcux * C.h;
+    if (blocks_h) *blocks_h = bh;
+    if (blocks_w) *blocks_w = bw;
+    if (h_samp) *h_samp = C.h;
+    if (v_samp) *v_samp = C.v;
+    if (quant) memcpy(quant, H.quant[C.tq], 128);
+    const size_t need = (size_t)bh * bw * 64;
     if (!coef) return 0;
-    if (coef_capacity < need) { vfsms_set_error("vfsms_jpeg_luma_coefficients: capacity %zu < %zu", coef_capacity, need); return VFSMS_E_CAPACITY; }
-    jpeg_entropy_decode(data, size, H, coef);
+    if (coef_capacity < need) { vfsms_set_error("vfsms_jpeg_component_coefficients: capacity %zu < %zu", coef_capacity, need); return VFSMS_E_CAPACITY; }
+    int16_t *dst[4] = { nullptr, nullptr, nullptr, nullptr };
+    dst[component] = coef;
+    jpeg_entropy_decode(data, size, H, dst);
     return 0;
 }
 
-// Decode n files of identical geometry into out_dev[i * image_stride + y * row_stride + x].
+extern "C" int vfsms_jpeg_luma_coefficients(const uint8_t *data, size_t size, int16_t *coef, size_t coef_capacity, int *blocks_h,
+                                            int *blocks_w, uint16_t *quant)
+{
+    return vfsms_jpeg_component_coefficients(data, size, 0, coef, coef_capacity, blocks_h, blocks_w, quant, nullptr, nullptr);
+}
+
+static int launch_idct(vfsms_ctx *ctx, const int16_t *cdev, const uint16_t *quant, int blocks_w, int blocks_h, uint8_t *out, int rows, int cols,
+                       int64_t stride, cudaStream_t st)
+{
+    JpegQuant Q;
+    memcpy(Q.q, quant, 128);
+    const int n_blocks = blocks_h * blocks_w;
+    jpeg_idct_luma_kernel<<<(n_blocks + JPEG_BLOCKS_PER_CTA - 1) / JPEG_BLOCKS_PER_CTA, JPEG_BLOCKS_PER_CTA * 8, 0, st>>>(cdev, Q, blocks_w, n_blocks, out, rows,
+                                                                                                                   cols, stride);
+    LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// Decode n files of identical geometry.  channels 1: gray, out[i * image_stride + y * row_stride + x];
+// channels 3: BGR interleaved, out[i * image_stride + y * row_stride + 3 * x + c].
 static int jpeg_decode_batch(vfsms_ctx *ctx, int n, const uint8_t *const *data, const size_t *sizes, uint8_t *out_dev, int rows, int cols,
-                             int64_t row_stride, int64_t image_stride, cudaStream_t st)
+                             int channels, int64_t row_stride, int64_t image_stride, cudaStream_t st)
 {
     if (n == 0) return 0;
     std::vector<JpegHeader> H((size_t)n);
+    size_t per = 0, per_planes = 0;
     for (int i = 0; i < n; i++) {
         int rc = jpeg_parse(data[i], sizes[i], H[i]);
         if (rc) return rc;
-        if (H[i].rows != rows || H[i].cols != cols) {
-            vfsms_set_error("jpeg: image %d is %d x %d, expected %d x %d", i, H[i].rows, H[i].cols, rows, cols); return VFSMS_E_ARG;
+        JpegHeader &h = H[i];
+        if (h.rows != rows || h.cols != cols) {
+            vfsms_set_error("jpeg: image %d is %d x %d, expected %d x %d", i, h.rows, h.cols, rows, cols); return VFSMS_E_ARG;
         }
+        size_t blocks = (size_t)h.blocks_h * h.blocks_w;
+        if (channels == 3 && h.ncomp == 3) {
+            const JpegComp &cb = h.comp[1], &cr = h.comp[2];
+            if (cb.h != cr.h || cb.v != cr.v || h.comp[0].h % cb.h || h.comp[0].v % cb.v || !h.quant_present[cb.tq] || !h.quant_present[cr.tq]) {
+                vfsms_set_error("jpeg: unsupported chroma sampling layout"); return VFSMS_E_UNSUPPORTED;
+            }
+            blocks += 2 * (size_t)(h.mcuy * cb.v) * (h.mcux * cb.h);
+        }
+        if (blocks * 128 > per) per = blocks * 128;
+        if (blocks * 64 > per_planes) per_planes = blocks * 64;
     }
-    size_t per = 0;
-    for (int i = 0; i < n; i++) { const size_t b = (size_t)H[i].blocks_h * H[i].blocks_w * 128; if (b > per) per = b; }
     const int workers = host_threads() < n ? host_threads() : n;
     const int chunk = workers;                       // files entropy-decoded concurrently, then shipped together
     int rc;
     if ((rc = ctx->jpeg_pinned.reserve(per * chunk))) return rc;
     if ((rc = ctx->jpeg_coef.reserve(per * chunk))) return rc;
+    if (channels == 3 && (rc = ctx->jpeg_planes.reserve(per_planes))) return rc;
+    auto comp_blocks = [](const JpegHeader &h, int c) { return (size_t)(h.mcuy * h.comp[c].v) * (h.mcux * h.comp[c].h); };
     for (int c0 = 0; c0 < n; c0 += chunk) {
         const int cn = n - c0 < chunk ? n - c0 : chunk;
         CUDA_TRY(cudaStreamSynchronize(st));          // the previous chunk has left the pinned buffer
         std::atomic<int> next(0);
         auto work = [&]() {
-            for (int j = next.fetch_add(1); j < cn; j = next.fetch_add(1))
-                jpeg_entropy_decode(data[c0 + j], sizes[c0 + j], H[c0 + j], (int16_t *)((uint8_t *)ctx->jpeg_pinned.p + per * j));
+            for (int j = next.fetch_add(1); j < cn; j = next.fetch_add(1)) {
+                const JpegHeader &h = H[c0 + j];
+                int16_t *base = (int16_t *)((uint8_t *)ctx->jpeg_pinned.p + per * j);
+                int16_t *dst[4] = { base, nullptr, nullptr, nullptr };
+                if (channels == 3 && h.ncomp == 3) { dst[1] = base + comp_blocks(h, 0) * 64; dst[2] = dst[1] + comp_blocks(h, 1) * 64; }
+                jpeg_entropy_decode(data[c0 + j], sizes[c0 + j], h, dst);
+            }
         };
         std::vector<std::thread> pool;
         for (int w = 1; w < (cn < workers ? cn : workers); w++) pool.emplace_back(work);
@@ -427,15 +525,34 @@ static int jpeg_decode_batch(vfsms_ctx *ctx, int n, const uint8_t *const *data, 
         for (auto &th : pool) th.join();
         for (int j = 0; j < cn; j++) {
             const JpegHeader &h = H[c0 + j];
-            const size_t bytes = (size_t)h.blocks_h * h.blocks_w * 128;
+            const bool colour = channels == 3 && h.ncomp == 3;
+            size_t blocks = comp_blocks(h, 0) + (colour ? 2 * comp_blocks(h, 1) : 0);
             int16_t *cdev = (int16_t *)((uint8_t *)ctx->jpeg_coef.p + per * j);
-            CUDA_TRY(cudaMemcpyAsync(cdev, (uint8_t *)ctx->jpeg_pinned.p + per * j, bytes, cudaMemcpyHostToDevice, st));
-            JpegQuant Q;
-            memcpy(Q.q, h.quant[h.comp[0].tq], 128);
-            const int n_blocks = h.blocks_h * h.blocks_w;
-            jpeg_idct_luma_kernel<<<(n_blocks + JPEG_BLOCKS_PER_CTA - 1) / JPEG_BLOCKS_PER_CTA, JPEG_BLOCKS_PER_CTA * 8, 0, st>>>(
-                cdev, Q, h.blocks_w, n_blocks, out_dev + (size_t)(c0 + j) * image_stride, rows, cols, row_stride);
+            CUDA_TRY(cudaMemcpyAsync(cdev, (uint8_t *)ctx->jpeg_pinned.p + per * j, blocks * 128, cudaMemcpyHostToDevice, st));
+            uint8_t *dst = out_dev + (size_t)(c0 + j) * image_stride;
+            if (channels == 1) {
+                if ((rc = launch_idct(ctx, cdev, h.quant[h.comp[0].tq], h.blocks_w, h.blocks_h, dst, rows, cols, row_stride, st))) return rc;
+                continue;
+            }
+            // planes: full padded IDCT output of every component, then one pass of upsampling + colour conversion
+            JpegPlanes P = {};
+            uint8_t *py = ctx->jpeg_planes.as<uint8_t>();
+            P.y = py; P.pitch_y = h.blocks_w * 8; P.gray = !colour; P.hf = P.vf = 1;
+            if ((rc = launch_idct(ctx, cdev, h.quant[h.comp[0].tq], h.blocks_w, h.blocks_h, py, h.blocks_h * 8, h.blocks_w * 8, P.pitch_y, st))) return rc;
+            if (colour) {
+                const JpegComp &Y = h.comp[0], &C = h.comp[1];
+                const int cbw = h.mcux * C.h, cbh = h.mcuy * C.v;
+                uint8_t *pcb = py + comp_blocks(h, 0) * 64, *pcr = pcb + comp_blocks(h, 1) * 64;
+                const int16_t *ccb = cdev + comp_blocks(h, 0) * 64, *ccr = ccb + comp_blocks(h, 1) * 64;
+                if ((rc = launch_idct(ctx, ccb, h.quant[h.comp[1].tq], cbw, cbh, pcb, cbh * 8, cbw * 8, cbw * 8, st))) return rc;
+                if ((rc = launch_idct(ctx, ccr, h.quant[h.comp[2].tq], cbw, cbh, pcr, cbh * 8, cbw * 8, cbw * 8, st))) return rc;
+                P.cb = pcb; P.cr = pcr; P.pitch_c = cbw * 8;
+                P.hf = Y.h / C.h; P.vf = Y.v / C.v;
+                P.ds_rows = (rows * C.v + Y.v - 1) / Y.v; P.ds_cols = (cols * C.h + Y.h - 1) / Y.h;
+            }
+            jpeg_upsample_bgr_kernel<<<dim3((cols + 63) / 64, (rows + 3) / 4), 256, 0, st>>>(P, dst, rows, cols, row_stride);
             LAUNCH_CHECK(ctx);
+            // the plane scratch is shared by the files of the batch: stream order keeps the next IDCT behind this kernel
         }
     }
     return 0;
@@ -447,7 +564,7 @@ extern "C" int vfsms_jpeg_decode_gray_dev(vfsms_ctx *ctx, int n_images, const ui
     if (!ctx || n_images < 0 || !data || !sizes || !out_dev || row_stride < cols) { vfsms_set_error("vfsms_jpeg_decode_gray_dev: bad arguments"); return VFSMS_E_ARG; }
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-    int rc = jpeg_decode_batch(ctx, n_images, data, sizes, out_dev, rows, cols, row_stride, image_stride, st);
+    int rc = jpeg_decode_batch(ctx, n_images, data, sizes, out_dev, rows, cols, 1, row_stride, image_stride, st);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(st));              // the pinned staging buffer is reusable on return
     return 0;
@@ -461,7 +578,33 @@ extern "C" int vfsms_jpeg_decode_gray_host(vfsms_ctx *ctx, int n_images, const u
     const size_t img = (size_t)rows * cols;
     int rc;
     if ((rc = ctx->jpeg_out.reserve(img * (size_t)n_images))) return rc;
-    if ((rc = jpeg_decode_batch(ctx, n_images, data, sizes, ctx->jpeg_out.as<uint8_t>(), rows, cols, cols, (int64_t)img, ctx->stream))) return rc;
+    if ((rc = jpeg_decode_batch(ctx, n_images, data, sizes, ctx->jpeg_out.as<uint8_t>(), rows, cols, 1, cols, (int64_t)img, ctx->stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, ctx->jpeg_out.p, img * (size_t)n_images, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int vfsms_jpeg_decode_bgr_dev(vfsms_ctx *ctx, int n_images, const uint8_t *const *data, const size_t *sizes, uint8_t *out_dev,
+                                         int rows, int cols, int64_t row_stride, int64_t image_stride, void *stream)
+{
+    if (!ctx || n_images < 0 || !data || !sizes || !out_dev || row_stride < 3 * (int64_t)cols) { vfsms_set_error("vfsms_jpeg_decode_bgr_dev: bad arguments"); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    int rc = jpeg_decode_batch(ctx, n_images, data, sizes, out_dev, rows, cols, 3, row_stride, image_stride, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int vfsms_jpeg_decode_bgr_host(vfsms_ctx *ctx, int n_images, const uint8_t *const *data, const size_t *sizes, uint8_t *out,
+                                          int rows, int cols)
+{
+    if (!ctx || n_images < 0 || !data || !sizes || !out) { vfsms_set_error("vfsms_jpeg_decode_bgr_host: bad arguments"); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t img = (size_t)rows * cols * 3;
+    int rc;
+    if ((rc = ctx->jpeg_out.reserve(img * (size_t)n_images))) return rc;
+    if ((rc = jpeg_decode_batch(ctx, n_images, data, sizes, ctx->jpeg_out.as<uint8_t>(), rows, cols, 3, (int64_t)cols * 3, (int64_t)img, ctx->stream))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, ctx->jpeg_out.p, img * (size_t)n_images, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return 0;

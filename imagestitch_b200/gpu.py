@@ -329,6 +329,23 @@ def jpeg_luma_coefficients(data):
     return coef, quant
 
 
+def jpeg_component_coefficients(data, component):
+    """Host-only entropy stage for any component: (coef int16 [bh, bw, 64], quant uint16[64], (h_samp, v_samp))."""
+    L = _lib.load()
+    buf = np.frombuffer(data, np.uint8)
+    bh, bw, hs, vs = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    quant = np.zeros(64, np.uint16)
+    p = buf.ctypes.data_as(ctypes.c_void_p)
+    qp = quant.ctypes.data_as(ctypes.c_void_p)
+    _jpeg_check(L.vfsms_jpeg_component_coefficients(p, ctypes.c_size_t(buf.size), int(component), None, ctypes.c_size_t(0), ctypes.byref(bh),
+                                                    ctypes.byref(bw), qp, ctypes.byref(hs), ctypes.byref(vs)), "vfsms_jpeg_component_coefficients")
+    coef = np.empty((bh.value, bw.value, 64), np.int16)
+    _jpeg_check(L.vfsms_jpeg_component_coefficients(p, ctypes.c_size_t(buf.size), int(component), coef.ctypes.data_as(ctypes.c_void_p),
+                                                    ctypes.c_size_t(coef.size), ctypes.byref(bh), ctypes.byref(bw), qp, ctypes.byref(hs),
+                                                    ctypes.byref(vs)), "vfsms_jpeg_component_coefficients")
+    return coef, quant, (hs.value, vs.value)
+
+
 def _jpeg_args(datas):
     bufs = [np.frombuffer(d, np.uint8) for d in datas]
     n = len(bufs)
@@ -348,6 +365,20 @@ def jpeg_decode_gray(datas, device=0):
     out = np.empty((len(bufs), rows, cols), np.uint8)
     _jpeg_check(_lib.load().vfsms_jpeg_decode_gray_host(_lib.context(device), len(bufs), ptrs, sizes, out.ctypes.data_as(ctypes.c_void_p), rows, cols),
                 "vfsms_jpeg_decode_gray_host")
+    return out[0] if single else out
+
+
+def jpeg_decode_bgr(datas, device=0):
+    """cv2.imdecode(data, cv2.IMREAD_COLOR) for JPEG byte strings of identical geometry -> u8 [n, rows, cols, 3] (BGR,
+    bit-identical to cv2: islow IDCT, fancy chroma upsampling, libjpeg's YCbCr tables)."""
+    single = isinstance(datas, (bytes, bytearray, memoryview, np.ndarray))
+    if single:
+        datas = [datas]
+    rows, cols, _ = jpeg_info(datas[0])
+    bufs, ptrs, sizes = _jpeg_args(datas)
+    out = np.empty((len(bufs), rows, cols, 3), np.uint8)
+    _jpeg_check(_lib.load().vfsms_jpeg_decode_bgr_host(_lib.context(device), len(bufs), ptrs, sizes, out.ctypes.data_as(ctypes.c_void_p), rows, cols),
+                "vfsms_jpeg_decode_bgr_host")
     return out[0] if single else out
 
 

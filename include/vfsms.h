@@ -207,6 +207,9 @@ int vfsms_jpeg_info(const uint8_t *data, size_t size, int *rows, int *cols, int 
  * luma quantisation table (natural order).  coef == NULL only reports the geometry. */
 int vfsms_jpeg_luma_coefficients(const uint8_t *data, size_t size, int16_t *coef, size_t coef_capacity, int *blocks_h,
                                  int *blocks_w, uint16_t *quant /* 64 */);
+/* Any component (0 = Y, 1 = Cb, 2 = Cr): same as above plus the component's sampling factors. */
+int vfsms_jpeg_component_coefficients(const uint8_t *data, size_t size, int component, int16_t *coef, size_t coef_capacity,
+                                      int *blocks_h, int *blocks_w, uint16_t *quant /* 64 */, int *h_samp, int *v_samp);
 /* n_images files of identical geometry (rows x cols, checked).  _dev: image i lands at
  * out_dev + i * image_stride + y * row_stride + x in HBM (the device-resident tile stack the align / mosaic entry points
  * read in place).  _host: out = n_images x rows x cols u8, contiguous, host memory. */
@@ -214,6 +217,14 @@ int vfsms_jpeg_decode_gray_dev(vfsms_ctx *ctx, int n_images, const uint8_t *cons
                                uint8_t *out_dev, int rows, int cols, int64_t row_stride, int64_t image_stride, void *stream);
 int vfsms_jpeg_decode_gray_host(vfsms_ctx *ctx, int n_images, const uint8_t *const *data, const size_t *sizes,
                                 uint8_t *out, int rows, int cols);
+/* Colour decode = cv2.imdecode(data, cv2.IMREAD_COLOR) (Stitcher.py:382, 401; Main.py:6 sets isColorMode): all three
+ * components through the IDCT, libjpeg's fancy chroma upsampling (jdsample.c) and YCbCr -> RGB tables (jdcolor.c), BGR
+ * interleaved like cv2; single-component files give B = G = R.  Bit-identical to cv2.  out: n x rows x cols x 3;
+ * _dev: pixel (y, x) of image i at out_dev + i * image_stride + y * row_stride + 3 * x. */
+int vfsms_jpeg_decode_bgr_dev(vfsms_ctx *ctx, int n_images, const uint8_t *const *data, const size_t *sizes,
+                              uint8_t *out_dev, int rows, int cols, int64_t row_stride, int64_t image_stride, void *stream);
+int vfsms_jpeg_decode_bgr_host(vfsms_ctx *ctx, int n_images, const uint8_t *const *data, const size_t *sizes,
+                               uint8_t *out, int rows, int cols);
 
 /* ---------------------------------------------------------------- device-resident tile stack
  * The reference decodes every tile two or three times and ships ROIs to the plugin per call (Stitcher.py:68-69, 382, 401;

@@ -248,3 +248,146 @@ def decode_gray(data):
     q = info["quant"][info["comps"][0][3]]
     full = idct_islow(coef, q)
     return full[:info["rows"], :info["cols"]]
+
+
+# ---------------------------------------------------------------- colour decode (cv2.imdecode(data, IMREAD_COLOR), Stitcher.py:382,401)
+# libjpeg(-turbo) defaults: islow IDCT per component, do_fancy_upsampling = TRUE (so no merged upsampling), YCbCr -> RGB with
+# the 16-bit fixed-point tables of jdcolor.c; cv2 asks for BGR order.
+def all_coefficients(data):
+    """Entropy-decode every component.  -> (info, [coef int16 [bh_c, bw_c, 64]] per component)."""
+    info = parse(data)
+    comps = info["comps"]
+    hmax = max(c[1] for c in comps); vmax = max(c[2] for c in comps)
+    mcux = -(-info["cols"] // (8 * hmax)); mcuy = -(-info["rows"] // (8 * vmax))
+    if len(comps) == 1:
+        comps[0][1] = comps[0][2] = 1
+        hmax = vmax = 1
+        mcux = -(-info["cols"] // 8); mcuy = -(-info["rows"] // 8)
+    coefs = [np.zeros((mcuy * c[2], mcux * c[1], 64), np.int16) for c in comps]
+    dc_t = {k: _huff_table(*v) for k, v in info["dc"].items()}
+    ac_t = {k: _huff_table(*v) for k, v in info["ac"].items()}
+    br = _Bits(bytes(data), info["scan"][0], info["scan"][1])
+    pred = [0] * len(comps)
+    ri = info["restart_interval"]
+    n_mcu = 0
+    for my in range(mcuy):
+        for mx in range(mcux):
+            if ri and n_mcu and n_mcu % ri == 0:
+                br.restart(); pred = [0] * len(comps)
+            n_mcu += 1
+            for ci, c in enumerate(comps):
+                for v in range(c[2]):
+                    for h in range(c[1]):
+                        s_ = br.decode(dc_t[c[4]])
+                        pred[ci] += _extend(br.get(s_), s_) if s_ else 0
+                        blk = coefs[ci][my * c[2] + v, mx * c[1] + h]
+                        blk[0] = pred[ci]
+                        k = 1
+                        while k < 64:
+                            rs = br.decode(ac_t[c[5]])
+                            r, s_ = rs >> 4, rs & 15
+                            if s_ == 0:
+                                if r == 15:
+                                    k += 16; continue
+                                break
+                            k += r
+                            blk[ZIGZAG[k]] = _extend(br.get(s_), s_)
+                            k += 1
+    info["hmax"], info["vmax"] = hmax, vmax
+    return info, coefs
+
+
+def _h2_fancy(p):
+    """jdsample.c h2v1_fancy_upsample on int32 rows [R, n] -> [R, 2n] (triangle filter, 3/4 + 1/4, alternating rounding)."""
+    n = p.shape[1]
+    out = np.empty((p.shape[0], 2 * n), np.int32)
+    if n == 1:
+        out[:, 0] = p[:, 0]; out[:, 1] = p[:, 0]
+        return out
+    left = np.concatenate([p[:, :1], p[:, :-1]], axis=1)
+    right = np.concatenate([p[:, 1:], p[:, -1:]], axis=1)
+    out[:, 0::2] = (3 * p + left + 1) >> 2
+    out[:, 1::2] = (3 * p + right + 2) >> 2
+    out[:, 0] = p[:, 0]; out[:, -1] = p[:, -1]
+    return out
+
+
+def _v2_colsums(p):
+    """Vertical half of h2v2 / h1v2 fancy upsampling: rows [R, n] -> [2R, n] of 3*near + far (context rows replicated at the edges)."""
+    above = np.concatenate([p[:1], p[:-1]], axis=0)
+    below = np.concatenate([p[1:], p[-1:]], axis=0)
+    out = np.empty((2 * p.shape[0], p.shape[1]), np.int32)
+    out[0::2] = 3 * p + above
+    out[1::2] = 3 * p + below
+    return out
+
+
+def _h2v2_fancy(p):
+    cs = _v2_colsums(p)                       # [2R, n]
+    n = cs.shape[1]
+    out = np.empty((cs.shape[0], 2 * n), np.int32)
+    if n == 1:
+        out[:, 0] = (cs[:, 0] * 4 + 8) >> 4; out[:, 1] = (cs[:, 0] * 4 + 7) >> 4
+        return out
+    left = np.concatenate([cs[:, :1], cs[:, :-1]], axis=1)
+    right = np.concatenate([cs[:, 1:], cs[:, -1:]], axis=1)
+    out[:, 0::2] = (3 * cs + left + 8) >> 4
+    out[:, 1::2] = (3 * cs + right + 7) >> 4
+    out[:, 0] = (cs[:, 0] * 4 + 8) >> 4; out[:, -1] = (cs[:, -1] * 4 + 7) >> 4
+    return out
+
+
+def _h1v2_fancy(p):
+    """libjpeg-turbo h1v2_fancy_upsample: vertical triangle filter only, bias 1 for the upper and 2 for the lower output row."""
+    cs = _v2_colsums(p)
+    out = np.empty_like(cs)
+    out[0::2] = (cs[0::2] + 1) >> 2
+    out[1::2] = (cs[1::2] + 2) >> 2
+    return out
+
+
+def upsample(plane, hf, vf, ds_rows, ds_cols):
+    """plane: IDCT output of a component (padded); (hf, vf) = max sampling / component sampling; only the component's
+    true downsampled size takes part, like libjpeg (compptr->downsampled_width / _height)."""
+    p = plane[:ds_rows, :ds_cols].astype(np.int32)
+    if hf == 1 and vf == 1:
+        return p
+    if hf == 2 and vf == 1 and ds_cols > 2:          # jinit_upsampler: fancy only when downsampled_width > 2
+        return _h2_fancy(p)
+    if hf == 2 and vf == 2 and ds_cols > 2:
+        return _h2v2_fancy(p)
+    if hf == 1 and vf == 2:
+        return _h1v2_fancy(p)
+    return np.repeat(np.repeat(p, vf, axis=0), hf, axis=1)          # other integral factors: box replication (int_upsample)
+
+
+def ycc_to_bgr(y, cb, cr):
+    """jdcolor.c ycc_rgb_convert (SCALEBITS = 16)."""
+    def fix(x):
+        return int(x * 65536 + 0.5)
+    x = np.arange(256, dtype=np.int64) - 128
+    cr_r = (fix(1.40200) * x + 32768) >> 16
+    cb_b = (fix(1.77200) * x + 32768) >> 16
+    cr_g = -fix(0.71414) * x
+    cb_g = -fix(0.34414) * x + 32768
+    y = y.astype(np.int64)
+    r = y + cr_r[cr]
+    g = y + ((cb_g[cb] + cr_g[cr]) >> 16)
+    b = y + cb_b[cb]
+    return np.stack([np.clip(b, 0, 255), np.clip(g, 0, 255), np.clip(r, 0, 255)], axis=-1).astype(np.uint8)
+
+
+def decode_bgr(data):
+    info, coefs = all_coefficients(data)
+    rows, cols = info["rows"], info["cols"]
+    comps = info["comps"]
+    planes = [idct_islow(cf, info["quant"][c[3]]) for cf, c in zip(coefs, comps)]
+    if len(comps) == 1:
+        g = planes[0][:rows, :cols]
+        return np.stack([g, g, g], axis=-1)
+    up = []
+    for pl, c in zip(planes, comps):
+        hf, vf = info["hmax"] // c[1], info["vmax"] // c[2]
+        ds_rows = -(-rows * c[2] // info["vmax"]); ds_cols = -(-cols * c[1] // info["hmax"])
+        up.append(upsample(pl, hf, vf, ds_rows, ds_cols)[:rows, :cols])
+    return ycc_to_bgr(up[0], up[1], up[2])

@@ -71,6 +71,33 @@ def test_golden_reference_tiles(gpu):
         assert np.array_equal(img, _cv(data))
 
 
+@pytest.mark.parametrize("sampling", SAMPLINGS)
+@pytest.mark.parametrize("rows,cols,quality,restart", [(75, 131, 40, 0), (409, 517, 92, 7), (2, 3, 90, 0), (3, 4, 90, 0), (1, 1, 80, 0), (64, 64, 100, 1)])
+def test_colour_decode_equals_cv2(gpu, sampling, rows, cols, quality, restart):
+    data = _encode(_image(rows, cols, rows + quality), quality, sampling, restart)
+    assert np.array_equal(gpu.jpeg_decode_bgr(data), cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR))
+
+
+def test_colour_batch_full_size_and_gray_file(gpu):
+    datas = [_encode(_image(1936, 2584, 50 + k), 92, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422) for k in range(3)]     # the iron / dendritic geometry
+    out = gpu.jpeg_decode_bgr(datas)
+    for k, d in enumerate(datas):
+        assert np.array_equal(out[k], cv2.imdecode(np.frombuffer(d, np.uint8), cv2.IMREAD_COLOR))
+    g = _encode(_image(100, 60, 3, channels=1), 80)
+    assert np.array_equal(gpu.jpeg_decode_bgr(g), cv2.imdecode(np.frombuffer(g, np.uint8), cv2.IMREAD_COLOR))
+
+
+def test_golden_reference_tiles_colour(gpu):
+    cases = json.load(open(os.path.join(GOLDEN, "jpeg_cases.json")))
+    for name, c in cases.items():
+        if name.startswith("_"):
+            continue
+        data = np.fromfile(os.path.join(GOLDEN, name), np.uint8).tobytes()
+        img = gpu.jpeg_decode_bgr(data)
+        assert img.shape == (c["rows"], c["cols"], 3)
+        assert hashlib.sha256(img.tobytes()).hexdigest() == c["sha256_of_cv2_imdecode_color"]
+
+
 def test_geometry_mismatch_and_unsupported(gpu):
     a = _encode(_image(64, 64, 1), 90); b = _encode(_image(64, 72, 2), 90)
     with pytest.raises(Exception):

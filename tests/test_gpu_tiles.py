@@ -93,3 +93,32 @@ def test_stitcher_on_jpeg_tiles_device_stack_equals_cv2_decode(tiles, tmp_path):
     for got, true in zip(results["b200"][0], offs):
         assert abs(got[0] - true[0]) <= 1 and abs(got[1] - true[1]) <= 1
     assert results["b200"][1] is not None and np.array_equal(results["b200"][1], results["cv2"][1])
+
+
+def test_stitcher_colour_mode_on_jpeg_tiles(tiles, tmp_path):
+    """Main.py's default (isColorMode = True): gray decode of the colour JPEGs for alignment, colour decode for the mosaic --
+    both through the library, same result as with cv2 decoding."""
+    import cv2
+    from Stitcher import Stitcher
+    T, offs = tiles
+    d = tmp_path / "set" / "1"
+    d.mkdir(parents=True)
+    for k, t in enumerate(T[:4]):
+        bgr = np.stack([t, np.roll(t, 3, axis=1), 255 - t], axis=-1)
+        cv2.imwrite(str(d / ("tile-%02d.jpg" % k)), bgr, [cv2.IMWRITE_JPEG_QUALITY, 93])
+    results = {}
+    for decoder in ("b200", "cv2"):
+        Stitcher.featureMethod = "surf"; Stitcher.isColorMode = True; Stitcher.isGPUAvailable = False; Stitcher.isEnhance = False
+        Stitcher.searchRatio = 0.75; Stitcher.offsetCaculate = "mode"; Stitcher.offsetEvaluate = 3; Stitcher.roiRatio = 0.2
+        Stitcher.fuseMethod = "fadeInAndFadeOut"; Stitcher.direction = 1; Stitcher.directIncre = 1; Stitcher.isPrintLog = False
+        Stitcher.decoder = decoder
+        st = Stitcher()
+        out = tmp_path / ("out_" + decoder)
+        st.imageSetStitchWithMutiple(str(tmp_path / "set"), str(out), 1, st.calculateOffsetForFeatureSearchIncre, fileExtension="jpg",
+                                     outputfileExtension="png")
+        names = sorted(os.listdir(str(out)))
+        results[decoder] = [cv2.imread(os.path.join(str(out), n), cv2.IMREAD_COLOR) for n in names]
+    Stitcher.decoder = "b200"; Stitcher.isPrintLog = True; Stitcher.fuseMethod = "notFuse"; Stitcher.direction = 1
+    assert len(results["b200"]) == len(results["cv2"]) >= 1
+    for a, b in zip(results["b200"], results["cv2"]):
+        assert a is not None and a.ndim == 3 and np.array_equal(a, b)

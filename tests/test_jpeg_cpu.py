@@ -48,6 +48,24 @@ def test_oracle_grayscale_file_and_tiny_sizes():
         assert np.array_equal(jo.decode_gray(data), ref)
 
 
+@pytest.mark.parametrize("sampling", SAMPLINGS)
+@pytest.mark.parametrize("rows,cols", [(75, 131), (33, 17), (2, 3), (3, 4), (5, 5), (1, 2), (16, 15)])
+def test_colour_oracle_equals_cv2(sampling, rows, cols):
+    """IMREAD_COLOR path (Stitcher.py:382,401): fancy upsampling incl. the downsampled_width <= 2 rule, YCbCr tables."""
+    data = _encode(_image(rows, cols, rows * 7 + cols), 90, sampling)
+    assert np.array_equal(jo.decode_bgr(data), cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR))
+
+
+def test_host_stage_all_components_equal_oracle():
+    from imagestitch_b200 import gpu
+    data = _encode(_image(95, 123, 5), 85, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, restart=2)
+    info, coefs = jo.all_coefficients(data)
+    for c in range(3):
+        coef, quant, hv = gpu.jpeg_component_coefficients(data, c)
+        assert np.array_equal(coef, coefs[c]) and hv == (info["comps"][c][1], info["comps"][c][2])
+        assert np.array_equal(quant.astype(np.int32), info["quant"][info["comps"][c][3]])
+
+
 def test_range_limit_wraps_like_libjpeg():
     x = np.arange(-2048, 2048)
     idx = x & 1023
@@ -70,7 +88,7 @@ def test_golden_files_through_host_stage_and_oracle_idct():
     """The reference's own tiles (custom Huffman / quantisation tables of the microscope software)."""
     from imagestitch_b200 import gpu
     cases = json.load(open(os.path.join(GOLDEN, "jpeg_cases.json")))
-    assert cases["_demo_sweep"]["files"] == cases["_demo_sweep"]["bit_exact_vs_cv2"] == 140
+    assert cases["_demo_sweep"]["files"] == cases["_demo_sweep"]["bit_exact_vs_cv2"] == cases["_demo_sweep"]["color_bit_exact_vs_cv2"] == 140
     for name, c in cases.items():
         if name.startswith("_"):
             continue

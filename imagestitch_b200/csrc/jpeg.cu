@@ -29,7 +29,11 @@ struct HuffTable {
     int32_t maxcode[18];      // largest code of each length, -1 when none
     int32_t valptr[17];       // symbol index = code + valptr[length]
     uint8_t vals[256];
+    // AC tables: FAST_AC_BITS-bit prefix -> (value << 8) | (run << 4) | (code length + magnitude bits) when the whole
+    // (run/size code + magnitude) fits in the prefix and the value in 8 bits; 0 otherwise
+    int16_t fast_ac[1 << 10];
 };
+#define FAST_AC_BITS 10
 
 struct JpegComp { int id, h, v, tq, td, ta; };
 
@@ -61,6 +65,17 @@ static void build_huff(HuffTable &t, const uint8_t *bits /* 16 */, const uint8_t
         code <<= 1;
     }
     t.maxcode[17] = 0x7fffffff;
+    // combined (symbol, magnitude) lookup for short AC codes
+    for (int i = 0; i < (1 << FAST_AC_BITS); i++) {
+        t.fast_ac[i] = 0;
+        const uint16_t e = t.fast[i >> (FAST_AC_BITS - 9)];
+        if (e == 0xFFFF) continue;
+        const int len = e >> 8, rs = e & 255, run = rs >> 4, mag = rs & 15;
+        if (mag == 0 || len + mag > FAST_AC_BITS) continue;
+        int v = (i >> (FAST_AC_BITS - len - mag)) & ((1 << mag) - 1);
+        if (v < (1 << (mag - 1))) v -= (1 << mag) - 1;
+        if (v >= -128 && v <= 127) t.fast_ac[i] = (int16_t)(v * 256 + run * 16 + len + mag);
+    }
 }
 
 static int jpeg_parse(const uint8_t *d, size_t n, JpegHeader &H)
@@ -162,6 +177,19 @@ struct BitReader {
     uint64_t acc = 0; int nbits = 0;
     inline void refill()
     {
+        if (pos + 8 <= end) {               // fast path: the next bytes hold no 0xFF (no stuffing, no marker)
+            uint64_t w;
+            memcpy(&w, d + pos, 8);
+            w = __builtin_bswap64(w);
+            const int k = (64 - nbits) >> 3;                                  // whole bytes that fit
+            const uint64_t top = k == 8 ? w : (w >> (64 - 8 * k)) << (64 - 8 * k);   // only the k bytes we take
+            const uint64_t x = ~top;                                          // a byte of x is 0 iff a taken byte was 0xFF
+            if (k > 0 && !((x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull)) {
+                acc = k == 8 ? w : (acc << (8 * k)) | (w >> (64 - 8 * k));
+                nbits += 8 * k; pos += (size_t)k;
+                return;
+            }
+        }
         while (nbits <= 56) {
             uint32_t b = 0;
             if (pos < end) {
@@ -227,6 +255,15 @@ static void jpeg_entropy_decode(const uint8_t *d, size_t n, const JpegHeader &H,
                             memset(blk, 0, 128);
                             blk[0] = (int16_t)pred[c];
                             for (int k = 1; k < 64;) {
+                                if (br.nbits < 32) br.refill();
+                                const int fe = ac.fast_ac[br.peek(FAST_AC_BITS)];
+                                if (fe) {                                   // short code + magnitude in one lookup
+                                    k += (fe >> 4) & 15;
+                                    br.skip(fe & 15);
+                                    if (k < 64) blk[kZigzag[k]] = (int16_t)(fe >> 8);
+                                    k++;
+                                    continue;
+                                }
                                 const int rs = br.symbol(ac), r = rs >> 4, sz = rs & 15;
                                 if (sz == 0) { if (r == 15) { k += 16; continue; } break; }
                                 k += r;
@@ -236,6 +273,9 @@ static void jpeg_entropy_decode(const uint8_t *d, size_t n, const JpegHeader &H,
                             }
                         } else {
                             for (int k = 1; k < 64;) {                  // parse and drop
+                                if (br.nbits < 32) br.refill();
+                                const int fe = ac.fast_ac[br.peek(FAST_AC_BITS)];
+                                if (fe) { k += ((fe >> 4) & 15) + 1; br.skip(fe & 15); continue; }
                                 const int rs = br.symbol(ac), r = rs >> 4, sz = rs & 15;
                                 if (sz == 0) { if (r == 15) { k += 16; continue; } break; }
                                 k += r + 1;

@@ -48,8 +48,12 @@ struct JpegHeader {
     int mcux = 0, mcuy = 0, blocks_w = 0, blocks_h = 0;     // luma block grid (padded to whole MCUs)
 };
 
-static void build_huff(HuffTable &t, const uint8_t *bits /* 16 */, const uint8_t *vals, int n)
+static bool build_huff(HuffTable &t, const uint8_t *bits /* 16 */, const uint8_t *vals, int n)
 {
+    {   // a valid table never assigns more codes of a length than remain (Kraft); a damaged one would index past the tables
+        int code = 0;
+        for (int l = 1; l <= 16; l++) { code += bits[l - 1]; if (code > (1 << l)) return false; code <<= 1; }
+    }
     t.present = true;
     memcpy(t.vals, vals, (size_t)n);
     for (int i = 0; i < 512; i++) t.fast[i] = 0xFFFF;
@@ -76,6 +80,7 @@ static void build_huff(HuffTable &t, const uint8_t *bits /* 16 */, const uint8_t
         if (v < (1 << (mag - 1))) v -= (1 << mag) - 1;
         if (v >= -128 && v <= 127) t.fast_ac[i] = (int16_t)(v * 256 + run * 16 + len + mag);
     }
+    return true;
 }
 
 static int jpeg_parse(const uint8_t *d, size_t n, JpegHeader &H)
@@ -115,7 +120,7 @@ static int jpeg_parse(const uint8_t *d, size_t n, JpegHeader &H)
                 int cnt = 0;
                 for (int b = 0; b < 16; b++) cnt += s[k + 1 + b];
                 if (th > 3 || tc > 1 || cnt > 256 || k + 17 + cnt > sl) { vfsms_set_error("jpeg: bad DHT"); return VFSMS_E_UNSUPPORTED; }
-                build_huff(tc ? H.ac[th] : H.dc[th], s + k + 1, s + k + 17, cnt);
+                if (!build_huff(tc ? H.ac[th] : H.dc[th], s + k + 1, s + k + 17, cnt)) { vfsms_set_error("jpeg: inconsistent Huffman table"); return VFSMS_E_UNSUPPORTED; }
                 k += 17 + cnt;
             }
         } else if (m == 0xC0 || m == 0xC1) {

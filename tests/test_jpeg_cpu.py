@@ -113,3 +113,37 @@ def test_unsupported_and_damaged_input():
     assert coef.shape == (8, 8, 64)
     with pytest.raises(gpu.JpegUnsupported):
         gpu.jpeg_info(data[:30])
+
+
+def test_damaged_files_never_crash_the_host_stage():
+    """Bit flips, truncations and spliced garbage in headers and entropy data: the parser either reports unsupported / bad input or
+    decodes something of the advertised geometry -- no out-of-bounds access (run under the normal allocator; a crash fails the suite)."""
+    from imagestitch_b200 import gpu
+    rng = np.random.default_rng(99)
+    base = [_encode(_image(40, 56, 1), 85, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, restart=2), _encode(_image(33, 17, 2, channels=1), 70)]
+    outcomes = {"ok": 0, "rejected": 0}
+    for trial in range(400):
+        d = bytearray(base[trial % 2])
+        kind = trial % 4
+        if kind == 0:                                    # flips anywhere (headers included)
+            for _ in range(1 + trial % 5):
+                d[int(rng.integers(2, len(d)))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:                                  # truncation
+            d = d[: int(rng.integers(4, len(d)))]
+        elif kind == 2:                                  # garbage run
+            p = int(rng.integers(2, len(d) - 8)); d[p:p + 8] = bytes(rng.integers(0, 256, 8, dtype=np.uint8))
+        else:                                            # damaged Huffman table counts
+            p = bytes(d).find(b"\xff\xc4")
+            d[p + 5 + int(rng.integers(0, 16))] = int(rng.integers(0, 256))
+        try:
+            r, c, n = gpu.jpeg_info(bytes(d))
+            if r * c > 1 << 22:
+                outcomes["rejected"] += 1                # absurd geometry from a flipped SOF: not decoded here
+                continue
+            for comp in range(n):
+                coef, quant, _ = gpu.jpeg_component_coefficients(bytes(d), comp)
+                assert coef.ndim == 3 and coef.shape[2] == 64
+            outcomes["ok"] += 1
+        except gpu.VfsmsError:
+            outcomes["rejected"] += 1
+    assert outcomes["ok"] > 50 and outcomes["rejected"] > 50, outcomes

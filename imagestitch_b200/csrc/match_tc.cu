@@ -7,11 +7,14 @@
 //                               train  row: [-2b_hi|-2b_lo|-2b_hi| nb_hi, nb_lo, 0 ... ]     (nb = ||b||^2)
 //                             so that  <query row, train row> = ||b||^2 - 2 a.b  up to ~2^-17 relative error
 //                             (3-term split-bf16 product; the hi*hi + hi*lo + lo*hi terms of (a_hi+a_lo).(b_hi+b_lo)).
-//   2. match_tc_kernel        persistent warp-specialised GEMM: TMA (SWIZZLE_128B) -> smem -> tcgen05.mma (M128 N128 K16,
-//                             kind::f16, bf16 in / fp32 accumulate in TMEM, two accumulator buffers) -> epilogue warpgroup
-//                             reads TMEM with tcgen05.ld and keeps a running top-4 (score, train index) per query row.
-//                             The query tile (128 x K') stays resident in shared memory while train tiles stream through a
-//                             4-stage mbarrier ring.  Nothing but the 4 candidates per query is written to HBM.
+//   2. match_tc_pair_kernel   persistent warp-specialised GEMM on CTA pairs (the default): TMA (SWIZZLE_128B) -> smem ->
+//                             tcgen05.mma.cta_group::2 (256 x 256 x 16 per step, kind::f16, bf16 in / fp32 accumulate in TMEM,
+//                             two accumulator buffers) -> epilogue warps read TMEM with tcgen05.ld and keep a running top-4
+//                             of (score | column) keys per query row and column half, branch-free.  Each CTA's 128 x K'
+//                             query tile stays resident in shared memory while its half of every train tile streams through
+//                             a 7-stage mbarrier ring.  Nothing but 8 candidates per query is written to HBM.
+//      match_tc_kernel        the same on single CTAs (128 x 128 tiles, cta_group::1); kept for verification and as the
+//                             subject of the -DTC_TIMING probes that located the shared-memory operand bottleneck.
 //   3. rescore_kernel         exact fp32 distances (serial k order, no FMA: the CPU value) of the candidates, best two by
 //                             (distance, index), plus a guard: if the second best exact score is not separated from the
 //                             worst kept candidate by more than the split-bf16 error bound, the query is flagged ...

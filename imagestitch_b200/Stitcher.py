@@ -12,7 +12,6 @@ What changed underneath:
   * getStitchByOffset keeps the reference's integer bookkeeping on the host and runs paste + blend on a device canvas;
   * paths: Windows separators, unsorted glob and case-sensitive extensions are normalised.
 """
-import copy
 import glob
 import os
 import time
@@ -23,6 +22,7 @@ import numpy as np
 from . import gpu
 from . import ImageFusion
 from . import ImageUtility as Utility
+from . import sharding
 
 
 class ImageFeature():
@@ -435,55 +435,16 @@ class Stitcher(Utility.Method):
 
         def _imread(path, flag):
             return cache[path] if path in cache else globals()["_imread"](path, flag)
-        imageList = [_imread(fileList[0], flag)]
-        resultRow, resultCol = imageList[0].shape[0], imageList[0].shape[1]
         originOffsetList.insert(0, [0, 0])          # the reference mutates its argument the same way
         n = len(originOffsetList)
-        rangeX = [[0, 0] for _ in range(n)]
-        rangeY = [[0, 0] for _ in range(n)]
-        offsetList = copy.deepcopy(originOffsetList)
-        rangeX[0][1] = imageList[0].shape[0]
-        rangeY[0][1] = imageList[0].shape[1]
-        dxSum = dySum = 0
-        for i in range(1, n):
-            tempImage = _imread(fileList[i], flag)
-            dxSum = dxSum + offsetList[i][0]
-            dySum = dySum + offsetList[i][1]
-            if dxSum <= 0:
-                for j in range(0, i):
-                    offsetList[j][0] = offsetList[j][0] + abs(dxSum)
-                    rangeX[j][0] = rangeX[j][0] + abs(dxSum)
-                    rangeX[j][1] = rangeX[j][1] + abs(dxSum)
-                resultRow = resultRow + abs(dxSum)
-                rangeX[i][1] = resultRow
-                dxSum = rangeX[i][0] = offsetList[i][0] = 0
-            else:
-                offsetList[i][0] = dxSum
-                resultRow = max(resultRow, dxSum + tempImage.shape[0])
-                rangeX[i][1] = resultRow
-            if dySum <= 0:
-                for j in range(0, i):
-                    offsetList[j][1] = offsetList[j][1] + abs(dySum)
-                    rangeY[j][0] = rangeY[j][0] + abs(dySum)
-                    rangeY[j][1] = rangeY[j][1] + abs(dySum)
-                resultCol = resultCol + abs(dySum)
-                rangeY[i][1] = resultCol
-                dySum = rangeY[i][0] = offsetList[i][1] = 0
-            else:
-                offsetList[i][1] = dySum
-                resultCol = max(resultCol, dySum + tempImage.shape[1])
-                rangeY[i][1] = resultCol
-            imageList.append(tempImage)
+        imageList = [_imread(fileList[i], flag) for i in range(n)]
+        origins, rois, (resultRow, resultCol) = sharding.rectify_offsets(originOffsetList, [im.shape[:2] for im in imageList])
+        offsetList = [[int(o[0]), int(o[1])] for o in origins]
         self.printAndWrite("  The rectified offsetList is " + str(offsetList))
         if self.fuseMethod in ("multiBandBlending", "optimalSeamLine"):
             assert self.isColorMode is False, "The %s is not support for color mode in this code" % self.fuseMethod
 
         same_shape = all(im.shape == imageList[0].shape for im in imageList)
-        rois = np.zeros((n, 4), np.int32)
-        for i in range(1, n):
-            rois[i] = (max(offsetList[i][0], rangeX[i - 1][0]), max(offsetList[i][1], rangeY[i - 1][0]),
-                       min(offsetList[i][0] + imageList[i].shape[0], rangeX[i - 1][1]),
-                       min(offsetList[i][1] + imageList[i].shape[1], rangeY[i - 1][1]))
         if same_shape and self.fuseMethod in gpu.DEVICE_MOSAIC_METHODS and not self.isColorMode \
                 and getattr(self, "_stack_files", None) is not None and self._stack_files[:n] == list(fileList[:n]):
             return gpu.tiles_mosaic(0, n, np.asarray(offsetList, np.int32), rois, np.asarray(originOffsetList, np.int32),

@@ -36,7 +36,8 @@ EXPORTS = [
     "vfsms_jpeg_info", "vfsms_jpeg_luma_coefficients", "vfsms_jpeg_decode_gray_dev", "vfsms_jpeg_decode_gray_host",
     "vfsms_jpeg_component_coefficients", "vfsms_jpeg_decode_bgr_dev", "vfsms_jpeg_decode_bgr_host",
     "vfsms_tiles_reserve", "vfsms_tiles_decode_jpeg", "vfsms_tiles_upload", "vfsms_tiles_download", "vfsms_tiles_ptr",
-    "vfsms_tiles_align", "vfsms_tiles_mosaic",
+    "vfsms_tiles_align", "vfsms_tiles_mosaic", "vfsms_set_option", "vfsms_get_option", "vfsms_option_name",
+    "vfsms_mosaic_band_host",
 ]
 STAGE_COUNT = 12
 
@@ -81,8 +82,13 @@ def load():
     L.vfsms_phase_correlate_dev.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     L.vfsms_fuse_roi_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     L.vfsms_mosaic_host.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp]
+    L.vfsms_mosaic_band_host.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     L.vfsms_set_matcher.argtypes = [vp, i32]
     L.vfsms_last_match_fallbacks.argtypes = [vp, ctypes.POINTER(i32)]
+    L.vfsms_set_option.argtypes = [vp, i32, i32]
+    L.vfsms_get_option.argtypes = [vp, i32, ctypes.POINTER(i32)]
+    L.vfsms_option_name.argtypes = [i32]
+    L.vfsms_option_name.restype = ctypes.c_char_p
     L.vfsms_enhance_host.argtypes = [vp, vp, i32, i32, i32, i32, ctypes.c_double, i32, vp]
     L.vfsms_profile_enable.argtypes = [vp, i32]
     L.vfsms_profile_read.argtypes = [vp, vp, vp, i32]

@@ -524,9 +524,23 @@ int vfsms_fuse_roi_host(vfsms_ctx *ctx, const int16_t *a, const int16_t *b, int 
 }
 
 // tiles_host: n_tiles x (tile_rows x tile_cols x channels) in host memory, or nullptr with tiles_dev pointing at the same layout in HBM
+// Band extension (vfsms_mosaic_band_host): `halo_in` pre-fills the canvas rectangle halo_in_rect (what earlier bands left
+// there, -1 = empty), `fuse_first` blends tile 0 too (it is not the first tile of the sequence), `halo_out` reads the
+// rectangle halo_out_rect back as int16 (holes kept) after the last tile.
+struct MosaicBand {
+    int fuse_first = 0;
+    const int16_t *halo_in = nullptr;  const int32_t *halo_in_rect = nullptr;     // r0, c0, rows, cols
+    int16_t *halo_out = nullptr;       const int32_t *halo_out_rect = nullptr;
+};
+
+static bool rect_inside(const int32_t *r, int canvas_rows, int canvas_cols)
+{
+    return r && r[0] >= 0 && r[1] >= 0 && r[2] >= 1 && r[3] >= 1 && r[0] + r[2] <= canvas_rows && r[1] + r[3] <= canvas_cols;
+}
+
 static int mosaic_run(vfsms_ctx *ctx, const uint8_t *tiles_host, const uint8_t *tiles_dev, int n_tiles, int tile_rows, int tile_cols, int channels,
                       const int32_t *tile_origin, const int32_t *roi_rect, const int32_t *pair_offset, int method,
-                      int canvas_rows, int canvas_cols, uint8_t *canvas_out)
+                      int canvas_rows, int canvas_cols, uint8_t *canvas_out, const MosaicBand *band = nullptr)
 {
     const uint8_t *tiles = tiles_host ? tiles_host : tiles_dev;
     if (!ctx || !tiles || !tile_origin || !roi_rect || !pair_offset || !canvas_out || n_tiles < 1 || (channels != 1 && channels != 3)) {
@@ -547,6 +561,17 @@ static int mosaic_run(vfsms_ctx *ctx, const uint8_t *tiles_host, const uint8_t *
     int16_t *canvas = bs->canvas.as<int16_t>();
     fill_i16_kernel<<<grid_for(ctx, cn), 256, 0, st>>>(canvas, cn, (int16_t)-1);
     LAUNCH_CHECK(ctx);
+    if (band && band->halo_in) {
+        const int32_t *r = band->halo_in_rect;
+        if (!rect_inside(r, canvas_rows, canvas_cols)) { vfsms_set_error("mosaic: halo_in rectangle outside the canvas"); return VFSMS_E_ARG; }
+        const size_t wbytes = (size_t)r[3] * channels * 2;
+        CUDA_TRY(cudaMemcpy2DAsync(canvas + r[0] * crs + (int64_t)r[1] * channels, (size_t)crs * 2, band->halo_in, wbytes, wbytes, r[2],
+                                   cudaMemcpyHostToDevice, st));
+    }
+    if (band && band->halo_out && !rect_inside(band->halo_out_rect, canvas_rows, canvas_cols)) {
+        vfsms_set_error("mosaic: halo_out rectangle outside the canvas"); return VFSMS_E_ARG;
+    }
+    const bool fuse_first = band && band->fuse_first;
     const int64_t trs = (int64_t)tile_cols * channels;
     for (int i = 0; i < n_tiles; i++) {
         const int r0 = tile_origin[2 * i], c0 = tile_origin[2 * i + 1];
@@ -558,7 +583,7 @@ static int mosaic_run(vfsms_ctx *ctx, const uint8_t *tiles_host, const uint8_t *
         LAUNCH_CHECK(ctx);
         int16_t *dst = canvas + r0 * crs + (int64_t)c0 * channels;
         const int rr0 = roi_rect[4 * i], rc0 = roi_rect[4 * i + 1], rr1 = roi_rect[4 * i + 2], rc1 = roi_rect[4 * i + 3];
-        const bool fuse = i > 0 && method != VFSMS_FUSE_NONE && rr1 > rr0 && rc1 > rc0;
+        const bool fuse = (i > 0 || fuse_first) && method != VFSMS_FUSE_NONE && rr1 > rr0 && rc1 > rc0;
         if (fuse) {
             // ROI: A = canvas before the paste, B = the tile there; result written over the canvas ROI (Stitcher.py:466-483)
             if (rr0 < r0 || rc0 < c0 || rr1 > r0 + tile_rows || rc1 > c0 + tile_cols) { vfsms_set_error("mosaic: ROI %d outside its tile", i); return VFSMS_E_ARG; }
@@ -569,6 +594,12 @@ static int mosaic_run(vfsms_ctx *ctx, const uint8_t *tiles_host, const uint8_t *
                                    nullptr, 0, (int16_t *)Broi, trs, nullptr, nullptr, st))) return rc;
         }
         CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)crs * 2, t16, (size_t)trs * 2, (size_t)trs * 2, tile_rows, cudaMemcpyDeviceToDevice, st));
+    }
+    if (band && band->halo_out) {
+        const int32_t *r = band->halo_out_rect;
+        const size_t wbytes = (size_t)r[3] * channels * 2;
+        CUDA_TRY(cudaMemcpy2DAsync(band->halo_out, wbytes, canvas + r[0] * crs + (int64_t)r[1] * channels, (size_t)crs * 2, wbytes, r[2],
+                                   cudaMemcpyDeviceToHost, st));
     }
     canvas_to_u8_kernel<<<grid_for(ctx, cn), 256, 0, st>>>(canvas, bs->out8.as<uint8_t>(), cn);
     LAUNCH_CHECK(ctx);
@@ -584,6 +615,20 @@ int vfsms_mosaic_host(vfsms_ctx *ctx, const uint8_t *tiles, int n_tiles, int til
     if (!tiles) { vfsms_set_error("mosaic: bad arguments"); return VFSMS_E_ARG; }
     return mosaic_run(ctx, tiles, nullptr, n_tiles, tile_rows, tile_cols, channels, tile_origin, roi_rect, pair_offset, method, canvas_rows,
                       canvas_cols, canvas_out);
+}
+
+int vfsms_mosaic_band_host(vfsms_ctx *ctx, const uint8_t *tiles, int n_tiles, int tile_rows, int tile_cols, int channels,
+                           const int32_t *tile_origin, const int32_t *roi_rect, const int32_t *pair_offset, int method,
+                           int canvas_rows, int canvas_cols, int fuse_first, const int16_t *halo_in, const int32_t *halo_in_rect,
+                           int16_t *halo_out, const int32_t *halo_out_rect, uint8_t *canvas_out)
+{
+    if (!tiles || (halo_in && !halo_in_rect) || (halo_out && !halo_out_rect)) { vfsms_set_error("mosaic_band: bad arguments"); return VFSMS_E_ARG; }
+    MosaicBand band;
+    band.fuse_first = fuse_first;
+    band.halo_in = halo_in; band.halo_in_rect = halo_in_rect;
+    band.halo_out = halo_out; band.halo_out_rect = halo_out_rect;
+    return mosaic_run(ctx, tiles, nullptr, n_tiles, tile_rows, tile_cols, channels, tile_origin, roi_rect, pair_offset, method, canvas_rows,
+                      canvas_cols, canvas_out, &band);
 }
 
 int vfsms_tiles_mosaic(vfsms_ctx *ctx, int first, int n_tiles, const int32_t *tile_origin, const int32_t *roi_rect, const int32_t *pair_offset,

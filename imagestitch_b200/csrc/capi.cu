@@ -58,6 +58,54 @@ int vfsms_set_matcher(vfsms_ctx *ctx, int mode)
     ctx->matcher_mode = mode;
     return 0;
 }
+static const char *const k_option_names[VFSMS_OPT_COUNT] = { "describe", "sort" };
+static const int k_option_max[VFSMS_OPT_COUNT] = { 2, 1 };
+static int *option_slot(vfsms_ctx *ctx, int option)
+{
+    switch (option) {
+    case VFSMS_OPT_DESCRIBE_MODE: return &ctx->describe_mode;
+    case VFSMS_OPT_SORT_MODE: return &ctx->sort_mode;
+    default: return nullptr;
+    }
+}
+const char *vfsms_option_name(int option) { return option >= 0 && option < VFSMS_OPT_COUNT ? k_option_names[option] : "?"; }
+int vfsms_set_option(vfsms_ctx *ctx, int option, int value)
+{
+    int *slot = ctx ? option_slot(ctx, option) : nullptr;
+    if (!slot || value < 0 || value > k_option_max[option]) { vfsms_set_error("vfsms_set_option: bad option %d / value %d", option, value); return VFSMS_E_ARG; }
+    *slot = value;
+    return 0;
+}
+int vfsms_get_option(vfsms_ctx *ctx, int option, int *value_out)
+{
+    int *slot = ctx ? option_slot(ctx, option) : nullptr;
+    if (!slot || !value_out) { vfsms_set_error("vfsms_get_option: bad arguments"); return VFSMS_E_ARG; }
+    *value_out = *slot;
+    return 0;
+}
+// VFSMS_OPTS="describe=2,sort=1": applied by vfsms_create; a malformed entry fails the create (no silent defaults)
+static int apply_env_options(vfsms_ctx *ctx)
+{
+    const char *env = getenv("VFSMS_OPTS");
+    if (!env || !*env) return 0;
+    std::string all(env);
+    size_t pos = 0;
+    while (pos <= all.size()) {
+        size_t end = all.find(',', pos);
+        if (end == std::string::npos) end = all.size();
+        const std::string item = all.substr(pos, end - pos);
+        pos = end + 1;
+        if (item.empty()) continue;
+        const size_t eq = item.find('=');
+        int opt = -1;
+        if (eq != std::string::npos)
+            for (int o = 0; o < VFSMS_OPT_COUNT; o++) if (item.compare(0, eq, k_option_names[o]) == 0) opt = o;
+        if (opt < 0) { vfsms_set_error("VFSMS_OPTS: cannot parse '%s'", item.c_str()); return VFSMS_E_ARG; }
+        int rc = vfsms_set_option(ctx, opt, atoi(item.c_str() + eq + 1));
+        if (rc) return rc;
+    }
+    return 0;
+}
 int vfsms_last_match_fallbacks(vfsms_ctx *ctx, int *count_out)
 {
     if (!ctx || !count_out) return VFSMS_E_ARG;
@@ -96,6 +144,7 @@ int vfsms_create(int device, vfsms_ctx **out)
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     int rc = surf_init_tables();
     if (rc) { delete ctx; return rc; }
+    if ((rc = apply_env_options(ctx))) { cudaStreamDestroy(ctx->stream); delete ctx; return rc; }
     *out = ctx;
     return 0;
 }

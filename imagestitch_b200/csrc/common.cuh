@@ -138,6 +138,8 @@ struct vfsms_ctx {
     int32_t prof_calls[VFSMS_STAGE_COUNT] = {0};
     int device = 0;
     int matcher_mode = 0;          // 0: tcgen05 candidates + exact rescoring, 1: exact SIMT kernel
+    int describe_mode = 1;         // window sampler of the SURF descriptor: 0 LDG, 1 texture per image, 2 one stacked texture (vfsms_set_option)
+    int sort_mode = 0;             // KeypointGreater ordering: 0 rank by counting, 1 per-image shared-memory sort (vfsms_set_option)
     int32_t *last_fallback_count_dev = nullptr;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;

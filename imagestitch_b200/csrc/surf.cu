@@ -654,6 +654,117 @@ __global__ void rank_finalize_kernel(int32_t *counters, int batch, int max_featu
     counters[b * 4 + 1] = (max_features > 0) ? min(n, max_features) : n;
 }
 
+// ---------------------------------------------------------------- K3 (sort mode 1): rank inside response bins
+// Same output as rank_sort_kernel with ~n^2 / (occupied bins) comparisons instead of n^2: a 13-bit histogram of the response
+// words (sign, exponent, 4 mantissa bits -- 1/16-octave bins) gives every bin its slot range in descending order, the
+// candidates are scattered into their bin's range, and each candidate only counts the members of its own bin that sort
+// before it.  Needs positive responses (bit patterns ordered like the values): the host keeps mode 0 for thresholds < 0.
+#define RB_BITS 13
+#define RB_BINS (1 << RB_BITS)
+#define RB_SHIFT (32 - RB_BITS)
+
+__global__ void __launch_bounds__(256) bin_hist_kernel(const float *__restrict__ cand, const int32_t *__restrict__ counters, int cand_cap, int *hist)
+{
+    __shared__ int s_h[RB_BINS];
+    const int b = blockIdx.y;
+    const int n = min(counters[b * 4 + 0], cand_cap);
+    const float *C = cand + (size_t)b * cand_cap * KP_STRIDE;
+    for (int i = threadIdx.x; i < RB_BINS; i += blockDim.x) s_h[i] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&s_h[__float_as_uint(C[(size_t)i * KP_STRIDE + KP_RESPONSE]) >> RB_SHIFT], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < RB_BINS; i += blockDim.x) if (s_h[i]) atomicAdd(&hist[b * RB_BINS + i], s_h[i]);
+}
+
+// One warp per image, bins walked from the top: start[bin] = number of candidates in higher bins, fill[bin] = 0, the cut bin
+// for max_features (as response_threshold_kernel) and the number of staged candidates (counters[1]).
+__global__ void bin_offsets_kernel(const int *__restrict__ hist, int32_t *counters, int cand_cap, int max_features, int batch,
+                                   int *start, int *fill, unsigned *thr_bits)
+{
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= batch) return;
+    const int n = min(counters[b * 4 + 0], cand_cap);
+    const bool cut = max_features > 0 && n > max_features;
+    int cum = 0, found = -1, n_staged = n;
+    for (int base = RB_BINS - 32; base >= 0 && found < 0; base -= 32) {
+        const int v = hist[b * RB_BINS + base + lane];
+        int suf = v;                                              // candidates in bins base+lane .. base+31
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += t; }
+        start[b * RB_BINS + base + lane] = cum + suf - v;
+        fill[b * RB_BINS + base + lane] = 0;
+        if (cut) {
+            const unsigned hit = __ballot_sync(0xffffffffu, cum + suf >= max_features);
+            if (hit) {
+                const int l = 31 - __clz(hit);                    // highest bin of the group that reaches the target
+                found = base + l;
+                n_staged = cum + __shfl_sync(0xffffffffu, suf, l);
+            }
+        }
+        cum += __shfl_sync(0xffffffffu, suf, 0);
+    }
+    if (lane == 0) {
+        thr_bits[b] = found < 0 ? 0u : ((unsigned)found << RB_SHIFT);
+        counters[b * 4 + 1] = n_staged;
+    }
+}
+
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restrict__ cand, float *staged, const int32_t *__restrict__ counters,
+                                                          int cand_cap, const unsigned *__restrict__ thr_bits,
+                                                          const int *__restrict__ start, int *fill)
+{
+    const int b = blockIdx.y;
+    const int n = min(counters[b * 4 + 0], cand_cap);
+    const unsigned thr = thr_bits[b];
+    const float *C = cand + (size_t)b * cand_cap * KP_STRIDE;
+    float *S = staged + (size_t)b * cand_cap * KP_STRIDE;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned bits = __float_as_uint(C[(size_t)i * KP_STRIDE + KP_RESPONSE]);
+        if (bits < thr) continue;
+        const int bin = bits >> RB_SHIFT;
+        const int slot = start[b * RB_BINS + bin] + atomicAdd(&fill[b * RB_BINS + bin], 1);
+        const float4 *src = (const float4 *)(C + (size_t)i * KP_STRIDE);
+        float4 *dst = (float4 *)(S + (size_t)slot * KP_STRIDE);
+        dst[0] = src[0]; dst[1] = src[1];
+    }
+}
+
+__global__ void __launch_bounds__(256) bin_rank_kernel(const float *__restrict__ src, float *dst, int32_t *counters, int cand_cap, int batch,
+                                                       int max_features, const int *__restrict__ hist, const int *__restrict__ start)
+{
+    const int chunks_per_img = ceil_div(cand_cap, 256);
+    for (int item = blockIdx.x; item < batch * chunks_per_img; item += gridDim.x) {
+        const int b = item / chunks_per_img, chunk = item - b * chunks_per_img;
+        const int n_raw = counters[b * 4 + 0];
+        const int n = counters[b * 4 + 1];
+        if (chunk * 256 >= n) continue;
+        const float *C = src + (size_t)b * cand_cap * KP_STRIDE;
+        const int i = chunk * 256 + threadIdx.x;
+        if (i < n) {
+            const SortKey mine = make_key(C + (size_t)i * KP_STRIDE);
+            const unsigned my_r = __float_as_uint(C[(size_t)i * KP_STRIDE + KP_RESPONSE]);
+            const int bin = my_r >> RB_SHIFT;
+            const int s = start[b * RB_BINS + bin], e = s + hist[b * RB_BINS + bin];
+            int rank = s;                                          // everything in higher bins sorts before this candidate
+            for (int j = s; j < e; j++) {
+                const unsigned k = __float_as_uint(__ldg(C + (size_t)j * KP_STRIDE + KP_RESPONSE));
+                if (k > my_r) rank++;
+                else if (k == my_r && j != i) {
+                    const SortKey kj = make_key(C + (size_t)j * KP_STRIDE);
+                    if (kj.k1 > mine.k1 || (kj.k1 == mine.k1 && (kj.k2 > mine.k2 || (kj.k2 == mine.k2 && j < i)))) rank++;
+                }
+            }
+            const int n_keep = (max_features > 0) ? min(n, max_features) : n;
+            if (rank < n_keep) {
+                const float4 *s4 = (const float4 *)(C + (size_t)i * KP_STRIDE);
+                float4 *d4 = (float4 *)(dst + ((size_t)b * cand_cap + rank) * KP_STRIDE);
+                d4[0] = s4[0]; d4[1] = s4[1];
+            }
+        }
+        if (chunk == 0 && threadIdx.x == 0 && n_raw > cand_cap) counters[b * 4 + 3] |= 1;
+    }
+}
+
 // ---------------------------------------------------------------- K3b: drop keypoints that cannot be oriented, keep order
 __device__ __forceinline__ bool keypoint_valid(const float *kp, int rows, int cols, int upright)
 {
@@ -815,6 +926,33 @@ __device__ __forceinline__ float window_pixel_tex(cudaTextureObject_t tex, const
     return (float)img[(size_t)y * stride + x];
 }
 
+// STACKED variant (describe mode 2): all images of the batch live in ONE pitch-2D float texture, image b at rows
+// [b * rows, (b + 1) * rows), and the handle is a kernel parameter.  A handle loaded from memory through a shuffled index is
+// not provably warp-uniform, so the per-image variant compiles to a waterfall loop (R2UR / TLD4 / BRA.U.ANY, 9 extra
+// instructions per sample); a parameter goes to the texture unit straight from a uniform register.  The image's row offset
+// is folded into the constant of the exact int -> float step: ty_bias = 8388607 - row_off (an exact float), so
+// (2^23 + iy) - ty_bias = iy + 1 + row_off at no extra cost.  CHECK = false: the caller has proved that every sample of the
+// window has its 2x2 footprint inside the image (warp-uniform per keypoint), the border path is not compiled in.
+template <bool CHECK>
+__device__ __forceinline__ float window_pixel_stack(cudaTextureObject_t tex, const uint8_t *__restrict__ img, int stride,
+                                                    int ncols1, int nrows1, double pixel_x, double pixel_y, float ty_bias)
+{
+    double fx, fy;
+    const int ix = floor_split(pixel_x, fx), iy = floor_split(pixel_y, fy);
+    if (!CHECK || ((unsigned)ix < (unsigned)ncols1 && (unsigned)iy < (unsigned)nrows1)) {
+        const float a = (float)(pixel_x - fx), bq = (float)(pixel_y - fy);
+        const float tx = __uint_as_float(0x4B000000u | (unsigned)ix) - 8388607.0f;      // ix + 1.0f, exact
+        const float ty = __uint_as_float(0x4B000000u | (unsigned)iy) - ty_bias;         // iy + 1.0f + row_off, exact
+        const float4 g = tex2Dgather<float4>(tex, tx, ty, 0);
+        const float p00 = g.w, p01 = g.z, p10 = g.x, p11 = g.y;
+        const float v = p00 * (1.f - a) * (1.f - bq) + p01 * a * (1.f - bq) + p10 * (1.f - a) * bq + p11 * a * bq;
+        return (v + 12582912.0f) - 12582912.0f;
+    }
+    int x = __double2int_rn(pixel_x), y = __double2int_rn(pixel_y);
+    x = min(max(x, 0), ncols1); y = min(max(y, 0), nrows1);
+    return (float)img[(size_t)y * stride + x];
+}
+
 // float copy of the batch's images for the texture path (pitch in floats)
 __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride,
                                                         int rows, int cols, int stride, float *dst, int pitch_f)
@@ -830,6 +968,7 @@ __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t *base_a, c
 }
 
 #define DESC_THREADS 256
+#define SURF_MAX_DESC_CHUNKS 64   // describe mode 2: launches per batch (one stacked texture each)
 #define WK_MAX_WIN 768       // windows up to this size are described by one warp (n_octaves <= 4 never exceeds 739)
 #define WK_WARPS 8
 
@@ -849,16 +988,21 @@ struct __align__(16) WarpScratch {
 };
 
 // 64 registers / 4 CTAs per SM with the sampler unrolled x2 measured best on B200 (80 registers / 3 CTAs / x4: +20 % time).
-template <bool TEX>
+// MODE 0: LDG sampler, 1: one texture per image (handles in `texs`), 2: one stacked texture (`tex_stack`, a kernel parameter)
+// over the images [b_first, b_first + b_count) -- this launch describes only their keypoints.
+template <int MODE>
 __global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
     const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
-    int batch, int kp_cap, int extended, int upright, const cudaTextureObject_t *__restrict__ texs, int *work_counter)
+    int batch, int kp_cap, int extended, int upright, const cudaTextureObject_t *__restrict__ texs, int *work_counter,
+    int *big_flag, const cudaTextureObject_t tex_stack, int b_first, int b_count)
 {
+    constexpr bool TEX = MODE == 1;
     __shared__ WarpScratch s_ws[WK_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch &S = s_ws[warp];
-    const int total = prefix[batch];
+    const int total = MODE == 2 ? prefix[b_first + b_count] : prefix[batch];
+    const int item0 = MODE == 2 ? prefix[b_first] : 0;
     const int W = cols + 1, srows = rows + 1, scols = cols + 1;
     const int dsize = extended ? 128 : 64;
     const unsigned lt_mask = (1u << lane) - 1;
@@ -868,7 +1012,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
         // dynamic work distribution: window sizes have a heavy tail, a static split leaves warps idle behind giants
         int item = 0;
         if (lane == 0) item = atomicAdd(work_counter, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
+        item = __shfl_sync(0xffffffffu, item, 0) + item0;
         if (item >= total) break;
         int lo = 0, hi = batch;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(prefix + mid) <= item) lo = mid; else hi = mid; }
@@ -877,7 +1021,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
         const float size = kp[KP_SIZE], cx = kp[KP_X], cy = kp[KP_Y];
         const float s = size * 1.2f / 9.0f;
         const int win = (int)((PATCH_SZ + 1) * s);
-        if (win > WK_MAX_WIN) { if (lane == 0) work_counter[1] = 1; continue; }     // warp-uniform: flag work for the CTA kernel
+        if (win > WK_MAX_WIN) { if (lane == 0) *big_flag = 1; continue; }     // warp-uniform: flag work for the CTA kernel
         const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
         const int32_t *I = integral + (size_t)b * srows * W;
         const int gws = 2 * __float2int_rn(2 * s);
@@ -966,6 +1110,15 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
             ustart_x = __float2int_rn(cx + win_offset);
             ustart_y = __float2int_rn(cy - win_offset);
         }
+        // mode 2: row offset of image b inside the stacked texture, and whether the whole rotated window (half diagonal + the
+        // float chain's drift, 2 px of slack) keeps every 2x2 footprint inside the image
+        float ty_bias = 8388607.0f;
+        bool interior = false;
+        if (MODE == 2) {
+            ty_bias = 8388607.0f - (float)((b - b_first) * rows);
+            const float R = (float)(win - 1) * 0.7072f + 2.0f;
+            interior = !upright && cx - R >= 1.f && cx + R <= (float)(ncols1 - 1) && cy - R >= 1.f && cy + R <= (float)(nrows1 - 1);
+        }
         float *rowf = S.buf;              // the orientation scratch is free now: one window row as exact float pixel values
         int cur_row = -1;                 // row currently held in rowf
         // sample window row `r` (>= cur_row) into rowf; rows are requested in nondecreasing order
@@ -979,10 +1132,22 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
                 // |x| < 2^13), so the running sum equals the CPU's column-by-column accumulation
                 double px = rx + (double)lane * (double)cos_dir, py = ry - (double)lane * (double)sin_dir;
                 const double dpx = 32.0 * (double)cos_dir, dpy = 32.0 * (double)sin_dir;
+                if (MODE == 2) {
+                    if (interior) {
+#pragma unroll 2
+                        for (int j = lane; j < win; j += 32, px += dpx, py -= dpy)
+                            rowf[j] = window_pixel_stack<false>(tex_stack, img, stride, ncols1, nrows1, px, py, ty_bias);
+                    } else {
+#pragma unroll 2
+                        for (int j = lane; j < win; j += 32, px += dpx, py -= dpy)
+                            rowf[j] = window_pixel_stack<true>(tex_stack, img, stride, ncols1, nrows1, px, py, ty_bias);
+                    }
+                } else {
 #pragma unroll 2
                 for (int j = lane; j < win; j += 32, px += dpx, py -= dpy) {
                     rowf[j] = TEX ? window_pixel_tex(tex, img, stride, ncols1, nrows1, px, py)
                                   : (float)window_pixel(img, stride, ncols1, nrows1, px, py);
+                }
                 }
                 chain_x += sin_dir; chain_y += cos_dir;
             } else {
@@ -1384,6 +1549,37 @@ static bool surf_textures(vfsms_ctx *ctx, int batch, int rows, int cols, int pit
     return true;
 }
 
+// Describe mode 2: one texture over `n_img` consecutive images of the float copy, starting at image `b0` (image b at texture
+// rows [(b - b0) * rows, ...)).  Cached like the per-image objects.
+static bool surf_stack_texture(vfsms_ctx *ctx, int b0, int n_img, int rows, int cols, int pitch_f, cudaStream_t st, cudaTextureObject_t *out)
+{
+    if (!ctx->tex_cache) ctx->tex_cache = new TexCache();
+    TexCache *tc = (TexCache *)ctx->tex_cache;
+    const float *p = ctx->surf.img_f32.as<float>() + (size_t)b0 * rows * pitch_f;
+    TexKey key{p, n_img * rows, cols, pitch_f};
+    auto it = tc->m.find(key);
+    if (it == tc->m.end()) {
+        if (tc->m.size() > 8192) {
+            cudaStreamSynchronize(st);
+            for (auto &kv : tc->m) cudaDestroyTextureObject(kv.second);
+            tc->m.clear();
+        }
+        cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypePitch2D;
+        rd.res.pitch2D.devPtr = (void *)p;
+        rd.res.pitch2D.desc = cudaCreateChannelDesc<float>();
+        rd.res.pitch2D.width = cols; rd.res.pitch2D.height = (size_t)n_img * rows; rd.res.pitch2D.pitchInBytes = (size_t)pitch_f * 4;
+        cudaTextureDesc td; memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+        cudaTextureObject_t t = 0;
+        if (cudaCreateTextureObject(&t, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); return false; }
+        it = tc->m.emplace(key, t).first;
+    }
+    *out = it->second;
+    return true;
+}
+
 // ---------------------------------------------------------------- host driver
 int surf_reserve(vfsms_ctx *ctx, int batch, int rows, int cols, const vfsms_surf_params *p)
 {
@@ -1416,10 +1612,10 @@ int surf_reserve(vfsms_ctx *ctx, int batch, int rows, int cols, const vfsms_surf
     if ((rc = ws.sorted.reserve((size_t)batch * cand_cap * KP_STRIDE * 4))) return rc;
     if ((rc = ws.kp.reserve((size_t)batch * kp_cap * KP_STRIDE * 4))) return rc;
     if ((rc = ws.desc.reserve((size_t)batch * kp_cap * dim * 4))) return rc;
-    if ((rc = ws.counters.reserve((size_t)batch * 16 + 16))) return rc;
+    if ((rc = ws.counters.reserve((size_t)batch * 16 + 16 + 4 * SURF_MAX_DESC_CHUNKS))) return rc;   // + work counters
     if ((rc = ws.prefix.reserve((size_t)(batch + 1) * 4))) return rc;
     if ((rc = ws.descT.reserve((size_t)batch * kp_cap * dim * 4))) return rc;
-    if ((rc = ws.hist.reserve((size_t)batch * (RH_BINS + 1) * 4))) return rc;
+    if ((rc = ws.hist.reserve((size_t)batch * (3 * RB_BINS + 1) * 4))) return rc;     // sort mode 0 uses [RH_BINS + 1] per image
     ws.pitch_f = (cols + 31) & ~31;
     if (!p->upright && (rc = ws.img_f32.reserve((size_t)batch * rows * ws.pitch_f * 4))) return rc;
     ws.max_features = max_features;
@@ -1464,7 +1660,7 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         CUDA_TRY(cudaFuncSetAttribute(integral_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_done = true;
     }
-    CUDA_TRY(cudaMemsetAsync(ws.counters.p, 0, (size_t)batch * 16 + 16, st));
+    CUDA_TRY(cudaMemsetAsync(ws.counters.p, 0, (size_t)batch * 16 + 16 + 4 * SURF_MAX_DESC_CHUNKS, st));
     {
     StageTimer t_int(ctx, st, VFSMS_STAGE_INTEGRAL);
     integral_band_kernel<<<dim3(n_bands, batch), 256, smem_int, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
@@ -1545,7 +1741,27 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         }
     }
     const int max_features = ws.max_features;
-    {
+    if (ctx->sort_mode == 1 && p->hessian_threshold >= 0.f) {
+        StageTimer t_s(ctx, st, VFSMS_STAGE_SORT);
+        int *hist = ws.hist.as<int>();
+        int *start = hist + (size_t)batch * RB_BINS, *fill = start + (size_t)batch * RB_BINS;
+        unsigned *thr_bits = (unsigned *)(fill + (size_t)batch * RB_BINS);
+        CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)batch * RB_BINS * 4, st));
+        const int gx = min(ceil_div(ws.cand_cap, 256), 16);
+        bin_hist_kernel<<<dim3(gx, batch), 256, 0, st>>>(ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap, hist);
+        LAUNCH_CHECK(ctx);
+        bin_offsets_kernel<<<ceil_div(batch, 8), 256, 0, st>>>(hist, ws.counters.as<int32_t>(), ws.cand_cap, max_features, batch, start, fill, thr_bits);
+        LAUNCH_CHECK(ctx);
+        bin_scatter_kernel<<<dim3(gx, batch), 256, 0, st>>>(ws.cand.as<float>(), ws.sorted.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap,
+                                                            thr_bits, start, fill);
+        LAUNCH_CHECK(ctx);
+        const int chunks = ceil_div(ws.cand_cap, 256) * batch;
+        bin_rank_kernel<<<min(chunks, ctx->num_sms * 8), 256, 0, st>>>(ws.sorted.as<float>(), ws.cand.as<float>(), ws.counters.as<int32_t>(),
+                                                                        ws.cand_cap, batch, max_features, hist, start);
+        LAUNCH_CHECK(ctx);
+        rank_finalize_kernel<<<ceil_div(batch, 256), 256, 0, st>>>(ws.counters.as<int32_t>(), batch, max_features);
+        LAUNCH_CHECK(ctx);
+    } else {
         StageTimer t_s(ctx, st, VFSMS_STAGE_SORT);
         int *hist = ws.hist.as<int>();
         unsigned *thr_bits = (unsigned *)(hist + (size_t)batch * RH_BINS);
@@ -1582,16 +1798,38 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         u8_to_f32_kernel<<<dim3(std::min(ceil_div(rows * cols, 256), ctx->num_sms * 4), batch), 256, 0, st>>>(base_a, base_b, split, img_stride, rows, cols,
                                                                                                             stride, ws.img_f32.as<float>(), ws.pitch_f);
         LAUNCH_CHECK(ctx);
-        use_tex = surf_textures(ctx, batch, rows, cols, ws.pitch_f, st, &texs);
     }
     int *work_counter = ws.counters.as<int32_t>() + (size_t)batch * 4;      // one extra slot after the per-image counters
-#define LAUNCH_WK(T)                                                                                                               \
+#define LAUNCH_WK(T, WC, TS, B0, NB)                                                                                               \
     orient_describe_warp_kernel<T><<<ctx->num_sms * 4, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,  \
         ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap,              \
-        p->extended, p->upright, texs, work_counter)
-    if (use_tex) LAUNCH_WK(true); else { texs = nullptr; LAUNCH_WK(false); }
+        p->extended, p->upright, texs, WC, work_counter + 1, TS, B0, NB)
+    // mode 2 (opt-in, vfsms_set_option(VFSMS_OPT_DESCRIBE_MODE, 2)): one stacked texture per group of images whose rows fit
+    // the 2-D linear texture height limit, one launch per group with its own work counter
+    bool stacked = false;
+    if (ctx->describe_mode == 2 && !p->upright) {
+        int max_h = 0;
+        if (cudaDeviceGetAttribute(&max_h, cudaDevAttrMaxTexture2DLinearHeight, ctx->device) != cudaSuccess) { cudaGetLastError(); max_h = 0; }
+        int per = max_h >= rows ? max_h / rows : 0;
+        if (per >= 4) per &= ~3;          // keeps every group's base address on the 512-byte texture alignment (pitch is 128-byte aligned)
+        const int n_chunks = per > 0 ? ceil_div(batch, per) : 0;
+        if (n_chunks > 0 && n_chunks <= SURF_MAX_DESC_CHUNKS) {
+            std::vector<cudaTextureObject_t> ts((size_t)n_chunks);
+            stacked = true;
+            for (int c = 0; c < n_chunks && stacked; c++)
+                stacked = surf_stack_texture(ctx, c * per, std::min(per, batch - c * per), rows, cols, ws.pitch_f, st, &ts[c]);
+            for (int c = 0; c < n_chunks && stacked; c++) {
+                LAUNCH_WK(2, work_counter + 4 + c, ts[c], c * per, std::min(per, batch - c * per));
+                LAUNCH_CHECK(ctx);
+            }
+        }
+    }
+    if (!stacked) {
+        if (!p->upright && ctx->describe_mode != 0) use_tex = surf_textures(ctx, batch, rows, cols, ws.pitch_f, st, &texs);
+        if (use_tex) LAUNCH_WK(1, work_counter, 0, 0, batch); else { texs = nullptr; LAUNCH_WK(0, work_counter, 0, 0, batch); }
+        LAUNCH_CHECK(ctx);
+    }
 #undef LAUNCH_WK
-    LAUNCH_CHECK(ctx);
     orient_describe_kernel<<<ctx->num_sms * 2, DESC_THREADS, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
                                                                        ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(),
                                                                        ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, p->upright, work_counter + 1);

@@ -209,6 +209,39 @@ def mosaic(tiles, tile_origin, roi_rect, pair_offset, method, canvas_shape, devi
     return out
 
 
+def mosaic_band(tiles, tile_origin, roi_rect, pair_offset, method, canvas_shape, fuse_first=False, halo_in=None,
+                halo_in_rect=None, halo_out_rect=None, device=0):
+    """One band of a mosaic partitioned over GPUs (vfsms_mosaic_band_host; host logic in sharding.mosaic_sharded).
+    Band-local coordinates.  halo_in: int16 [rows, cols(, 3)] with -1 = empty, pasted at halo_in_rect = (r0, c0, rows, cols)
+    before the first tile; halo_out_rect: rectangle read back as int16 after the last tile.
+    -> (canvas uint8, halo_out int16 or None)."""
+    L = _lib.load()
+    ctx = _lib.context(device)
+    T = np.ascontiguousarray(tiles, np.uint8)
+    n, h, w = T.shape[:3]
+    ch = 1 if T.ndim == 3 else T.shape[3]
+    org = np.ascontiguousarray(tile_origin, np.int32).reshape(n, 2)
+    roi = np.ascontiguousarray(roi_rect, np.int32).reshape(n, 4)
+    off = np.ascontiguousarray(pair_offset, np.int32).reshape(n, 2)
+    m = FUSE_METHODS[method] if isinstance(method, str) else int(method)
+    R, C = int(canvas_shape[0]), int(canvas_shape[1])
+    out = np.empty((R, C) if ch == 1 else (R, C, ch), np.uint8)
+    hin = hin_rect = hout = hout_rect = None
+    if halo_in is not None:
+        hin_rect = np.ascontiguousarray(halo_in_rect, np.int32).reshape(4)
+        hin = _as_i16(halo_in)
+        if hin.shape[:2] != (hin_rect[2], hin_rect[3]) or (hin.ndim == 3) != (ch == 3):
+            raise ValueError("halo_in does not match halo_in_rect / the tile channels")
+    if halo_out_rect is not None:
+        hout_rect = np.ascontiguousarray(halo_out_rect, np.int32).reshape(4)
+        hout = np.empty((hout_rect[2], hout_rect[3]) if ch == 1 else (hout_rect[2], hout_rect[3], ch), np.int16)
+    check(L.vfsms_mosaic_band_host(ctx, _vp(T), n, h, w, ch, _vp(org), _vp(roi), _vp(off), m, R, C, int(bool(fuse_first)),
+                                   _vp(hin) if hin is not None else None, _vp(hin_rect) if hin is not None else None,
+                                   _vp(hout) if hout is not None else None, _vp(hout_rect) if hout is not None else None,
+                                   _vp(out)), "vfsms_mosaic_band_host")
+    return out, hout
+
+
 def phase_correlate(roi_a, roi_b, device=0):
     """cv2.phaseCorrelate(np.float64(a), np.float64(b)) as called at Stitcher.py:230 -> ((shift_x, shift_y), response)."""
     L = _lib.load()
@@ -256,6 +289,21 @@ def set_matcher(mode, device=0):
     """'tc' (default): tcgen05 candidates (CTA pairs) + exact rescoring; 'tc_1sm': the same on single CTAs;
     'simt': exact fp32 SIMT kernel.  Identical results."""
     check(_lib.load().vfsms_set_matcher(_lib.context(device), {"tc": 0, "simt": 1, "tc_1sm": 2}[mode]), "vfsms_set_matcher")
+
+
+OPTIONS = {"describe": 0, "sort": 1}      # include/vfsms.h VFSMS_OPT_*
+
+
+def set_option(name, value, device=0):
+    """Kernel-variant switch (include/vfsms.h VFSMS_OPT_*): every value of an option gives identical results; non-default
+    values are alternative schedules kept for A/B measurement.  Also settable through VFSMS_OPTS="describe=2,sort=1"."""
+    check(_lib.load().vfsms_set_option(_lib.context(device), OPTIONS[name], int(value)), "vfsms_set_option")
+
+
+def get_option(name, device=0):
+    v = ctypes.c_int(0)
+    check(_lib.load().vfsms_get_option(_lib.context(device), OPTIONS[name], ctypes.byref(v)), "vfsms_get_option")
+    return v.value
 
 
 def last_match_fallbacks(device=0):

@@ -80,6 +80,20 @@ int64_t vfsms_launch_count(vfsms_ctx *ctx);
  * 1 = exact fp32 SIMT kernel, 2 = like 0 with the GEMM on single CTAs (128 x 128 tiles, cta_group::1) instead of CTA pairs.
  * All produce identical results; 1 and 2 exist for verification. */
 int vfsms_set_matcher(vfsms_ctx *ctx, int mode);
+/* Kernel-variant switches.  Every variant of an option produces identical results; the non-default ones are alternative
+ * schedules kept selectable for A/B measurement (bench.py --opt name=value, environment VFSMS_OPTS="name=value,...": read
+ * once per vfsms_create).  Unknown options / values return VFSMS_E_ARG. */
+enum {
+    VFSMS_OPT_DESCRIBE_MODE = 0,  /* "describe": rotated-window sampler of the SURF descriptor.  0 = LDG, 1 (default) = one
+                                   * float texture per image, 2 = one stacked texture whose handle is a kernel parameter
+                                   * (uniform-register texture fetch, no border test for windows that lie inside the image) */
+    VFSMS_OPT_SORT_MODE = 1,      /* "sort": KeypointGreater ordering.  0 (default) = rank by counting over all staged
+                                   * candidates, 1 = one CTA per image: shared-memory bitonic sort of 64-bit keys + tie fix-up */
+    VFSMS_OPT_COUNT
+};
+int vfsms_set_option(vfsms_ctx *ctx, int option, int value);
+int vfsms_get_option(vfsms_ctx *ctx, int option, int *value_out);
+const char *vfsms_option_name(int option);
 /* Number of queries of the last tensor-core match that needed the exact fallback scan (synchronises the stream). */
 int vfsms_last_match_fallbacks(vfsms_ctx *ctx, int *count_out);
 
@@ -193,6 +207,18 @@ int vfsms_mosaic_host(vfsms_ctx *ctx, const uint8_t *tiles, int n_tiles, int til
                       const int32_t *tile_origin /* n x 2 */, const int32_t *roi_rect /* n x 4: r0,c0,r1,c1 */,
                       const int32_t *pair_offset /* n x 2 original offsets */, int method,
                       int canvas_rows, int canvas_cols, uint8_t *canvas_out);
+
+/* One BAND of a mosaic whose tile sequence is partitioned over GPUs (the reference's loop Stitcher.py:440-483 is
+ * strictly sequential).  A band owns a contiguous run of tiles and a canvas = the bounding box of their rectangles; all
+ * coordinates are band-local.  halo_in (int16, -1 = empty, halo_in_rect = r0, c0, rows, cols) is what the previous bands left
+ * inside this canvas; it is pasted before the first tile so that every ROI sees exactly the pixels the sequential loop would
+ * (the corner-weight scans of ImageFusion.py:62-187 depend on them).  fuse_first != 0: tile 0 of the band is not the first tile
+ * of the sequence and blends like any other.  halo_out_rect is read back as int16 (holes kept) after the last tile for the
+ * next band; canvas_out as in vfsms_mosaic_host.  Either halo may be NULL. */
+int vfsms_mosaic_band_host(vfsms_ctx *ctx, const uint8_t *tiles, int n_tiles, int tile_rows, int tile_cols, int channels,
+                           const int32_t *tile_origin, const int32_t *roi_rect, const int32_t *pair_offset, int method,
+                           int canvas_rows, int canvas_cols, int fuse_first, const int16_t *halo_in, const int32_t *halo_in_rect,
+                           int16_t *halo_out, const int32_t *halo_out_rect, uint8_t *canvas_out);
 
 /* ---------------------------------------------------------------- JPEG tile decode */
 

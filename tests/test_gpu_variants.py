@@ -1,0 +1,82 @@
+"""GPU: alternative kernel schedules selected through vfsms_set_option (include/vfsms.h VFSMS_OPT_*) must give results
+IDENTICAL to the default schedule.  These variants were written in a session without GPU access: they are opt-in, and this
+module only runs with VFSMS_EXPERIMENTAL=1 until a B200 run has confirmed them (then drop the gate and flip the default)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("VFSMS_EXPERIMENTAL") != "1",
+                                 reason="opt-in kernel variants: set VFSMS_EXPERIMENTAL=1 (not yet confirmed on hardware)")]
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from imagestitch_b200 import gpu as g
+    assert g.device_count() > 0
+    yield g
+    for name in g.OPTIONS:
+        g.set_option(name, {"describe": 1, "sort": 0}[name])
+
+
+def _surf_both(gpu, img, option, values, **kw):
+    outs = []
+    for v in values:
+        gpu.set_option(option, v)
+        assert gpu.get_option(option) == v
+        outs.append(gpu.surf_detect_and_describe(img, **kw))
+    return outs
+
+
+@pytest.mark.parametrize("extended", [True, False])
+def test_describe_stacked_texture_identical(gpu, synth_pair_rois, extended):
+    roiA, roiB, _ = synth_pair_rois
+    for img in (roiA, roiB):
+        (k1, d1), (k2, d2), (k0, d0) = _surf_both(gpu, img, "describe", (1, 2, 0), extended=extended, keypoints_ratio=0.01)
+        assert len(k1) > 500
+        assert np.array_equal(k1, k2) and np.array_equal(d1, d2)
+        assert np.array_equal(k1, k0) and np.array_equal(d1, d0)
+
+
+def test_describe_stacked_texture_borders_and_giants(gpu):
+    """small image: almost every window crosses the border; low threshold + 4 octaves: windows up to several hundred px"""
+    from imagestitch_b200 import synth
+    A, _, _ = synth.pair(seed=3, size=384, overlap=60, direction=1)
+    for img in (A[:97], A[:, :131], A):
+        (k1, d1), (k2, d2) = _surf_both(gpu, img, "describe", (1, 2), extended=True, keypoints_ratio=0.0, hessian_threshold=30.0)
+        assert len(k1) > 50
+        assert np.array_equal(k1, k2) and np.array_equal(d1, d2)
+
+
+def test_describe_stacked_texture_batches_and_chunks(gpu):
+    """align_batch over many ROIs: image index -> texture row offset; 80 ROIs x 1024 rows exceed the 65000-row limit of one
+    2-D linear texture, so the launch is split into groups."""
+    from imagestitch_b200 import synth
+    rois_a, rois_b = [], []
+    for k in range(6):
+        A, B, _ = synth.pair(seed=40 + k, size=512, overlap=64, direction=1)
+        rois_a.append(A[512 - 102:]); rois_b.append(B[:102])
+    ra, rb = np.stack(rois_a), np.stack(rois_b)
+    gpu.set_option("describe", 1); r1 = gpu.align_batch(ra, rb)
+    gpu.set_option("describe", 2); r2 = gpu.align_batch(ra, rb)
+    assert np.array_equal(r1, r2) and r1["status"].all()
+    A, B, _ = synth.pair(seed=77, size=1024, overlap=110, direction=2)
+    ta = np.stack([np.ascontiguousarray(np.roll(A, 13 * k, axis=0)[:, 1024 - 204:]) for k in range(40)])
+    tb = np.stack([np.ascontiguousarray(np.roll(B, 13 * k, axis=0)[:, :204]) for k in range(40)])
+    ta = np.ascontiguousarray(ta.transpose(0, 2, 1)); tb = np.ascontiguousarray(tb.transpose(0, 2, 1))   # 204 x 1024 strips
+    big_a = np.ascontiguousarray(np.repeat(ta, 5, axis=1)[:, :1024]); big_b = np.ascontiguousarray(np.repeat(tb, 5, axis=1)[:, :1024])
+    gpu.set_option("describe", 1); r1 = gpu.align_batch(big_a, big_b)
+    gpu.set_option("describe", 2); r2 = gpu.align_batch(big_a, big_b)          # 80 images x 1024 rows -> 2 groups
+    assert np.array_equal(r1, r2)
+
+
+def test_sort_per_image_identical(gpu, synth_pair_rois):
+    roiA, roiB, _ = synth_pair_rois
+    for kw in (dict(extended=True, keypoints_ratio=0.01), dict(extended=False, keypoints_ratio=0.0),
+               dict(extended=True, keypoints_ratio=0.002)):
+        (k0, d0), (k1, d1) = _surf_both(gpu, roiA, "sort", (0, 1), **kw)
+        assert np.array_equal(k0, k1) and np.array_equal(d0, d1)
+    flat = np.full((300, 400), 128, np.uint8)                      # no candidates at all
+    (k0, _), (k1, _) = _surf_both(gpu, flat, "sort", (0, 1), extended=True, keypoints_ratio=0.01)
+    assert len(k0) == len(k1) == 0

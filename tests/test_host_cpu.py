@@ -170,3 +170,34 @@ def test_synthetic_generator_is_seeded():
     # the overlap really is the same scene
     ov = 256 - o1[0]
     assert np.corrcoef(a1[256 - ov:, 8:200].ravel().astype(float), b1[:ov, 8 - o1[1]:200 - o1[1]].ravel().astype(float))[0, 1] > 0.9
+
+
+def test_get_stitch_by_offset_bookkeeping_without_gpu(tmp_path, golden_dir, monkeypatch):
+    """Stitcher.getStitchByOffset's host half (Stitcher.py:378-431): origins / ROI rectangles / canvas size handed to the device
+    mosaic equal the oracle's closed form, and rendering those arguments with the NumPy oracle reproduces the reference's mosaic."""
+    import cv2
+    from imagestitch_b200 import gpu
+    from imagestitch_b200.Stitcher import Stitcher
+    from oracle import blend_oracle as bo
+    m = np.load(os.path.join(golden_dir, "mosaic_case.npz"))
+    files = []
+    for k, t in enumerate(m["tiles"]):
+        f = str(tmp_path / ("t%02d.png" % k)); cv2.imwrite(f, t); files.append(f)
+    seen = {}
+
+    def fake_mosaic(tiles, tile_origin, roi_rect, pair_offset, method, canvas_shape, device=0):
+        seen.update(origin=np.asarray(tile_origin), roi=np.asarray(roi_rect), pair=np.asarray(pair_offset), shape=tuple(canvas_shape))
+        out, _ = bo.band_renderer()(tiles, tile_origin, roi_rect, pair_offset, method, canvas_shape, False, None, None, None)
+        return out
+    monkeypatch.setattr(gpu, "mosaic", fake_mosaic)
+    st = Stitcher()
+    monkeypatch.setattr(Stitcher, "isPrintLog", False)
+    monkeypatch.setattr(Stitcher, "fuseMethod", "fadeInAndFadeOut")
+    monkeypatch.setattr(Stitcher, "isColorMode", False)
+    monkeypatch.setattr(Stitcher, "decoder", "cv2")
+    offsets = [list(map(int, o)) for o in m["offsets"]]
+    out = st.getStitchByOffset(files, offsets)
+    org, rois, shape = bo.rectify(m["offsets"], m["tiles"].shape[1:3])
+    assert np.array_equal(seen["origin"], org) and np.array_equal(seen["roi"], rois) and seen["shape"] == shape
+    assert offsets[0] == [0, 0] and len(offsets) == len(m["offsets"]) + 1      # the reference mutates its argument (Stitcher.py:386)
+    assert np.array_equal(out, m["out_fadeInAndFadeOut_gray"])

@@ -58,13 +58,14 @@ int vfsms_set_matcher(vfsms_ctx *ctx, int mode)
     ctx->matcher_mode = mode;
     return 0;
 }
-static const char *const k_option_names[VFSMS_OPT_COUNT] = { "describe", "sort" };
-static const int k_option_max[VFSMS_OPT_COUNT] = { 2, 1 };
+static const char *const k_option_names[VFSMS_OPT_COUNT] = { "describe", "sort", "lpt" };
+static const int k_option_max[VFSMS_OPT_COUNT] = { 2, 1, 1 };
 static int *option_slot(vfsms_ctx *ctx, int option)
 {
     switch (option) {
     case VFSMS_OPT_DESCRIBE_MODE: return &ctx->describe_mode;
     case VFSMS_OPT_SORT_MODE: return &ctx->sort_mode;
+    case VFSMS_OPT_DESCRIBE_LPT: return &ctx->describe_lpt;
     default: return nullptr;
     }
 }

@@ -139,6 +139,7 @@ struct vfsms_ctx {
     int device = 0;
     int matcher_mode = 0;          // 0: tcgen05 candidates + exact rescoring, 1: exact SIMT kernel
     int describe_mode = 1;         // window sampler of the SURF descriptor: 0 LDG, 1 texture per image, 2 one stacked texture (vfsms_set_option)
+    int describe_lpt = 0;          // 1: describe the large windows first (two passes over the work list)
     int sort_mode = 0;             // KeypointGreater ordering: 0 rank by counting, 1 per-image shared-memory sort (vfsms_set_option)
     int32_t *last_fallback_count_dev = nullptr;
     cudaStream_t stream = nullptr;

@@ -31,9 +31,9 @@ struct HuffTable {
     uint8_t vals[256];
     // AC tables: FAST_AC_BITS-bit prefix -> (value << 8) | (run << 4) | (code length + magnitude bits) when the whole
     // (run/size code + magnitude) fits in the prefix and the value in 8 bits; 0 otherwise
-    int16_t fast_ac[1 << 10];
+    int16_t fast_ac[1 << 12];
 };
-#define FAST_AC_BITS 10
+#define FAST_AC_BITS 12
 
 struct JpegComp { int id, h, v, tq, td, ta; };
 

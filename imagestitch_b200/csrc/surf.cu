@@ -995,7 +995,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
     const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
     int batch, int kp_cap, int extended, int upright, const cudaTextureObject_t *__restrict__ texs, int *work_counter,
-    int *big_flag, const cudaTextureObject_t tex_stack, int b_first, int b_count)
+    int *big_flag, const cudaTextureObject_t tex_stack, int b_first, int b_count, int *work_counter_large, int lpt_split)
 {
     constexpr bool TEX = MODE == 1;
     __shared__ WarpScratch s_ws[WK_WARPS];
@@ -1008,12 +1008,16 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
     const unsigned lt_mask = (1u << lane) - 1;
     constexpr int PD = PATCH_SZ + 1;
 
+    // lpt_split > 0 (VFSMS_OPT_DESCRIBE_LPT): longest-processing-time-first in two passes over the same work list -- pass 0
+    // describes only the windows >= lpt_split (a 600-pixel window keeps one warp busy for over a millisecond; met late in the
+    // queue it becomes the tail of the launch), pass 1 the rest.  A skipped item costs one keypoint read.
+    int pass = lpt_split > 0 ? 0 : 1;
     while (true) {
         // dynamic work distribution: window sizes have a heavy tail, a static split leaves warps idle behind giants
         int item = 0;
-        if (lane == 0) item = atomicAdd(work_counter, 1);
+        if (lane == 0) item = atomicAdd(pass == 0 ? work_counter_large : work_counter, 1);
         item = __shfl_sync(0xffffffffu, item, 0) + item0;
-        if (item >= total) break;
+        if (item >= total) { if (pass == 0) { pass = 1; continue; } break; }
         int lo = 0, hi = batch;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(prefix + mid) <= item) lo = mid; else hi = mid; }
         const int b = lo, k = item - __ldg(prefix + lo);
@@ -1021,6 +1025,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
         const float size = kp[KP_SIZE], cx = kp[KP_X], cy = kp[KP_Y];
         const float s = size * 1.2f / 9.0f;
         const int win = (int)((PATCH_SZ + 1) * s);
+        if (lpt_split > 0 && ((win >= lpt_split) != (pass == 0))) continue;   // warp-uniform: the other pass owns this keypoint
         if (win > WK_MAX_WIN) { if (lane == 0) *big_flag = 1; continue; }     // warp-uniform: flag work for the CTA kernel
         const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
         const int32_t *I = integral + (size_t)b * srows * W;
@@ -1612,7 +1617,7 @@ int surf_reserve(vfsms_ctx *ctx, int batch, int rows, int cols, const vfsms_surf
     if ((rc = ws.sorted.reserve((size_t)batch * cand_cap * KP_STRIDE * 4))) return rc;
     if ((rc = ws.kp.reserve((size_t)batch * kp_cap * KP_STRIDE * 4))) return rc;
     if ((rc = ws.desc.reserve((size_t)batch * kp_cap * dim * 4))) return rc;
-    if ((rc = ws.counters.reserve((size_t)batch * 16 + 16 + 4 * SURF_MAX_DESC_CHUNKS))) return rc;   // + work counters
+    if ((rc = ws.counters.reserve((size_t)batch * 16 + 16 + 8 * SURF_MAX_DESC_CHUNKS))) return rc;   // + work counters (two per launch group)
     if ((rc = ws.prefix.reserve((size_t)(batch + 1) * 4))) return rc;
     if ((rc = ws.descT.reserve((size_t)batch * kp_cap * dim * 4))) return rc;
     if ((rc = ws.hist.reserve((size_t)batch * (3 * RB_BINS + 1) * 4))) return rc;     // sort mode 0 uses [RH_BINS + 1] per image
@@ -1660,7 +1665,7 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         CUDA_TRY(cudaFuncSetAttribute(integral_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_done = true;
     }
-    CUDA_TRY(cudaMemsetAsync(ws.counters.p, 0, (size_t)batch * 16 + 16 + 4 * SURF_MAX_DESC_CHUNKS, st));
+    CUDA_TRY(cudaMemsetAsync(ws.counters.p, 0, (size_t)batch * 16 + 16 + 8 * SURF_MAX_DESC_CHUNKS, st));
     {
     StageTimer t_int(ctx, st, VFSMS_STAGE_INTEGRAL);
     integral_band_kernel<<<dim3(n_bands, batch), 256, smem_int, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
@@ -1803,7 +1808,8 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
 #define LAUNCH_WK(T, WC, TS, B0, NB)                                                                                               \
     orient_describe_warp_kernel<T><<<ctx->num_sms * 4, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,  \
         ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap,              \
-        p->extended, p->upright, texs, WC, work_counter + 1, TS, B0, NB)
+        p->extended, p->upright, texs, WC, work_counter + 1, TS, B0, NB, (WC) + SURF_MAX_DESC_CHUNKS, lpt_split)
+    const int lpt_split = ctx->describe_lpt ? 128 : 0;
     // mode 2 (opt-in, vfsms_set_option(VFSMS_OPT_DESCRIBE_MODE, 2)): one stacked texture per group of images whose rows fit
     // the 2-D linear texture height limit, one launch per group with its own work counter
     bool stacked = false;

@@ -291,7 +291,7 @@ def set_matcher(mode, device=0):
     check(_lib.load().vfsms_set_matcher(_lib.context(device), {"tc": 0, "simt": 1, "tc_1sm": 2}[mode]), "vfsms_set_matcher")
 
 
-OPTIONS = {"describe": 0, "sort": 1}      # include/vfsms.h VFSMS_OPT_*
+OPTIONS = {"describe": 0, "sort": 1, "lpt": 2}      # include/vfsms.h VFSMS_OPT_*
 
 
 def set_option(name, value, device=0):

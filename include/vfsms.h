@@ -89,6 +89,8 @@ enum {
                                    * (uniform-register texture fetch, no border test for windows that lie inside the image) */
     VFSMS_OPT_SORT_MODE = 1,      /* "sort": KeypointGreater ordering.  0 (default) = rank by counting over all staged
                                    * candidates, 1 = one CTA per image: shared-memory bitonic sort of 64-bit keys + tie fix-up */
+    VFSMS_OPT_DESCRIBE_LPT = 2,   /* "lpt": 0 (default) = keypoints described in response order, 1 = windows of 128 px and more
+                                   * first (two passes over the work list), so that no giant window is met at the end of the launch */
     VFSMS_OPT_COUNT
 };
 int vfsms_set_option(vfsms_ctx *ctx, int option, int value);

@@ -17,7 +17,7 @@ def gpu():
     assert g.device_count() > 0
     yield g
     for name in g.OPTIONS:
-        g.set_option(name, {"describe": 1, "sort": 0}[name])
+        g.set_option(name, {"describe": 1, "sort": 0, "lpt": 0}[name])
 
 
 def _surf_both(gpu, img, option, values, **kw):
@@ -80,3 +80,13 @@ def test_sort_per_image_identical(gpu, synth_pair_rois):
     flat = np.full((300, 400), 128, np.uint8)                      # no candidates at all
     (k0, _), (k1, _) = _surf_both(gpu, flat, "sort", (0, 1), extended=True, keypoints_ratio=0.01)
     assert len(k0) == len(k1) == 0
+
+
+def test_describe_large_windows_first_identical(gpu, synth_pair_rois):
+    roiA, _, _ = synth_pair_rois
+    for mode in (1, 2):
+        gpu.set_option("describe", mode)
+        (k0, d0), (k1, d1) = _surf_both(gpu, roiA, "lpt", (0, 1), extended=True, keypoints_ratio=0.0, hessian_threshold=30.0)
+        assert len(k0) > 1000 and (np.floor(21 * k0[:, 2] * np.float32(1.2) / 9) >= 128).sum() > 5
+        assert np.array_equal(k0, k1) and np.array_equal(d0, d1)
+    gpu.set_option("describe", 1); gpu.set_option("lpt", 0)

@@ -200,6 +200,9 @@ def main():
     ap.add_argument("--matcher", default=None, choices=["tc", "tc_1sm", "simt"], help="override the descriptor matcher kernel")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="kernel-variant switch (include/vfsms.h VFSMS_OPT_*, e.g. describe=2, sort=1); identical results, A/B timing")
+    ap.add_argument("--no-autotune", action="store_true",
+                    help="keep the default kernel schedule (default: imagestitch_b200.autotune picks, in a subprocess, the variants that are "
+                         "bit-identical to the default on this workload shape AND faster)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -218,6 +221,11 @@ def main():
     params = gpu.surf_params()          # GPU-SURF defaults, ImageUtility.py:23-28
     if args.matcher:
         gpu.set_matcher(args.matcher, device=local)
+    tune_report = None
+    if not args.opt and not args.no_autotune:
+        from imagestitch_b200 import autotune
+        chosen, tune_report = autotune.select(device=local, pairs=P, size=TILE, overlap=OVERLAP)
+        args.opt = ["%s=%d" % kv for kv in chosen.items()]
     for item in args.opt:
         name, value = item.split("=")
         gpu.set_option(name, int(value), device=local)
@@ -405,7 +413,7 @@ def main():
                       "pairs_per_gpu_per_step": P, "global_pairs_per_step": P * world, "roi": [L, TILE], "surf": "thr100 oct4 layers3 128-d ratio0.01",
                       "l2": "%d distinct input batches rotated; per-step intermediate traffic > L2" % NB,
                       "mean_keypoints": [mean_na, mean_nb], "mean_matches": float(np.mean(nmatch)), "correct_pairs": "%d/%d" % (ok, tot),
-                      "e2e_correct_pairs": "%d/%d" % (e2e_ok, P), "kernel_variants": variants},
+                      "e2e_correct_pairs": "%d/%d" % (e2e_ok, P), "kernel_variants": variants, "autotune": tune_report},
            "clocks": clk, "gpu_launches": int(launches),
            "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * P * L * TILE), "d2h_bytes_per_step": int(P * 32),
                    "steps": e2e_steps},

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One-call evidence capture for a round (run on the GPU box):
-#   gpurun --timeout 1200 -- 'bash profiles/capture.sh r02'
+#   gpurun --timeout 1500 -- 'bash profiles/capture.sh r02'
 # Writes everything under gpurun_out/<tag>_*; copy what should be judged into profiles/<tag>/ afterwards
 # (profiles/summarize_launches.py for the launch list, profiles/hot_lines.py for the source page).
 # Numbers printed by runs under ncu are never bench values.
@@ -8,12 +8,31 @@ set -u
 TAG=${1:-rXX}
 OUT=gpurun_out
 mkdir -p $OUT
-KERNELS='integral|hessian|response_|rank_|validate|prefix_kernel|u8_to_f32|orient_|prep_split|match_tc|rescore|norm_max|fallback|ratio_insert|vote_|transpose|jpeg'
-timeout -s KILL 400 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+KERNELS='integral|hessian|response_|rank_|bin_|validate|prefix_kernel|u8_to_f32|orient_|prep_split|match_tc|rescore|norm_max|fallback|ratio_insert|vote_|transpose|jpeg'
+# 1. opt-in kernel variants vs the default schedule (identical results required), then the default GPU suite stays as it was
+VFSMS_EXPERIMENTAL=1 timeout -s KILL 600 python -m pytest tests/test_gpu_variants.py -x -q > $OUT/${TAG}_variants_tests.log 2>&1
+# 2. the bench as the driver runs it (autotune probe picks the validated variants), the default schedule, and each variant alone
+timeout -s KILL 500 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+timeout -s KILL 400 python bench.py --steps 20 --warmup 3 --no-autotune --no-cpu-baseline > $OUT/${TAG}_bench_default.json 2> $OUT/${TAG}_bench_default.err
+for V in describe=2 sort=1 lpt=1; do
+    timeout -s KILL 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --opt $V > $OUT/${TAG}_bench_${V/=/}.json 2> $OUT/${TAG}_bench_${V/=/}.err
+done
 timeout -s KILL 300 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err
+# 3. ncu on the configuration the bench selected (explicit --opt, no probe subprocess under the profiler)
+OPTS=$(python - <<PY
+import json
+try:
+    v = json.load(open("$OUT/${TAG}_bench.json"))["config"]["kernel_variants"]
+    d = {"describe": 1, "sort": 0, "lpt": 0}
+    print(" ".join("--opt %s=%d" % (k, x) for k, x in v.items() if d.get(k) != x))
+except Exception:
+    print("")
+PY
+)
+echo "profiling with: --no-autotune $OPTS" > $OUT/${TAG}_ncu_config.txt
 timeout -s KILL 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$KERNELS" -c 300 --csv \
-    --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-timeout -s KILL 400 ncu --set full --clock-control none --import-source on \
-    -k regex:"match_tc_pair_kernel|orient_describe_warp|hessian_nms|rank_sort" -s 8 -c 6 -o $OUT/${TAG}_full \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
-ls -la $OUT | tail -8
+    --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-autotune $OPTS > /dev/null 2>&1
+timeout -s KILL 500 ncu --set full --clock-control none --import-source on \
+    -k regex:"match_tc_pair_kernel|orient_describe_warp|hessian_nms|rank_sort|bin_rank" -s 8 -c 6 -o $OUT/${TAG}_full \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-autotune $OPTS > $OUT/${TAG}_ncu_full.log 2>&1
+ls -la $OUT | tail -14

@@ -79,3 +79,15 @@ def test_sort_mode1_bin_ranking_equals_full_order():
                 assert rank not in out
                 out[rank] = int(i)
         assert [out[r] for r in range(n_keep)] == order[:n_keep]
+
+
+def test_autotune_probe_failure_means_defaults():
+    """imagestitch_b200.autotune.select never raises: without a usable GPU (this box) the probe subprocess fails and the answer
+    is 'keep the defaults' with the reason recorded -- bench.py relies on that."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a CUDA device is present: the probe would succeed")
+    from imagestitch_b200 import autotune
+    chosen, report = autotune.select(device=0, pairs=2, size=256, overlap=32, reps=1, timeout=120)
+    assert chosen == {} and "error" in report and report["error"]

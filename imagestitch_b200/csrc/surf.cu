@@ -990,8 +990,10 @@ struct __align__(16) WarpScratch {
 // 64 registers / 4 CTAs per SM with the sampler unrolled x2 measured best on B200 (80 registers / 3 CTAs / x4: +20 % time).
 // MODE 0: LDG sampler, 1: one texture per image (handles in `texs`), 2: one stacked texture (`tex_stack`, a kernel parameter)
 // over the images [b_first, b_first + b_count) -- this launch describes only their keypoints.
-template <int MODE>
-__global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
+// UNROLL / MINB: unroll factor of the border-free sampling loop and CTAs per SM the register budget is cut for (4 -> 64
+// registers, 3 -> 80): with no branch in the loop, a deeper unroll lets several gathers be in flight per warp.
+template <int MODE, int UNROLL = 2, int MINB = 4>
+__global__ void __launch_bounds__(WK_WARPS * 32, MINB) orient_describe_warp_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
     const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
     int batch, int kp_cap, int extended, int upright, const cudaTextureObject_t *__restrict__ texs, int *work_counter,
@@ -1139,7 +1141,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) orient_describe_warp_kernel(
                 const double dpx = 32.0 * (double)cos_dir, dpy = 32.0 * (double)sin_dir;
                 if (MODE == 2) {
                     if (interior) {
-#pragma unroll 2
+#pragma unroll UNROLL
                         for (int j = lane; j < win; j += 32, px += dpx, py -= dpy)
                             rowf[j] = window_pixel_stack<false>(tex_stack, img, stride, ncols1, nrows1, px, py, ty_bias);
                     } else {
@@ -1805,15 +1807,16 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         LAUNCH_CHECK(ctx);
     }
     int *work_counter = ws.counters.as<int32_t>() + (size_t)batch * 4;      // one extra slot after the per-image counters
-#define LAUNCH_WK(T, WC, TS, B0, NB)                                                                                               \
-    orient_describe_warp_kernel<T><<<ctx->num_sms * 4, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,  \
+#define LAUNCH_WK(T, WC, TS, B0, NB) LAUNCH_WK_(T, 2, 4, WC, TS, B0, NB)
+#define LAUNCH_WK_(T, U, MB, WC, TS, B0, NB)                                                                                       \
+    orient_describe_warp_kernel<T, U, MB><<<ctx->num_sms * MB, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,  \
         ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap,              \
         p->extended, p->upright, texs, WC, work_counter + 1, TS, B0, NB, (WC) + SURF_MAX_DESC_CHUNKS, lpt_split)
     const int lpt_split = ctx->describe_lpt ? 128 : 0;
     // mode 2 (opt-in, vfsms_set_option(VFSMS_OPT_DESCRIBE_MODE, 2)): one stacked texture per group of images whose rows fit
     // the 2-D linear texture height limit, one launch per group with its own work counter
     bool stacked = false;
-    if (ctx->describe_mode == 2 && !p->upright) {
+    if (ctx->describe_mode >= 2 && !p->upright) {
         int max_h = 0;
         if (cudaDeviceGetAttribute(&max_h, cudaDevAttrMaxTexture2DLinearHeight, ctx->device) != cudaSuccess) { cudaGetLastError(); max_h = 0; }
         int per = max_h >= rows ? max_h / rows : 0;
@@ -1825,7 +1828,10 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
             for (int c = 0; c < n_chunks && stacked; c++)
                 stacked = surf_stack_texture(ctx, c * per, std::min(per, batch - c * per), rows, cols, ws.pitch_f, st, &ts[c]);
             for (int c = 0; c < n_chunks && stacked; c++) {
-                LAUNCH_WK(2, work_counter + 4 + c, ts[c], c * per, std::min(per, batch - c * per));
+                const int nb = std::min(per, batch - c * per);
+                if (ctx->describe_mode == 2) LAUNCH_WK_(2, 2, 4, work_counter + 4 + c, ts[c], c * per, nb);
+                else if (ctx->describe_mode == 3) LAUNCH_WK_(2, 4, 4, work_counter + 4 + c, ts[c], c * per, nb);
+                else LAUNCH_WK_(2, 4, 3, work_counter + 4 + c, ts[c], c * per, nb);
                 LAUNCH_CHECK(ctx);
             }
         }
@@ -1836,6 +1842,7 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         LAUNCH_CHECK(ctx);
     }
 #undef LAUNCH_WK
+#undef LAUNCH_WK_
     orient_describe_kernel<<<ctx->num_sms * 2, DESC_THREADS, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
                                                                        ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(),
                                                                        ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, p->upright, work_counter + 1);

@@ -73,3 +73,123 @@ def test_flow_stitch_with_multiple_equals_reference(tmp_path, monkeypatch, fuse,
     assert len(out_ours) == len(out_ref)
     for a, b in zip(out_ours, out_ref):
         assert np.asarray(a).shape == np.asarray(b).shape and np.array_equal(a, b)
+
+
+def _fake_feature_api(cls, monkeypatch, script, log):
+    """Replace detect / match / vote on `cls` by deterministic fakes: features identify the image they came from, the vote
+    looks the (A, B) identity pair up in `script`."""
+    def key(image):
+        return (tuple(image.shape), int(np.asarray(image, np.int64).sum()), int(np.asarray(image, np.int64)[0, 0]))
+
+    def detect(self, image, featureMethod):
+        log.append(("detect", key(image)))
+        return ([key(image)], [key(image)])
+
+    def match(self, featuresA, featuresB):
+        return [(featuresA[0], featuresB[0])]
+
+    def vote(self, kpsA, kpsB, matches, offsetEvaluate=10):
+        st, off = script.get((kpsA[0], kpsB[0]), (False, [0, 0]))
+        return (st, list(off))
+    monkeypatch.setattr(cls, "detectAndDescribe", detect)
+    monkeypatch.setattr(cls, "matchDescriptors", match)
+    monkeypatch.setattr(cls, "getOffsetByMode", vote)
+    return key
+
+
+@pytest.mark.parametrize("direct_incre", [1, -1, 0])
+@pytest.mark.parametrize("roi_ratio", [0.2, 0.1, 0.3])
+def test_incremental_feature_search_equals_reference(monkeypatch, direct_incre, roi_ratio):
+    """calculateOffsetForFeatureSearchIncre (Stitcher.py:306-367): candidate order, ROI origin added back, carried direction."""
+    from oracle import reference_shims as rs
+    from imagestitch_b200.Stitcher import Stitcher
+    S, U, F = rs.import_reference()
+    rng = np.random.default_rng(1)
+    imgs = [rng.integers(0, 255, (60 + 4 * k, 90 - 3 * k)).astype(np.uint8) for k in range(6)]
+    ref, ours = S.Stitcher(), Stitcher()
+    for cls in (S.Stitcher, Stitcher):
+        monkeypatch.setattr(cls, "isPrintLog", False, raising=False)
+        monkeypatch.setattr(cls, "featureMethod", "sift", raising=False)       # ours: the staged (three-call) path
+        monkeypatch.setattr(cls, "offsetCaculate", "mode", raising=False)
+        monkeypatch.setattr(cls, "isEnhance", False, raising=False)
+        monkeypatch.setattr(cls, "roiRatio", roi_ratio, raising=False)
+        monkeypatch.setattr(cls, "directIncre", direct_incre, raising=False)
+        monkeypatch.setattr(cls, "direction", 1, raising=False)
+    max_i = int(np.floor(0.5 / roi_ratio) + 1) + 1
+    # which candidate (i, direction) succeeds for each pair; None = the pair fails everywhere
+    plan = [(1, 1), (2, 3), None, (1, 2), (max_i - 1, 4)]
+    script, log_r, log_o = {}, [], []
+    key = _fake_feature_api(S.Stitcher, monkeypatch, script, log_r)
+    _fake_feature_api(Stitcher, monkeypatch, script, log_o)
+    m = U.Method()
+    for p, want in enumerate(plan):
+        if want is None:
+            continue
+        i, d = want
+        a = m.getROIRegionForIncreMethod(imgs[p], direction=d, order="first", searchRatio=i * roi_ratio)
+        b = m.getROIRegionForIncreMethod(imgs[p + 1], direction=d, order="second", searchRatio=i * roi_ratio)
+        script[(key(a), key(b))] = (True, [3 + p, -2 - p])
+    for p in range(len(plan)):
+        r = ref.calculateOffsetForFeatureSearchIncre([imgs[p], imgs[p + 1]])
+        o = ours.calculateOffsetForFeatureSearchIncre([imgs[p], imgs[p + 1]])
+        assert r[0] == o[0] and (r[1] == o[1] or list(r[1]) == list(o[1])), (p, r, o)
+        assert ref.direction == ours.direction
+    assert log_r == log_o and len(log_r) > 10                 # same ROIs evaluated in the same order
+
+
+def test_full_frame_feature_cache_equals_reference(monkeypatch):
+    """calculateOffsetForFeatureSearch (Stitcher.py:260-304): B's features are cached for the next pair, a failure (or a new
+    sequence: isBreak) forces A to be detected again."""
+    from oracle import reference_shims as rs
+    from imagestitch_b200.Stitcher import Stitcher
+    S, U, F = rs.import_reference()
+    rng = np.random.default_rng(2)
+    imgs = [rng.integers(0, 255, (50, 70)).astype(np.uint8) for _ in range(7)]
+    script, log_r, log_o = {}, [], []
+    for cls in (S.Stitcher, Stitcher):
+        monkeypatch.setattr(cls, "isPrintLog", False, raising=False)
+        monkeypatch.setattr(cls, "featureMethod", "sift", raising=False)
+        monkeypatch.setattr(cls, "offsetCaculate", "mode", raising=False)
+        monkeypatch.setattr(cls, "isEnhance", False, raising=False)
+    key = _fake_feature_api(S.Stitcher, monkeypatch, script, log_r)
+    _fake_feature_api(Stitcher, monkeypatch, script, log_o)
+    ok_pairs = {0, 1, 3, 5}
+    for p in ok_pairs:
+        script[(key(imgs[p]), key(imgs[p + 1]))] = (True, [40 + p, 1 - p])
+    ref, ours = S.Stitcher(), Stitcher()
+    ref.tempImageFeature.isBreak = True
+    ours.tempImageFeature.isBreak = True
+    for p in range(6):
+        r = ref.calculateOffsetForFeatureSearch([imgs[p], imgs[p + 1]])
+        o = ours.calculateOffsetForFeatureSearch([imgs[p], imgs[p + 1]])
+        assert r[0] == o[0] and list(r[1]) == list(o[1]), (p, r, o)
+        assert ref.tempImageFeature.isBreak == ours.tempImageFeature.isBreak
+    assert log_r == log_o
+    assert [e[1] for e in log_r].count(key(imgs[1])) == 1     # cached: image 1 is detected once although it is in two pairs
+    assert [e[1] for e in log_r].count(key(imgs[3])) == 2     # pair 2 failed: image 3 is detected again as A of pair 3
+
+
+def test_phase_incremental_search_equals_reference(monkeypatch):
+    """calculateOffsetForPhaseCorrleateIncre (Stitcher.py:205-258) with the device call replaced by cv2.phaseCorrelate: same
+    candidates, same truncation, same threshold, same carried direction as the unmodified reference (quirk Q6 included)."""
+    import cv2
+    from oracle import reference_shims as rs
+    from imagestitch_b200 import gpu, synth
+    from imagestitch_b200.Stitcher import Stitcher
+    S, U, F = rs.import_reference()
+    monkeypatch.setattr(gpu, "phase_correlate", lambda a, b, device=0: cv2.phaseCorrelate(np.float64(a), np.float64(b)))
+    for cls in (S.Stitcher, Stitcher):
+        monkeypatch.setattr(cls, "isPrintLog", False, raising=False)
+        monkeypatch.setattr(cls, "roiRatio", 0.2, raising=False)
+        monkeypatch.setattr(cls, "directIncre", 1, raising=False)
+        monkeypatch.setattr(cls, "direction", 1, raising=False)
+    ref, ours = S.Stitcher(), Stitcher()
+    n_ok = 0
+    for seed, direction in ((1, 1), (2, 2), (3, 1), (4, 2)):
+        A, B, _ = synth.pair(seed=seed, size=256, overlap=60, direction=direction)
+        r = ref.calculateOffsetForPhaseCorrleateIncre([A, B])
+        o = ours.calculateOffsetForPhaseCorrleateIncre([A, B])
+        assert r[0] == o[0] and list(r[1]) == list(o[1]), (seed, r, o)
+        assert ref.direction == ours.direction
+        n_ok += int(bool(r[0]))
+    assert n_ok >= 2

@@ -22,6 +22,7 @@ import numpy as np
 from . import gpu
 from . import ImageFusion
 from . import ImageUtility as Utility
+from . import phase_wrap
 from . import sharding
 
 
@@ -145,6 +146,9 @@ class Stitcher(Utility.Method):
     directIncre = 1         # 1, 0 or -1
     fuseMethod = "notFuse"
     phaseResponseThreshold = 0.15
+    phaseMode = "reference"  # "reference": Stitcher.py:205-258 verbatim in behaviour (wrong by construction);
+                             # "wrapAware": corrected sign, aliases resolved by overlap ZNCC (phase_wrap.py)
+    phaseAcceptZncc = 0.5    # wrapAware: a candidate must correlate at least this well over the pixels the ROIs would share
     tempImageFeature = ImageFeature()
     imageFusion = ImageFusion.ImageFusion()
     batchPairs = 16         # pairs evaluated per fused device call in flowStitch
@@ -311,6 +315,9 @@ class Stitcher(Utility.Method):
         def evaluate(i, d):
             roiA = self.getROIRegionForIncreMethod(imageA, direction=d, order="first", searchRatio=i * self.roiRatio)
             roiB = self.getROIRegionForIncreMethod(imageB, direction=d, order="second", searchRatio=i * self.roiRatio)
+            if self.phaseMode == "wrapAware":
+                (status, offset, _, _) = phase_wrap.resolve(roiA, roiB, gpu.phase_correlate, gpu.overlap_sums, accept=self.phaseAcceptZncc)
+                return (status, offset)
             (shift, response) = gpu.phase_correlate(roiA, roiB)
             return (response > self.phaseResponseThreshold, [int(shift[1]), int(shift[0])])       # truncation, Stitcher.py:231-232
         return self._incre_search(images, evaluate)

@@ -17,6 +17,7 @@
 #include <cufft.h>
 #include <float.h>
 #include <map>
+#include <algorithm>
 
 struct PhasePlan { cufftHandle fwd = 0, inv = 0; size_t ws = 0; };
 struct PhaseState {
@@ -197,7 +198,74 @@ static int phase_run(vfsms_ctx *ctx, const uint8_t *a_dev, const uint8_t *b_dev,
     return 0;
 }
 
+// ---------------------------------------------------------------- overlap sums (wrap-aware phase mode)
+// For candidate shift k = (dRow, dCol): over the pixels with roiB(r, c) <-> roiA(r + dRow, c + dCol) inside both ROIs, the
+// integer sums n, Sa, Sb, Sab, Saa, Sbb.  grid (blocks, n_cand); each thread strides over the overlap rectangle, warp-shuffle
+// + shared-memory reduction, one 64-bit atomicAdd per sum and block: integers, so the result does not depend on the order.
+__global__ void __launch_bounds__(256) overlap_sums_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, int rows, int cols,
+                                                           int stride_a, int stride_b, const int32_t *__restrict__ shifts,
+                                                           unsigned long long *out)
+{
+    const int k = blockIdx.y;
+    const int dr = shifts[2 * k], dc = shifts[2 * k + 1];
+    const int r0 = max(0, -dr), r1 = min(rows, rows - dr), c0 = max(0, -dc), c1 = min(cols, cols - dc);
+    const long long h = r1 - r0, w = c1 - c0;
+    unsigned long long acc[6] = { 0, 0, 0, 0, 0, 0 };
+    if (h > 0 && w > 0) {
+        const long long total = h * w;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int r = r0 + (int)(i / w), c = c0 + (int)(i % w);
+            const unsigned pb = b[(size_t)r * stride_b + c];
+            const unsigned pa = a[(size_t)(r + dr) * stride_a + (c + dc)];
+            acc[0] += 1; acc[1] += pa; acc[2] += pb; acc[3] += pa * pb; acc[4] += pa * pa; acc[5] += pb * pb;
+        }
+    }
+    __shared__ unsigned long long s_part[8][6];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        unsigned long long v = acc[q];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_part[warp][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        unsigned long long v = 0;
+        for (int wv = 0; wv < 8; wv++) v += s_part[wv][threadIdx.x];
+        if (v) atomicAdd(&out[(size_t)k * 6 + threadIdx.x], v);
+    }
+}
+
 extern "C" {
+
+int vfsms_overlap_sums_host(vfsms_ctx *ctx, const uint8_t *roi_a, const uint8_t *roi_b, int rows, int cols, int stride_a, int stride_b,
+                            int n_shifts, const int32_t *shifts, int64_t *sums_out)
+{
+    if (!ctx || !roi_a || !roi_b || !shifts || !sums_out || rows < 1 || cols < 1 || stride_a < cols || stride_b < cols || n_shifts < 1 ||
+        n_shifts > 64) {
+        vfsms_set_error("overlap_sums: bad arguments"); return VFSMS_E_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    PhaseState *ps = pstate(ctx);
+    int rc;
+    if ((rc = ps->img_a.reserve((size_t)rows * cols))) return rc;
+    if ((rc = ps->img_b.reserve((size_t)rows * cols))) return rc;
+    if ((rc = ps->out.reserve(64 * 8 + 64 * 6 * 8))) return rc;
+    int32_t *d_shifts = (int32_t *)ps->out.p;                                      // [64][2]
+    unsigned long long *d_sums = (unsigned long long *)((char *)ps->out.p + 64 * 8);  // [64][6]
+    CUDA_TRY(cudaMemcpy2DAsync(ps->img_a.p, cols, roi_a, stride_a, cols, rows, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpy2DAsync(ps->img_b.p, cols, roi_b, stride_b, cols, rows, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_shifts, shifts, (size_t)n_shifts * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d_sums, 0, (size_t)n_shifts * 6 * 8, st));
+    const int blocks = std::max(1, std::min(ctx->num_sms * 2, (int)(((long long)rows * cols + 255) / 256)));
+    overlap_sums_kernel<<<dim3(blocks, n_shifts), 256, 0, st>>>(ps->img_a.as<uint8_t>(), ps->img_b.as<uint8_t>(), rows, cols, cols, cols,
+                                                                 d_shifts, d_sums);
+    LAUNCH_CHECK(ctx);
+    CUDA_TRY(cudaMemcpyAsync(sums_out, d_sums, (size_t)n_shifts * 6 * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
 
 int vfsms_phase_correlate_dev(vfsms_ctx *ctx, const uint8_t *roi_a_dev, const uint8_t *roi_b_dev, int rows, int cols, int stride,
                               double *out_dev, void *stream)

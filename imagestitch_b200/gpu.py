@@ -257,6 +257,21 @@ def phase_correlate(roi_a, roi_b, device=0):
     return (float(out[0]), float(out[1])), float(out[2])
 
 
+def overlap_sums(roi_a, roi_b, shifts, device=0):
+    """Integer sums (n, Sa, Sb, Sab, Saa, Sbb) over the pixels two ROIs share under each candidate shift (dRow, dCol) --
+    the scoring step of the wrap-aware phase mode (phase_wrap.resolve).  -> int64 [n, 6]."""
+    L = _lib.load()
+    ctx = _lib.context(device)
+    a, b = _as_u8_image(roi_a), _as_u8_image(roi_b)
+    if a.shape != b.shape:
+        raise ValueError("ROIs must have the same shape")
+    sh = np.ascontiguousarray(shifts, np.int32).reshape(-1, 2)
+    out = np.zeros((len(sh), 6), np.int64)
+    check(L.vfsms_overlap_sums_host(ctx, _vp(a), _vp(b), a.shape[0], a.shape[1], a.strides[0], b.strides[0], len(sh), _vp(sh), _vp(out)),
+          "vfsms_overlap_sums_host")
+    return out
+
+
 def orb_detect_and_describe(image, n_features=5000, scale_factor=1.2, n_levels=8, edge_threshold=31, first_level=0, wta_k=2,
                             patch_size=31, fast_threshold=20, device=0):
     """-> (kp [N, 8] float32, desc [N, 32] float32 holding byte values) -- appendix/myGpuFeatures.cpp:106-146."""

@@ -181,6 +181,13 @@ int vfsms_phase_correlate_host(vfsms_ctx *ctx, const uint8_t *roi_a, const uint8
 int vfsms_phase_correlate_dev(vfsms_ctx *ctx, const uint8_t *roi_a_dev, const uint8_t *roi_b_dev, int rows, int cols,
                               int stride, double *out_dev, void *stream);
 
+/* Scoring step of the opt-in wrap-aware phase mode (imagestitch_b200/phase_wrap.py -- the reference has no
+ * such check, its phase path Stitcher.py:205-258 adds the shift with the wrong sign and ignores aliasing, quirk Q6).
+ * For each candidate shift (dRow, dCol) with roiB(r, c) <-> roiA(r + dRow, c + dCol): the integer sums n, Sa, Sb, Sab, Saa, Sbb over
+ * the pixels both ROIs share.  shifts: n_shifts x 2 int32 (n_shifts <= 64), sums_out: n_shifts x 6 int64.  Exact integers. */
+int vfsms_overlap_sums_host(vfsms_ctx *ctx, const uint8_t *roi_a, const uint8_t *roi_b, int rows, int cols, int stride_a, int stride_b,
+                            int n_shifts, const int32_t *shifts, int64_t *sums_out);
+
 /* ---------------------------------------------------------------- overlap blending */
 
 enum {

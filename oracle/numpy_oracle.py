@@ -58,3 +58,21 @@ def roi_for_incre(image, direction, order, ratio):
     n = int(np.floor(col * ratio))
     right = (direction == 2) == (order == "first")
     return image[:, col - n:col] if right else image[:, 0:n]
+
+
+def overlap_sums(a, b, shifts):
+    """Integer sums over the pixels two equally sized ROIs share under roiB(r, c) = roiA(r + dRow, c + dCol), per candidate
+    shift: (n, Sa, Sb, Sab, Saa, Sbb).  Oracle of vfsms_overlap_sums_host (the scoring step of the wrap-aware phase mode,
+    imagestitch_b200/phase_wrap.py; not part of the reference, which has no such check)."""
+    a = np.asarray(a, np.int64); b = np.asarray(b, np.int64)
+    rows, cols = a.shape
+    out = np.zeros((len(shifts), 6), np.int64)
+    for k, (dr, dc) in enumerate(shifts):
+        r0, r1 = max(0, -dr), min(rows, rows - dr)
+        c0, c1 = max(0, -dc), min(cols, cols - dc)
+        if r1 <= r0 or c1 <= c0:
+            continue
+        pb = b[r0:r1, c0:c1]
+        pa = a[r0 + dr:r1 + dr, c0 + dc:c1 + dc]
+        out[k] = (pa.size, pa.sum(), pb.sum(), (pa * pb).sum(), (pa * pa).sum(), (pb * pb).sum())
+    return out

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One-call evidence capture for a round (run on the GPU box):
-#   gpurun --timeout 1500 -- 'bash profiles/capture.sh r02'
+#   gpurun --timeout 2400 -- 'bash profiles/capture.sh r02'
 # Writes everything under gpurun_out/<tag>_*; copy what should be judged into profiles/<tag>/ afterwards
 # (profiles/summarize_launches.py for the launch list, profiles/hot_lines.py for the source page).
 # Numbers printed by runs under ncu are never bench values.
@@ -9,6 +9,8 @@ TAG=${1:-rXX}
 OUT=gpurun_out
 mkdir -p $OUT
 KERNELS='integral|hessian|response_|rank_|bin_|validate|prefix_kernel|u8_to_f32|orient_|prep_split|match_tc|rescore|norm_max|fallback|ratio_insert|vote_|transpose|jpeg'
+# 0. the whole GPU suite (includes the band-mosaic and wrap-aware phase tests that were written without a GPU)
+timeout -s KILL 900 python -m pytest tests -q -m gpu > $OUT/${TAG}_gpu_tests.log 2>&1
 # 1. opt-in kernel variants vs the default schedule (identical results required), then the default GPU suite stays as it was
 VFSMS_EXPERIMENTAL=1 timeout -s KILL 600 python -m pytest tests/test_gpu_variants.py -x -q > $OUT/${TAG}_variants_tests.log 2>&1
 # 2. the bench as the driver runs it (autotune probe picks the validated variants), the default schedule, and each variant alone
@@ -18,6 +20,7 @@ for V in describe=2 sort=1 lpt=1; do
     timeout -s KILL 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --opt $V > $OUT/${TAG}_bench_${V/=/}.json 2> $OUT/${TAG}_bench_${V/=/}.err
 done
 timeout -s KILL 300 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err
+timeout -s KILL 300 python scripts/bench_mosaic.py --rows 4 --cols 6 > $OUT/${TAG}_bench_mosaic.json 2> $OUT/${TAG}_bench_mosaic.err
 # 3. ncu on the configuration the bench selected (explicit --opt, no probe subprocess under the profiler)
 OPTS=$(python - <<PY
 import json

@@ -9,15 +9,46 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# VFSMS_EMU=1 (set only by tests/test_kernels_emulated_cpu.py for its pytest subprocess): the `gpu` tests of this directory
+# run against tests/cuda_emu/_build/libvfsms_emu.so -- the same .cu sources compiled by g++ on a CUDA-on-CPU execution model.
+# Test infrastructure only: the product (imagestitch_b200._lib) knows nothing about it and still fails without libvfsms.so.
+EMU = os.environ.get("VFSMS_EMU") == "1"
+if EMU:
+    sys.path.insert(0, os.path.join(ROOT, "tests", "cuda_emu"))
+    import build_emu
+    from imagestitch_b200 import _lib as _vfsms_lib
+    _vfsms_lib.SO_PATH = build_emu.build()
+    _real_context = _vfsms_lib.context
+
+    def _emu_context(device=0):
+        fresh = device not in _vfsms_lib._contexts
+        h = _real_context(device)
+        if fresh:       # match_tc.cu (tcgen05 inline PTX) is not emulated: the exact SIMT matcher, whatever a test selects
+            L = _vfsms_lib.load()
+            set_matcher = L.vfsms_set_matcher
+            if not getattr(set_matcher, "_emu", False):
+                wrapper = lambda ctx, mode: set_matcher(ctx, 1)
+                wrapper._emu = True
+                L.vfsms_set_matcher = wrapper
+            set_matcher(h, 1)
+        return h
+    _vfsms_lib.context = _emu_context
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
 
 
+# under emulation: no tcgen05 / TMA (inline PTX), no torch CUDA tensors, and the full-size cases would take hours
+_EMU_SKIP = ("test_gpu_match_tc.py", "test_gpu_fullsize.py", "test_decode_into_device_tile_stack")
+
+
 def pytest_collection_modifyitems(config, items):
     ref = os.path.isdir("/root/reference")
     for it in items:
+        if EMU and any(s in it.nodeid for s in _EMU_SKIP):
+            it.add_marker(pytest.mark.skip(reason="not covered by the CUDA-on-CPU emulation"))
         if "reference" in it.keywords and not ref:
             it.add_marker(pytest.mark.skip(reason="/root/reference not present on this box"))
 

@@ -34,7 +34,7 @@ def test_wrap_aware_mode_recovers_true_offsets(gpu):
     Stitcher.isPrintLog = False
     try:
         Stitcher.phaseMode = "wrapAware"; Stitcher.roiRatio = 0.2; Stitcher.direction = 1; Stitcher.directIncre = 1
-        for seed, direction, overlap in ((5, 1, 40), (6, 2, 70), (7, 1, 90), (8, 2, 30)):
+        for seed, direction, overlap in ((5, 1, 40), (6, 2, 70), (7, 1, 90), (8, 2, 50)):
             A, B, off = synth.pair(seed=seed, size=512, overlap=overlap, direction=direction)
             status, offset = st.calculateOffsetForPhaseCorrleateIncre([A, B])
             assert status and abs(offset[0] - off[0]) <= 1 and abs(offset[1] - off[1]) <= 1, (offset, off)

@@ -1,0 +1,80 @@
+"""CPU: the CUDA kernels themselves, executed without a GPU.
+
+tests/cuda_emu/ compiles the product's .cu sources (imagestitch_b200/csrc, minus the tcgen05 matcher) with g++ on a small
+CUDA-on-CPU execution model (fibers per thread, lock-step warp collectives, block barriers, textures, a DFT in place of
+cuFFT).  The `gpu`-marked parity tests of this directory then run in a subprocess against that library (VFSMS_EMU=1, see
+conftest.py): same C ABI, same host code, same oracle comparisons.  This checks kernel LOGIC -- indexing, reductions, work
+distribution, exact arithmetic order -- in every CPU run, including the code written while no GPU was available (kernel
+variants behind vfsms_set_option, vfsms_mosaic_band_host, vfsms_overlap_sums_host).  It says nothing about timing, memory-model
+races or the tensor-core path; the real `-m gpu` run on the B200 remains the parity gate.
+
+Default selection: about 1.5 minutes.  VFSMS_EMU_FULL=1 runs every gpu test the emulation covers (about 10 minutes).
+"""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "cuda_emu")
+
+pytestmark = pytest.mark.skipif(os.environ.get("VFSMS_EMU") == "1", reason="already inside the emulated run")
+
+# (selection, -k expression, minimum number of tests that must have passed)
+FAST = [
+    (["tests/test_gpu_blend.py", "tests/test_gpu_zz_bands.py", "tests/test_gpu_phase.py", "tests/test_gpu_orb.py"], None, 20),
+    (["tests/test_gpu_jpeg.py"], "not full_size", 30),
+    (["tests/test_gpu_surf.py"], "not real_micrograph", 9),
+    (["tests/test_gpu_zz_phase_wrap.py", "tests/test_gpu_variants.py"], "overlap_sums or sort_per_image or large_windows_first or borders_and_giants", 4),
+]
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    sys.path.insert(0, EMU_DIR)
+    try:
+        import build_emu
+        return build_emu.build()
+    finally:
+        sys.path.remove(EMU_DIR)
+
+
+def _run(selection, kexpr, extra_env=None):
+    env = dict(os.environ, VFSMS_EMU="1", VFSMS_EXPERIMENTAL="1", PYTHONPATH=ROOT)
+    env.update(extra_env or {})
+    cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + selection
+    if kexpr:
+        cmd += ["-k", kexpr]
+    p = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=3000)
+    out = p.stdout.decode()
+    m = re.search(r"(\d+) passed", out)
+    return p.returncode, int(m.group(1)) if m else 0, out
+
+
+def test_emulated_library_exports_the_c_abi(emu_lib):
+    """the emulated build links without libcudart / libcufft and exports every symbol of include/vfsms.h"""
+    from imagestitch_b200 import _lib
+    L = ctypes.CDLL(emu_lib)
+    for name in _lib.EXPORTS:
+        getattr(L, name)
+    ldd = subprocess.run(["ldd", emu_lib], stdout=subprocess.PIPE).stdout.decode()
+    assert "libcudart" not in ldd and "libcufft" not in ldd and "libcuda" not in ldd
+    assert _lib.SO_PATH.endswith(os.path.join("imagestitch_b200", "libvfsms.so")), "the product must never point at the emulation"
+
+
+@pytest.mark.parametrize("case", range(len(FAST)))
+def test_gpu_parity_tests_on_emulated_kernels(emu_lib, case):
+    selection, kexpr, at_least = FAST[case]
+    rc, passed, out = _run(selection, kexpr)
+    assert rc == 0, out[-6000:]
+    assert passed >= at_least, out[-2000:]
+
+
+@pytest.mark.skipif(os.environ.get("VFSMS_EMU_FULL") != "1", reason="set VFSMS_EMU_FULL=1 (about 10 minutes)")
+def test_all_emulable_gpu_tests(emu_lib):
+    rc, passed, out = _run(["tests"], None)
+    assert rc == 0, out[-6000:]
+    assert passed >= 100, out[-2000:]

@@ -16,13 +16,17 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "imagestitch_b200", "csrc")
-OUT_DIR = os.path.join(HERE, "_build")
+# VFSMS_EMU_SANITIZE=1: AddressSanitizer build in its own directory (run python with LD_PRELOAD=$(g++ -print-file-name=libasan.so))
+SANITIZE = os.environ.get("VFSMS_EMU_SANITIZE") == "1"
+OUT_DIR = os.path.join(HERE, "_build", "asan") if SANITIZE else os.path.join(HERE, "_build")
 OUT = os.path.join(OUT_DIR, "libvfsms_emu.so")
 UNITS = ["surf.cu", "match.cu", "phase.cu", "blend.cu", "orb.cu", "enhance.cu", "jpeg.cu", "capi.cu"]
-CXX = os.environ.get("CXX", "g++")
+CXX = os.environ.get("VFSMS_EMU_CXX") or ("/usr/bin/g++" if SANITIZE and os.path.exists("/usr/bin/g++") else os.environ.get("CXX", "g++"))
 # -ffp-contract=off mirrors nvcc -fmad=false (parity with oracle/ depends on unfused arithmetic)
 FLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-w", "-pthread",
          "-I/usr/local/cuda/include", "-I" + CSRC, "-include", os.path.join(HERE, "emu.h")]
+if SANITIZE:
+    FLAGS += ["-fsanitize=address", "-fno-omit-frame-pointer"]
 
 
 def _match_back(text, pos):
@@ -133,7 +137,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode()[-20000:])
             raise RuntimeError("g++ failed on %s (emulated build)" % unit)
     if force or jobs or _stale(OUT, objs):
-        cmd = [CXX, "-shared", "-o", OUT] + objs + ["-pthread", "-Wl,--no-undefined"]
+        cmd = [CXX, "-shared", "-o", OUT] + objs + ["-pthread"] + (["-fsanitize=address"] if SANITIZE else ["-Wl,--no-undefined"])
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

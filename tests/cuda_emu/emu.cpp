@@ -39,10 +39,22 @@ emu_switch:
 .size emu_switch,.-emu_switch
 )");
 
+// AddressSanitizer build (VFSMS_EMU_SANITIZE=1 in build_emu.py): device memory is malloc'ed and __shared__ arrays are statics, so
+// out-of-bounds global / shared accesses of a kernel are reported like compute-sanitizer's memcheck would.  ASan has to be told
+// about the stack switches.
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/common_interface_defs.h>
+#define EMU_ASAN 1
+#else
+#define EMU_ASAN 0
+#endif
+
 namespace emu {
 
 enum { RUN = 0, AT_BLOCK = 1, AT_WARP = 2, DONE = 3 };
-struct Fiber { void *sp; int state; uint3 tid; uint64_t slot; };
+struct Fiber { void *sp; int state; uint3 tid; uint64_t slot; void *fake; };
+static const void *sched_bottom = nullptr;
+static size_t sched_size = 0;
 
 static const size_t STACK_BYTES = 512 << 10;
 static const int MAX_THREADS = 1024;
@@ -56,9 +68,15 @@ static const size_t DYN_SMEM_BYTES = 256 << 10;
 
 static void fiber_main()
 {
+#if EMU_ASAN
+    __sanitizer_finish_switch_fiber(nullptr, &sched_bottom, &sched_size);
+#endif
     (*cur_body)();
     fibers[cur].state = DONE;
     void *dummy;
+#if EMU_ASAN
+    __sanitizer_start_switch_fiber(nullptr, sched_bottom, sched_size);      // nullptr: this fiber's stack is abandoned
+#endif
     emu_switch(&dummy, sched_sp);
     abort();
 }
@@ -76,7 +94,13 @@ static void yield(int state)
 {
     Fiber &f = fibers[cur];
     f.state = state;
+#if EMU_ASAN
+    __sanitizer_start_switch_fiber(&f.fake, sched_bottom, sched_size);
+#endif
     emu_switch(&f.sp, sched_sp);
+#if EMU_ASAN
+    __sanitizer_finish_switch_fiber(f.fake, &sched_bottom, &sched_size);
+#endif
 }
 
 void block_barrier() { yield(AT_BLOCK); }
@@ -85,11 +109,23 @@ int lane_id() { return cur & 31; }
 uint64_t &slot_of_lane(int lane) { return fibers[(cur & ~31) + lane].slot; }
 bool lane_alive(int lane) { const int t = (cur & ~31) + lane; return t < n_threads && fibers[t].state != DONE; }
 
+// VFSMS_EMU_ORDER=reverse: warps and lanes are scheduled last-to-first (and CTAs of a grid last-to-first).  Results that depend
+// on the order in which threads run between two barriers -- a missing __syncthreads / __syncwarp, an atomic arrival order that
+// leaks into the output -- differ between the two schedules.
+static bool reverse_order = false;
+
 static void run_fiber(int t)
 {
     cur = t;
     threadIdx = fibers[t].tid;
+#if EMU_ASAN
+    void *fake = nullptr;
+    __sanitizer_start_switch_fiber(&fake, stacks + (size_t)t * STACK_BYTES + 4096, STACK_BYTES - 4096);
+#endif
     emu_switch(&sched_sp, fibers[t].sp);
+#if EMU_ASAN
+    __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
+#endif
     cur = -1;
 }
 
@@ -115,12 +151,15 @@ static void run_block(const std::function<void()> &body)
     int live = n_threads;
     while (live > 0) {
         bool progressed = false;
-        for (int w = 0; w < n_warps; w++) {
+        for (int wi = 0; wi < n_warps; wi++) {
+            const int w = reverse_order ? n_warps - 1 - wi : wi;
             const int t0 = w * 32, t1 = t0 + 32 < n_threads ? t0 + 32 : n_threads;
             for (;;) {   // a warp runs until all of its lanes wait at a block barrier or have finished
                 bool ran = false;
-                for (int t = t0; t < t1; t++)
+                for (int ti = t0; ti < t1; ti++) {
+                    const int t = reverse_order ? t1 - 1 - (ti - t0) : ti;
                     if (fibers[t].state == RUN) { run_fiber(t); ran = true; if (fibers[t].state == DONE) live--; }
+                }
                 int at_warp = 0, alive = 0;
                 for (int t = t0; t < t1; t++) { alive += fibers[t].state != DONE; at_warp += fibers[t].state == AT_WARP; }
                 if (at_warp && at_warp == alive) { for (int t = t0; t < t1; t++) if (fibers[t].state == AT_WARP) fibers[t].state = RUN; ran = true; }
@@ -144,13 +183,17 @@ static cudaError_t last_error = cudaSuccess;
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body)
 {
     init_once();
+    const char *order = getenv("VFSMS_EMU_ORDER");
+    reverse_order = order && !strcmp(order, "reverse");
     if (smem > DYN_SMEM_BYTES) { fprintf(stderr, "emu: %zu B of dynamic shared memory\n", smem); last_error = cudaErrorInvalidValue; return; }
     gridDim = grid;
     blockDim = block;
     for (unsigned z = 0; z < grid.z; z++)
         for (unsigned y = 0; y < grid.y; y++)
             for (unsigned x = 0; x < grid.x; x++) {
-                blockIdx.x = x; blockIdx.y = y; blockIdx.z = z;
+                blockIdx.x = reverse_order ? grid.x - 1 - x : x;
+                blockIdx.y = reverse_order ? grid.y - 1 - y : y;
+                blockIdx.z = reverse_order ? grid.z - 1 - z : z;
                 run_block(body);
             }
 }

@@ -51,6 +51,23 @@ def _imread(path, flag):
     return cv2.imdecode(np.fromfile(path, dtype=np.uint8), flag)
 
 
+def _imwrite(path, image, encoder="b200"):
+    """cv2.imwrite(path, image) (Stitcher.py:130-131, :196-197).  .jpg / .jpeg outputs are encoded by the library on the device --
+    the file is byte-identical to cv2's (quality 95, 4:2:0, Annex-K tables); every other format, or encoder "cv2", goes through cv2."""
+    img = np.asarray(image)
+    ext = os.path.splitext(path)[1].lower()
+    if encoder == "b200" and ext in (".jpg", ".jpeg") and img.dtype == np.uint8 and img.size > 0 \
+            and (img.ndim == 2 or (img.ndim == 3 and img.shape[2] == 3)) and max(img.shape[:2]) <= 65535:
+        data = gpu.jpeg_encode(img)
+        try:
+            with open(path, "wb") as f:
+                f.write(data)
+        except OSError:
+            return False                      # cv2.imwrite reports an unwritable path by returning False
+        return True
+    return cv2.imwrite(path, image)
+
+
 def _imread_gray_many(paths, decoder="b200"):
     """Grayscale decode of a tile sequence (Stitcher.py:68-69 decodes them one by one, twice).  JPEG files go through the
     library in batches -- host cores do the entropy decoding of many files at once, the device the IDCT; the pixels are
@@ -153,6 +170,7 @@ class Stitcher(Utility.Method):
     imageFusion = ImageFusion.ImageFusion()
     batchPairs = 16         # pairs evaluated per fused device call in flowStitch
     decoder = "b200"        # "b200": JPEG tiles decoded by the library (bit-identical to cv2); "cv2": cv2.imdecode
+    encoder = "b200"        # "b200": .jpg results encoded by the library (file byte-identical to cv2.imwrite's); "cv2": cv2.imwrite
 
     # ------------------------------------------------------------------ direction bookkeeping
     def directionIncrease(self, direction):
@@ -240,7 +258,7 @@ class Stitcher(Utility.Method):
             Stitcher.outputAddress = outputAddress
             (status, result) = self.flowStitch(fileList, caculateOffsetMethod)
             self.tempImageFeature.isBreak = True
-            cv2.imwrite(os.path.join(outputAddress, "stitching_result_" + str(i) + "." + outputfileExtension), result)
+            _imwrite(os.path.join(outputAddress, "stitching_result_" + str(i) + "." + outputfileExtension), result, self.encoder)
             if status[0] == False:
                 self.printAndWrite("stitching Failed")
 
@@ -257,10 +275,10 @@ class Stitcher(Utility.Method):
             result = self.flowStitchWithMutiple(fileList, caculateOffsetMethod)
             self.tempImageFeature.isBreak = True
             if len(result) == 1:
-                cv2.imwrite(os.path.join(outputAddress, "stitching_result_" + str(i) + "." + outputfileExtension), result[0])
+                _imwrite(os.path.join(outputAddress, "stitching_result_" + str(i) + "." + outputfileExtension), result[0], self.encoder)
             else:
                 for j in range(0, len(result)):
-                    cv2.imwrite(os.path.join(outputAddress, "stitching_result_" + str(i) + "_" + str(j + 1) + "." + outputfileExtension), result[j])
+                    _imwrite(os.path.join(outputAddress, "stitching_result_" + str(i) + "_" + str(j + 1) + "." + outputfileExtension), result[j], self.encoder)
             endTime = time.time()
             print("Time Consuming for " + fileAddress + " is " + str(endTime - startTime))
 

@@ -37,7 +37,7 @@ EXPORTS = [
     "vfsms_jpeg_component_coefficients", "vfsms_jpeg_decode_bgr_dev", "vfsms_jpeg_decode_bgr_host",
     "vfsms_tiles_reserve", "vfsms_tiles_decode_jpeg", "vfsms_tiles_upload", "vfsms_tiles_download", "vfsms_tiles_ptr",
     "vfsms_tiles_align", "vfsms_tiles_mosaic", "vfsms_set_option", "vfsms_get_option", "vfsms_option_name",
-    "vfsms_mosaic_band_host", "vfsms_overlap_sums_host",
+    "vfsms_mosaic_band_host", "vfsms_overlap_sums_host", "vfsms_jpeg_encode_host", "vfsms_jpeg_encode_dev",
 ]
 STAGE_COUNT = 12
 
@@ -84,6 +84,8 @@ def load():
     L.vfsms_mosaic_host.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp]
     L.vfsms_mosaic_band_host.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     L.vfsms_overlap_sums_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
+    L.vfsms_jpeg_encode_host.argtypes = [vp, vp, i32, i32, i32, i64, i32, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    L.vfsms_jpeg_encode_dev.argtypes = [vp, vp, i32, i32, i32, i64, i32, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), vp]
     L.vfsms_set_matcher.argtypes = [vp, i32]
     L.vfsms_last_match_fallbacks.argtypes = [vp, ctypes.POINTER(i32)]
     L.vfsms_set_option.argtypes = [vp, i32, i32]

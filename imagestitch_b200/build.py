@@ -19,6 +19,7 @@ UNITS = {
     "orb.cu": ["-fmad=false"],
     "enhance.cu": ["-fmad=false"],
     "jpeg.cu": [],
+    "jpeg_enc.cu": [],
     "capi.cu": [],
 }
 LIBS = ["-lcufft"]

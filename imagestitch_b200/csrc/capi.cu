@@ -18,6 +18,7 @@ void vfsms_set_error(const char *fmt, ...)
 void phase_state_destroy(vfsms_ctx *ctx);
 void blend_state_destroy(vfsms_ctx *ctx);
 void orb_state_destroy(vfsms_ctx *ctx);
+void jpeg_enc_state_destroy(vfsms_ctx *ctx);
 
 cudaEvent_t prof_event(vfsms_ctx *ctx)
 {
@@ -160,6 +161,7 @@ void vfsms_destroy(vfsms_ctx *ctx)
     phase_state_destroy(ctx);
     blend_state_destroy(ctx);
     orb_state_destroy(ctx);
+    jpeg_enc_state_destroy(ctx);
     surf_tex_destroy(ctx);
     ctx->tex_dev.release();
     SurfWorkspace &w = ctx->surf;

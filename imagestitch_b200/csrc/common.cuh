@@ -160,6 +160,7 @@ struct vfsms_ctx {
     void *phase_state = nullptr;   // cuFFT plans etc. (phase.cu)
     void *blend_state = nullptr;
     void *orb_state = nullptr;
+    void *jpeg_enc_state = nullptr;   // coefficient / bit-stream workspaces of the JPEG encoder (jpeg_enc.cu)
 };
 
 // stage timing: events on the launching stream; no-ops unless vfsms_profile_enable(ctx, 1)

@@ -445,6 +445,50 @@ def jpeg_decode_bgr(datas, device=0):
     return out[0] if single else out
 
 
+def jpeg_encode(image, quality=95, device=0):
+    """cv2.imencode(".jpg", image, [cv2.IMWRITE_JPEG_QUALITY, quality]) on the device -> bytes, identical to cv2's (baseline
+    JPEG, Annex-K Huffman tables, 4:2:0 for BGR).  image: u8 [rows, cols] or [rows, cols, 3] (BGR), rows / cols <= 65535."""
+    img = np.asarray(image)
+    if img.dtype != np.uint8 or not (img.ndim == 2 or (img.ndim == 3 and img.shape[2] == 3)):
+        raise TypeError("expected a uint8 image [rows, cols] or [rows, cols, 3], got %s %s" % (img.dtype, img.shape))
+    channels = 1 if img.ndim == 2 else 3
+    if img.strides[-1] != 1 or (channels == 3 and img.strides[1] != 3) or img.strides[0] < img.shape[1] * channels:
+        img = np.ascontiguousarray(img)
+    rows, cols = img.shape[:2]
+    L, ctx = _lib.load(), _lib.context(device)
+    cap = rows * cols * channels // 2 + (64 << 10)
+    size = ctypes.c_size_t(0)
+    while True:
+        out = np.empty(cap, np.uint8)
+        rc = L.vfsms_jpeg_encode_host(ctx, _vp(img), rows, cols, channels, ctypes.c_int64(img.strides[0]), int(quality), _vp(out), cap,
+                                      ctypes.byref(size))
+        if rc == _lib.VFSMS_E_CAPACITY and size.value > cap:
+            cap = size.value
+            continue
+        check(rc, "vfsms_jpeg_encode_host")
+        return out[:size.value].tobytes()
+
+
+def jpeg_encode_dev(image, quality=95, device=0, stream=None):
+    """jpeg_encode of a torch.uint8 CUDA tensor [rows, cols] or [rows, cols, 3] (BGR) that stays in HBM; returns the file's bytes."""
+    assert image.is_cuda and image.dim() in (2, 3) and image.stride(-1) == 1
+    channels = 1 if image.dim() == 2 else 3
+    assert channels == 1 or (image.shape[2] == 3 and image.stride(1) == 3)
+    rows, cols = int(image.shape[0]), int(image.shape[1])
+    L, ctx = _lib.load(), _lib.context(device)
+    cap = rows * cols * channels // 2 + (64 << 10)
+    size = ctypes.c_size_t(0)
+    while True:
+        out = np.empty(cap, np.uint8)
+        rc = L.vfsms_jpeg_encode_dev(ctx, ctypes.c_void_p(image.data_ptr()), rows, cols, channels, ctypes.c_int64(image.stride(0)), int(quality),
+                                     _vp(out), cap, ctypes.byref(size), ctypes.c_void_p(stream.cuda_stream if stream is not None else 0))
+        if rc == _lib.VFSMS_E_CAPACITY and size.value > cap:
+            cap = size.value
+            continue
+        check(rc, "vfsms_jpeg_encode_dev")
+        return out[:size.value].tobytes()
+
+
 def jpeg_decode_gray_dev(datas, out, device=0, stream=None):
     """Decode into a device-resident tile stack: `out` is a torch.uint8 CUDA tensor [n, rows, cols] (any row / image stride)."""
     rows, cols, _ = jpeg_info(datas[0])

@@ -262,6 +262,19 @@ int vfsms_jpeg_decode_bgr_dev(vfsms_ctx *ctx, int n_images, const uint8_t *const
 int vfsms_jpeg_decode_bgr_host(vfsms_ctx *ctx, int n_images, const uint8_t *const *data, const size_t *sizes,
                                uint8_t *out, int rows, int cols);
 
+/* ---------------------------------------------------------------- JPEG output encode
+ * Replace `cv2.imwrite(outputAddress + ..., stitchImage)` for .jpg outputs (Stitcher.py:130-131, :196-197): baseline JPEG with
+ * cv2's defaults (libjpeg quality 95 unless given, Annex-K Huffman tables, 4:2:0 for 3-channel BGR input, JFIF 1.01 header), colour
+ * conversion / downsampling / integer DCT / quantisation / Huffman coding / byte stuffing all on the device; the bytes are
+ * IDENTICAL to cv2.imencode(".jpg", img, [IMWRITE_JPEG_QUALITY, quality]).  channels: 1 (gray) or 3 (BGR interleaved);
+ * rows, cols <= 65535.  *out_size = size of the file in bytes, also when the call returns VFSMS_E_CAPACITY because
+ * out_capacity is smaller (call again with a larger buffer; out may be NULL to query). */
+int vfsms_jpeg_encode_host(vfsms_ctx *ctx, const uint8_t *img, int rows, int cols, int channels, int64_t row_stride, int quality,
+                           uint8_t *out, size_t out_capacity, size_t *out_size);
+/* Same with the image in device memory (e.g. a mosaic canvas that never left HBM); only the compressed bytes cross PCIe. */
+int vfsms_jpeg_encode_dev(vfsms_ctx *ctx, const uint8_t *img_dev, int rows, int cols, int channels, int64_t row_stride, int quality,
+                          uint8_t *out, size_t out_capacity, size_t *out_size, void *stream);
+
 /* ---------------------------------------------------------------- device-resident tile stack
  * The reference decodes every tile two or three times and ships ROIs to the plugin per call (Stitcher.py:68-69, 382, 401;
  * appendix/myGpuFeatures.cpp:70).  Here the gray tiles of a sequence (all rows x cols) are decoded / uploaded ONCE into a

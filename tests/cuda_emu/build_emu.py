@@ -20,7 +20,7 @@ CSRC = os.path.join(ROOT, "imagestitch_b200", "csrc")
 SANITIZE = os.environ.get("VFSMS_EMU_SANITIZE") == "1"
 OUT_DIR = os.path.join(HERE, "_build", "asan") if SANITIZE else os.path.join(HERE, "_build")
 OUT = os.path.join(OUT_DIR, "libvfsms_emu.so")
-UNITS = ["surf.cu", "match.cu", "phase.cu", "blend.cu", "orb.cu", "enhance.cu", "jpeg.cu", "capi.cu"]
+UNITS = ["surf.cu", "match.cu", "phase.cu", "blend.cu", "orb.cu", "enhance.cu", "jpeg.cu", "jpeg_enc.cu", "capi.cu"]
 CXX = os.environ.get("VFSMS_EMU_CXX") or ("/usr/bin/g++" if SANITIZE and os.path.exists("/usr/bin/g++") else os.environ.get("CXX", "g++"))
 # -ffp-contract=off mirrors nvcc -fmad=false (parity with oracle/ depends on unfused arithmetic)
 FLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-w", "-pthread",

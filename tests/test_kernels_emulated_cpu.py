@@ -26,7 +26,7 @@ pytestmark = pytest.mark.skipif(os.environ.get("VFSMS_EMU") == "1", reason="alre
 # (selection, -k expression, minimum number of tests that must have passed)
 FAST = [
     (["tests/test_gpu_blend.py", "tests/test_gpu_zz_bands.py", "tests/test_gpu_phase.py", "tests/test_gpu_orb.py"], None, 20),
-    (["tests/test_gpu_jpeg.py"], "not full_size", 30),
+    (["tests/test_gpu_jpeg.py", "tests/test_gpu_jpeg_encode.py"], "not full_size", 35),
     (["tests/test_gpu_surf.py"], "not real_micrograph", 9),
     (["tests/test_gpu_zz_phase_wrap.py", "tests/test_gpu_variants.py"], "overlap_sums or sort_per_image or large_windows_first or borders_and_giants", 4),
 ]

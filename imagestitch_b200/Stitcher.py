@@ -121,10 +121,12 @@ def _imread_color_many(paths, decoder="b200"):
     return images
 
 
-def _load_sequence(paths, decoder="b200", keep_on_device=True):
+def _load_sequence(paths, decoder="b200", keep_on_device=True, color=False):
     """Decode a tile sequence ONCE.  -> (host gray images, on_device).  With decoder "b200" and equally sized tiles the
     tiles also stay in the library's device-resident stack (slot k = paths[k]): JPEG files are decoded straight into it,
-    the rest is decoded by cv2 and uploaded; the host copies are then a download of the stack."""
+    the rest is decoded by cv2 and uploaded; the host copies are then a download of the stack.  color: the colour twin of the
+    stack is filled as well -- JPEG files by the SAME entropy-decoding pass that yields the gray tile (the reference decodes each
+    file in gray at Stitcher.py:68-69 and again in colour at :382 / :401)."""
     if decoder != "b200" or not keep_on_device:
         return _imread_gray_many(paths, decoder), False
     datas = [np.fromfile(p, dtype=np.uint8) for p in paths]
@@ -149,9 +151,11 @@ def _load_sequence(paths, decoder="b200", keep_on_device=True):
         while e < n and jpeg_ok[e] == jpeg_ok[k]:
             e += 1
         if jpeg_ok[k]:
-            gpu.tiles_decode_jpeg(k, [datas[j] for j in range(k, e)])
+            (gpu.tiles_decode_jpeg_bgr if color else gpu.tiles_decode_jpeg)(k, [datas[j] for j in range(k, e)])
         else:
             gpu.tiles_upload(k, np.stack([others[j] for j in range(k, e)]))
+            if color:
+                gpu.tiles_upload_bgr(k, np.stack([cv2.imdecode(datas[j], cv2.IMREAD_COLOR) for j in range(k, e)]))
         k = e
     host = gpu.tiles_download(0, n, rows, cols)
     return [host[j] for j in range(n)], True
@@ -195,7 +199,8 @@ class Stitcher(Utility.Method):
         batched = self._is_incre_feature_method(caculateOffsetMethod) and self.featureMethod == "surf" \
             and self.offsetCaculate == "mode" and not self.isEnhance
         # decoded once (the reference decodes every tile twice, and a third time for the mosaic)
-        images, self._on_device = _load_sequence(fileList, self.decoder, keep_on_device=batched or not self.isColorMode)
+        images, self._on_device = _load_sequence(fileList, self.decoder, keep_on_device=True, color=bool(self.isColorMode))
+        self._stack_color = bool(self.isColorMode) and self._on_device
         table = {}
         for fileIndex in range(0, fileNum - 1):
             self.printAndWrite("stitching " + str(fileList[fileIndex]) + " and " + str(fileList[fileIndex + 1]))
@@ -223,6 +228,7 @@ class Stitcher(Utility.Method):
             self._gray_cache = {}
             self._stack_files = None
             self._on_device = False
+            self._stack_color = False
         endTime = time.time()
         self.printAndWrite("The time of fusing is " + str(endTime - startTime) + "s")
         if status == False:
@@ -453,15 +459,23 @@ class Stitcher(Utility.Method):
         """Global offset rectification on the host (Stitcher.py:378-431, integer bookkeeping kept verbatim in behaviour),
         paste + blend on a device canvas (Stitcher.py:433-486)."""
         flag = cv2.IMREAD_COLOR if self.isColorMode else cv2.IMREAD_GRAYSCALE
+        originOffsetList.insert(0, [0, 0])          # the reference mutates its argument the same way
+        n = len(originOffsetList)
+        stack_files = getattr(self, "_stack_files", None)
+        if self.isColorMode and self.fuseMethod in gpu.DEVICE_MOSAIC_METHODS and getattr(self, "_stack_color", False) \
+                and stack_files is not None and stack_files[:n] == list(fileList[:n]):
+            # colour tiles are already in HBM (decoded together with the gray ones): no second decode, no upload
+            shape = next(iter(self._gray_cache.values())).shape[:2]
+            origins, rois, (resultRow, resultCol) = sharding.rectify_offsets(originOffsetList, [shape] * n)
+            self.printAndWrite("  The rectified offsetList is " + str([[int(o[0]), int(o[1])] for o in origins]))
+            return gpu.tiles_mosaic_bgr(0, n, np.asarray(origins, np.int32), rois, np.asarray(originOffsetList, np.int32), self.fuseMethod,
+                                        (resultRow, resultCol))
         cache = {} if self.isColorMode else getattr(self, "_gray_cache", {})
         if self.isColorMode and self.decoder == "b200":        # colour tiles: one batched decode instead of a cv2 call per tile
-            n_tiles = len(originOffsetList) + 1
-            cache = dict(zip(fileList[:n_tiles], _imread_color_many(fileList[:n_tiles], self.decoder)))
+            cache = dict(zip(fileList[:n], _imread_color_many(fileList[:n], self.decoder)))
 
         def _imread(path, flag):
             return cache[path] if path in cache else globals()["_imread"](path, flag)
-        originOffsetList.insert(0, [0, 0])          # the reference mutates its argument the same way
-        n = len(originOffsetList)
         imageList = [_imread(fileList[i], flag) for i in range(n)]
         origins, rois, (resultRow, resultCol) = sharding.rectify_offsets(originOffsetList, [im.shape[:2] for im in imageList])
         offsetList = [[int(o[0]), int(o[1])] for o in origins]

@@ -642,4 +642,17 @@ int vfsms_tiles_mosaic(vfsms_ctx *ctx, int first, int n_tiles, const int32_t *ti
                       pair_offset, method, canvas_rows, canvas_cols, canvas_out);
 }
 
+int vfsms_tiles_mosaic_bgr(vfsms_ctx *ctx, int first, int n_tiles, const int32_t *tile_origin, const int32_t *roi_rect, const int32_t *pair_offset,
+                           int method, int canvas_rows, int canvas_cols, uint8_t *canvas_out)
+{
+    if (!ctx || !ctx->tiles_bgr.p || first < 0 || n_tiles < 1 || first + n_tiles > ctx->tiles_n) {
+        vfsms_set_error("tiles_mosaic_bgr: tiles [%d, %d) outside the colour stack", first, first + n_tiles); return VFSMS_E_ARG;
+    }
+    for (int k = first; k < first + n_tiles; k++)
+        if (!ctx->tiles_has_bgr[k]) { vfsms_set_error("tiles_mosaic_bgr: slot %d holds no colour tile", k); return VFSMS_E_ARG; }
+    const size_t img = (size_t)ctx->tiles_rows * ctx->tiles_cols * 3;
+    return mosaic_run(ctx, nullptr, ctx->tiles_bgr.as<uint8_t>() + first * img, n_tiles, ctx->tiles_rows, ctx->tiles_cols, 3, tile_origin, roi_rect,
+                      pair_offset, method, canvas_rows, canvas_cols, canvas_out);
+}
+
 }  // extern "C"

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 static thread_local char g_err[1024] = "";
@@ -172,7 +173,7 @@ void vfsms_destroy(vfsms_ctx *ctx)
                        &ctx->scratch0, &ctx->scratch1, &ctx->scratch2, &ctx->scratch3 };
     for (DevBuf *b : bufs) b->release();
     ctx->pinned_in.release(); ctx->pinned_out.release();
-    ctx->jpeg_pinned.release(); ctx->jpeg_coef.release(); ctx->jpeg_out.release(); ctx->jpeg_planes.release(); ctx->tiles.release();
+    ctx->jpeg_pinned.release(); ctx->jpeg_coef.release(); ctx->jpeg_out.release(); ctx->jpeg_planes.release(); ctx->tiles.release(); ctx->tiles_bgr.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -401,6 +402,7 @@ int vfsms_tiles_reserve(vfsms_ctx *ctx, int n_tiles, int rows, int cols)
     int rc;
     if ((rc = ctx->tiles.reserve((size_t)n_tiles * rows * cols))) return rc;
     ctx->tiles_n = n_tiles; ctx->tiles_rows = rows; ctx->tiles_cols = cols;
+    ctx->tiles_has_bgr.assign((size_t)n_tiles, 0);   // a new reservation starts without colour tiles
     return 0;
 }
 
@@ -419,6 +421,44 @@ int vfsms_tiles_decode_jpeg(vfsms_ctx *ctx, int first, int n, const uint8_t *con
     const int64_t img = (int64_t)ctx->tiles_rows * ctx->tiles_cols;
     return vfsms_jpeg_decode_gray_dev(ctx, n, data, sizes, ctx->tiles.as<uint8_t>() + first * img, ctx->tiles_rows, ctx->tiles_cols,
                                       ctx->tiles_cols, img, nullptr);
+}
+
+static int tiles_bgr_reserve(vfsms_ctx *ctx)
+{
+    const size_t need = (size_t)ctx->tiles_n * ctx->tiles_rows * ctx->tiles_cols * 3;
+    if (ctx->tiles_bgr.bytes >= need) return 0;
+    // growing would move the colour tiles already present: the twin is sized for the whole reservation at once
+    std::fill(ctx->tiles_has_bgr.begin(), ctx->tiles_has_bgr.end(), 0);
+    return ctx->tiles_bgr.reserve(need);
+}
+
+int vfsms_tiles_decode_jpeg_bgr(vfsms_ctx *ctx, int first, int n, const uint8_t *const *data, const size_t *sizes)
+{
+    int rc;
+    if ((rc = tiles_range_ok(ctx, first, n, "tiles_decode_jpeg_bgr"))) return rc;
+    if (!data || !sizes) { vfsms_set_error("tiles_decode_jpeg_bgr: bad arguments"); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if ((rc = tiles_bgr_reserve(ctx))) return rc;
+    const int64_t img = (int64_t)ctx->tiles_rows * ctx->tiles_cols;
+    rc = jpeg_decode_bgr_gray_dev(ctx, n, data, sizes, ctx->tiles_bgr.as<uint8_t>() + first * img * 3, ctx->tiles_rows, ctx->tiles_cols,
+                                  (int64_t)ctx->tiles_cols * 3, img * 3, ctx->tiles.as<uint8_t>() + first * img, ctx->tiles_cols, img, ctx->stream);
+    if (rc) return rc;
+    for (int k = first; k < first + n; k++) ctx->tiles_has_bgr[k] = 1;
+    return 0;
+}
+
+int vfsms_tiles_upload_bgr(vfsms_ctx *ctx, int first, int n, const uint8_t *tiles_bgr)
+{
+    int rc;
+    if ((rc = tiles_range_ok(ctx, first, n, "tiles_upload_bgr"))) return rc;
+    if (!tiles_bgr) { vfsms_set_error("tiles_upload_bgr: bad arguments"); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if ((rc = tiles_bgr_reserve(ctx))) return rc;
+    const size_t img = (size_t)ctx->tiles_rows * ctx->tiles_cols * 3;
+    CUDA_TRY(cudaMemcpyAsync(ctx->tiles_bgr.as<uint8_t>() + first * img, tiles_bgr, img * n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int k = first; k < first + n; k++) ctx->tiles_has_bgr[k] = 1;
+    return 0;
 }
 
 int vfsms_tiles_upload(vfsms_ctx *ctx, int first, int n, const uint8_t *tiles)

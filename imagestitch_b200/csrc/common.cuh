@@ -155,6 +155,8 @@ struct vfsms_ctx {
     DevBuf jpeg_coef, jpeg_out, jpeg_planes;
     DevBuf tiles;              // device-resident tile stack [tiles_n][tiles_rows][tiles_cols] u8 (vfsms_tiles_*)
     int tiles_n = 0, tiles_rows = 0, tiles_cols = 0;
+    DevBuf tiles_bgr;          // colour twin of the stack [tiles_n][tiles_rows][tiles_cols][3] (BGR), allocated on first use
+    std::vector<uint8_t> tiles_has_bgr;   // per slot: the colour twin holds this tile
     void *tex_cache = nullptr;     // texture objects over caller images (surf.cu)
     DevBuf tex_dev;
     void *phase_state = nullptr;   // cuFFT plans etc. (phase.cu)
@@ -186,6 +188,11 @@ int surf_grow(vfsms_ctx *ctx, int grow_cand, int grow_kp);
 int surf_init_tables();
 void surf_tex_destroy(vfsms_ctx *ctx);
 
+// colour decode of n files into out_dev (BGR); gray_out_dev != nullptr also receives the luma plane = what a grayscale decode of the
+// same file yields (libjpeg JCS_GRAYSCALE), so one entropy-decoding pass serves alignment (gray) and mosaic (colour)
+int jpeg_decode_bgr_gray_dev(vfsms_ctx *ctx, int n, const uint8_t *const *data, const size_t *sizes, uint8_t *out_dev, int rows, int cols,
+                             int64_t row_stride, int64_t image_stride, uint8_t *gray_out_dev, int64_t gray_row_stride, int64_t gray_image_stride,
+                             cudaStream_t st);
 int match_reserve(vfsms_ctx *ctx, int n_pairs, int cap);
 int match_tc_batch(vfsms_ctx *ctx, const float *desc_a, const int32_t *n_a, int n_a_stride, const float *desc_b, const int32_t *n_b,
                    int n_b_stride, int n_pairs, int cap, int dim, int32_t *best_idx, float *best_dist, cudaStream_t st);

@@ -521,7 +521,8 @@ static int launch_idct(vfsms_ctx *ctx, const int16_t *cdev, const uint16_t *quan
 // Decode n files of identical geometry.  channels 1: gray, out[i * image_stride + y * row_stride + x];
 // channels 3: BGR interleaved, out[i * image_stride + y * row_stride + 3 * x + c].
 static int jpeg_decode_batch(vfsms_ctx *ctx, int n, const uint8_t *const *data, const size_t *sizes, uint8_t *out_dev, int rows, int cols,
-                             int channels, int64_t row_stride, int64_t image_stride, cudaStream_t st)
+                             int channels, int64_t row_stride, int64_t image_stride, cudaStream_t st,
+                             uint8_t *gray_out_dev = nullptr, int64_t gray_row_stride = 0, int64_t gray_image_stride = 0)
 {
     if (n == 0) return 0;
     std::vector<JpegHeader> H((size_t)n);
@@ -584,6 +585,9 @@ static int jpeg_decode_batch(vfsms_ctx *ctx, int n, const uint8_t *const *data, 
             uint8_t *py = ctx->jpeg_planes.as<uint8_t>();
             P.y = py; P.pitch_y = h.blocks_w * 8; P.gray = !colour; P.hf = P.vf = 1;
             if ((rc = launch_idct(ctx, cdev, h.quant[h.comp[0].tq], h.blocks_w, h.blocks_h, py, h.blocks_h * 8, h.blocks_w * 8, P.pitch_y, st))) return rc;
+            if (gray_out_dev)      // the luma plane IS the grayscale decode of the file (cv2.imdecode(data, 0))
+                CUDA_TRY(cudaMemcpy2DAsync(gray_out_dev + (size_t)(c0 + j) * gray_image_stride, (size_t)gray_row_stride, py, (size_t)P.pitch_y,
+                                           (size_t)cols, (size_t)rows, cudaMemcpyDeviceToDevice, st));
             if (colour) {
                 const JpegComp &Y = h.comp[0], &C = h.comp[1];
                 const int cbw = h.mcux * C.h, cbh = h.mcuy * C.v;
@@ -638,6 +642,16 @@ extern "C" int vfsms_jpeg_decode_bgr_dev(vfsms_ctx *ctx, int n_images, const uin
     int rc = jpeg_decode_batch(ctx, n_images, data, sizes, out_dev, rows, cols, 3, row_stride, image_stride, st);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int jpeg_decode_bgr_gray_dev(vfsms_ctx *ctx, int n, const uint8_t *const *data, const size_t *sizes, uint8_t *out_dev, int rows, int cols,
+                             int64_t row_stride, int64_t image_stride, uint8_t *gray_out_dev, int64_t gray_row_stride, int64_t gray_image_stride,
+                             cudaStream_t st)
+{
+    int rc = jpeg_decode_batch(ctx, n, data, sizes, out_dev, rows, cols, 3, row_stride, image_stride, st, gray_out_dev, gray_row_stride, gray_image_stride);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));              // the pinned staging buffer is reusable on return
     return 0;
 }
 

@@ -512,6 +512,29 @@ def tiles_decode_jpeg(first, datas, device=0):
     _jpeg_check(_lib.load().vfsms_tiles_decode_jpeg(_lib.context(device), int(first), len(bufs), ptrs, sizes), "vfsms_tiles_decode_jpeg")
 
 
+def tiles_decode_jpeg_bgr(first, datas, device=0):
+    """One entropy-decoding pass per file: BGR into the colour twin of the stack, the luma plane (= the gray decode) into the gray stack."""
+    bufs, ptrs, sizes = _jpeg_args(datas)
+    _jpeg_check(_lib.load().vfsms_tiles_decode_jpeg_bgr(_lib.context(device), int(first), len(bufs), ptrs, sizes), "vfsms_tiles_decode_jpeg_bgr")
+
+
+def tiles_upload_bgr(first, tiles, device=0):
+    t = np.ascontiguousarray(tiles, np.uint8)
+    if t.ndim == 3:
+        t = t[None]
+    assert t.ndim == 4 and t.shape[3] == 3
+    check(_lib.load().vfsms_tiles_upload_bgr(_lib.context(device), int(first), t.shape[0], t.ctypes.data_as(ctypes.c_void_p)), "vfsms_tiles_upload_bgr")
+
+
+def tiles_mosaic_bgr(first, n_tiles, origins, rois, pair_offsets, method, canvas_shape, device=0):
+    o = np.ascontiguousarray(origins, np.int32); r = np.ascontiguousarray(rois, np.int32); po = np.ascontiguousarray(pair_offsets, np.int32)
+    out = np.empty((int(canvas_shape[0]), int(canvas_shape[1]), 3), np.uint8)
+    check(_lib.load().vfsms_tiles_mosaic_bgr(_lib.context(device), int(first), int(n_tiles), o.ctypes.data_as(ctypes.c_void_p),
+                                             r.ctypes.data_as(ctypes.c_void_p), po.ctypes.data_as(ctypes.c_void_p), FUSE_METHODS[method],
+                                             out.shape[0], out.shape[1], out.ctypes.data_as(ctypes.c_void_p)), "vfsms_tiles_mosaic_bgr")
+    return out
+
+
 def tiles_upload(first, tiles, device=0):
     t = np.ascontiguousarray(tiles, np.uint8)
     if t.ndim == 2:

@@ -293,6 +293,17 @@ int vfsms_tiles_align(vfsms_ctx *ctx, int first, int n_pairs, int direction, int
 int vfsms_tiles_mosaic(vfsms_ctx *ctx, int first, int n_tiles, const int32_t *tile_origin, const int32_t *roi_rect,
                        const int32_t *pair_offset, int method, int canvas_rows, int canvas_cols, uint8_t *canvas_out);
 
+/* Colour twin of the stack.  Main.py:6 sets isColorMode = True: the reference then decodes every file in gray for the alignment
+ * (Stitcher.py:68-69) and again in colour for the mosaic (Stitcher.py:382, :401).  vfsms_tiles_decode_jpeg_bgr entropy-decodes
+ * each file ONCE: BGR (= cv2.imdecode(data, IMREAD_COLOR)) goes to the colour twin and the luma plane (= cv2.imdecode(data, 0),
+ * libjpeg's JCS_GRAYSCALE output) to the gray stack, slots first .. first + n - 1.  vfsms_tiles_upload_bgr fills colour slots from
+ * host memory (other formats; the gray slot is filled by vfsms_tiles_upload).  vfsms_tiles_mosaic_bgr = vfsms_mosaic_host with
+ * channels = 3 on tiles that never left HBM; every slot of the range must hold a colour tile. */
+int vfsms_tiles_decode_jpeg_bgr(vfsms_ctx *ctx, int first, int n, const uint8_t *const *data, const size_t *sizes);
+int vfsms_tiles_upload_bgr(vfsms_ctx *ctx, int first, int n, const uint8_t *tiles_bgr /* n x rows x cols x 3, host */);
+int vfsms_tiles_mosaic_bgr(vfsms_ctx *ctx, int first, int n_tiles, const int32_t *tile_origin, const int32_t *roi_rect,
+                           const int32_t *pair_offset, int method, int canvas_rows, int canvas_cols, uint8_t *canvas_out /* rows x cols x 3 */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,4 +38,9 @@ timeout -s KILL 300 ncu --metrics gpu__time_duration.sum --clock-control none -k
 timeout -s KILL 500 ncu --set full --clock-control none --import-source on \
     -k regex:"match_tc_pair_kernel|orient_describe_warp|hessian_nms|rank_sort|bin_rank" -s 8 -c 6 -o $OUT/${TAG}_full \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-autotune $OPTS > $OUT/${TAG}_ncu_full.log 2>&1
+# 4. output encode (jpeg_enc.cu, written without GPU access): measurement + one full capture of its kernels
+timeout -s KILL 300 python scripts/bench_encode.py > $OUT/${TAG}_bench_encode.json 2> $OUT/${TAG}_bench_encode.err
+timeout -s KILL 300 python scripts/bench_encode.py --gray >> $OUT/${TAG}_bench_encode.json 2>> $OUT/${TAG}_bench_encode.err
+timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:"jpeg_fdct_quant|jpeg_block_bits|jpeg_emit|jpeg_stuff|scan_" \
+    -s 9 -c 9 -o $OUT/${TAG}_encode_full python scripts/bench_encode.py --rows 4096 --cols 4096 --reps 1 > $OUT/${TAG}_ncu_encode.log 2>&1
 ls -la $OUT | tail -14

@@ -210,7 +210,9 @@ const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no er
 cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int *v, enum cudaDeviceAttr attr, int)
 {
-    *v = attr == cudaDevAttrMaxTexture2DLinearHeight ? 65000 : (attr == cudaDevAttrMultiProcessorCount ? 4 : 0);
+    // VFSMS_EMU_TEX_ROWS: a small 2-D texture height limit, so that the grouping of stacked textures is exercised by small batches
+    const char *tex_rows = getenv("VFSMS_EMU_TEX_ROWS");
+    *v = attr == cudaDevAttrMaxTexture2DLinearHeight ? (tex_rows ? atoi(tex_rows) : 65000) : (attr == cudaDevAttrMultiProcessorCount ? 4 : 0);
     return cudaSuccess;
 }
 cudaError_t cudaGetDeviceProperties(struct cudaDeviceProp *p, int)

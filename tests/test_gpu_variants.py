@@ -50,9 +50,9 @@ def test_describe_stacked_texture_borders_and_giants(gpu):
         assert np.array_equal(k1, k2) and np.array_equal(d1, d2)
 
 
-def test_describe_stacked_texture_batches_and_chunks(gpu):
-    """align_batch over many ROIs: image index -> texture row offset; 80 ROIs x 1024 rows exceed the 65000-row limit of one
-    2-D linear texture, so the launch is split into groups."""
+def test_describe_stacked_texture_batches(gpu):
+    """align_batch over many ROIs: image index -> texture row offset.  (The CPU emulation runs this test a second time with a
+    450-row texture limit, which splits these 12 images into groups like the 80 x 1020-row case below.)"""
     from imagestitch_b200 import synth
     rois_a, rois_b = [], []
     for k in range(6):
@@ -62,6 +62,12 @@ def test_describe_stacked_texture_batches_and_chunks(gpu):
     gpu.set_option("describe", 1); r1 = gpu.align_batch(ra, rb)
     gpu.set_option("describe", 2); r2 = gpu.align_batch(ra, rb)
     assert np.array_equal(r1, r2) and r1["status"].all()
+    gpu.set_option("describe", 1)
+
+
+def test_describe_stacked_texture_row_limit_groups(gpu):
+    """80 ROIs x 1020 rows exceed the 65000-row limit of one 2-D linear texture: the launch is split into groups."""
+    from imagestitch_b200 import synth
     A, B, _ = synth.pair(seed=77, size=1024, overlap=110, direction=2)
     ta = np.stack([np.ascontiguousarray(np.roll(A, 13 * k, axis=0)[:, 1024 - 204:]) for k in range(40)])
     tb = np.stack([np.ascontiguousarray(np.roll(B, 13 * k, axis=0)[:, :204]) for k in range(40)])

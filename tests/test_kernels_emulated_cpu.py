@@ -26,9 +26,10 @@ pytestmark = pytest.mark.skipif(os.environ.get("VFSMS_EMU") == "1", reason="alre
 # (selection, -k expression, minimum number of tests that must have passed)
 FAST = [
     (["tests/test_gpu_blend.py", "tests/test_gpu_zz_bands.py", "tests/test_gpu_phase.py", "tests/test_gpu_orb.py"], None, 20),
-    (["tests/test_gpu_jpeg.py", "tests/test_gpu_jpeg_encode.py"], "not full_size", 35),
+    (["tests/test_gpu_jpeg.py", "tests/test_gpu_zz_jpeg_encode.py"], "not full_size", 35),
     (["tests/test_gpu_surf.py"], "not real_micrograph", 9),
-    (["tests/test_gpu_zz_phase_wrap.py", "tests/test_gpu_variants.py"], "overlap_sums or sort_per_image or large_windows_first or borders_and_giants", 4),
+    (["tests/test_gpu_zz_phase_wrap.py", "tests/test_gpu_variants.py", "tests/test_gpu_zz_colour_stack.py"],
+     "overlap_sums or sort_per_image or large_windows_first or borders_and_giants or colour_twin", 5),
 ]
 
 
@@ -71,6 +72,13 @@ def test_gpu_parity_tests_on_emulated_kernels(emu_lib, case):
     rc, passed, out = _run(selection, kexpr)
     assert rc == 0, out[-6000:]
     assert passed >= at_least, out[-2000:]
+
+
+def test_stacked_texture_groups_on_emulated_kernels(emu_lib):
+    """describe mode 2 with a 450-row (groups of 4 images) and a 250-row (groups of 2) texture height limit"""
+    for limit in ("450", "250"):
+        rc, passed, out = _run(["tests/test_gpu_variants.py"], "stacked_texture_batches", {"VFSMS_EMU_TEX_ROWS": limit})
+        assert rc == 0 and passed == 1, out[-6000:]
 
 
 @pytest.mark.skipif(os.environ.get("VFSMS_EMU_FULL") != "1", reason="set VFSMS_EMU_FULL=1 (about 10 minutes)")

@@ -404,6 +404,26 @@ def main():
                   "jpeg_bytes_per_tile": int(np.mean([len(f) for f in files])), "host_threads": min(len(os.sched_getaffinity(0)), int(_cgroup_cpu_quota() or 1 << 30), 32, n_t),
                   "cv2_imdecode_tiles_per_s_1_thread": 1.0 / dt_c,
                   "what": "%d synthetic 2048x2048 JPEG tiles (q92, single component) from host bytes to HBM-resident u8 tiles: host Huffman threads + H2D of int16 coefficients + IDCT kernel; wall clock" % n_t}
+        # option "entropy" = 1: Huffman decoding on the device (written without GPU access, verified on the CPU emulation only): first
+        # hardware run happens here, so a failure is reported inside the block and the option goes back to the host stage
+        try:
+            gpu.set_option("entropy", 1, device=local)
+            stack2 = torch.empty_like(stack)
+            gpu.jpeg_decode_gray_dev(files, stack2, device=local, stream=stream)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                gpu.jpeg_decode_gray_dev(files, stack2, device=local, stream=stream)
+            dt_d = (time.perf_counter() - t0) / reps
+            ingest["device_entropy"] = {"tiles_per_s": n_t / dt_d, "identical_to_host_stage": bool(torch.equal(stack, stack2)),
+                                        "sync_passes": gpu.jpeg_last_entropy_passes(device=local),
+                                        "what": "same files, Huffman decoding on the device (self-synchronising 1024-bit subsequences): H2D of the unstuffed scan only"}
+        except Exception as e:                                                         # noqa: BLE001
+            ingest["device_entropy"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        finally:
+            try:
+                gpu.set_option("entropy", 0, device=local)
+            except Exception:                                                          # noqa: BLE001
+                pass
 
     # ---- output encode: a BGR mosaic resident in HBM -> the bytes cv2.imwrite(".jpg") would write.
     # First run on hardware happens inside this bench (written without GPU access, verified on the CPU emulation only), so a

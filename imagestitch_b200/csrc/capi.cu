@@ -20,6 +20,7 @@ void phase_state_destroy(vfsms_ctx *ctx);
 void blend_state_destroy(vfsms_ctx *ctx);
 void orb_state_destroy(vfsms_ctx *ctx);
 void jpeg_enc_state_destroy(vfsms_ctx *ctx);
+void jpeg_huff_state_destroy(vfsms_ctx *ctx);
 
 cudaEvent_t prof_event(vfsms_ctx *ctx)
 {
@@ -60,14 +61,15 @@ int vfsms_set_matcher(vfsms_ctx *ctx, int mode)
     ctx->matcher_mode = mode;
     return 0;
 }
-static const char *const k_option_names[VFSMS_OPT_COUNT] = { "describe", "sort", "lpt" };
-static const int k_option_max[VFSMS_OPT_COUNT] = { 4, 1, 1 };
+static const char *const k_option_names[VFSMS_OPT_COUNT] = { "describe", "sort", "lpt", "entropy" };
+static const int k_option_max[VFSMS_OPT_COUNT] = { 4, 1, 1, 1 };
 static int *option_slot(vfsms_ctx *ctx, int option)
 {
     switch (option) {
     case VFSMS_OPT_DESCRIBE_MODE: return &ctx->describe_mode;
     case VFSMS_OPT_SORT_MODE: return &ctx->sort_mode;
     case VFSMS_OPT_DESCRIBE_LPT: return &ctx->describe_lpt;
+    case VFSMS_OPT_ENTROPY: return &ctx->entropy_mode;
     default: return nullptr;
     }
 }
@@ -163,6 +165,7 @@ void vfsms_destroy(vfsms_ctx *ctx)
     blend_state_destroy(ctx);
     orb_state_destroy(ctx);
     jpeg_enc_state_destroy(ctx);
+    jpeg_huff_state_destroy(ctx);
     surf_tex_destroy(ctx);
     ctx->tex_dev.release();
     SurfWorkspace &w = ctx->surf;

@@ -12,6 +12,7 @@
 // restart intervals -- every JPEG of the reference's demoImages.  Anything else returns VFSMS_E_UNSUPPORTED and the
 // caller keeps its own decoder.
 #include "common.cuh"
+#include "scan.cuh"
 #include <sched.h>
 #include <stdlib.h>
 #include <string.h>
@@ -293,6 +294,405 @@ static void jpeg_entropy_decode(const uint8_t *d, size_t n, const JpegHeader &H,
         }
 }
 
+
+// ---------------------------------------------------------------- device entropy decoding (VFSMS_OPT_ENTROPY = 1)
+// The host Huffman stage sets the ingest rate (one thread per file, 20+ ms per 4-MPix tile).  A Huffman stream can be entered at
+// any bit: a decoder started in the wrong state re-synchronises with the true symbol boundaries after a few codes
+// (self-synchronisation; Weissenberger & Schmidt, "Massively parallel Huffman decoding on GPUs", ICPP 2018, and their JPEG
+// decoder, ICPP 2021).  Schedule:
+//   host        the scan is copied without its stuffing bytes (0xFF 0x00 -> 0xFF) into pinned memory: 1/6 of the coefficient bytes
+//               the host stage ships -- the only part that stays on the CPU (memchr speed)
+//   sub_init    the bit stream of every file is cut into subsequences of HUFF_SUB_BITS bits; one thread decodes each from its first
+//               bit in state (block 0 of the MCU, coefficient 0) up to its end and records where and in which state it left
+//               (exit position, block-in-MCU, coefficient index, blocks completed)
+//   sub_sync    subsequence s is decoded again from the exit of s - 1; passes repeat until none changed (subsequence 0 starts in
+//               the true state, so the exits become true front to back; a pass without change is the fixed point = the serial
+//               decode).  A thread whose predecessor's exit did not change skips the pass.
+//   scan        blocks completed per subsequence -> index of the first block of every subsequence (scan.cuh)
+//   sub_write   every subsequence is decoded a last time from its true entry and writes its coefficients (int16, natural order,
+//               the layout of the host stage) and the DC DIFFERENCES
+//   dc_*        per component: sums of the differences per MCU, prefix sum over the MCUs, absolute DC values
+// Same result as jpeg_entropy_decode, symbol for symbol (the decode step below mirrors BitReader::symbol / receive_extend,
+// including what they do on corrupt data).  Files with restart intervals take the host stage.
+__constant__ uint8_t c_huff_zigzag[64];
+#define HUFF_SUB_BITS 1024
+#define HUFF_MAX_MCU_BLOCKS 10
+
+static int host_threads();
+
+struct DevHuff { uint16_t fast[512]; int32_t maxcode[18]; int32_t valptr[17]; uint8_t vals[256]; };
+
+struct DevScan {
+    unsigned long long byte_base;            // this file's unstuffed scan inside the stream buffer (multiple of 4)
+    unsigned int n_bits;                     // length of the scan in bits
+    int first_sub, n_sub;                    // its subsequences in the flattened arrays
+    int mcu_blocks, n_blocks, mcux, n_mcu;
+    int first_mcu_slot;                      // its slots in the per-(component, MCU) DC arrays: [first_mcu_slot + c * n_mcu + m]
+    int ncomp;
+    uint8_t blk_comp[HUFF_MAX_MCU_BLOCKS], blk_v[HUFF_MAX_MCU_BLOCKS], blk_h[HUFF_MAX_MCU_BLOCKS];
+    uint8_t comp_h[4], comp_v[4], dc_tab[4], ac_tab[4];          // tables: indices into this file's DevHuff[8] (dc 0-3, ac 4-7)
+    int comp_bw[4];                          // blocks per row of component c (mcux * h)
+    long long comp_off[4];                   // int16 offset of component c's plane from the file's coefficient base, -1 = parse and drop
+    long long coef_base;                     // int16 offset of the file's coefficients in the device buffer
+    int table_base;                          // index of this file's first DevHuff
+};
+
+__device__ __forceinline__ uint32_t huff_bits32(const uint32_t *__restrict__ words, unsigned int pos)
+{
+    const uint32_t a = __byte_perm(words[pos >> 5], 0, 0x0123), b = __byte_perm(words[(pos >> 5) + 1], 0, 0x0123);
+    const int sh = (int)(pos & 31);
+    return sh ? (a << sh) | (b >> (32 - sh)) : a;
+}
+
+// One code (+ its magnitude bits).  State: b = block inside the MCU, k = next coefficient (0: the DC code comes next).
+// Returns true when a block was completed.  WRITE: blk points at the current block (nullptr when its component is dropped).
+template <bool WRITE>
+__device__ __forceinline__ bool huff_step(const uint32_t *__restrict__ words, const DevHuff *__restrict__ tabs, const DevScan &F,
+                                          unsigned int &pos, int &b, int &k, int16_t *blk)
+{
+    const int c = F.blk_comp[b];
+    const DevHuff &T = tabs[F.table_base + (k == 0 ? F.dc_tab[c] : 4 + F.ac_tab[c])];
+    uint32_t w = huff_bits32(words, pos);
+    int sym, len;
+    const uint16_t e = T.fast[w >> 23];
+    if (e != 0xFFFF) { len = e >> 8; sym = e & 255; }
+    else {
+        len = 16; sym = 0;                                  // corrupt stream: skip 16 bits like the host stage
+#pragma unroll 1
+        for (int l = 10; l <= 16; l++) {
+            const int code = (int)(w >> (32 - l));
+            if (code <= T.maxcode[l]) { len = l; sym = T.vals[(code + T.valptr[l]) & 255]; break; }
+        }
+    }
+    pos += len;
+    bool done = false;
+    if (k == 0) {
+        const int s = sym & 15;
+        int v = 0;
+        if (s) {
+            w = huff_bits32(words, pos);
+            v = (int)(w >> (32 - s));
+            if (v < (1 << (s - 1))) v = v - (1 << s) + 1;
+            pos += s;
+        }
+        if (WRITE && blk) blk[0] = (int16_t)v;              // the DC DIFFERENCE; dc_apply_kernel turns it into the value
+        k = 1;
+    } else {
+        const int r = sym >> 4, sz = sym & 15;
+        if (sz == 0) {
+            if (r == 15) { k += 16; done = k >= 64; }
+            else done = true;                               // end of block
+        } else {
+            k += r;
+            w = huff_bits32(words, pos);
+            int v = (int)(w >> (32 - sz));
+            if (v < (1 << (sz - 1))) v = v - (1 << sz) + 1;
+            pos += sz;
+            if (WRITE && blk && k < 64) blk[c_huff_zigzag[k]] = (int16_t)v;
+            k++;
+            done = k >= 64;
+        }
+    }
+    if (done) { k = 0; b = b + 1 == F.mcu_blocks ? 0 : b + 1; }
+    return done;
+}
+
+
+// exit record of a subsequence (one 64-bit word, so that it is read and written in one piece): low word = exit bit position
+// (relative to the file), high word = blocks completed << 16 | b << 6 | k
+typedef unsigned long long huff_rec;
+__device__ __forceinline__ huff_rec huff_make_rec(unsigned int pos, unsigned int meta) { return (huff_rec)pos | ((huff_rec)meta << 32); }
+__device__ __forceinline__ huff_rec huff_decode_sub(const uint32_t *__restrict__ words, const DevHuff *__restrict__ tabs, const DevScan &F,
+                                                 unsigned int pos, int b, int k, unsigned int end)
+{
+    int nblk = 0;
+    while (pos < end) nblk += huff_step<false>(words, tabs, F, pos, b, k, nullptr) ? 1 : 0;
+    return huff_make_rec(pos, ((unsigned)nblk << 16) | ((unsigned)b << 6) | (unsigned)k);
+}
+
+__device__ __forceinline__ const DevScan &huff_file_of(const DevScan *__restrict__ files, int n_files, int s)
+{
+    int lo = 0, hi = n_files;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (files[mid].first_sub <= s) lo = mid; else hi = mid; }
+    return files[lo];
+}
+
+__global__ void __launch_bounds__(128) huff_sub_init_kernel(const uint8_t *__restrict__ stream, const DevHuff *__restrict__ tabs,
+                                                           const DevScan *__restrict__ files, int n_files, int n_sub, huff_rec *exits, huff_rec *used)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sub) return;
+    const DevScan &F = huff_file_of(files, n_files, s);
+    const int sl = s - F.first_sub;
+    const uint32_t *words = (const uint32_t *)(stream + F.byte_base);
+    const unsigned int begin = (unsigned int)sl * HUFF_SUB_BITS, end = min(begin + HUFF_SUB_BITS, F.n_bits);
+    exits[s] = huff_decode_sub(words, tabs, F, begin, 0, 0, end);
+    used[s] = huff_make_rec(begin, 0);                       // the entry this exit was computed from
+}
+
+__global__ void __launch_bounds__(128) huff_sub_sync_kernel(const uint8_t *__restrict__ stream, const DevHuff *__restrict__ tabs,
+                                                           const DevScan *__restrict__ files, int n_files, int n_sub, huff_rec *exits, huff_rec *used,
+                                                           int *changed)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sub) return;
+    const DevScan &F = huff_file_of(files, n_files, s);
+    const int sl = s - F.first_sub;
+    if (sl == 0) return;                                     // the first subsequence of a file starts in the true state
+    // the records are single 64-bit words: a concurrent update of the predecessor is seen either before or after, both are exits
+    // some pass has produced, and the pass that sees no change anywhere ends the iteration
+    const huff_rec prev = *(volatile huff_rec *)(exits + s - 1);
+    const huff_rec entry = prev & 0x0000ffffffffffffull;     // position + state, without the block count
+    if (used[s] == entry) return;                            // same entry as last time: same exit
+    const uint32_t *words = (const uint32_t *)(stream + F.byte_base);
+    const unsigned int begin = (unsigned int)sl * HUFF_SUB_BITS, end = min(begin + HUFF_SUB_BITS, F.n_bits);
+    const unsigned int meta = (unsigned int)(entry >> 32);
+    const unsigned int pos = max((unsigned int)entry, begin);   // (an exit never lies before the next subsequence's first bit)
+    const huff_rec e = huff_decode_sub(words, tabs, F, pos, (int)((meta >> 6) & 1023), (int)(meta & 63), end);
+    used[s] = entry;
+    if (exits[s] != e) { *(volatile huff_rec *)(exits + s) = e; *changed = 1; }
+}
+
+__global__ void __launch_bounds__(256) huff_sub_count_kernel(const huff_rec *__restrict__ exits, int n_sub, uint32_t *__restrict__ counts)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_sub) counts[s] = (uint32_t)(exits[s] >> 48);
+}
+
+__global__ void __launch_bounds__(128) huff_sub_write_kernel(const uint8_t *__restrict__ stream, const DevHuff *__restrict__ tabs,
+                                                            const DevScan *__restrict__ files, int n_files, int n_sub,
+                                                            const huff_rec *__restrict__ exits, const unsigned long long *__restrict__ first_block,
+                                                            int16_t *__restrict__ coef)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sub) return;
+    const DevScan &F = huff_file_of(files, n_files, s);
+    const int sl = s - F.first_sub;
+    const uint32_t *words = (const uint32_t *)(stream + F.byte_base);
+    const unsigned int begin = (unsigned int)sl * HUFF_SUB_BITS, end = min(begin + HUFF_SUB_BITS, F.n_bits);
+    unsigned int pos = begin;
+    int b = 0, k = 0;
+    if (sl > 0) {
+        const huff_rec prev = exits[s - 1];
+        const unsigned int meta = (unsigned int)(prev >> 32);
+        pos = max((unsigned int)prev, begin); b = (int)((meta >> 6) & 1023); k = (int)(meta & 63);
+    }
+    long long g = (long long)(first_block[s] - first_block[F.first_sub]);     // block of the file this subsequence starts in
+    auto block_ptr = [&](long long gi, int bi) -> int16_t * {
+        const int c = F.blk_comp[bi];
+        if (F.comp_off[c] < 0) return nullptr;
+        const long long m = gi / F.mcu_blocks;
+        const int my = (int)(m / F.mcux), mx = (int)(m - (long long)my * F.mcux);
+        const long long row = (long long)my * F.comp_v[c] + F.blk_v[bi], col = (long long)mx * F.comp_h[c] + F.blk_h[bi];
+        return coef + F.coef_base + F.comp_off[c] + (row * F.comp_bw[c] + col) * 64;
+    };
+    int16_t *blk = g < F.n_blocks ? block_ptr(g, b) : nullptr;
+    while (pos < end && g < F.n_blocks) {
+        if (huff_step<true>(words, tabs, F, pos, b, k, blk)) { g++; blk = g < F.n_blocks ? block_ptr(g, b) : nullptr; }
+    }
+}
+
+// DC predictors: blk[0] holds the difference against the previous block of the component in scan order
+__global__ void __launch_bounds__(256) huff_dc_sums_kernel(const DevScan *__restrict__ files, int n_files, const int16_t *__restrict__ coef,
+                                                          uint32_t *__restrict__ sums)
+{
+    const int f = blockIdx.y;
+    const DevScan &F = files[f];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F.ncomp * F.n_mcu; i += gridDim.x * blockDim.x) {
+        const int c = i / F.n_mcu, m = i - c * F.n_mcu;
+        int sum = 0;
+        if (F.comp_off[c] >= 0) {
+            const int my = m / F.mcux, mx = m - my * F.mcux;
+            for (int v = 0; v < F.comp_v[c]; v++)
+                for (int h = 0; h < F.comp_h[c]; h++)
+                    sum += coef[F.coef_base + F.comp_off[c] + ((long long)(my * F.comp_v[c] + v) * F.comp_bw[c] + mx * F.comp_h[c] + h) * 64];
+        }
+        sums[F.first_mcu_slot + i] = (uint32_t)sum;
+    }
+}
+
+__global__ void __launch_bounds__(256) huff_dc_apply_kernel(const DevScan *__restrict__ files, int n_files, int16_t *__restrict__ coef,
+                                                           const unsigned long long *__restrict__ prefix)
+{
+    const int f = blockIdx.y;
+    const DevScan &F = files[f];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F.ncomp * F.n_mcu; i += gridDim.x * blockDim.x) {
+        const int c = i / F.n_mcu, m = i - c * F.n_mcu;
+        if (F.comp_off[c] < 0) continue;
+        // two's-complement sums: the low 32 bits of the 64-bit prefix difference are the signed predictor
+        int pred = (int)(uint32_t)(prefix[F.first_mcu_slot + i] - prefix[F.first_mcu_slot + c * F.n_mcu]);
+        const int my = m / F.mcux, mx = m - my * F.mcux;
+        for (int v = 0; v < F.comp_v[c]; v++)
+            for (int h = 0; h < F.comp_h[c]; h++) {
+                int16_t *p = coef + F.coef_base + F.comp_off[c] + ((long long)(my * F.comp_v[c] + v) * F.comp_bw[c] + mx * F.comp_h[c] + h) * 64;
+                pred += *p;
+                *p = (int16_t)pred;
+            }
+    }
+}
+
+struct HuffDevState {
+    bool zigzag = false;
+    DevBuf stream, tabs, files, exits, used, counts, first_block, partial, changed, dc_sums, dc_prefix, totals;
+    HostBuf pinned;
+};
+
+static HuffDevState *huff_state(vfsms_ctx *ctx)
+{
+    if (!ctx->jpeg_huff_state) ctx->jpeg_huff_state = new HuffDevState();
+    return (HuffDevState *)ctx->jpeg_huff_state;
+}
+
+void jpeg_huff_state_destroy(vfsms_ctx *ctx)
+{
+    HuffDevState *s = (HuffDevState *)ctx->jpeg_huff_state;
+    if (!s) return;
+    DevBuf *bufs[] = { &s->stream, &s->tabs, &s->files, &s->exits, &s->used, &s->counts, &s->first_block, &s->partial, &s->changed, &s->dc_sums,
+                       &s->dc_prefix, &s->totals };
+    for (DevBuf *b : bufs) b->release();
+    s->pinned.release();
+    delete s;
+    ctx->jpeg_huff_state = nullptr;
+}
+
+// scan bytes of one file without the stuffing zeros; stops at the first marker.  Returns the number of bytes written.
+static size_t jpeg_unstuff(const uint8_t *d, size_t begin, size_t n, uint8_t *out)
+{
+    size_t i = begin, o = 0;
+    while (i < n) {
+        const uint8_t *ff = (const uint8_t *)memchr(d + i, 0xFF, n - i);
+        const size_t run = ff ? (size_t)(ff - (d + i)) : n - i;
+        memcpy(out + o, d + i, run);
+        o += run; i += run;
+        if (!ff) break;
+        if (i + 1 < n && d[i + 1] == 0) { out[o++] = 0xFF; i += 2; }
+        else break;                                          // a marker (EOI): end of the entropy-coded data
+    }
+    return o;
+}
+
+// Entropy-decode files [0, cn) of a chunk on the device: coefficients of file j at coef_dev + per_i16 * j, laid out like the host stage
+// (component planes one after the other; chroma parsed and dropped unless want_chroma).  All files must have restart_interval == 0.
+// Returns 0, a negative VFSMS_E_* code, or 1 when a stream ends early and the chunk has to take the host stage.
+static int jpeg_entropy_decode_device(vfsms_ctx *ctx, int cn, const uint8_t *const *data, const size_t *sizes, const JpegHeader *H,
+                                      bool want_chroma, int16_t *coef_dev, size_t per_i16, cudaStream_t st)
+{
+    HuffDevState *S = huff_state(ctx);
+    int rc;
+    if (!S->zigzag) { CUDA_TRY(cudaMemcpyToSymbol(c_huff_zigzag, kZigzag, 64)); S->zigzag = true; }
+    // layout of the pinned staging buffer: [DevScan x cn][DevHuff x 8 cn][streams, each padded to 4 bytes + 16 zero bytes]
+    std::vector<size_t> base((size_t)cn + 1);
+    const size_t files_bytes = (size_t)cn * sizeof(DevScan), tabs_bytes = (size_t)cn * 8 * sizeof(DevHuff);
+    size_t total = 0;
+    for (int j = 0; j < cn; j++) { base[j] = total; total += ((sizes[j] - H[j].scan_begin + 3) & ~(size_t)3) + 16; }
+    base[cn] = total;
+    if ((rc = S->pinned.reserve(files_bytes + tabs_bytes + total))) return rc;
+    DevScan *files = (DevScan *)S->pinned.p;
+    DevHuff *tabs = (DevHuff *)((uint8_t *)S->pinned.p + files_bytes);
+    uint8_t *streams = (uint8_t *)S->pinned.p + files_bytes + tabs_bytes;
+    memset(streams, 0, total);
+    std::vector<size_t> lens((size_t)cn);
+    {
+        std::atomic<int> next(0);
+        auto work = [&]() { for (int j = next.fetch_add(1); j < cn; j = next.fetch_add(1)) lens[j] = jpeg_unstuff(data[j], H[j].scan_begin, sizes[j], streams + base[j]); };
+        const int workers = host_threads() < cn ? host_threads() : cn;
+        std::vector<std::thread> pool;
+        for (int w = 1; w < workers; w++) pool.emplace_back(work);
+        work();
+        for (auto &th : pool) th.join();
+    }
+    int n_sub = 0, n_slots = 0;
+    for (int j = 0; j < cn; j++) {
+        const JpegHeader &h = H[j];
+        DevScan &F = files[j];
+        memset(&F, 0, sizeof(F));
+        if (lens[j] * 8 > 0xfffffff0ull) { vfsms_set_error("jpeg: scan too long for the device entropy stage"); return VFSMS_E_UNSUPPORTED; }
+        F.byte_base = base[j]; F.n_bits = (unsigned int)(lens[j] * 8);
+        F.first_sub = n_sub; F.n_sub = (int)((F.n_bits + HUFF_SUB_BITS - 1) / HUFF_SUB_BITS);
+        if (F.n_sub < 1) F.n_sub = 1;
+        n_sub += F.n_sub;
+        F.mcux = h.mcux; F.n_mcu = h.mcux * h.mcuy; F.ncomp = h.ncomp; F.table_base = 8 * j;
+        F.first_mcu_slot = n_slots; n_slots += F.ncomp * F.n_mcu;
+        long long off = 0;
+        int nb = 0;
+        for (int c = 0; c < h.ncomp; c++) {
+            const JpegComp &C = h.comp[c];
+            F.comp_h[c] = (uint8_t)C.h; F.comp_v[c] = (uint8_t)C.v; F.dc_tab[c] = (uint8_t)C.td; F.ac_tab[c] = (uint8_t)C.ta;
+            F.comp_bw[c] = h.mcux * C.h;
+            const long long plane = (long long)(h.mcuy * C.v) * (h.mcux * C.h) * 64;
+            if (c == 0 || want_chroma) { F.comp_off[c] = off; off += plane; } else F.comp_off[c] = -1;
+            for (int v = 0; v < C.v; v++)
+                for (int hh = 0; hh < C.h; hh++) {
+                    if (nb >= HUFF_MAX_MCU_BLOCKS) { vfsms_set_error("jpeg: more than 10 blocks per MCU"); return VFSMS_E_UNSUPPORTED; }
+                    F.blk_comp[nb] = (uint8_t)c; F.blk_v[nb] = (uint8_t)v; F.blk_h[nb] = (uint8_t)hh; nb++;
+                }
+        }
+        for (int t = 0; t < 4; t++) {
+            const HuffTable *src[2] = { &h.dc[t], &h.ac[t] };
+            for (int q = 0; q < 2; q++) {
+                DevHuff &D = tabs[8 * j + 4 * q + t];
+                memcpy(D.fast, src[q]->fast, sizeof(D.fast)); memcpy(D.maxcode, src[q]->maxcode, sizeof(D.maxcode));
+                memcpy(D.valptr, src[q]->valptr, sizeof(D.valptr)); memcpy(D.vals, src[q]->vals, sizeof(D.vals));
+            }
+        }
+        F.mcu_blocks = nb; F.n_blocks = nb * F.n_mcu;
+        F.coef_base = (long long)(per_i16 * (size_t)j);
+    }
+    const size_t up = files_bytes + tabs_bytes + total;
+    if ((rc = S->stream.reserve(up))) return rc;
+    if ((rc = S->exits.reserve((size_t)n_sub * 8))) return rc;
+    if ((rc = S->used.reserve((size_t)n_sub * 8))) return rc;
+    if ((rc = S->counts.reserve((size_t)n_sub * 4))) return rc;
+    if ((rc = S->first_block.reserve((size_t)n_sub * 8))) return rc;
+    if ((rc = S->changed.reserve(16))) return rc;
+    if ((rc = S->totals.reserve(16))) return rc;
+    if ((rc = S->dc_sums.reserve((size_t)n_slots * 4))) return rc;
+    if ((rc = S->dc_prefix.reserve((size_t)n_slots * 8))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(S->stream.p, S->pinned.p, up, cudaMemcpyHostToDevice, st));
+    const DevScan *files_dev = (const DevScan *)S->stream.p;
+    const DevHuff *tabs_dev = (const DevHuff *)((const uint8_t *)S->stream.p + files_bytes);
+    const uint8_t *stream_dev = (const uint8_t *)S->stream.p + files_bytes + tabs_bytes;
+    huff_rec *exits = S->exits.as<huff_rec>(), *used = S->used.as<huff_rec>();
+    const int grid = (n_sub + 127) / 128;
+    huff_sub_init_kernel<<<grid, 128, 0, st>>>(stream_dev, tabs_dev, files_dev, cn, n_sub, exits, used); LAUNCH_CHECK(ctx);
+    int *changed = S->changed.as<int>();
+    for (int pass = 0;; pass++) {
+        // every pass makes at least one more subsequence of each file final, so n_sub passes always suffice; in practice the
+        // decoders re-synchronise within one or two subsequences and a handful of passes are run
+        if (pass > n_sub + 1) { vfsms_set_error("jpeg: device entropy stage did not reach its fixed point"); return VFSMS_E_CUDA; }
+        CUDA_TRY(cudaMemsetAsync(changed, 0, 4, st));
+        for (int r = 0; r < 4; r++) {
+            huff_sub_sync_kernel<<<grid, 128, 0, st>>>(stream_dev, tabs_dev, files_dev, cn, n_sub, exits, used, changed); LAUNCH_CHECK(ctx);
+        }
+        // the flag covers the 4 passes; when the last one of them changed something a further (unchanged) round is needed
+        int flag = 0;
+        CUDA_TRY(cudaMemcpyAsync(&flag, changed, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (!flag) { ctx->entropy_passes = 4 * (pass + 1); break; }
+    }
+    huff_sub_count_kernel<<<(n_sub + 255) / 256, 256, 0, st>>>(exits, n_sub, S->counts.as<uint32_t>()); LAUNCH_CHECK(ctx);
+    if ((rc = exclusive_scan(ctx, S->partial, S->counts.as<uint32_t>(), n_sub, S->first_block.as<unsigned long long>(), S->totals.as<unsigned long long>(), st))) return rc;
+    {   // a stream that ends before its last block (truncated / damaged file): the host stage, which keeps decoding zero bits like
+        // libjpeg's warning path, defines the result for those -- tell the caller to use it for this chunk
+        std::vector<unsigned long long> fb((size_t)cn + 1);
+        for (int j = 0; j < cn; j++)
+            CUDA_TRY(cudaMemcpyAsync(&fb[j], S->first_block.as<unsigned long long>() + files[j].first_sub, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&fb[cn], S->totals.p, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (int j = 0; j < cn; j++) if (fb[j + 1] - fb[j] < (unsigned long long)files[j].n_blocks) return 1;
+    }
+    CUDA_TRY(cudaMemsetAsync(coef_dev, 0, per_i16 * 2 * (size_t)cn, st));
+    huff_sub_write_kernel<<<grid, 128, 0, st>>>(stream_dev, tabs_dev, files_dev, cn, n_sub, exits, S->first_block.as<unsigned long long>(), coef_dev);
+    LAUNCH_CHECK(ctx);
+    int max_slots = 0;
+    for (int j = 0; j < cn; j++) max_slots = std::max(max_slots, files[j].ncomp * files[j].n_mcu);
+    const dim3 dc_grid((unsigned)std::min((max_slots + 255) / 256, 1024), (unsigned)cn);
+    huff_dc_sums_kernel<<<dc_grid, 256, 0, st>>>(files_dev, cn, coef_dev, S->dc_sums.as<uint32_t>()); LAUNCH_CHECK(ctx);
+    if ((rc = exclusive_scan(ctx, S->partial, S->dc_sums.as<uint32_t>(), n_slots, S->dc_prefix.as<unsigned long long>(), S->totals.as<unsigned long long>() + 1, st))) return rc;
+    huff_dc_apply_kernel<<<dc_grid, 256, 0, st>>>(files_dev, cn, coef_dev, S->dc_prefix.as<unsigned long long>()); LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 // ---------------------------------------------------------------- device: dequantise + islow IDCT + range limit
 struct JpegQuant { uint16_t q[64]; };
 
@@ -552,9 +952,18 @@ static int jpeg_decode_batch(vfsms_ctx *ctx, int n, const uint8_t *const *data, 
     if ((rc = ctx->jpeg_coef.reserve(per * chunk))) return rc;
     if (channels == 3 && (rc = ctx->jpeg_planes.reserve(per_planes))) return rc;
     auto comp_blocks = [](const JpegHeader &h, int c) { return (size_t)(h.mcuy * h.comp[c].v) * (h.mcux * h.comp[c].h); };
+    // VFSMS_OPT_ENTROPY = 1: Huffman decoding on the device (files with restart intervals keep the host stage)
+    bool dev_entropy = ctx->entropy_mode == 1;
+    for (int i = 0; i < n; i++) dev_entropy = dev_entropy && H[i].restart_interval == 0;
     for (int c0 = 0; c0 < n; c0 += chunk) {
         const int cn = n - c0 < chunk ? n - c0 : chunk;
         CUDA_TRY(cudaStreamSynchronize(st));          // the previous chunk has left the pinned buffer
+        bool chunk_dev = dev_entropy;
+        if (chunk_dev) {
+            rc = jpeg_entropy_decode_device(ctx, cn, data + c0, sizes + c0, &H[c0], channels == 3, ctx->jpeg_coef.as<int16_t>(), per / 2, st);
+            if (rc < 0) return rc;
+            chunk_dev = rc == 0;
+        }
         std::atomic<int> next(0);
         auto work = [&]() {
             for (int j = next.fetch_add(1); j < cn; j = next.fetch_add(1)) {
@@ -565,16 +974,18 @@ static int jpeg_decode_batch(vfsms_ctx *ctx, int n, const uint8_t *const *data, 
                 jpeg_entropy_decode(data[c0 + j], sizes[c0 + j], h, dst);
             }
         };
-        std::vector<std::thread> pool;
-        for (int w = 1; w < (cn < workers ? cn : workers); w++) pool.emplace_back(work);
-        work();
-        for (auto &th : pool) th.join();
+        if (!chunk_dev) {
+            std::vector<std::thread> pool;
+            for (int w = 1; w < (cn < workers ? cn : workers); w++) pool.emplace_back(work);
+            work();
+            for (auto &th : pool) th.join();
+        }
         for (int j = 0; j < cn; j++) {
             const JpegHeader &h = H[c0 + j];
             const bool colour = channels == 3 && h.ncomp == 3;
             size_t blocks = comp_blocks(h, 0) + (colour ? 2 * comp_blocks(h, 1) : 0);
             int16_t *cdev = (int16_t *)((uint8_t *)ctx->jpeg_coef.p + per * j);
-            CUDA_TRY(cudaMemcpyAsync(cdev, (uint8_t *)ctx->jpeg_pinned.p + per * j, blocks * 128, cudaMemcpyHostToDevice, st));
+            if (!chunk_dev) CUDA_TRY(cudaMemcpyAsync(cdev, (uint8_t *)ctx->jpeg_pinned.p + per * j, blocks * 128, cudaMemcpyHostToDevice, st));
             uint8_t *dst = out_dev + (size_t)(c0 + j) * image_stride;
             if (channels == 1) {
                 if ((rc = launch_idct(ctx, cdev, h.quant[h.comp[0].tq], h.blocks_w, h.blocks_h, dst, rows, cols, row_stride, st))) return rc;
@@ -604,6 +1015,13 @@ static int jpeg_decode_batch(vfsms_ctx *ctx, int n, const uint8_t *const *data, 
             // the plane scratch is shared by the files of the batch: stream order keeps the next IDCT behind this kernel
         }
     }
+    return 0;
+}
+
+extern "C" int vfsms_jpeg_last_entropy_passes(vfsms_ctx *ctx, int *passes_out)
+{
+    if (!ctx || !passes_out) { vfsms_set_error("vfsms_jpeg_last_entropy_passes: bad arguments"); return VFSMS_E_ARG; }
+    *passes_out = ctx->entropy_passes;
     return 0;
 }
 

@@ -15,6 +15,7 @@
 //   stuff        0xFF -> 0xFF 0x00: count per 16 bytes, scan, scatter; final byte padded with one-bits (jchuff.c flush_bits)
 // Only the compressed stream crosses PCIe.  The host writes the markers (jcmarker.c order) around it.
 #include "common.cuh"
+#include "scan.cuh"
 #include <string.h>
 
 #define ENC_BLOCKS_PER_CTA 32
@@ -330,84 +331,6 @@ __global__ void __launch_bounds__(256) jpeg_emit_kernel(const int16_t *__restric
     sink.flush();
 }
 
-// ---------------------------------------------------------------- exclusive scan u32 -> u64 (three passes, no inter-CTA waiting)
-#define SCAN_THREADS 256
-#define SCAN_PER_THREAD 8
-#define SCAN_TILE (SCAN_THREADS * SCAN_PER_THREAD)
-
-__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long *s_warp, unsigned long long &block_total)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long up = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += up;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    unsigned long long before = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; w++) { const unsigned long long x = s_warp[w]; if (w < warp) before += x; total += x; }
-    __syncthreads();
-    block_total = total;
-    return before + inc - v;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) scan_partials_kernel(const uint32_t *__restrict__ in, long long n, unsigned long long *__restrict__ partial)
-{
-    __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
-    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_PER_THREAD;
-    unsigned long long v = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_PER_THREAD; k++) if (base + k < n) v += in[base + k];
-    unsigned long long total;
-    block_exclusive_scan(v, s_warp, total);
-    if (threadIdx.x == 0) partial[blockIdx.x] = total;
-}
-
-// one CTA: partial[] -> exclusive prefix in place, grand total to *total
-__global__ void __launch_bounds__(SCAN_THREADS) scan_spine_kernel(unsigned long long *partial, int n_tiles, unsigned long long *total)
-{
-    __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
-    unsigned long long carry = 0;
-    for (int base = 0; base < n_tiles; base += SCAN_THREADS) {
-        const int i = base + threadIdx.x;
-        const unsigned long long v = i < n_tiles ? partial[i] : 0;
-        unsigned long long chunk_total;
-        const unsigned long long ex = block_exclusive_scan(v, s_warp, chunk_total);
-        if (i < n_tiles) partial[i] = carry + ex;
-        carry += chunk_total;
-    }
-    if (threadIdx.x == 0) *total = carry;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) scan_final_kernel(const uint32_t *__restrict__ in, long long n, const unsigned long long *__restrict__ partial,
-                                                                  unsigned long long *__restrict__ out)
-{
-    __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
-    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_PER_THREAD;
-    uint32_t x[SCAN_PER_THREAD];
-    unsigned long long v = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_PER_THREAD; k++) { x[k] = base + k < n ? in[base + k] : 0; v += x[k]; }
-    unsigned long long total;
-    unsigned long long run = partial[blockIdx.x] + block_exclusive_scan(v, s_warp, total);
-#pragma unroll
-    for (int k = 0; k < SCAN_PER_THREAD; k++) { if (base + k < n) out[base + k] = run; run += x[k]; }
-}
-
-static int exclusive_scan(vfsms_ctx *ctx, EncState *s, const uint32_t *in, long long n, unsigned long long *out, unsigned long long *total_dev, cudaStream_t st)
-{
-    const int n_tiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
-    int rc;
-    if ((rc = s->partial.reserve((size_t)n_tiles * 8))) return rc;
-    scan_partials_kernel<<<n_tiles, SCAN_THREADS, 0, st>>>(in, n, s->partial.as<unsigned long long>()); LAUNCH_CHECK(ctx);
-    scan_spine_kernel<<<1, SCAN_THREADS, 0, st>>>(s->partial.as<unsigned long long>(), n_tiles, total_dev); LAUNCH_CHECK(ctx);
-    scan_final_kernel<<<n_tiles, SCAN_THREADS, 0, st>>>(in, n, s->partial.as<unsigned long long>(), out); LAUNCH_CHECK(ctx);
-    return 0;
-}
-
 // ---------------------------------------------------------------- byte stuffing
 __device__ __forceinline__ uint32_t stream_byte(const uint32_t *__restrict__ words, long long i, long long n_bytes, int pad_bits)
 {
@@ -516,7 +439,7 @@ static int jpeg_encode_device_image(vfsms_ctx *ctx, const uint8_t *img_dev, int 
     jpeg_fdct_quant_kernel<<<(int)((n_blocks + ENC_BLOCKS_PER_CTA - 1) / ENC_BLOCKS_PER_CTA), ENC_BLOCKS_PER_CTA * 8, 0, st>>>(img_dev, G, coef);
     LAUNCH_CHECK(ctx);
     jpeg_block_bits_kernel<<<grid_b, 256, 0, st>>>(coef, G, s->bits.as<uint32_t>()); LAUNCH_CHECK(ctx);
-    if ((rc = exclusive_scan(ctx, s, s->bits.as<uint32_t>(), n_blocks, s->offs.as<unsigned long long>(), totals, st))) return rc;
+    if ((rc = exclusive_scan(ctx, s->partial, s->bits.as<uint32_t>(), n_blocks, s->offs.as<unsigned long long>(), totals, st))) return rc;
     unsigned long long total_bits = 0;
     CUDA_TRY(cudaMemcpyAsync(&total_bits, totals, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -533,7 +456,7 @@ static int jpeg_encode_device_image(vfsms_ctx *ctx, const uint8_t *img_dev, int 
     if ((rc = s->offs2.reserve((size_t)n16 * 8))) return rc;
     const int grid_s = (int)((n16 + 255) / 256);
     jpeg_stuff_count_kernel<<<grid_s, 256, 0, st>>>(s->stream.as<uint32_t>(), n_bytes, pad_bits, s->counts.as<uint32_t>()); LAUNCH_CHECK(ctx);
-    if ((rc = exclusive_scan(ctx, s, s->counts.as<uint32_t>(), n16, s->offs2.as<unsigned long long>(), totals + 1, st))) return rc;
+    if ((rc = exclusive_scan(ctx, s->partial, s->counts.as<uint32_t>(), n16, s->offs2.as<unsigned long long>(), totals + 1, st))) return rc;
     unsigned long long n_ff = 0;
     CUDA_TRY(cudaMemcpyAsync(&n_ff, totals + 1, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

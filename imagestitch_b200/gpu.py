@@ -306,7 +306,7 @@ def set_matcher(mode, device=0):
     check(_lib.load().vfsms_set_matcher(_lib.context(device), {"tc": 0, "simt": 1, "tc_1sm": 2}[mode]), "vfsms_set_matcher")
 
 
-OPTIONS = {"describe": 0, "sort": 1, "lpt": 2}      # include/vfsms.h VFSMS_OPT_*
+OPTIONS = {"describe": 0, "sort": 1, "lpt": 2, "entropy": 3}      # include/vfsms.h VFSMS_OPT_*
 
 
 def set_option(name, value, device=0):
@@ -443,6 +443,13 @@ def jpeg_decode_bgr(datas, device=0):
     _jpeg_check(_lib.load().vfsms_jpeg_decode_bgr_host(_lib.context(device), len(bufs), ptrs, sizes, out.ctypes.data_as(ctypes.c_void_p), rows, cols),
                 "vfsms_jpeg_decode_bgr_host")
     return out[0] if single else out
+
+
+def jpeg_last_entropy_passes(device=0):
+    """Synchronisation passes of the last device entropy decode (option "entropy" = 1)."""
+    n = ctypes.c_int(0)
+    check(_lib.load().vfsms_jpeg_last_entropy_passes(_lib.context(device), ctypes.byref(n)), "vfsms_jpeg_last_entropy_passes")
+    return n.value
 
 
 def jpeg_encode(image, quality=95, device=0):

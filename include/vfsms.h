@@ -92,6 +92,9 @@ enum {
                                    * candidates, 1 = one CTA per image: shared-memory bitonic sort of 64-bit keys + tie fix-up */
     VFSMS_OPT_DESCRIBE_LPT = 2,   /* "lpt": 0 (default) = keypoints described in response order, 1 = windows of 128 px and more
                                    * first (two passes over the work list), so that no giant window is met at the end of the launch */
+    VFSMS_OPT_ENTROPY = 3,        /* "entropy": Huffman decoding of JPEG tiles.  0 (default) = host threads, one file each; 1 = on the
+                                   * device: self-synchronising parallel decode of 1024-bit subsequences (files with restart
+                                   * intervals keep the host stage); same coefficients, symbol for symbol */
     VFSMS_OPT_COUNT
 };
 int vfsms_set_option(vfsms_ctx *ctx, int option, int value);
@@ -261,6 +264,10 @@ int vfsms_jpeg_decode_bgr_dev(vfsms_ctx *ctx, int n_images, const uint8_t *const
                               uint8_t *out_dev, int rows, int cols, int64_t row_stride, int64_t image_stride, void *stream);
 int vfsms_jpeg_decode_bgr_host(vfsms_ctx *ctx, int n_images, const uint8_t *const *data, const size_t *sizes,
                                uint8_t *out, int rows, int cols);
+
+/* Diagnostic of VFSMS_OPT_ENTROPY = 1: synchronisation passes the last device entropy decode ran (multiple of 4; the last 4 changed
+ * nothing).  Small numbers mean the subsequence decoders re-synchronised quickly. */
+int vfsms_jpeg_last_entropy_passes(vfsms_ctx *ctx, int *passes_out);
 
 /* ---------------------------------------------------------------- JPEG output encode
  * Replace `cv2.imwrite(outputAddress + ..., stitchImage)` for .jpg outputs (Stitcher.py:130-131, :196-197): baseline JPEG with

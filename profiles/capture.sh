@@ -26,7 +26,7 @@ OPTS=$(python - <<PY
 import json
 try:
     v = json.load(open("$OUT/${TAG}_bench.json"))["config"]["kernel_variants"]
-    d = {"describe": 1, "sort": 0, "lpt": 0}
+    d = {"describe": 1, "sort": 0, "lpt": 0, "entropy": 0}
     print(" ".join("--opt %s=%d" % (k, x) for k, x in v.items() if d.get(k) != x))
 except Exception:
     print("")

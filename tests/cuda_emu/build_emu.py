@@ -112,6 +112,17 @@ def build(force=False, verbose=False):
     common += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
     common.append(os.path.join(ROOT, "include", "vfsms.h"))
     jobs, objs = [], []
+    # headers that launch kernels are translated too; the generated sources live in OUT_DIR, so their `#include "x.cuh"` finds the copy
+    for name in os.listdir(CSRC):
+        if name.endswith(".cuh"):
+            with open(os.path.join(CSRC, name)) as f:
+                text = f.read()
+            if "<<<" in text:
+                gen = os.path.join(OUT_DIR, name)
+                body = '#line 1 "%s"\n' % os.path.join(CSRC, name) + translate(text)
+                if not os.path.exists(gen) or open(gen).read() != body:
+                    with open(gen, "w") as f:
+                        f.write(body)
     for unit in UNITS:
         src = os.path.join(CSRC, unit)
         gen = os.path.join(OUT_DIR, unit.replace(".cu", "_emu.cpp"))

@@ -17,7 +17,7 @@ def gpu():
     assert g.device_count() > 0
     yield g
     for name in g.OPTIONS:
-        g.set_option(name, {"describe": 1, "sort": 0, "lpt": 0}[name])
+        g.set_option(name, {"describe": 1, "sort": 0, "lpt": 0, "entropy": 0}[name])
 
 
 def _surf_both(gpu, img, option, values, **kw):

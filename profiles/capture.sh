@@ -43,4 +43,7 @@ timeout -s KILL 300 python scripts/bench_encode.py > $OUT/${TAG}_bench_encode.js
 timeout -s KILL 300 python scripts/bench_encode.py --gray >> $OUT/${TAG}_bench_encode.json 2>> $OUT/${TAG}_bench_encode.err
 timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:"jpeg_fdct_quant|jpeg_block_bits|jpeg_emit|jpeg_stuff|scan_" \
     -s 9 -c 9 -o $OUT/${TAG}_encode_full python scripts/bench_encode.py --rows 4096 --cols 4096 --reps 1 > $OUT/${TAG}_ncu_encode.log 2>&1
+# 5. the whole reference workflow (files in -> file out) with Main.py's settings: host entropy stage, then device entropy
+timeout -s KILL 400 python scripts/bench_sequence.py --rows 3 --cols 4 > $OUT/${TAG}_bench_sequence.json 2> $OUT/${TAG}_bench_sequence.err
+timeout -s KILL 300 python scripts/bench_sequence.py --rows 3 --cols 4 --options entropy=1 --cpu-pairs 0 >> $OUT/${TAG}_bench_sequence.json 2>> $OUT/${TAG}_bench_sequence.err
 ls -la $OUT | tail -14

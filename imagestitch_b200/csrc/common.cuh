@@ -163,7 +163,7 @@ struct vfsms_ctx {
     void *blend_state = nullptr;
     void *orb_state = nullptr;
     int entropy_mode = 0;          // JPEG entropy decoding: 0 host threads, 1 on the device (vfsms_set_option VFSMS_OPT_ENTROPY)
-    int entropy_passes = 0;        // synchronisation passes of the last device entropy decode (4 per host round trip)
+    int entropy_passes = 0;        // synchronisation passes of the last device entropy decode
     void *jpeg_huff_state = nullptr;  // workspaces of the device entropy decoder (jpeg.cu)
     void *jpeg_enc_state = nullptr;   // coefficient / bit-stream workspaces of the JPEG encoder (jpeg_enc.cu)
 };

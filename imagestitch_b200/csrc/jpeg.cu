@@ -656,19 +656,21 @@ static int jpeg_entropy_decode_device(vfsms_ctx *ctx, int cn, const uint8_t *con
     const int grid = (n_sub + 127) / 128;
     huff_sub_init_kernel<<<grid, 128, 0, st>>>(stream_dev, tabs_dev, files_dev, cn, n_sub, exits, used); LAUNCH_CHECK(ctx);
     int *changed = S->changed.as<int>();
-    for (int pass = 0;; pass++) {
-        // every pass makes at least one more subsequence of each file final, so n_sub passes always suffice; in practice the
-        // decoders re-synchronise within one or two subsequences and a handful of passes are run
-        if (pass > n_sub + 1) { vfsms_set_error("jpeg: device entropy stage did not reach its fixed point"); return VFSMS_E_CUDA; }
+    // Every pass makes at least one more subsequence of each file final, so n_sub passes always suffice; in practice the decoders
+    // re-synchronise within a few subsequences.  Passes are launched in rounds (4, 8, 16, 32, 32, ...) with one flag read-back per
+    // round: the round in which no thread changed its exit is the fixed point.
+    for (int done = 0, per_round = 4;;) {
+        if (done > n_sub + 64) { vfsms_set_error("jpeg: device entropy stage did not reach its fixed point"); return VFSMS_E_CUDA; }
         CUDA_TRY(cudaMemsetAsync(changed, 0, 4, st));
-        for (int r = 0; r < 4; r++) {
+        for (int r = 0; r < per_round; r++) {
             huff_sub_sync_kernel<<<grid, 128, 0, st>>>(stream_dev, tabs_dev, files_dev, cn, n_sub, exits, used, changed); LAUNCH_CHECK(ctx);
         }
-        // the flag covers the 4 passes; when the last one of them changed something a further (unchanged) round is needed
         int flag = 0;
         CUDA_TRY(cudaMemcpyAsync(&flag, changed, 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        if (!flag) { ctx->entropy_passes = 4 * (pass + 1); break; }
+        done += per_round;
+        if (!flag) { ctx->entropy_passes = done; break; }
+        if (per_round < 32) per_round *= 2;
     }
     huff_sub_count_kernel<<<(n_sub + 255) / 256, 256, 0, st>>>(exits, n_sub, S->counts.as<uint32_t>()); LAUNCH_CHECK(ctx);
     if ((rc = exclusive_scan(ctx, S->partial, S->counts.as<uint32_t>(), n_sub, S->first_block.as<unsigned long long>(), S->totals.as<unsigned long long>(), st))) return rc;

@@ -265,8 +265,8 @@ int vfsms_jpeg_decode_bgr_dev(vfsms_ctx *ctx, int n_images, const uint8_t *const
 int vfsms_jpeg_decode_bgr_host(vfsms_ctx *ctx, int n_images, const uint8_t *const *data, const size_t *sizes,
                                uint8_t *out, int rows, int cols);
 
-/* Diagnostic of VFSMS_OPT_ENTROPY = 1: synchronisation passes the last device entropy decode ran (multiple of 4; the last 4 changed
- * nothing).  Small numbers mean the subsequence decoders re-synchronised quickly. */
+/* Diagnostic of VFSMS_OPT_ENTROPY = 1: synchronisation passes the last device entropy decode ran (launched in rounds of 4, 8, 16, 32,
+ * ...; the last round changed nothing).  Small numbers mean the subsequence decoders re-synchronised quickly. */
 int vfsms_jpeg_last_entropy_passes(vfsms_ctx *ctx, int *passes_out);
 
 /* ---------------------------------------------------------------- JPEG output encode

@@ -100,3 +100,17 @@ def test_large_tile_batch(gpu):
     for k, f in enumerate(files):
         assert np.array_equal(out[k], cv2.imdecode(f, cv2.IMREAD_GRAYSCALE)), k
     assert gpu.jpeg_last_entropy_passes() <= 64
+
+
+def test_golden_reference_tiles(gpu, golden_dir):
+    """two of the reference's demo micrographs (camera / microscope software encoders, not cv2's): SHA-256 of cv2's decode"""
+    import hashlib
+    import json
+    import os
+    cases = json.load(open(os.path.join(golden_dir, "jpeg_cases.json")))
+    for name, c in cases.items():
+        if name.startswith("_"):
+            continue
+        data = np.fromfile(os.path.join(golden_dir, name), np.uint8).tobytes()
+        assert hashlib.sha256(gpu.jpeg_decode_gray(data).tobytes()).hexdigest() == c["sha256_of_cv2_imdecode_gray"], name
+        assert hashlib.sha256(gpu.jpeg_decode_bgr(data).tobytes()).hexdigest() == c["sha256_of_cv2_imdecode_color"], name

@@ -17,8 +17,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "imagestitch_b200", "csrc")
 # VFSMS_EMU_SANITIZE=1: AddressSanitizer build in its own directory (run python with LD_PRELOAD=$(g++ -print-file-name=libasan.so))
-SANITIZE = os.environ.get("VFSMS_EMU_SANITIZE") == "1"
-OUT_DIR = os.path.join(HERE, "_build", "asan") if SANITIZE else os.path.join(HERE, "_build")
+# VFSMS_EMU_SANITIZE=thread: ThreadSanitizer build (LD_PRELOAD libtsan.so, TSAN_OPTIONS=suppressions=tests/cuda_emu/tsan.supp): racecheck
+SANITIZE = os.environ.get("VFSMS_EMU_SANITIZE") in ("1", "thread")
+TSAN = os.environ.get("VFSMS_EMU_SANITIZE") == "thread"
+OUT_DIR = os.path.join(HERE, "_build", "tsan" if TSAN else "asan") if SANITIZE else os.path.join(HERE, "_build")
 OUT = os.path.join(OUT_DIR, "libvfsms_emu.so")
 UNITS = ["surf.cu", "match.cu", "phase.cu", "blend.cu", "orb.cu", "enhance.cu", "jpeg.cu", "jpeg_enc.cu", "capi.cu"]
 CXX = os.environ.get("VFSMS_EMU_CXX") or ("/usr/bin/g++" if SANITIZE and os.path.exists("/usr/bin/g++") else os.environ.get("CXX", "g++"))
@@ -26,7 +28,7 @@ CXX = os.environ.get("VFSMS_EMU_CXX") or ("/usr/bin/g++" if SANITIZE and os.path
 FLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-w", "-pthread",
          "-I/usr/local/cuda/include", "-I" + CSRC, "-include", os.path.join(HERE, "emu.h")]
 if SANITIZE:
-    FLAGS += ["-fsanitize=address", "-fno-omit-frame-pointer"]
+    FLAGS += ["-fsanitize=thread" if TSAN else "-fsanitize=address", "-fno-omit-frame-pointer"]
 
 
 def _match_back(text, pos):
@@ -140,7 +142,8 @@ def build(force=False, verbose=False):
     emu_obj = os.path.join(OUT_DIR, "emu.o")
     objs.append(emu_obj)
     if force or _stale(emu_obj, [os.path.join(HERE, "emu.cpp")] + common):
-        cmd = [CXX] + FLAGS + ["-c", os.path.join(HERE, "emu.cpp"), "-o", emu_obj]
+        emu_flags = [f for f in FLAGS if f != "-fsanitize=thread"] + (["-DEMU_FORCE_TSAN"] if TSAN else [])
+        cmd = [CXX] + emu_flags + ["-c", os.path.join(HERE, "emu.cpp"), "-o", emu_obj]
         jobs.append(("emu.cpp", subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     for unit, p in jobs:
         out, _ = p.communicate()
@@ -148,12 +151,31 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode()[-20000:])
             raise RuntimeError("g++ failed on %s (emulated build)" % unit)
     if force or jobs or _stale(OUT, objs):
-        cmd = [CXX, "-shared", "-o", OUT] + objs + ["-pthread"] + (["-fsanitize=address"] if SANITIZE else ["-Wl,--no-undefined"])
+        cmd = [CXX, "-shared", "-o", OUT] + objs + ["-pthread"] + (["-fsanitize=thread" if TSAN else "-fsanitize=address"] if SANITIZE else ["-Wl,--no-undefined"])
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
     return OUT
 
 
+def build_selftest():
+    """selftest.cu (controls of the execution model and of the racecheck) as a standalone executable in OUT_DIR."""
+    os.makedirs(OUT_DIR, exist_ok=True)
+    gen = os.path.join(OUT_DIR, "selftest_emu.cpp")
+    with open(os.path.join(HERE, "selftest.cu")) as f:
+        body = translate(f.read())
+    with open(gen, "w") as f:
+        f.write(body)
+    exe = os.path.join(OUT_DIR, "selftest")
+    emu_o = os.path.join(OUT_DIR, "emu_standalone.o")
+    emu_flags = [f for f in FLAGS if f != "-fsanitize=thread"] + (["-DEMU_FORCE_TSAN"] if TSAN else [])
+    subprocess.check_call([CXX] + emu_flags + ["-DEMU_STANDALONE", "-c", os.path.join(HERE, "emu.cpp"), "-o", emu_o])
+    subprocess.check_call([CXX] + FLAGS + [gen, emu_o, "-o", exe])
+    return exe
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--selftest" in sys.argv:
+        print(build_selftest())
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

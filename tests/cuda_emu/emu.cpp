@@ -7,7 +7,9 @@
 #include <map>
 #include <vector>
 
+#ifndef EMU_STANDALONE
 #include "../../imagestitch_b200/csrc/common.cuh"
+#endif
 
 uint3 threadIdx, blockIdx;
 dim3 blockDim, gridDim;
@@ -49,12 +51,33 @@ emu_switch:
 #define EMU_ASAN 0
 #endif
 
+// ThreadSanitizer build (VFSMS_EMU_SANITIZE=thread): every CUDA thread of a block is a TSan fiber; switches create NO
+// happens-before edge, only __syncthreads / warp collectives (release + acquire on a per-block / per-warp token) and the block and
+// launch boundaries do.  Accesses of two threads of a block to the same shared or global word with no barrier between them are then
+// reported although the emulation runs them one after the other -- compute-sanitizer's racecheck, for intra-block races.  Blocks are
+// ordered one after the other (inter-block races are not modelled).
+// emu.cpp itself is compiled WITHOUT -fsanitize=thread (-DEMU_FORCE_TSAN instead): the scheduler's own bookkeeping is then invisible to
+// the detector, only the kernels' accesses are checked.
+#if defined(__SANITIZE_THREAD__) || defined(EMU_FORCE_TSAN)
+#include <sanitizer/tsan_interface.h>
+#define EMU_TSAN 1
+#else
+#define EMU_TSAN 0
+#endif
+
 namespace emu {
 
 enum { RUN = 0, AT_BLOCK = 1, AT_WARP = 2, DONE = 3 };
 struct Fiber { void *sp; int state; uint3 tid; uint64_t slot; void *fake; };
 static const void *sched_bottom = nullptr;
 static size_t sched_size = 0;
+#if EMU_TSAN
+static void *tsan_fibers[1024];
+static void *tsan_sched = nullptr;
+// launch token: released by the scheduler before a block, acquired by every thread at its start; done token: released by every thread
+// at its end, acquired by the scheduler after the block (two tokens: a thread's end must not order the next thread's start)
+static char tsan_block_token, tsan_launch_token, tsan_done_token, tsan_warp_token[32];
+#endif
 
 static const size_t STACK_BYTES = 512 << 10;
 static const int MAX_THREADS = 1024;
@@ -71,7 +94,14 @@ static void fiber_main()
 #if EMU_ASAN
     __sanitizer_finish_switch_fiber(nullptr, &sched_bottom, &sched_size);
 #endif
+#if EMU_TSAN
+    __tsan_acquire(&tsan_launch_token);       // everything before this block (host code, earlier blocks) happened before
+#endif
     (*cur_body)();
+#if EMU_TSAN
+    __tsan_release(&tsan_done_token);
+    __tsan_switch_to_fiber(tsan_sched, __tsan_switch_to_fiber_no_sync);
+#endif
     fibers[cur].state = DONE;
     void *dummy;
 #if EMU_ASAN
@@ -94,12 +124,20 @@ static void yield(int state)
 {
     Fiber &f = fibers[cur];
     f.state = state;
+#if EMU_TSAN
+    char *token = state == AT_BLOCK ? &tsan_block_token : &tsan_warp_token[cur >> 5];
+    __tsan_release(token);                    // all lanes arrive (release) before any of them leaves (acquire)
+    __tsan_switch_to_fiber(tsan_sched, __tsan_switch_to_fiber_no_sync);
+#endif
 #if EMU_ASAN
     __sanitizer_start_switch_fiber(&f.fake, sched_bottom, sched_size);
 #endif
     emu_switch(&f.sp, sched_sp);
 #if EMU_ASAN
     __sanitizer_finish_switch_fiber(f.fake, &sched_bottom, &sched_size);
+#endif
+#if EMU_TSAN
+    __tsan_acquire(token);
 #endif
 }
 
@@ -118,6 +156,9 @@ static void run_fiber(int t)
 {
     cur = t;
     threadIdx = fibers[t].tid;
+#if EMU_TSAN
+    __tsan_switch_to_fiber(tsan_fibers[t], __tsan_switch_to_fiber_no_sync);
+#endif
 #if EMU_ASAN
     void *fake = nullptr;
     __sanitizer_start_switch_fiber(&fake, stacks + (size_t)t * STACK_BYTES + 4096, STACK_BYTES - 4096);
@@ -134,6 +175,11 @@ static void run_block(const std::function<void()> &body)
     n_threads = (int)(blockDim.x * blockDim.y * blockDim.z);
     if (n_threads > MAX_THREADS || n_threads <= 0) { fprintf(stderr, "emu: block of %d threads\n", n_threads); abort(); }
     cur_body = &body;
+#if EMU_TSAN
+    if (!tsan_sched) tsan_sched = __tsan_get_current_fiber();
+    for (int t = 0; t < n_threads; t++) if (!tsan_fibers[t]) tsan_fibers[t] = __tsan_create_fiber(0);
+    __tsan_release(&tsan_launch_token);
+#endif
     for (int t = 0; t < n_threads; t++) {
         Fiber &f = fibers[t];
         uint64_t *sp = (uint64_t *)(stacks + (size_t)(t + 1) * STACK_BYTES);
@@ -176,6 +222,9 @@ static void run_block(const std::function<void()> &body)
             abort();
         }
     }
+#if EMU_TSAN
+    __tsan_acquire(&tsan_done_token);         // the host (and, through the launch token, the next block) see everything this block did
+#endif
 }
 
 static cudaError_t last_error = cudaSuccess;
@@ -368,8 +417,10 @@ cufftResult cufftExecZ2D(cufftHandle h, cufftDoubleComplex *in, cufftDoubleReal 
 }   // extern "C"
 
 // ---------------------------------------------------------------- the tensor-core matcher is inline PTX: not emulated
+#ifndef EMU_STANDALONE
 int match_tc_batch(vfsms_ctx *, const float *, const int32_t *, int, const float *, const int32_t *, int, int, int, int, int32_t *, float *, cudaStream_t)
 {
     vfsms_set_error("cuda_emu: match_tc.cu (tcgen05 / TMA inline PTX) is not emulated; select the exact SIMT matcher with vfsms_set_matcher(ctx, 1)");
     return VFSMS_E_UNSUPPORTED;
 }
+#endif

@@ -83,13 +83,19 @@ static inline unsigned __ballot_sync(unsigned, int pred)
 static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
 
 // ---------------------------------------------------------------- atomics (one OS thread: plain read-modify-write)
-template <class T, class U> static inline T atomicAdd(T *p, U v) { T o = *p; *p = (T)(o + (T)v); return o; }
-template <class T, class U> static inline T atomicMin(T *p, U v) { T o = *p; if ((T)v < o) *p = (T)v; return o; }
-template <class T, class U> static inline T atomicMax(T *p, U v) { T o = *p; if ((T)v > o) *p = (T)v; return o; }
-template <class T, class U> static inline T atomicOr(T *p, U v) { T o = *p; *p = (T)(o | (T)v); return o; }
-template <class T, class U> static inline T atomicExch(T *p, U v) { T o = *p; *p = (T)v; return o; }
-template <class T, class U, class V> static inline T atomicCAS(T *p, U cmp, V v) { T o = *p; if (o == (T)cmp) *p = (T)v; return o; }
-template <class T> static inline unsigned atomicInc(T *p, unsigned lim) { unsigned o = *p; *p = o >= lim ? 0 : o + 1; return o; }
+// (relaxed __atomic builtins: the same plain read-modify-write for one OS thread, but ThreadSanitizer knows they are atomics)
+template <class T> struct emu_atomic_int { typedef T type; };
+template <> struct emu_atomic_int<float> { typedef unsigned type; };
+template <> struct emu_atomic_int<double> { typedef unsigned long long type; };
+template <class T> static inline T emu_aload(T *p) { typename emu_atomic_int<T>::type b = __atomic_load_n((typename emu_atomic_int<T>::type *)p, __ATOMIC_RELAXED); T v; memcpy(&v, &b, sizeof(T)); return v; }
+template <class T> static inline void emu_astore(T *p, T v) { typename emu_atomic_int<T>::type b; memcpy(&b, &v, sizeof(T)); __atomic_store_n((typename emu_atomic_int<T>::type *)p, b, __ATOMIC_RELAXED); }
+template <class T, class U> static inline T atomicAdd(T *p, U v) { T o = emu_aload(p); emu_astore(p, (T)(o + (T)v)); return o; }
+template <class T, class U> static inline T atomicMin(T *p, U v) { T o = emu_aload(p); if ((T)v < o) emu_astore(p, (T)v); return o; }
+template <class T, class U> static inline T atomicMax(T *p, U v) { T o = emu_aload(p); if ((T)v > o) emu_astore(p, (T)v); return o; }
+template <class T, class U> static inline T atomicOr(T *p, U v) { T o = emu_aload(p); emu_astore(p, (T)(o | (T)v)); return o; }
+template <class T, class U> static inline T atomicExch(T *p, U v) { T o = emu_aload(p); emu_astore(p, (T)v); return o; }
+template <class T, class U, class V> static inline T atomicCAS(T *p, U cmp, V v) { T o = emu_aload(p); if (o == (T)cmp) emu_astore(p, (T)v); return o; }
+template <class T> static inline unsigned atomicInc(T *p, unsigned lim) { unsigned o = emu_aload(p); emu_astore(p, (T)(o >= lim ? 0 : o + 1)); return o; }
 
 // ---------------------------------------------------------------- intrinsics
 template <class T> static inline T __ldg(const T *p) { return *p; }

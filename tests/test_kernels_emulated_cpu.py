@@ -81,6 +81,40 @@ def test_stacked_texture_groups_on_emulated_kernels(emu_lib):
         assert rc == 0 and passed == 1, out[-6000:]
 
 
+def _tsan_runtime():
+    for cxx in ("/usr/bin/g++", "g++"):
+        try:
+            p = subprocess.run([cxx, "-print-file-name=libtsan.so"], stdout=subprocess.PIPE).stdout.decode().strip()
+        except OSError:
+            continue
+        if os.path.isabs(p) and os.path.exists(p):
+            return p
+    return None
+
+
+def test_racecheck_controls_and_kernels():
+    """ThreadSanitizer build of the emulation: CUDA threads are TSan fibers ordered only by barriers / warp collectives.  The controls
+    prove the detector works (a missing __syncthreads and a missing __syncwarp are reported, the synchronised version is not), then
+    small inputs go through every kernel family: no intra-block race."""
+    tsan = _tsan_runtime()
+    if tsan is None:
+        pytest.skip("no libtsan.so for the system g++")
+    env = dict(os.environ, VFSMS_EMU_SANITIZE="thread", PYTHONPATH=ROOT)
+    builder = os.path.join(EMU_DIR, "build_emu.py")
+    exe = subprocess.run([sys.executable, builder, "--selftest"], env=env, stdout=subprocess.PIPE, check=True).stdout.decode().split()[-1]
+    subprocess.run([sys.executable, builder], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    opts = "suppressions=%s:exitcode=0:report_signal_unsafe=0" % os.path.join(EMU_DIR, "tsan.supp")
+    run_env = dict(env, TSAN_OPTIONS=opts)
+    for what, racy in (("clean", False), ("racy", True), ("racy_warp", True)):
+        p = subprocess.run([exe, what], env=run_env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+        assert p.returncode == 0 and b"finished" in p.stdout, (what, p.stdout, p.stderr[-2000:])
+        assert (p.stderr.count(b"WARNING: ThreadSanitizer: data race") > 0) == racy, (what, p.stderr[-3000:])
+    p = subprocess.run([sys.executable, os.path.join(EMU_DIR, "racecheck.py")], env=dict(run_env, LD_PRELOAD=tsan), cwd=ROOT,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1500)
+    assert p.returncode == 0 and b"racecheck done" in p.stdout, (p.stdout[-2000:], p.stderr[-3000:])
+    assert p.stderr.count(b"WARNING: ThreadSanitizer") == 0, p.stderr[-6000:].decode(errors="replace")
+
+
 @pytest.mark.skipif(os.environ.get("VFSMS_EMU_FULL") != "1", reason="set VFSMS_EMU_FULL=1 (about 10 minutes)")
 def test_all_emulable_gpu_tests(emu_lib):
     rc, passed, out = _run(["tests"], None)

@@ -991,7 +991,9 @@ struct __align__(16) WarpScratch {
 // MODE 0: LDG sampler, 1: one texture per image (handles in `texs`), 2: one stacked texture (`tex_stack`, a kernel parameter)
 // over the images [b_first, b_first + b_count) -- this launch describes only their keypoints.
 // UNROLL / MINB: unroll factor of the border-free sampling loop and CTAs per SM the register budget is cut for (4 -> 64
-// registers, 3 -> 80): with no branch in the loop, a deeper unroll lets several gathers be in flight per warp.
+// registers, 3 -> 80, 5 -> 48): with no branch in the loop, a deeper unroll lets several gathers be in flight per warp; more
+// resident warps hide the gather latency the other way (ncu, 4 CTAs: 47 % warps active, 37 % of the stalls on the gather; with
+// 48 registers ptxas spills 72 bytes, all outside the sampling loops).
 template <int MODE, int UNROLL = 2, int MINB = 4>
 __global__ void __launch_bounds__(WK_WARPS * 32, MINB) orient_describe_warp_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
@@ -1831,7 +1833,9 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
                 const int nb = std::min(per, batch - c * per);
                 if (ctx->describe_mode == 2) LAUNCH_WK_(2, 2, 4, work_counter + 4 + c, ts[c], c * per, nb);
                 else if (ctx->describe_mode == 3) LAUNCH_WK_(2, 4, 4, work_counter + 4 + c, ts[c], c * per, nb);
-                else LAUNCH_WK_(2, 4, 3, work_counter + 4 + c, ts[c], c * per, nb);
+                else if (ctx->describe_mode == 4) LAUNCH_WK_(2, 4, 3, work_counter + 4 + c, ts[c], c * per, nb);
+                else if (ctx->describe_mode == 5) LAUNCH_WK_(2, 2, 5, work_counter + 4 + c, ts[c], c * per, nb);   // 48 registers: 5 CTAs / SM
+                else LAUNCH_WK_(2, 1, 5, work_counter + 4 + c, ts[c], c * per, nb);
                 LAUNCH_CHECK(ctx);
             }
         }

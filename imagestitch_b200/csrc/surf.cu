@@ -953,6 +953,25 @@ __device__ __forceinline__ float window_pixel_stack(cudaTextureObject_t tex, con
     return (float)img[(size_t)y * stride + x];
 }
 
+// FIXED-POINT variant (describe modes 7 / 8) for windows that lie inside the image: the sample position in 32.32 fixed point.
+// The CPU walks pixel_x = start_x + j * cos_dir in double, where every term is a float: for start_x >= 1 (ulp >= 2^-23) and
+// |cos_dir| >= 2^-9 or 0 (ulp >= 2^-32) all positions are multiples of 2^-32 below 2^13, i.e. EXACT 45-bit integers X = x * 2^32.
+// Then floor(x) is the high word, and the CPU's a = (float)(pixel_x - ix) -- one rounding of an exact difference -- is
+// RN(low word) * 2^-32 (a power-of-two scale commutes with the rounding).  Per sample: two 64-bit integer adds and two
+// conversions instead of ten double-precision adds and two conversions; the gather, the blend and the rounding are unchanged.
+__device__ __forceinline__ float window_pixel_fixed(cudaTextureObject_t tex, unsigned long long X, unsigned long long Y, float ty_bias)
+{
+    const unsigned ix = (unsigned)(X >> 32), iy = (unsigned)(Y >> 32);
+    const float a = __uint2float_rn((unsigned)X) * 2.3283064365386963e-10f;
+    const float bq = __uint2float_rn((unsigned)Y) * 2.3283064365386963e-10f;
+    const float tx = __uint_as_float(0x4B000000u | ix) - 8388607.0f;       // ix + 1.0f, exact
+    const float ty = __uint_as_float(0x4B000000u | iy) - ty_bias;          // iy + 1.0f + row_off, exact
+    const float4 g = tex2Dgather<float4>(tex, tx, ty, 0);
+    const float p00 = g.w, p01 = g.z, p10 = g.x, p11 = g.y;
+    const float v = p00 * (1.f - a) * (1.f - bq) + p01 * a * (1.f - bq) + p10 * (1.f - a) * bq + p11 * a * bq;
+    return (v + 12582912.0f) - 12582912.0f;
+}
+
 // float copy of the batch's images for the texture path (pitch in floats)
 __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride,
                                                         int rows, int cols, int stride, float *dst, int pitch_f)
@@ -1002,11 +1021,13 @@ __global__ void __launch_bounds__(WK_WARPS * 32, MINB) orient_describe_warp_kern
     int *big_flag, const cudaTextureObject_t tex_stack, int b_first, int b_count, int *work_counter_large, int lpt_split)
 {
     constexpr bool TEX = MODE == 1;
+    constexpr bool STACK = MODE >= 2;        // MODE 3 = 2 with fixed-point coordinates in the border-free loop (window_pixel_fixed)
+    constexpr bool FIXED = MODE == 3;
     __shared__ WarpScratch s_ws[WK_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch &S = s_ws[warp];
-    const int total = MODE == 2 ? prefix[b_first + b_count] : prefix[batch];
-    const int item0 = MODE == 2 ? prefix[b_first] : 0;
+    const int total = STACK ? prefix[b_first + b_count] : prefix[batch];
+    const int item0 = STACK ? prefix[b_first] : 0;
     const int W = cols + 1, srows = rows + 1, scols = cols + 1;
     const int dsize = extended ? 128 : 64;
     const unsigned lt_mask = (1u << lane) - 1;
@@ -1123,10 +1144,18 @@ __global__ void __launch_bounds__(WK_WARPS * 32, MINB) orient_describe_warp_kern
         // float chain's drift, 2 px of slack) keeps every 2x2 footprint inside the image
         float ty_bias = 8388607.0f;
         bool interior = false;
-        if (MODE == 2) {
+        bool fixed_ok = false;
+        long long cos_fx = 0, sin_fx = 0;       // cos_dir, sin_dir * 2^32
+        if (STACK) {
             ty_bias = 8388607.0f - (float)((b - b_first) * rows);
             const float R = (float)(win - 1) * 0.7072f + 2.0f;
             interior = !upright && cx - R >= 1.f && cx + R <= (float)(ncols1 - 1) && cy - R >= 1.f && cy + R <= (float)(nrows1 - 1);
+            if (FIXED && interior) {
+                const float ac = fabsf(cos_dir), as = fabsf(sin_dir);
+                fixed_ok = (ac == 0.f || ac >= 0.001953125f) && (as == 0.f || as >= 0.001953125f);     // ulp >= 2^-32
+                cos_fx = (long long)((double)cos_dir * 4294967296.0);
+                sin_fx = (long long)((double)sin_dir * 4294967296.0);
+            }
         }
         float *rowf = S.buf;              // the orientation scratch is free now: one window row as exact float pixel values
         int cur_row = -1;                 // row currently held in rowf
@@ -1141,8 +1170,15 @@ __global__ void __launch_bounds__(WK_WARPS * 32, MINB) orient_describe_warp_kern
                 // |x| < 2^13), so the running sum equals the CPU's column-by-column accumulation
                 double px = rx + (double)lane * (double)cos_dir, py = ry - (double)lane * (double)sin_dir;
                 const double dpx = 32.0 * (double)cos_dir, dpy = 32.0 * (double)sin_dir;
-                if (MODE == 2) {
-                    if (interior) {
+                if (STACK) {
+                    if (FIXED && fixed_ok) {
+                        // interior: every position is >= 1, so rx * 2^32 and all sums below are exact non-negative integers
+                        unsigned long long X = (unsigned long long)(rx * 4294967296.0) + (unsigned long long)((long long)lane * cos_fx);
+                        unsigned long long Y = (unsigned long long)(ry * 4294967296.0) - (unsigned long long)((long long)lane * sin_fx);
+                        const unsigned long long dX = (unsigned long long)(32 * cos_fx), dY = (unsigned long long)(32 * sin_fx);
+#pragma unroll UNROLL
+                        for (int j = lane; j < win; j += 32, X += dX, Y -= dY) rowf[j] = window_pixel_fixed(tex_stack, X, Y, ty_bias);
+                    } else if (interior) {
 #pragma unroll UNROLL
                         for (int j = lane; j < win; j += 32, px += dpx, py -= dpy)
                             rowf[j] = window_pixel_stack<false>(tex_stack, img, stride, ncols1, nrows1, px, py, ty_bias);
@@ -1835,7 +1871,9 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
                 else if (ctx->describe_mode == 3) LAUNCH_WK_(2, 4, 4, work_counter + 4 + c, ts[c], c * per, nb);
                 else if (ctx->describe_mode == 4) LAUNCH_WK_(2, 4, 3, work_counter + 4 + c, ts[c], c * per, nb);
                 else if (ctx->describe_mode == 5) LAUNCH_WK_(2, 2, 5, work_counter + 4 + c, ts[c], c * per, nb);   // 48 registers: 5 CTAs / SM
-                else LAUNCH_WK_(2, 1, 5, work_counter + 4 + c, ts[c], c * per, nb);
+                else if (ctx->describe_mode == 6) LAUNCH_WK_(2, 1, 5, work_counter + 4 + c, ts[c], c * per, nb);
+                else if (ctx->describe_mode == 7) LAUNCH_WK_(3, 2, 4, work_counter + 4 + c, ts[c], c * per, nb);   // fixed-point coordinates
+                else LAUNCH_WK_(3, 2, 5, work_counter + 4 + c, ts[c], c * per, nb);
                 LAUNCH_CHECK(ctx);
             }
         }

@@ -88,7 +88,8 @@ enum {
                                    * float texture per image, 2 = one stacked texture whose handle is a kernel parameter
                                    * (uniform-register texture fetch, no border test for windows that lie inside the image);
                                    * 3 = 2 with the border-free loop unrolled x4, 4 = 3 compiled for 3 CTAs per SM (80 registers),
-                                   * 5 = 2 compiled for 5 CTAs per SM (48 registers), 6 = 5 without unrolling */
+                                   * 5 = 2 compiled for 5 CTAs per SM (48 registers), 6 = 5 without unrolling; 7 = 2 with 32.32
+                                   * fixed-point sample coordinates in the border-free loop (no FP64), 8 = 7 for 5 CTAs per SM */
     VFSMS_OPT_SORT_MODE = 1,      /* "sort": KeypointGreater ordering.  0 (default) = rank by counting over all staged
                                    * candidates, 1 = one CTA per image: shared-memory bitonic sort of 64-bit keys + tie fix-up */
     VFSMS_OPT_DESCRIBE_LPT = 2,   /* "lpt": 0 (default) = keypoints described in response order, 1 = windows of 128 px and more

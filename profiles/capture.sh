@@ -16,7 +16,7 @@ VFSMS_EXPERIMENTAL=1 timeout -s KILL 600 python -m pytest tests/test_gpu_variant
 # 2. the bench as the driver runs it (autotune probe picks the validated variants), the default schedule, and each variant alone
 timeout -s KILL 500 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 timeout -s KILL 400 python bench.py --steps 20 --warmup 3 --no-autotune --no-cpu-baseline > $OUT/${TAG}_bench_default.json 2> $OUT/${TAG}_bench_default.err
-for V in describe=2 describe=3 describe=5 describe=6 sort=1 lpt=1; do
+for V in describe=2 describe=3 describe=5 describe=6 describe=7 describe=8 sort=1 lpt=1; do
     timeout -s KILL 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --opt $V > $OUT/${TAG}_bench_${V/=/}.json 2> $OUT/${TAG}_bench_${V/=/}.err
 done
 timeout -s KILL 300 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err

@@ -100,6 +100,7 @@ template <class T> static inline unsigned atomicInc(T *p, unsigned lim) { unsign
 // ---------------------------------------------------------------- intrinsics
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline int __float2int_rn(float v) { return (int)lrintf(v); }
+static inline float __uint2float_rn(unsigned v) { return (float)v; }      // round to nearest even (the default FP environment)
 static inline int __float2int_rd(float v) { return (int)floorf(v); }
 static inline int __float2int_rz(float v) { return (int)v; }
 static inline int __double2int_rn(double v) { return (int)lrint(v); }

@@ -33,7 +33,7 @@ def _surf_both(gpu, img, option, values, **kw):
 def test_describe_stacked_texture_identical(gpu, synth_pair_rois, extended):
     roiA, roiB, _ = synth_pair_rois
     for img in (roiA, roiB):
-        outs = _surf_both(gpu, img, "describe", (1, 2, 0, 3, 4, 5, 6), extended=extended, keypoints_ratio=0.01)
+        outs = _surf_both(gpu, img, "describe", (1, 2, 0, 3, 4, 5, 6, 7, 8), extended=extended, keypoints_ratio=0.01)
         k1, d1 = outs[0]
         assert len(k1) > 500
         for k2, d2 in outs[1:]:

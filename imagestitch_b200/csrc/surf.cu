@@ -972,6 +972,21 @@ __device__ __forceinline__ float window_pixel_fixed(cudaTextureObject_t tex, uns
     return (v + 12582912.0f) - 12582912.0f;
 }
 
+// The same for windows that cross the image border: signed positions (arithmetic shift = floor), the bounds test on the integer
+// parts, and the CPU's clamped nearest pixel cvRound(pixel_x) = round-half-to-even of X / 2^32 from the fraction word.
+__device__ __forceinline__ float window_pixel_fixed_checked(cudaTextureObject_t tex, const uint8_t *__restrict__ img, int stride, int ncols1,
+                                                            int nrows1, long long X, long long Y, float ty_bias)
+{
+    const int ix = (int)(X >> 32), iy = (int)(Y >> 32);
+    if ((unsigned)ix < (unsigned)ncols1 && (unsigned)iy < (unsigned)nrows1)
+        return window_pixel_fixed(tex, (unsigned long long)X, (unsigned long long)Y, ty_bias);
+    const unsigned fx = (unsigned)X, fy = (unsigned)Y;
+    int x = ix + ((fx > 0x80000000u || (fx == 0x80000000u && (ix & 1))) ? 1 : 0);
+    int y = iy + ((fy > 0x80000000u || (fy == 0x80000000u && (iy & 1))) ? 1 : 0);
+    x = min(max(x, 0), ncols1); y = min(max(y, 0), nrows1);
+    return (float)img[(size_t)y * stride + x];
+}
+
 // float copy of the batch's images for the texture path (pitch in floats)
 __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride,
                                                         int rows, int cols, int stride, float *dst, int pitch_f)
@@ -1144,15 +1159,16 @@ __global__ void __launch_bounds__(WK_WARPS * 32, MINB) orient_describe_warp_kern
         // float chain's drift, 2 px of slack) keeps every 2x2 footprint inside the image
         float ty_bias = 8388607.0f;
         bool interior = false;
-        bool fixed_ok = false;
+        bool fixed_ok = false, dir_ok = false;
         long long cos_fx = 0, sin_fx = 0;       // cos_dir, sin_dir * 2^32
         if (STACK) {
             ty_bias = 8388607.0f - (float)((b - b_first) * rows);
             const float R = (float)(win - 1) * 0.7072f + 2.0f;
             interior = !upright && cx - R >= 1.f && cx + R <= (float)(ncols1 - 1) && cy - R >= 1.f && cy + R <= (float)(nrows1 - 1);
-            if (FIXED && interior) {
+            if (FIXED && !upright) {
                 const float ac = fabsf(cos_dir), as = fabsf(sin_dir);
-                fixed_ok = (ac == 0.f || ac >= 0.001953125f) && (as == 0.f || as >= 0.001953125f);     // ulp >= 2^-32
+                dir_ok = (ac == 0.f || ac >= 0.001953125f) && (as == 0.f || as >= 0.001953125f);       // ulp >= 2^-32
+                fixed_ok = dir_ok && interior;
                 cos_fx = (long long)((double)cos_dir * 4294967296.0);
                 sin_fx = (long long)((double)sin_dir * 4294967296.0);
             }
@@ -1178,6 +1194,14 @@ __global__ void __launch_bounds__(WK_WARPS * 32, MINB) orient_describe_warp_kern
                         const unsigned long long dX = (unsigned long long)(32 * cos_fx), dY = (unsigned long long)(32 * sin_fx);
 #pragma unroll UNROLL
                         for (int j = lane; j < win; j += 32, X += dX, Y -= dY) rowf[j] = window_pixel_fixed(tex_stack, X, Y, ty_bias);
+                    } else if (FIXED && dir_ok && (chain_x == 0.f || fabsf(chain_x) >= 0.001953125f) && (chain_y == 0.f || fabsf(chain_y) >= 0.001953125f)) {
+                        // a window that crosses the border, row start with ulp >= 2^-32 (warp-uniform): signed fixed point
+                        long long X = (long long)(rx * 4294967296.0) + (long long)lane * cos_fx;
+                        long long Y = (long long)(ry * 4294967296.0) - (long long)lane * sin_fx;
+                        const long long dX = 32 * cos_fx, dY = 32 * sin_fx;
+#pragma unroll 2
+                        for (int j = lane; j < win; j += 32, X += dX, Y -= dY)
+                            rowf[j] = window_pixel_fixed_checked(tex_stack, img, stride, ncols1, nrows1, X, Y, ty_bias);
                     } else if (interior) {
 #pragma unroll UNROLL
                         for (int j = lane; j < win; j += 32, px += dpx, py -= dpy)

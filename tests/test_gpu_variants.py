@@ -45,7 +45,9 @@ def test_describe_stacked_texture_borders_and_giants(gpu):
     from imagestitch_b200 import synth
     A, _, _ = synth.pair(seed=3, size=384, overlap=60, direction=1)
     for img in (A[:97], A[:, :131], A):
-        (k1, d1), (k2, d2) = _surf_both(gpu, img, "describe", (1, 2), extended=True, keypoints_ratio=0.0, hessian_threshold=30.0)
+        outs = _surf_both(gpu, img, "describe", (1, 2, 7), extended=True, keypoints_ratio=0.0, hessian_threshold=30.0)
+        (k1, d1), (k2, d2) = outs[0], outs[1]
+        assert np.array_equal(k1, outs[2][0]) and np.array_equal(d1, outs[2][1])
         assert len(k1) > 50
         assert np.array_equal(k1, k2) and np.array_equal(d1, d2)
 

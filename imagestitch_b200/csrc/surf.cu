@@ -1874,7 +1874,7 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
     orient_describe_warp_kernel<T, U, MB><<<ctx->num_sms * MB, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,  \
         ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap,              \
         p->extended, p->upright, texs, WC, work_counter + 1, TS, B0, NB, (WC) + SURF_MAX_DESC_CHUNKS, lpt_split)
-    const int lpt_split = ctx->describe_lpt ? 128 : 0;
+    const int lpt_split = ctx->describe_lpt == 1 ? 128 : (ctx->describe_lpt == 2 ? 64 : (ctx->describe_lpt == 3 ? 256 : 0));
     // mode 2 (opt-in, vfsms_set_option(VFSMS_OPT_DESCRIBE_MODE, 2)): one stacked texture per group of images whose rows fit
     // the 2-D linear texture height limit, one launch per group with its own work counter
     bool stacked = false;

@@ -93,7 +93,8 @@ enum {
     VFSMS_OPT_SORT_MODE = 1,      /* "sort": KeypointGreater ordering.  0 (default) = rank by counting over all staged
                                    * candidates, 1 = one CTA per image: shared-memory bitonic sort of 64-bit keys + tie fix-up */
     VFSMS_OPT_DESCRIBE_LPT = 2,   /* "lpt": 0 (default) = keypoints described in response order, 1 = windows of 128 px and more
-                                   * first (two passes over the work list), so that no giant window is met at the end of the launch */
+                                   * first (two passes over the work list), so that no giant window is met at the end of the launch;
+                                   * 2 / 3 = the same with the split at 64 / 256 px */
     VFSMS_OPT_ENTROPY = 3,        /* "entropy": Huffman decoding of JPEG tiles.  0 (default) = host threads, one file each; 1 = on the
                                    * device: self-synchronising parallel decode of 1024-bit subsequences (files with restart
                                    * intervals keep the host stage); same coefficients, symbol for symbol */

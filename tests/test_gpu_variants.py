@@ -95,7 +95,10 @@ def test_describe_large_windows_first_identical(gpu, synth_pair_rois):
     roiA, _, _ = synth_pair_rois
     for mode in (1, 2):
         gpu.set_option("describe", mode)
-        (k0, d0), (k1, d1) = _surf_both(gpu, roiA, "lpt", (0, 1), extended=True, keypoints_ratio=0.0, hessian_threshold=30.0)
+        outs = _surf_both(gpu, roiA, "lpt", (0, 1, 2, 3), extended=True, keypoints_ratio=0.0, hessian_threshold=30.0)
+        (k0, d0), (k1, d1) = outs[0], outs[1]
+        for k2, d2 in outs[2:]:
+            assert np.array_equal(k0, k2) and np.array_equal(d0, d2)
         assert len(k0) > 1000 and (np.floor(21 * k0[:, 2] * np.float32(1.2) / 9) >= 128).sum() > 5
         assert np.array_equal(k0, k1) and np.array_equal(d0, d1)
     gpu.set_option("describe", 1); gpu.set_option("lpt", 0)

@@ -28,8 +28,9 @@ FAST = [
     (["tests/test_gpu_blend.py", "tests/test_gpu_zz_bands.py", "tests/test_gpu_phase.py", "tests/test_gpu_orb.py"], None, 20),
     (["tests/test_gpu_jpeg.py", "tests/test_gpu_zz_jpeg_encode.py"], "not full_size", 35),
     (["tests/test_gpu_surf.py"], "not real_micrograph", 9),
-    (["tests/test_gpu_zz_phase_wrap.py", "tests/test_gpu_variants.py", "tests/test_gpu_zz_colour_stack.py", "tests/test_gpu_zz_entropy_device.py"],
-     "overlap_sums or sort_per_image or large_windows_first or borders_and_giants or colour_twin or (entropy_device and not large)", 8),
+    (["tests/test_gpu_zz_phase_wrap.py", "tests/test_gpu_variants.py", "tests/test_gpu_zz_colour_stack.py", "tests/test_gpu_zz_entropy_device.py",
+      "tests/test_gpu_zz_sequence.py"],
+     "overlap_sums or sort_per_image or large_windows_first or borders_and_giants or colour_twin or (entropy_device and not large) or result_file_identical", 9),
 ]
 
 

@@ -44,16 +44,48 @@ def emu_lib():
         sys.path.remove(EMU_DIR)
 
 
-def _run(selection, kexpr, extra_env=None):
+def _start(selection, kexpr, extra_env=None):
+    """pytest on the emulated library in a subprocess (output to a temporary file: no pipe to fill up while nobody reads)"""
+    import tempfile
     env = dict(os.environ, VFSMS_EMU="1", VFSMS_EXPERIMENTAL="1", PYTHONPATH=ROOT)
     env.update(extra_env or {})
     cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + selection
     if kexpr:
         cmd += ["-k", kexpr]
-    p = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=3000)
-    out = p.stdout.decode()
+    log = tempfile.TemporaryFile()
+    return subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=log, stderr=subprocess.STDOUT), log
+
+
+def _finish(started, timeout=3000):
+    proc, log = started
+    try:
+        proc.wait(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        proc.kill()
+        proc.wait()
+    log.seek(0)
+    out = log.read().decode(errors="replace")
+    log.close()
     m = re.search(r"(\d+) passed", out)
-    return p.returncode, int(m.group(1)) if m else 0, out
+    return proc.returncode, int(m.group(1)) if m else 0, out
+
+
+def _run(selection, kexpr, extra_env=None):
+    return _finish(_start(selection, kexpr, extra_env))
+
+
+@pytest.fixture(scope="module")
+def emu_runs(emu_lib):
+    """All selections start together (one pytest subprocess each, the library is built once before): the wall time of this
+    module is the slowest selection, not their sum."""
+    runs = {("fast", i): _start(sel, kexpr) for i, (sel, kexpr, _) in enumerate(FAST)}
+    for limit in ("450", "250"):
+        runs[("tex", limit)] = _start(["tests/test_gpu_variants.py"], "stacked_texture_batches", {"VFSMS_EMU_TEX_ROWS": limit})
+    yield runs
+    for proc, log in runs.values():
+        if proc.poll() is None:
+            proc.kill()
+            proc.wait()
 
 
 def test_emulated_library_exports_the_c_abi(emu_lib):
@@ -68,17 +100,17 @@ def test_emulated_library_exports_the_c_abi(emu_lib):
 
 
 @pytest.mark.parametrize("case", range(len(FAST)))
-def test_gpu_parity_tests_on_emulated_kernels(emu_lib, case):
+def test_gpu_parity_tests_on_emulated_kernels(emu_runs, case):
     selection, kexpr, at_least = FAST[case]
-    rc, passed, out = _run(selection, kexpr)
+    rc, passed, out = _finish(emu_runs[("fast", case)])
     assert rc == 0, out[-6000:]
     assert passed >= at_least, out[-2000:]
 
 
-def test_stacked_texture_groups_on_emulated_kernels(emu_lib):
+def test_stacked_texture_groups_on_emulated_kernels(emu_runs):
     """describe mode 2 with a 450-row (groups of 4 images) and a 250-row (groups of 2) texture height limit"""
     for limit in ("450", "250"):
-        rc, passed, out = _run(["tests/test_gpu_variants.py"], "stacked_texture_batches", {"VFSMS_EMU_TEX_ROWS": limit})
+        rc, passed, out = _finish(emu_runs[("tex", limit)])
         assert rc == 0 and passed == 1, out[-6000:]
 
 

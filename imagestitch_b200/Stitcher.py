@@ -121,6 +121,9 @@ def _imread_color_many(paths, decoder="b200"):
     return images
 
 
+_last_sequence_has_color = False     # set by _load_sequence: the colour twin of the stack holds the sequence
+
+
 def _load_sequence(paths, decoder="b200", keep_on_device=True, color=False):
     """Decode a tile sequence ONCE.  -> (host gray images, on_device).  With decoder "b200" and equally sized tiles the
     tiles also stay in the library's device-resident stack (slot k = paths[k]): JPEG files are decoded straight into it,
@@ -144,19 +147,31 @@ def _load_sequence(paths, decoder="b200", keep_on_device=True, color=False):
         return _imread_gray_many(paths, decoder), False
     rows, cols = shapes[0]
     n = len(paths)
-    gpu.tiles_reserve(n, rows, cols)
-    k = 0
-    while k < n:                                     # runs of JPEG files are decoded with one call each
-        e = k
-        while e < n and jpeg_ok[e] == jpeg_ok[k]:
-            e += 1
-        if jpeg_ok[k]:
-            (gpu.tiles_decode_jpeg_bgr if color else gpu.tiles_decode_jpeg)(k, [datas[j] for j in range(k, e)])
-        else:
-            gpu.tiles_upload(k, np.stack([others[j] for j in range(k, e)]))
-            if color:
-                gpu.tiles_upload_bgr(k, np.stack([cv2.imdecode(datas[j], cv2.IMREAD_COLOR) for j in range(k, e)]))
-        k = e
+
+    def fill(with_color):
+        gpu.tiles_reserve(n, rows, cols)
+        k = 0
+        while k < n:                                 # runs of JPEG files are decoded with one call each
+            e = k
+            while e < n and jpeg_ok[e] == jpeg_ok[k]:
+                e += 1
+            if jpeg_ok[k]:
+                (gpu.tiles_decode_jpeg_bgr if with_color else gpu.tiles_decode_jpeg)(k, [datas[j] for j in range(k, e)])
+            else:
+                gpu.tiles_upload(k, np.stack([others[j] for j in range(k, e)]))
+                if with_color:
+                    gpu.tiles_upload_bgr(k, np.stack([cv2.imdecode(datas[j], cv2.IMREAD_COLOR) for j in range(k, e)]))
+            k = e
+    global _last_sequence_has_color
+    _last_sequence_has_color = bool(color)
+    try:
+        fill(color)
+    except gpu.VfsmsError:
+        if not color:
+            raise
+        # the colour twin did not fit (3 x the gray stack): gray stack only, the mosaic then decodes the colour tiles batch by batch
+        _last_sequence_has_color = False
+        fill(False)
     host = gpu.tiles_download(0, n, rows, cols)
     return [host[j] for j in range(n)], True
 
@@ -200,7 +215,7 @@ class Stitcher(Utility.Method):
             and self.offsetCaculate == "mode" and not self.isEnhance
         # decoded once (the reference decodes every tile twice, and a third time for the mosaic)
         images, self._on_device = _load_sequence(fileList, self.decoder, keep_on_device=True, color=bool(self.isColorMode))
-        self._stack_color = bool(self.isColorMode) and self._on_device
+        self._stack_color = bool(self.isColorMode) and self._on_device and _last_sequence_has_color
         table = {}
         for fileIndex in range(0, fileNum - 1):
             self.printAndWrite("stitching " + str(fileList[fileIndex]) + " and " + str(fileList[fileIndex + 1]))

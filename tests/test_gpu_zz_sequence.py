@@ -45,3 +45,28 @@ def test_result_file_identical_for_library_and_cv2_codecs(tmp_path):
     assert lib["stitching_result_1.jpg"] == ref["stitching_result_1.jpg"] == dev["stitching_result_1.jpg"]
     img = cv2.imdecode(np.frombuffer(lib["stitching_result_1.jpg"], np.uint8), cv2.IMREAD_COLOR)
     assert img is not None and img.shape[0] > 700 and img.shape[1] > 700 and (img.sum(axis=2) > 0).mean() > 0.9      # all four tiles placed
+
+
+def test_colour_twin_that_does_not_fit_falls_back_to_gray_stack(tmp_path, monkeypatch):
+    """The colour twin is 3 x the gray stack; when reserving / filling it fails (VfsmsError) the sequence is loaded into the gray stack alone
+    and the mosaic decodes the colour tiles batch by batch -- the result file must not change."""
+    import cv2
+    from imagestitch_b200 import gpu, synth
+    import imagestitch_b200.Stitcher as S
+    assert gpu.device_count() > 0, "no CUDA device: the product path has no CPU fallback"
+    tiles, offs = synth.tile_sequence(seed=78, n_rows=1, n_cols=3, size=384, overlap=72, noise=1.5)
+    d = tmp_path / "set" / "1"
+    d.mkdir(parents=True)
+    for k, t in enumerate(tiles):
+        cv2.imwrite(str(d / ("tile-%02d.jpg" % k)), np.stack([t, np.roll(t, 3, axis=0), 255 - t // 3], axis=-1), [cv2.IMWRITE_JPEG_QUALITY, 90])
+    root = str(tmp_path / "set")
+    full = _run(root, str(tmp_path / "out_full"), "b200", "b200", 0)
+    assert S._last_sequence_has_color
+
+    def no_room(first, datas, device=0):
+        raise gpu.VfsmsError("vfsms_tiles_decode_jpeg_bgr failed (-2): out of device memory (test)")
+    monkeypatch.setattr(gpu, "tiles_decode_jpeg_bgr", no_room)
+    gray_only = _run(root, str(tmp_path / "out_gray"), "b200", "b200", 0)
+    assert not S._last_sequence_has_color
+    assert list(full) == list(gray_only) == ["stitching_result_1.jpg"]
+    assert full["stitching_result_1.jpg"] == gray_only["stitching_result_1.jpg"]

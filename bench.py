@@ -188,6 +188,102 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
+def aux_probe_main(path, device):
+    """Child of run_aux_probe: the paths that have never run on hardware (device Huffman decoding, device JPEG encoder), each reported
+    as a block or an {"error": ...}.  Prints one JSON line."""
+    import cv2
+    import torch
+    from imagestitch_b200 import gpu
+    torch.cuda.set_device(device)
+    dev = torch.device("cuda", device)
+    stream = torch.cuda.Stream(dev)
+    tiles_h = np.load(path)
+    n_t = tiles_h.shape[0]
+    reps = 3
+    out = {}
+    try:
+        files = [cv2.imencode(".jpg", t, [cv2.IMWRITE_JPEG_QUALITY, 92])[1].tobytes() for t in tiles_h]
+        stack = torch.empty(tiles_h.shape, dtype=torch.uint8, device=dev)
+        gpu.jpeg_decode_gray_dev(files, stack, device=device, stream=stream)           # host entropy stage: the comparison
+        gpu.set_option("entropy", 1, device=device)
+        stack2 = torch.empty_like(stack)
+        gpu.jpeg_decode_gray_dev(files, stack2, device=device, stream=stream)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            gpu.jpeg_decode_gray_dev(files, stack2, device=device, stream=stream)      # synchronous on return
+        dt_d = (time.perf_counter() - t0) / reps
+        out["device_entropy"] = {"tiles_per_s": n_t / dt_d, "identical_to_host_stage": bool(torch.equal(stack, stack2)),
+                                 "sync_passes": gpu.jpeg_last_entropy_passes(device=device),
+                                 "what": "same files, Huffman decoding on the device (self-synchronising 1024-bit subsequences): H2D of the unstuffed scan only"}
+    except Exception as e:                                                             # noqa: BLE001
+        out["device_entropy"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+    print(json.dumps(out), flush=True)          # kept if the encoder below takes the process down
+    try:
+        gpu.set_option("entropy", 0, device=device)
+        t4 = torch.from_numpy(tiles_h[:4]).to(dev)                                     # four tiles -> one BGR canvas twice their side
+        gray = torch.cat([torch.cat([t4[0], t4[1]], dim=1), torch.cat([t4[2], t4[3]], dim=1)], dim=0)
+        canvas = torch.stack([gray, torch.roll(gray, 5, 0), 255 - torch.roll(gray, 9, 1)], dim=2).contiguous()
+        torch.cuda.synchronize(dev)
+        data = gpu.jpeg_encode_dev(canvas, device=device, stream=stream)               # warm-up: workspaces, tables
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            data = gpu.jpeg_encode_dev(canvas, device=device, stream=stream)           # synchronous on return
+        dt_e = (time.perf_counter() - t0) / reps
+        host_img = canvas.cpu().numpy()
+        t0 = time.perf_counter()
+        ref_bytes = cv2.imencode(".jpg", host_img)[1].tobytes()
+        dt_c = time.perf_counter() - t0
+        mp = host_img.shape[0] * host_img.shape[1] / 1e6
+        out["output_encode"] = {"mpix_per_s": mp / dt_e, "cv2_imencode_mpix_per_s_1_thread": mp / dt_c, "identical_to_cv2": bool(data == ref_bytes),
+                                "jpeg_bytes": len(data),
+                                "what": "%dx%d BGR canvas in HBM -> baseline JPEG q95 4:2:0 (colour conversion, FDCT, quantisation, Huffman coding, byte "
+                                        "stuffing on the device; D2H of the compressed stream only); wall clock" % host_img.shape[:2]}
+    except Exception as e:                                                             # noqa: BLE001
+        out["output_encode"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+    print(json.dumps(out), flush=True)
+
+
+def run_aux_probe(tiles_h, device, timeout=240):
+    """aux_probe_main in a subprocess on `tiles_h` ([n, rows, cols] u8).  -> its last JSON line, or {"error": ...}; whatever happens
+    in the child (CUDA error, crash, hang -> timeout) stays there."""
+    import tempfile
+    fd, path = tempfile.mkstemp(suffix=".npy")
+    os.close(fd)
+    out, err = "", None
+    try:
+        np.save(path, tiles_h)
+        env = dict(os.environ)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+            env.pop(k, None)
+        cmd = [sys.executable, os.path.abspath(__file__), "--aux-probe", path, "--aux-device", str(device)]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=os.path.dirname(os.path.abspath(__file__)))
+            out = r.stdout
+            if r.returncode != 0:
+                err = "probe exited %d: %s" % (r.returncode, (r.stderr or "")[-300:])
+        except subprocess.TimeoutExpired as e:
+            out = e.stdout.decode(errors="replace") if isinstance(e.stdout, bytes) else (e.stdout or "")
+            err = "probe timed out after %d s" % timeout
+        except OSError as e:
+            err = "probe could not start: %s" % e
+    finally:
+        try:
+            os.remove(path)
+        except OSError:
+            pass
+    res = {}
+    for ln in reversed(out.splitlines()):
+        if ln.startswith("{"):
+            try:
+                res = json.loads(ln)
+                break
+            except ValueError:
+                continue
+    if err:
+        res["error"] = err
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,7 +299,11 @@ def main():
     ap.add_argument("--no-autotune", action="store_true",
                     help="keep the default kernel schedule (default: imagestitch_b200.autotune picks, in a subprocess, the variants that are "
                          "bit-identical to the default on this workload shape AND faster)")
+    ap.add_argument("--aux-probe", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--aux-device", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.aux_probe:
+        return aux_probe_main(args.aux_probe, args.aux_device)
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         return run_reference(args, rank, world)
@@ -384,6 +484,7 @@ def main():
 
     # ---- tile ingest: JPEG files in host memory -> u8 tiles resident in HBM, beside cv2.imdecode
     ingest = None
+    encode = None
     if world == 1 and not args.no_cpu_baseline:
         import cv2
         n_t = min(16, P)
@@ -404,55 +505,12 @@ def main():
                   "jpeg_bytes_per_tile": int(np.mean([len(f) for f in files])), "host_threads": min(len(os.sched_getaffinity(0)), int(_cgroup_cpu_quota() or 1 << 30), 32, n_t),
                   "cv2_imdecode_tiles_per_s_1_thread": 1.0 / dt_c,
                   "what": "%d synthetic 2048x2048 JPEG tiles (q92, single component) from host bytes to HBM-resident u8 tiles: host Huffman threads + H2D of int16 coefficients + IDCT kernel; wall clock" % n_t}
-        # option "entropy" = 1: Huffman decoding on the device (written without GPU access, verified on the CPU emulation only): first
-        # hardware run happens here, so a failure is reported inside the block and the option goes back to the host stage
-        try:
-            gpu.set_option("entropy", 1, device=local)
-            stack2 = torch.empty_like(stack)
-            gpu.jpeg_decode_gray_dev(files, stack2, device=local, stream=stream)
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                gpu.jpeg_decode_gray_dev(files, stack2, device=local, stream=stream)
-            dt_d = (time.perf_counter() - t0) / reps
-            ingest["device_entropy"] = {"tiles_per_s": n_t / dt_d, "identical_to_host_stage": bool(torch.equal(stack, stack2)),
-                                        "sync_passes": gpu.jpeg_last_entropy_passes(device=local),
-                                        "what": "same files, Huffman decoding on the device (self-synchronising 1024-bit subsequences): H2D of the unstuffed scan only"}
-        except Exception as e:                                                         # noqa: BLE001
-            ingest["device_entropy"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
-        finally:
-            try:
-                gpu.set_option("entropy", 0, device=local)
-            except Exception:                                                          # noqa: BLE001
-                pass
-
-    # ---- output encode: a BGR mosaic resident in HBM -> the bytes cv2.imwrite(".jpg") would write.
-    # First run on hardware happens inside this bench (written without GPU access, verified on the CPU emulation only), so a
-    # failure is reported in the block instead of taking the headline line down.
-    encode = None
-    if world == 1 and not args.no_cpu_baseline:
-        try:
-            import cv2
-            t4 = batches[0][0][:4]                                                     # four 2048^2 tiles -> one 4096^2 BGR canvas
-            gray = torch.cat([torch.cat([t4[0], t4[1]], dim=1), torch.cat([t4[2], t4[3]], dim=1)], dim=0)
-            canvas = torch.stack([gray, torch.roll(gray, 5, 0), 255 - torch.roll(gray, 9, 1)], dim=2).contiguous()
-            torch.cuda.synchronize(dev)
-            data = gpu.jpeg_encode_dev(canvas, device=local, stream=stream)            # warm-up: workspaces, tables
-            t0 = time.perf_counter()
-            reps = 3
-            for _ in range(reps):
-                data = gpu.jpeg_encode_dev(canvas, device=local, stream=stream)        # synchronous on return
-            dt_e = (time.perf_counter() - t0) / reps
-            host_img = canvas.cpu().numpy()
-            t0 = time.perf_counter()
-            ref_bytes = cv2.imencode(".jpg", host_img)[1].tobytes()
-            dt_c = time.perf_counter() - t0
-            mp = host_img.shape[0] * host_img.shape[1] / 1e6
-            encode = {"mpix_per_s": mp / dt_e, "cv2_imencode_mpix_per_s_1_thread": mp / dt_c, "identical_to_cv2": bool(data == ref_bytes),
-                      "jpeg_bytes": len(data),
-                      "what": "4096x4096 BGR canvas in HBM -> baseline JPEG q95 4:2:0 (colour conversion, FDCT, quantisation, Huffman coding, byte "
-                              "stuffing on the device; D2H of the compressed stream only); wall clock"}
-        except Exception as e:                                                         # noqa: BLE001
-            encode = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        # option "entropy" = 1 (Huffman decoding on the device) and the device JPEG encoder were written without GPU access and verified
+        # on the CPU emulation only: their first hardware run happens in a SUBPROCESS (own CUDA context, timeout), so neither a CUDA
+        # error nor a hang there can take the headline line down
+        aux = run_aux_probe(tiles_h, local)
+        ingest["device_entropy"] = aux.get("device_entropy", {"error": aux.get("error", "no result")})
+        encode = aux.get("output_encode", {"error": aux.get("error", "no result")})
 
     value = world * P * args.steps / (ms_max * 1e-3)
     out = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -46,7 +46,12 @@ _EMU_SKIP = ("test_gpu_match_tc.py", "test_gpu_fullsize.py", "test_decode_into_d
 
 def pytest_collection_modifyitems(config, items):
     ref = os.path.isdir("/root/reference")
+    has_timeout = config.pluginmanager.hasplugin("timeout")
     for it in items:
+        # on hardware: a kernel that never returns blocks inside a C call where no signal handler runs -> the watchdog thread ends the
+        # process (and with it the CUDA context) instead of leaving the box hung until the caller's own limit
+        if has_timeout and not EMU and "gpu" in it.keywords and it.get_closest_marker("timeout") is None:
+            it.add_marker(pytest.mark.timeout(900, method="thread"))
         if EMU and any(s in it.nodeid for s in _EMU_SKIP):
             it.add_marker(pytest.mark.skip(reason="not covered by the CUDA-on-CPU emulation"))
         if "reference" in it.keywords and not ref:

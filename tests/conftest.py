@@ -44,8 +44,16 @@ def pytest_configure(config):
 _EMU_SKIP = ("test_gpu_match_tc.py", "test_gpu_fullsize.py", "test_decode_into_device_tile_stack", "test_describe_stacked_texture_row_limit_groups")
 
 
+# gpu tests written after the round's last GPU call (so far verified on the emulation only): they run AFTER everything that has
+# already passed on the B200, so that under `-x` a first-hardware-run failure cannot hide the proven tests.  (The test_gpu_zz_* files
+# are in that group by name.)  Empty this list once a hardware run has passed them.
+_AFTER_PROVEN = ("test_gpu_zz_", "test_colour_decode_equals_cv2", "test_colour_batch_full_size_and_gray_file",
+                 "test_golden_reference_tiles_colour", "test_stitcher_colour_mode_on_jpeg_tiles")
+
+
 def pytest_collection_modifyitems(config, items):
     ref = os.path.isdir("/root/reference")
+    items.sort(key=lambda it: any(s in it.nodeid for s in _AFTER_PROVEN))       # stable: order inside each group is kept
     has_timeout = config.pluginmanager.hasplugin("timeout")
     for it in items:
         # on hardware: a kernel that never returns blocks inside a C call where no signal handler runs -> the watchdog thread ends the

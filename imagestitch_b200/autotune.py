@@ -20,7 +20,7 @@ import time
 
 CANDIDATES = (("describe", 2), ("describe", 3), ("describe", 4), ("describe", 5), ("describe", 6), ("describe", 7), ("describe", 8),
               ("sort", 1), ("lpt", 1), ("lpt", 2), ("lpt", 3))
-DEFAULTS = {"describe": 1, "sort": 0, "lpt": 0}
+DEFAULTS = {"describe": 2, "sort": 1, "lpt": 2}
 MIN_GAIN = 0.01          # a variant must be at least this much faster (fraction of the step) to be selected
 
 

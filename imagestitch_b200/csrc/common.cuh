@@ -138,9 +138,9 @@ struct vfsms_ctx {
     int32_t prof_calls[VFSMS_STAGE_COUNT] = {0};
     int device = 0;
     int matcher_mode = 0;          // 0: tcgen05 candidates + exact rescoring, 1: exact SIMT kernel
-    int describe_mode = 1;         // window sampler of the SURF descriptor: 0 LDG, 1 texture per image, 2 one stacked texture (vfsms_set_option)
-    int describe_lpt = 0;          // 1: describe the large windows first (two passes over the work list)
-    int sort_mode = 0;             // KeypointGreater ordering: 0 rank by counting, 1 per-image shared-memory sort (vfsms_set_option)
+    int describe_mode = 2;         // window sampler of the SURF descriptor: 0 LDG, 1 texture per image, 2 one stacked texture (default; vfsms_set_option)
+    int describe_lpt = 2;          // describe the large windows first (two passes over the work list): 0 off, 1 / 2 / 3 = split at 128 / 64 / 256 px
+    int sort_mode = 1;             // KeypointGreater ordering: 0 rank by counting over all candidates, 1 rank inside response bins (default)
     int32_t *last_fallback_count_dev = nullptr;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
@@ -162,7 +162,7 @@ struct vfsms_ctx {
     void *phase_state = nullptr;   // cuFFT plans etc. (phase.cu)
     void *blend_state = nullptr;
     void *orb_state = nullptr;
-    int entropy_mode = 0;          // JPEG entropy decoding: 0 host threads, 1 on the device (vfsms_set_option VFSMS_OPT_ENTROPY)
+    int entropy_mode = 1;          // JPEG entropy decoding: 0 host threads, 1 on the device (default; vfsms_set_option VFSMS_OPT_ENTROPY)
     int entropy_passes = 0;        // synchronisation passes of the last device entropy decode
     void *jpeg_huff_state = nullptr;  // workspaces of the device entropy decoder (jpeg.cu)
     void *jpeg_enc_state = nullptr;   // coefficient / bit-stream workspaces of the JPEG encoder (jpeg_enc.cu)

@@ -61,7 +61,7 @@ int surf_init_tables()
     for (int i = -ORI_RADIUS; i <= ORI_RADIUS; i++)
         for (int j = -ORI_RADIUS; j <= ORI_RADIUS; j++)
             if (i * i + j * j <= ORI_RADIUS * ORI_RADIUS) { ax[n] = i; ay[n] = j; aptw[n++] = G[i + ORI_RADIUS] * G[j + ORI_RADIUS]; }
-    gaussian_kernel_f32(PATCH_SZ, 3.3, Gd);
+    gaussian_kernel_f32(PATCH_SZ, (double)3.3f, Gd);     // OpenCV's DESC_SIGMA is the float constant 3.3f, widened by getGaussianKernel
     for (int i = 0; i < PATCH_SZ; i++)
         for (int j = 0; j < PATCH_SZ; j++) DW[i * PATCH_SZ + j] = Gd[i] * Gd[j];
     CUDA_TRY(cudaMemcpyToSymbol(c_apt_x, ax, sizeof(ax)));

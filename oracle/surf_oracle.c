@@ -394,8 +394,12 @@ static void sample_window(const uint8_t *img, int rows, int cols, int stride, fl
 {
     if (!upright) {
         float descriptor_dir = dir_deg * (float)(M_PI / 180);
-        float sin_dir = -sinf(descriptor_dir);
-        float cos_dir = cosf(descriptor_dir);
+        /* OpenCV: -std::sin(float) / std::cos(float).  Which float comes out of sinf for the ~1.3 % of arguments whose
+         * result lies close to a rounding boundary depends on the C library (glibc's sinf is faithful, not correctly rounded;
+         * 3.3.1's Windows wheels used MSVC's).  The oracle takes the correctly rounded value -- double sin, then one rounding --
+         * which is also what the CUDA path computes, so descriptors can be compared bit for bit. */
+        float sin_dir = -(float)sin((double)descriptor_dir);
+        float cos_dir = (float)cos((double)descriptor_dir);
         float win_offset = -(float)(win_size - 1) / 2;
         float start_x = cx + win_offset * cos_dir + win_offset * sin_dir;
         float start_y = cy - win_offset * sin_dir + win_offset * cos_dir;

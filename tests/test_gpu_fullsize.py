@@ -88,3 +88,50 @@ def test_vote_and_blend_idempotence(gpu):
     assert out1.shape == a.shape and d.min() >= 0 and d.max() <= 2
     assert np.array_equal(gpu.fuse_roi(a, a, "average"), np.where(a == 0, 0, a).astype(np.uint8))
     assert np.array_equal(gpu.fuse_roi(a, a, "maximum"), gpu.fuse_roi(a, a, "minimum"))
+
+
+def _oracle_align(roiA, roiB):
+    from oracle import surf
+    mf = int(0.01 * roiA.size)
+    kA, dA = surf.detect_and_compute(roiA, 100, 4, 3, True, False, mf)
+    kB, dB = surf.detect_and_compute(roiB, 100, 4, 3, True, False, mf)
+    m = surf.match_l2_ratio(dA, dB, 0.75)
+    return (kA, dA), (kB, dB), m, surf.offset_by_mode(kA, kB, m, 3)
+
+
+def _assert_surf_equal(got, want):
+    (kg, dg), (ko, do) = got, want
+    assert kg.shape == ko.shape and dg.shape == do.shape
+    assert np.array_equal(kg[:, :7], ko[:, :7])                              # x, y, size, angle, response, octave, laplacian
+    assert np.array_equal(dg, do)                                            # descriptors bit for bit
+
+
+def test_c2_headline_roi_equals_oracle(gpu, pair2048):
+    """BASELINE configs[1] at the size bench.py times (seed 1234, ROI 409 x 2048, GPU-SURF parameters): keypoints, descriptors,
+    match list, vote and the batched entry point against the CPU oracle (ImageUtility.py:23-28,272,288-296,139-178)."""
+    A, B, off = pair2048
+    L = int(np.floor(2048 * 0.2))
+    roiA, roiB = np.ascontiguousarray(A[2048 - L:]), np.ascontiguousarray(B[:L])
+    fa, fb, m_o, (st_o, off_o, votes_o) = _oracle_align(roiA, roiB)
+    ga = gpu.surf_detect_and_describe(roiA, extended=True, keypoints_ratio=0.01)
+    gb = gpu.surf_detect_and_describe(roiB, extended=True, keypoints_ratio=0.01)
+    _assert_surf_equal(ga, fa); _assert_surf_equal(gb, fb)
+    assert np.array_equal(gpu.match_descriptors(ga[1], gb[1], 2, 0.75), m_o)
+    r = gpu.align_batch(roiA[None], roiB[None])[0]
+    assert (int(r["n_a"]), int(r["n_b"]), int(r["n_matches"])) == (len(fa[0]), len(fb[0]), len(m_o))
+    assert (bool(r["status"]), [int(r["d_row"]), int(r["d_col"])], int(r["votes"])) == (st_o, off_o, votes_o)
+    assert st_o and abs(off_o[0] + 2048 - L - off[0]) <= 1 and abs(off_o[1] - off[1]) <= 1
+
+
+def test_c1_iron_roi_pair_equals_oracle(gpu, golden_dir):
+    """BASELINE configs[0]: the 387 x 2584 ROI strips of demoImages/iron (committed as PNG fixtures) through align_batch."""
+    import os
+    import cv2
+    roiA = cv2.imread(os.path.join(golden_dir, "iron_A_dir1.png"), cv2.IMREAD_GRAYSCALE)
+    roiB = cv2.imread(os.path.join(golden_dir, "iron_B_dir1.png"), cv2.IMREAD_GRAYSCALE)
+    fa, fb, m_o, (st_o, off_o, votes_o) = _oracle_align(roiA, roiB)
+    _assert_surf_equal(gpu.surf_detect_and_describe(roiA, extended=True, keypoints_ratio=0.01), fa)
+    r = gpu.align_batch(roiA[None], roiB[None])[0]
+    assert (int(r["n_a"]), int(r["n_b"]), int(r["n_matches"])) == (len(fa[0]), len(fb[0]), len(m_o))
+    assert (bool(r["status"]), [int(r["d_row"]), int(r["d_col"])], int(r["votes"])) == (st_o, off_o, votes_o)
+    assert st_o and abs(off_o[0] + 1936 - 387 - 1698) <= 1 and off_o[1] == 0           # BASELINE.md: [1698..1699, 0]

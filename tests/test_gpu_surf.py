@@ -32,10 +32,8 @@ def _compare_surf(gpu, img, extended, ratio, upright=False, thr=100.0):
         assert np.array_equal(kp_g[:, col], kp_o[:, col]), "column %d differs" % col
     # orientation: same polynomial atan, same summation order -> exact
     assert np.array_equal(kp_g[:, 3], kp_o[:, 3])
-    # descriptors: identical up to sin/cos ulp effects on a handful of window pixels
-    err = np.abs(d_g - d_o).max(axis=1)
-    assert np.mean(err < 1e-6) > 0.99, np.mean(err < 1e-6)
-    assert err.max() < 0.05, err.max()
+    # descriptors: bit for bit (the oracle takes the correctly rounded sin / cos of the orientation, like the device code)
+    assert np.array_equal(d_g, d_o), (np.abs(d_g - d_o).max(), int((np.abs(d_g - d_o).max(axis=1) > 0).sum()))
     return kp_g, d_g, kp_o, d_o
 
 
@@ -134,7 +132,7 @@ def test_align_batch_matches_stagewise(gpu, synth_pair_rois):
     st, off, votes = surf.offset_by_mode(kA, kB, m, 3)
     for r in res:
         assert r["n_a"] == len(kA) and r["n_b"] == len(kB)
-        assert abs(int(r["n_matches"]) - len(m)) <= max(2, len(m) // 200)     # descriptor ulp noise at the ratio boundary
+        assert int(r["n_matches"]) == len(m)
         assert bool(r["status"]) == st and [int(r["d_row"]), int(r["d_col"])] == off
-        assert abs(int(r["votes"]) - votes) <= max(2, votes // 100)
+        assert int(r["votes"]) == votes
     assert abs(off[0] - true_off[0]) <= 1 and abs(off[1] - true_off[1]) <= 1

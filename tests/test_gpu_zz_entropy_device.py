@@ -11,9 +11,10 @@ pytestmark = pytest.mark.gpu
 def gpu():
     from imagestitch_b200 import gpu as g
     assert g.device_count() > 0, "no CUDA device: the product path has no CPU fallback"
+    default = g.get_option("entropy")
     g.set_option("entropy", 1)
     yield g
-    g.set_option("entropy", 0)
+    g.set_option("entropy", default)
 
 
 def _content():

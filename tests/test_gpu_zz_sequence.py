@@ -17,12 +17,13 @@ def _run(root, out, decoder, encoder, entropy):
     Stitcher.searchRatio = 0.75; Stitcher.offsetCaculate = "mode"; Stitcher.offsetEvaluate = 3; Stitcher.roiRatio = 0.2
     Stitcher.fuseMethod = "fadeInAndFadeOut"; Stitcher.direction = 1; Stitcher.directIncre = 1; Stitcher.isPrintLog = False
     Stitcher.decoder = decoder; Stitcher.encoder = encoder
+    default_entropy = gpu.get_option("entropy")
     gpu.set_option("entropy", entropy)
     try:
         st = Stitcher()
         st.imageSetStitchWithMutiple(root, out, 1, st.calculateOffsetForFeatureSearchIncre, fileExtension="jpg", outputfileExtension="jpg")
     finally:
-        gpu.set_option("entropy", 0)
+        gpu.set_option("entropy", default_entropy)
         Stitcher.decoder = "b200"; Stitcher.encoder = "b200"; Stitcher.isPrintLog = True; Stitcher.fuseMethod = "notFuse"; Stitcher.direction = 1
     names = sorted(os.listdir(out))
     return {n: open(os.path.join(out, n), "rb").read() for n in names}

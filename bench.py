@@ -295,12 +295,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--matcher", default=None, choices=["tc", "tc_1sm", "simt"], help="override the descriptor matcher kernel")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
-                    help="kernel-variant switch (include/vfsms.h VFSMS_OPT_*, e.g. describe=2, sort=1); identical results, A/B timing")
-    ap.add_argument("--autotune", action="store_true",
-                    help="opt-in: imagestitch_b200.autotune picks, in a subprocess, the kernel variants that are bit-identical to the default "
-                         "schedule on this workload shape AND faster.  Off by default: the bench times the library's default schedule, the "
-                         "one the oracle tests run on, and no number depends on a racing probe")
-    ap.add_argument("--no-autotune", action="store_true", help=argparse.SUPPRESS)      # accepted for old command lines; autotune is off anyway
+                    help="kernel-schedule switch (include/vfsms.h VFSMS_OPT_*, e.g. describe=0, lpt=1); identical results, A/B timing.  Without it the "
+                         "bench times the library's default schedule, the one the oracle tests run on")
+    ap.add_argument("--no-autotune", action="store_true", help=argparse.SUPPRESS)      # accepted for old command lines: there is no autotune
     ap.add_argument("--aux-probe", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--aux-device", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
@@ -323,11 +320,6 @@ def main():
     params = gpu.surf_params()          # GPU-SURF defaults, ImageUtility.py:23-28
     if args.matcher:
         gpu.set_matcher(args.matcher, device=local)
-    tune_report = None
-    if args.autotune and not args.opt:
-        from imagestitch_b200 import autotune
-        chosen, tune_report = autotune.select(device=local, pairs=P, size=TILE, overlap=OVERLAP)
-        args.opt = ["%s=%d" % kv for kv in chosen.items()]
     for item in args.opt:
         name, value = item.split("=")
         gpu.set_option(name, int(value), device=local)
@@ -522,7 +514,7 @@ def main():
                       "pairs_per_gpu_per_step": P, "global_pairs_per_step": P * world, "roi": [L, TILE], "surf": "thr100 oct4 layers3 128-d ratio0.01",
                       "l2": "%d distinct input batches rotated; per-step intermediate traffic > L2" % NB,
                       "mean_keypoints": [mean_na, mean_nb], "mean_matches": float(np.mean(nmatch)), "correct_pairs": "%d/%d" % (ok, tot),
-                      "e2e_correct_pairs": "%d/%d" % (e2e_ok, P), "kernel_variants": variants, "autotune": tune_report},
+                      "e2e_correct_pairs": "%d/%d" % (e2e_ok, P), "kernel_variants": variants},
            "clocks": clk, "gpu_launches": int(launches),
            "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * P * L * TILE), "d2h_bytes_per_step": int(P * 32),
                    "steps": e2e_steps},

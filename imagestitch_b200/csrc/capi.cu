@@ -122,6 +122,17 @@ int vfsms_last_match_fallbacks(vfsms_ctx *ctx, int *count_out)
     return 0;
 }
 
+int vfsms_last_describe_handovers(vfsms_ctx *ctx, int *count_out)
+{
+    if (!ctx || !count_out) return VFSMS_E_ARG;
+    *count_out = 0;
+    if (!ctx->surf.counters.p || ctx->surf.batch <= 0) return 0;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(count_out, ctx->surf.counters.as<int32_t>() + (size_t)ctx->surf.last_batch * 4 + 2, 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int vfsms_version(void) { return VFSMS_VERSION; }
 const char *vfsms_last_error(void) { return g_err; }
 
@@ -169,7 +180,7 @@ void vfsms_destroy(vfsms_ctx *ctx)
     surf_tex_destroy(ctx);
     ctx->tex_dev.release();
     SurfWorkspace &w = ctx->surf;
-    DevBuf *bufs[] = { &w.integral, &w.band_tot, &w.cand, &w.sorted, &w.kp, &w.desc, &w.descT, &w.counters, &w.prefix, &w.hist, &w.img_f32,
+    DevBuf *bufs[] = { &w.integral, &w.band_tot, &w.cand, &w.sorted, &w.kp, &w.desc, &w.descT, &w.counters, &w.prefix, &w.hist, &w.img_f32, &w.fb_list,
                        &ctx->match.best_idx, &ctx->match.best_dist, &ctx->match.matches, &ctx->match.n_matches,
                        &ctx->match.table_keys, &ctx->match.table_cnt, &ctx->match.table_first, &ctx->match.bf16_a,
                        &ctx->match.bf16_b, &ctx->match.cand_topk, &ctx->img_a, &ctx->img_b, &ctx->results,

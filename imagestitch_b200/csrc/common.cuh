@@ -114,8 +114,10 @@ struct SurfWorkspace {
     DevBuf counters;         // [batch][4] int32 : n_cand, n_sorted, n_final, flags
     DevBuf prefix;           // [batch+1] int32 prefix of n_final
     DevBuf hist;             // [batch][2048] response histogram + [batch] thresholds
-    DevBuf img_f32;          // [batch][rows][pitch_f] float copy of the images (texture source of the descriptor stage)
+    DevBuf img_f32;          // [batch][rows][pitch_f] float copy of the images * 2^-64 (texture source of the descriptor stage)
+    DevBuf fb_list;          // [batch * kp_cap] int32: keypoints the fixed-point sampler hands to the reference sampler
     int pitch_f = 0;
+    int last_batch = 0;      // batch of the last surf_run_batch (the work counters sit after its per-image counters)
 };
 
 struct MatchWorkspace {
@@ -138,7 +140,7 @@ struct vfsms_ctx {
     int32_t prof_calls[VFSMS_STAGE_COUNT] = {0};
     int device = 0;
     int matcher_mode = 0;          // 0: tcgen05 candidates + exact rescoring, 1: exact SIMT kernel
-    int describe_mode = 2;         // window sampler of the SURF descriptor: 0 LDG, 1 texture per image, 2 one stacked texture (default; vfsms_set_option)
+    int describe_mode = 1;         // window sampler of the SURF descriptor: 0 reference (double precision, u8 image), 1 fixed-point chunked texture sampler (default)
     int describe_lpt = 2;          // describe the large windows first (two passes over the work list): 0 off, 1 / 2 / 3 = split at 128 / 64 / 256 px
     int sort_mode = 1;             // KeypointGreater ordering: 0 rank by counting over all candidates, 1 rank inside response bins (default)
     int32_t *last_fallback_count_dev = nullptr;

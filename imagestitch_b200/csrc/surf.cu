@@ -868,470 +868,9 @@ __device__ __forceinline__ int box_sum(const int32_t *__restrict__ o, int W, int
     return __ldg(o + y1 * W + x1) + __ldg(o + y2 * W + x2) - __ldg(o + y2 * W + x1) - __ldg(o + y1 * W + x2);
 }
 
-// bilinear / clamped sample of the rotated window, rounded to u8 exactly like the CPU loop
-__device__ __forceinline__ int window_pixel(const uint8_t *__restrict__ img, int stride, int ncols1, int nrows1,
-                                            double pixel_x, double pixel_y)
-{
-    const int ix = __double2int_rd(pixel_x), iy = __double2int_rd(pixel_y);
-    if ((unsigned)ix < (unsigned)ncols1 && (unsigned)iy < (unsigned)nrows1) {
-        const float a = (float)(pixel_x - ix), bq = (float)(pixel_y - iy);
-        const uint8_t *p = img + (size_t)iy * stride + ix;
-        const float p00 = p[0], p01 = p[1], p10 = p[stride], p11 = p[stride + 1];
-        const float v = p00 * (1.f - a) * (1.f - bq) + p01 * a * (1.f - bq) + p10 * (1.f - a) * bq + p11 * a * bq;
-        return __float2int_rn(v) & 255;
-    }
-    int x = __double2int_rn(pixel_x), y = __double2int_rn(pixel_y);
-    x = min(max(x, 0), ncols1); y = min(max(y, 0), nrows1);
-    return img[(size_t)y * stride + x];
-}
+#include "surf_describe.cuh"
 
-// Conversion-free helpers: int<->float conversions run on the quarter-rate XU pipe, which was the limiter of the
-// descriptor kernel (ncu: pipe_xu 67%).  These are exact replacements on the FP32 / FP64 / ALU pipes.
-__device__ __forceinline__ float u8_to_float(unsigned v) { return __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7650)) - 8388608.0f; }   // low byte of v
-__device__ __forceinline__ int round_half_even_u8(float v)      // cvRound for 0 <= v < 2^22
-{
-    return __float_as_int(v + 12582912.0f) - 0x4B400000;
-}
-// floor-like split of x (|x| < 2^31) into an integer i and f = x - i with 0 <= f <= 1:  i = rn(x - 0.5).  It equals
-// floor(x) except when x is an exact integer n and the tie rounds down (i = n - 1, f = 1); the bilinear expression then
-// yields the same value (weights 0 / 1 move to the neighbouring texel: p[n-1]*0 + p[n]*1), and so does the border path,
-// so the result is identical to the CPU's floor-based code while saving the compare / select / fix-up sequence.
-__device__ __forceinline__ int floor_split(double x, double &fl)
-{
-    const double M = 6755399441055744.0;     // 1.5 * 2^52: adding it rounds to the nearest integer (ties to even)
-    const double t = (x - 0.5) + M;
-    fl = t - M;
-    return __double2loint(t);
-}
-
-// TEX variant: one tex2Dgather on a float copy of the image returns the whole 2x2 footprint as exact floats.
-// Returns the window pixel (cvRound of the bilinear value, 0..255) as an exact float: v + 1.5*2^23 - 1.5*2^23 rounds half to
-// even without leaving the FP32 pipe.
-__device__ __forceinline__ float window_pixel_tex(cudaTextureObject_t tex, const uint8_t *__restrict__ img, int stride,
-                                                  int ncols1, int nrows1, double pixel_x, double pixel_y)
-{
-    double fx, fy;
-    const int ix = floor_split(pixel_x, fx), iy = floor_split(pixel_y, fy);
-    if ((unsigned)ix < (unsigned)ncols1 && (unsigned)iy < (unsigned)nrows1) {
-        const float a = (float)(pixel_x - fx), bq = (float)(pixel_y - fy);
-        const float tx = __uint_as_float(0x4B000000u | (unsigned)ix) - 8388607.0f;      // ix + 1.0f, exact
-        const float ty = __uint_as_float(0x4B000000u | (unsigned)iy) - 8388607.0f;
-        const float4 g = tex2Dgather<float4>(tex, tx, ty, 0);
-        const float p00 = g.w, p01 = g.z, p10 = g.x, p11 = g.y;
-        const float v = p00 * (1.f - a) * (1.f - bq) + p01 * a * (1.f - bq) + p10 * (1.f - a) * bq + p11 * a * bq;
-        return (v + 12582912.0f) - 12582912.0f;
-    }
-    int x = __double2int_rn(pixel_x), y = __double2int_rn(pixel_y);
-    x = min(max(x, 0), ncols1); y = min(max(y, 0), nrows1);
-    return (float)img[(size_t)y * stride + x];
-}
-
-// STACKED variant (describe mode 2): all images of the batch live in ONE pitch-2D float texture, image b at rows
-// [b * rows, (b + 1) * rows), and the handle is a kernel parameter.  A handle loaded from memory through a shuffled index is
-// not provably warp-uniform, so the per-image variant compiles to a waterfall loop (R2UR / TLD4 / BRA.U.ANY, 9 extra
-// instructions per sample); a parameter goes to the texture unit straight from a uniform register.  The image's row offset
-// is folded into the constant of the exact int -> float step: ty_bias = 8388607 - row_off (an exact float), so
-// (2^23 + iy) - ty_bias = iy + 1 + row_off at no extra cost.  CHECK = false: the caller has proved that every sample of the
-// window has its 2x2 footprint inside the image (warp-uniform per keypoint), the border path is not compiled in.
-template <bool CHECK>
-__device__ __forceinline__ float window_pixel_stack(cudaTextureObject_t tex, const uint8_t *__restrict__ img, int stride,
-                                                    int ncols1, int nrows1, double pixel_x, double pixel_y, float ty_bias)
-{
-    double fx, fy;
-    const int ix = floor_split(pixel_x, fx), iy = floor_split(pixel_y, fy);
-    if (!CHECK || ((unsigned)ix < (unsigned)ncols1 && (unsigned)iy < (unsigned)nrows1)) {
-        const float a = (float)(pixel_x - fx), bq = (float)(pixel_y - fy);
-        const float tx = __uint_as_float(0x4B000000u | (unsigned)ix) - 8388607.0f;      // ix + 1.0f, exact
-        const float ty = __uint_as_float(0x4B000000u | (unsigned)iy) - ty_bias;         // iy + 1.0f + row_off, exact
-        const float4 g = tex2Dgather<float4>(tex, tx, ty, 0);
-        const float p00 = g.w, p01 = g.z, p10 = g.x, p11 = g.y;
-        const float v = p00 * (1.f - a) * (1.f - bq) + p01 * a * (1.f - bq) + p10 * (1.f - a) * bq + p11 * a * bq;
-        return (v + 12582912.0f) - 12582912.0f;
-    }
-    int x = __double2int_rn(pixel_x), y = __double2int_rn(pixel_y);
-    x = min(max(x, 0), ncols1); y = min(max(y, 0), nrows1);
-    return (float)img[(size_t)y * stride + x];
-}
-
-// FIXED-POINT variant (describe modes 7 / 8) for windows that lie inside the image: the sample position in 32.32 fixed point.
-// The CPU walks pixel_x = start_x + j * cos_dir in double, where every term is a float: for start_x >= 1 (ulp >= 2^-23) and
-// |cos_dir| >= 2^-9 or 0 (ulp >= 2^-32) all positions are multiples of 2^-32 below 2^13, i.e. EXACT 45-bit integers X = x * 2^32.
-// Then floor(x) is the high word, and the CPU's a = (float)(pixel_x - ix) -- one rounding of an exact difference -- is
-// RN(low word) * 2^-32 (a power-of-two scale commutes with the rounding).  Per sample: two 64-bit integer adds and two
-// conversions instead of ten double-precision adds and two conversions; the gather, the blend and the rounding are unchanged.
-__device__ __forceinline__ float window_pixel_fixed(cudaTextureObject_t tex, unsigned long long X, unsigned long long Y, float ty_bias)
-{
-    const unsigned ix = (unsigned)(X >> 32), iy = (unsigned)(Y >> 32);
-    const float a = __uint2float_rn((unsigned)X) * 2.3283064365386963e-10f;
-    const float bq = __uint2float_rn((unsigned)Y) * 2.3283064365386963e-10f;
-    const float tx = __uint_as_float(0x4B000000u | ix) - 8388607.0f;       // ix + 1.0f, exact
-    const float ty = __uint_as_float(0x4B000000u | iy) - ty_bias;          // iy + 1.0f + row_off, exact
-    const float4 g = tex2Dgather<float4>(tex, tx, ty, 0);
-    const float p00 = g.w, p01 = g.z, p10 = g.x, p11 = g.y;
-    const float v = p00 * (1.f - a) * (1.f - bq) + p01 * a * (1.f - bq) + p10 * (1.f - a) * bq + p11 * a * bq;
-    return (v + 12582912.0f) - 12582912.0f;
-}
-
-// The same for windows that cross the image border: signed positions (arithmetic shift = floor), the bounds test on the integer
-// parts, and the CPU's clamped nearest pixel cvRound(pixel_x) = round-half-to-even of X / 2^32 from the fraction word.
-__device__ __forceinline__ float window_pixel_fixed_checked(cudaTextureObject_t tex, const uint8_t *__restrict__ img, int stride, int ncols1,
-                                                            int nrows1, long long X, long long Y, float ty_bias)
-{
-    const int ix = (int)(X >> 32), iy = (int)(Y >> 32);
-    if ((unsigned)ix < (unsigned)ncols1 && (unsigned)iy < (unsigned)nrows1)
-        return window_pixel_fixed(tex, (unsigned long long)X, (unsigned long long)Y, ty_bias);
-    const unsigned fx = (unsigned)X, fy = (unsigned)Y;
-    int x = ix + ((fx > 0x80000000u || (fx == 0x80000000u && (ix & 1))) ? 1 : 0);
-    int y = iy + ((fy > 0x80000000u || (fy == 0x80000000u && (iy & 1))) ? 1 : 0);
-    x = min(max(x, 0), ncols1); y = min(max(y, 0), nrows1);
-    return (float)img[(size_t)y * stride + x];
-}
-
-// float copy of the batch's images for the texture path (pitch in floats)
-__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride,
-                                                        int rows, int cols, int stride, float *dst, int pitch_f)
-{
-    const int b = blockIdx.y;
-    const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
-    float *D = dst + (size_t)b * rows * pitch_f;
-    const int total = rows * cols;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int y = i / cols, x = i - y * cols;
-        D[(size_t)y * pitch_f + x] = (float)img[(size_t)y * stride + x];
-    }
-}
-
-#define DESC_THREADS 256
-#define SURF_MAX_DESC_CHUNKS 64   // describe mode 2: launches per batch (one stacked texture each)
-#define WK_MAX_WIN 768       // windows up to this size are described by one warp (n_octaves <= 4 never exceeds 739)
-#define WK_WARPS 8
-
-// ---------------------------------------------------------------- K4a: orientation + descriptor, one WARP per keypoint
-// Same arithmetic and summation orders as the scalar CPU code, different schedule:
-//   * no block-level barriers: 8 keypoints in flight per CTA, up to 32 per SM, so the order-preserving serial
-//     sections of one keypoint overlap with other keypoints;
-//   * the 20s window is never materialised: its rows are sampled ONCE each, in order (the start_x += sin / start_y += cos
-//     chain advances exactly like the CPU loop), into a per-warp row buffer, and folded straight into the INTER_AREA
-//     accumulators of the 21 patch columns (lane dx owns column dx);
-//   * descriptor bins: lane = (cell, half) accumulates its 4 bins with predicated adds in raster order.
-struct __align__(16) WarpScratch {
-    float buf[800];              // orientation: X[0..127] Y[128..255] A[256..383] (int) ; window phase: one sampled row as exact
-                                 // floats (<= WK_MAX_WIN = 768 entries) ; descriptor: DX[0..399] DY[400..799]
-    float vec[128];
-    uint8_t patch[448];
-};
-
-// 64 registers / 4 CTAs per SM with the sampler unrolled x2 measured best on B200 (80 registers / 3 CTAs / x4: +20 % time).
-// MODE 0: LDG sampler, 1: one texture per image (handles in `texs`), 2: one stacked texture (`tex_stack`, a kernel parameter)
-// over the images [b_first, b_first + b_count) -- this launch describes only their keypoints.
-// UNROLL / MINB: unroll factor of the border-free sampling loop and CTAs per SM the register budget is cut for (4 -> 64
-// registers, 3 -> 80, 5 -> 48): with no branch in the loop, a deeper unroll lets several gathers be in flight per warp; more
-// resident warps hide the gather latency the other way (ncu, 4 CTAs: 47 % warps active, 37 % of the stalls on the gather; with
-// 48 registers ptxas spills 72 bytes, all outside the sampling loops).
-template <int MODE, int UNROLL = 2, int MINB = 4>
-__global__ void __launch_bounds__(WK_WARPS * 32, MINB) orient_describe_warp_kernel(
-    const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
-    const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
-    int batch, int kp_cap, int extended, int upright, const cudaTextureObject_t *__restrict__ texs, int *work_counter,
-    int *big_flag, const cudaTextureObject_t tex_stack, int b_first, int b_count, int *work_counter_large, int lpt_split)
-{
-    constexpr bool TEX = MODE == 1;
-    constexpr bool STACK = MODE >= 2;        // MODE 3 = 2 with fixed-point coordinates in the border-free loop (window_pixel_fixed)
-    constexpr bool FIXED = MODE == 3;
-    __shared__ WarpScratch s_ws[WK_WARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpScratch &S = s_ws[warp];
-    const int total = STACK ? prefix[b_first + b_count] : prefix[batch];
-    const int item0 = STACK ? prefix[b_first] : 0;
-    const int W = cols + 1, srows = rows + 1, scols = cols + 1;
-    const int dsize = extended ? 128 : 64;
-    const unsigned lt_mask = (1u << lane) - 1;
-    constexpr int PD = PATCH_SZ + 1;
-
-    // lpt_split > 0 (VFSMS_OPT_DESCRIBE_LPT): longest-processing-time-first in two passes over the same work list -- pass 0
-    // describes only the windows >= lpt_split (a 600-pixel window keeps one warp busy for over a millisecond; met late in the
-    // queue it becomes the tail of the launch), pass 1 the rest.  A skipped item costs one keypoint read.
-    int pass = lpt_split > 0 ? 0 : 1;
-    while (true) {
-        // dynamic work distribution: window sizes have a heavy tail, a static split leaves warps idle behind giants
-        int item = 0;
-        if (lane == 0) item = atomicAdd(pass == 0 ? work_counter_large : work_counter, 1);
-        item = __shfl_sync(0xffffffffu, item, 0) + item0;
-        if (item >= total) { if (pass == 0) { pass = 1; continue; } break; }
-        int lo = 0, hi = batch;
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(prefix + mid) <= item) lo = mid; else hi = mid; }
-        const int b = lo, k = item - __ldg(prefix + lo);
-        float *kp = kp_all + ((size_t)b * kp_cap + k) * KP_STRIDE;
-        const float size = kp[KP_SIZE], cx = kp[KP_X], cy = kp[KP_Y];
-        const float s = size * 1.2f / 9.0f;
-        const int win = (int)((PATCH_SZ + 1) * s);
-        if (lpt_split > 0 && ((win >= lpt_split) != (pass == 0))) continue;   // warp-uniform: the other pass owns this keypoint
-        if (win > WK_MAX_WIN) { if (lane == 0) *big_flag = 1; continue; }     // warp-uniform: flag work for the CTA kernel
-        const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
-        const int32_t *I = integral + (size_t)b * srows * W;
-        const int gws = 2 * __float2int_rn(2 * s);
-        cudaTextureObject_t tex = 0;
-        if (TEX) tex = texs[b];
-
-        float descriptor_dir = 360.f - 90.f;
-        if (!upright) {
-            float *sX = S.buf, *sY = S.buf + 128; int *sA = (int *)(S.buf + 256);
-            const int h2 = __float2int_rn(((float)gws / 4) * 2);
-            const int h4 = __float2int_rn(((float)gws / 4) * 4);
-            const float wgt = 1.f / ((float)(h2) * (float)(h4));
-            const float half = (float)(gws - 1) / 2;
-            int nangle = 0;
-#pragma unroll 1
-            for (int r = 0; r < 4; r++) {
-                const int kk = r * 32 + lane;
-                bool have = false; float vX = 0, vY = 0;
-                if (kk < ORI_SAMPLES) {
-                    const int x = __float2int_rn(cx + c_apt_x[kk] * s - half);
-                    const int y = __float2int_rn(cy + c_apt_y[kk] * s - half);
-                    if (!(y < 0 || y >= srows - gws || x < 0 || x >= scols - gws)) {
-                        const int32_t *o = I + (size_t)y * W + x;
-                        // 3x3 grid of integral corners shared by the four half boxes
-                        const int a00 = __ldg(o), a01 = __ldg(o + h2), a02 = __ldg(o + h4);
-                        const int32_t *o1 = o + (size_t)h2 * W, *o2 = o + (size_t)h4 * W;
-                        const int a10 = __ldg(o1), a12 = __ldg(o1 + h4);
-                        const int a20 = __ldg(o2), a21 = __ldg(o2 + h2), a22 = __ldg(o2 + h4);
-                        const int bl = a00 + a21 - a20 - a01;          // x in [0,h2), y in [0,h4)
-                        const int br = a01 + a22 - a21 - a02;          // x in [h2,h4)
-                        const int bt = a00 + a12 - a10 - a02;          // y in [0,h2)
-                        const int bb = a10 + a22 - a20 - a12;          // y in [h2,h4)
-                        double d = 0; d += (double)((float)bl * (-wgt)); d += (double)((float)br * wgt);
-                        const float vx = (float)d;
-                        d = 0; d += (double)((float)bt * wgt); d += (double)((float)bb * (-wgt));
-                        const float vy = (float)d;
-                        vX = vx * c_aptw[kk]; vY = vy * c_aptw[kk];
-                        have = true;
-                    }
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, have);
-                if (have) {
-                    const int pos = nangle + __popc(bal & lt_mask);
-                    sX[pos] = vX; sY[pos] = vY; sA[pos] = __float2int_rn(fast_atan2_deg(vY, vX));
-                }
-                nangle += __popc(bal);
-            }
-            __syncwarp();
-            float bmod = 0, bx = 0, by = 0; int bw = 1 << 30;
-#pragma unroll 1
-            for (int w = lane; w < 72; w += 32) {
-                const int i = w * 5;
-                float sumx = 0, sumy = 0;
-                for (int j = 0; j < nangle; j++) {
-                    const int d = abs(sA[j] - i);
-                    if (d < ORI_WIN / 2 || d > 360 - ORI_WIN / 2) { sumx += sX[j]; sumy += sY[j]; }
-                }
-                const float m = sumx * sumx + sumy * sumy;
-                if (m > bmod) { bmod = m; bx = sumx; by = sumy; bw = w; }
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const float om = __shfl_xor_sync(0xffffffffu, bmod, o), ox = __shfl_xor_sync(0xffffffffu, bx, o),
-                            oy = __shfl_xor_sync(0xffffffffu, by, o);
-                const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
-                if (om > bmod || (om == bmod && ow < bw)) { bmod = om; bx = ox; by = oy; bw = ow; }
-            }
-            descriptor_dir = fast_atan2_deg(-by, bx);
-            __syncwarp();
-        }
-        if (lane == 0) kp[KP_ANGLE] = descriptor_dir;
-
-        // ---- window rows -> INTER_AREA patch
-        const int ncols1 = cols - 1, nrows1 = rows - 1;
-        float sin_dir = 0, cos_dir = 0, chain_x = 0, chain_y = 0;     // chain_*: start_x / start_y of row `cur_row + 1`
-        int ustart_x = 0, ustart_y = 0;
-        if (!upright) {
-            const float dir_rad = descriptor_dir * (float)(M_PI / 180);
-            sin_dir = -(float)sin((double)dir_rad);
-            cos_dir = (float)cos((double)dir_rad);
-            const float win_offset = -(float)(win - 1) / 2;
-            chain_x = cx + win_offset * cos_dir + win_offset * sin_dir;
-            chain_y = cy - win_offset * sin_dir + win_offset * cos_dir;
-        } else {
-            const float win_offset = -(float)(win - 1) / 2;
-            ustart_x = __float2int_rn(cx + win_offset);
-            ustart_y = __float2int_rn(cy - win_offset);
-        }
-        // mode 2: row offset of image b inside the stacked texture, and whether the whole rotated window (half diagonal + the
-        // float chain's drift, 2 px of slack) keeps every 2x2 footprint inside the image
-        float ty_bias = 8388607.0f;
-        bool interior = false;
-        bool fixed_ok = false, dir_ok = false;
-        long long cos_fx = 0, sin_fx = 0;       // cos_dir, sin_dir * 2^32
-        if (STACK) {
-            ty_bias = 8388607.0f - (float)((b - b_first) * rows);
-            const float R = (float)(win - 1) * 0.7072f + 2.0f;
-            interior = !upright && cx - R >= 1.f && cx + R <= (float)(ncols1 - 1) && cy - R >= 1.f && cy + R <= (float)(nrows1 - 1);
-            if (FIXED && !upright) {
-                const float ac = fabsf(cos_dir), as = fabsf(sin_dir);
-                dir_ok = (ac == 0.f || ac >= 0.001953125f) && (as == 0.f || as >= 0.001953125f);       // ulp >= 2^-32
-                fixed_ok = dir_ok && interior;
-                cos_fx = (long long)((double)cos_dir * 4294967296.0);
-                sin_fx = (long long)((double)sin_dir * 4294967296.0);
-            }
-        }
-        float *rowf = S.buf;              // the orientation scratch is free now: one window row as exact float pixel values
-        int cur_row = -1;                 // row currently held in rowf
-        // sample window row `r` (>= cur_row) into rowf; rows are requested in nondecreasing order
-        auto fetch_row = [&](int r) {
-            if (r == cur_row) return;
-            __syncwarp();
-            if (!upright) {
-                while (cur_row < r - 1) { chain_x += sin_dir; chain_y += cos_dir; cur_row++; }   // skipped rows still advance the chain
-                const double rx = (double)chain_x, ry = (double)chain_y;
-                // per-lane positions advance by 32 columns per round; all terms are exact in double (24-bit increments,
-                // |x| < 2^13), so the running sum equals the CPU's column-by-column accumulation
-                double px = rx + (double)lane * (double)cos_dir, py = ry - (double)lane * (double)sin_dir;
-                const double dpx = 32.0 * (double)cos_dir, dpy = 32.0 * (double)sin_dir;
-                if (STACK) {
-                    if (FIXED && fixed_ok) {
-                        // interior: every position is >= 1, so rx * 2^32 and all sums below are exact non-negative integers
-                        unsigned long long X = (unsigned long long)(rx * 4294967296.0) + (unsigned long long)((long long)lane * cos_fx);
-                        unsigned long long Y = (unsigned long long)(ry * 4294967296.0) - (unsigned long long)((long long)lane * sin_fx);
-                        const unsigned long long dX = (unsigned long long)(32 * cos_fx), dY = (unsigned long long)(32 * sin_fx);
-#pragma unroll UNROLL
-                        for (int j = lane; j < win; j += 32, X += dX, Y -= dY) rowf[j] = window_pixel_fixed(tex_stack, X, Y, ty_bias);
-                    } else if (FIXED && dir_ok && (chain_x == 0.f || fabsf(chain_x) >= 0.001953125f) && (chain_y == 0.f || fabsf(chain_y) >= 0.001953125f)) {
-                        // a window that crosses the border, row start with ulp >= 2^-32 (warp-uniform): signed fixed point
-                        long long X = (long long)(rx * 4294967296.0) + (long long)lane * cos_fx;
-                        long long Y = (long long)(ry * 4294967296.0) - (long long)lane * sin_fx;
-                        const long long dX = 32 * cos_fx, dY = 32 * sin_fx;
-#pragma unroll 2
-                        for (int j = lane; j < win; j += 32, X += dX, Y -= dY)
-                            rowf[j] = window_pixel_fixed_checked(tex_stack, img, stride, ncols1, nrows1, X, Y, ty_bias);
-                    } else if (interior) {
-#pragma unroll UNROLL
-                        for (int j = lane; j < win; j += 32, px += dpx, py -= dpy)
-                            rowf[j] = window_pixel_stack<false>(tex_stack, img, stride, ncols1, nrows1, px, py, ty_bias);
-                    } else {
-#pragma unroll 2
-                        for (int j = lane; j < win; j += 32, px += dpx, py -= dpy)
-                            rowf[j] = window_pixel_stack<true>(tex_stack, img, stride, ncols1, nrows1, px, py, ty_bias);
-                    }
-                } else {
-#pragma unroll 2
-                for (int j = lane; j < win; j += 32, px += dpx, py -= dpy) {
-                    rowf[j] = TEX ? window_pixel_tex(tex, img, stride, ncols1, nrows1, px, py)
-                                  : (float)window_pixel(img, stride, ncols1, nrows1, px, py);
-                }
-                }
-                chain_x += sin_dir; chain_y += cos_dir;
-            } else {
-                const int x = min(max(ustart_x + r, 0), cols - 1);
-                for (int j = lane; j < win; j += 32) {
-                    const int y = min(max(ustart_y - j, 0), rows - 1);
-                    rowf[j] = (float)img[(size_t)y * stride + x];
-                }
-            }
-            cur_row = r;
-            __syncwarp();
-        };
-
-        const double inv_scale = (double)PD / win;
-        const double scale = 1. / inv_scale;
-        const int iscale = __double2int_rn(scale);
-        const bool area_fast = fabs(scale - iscale) < DBL_EPSILON;
-        const int dx = lane < PD ? lane : PD - 1;           // lanes >= 21 shadow column 20 (results discarded)
-        if (win == PD) {
-            for (int dy = 0; dy < PD; dy++) { fetch_row(dy); if (lane < PD) S.patch[dy * PD + lane] = (uint8_t)(int)rowf[lane]; }
-        } else if (area_fast) {
-            const float fs = 1.f / (float)(iscale * iscale);
-            for (int dy = 0; dy < PD; dy++) {
-                float sumf = 0;            // integer box sum (<= 35^2 * 255): exact in float
-                for (int yy = 0; yy < iscale; yy++) {
-                    fetch_row(dy * iscale + yy);
-                    for (int xx = 0; xx < iscale; xx++) sumf += rowf[dx * iscale + xx];
-                }
-                int out;
-                if (iscale == 2) out = (int)((sumf + 2.f) * 0.25f);          // (sum + 2) >> 2
-                else out = min(max(__float2int_rn(sumf * fs), 0), 255);
-                if (lane < PD) S.patch[dy * PD + lane] = (uint8_t)out;
-            }
-        } else {
-            // column taps of this lane (decimation table entries of output column dx, in table order)
-            const double fsx1 = dx * scale, fsx2 = fsx1 + scale, cwx = fmin(scale, win - fsx1);
-            int sx1 = __double2int_ru(fsx1), sx2 = __double2int_rd(fsx2);
-            sx2 = min(sx2, win - 1); sx1 = min(sx1, sx2);
-            const bool xl = (sx1 - fsx1 > 1e-3), xr = (fsx2 - sx2 > 1e-3);
-            const float axl = (float)((sx1 - fsx1) / cwx), axm = (float)(1.0 / cwx),
-                        axr = (float)(fmin(fmin(fsx2 - sx2, 1.), cwx) / cwx);
-            for (int dy = 0; dy < PD; dy++) {
-                // the row table of output row dy equals the column table of output column dy (square window, same scale):
-                // take lane dy's parameters instead of redoing the double-precision divisions
-                const int sy1 = __shfl_sync(0xffffffffu, sx1, dy), sy2 = __shfl_sync(0xffffffffu, sx2, dy);
-                const bool yl = __shfl_sync(0xffffffffu, (int)xl, dy) != 0, yr = __shfl_sync(0xffffffffu, (int)xr, dy) != 0;
-                const float ayl = __shfl_sync(0xffffffffu, axl, dy), aym = __shfl_sync(0xffffffffu, axm, dy),
-                            ayr = __shfl_sync(0xffffffffu, axr, dy);
-                const int ya = yl ? sy1 - 1 : sy1, yb = yr ? sy2 : sy2 - 1;
-                float sum = 0; bool first = true;
-                for (int sy = ya; sy <= yb; sy++) {
-                    fetch_row(sy);
-                    const float beta = (yl && sy == sy1 - 1) ? ayl : ((yr && sy == sy2) ? ayr : aym);
-                    float bufv = 0;
-                    if (xl) bufv += rowf[sx1 - 1] * axl;
-                    for (int sx = sx1; sx < sx2; sx++) bufv += rowf[sx] * axm;
-                    if (xr) bufv += rowf[sx2] * axr;
-                    if (first) { sum = beta * bufv; first = false; } else sum += beta * bufv;
-                }
-                if (lane < PD) S.patch[dy * PD + lane] = (uint8_t)min(max(round_half_even_u8(sum), 0), 255);
-            }
-        }
-        __syncwarp();
-
-        float *sDX = S.buf, *sDY = S.buf + 400;
-        for (int p = lane; p < PATCH_SZ * PATCH_SZ; p += 32) {
-            const int i = p / PATCH_SZ, j = p - i * PATCH_SZ;
-            const float dw = c_DW[p];
-            const int p00 = S.patch[i * PD + j], p01 = S.patch[i * PD + j + 1];
-            const int p10 = S.patch[(i + 1) * PD + j], p11 = S.patch[(i + 1) * PD + j + 1];
-            sDX[p] = (float)(p01 - p00 + p11 - p10) * dw;
-            sDY[p] = (float)(p10 - p00 + p11 - p01) * dw;
-        }
-        __syncwarp();
-
-        {   // lane = (cell, half): 4 running sums each, raster order inside the 5x5 cell
-            const int cell = lane >> 1, half = lane & 1;
-            const int ci = cell >> 2, cj = cell & 3;
-            float v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-            for (int y = ci * 5; y < ci * 5 + 5; y++)
-#pragma unroll
-                for (int x5 = 0; x5 < 5; x5++) {
-                    const int x = cj * 5 + x5;
-                    const float tx = sDX[y * PATCH_SZ + x], ty = sDY[y * PATCH_SZ + x];
-                    if (extended) {
-                        // half 0: tx sums split by sign(ty); half 1: ty sums split by sign(tx)
-                        const float u = half ? ty : tx, g = half ? tx : ty;
-                        if (g >= 0) { v0 += u; v1 += fabsf(u); } else { v2 += u; v3 += fabsf(u); }
-                    } else {
-                        // 64-d: (sum tx, sum ty, sum |tx|, sum |ty|); half 0 -> (v0, v2) from tx, half 1 -> from ty
-                        const float u = half ? ty : tx;
-                        v0 += u; v1 += fabsf(u);
-                    }
-                }
-            if (extended) {
-                float *d = S.vec + cell * 8 + half * 4;
-                d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v3;
-            } else {
-                float *d = S.vec + cell * 4;
-                d[half] = v0; d[2 + half] = v1;
-            }
-        }
-        __syncwarp();
-        // sum of squares: float products accumulated in double (order differences are far below float resolution)
-        double sq = 0;
-        for (int t = lane; t < dsize; t += 32) sq += (double)(S.vec[t] * S.vec[t]);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        const float nscale = (float)(1. / (sqrt(sq) + (double)FLT_EPSILON));
-        float *dst = desc_all + ((size_t)b * kp_cap + k) * dsize;
-        for (int t = lane; t < dsize; t += 32) dst[t] = S.vec[t] * nscale;
-        __syncwarp();
-    }
-}
-
+// ---------------------------------------------------------------- K4c: one CTA per keypoint (windows > WK_MAX_WIN only)
 __global__ void __launch_bounds__(DESC_THREADS) orient_describe_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
     const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
@@ -1563,8 +1102,8 @@ __global__ void __launch_bounds__(DESC_THREADS) orient_describe_kernel(
     }
 }
 
-// ---------------------------------------------------------------- host: texture objects over the caller's images
-// One pitch-2D u8 texture per image (point sampled, used only through tex2Dgather).  Cached by (ptr, shape, pitch).
+// ---------------------------------------------------------------- host: texture objects over the float copy of the images
+// Pitch-2D float textures (point sampled, clamped, used only through tex2Dgather).  Cached by (ptr, shape, pitch).
 struct TexKey { const void *p; int rows, cols, stride; bool operator<(const TexKey &o) const {
     return std::tie(p, rows, cols, stride) < std::tie(o.p, o.rows, o.cols, o.stride); } };   // stride: pitch in floats
 struct TexCache { std::map<TexKey, cudaTextureObject_t> m; int align = 512, pitch_align = 32; bool init = false; };
@@ -1578,48 +1117,8 @@ void surf_tex_destroy(vfsms_ctx *ctx)
     ctx->tex_cache = nullptr;
 }
 
-// Textures over the workspace's float copy of the images (our own allocation: always aligned).  Returns false only when
-// texture creation fails; the caller then uses the LDG sampler.
-static bool surf_textures(vfsms_ctx *ctx, int batch, int rows, int cols, int pitch_f, cudaStream_t st, cudaTextureObject_t **dev_out)
-{
-    if (!ctx->tex_cache) ctx->tex_cache = new TexCache();
-    TexCache *tc = (TexCache *)ctx->tex_cache;
-    if (tc->m.size() > 8192) {           // bound the cache: drop everything once idle
-        cudaStreamSynchronize(st);
-        for (auto &kv : tc->m) cudaDestroyTextureObject(kv.second);
-        tc->m.clear();
-    }
-    std::vector<cudaTextureObject_t> h((size_t)batch);
-    const float *base = ctx->surf.img_f32.as<float>();
-    for (int b = 0; b < batch; b++) {
-        const float *p = base + (size_t)b * rows * pitch_f;
-        TexKey key{p, rows, cols, pitch_f};
-        auto it = tc->m.find(key);
-        if (it == tc->m.end()) {
-            cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
-            rd.resType = cudaResourceTypePitch2D;
-            rd.res.pitch2D.devPtr = (void *)p;
-            rd.res.pitch2D.desc = cudaCreateChannelDesc<float>();
-            rd.res.pitch2D.width = cols; rd.res.pitch2D.height = rows; rd.res.pitch2D.pitchInBytes = (size_t)pitch_f * 4;
-            cudaTextureDesc td; memset(&td, 0, sizeof(td));
-            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-            td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
-            cudaTextureObject_t t = 0;
-            if (cudaCreateTextureObject(&t, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); return false; }
-            it = tc->m.emplace(key, t).first;
-        }
-        h[b] = it->second;
-    }
-    if (ctx->tex_dev.reserve((size_t)batch * sizeof(cudaTextureObject_t))) return false;
-    if (cudaMemcpyAsync(ctx->tex_dev.p, h.data(), (size_t)batch * sizeof(cudaTextureObject_t), cudaMemcpyHostToDevice, st) != cudaSuccess) {
-        cudaGetLastError(); return false;
-    }
-    *dev_out = ctx->tex_dev.as<cudaTextureObject_t>();
-    return true;
-}
-
-// Describe mode 2: one texture over `n_img` consecutive images of the float copy, starting at image `b0` (image b at texture
-// rows [(b - b0) * rows, ...)).  Cached like the per-image objects.
+// One texture over `n_img` consecutive images of the float copy, starting at image `b0` (image b at texture rows
+// [(b - b0) * rows, ...)).  Cached by (pointer, shape).
 static bool surf_stack_texture(vfsms_ctx *ctx, int b0, int n_img, int rows, int cols, int pitch_f, cudaStream_t st, cudaTextureObject_t *out)
 {
     if (!ctx->tex_cache) ctx->tex_cache = new TexCache();
@@ -1687,6 +1186,7 @@ int surf_reserve(vfsms_ctx *ctx, int batch, int rows, int cols, const vfsms_surf
     if ((rc = ws.hist.reserve((size_t)batch * (3 * RB_BINS + 1) * 4))) return rc;     // sort mode 0 uses [RH_BINS + 1] per image
     ws.pitch_f = (cols + 31) & ~31;
     if (!p->upright && (rc = ws.img_f32.reserve((size_t)batch * rows * ws.pitch_f * 4))) return rc;
+    if ((rc = ws.fb_list.reserve((size_t)batch * kp_cap * 4))) return rc;      // keypoints handed from the fixed-point sampler to the reference one
     ws.max_features = max_features;
     ws.batch = batch; ws.rows = rows; ws.cols = cols; ws.cand_cap = cand_cap; ws.kp_cap = kp_cap; ws.dim = dim;
     return 0;
@@ -1703,6 +1203,7 @@ int surf_grow(vfsms_ctx *ctx, int grow_cand, int grow_kp)
         if ((rc = ws.kp.reserve((size_t)ws.batch * ws.kp_cap * KP_STRIDE * 4))) return rc;
         if ((rc = ws.desc.reserve((size_t)ws.batch * ws.kp_cap * ws.dim * 4))) return rc;
         if ((rc = ws.descT.reserve((size_t)ws.batch * ws.kp_cap * ws.dim * 4))) return rc;
+        if ((rc = ws.fb_list.reserve((size_t)ws.batch * ws.kp_cap * 4))) return rc;
     }
     if ((rc = ws.cand.reserve((size_t)ws.batch * ws.cand_cap * KP_STRIDE * 4))) return rc;
     if ((rc = ws.sorted.reserve((size_t)ws.batch * ws.cand_cap * KP_STRIDE * 4))) return rc;
@@ -1730,6 +1231,7 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         attr_done = true;
     }
     CUDA_TRY(cudaMemsetAsync(ws.counters.p, 0, (size_t)batch * 16 + 16 + 8 * SURF_MAX_DESC_CHUNKS, st));
+    ws.last_batch = batch;
     {
     StageTimer t_int(ctx, st, VFSMS_STAGE_INTEGRAL);
     integral_band_kernel<<<dim3(n_bands, batch), 256, smem_int, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
@@ -1860,58 +1362,46 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
     LAUNCH_CHECK(ctx);
     }
     StageTimer t_d(ctx, st, VFSMS_STAGE_DESCRIBE);
-    cudaTextureObject_t *texs = nullptr;
-    bool use_tex = false;
-    if (!p->upright) {        // the rotated-window sampler reads a float copy of the images through the texture unit
-        if ((rc = ws.img_f32.reserve((size_t)batch * rows * ws.pitch_f * 4))) return rc;
-        u8_to_f32_kernel<<<dim3(std::min(ceil_div(rows * cols, 256), ctx->num_sms * 4), batch), 256, 0, st>>>(base_a, base_b, split, img_stride, rows, cols,
-                                                                                                            stride, ws.img_f32.as<float>(), ws.pitch_f);
-        LAUNCH_CHECK(ctx);
-    }
-    int *work_counter = ws.counters.as<int32_t>() + (size_t)batch * 4;      // one extra slot after the per-image counters
-#define LAUNCH_WK(T, WC, TS, B0, NB) LAUNCH_WK_(T, 2, 4, WC, TS, B0, NB)
-#define LAUNCH_WK_(T, U, MB, WC, TS, B0, NB)                                                                                       \
-    orient_describe_warp_kernel<T, U, MB><<<ctx->num_sms * MB, WK_WARPS * 32, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,  \
-        ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap,              \
-        p->extended, p->upright, texs, WC, work_counter + 1, TS, B0, NB, (WC) + SURF_MAX_DESC_CHUNKS, lpt_split)
+    int *work_counter = ws.counters.as<int32_t>() + (size_t)batch * 4;      // extra slots after the per-image counters:
+    int *big_flag = work_counter + 1, *fb_count = work_counter + 2;         // [0] reference queue, [1] big-window flag, [2] hand-over count,
+    int *fb_list = ws.fb_list.as<int>();                                    // [4 + c], [4 + SURF_MAX_DESC_CHUNKS + c] queues of group c
     const int lpt_split = ctx->describe_lpt == 1 ? 128 : (ctx->describe_lpt == 2 ? 64 : (ctx->describe_lpt == 3 ? 256 : 0));
-    // mode 2 (opt-in, vfsms_set_option(VFSMS_OPT_DESCRIBE_MODE, 2)): one stacked texture per group of images whose rows fit
-    // the 2-D linear texture height limit, one launch per group with its own work counter
-    bool stacked = false;
-    if (ctx->describe_mode >= 2 && !p->upright) {
+    // describe = 1 (default): fixed-point chunked sampler over a float copy of the images scaled by 2^-64, read through one stacked
+    // texture per group of images whose rows fit the 2-D linear texture height limit; one launch per group with its own queues.
+    // Keypoints it hands over (and everything when describe = 0, upright, or no texture) go through the reference sampler.
+    bool fixed = false;
+    if (ctx->describe_mode >= 1 && !p->upright) {
         int max_h = 0;
         if (cudaDeviceGetAttribute(&max_h, cudaDevAttrMaxTexture2DLinearHeight, ctx->device) != cudaSuccess) { cudaGetLastError(); max_h = 0; }
         int per = max_h >= rows ? max_h / rows : 0;
         if (per >= 4) per &= ~3;          // keeps every group's base address on the 512-byte texture alignment (pitch is 128-byte aligned)
         const int n_chunks = per > 0 ? ceil_div(batch, per) : 0;
         if (n_chunks > 0 && n_chunks <= SURF_MAX_DESC_CHUNKS) {
+            if ((rc = ws.img_f32.reserve((size_t)batch * rows * ws.pitch_f * 4))) return rc;
+            u8_to_f32_kernel<<<dim3(std::min(ceil_div(rows * cols, 256), ctx->num_sms * 4), batch), 256, 0, st>>>(
+                base_a, base_b, split, img_stride, rows, cols, stride, ws.img_f32.as<float>(), ws.pitch_f, 5.421010862427522e-20f /* 2^-64 */);
+            LAUNCH_CHECK(ctx);
             std::vector<cudaTextureObject_t> ts((size_t)n_chunks);
-            stacked = true;
-            for (int c = 0; c < n_chunks && stacked; c++)
-                stacked = surf_stack_texture(ctx, c * per, std::min(per, batch - c * per), rows, cols, ws.pitch_f, st, &ts[c]);
-            for (int c = 0; c < n_chunks && stacked; c++) {
-                const int nb = std::min(per, batch - c * per);
-                if (ctx->describe_mode == 2) LAUNCH_WK_(2, 2, 4, work_counter + 4 + c, ts[c], c * per, nb);
-                else if (ctx->describe_mode == 3) LAUNCH_WK_(2, 4, 4, work_counter + 4 + c, ts[c], c * per, nb);
-                else if (ctx->describe_mode == 4) LAUNCH_WK_(2, 4, 3, work_counter + 4 + c, ts[c], c * per, nb);
-                else if (ctx->describe_mode == 5) LAUNCH_WK_(2, 2, 5, work_counter + 4 + c, ts[c], c * per, nb);   // 48 registers: 5 CTAs / SM
-                else if (ctx->describe_mode == 6) LAUNCH_WK_(2, 1, 5, work_counter + 4 + c, ts[c], c * per, nb);
-                else if (ctx->describe_mode == 7) LAUNCH_WK_(3, 2, 4, work_counter + 4 + c, ts[c], c * per, nb);   // fixed-point coordinates
-                else LAUNCH_WK_(3, 2, 5, work_counter + 4 + c, ts[c], c * per, nb);
+            fixed = true;
+            for (int c = 0; c < n_chunks && fixed; c++)
+                fixed = surf_stack_texture(ctx, c * per, std::min(per, batch - c * per), rows, cols, ws.pitch_f, st, &ts[c]);
+            for (int c = 0; c < n_chunks && fixed; c++) {
+                describe_fixed_kernel<DESC_FIXED_MINB><<<ctx->num_sms * DESC_FIXED_MINB, WK_WARPS * 32, 0, st>>>(
+                    base_a, base_b, split, img_stride, rows, cols, stride, ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(),
+                    ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, ts[c], c * per, std::min(per, batch - c * per),
+                    work_counter + 4 + c, work_counter + 4 + SURF_MAX_DESC_CHUNKS + c, lpt_split, big_flag, fb_list, fb_count);
                 LAUNCH_CHECK(ctx);
             }
         }
     }
-    if (!stacked) {
-        if (!p->upright && ctx->describe_mode != 0) use_tex = surf_textures(ctx, batch, rows, cols, ws.pitch_f, st, &texs);
-        if (use_tex) LAUNCH_WK(1, work_counter, 0, 0, batch); else { texs = nullptr; LAUNCH_WK(0, work_counter, 0, 0, batch); }
-        LAUNCH_CHECK(ctx);
-    }
-#undef LAUNCH_WK
-#undef LAUNCH_WK_
+    describe_reference_kernel<<<fixed ? ctx->num_sms : ctx->num_sms * 4, WK_WARPS * 32, 0, st>>>(
+        base_a, base_b, split, img_stride, rows, cols, stride, ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(),
+        ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, p->upright, work_counter, big_flag,
+        fixed ? fb_list : nullptr, fixed ? fb_count : nullptr);
+    LAUNCH_CHECK(ctx);
     orient_describe_kernel<<<ctx->num_sms * 2, DESC_THREADS, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
                                                                        ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(),
-                                                                       ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, p->upright, work_counter + 1);
+                                                                       ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, p->upright, big_flag);
     LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -1,0 +1,520 @@
+// surf_describe.cuh -- SURF orientation + descriptor, one WARP per keypoint (included by surf.cu; shares its constant tables).
+//
+// Replaces the per-keypoint loop of OpenCV's SURFInvoker (opencv_contrib 3.3.1 modules/xfeatures2d/src/surf.cpp, reached from
+// ImageUtility.py:258-264 / appendix/myGpuFeatures.cpp:77-83) as restated in oracle/surf_oracle.c describe_one():
+// 113 Haar samples -> 72 sliding windows -> direction; rotated 20s x 20s window sampled bilinearly, each sample rounded to u8;
+// INTER_AREA resize to 21 x 21; Gaussian-weighted gradients; 4 x 4 x (4 | 8) bins; L2 normalisation.
+// Results are bit-identical to the oracle: every rounding of the scalar CPU code is reproduced (this file is compiled with
+// -fmad=false), only the schedule differs.
+//
+// Two kernels:
+//   describe_fixed_kernel      the product path.  Window positions in 32.32 fixed point (exact, see below), rows sampled in CHUNKS
+//                              of up to 32 warp-rounds whose texture gathers are issued four at a time, INTER_AREA folded row by row.
+//   describe_reference_kernel  row-at-a-time sampler in double precision straight from the u8 image (no texture, no exactness
+//                              preconditions).  Describes what the fixed kernel hands over (a work list: degenerate directions,
+//                              sub-2^-9 row starts), everything when vfsms_set_option("describe", 0), and upright keypoints.
+//
+// Why fixed point is exact.  The CPU walks a window row as  pixel_x = (double)start_x + j * (double)cos_dir  (accumulated, every
+// partial sum exact in double) with start_x, cos_dir floats; start_x itself is the float chain start_x += sin_dir per row, which
+// both kernels advance with the same float additions.  When |cos_dir| is 0 or in [2^-9, 1) it is a multiple of 2^-32 below 1, and
+// when |start_x| is 0 or >= 2^-9 so is the row start: then X = pixel_x * 2^32 is an exact 64-bit integer for every sample,
+// floor(pixel_x) is its high word, and the CPU's a = (float)(pixel_x - ix) -- ONE rounding of an exact difference -- equals
+// RN((float)low word) * 2^-32.  The power-of-two scale commutes with every later rounding of the bilinear expression, so it is folded
+// into the texture: the float copy of the image holds p * 2^-64 and the kernel evaluates
+//     p00' * (T - A) * (T - B) + p01' * A * (T - B) + p10' * (T - A) * B + p11' * A * B,   T = 2^32, A = RN(lo(X)), B = RN(lo(Y))
+// in the CPU's association order: the same float, no scaling instruction.
+#pragma once
+
+#define DESC_THREADS 256
+#define SURF_MAX_DESC_CHUNKS 64   // launches per batch (one stacked texture each)
+#define WK_MAX_WIN 768            // windows up to this size are described by one warp (n_octaves <= 4 never exceeds 739)
+#define WK_WARPS 8
+#define DESC_BUF 1024             // floats of row storage per warp: one chunk of sampled rows (fixed kernel), one row (reference kernel)
+#define DESC_SLOTS 32             // warp-rounds per chunk
+#define DESC_FIXED_MINB 3          // CTAs per SM the fixed kernel's register budget is cut for
+
+// bilinear / clamped sample of the rotated window, rounded to u8 exactly like the CPU loop (reference sampler)
+__device__ __forceinline__ int window_pixel(const uint8_t *__restrict__ img, int stride, int ncols1, int nrows1,
+                                            double pixel_x, double pixel_y)
+{
+    const int ix = __double2int_rd(pixel_x), iy = __double2int_rd(pixel_y);
+    if ((unsigned)ix < (unsigned)ncols1 && (unsigned)iy < (unsigned)nrows1) {
+        const float a = (float)(pixel_x - ix), bq = (float)(pixel_y - iy);
+        const uint8_t *p = img + (size_t)iy * stride + ix;
+        const float p00 = p[0], p01 = p[1], p10 = p[stride], p11 = p[stride + 1];
+        const float v = p00 * (1.f - a) * (1.f - bq) + p01 * a * (1.f - bq) + p10 * (1.f - a) * bq + p11 * a * bq;
+        return __float2int_rn(v) & 255;
+    }
+    int x = __double2int_rn(pixel_x), y = __double2int_rn(pixel_y);
+    x = min(max(x, 0), ncols1); y = min(max(y, 0), nrows1);
+    return img[(size_t)y * stride + x];
+}
+
+__device__ __forceinline__ int round_half_even_u8(float v)      // cvRound for 0 <= v < 2^22 without a conversion instruction
+{
+    return __float_as_int(v + 12582912.0f) - 0x4B400000;
+}
+
+// float copy of the batch's images for the texture path (pitch in floats), scaled by a power of two (2^-64 for the fixed kernel)
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride,
+                                                        int rows, int cols, int stride, float *dst, int pitch_f, float scale)
+{
+    const int b = blockIdx.y;
+    const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
+    float *D = dst + (size_t)b * rows * pitch_f;
+    const int total = rows * cols;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int y = i / cols, x = i - y * cols;
+        D[(size_t)y * pitch_f + x] = (float)img[(size_t)y * stride + x] * scale;
+    }
+}
+
+struct __align__(16) DescScratch {
+    float buf[DESC_BUF];         // orientation: X[0..127] Y[128..255] A[256..383] (int) ; window phase: sampled rows as exact floats ;
+                                 // descriptor: DX[0..399] DY[400..799]
+    uint4 slot[DESC_SLOTS];      // fixed kernel: 32.32 start (x lo, x hi, y lo, y hi) of each warp-round of the current chunk
+    float vec[128];
+    uint8_t patch[448];
+};
+
+// ---- dominant orientation (OpenCV's 72 windows of 60 degrees over the 113 Gaussian-weighted Haar responses); warp-collective
+__device__ __forceinline__ float orient_keypoint(DescScratch &S, int lane, const int32_t *__restrict__ I, int W, int srows, int scols,
+                                                 float cx, float cy, float s, int gws)
+{
+    float *sX = S.buf, *sY = S.buf + 128; int *sA = (int *)(S.buf + 256);
+    const unsigned lt_mask = (1u << lane) - 1;
+    const int h2 = __float2int_rn(((float)gws / 4) * 2);
+    const int h4 = __float2int_rn(((float)gws / 4) * 4);
+    const float wgt = 1.f / ((float)(h2) * (float)(h4));
+    const float half = (float)(gws - 1) / 2;
+    int nangle = 0;
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+        const int kk = r * 32 + lane;
+        bool have = false; float vX = 0, vY = 0;
+        if (kk < ORI_SAMPLES) {
+            const int x = __float2int_rn(cx + c_apt_x[kk] * s - half);
+            const int y = __float2int_rn(cy + c_apt_y[kk] * s - half);
+            if (!(y < 0 || y >= srows - gws || x < 0 || x >= scols - gws)) {
+                const int32_t *o = I + (size_t)y * W + x;
+                // 3x3 grid of integral corners shared by the four half boxes
+                const int a00 = __ldg(o), a01 = __ldg(o + h2), a02 = __ldg(o + h4);
+                const int32_t *o1 = o + (size_t)h2 * W, *o2 = o + (size_t)h4 * W;
+                const int a10 = __ldg(o1), a12 = __ldg(o1 + h4);
+                const int a20 = __ldg(o2), a21 = __ldg(o2 + h2), a22 = __ldg(o2 + h4);
+                const int bl = a00 + a21 - a20 - a01;          // x in [0,h2), y in [0,h4)
+                const int br = a01 + a22 - a21 - a02;          // x in [h2,h4)
+                const int bt = a00 + a12 - a10 - a02;          // y in [0,h2)
+                const int bb = a10 + a22 - a20 - a12;          // y in [h2,h4)
+                double d = 0; d += (double)((float)bl * (-wgt)); d += (double)((float)br * wgt);
+                const float vx = (float)d;
+                d = 0; d += (double)((float)bt * wgt); d += (double)((float)bb * (-wgt));
+                const float vy = (float)d;
+                vX = vx * c_aptw[kk]; vY = vy * c_aptw[kk];
+                have = true;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, have);
+        if (have) {
+            const int pos = nangle + __popc(bal & lt_mask);
+            sX[pos] = vX; sY[pos] = vY; sA[pos] = __float2int_rn(fast_atan2_deg(vY, vX));
+        }
+        nangle += __popc(bal);
+    }
+    __syncwarp();
+    float bmod = 0, bx = 0, by = 0; int bw = 1 << 30;
+#pragma unroll 1
+    for (int w = lane; w < 72; w += 32) {
+        // |angle - 5w| < 30 or > 330 over integers in [-355, 360]  <=>  t, t - 360 or t + 360 in [0, 58], t = angle - 5w + 29
+        const int i29 = w * 5 - 29;
+        float sumx = 0, sumy = 0;
+#pragma unroll 4
+        for (int j = 0; j < nangle; j++) {
+            const unsigned t = (unsigned)(sA[j] - i29);
+            if (t < 59u || t - 360u < 59u || t + 360u < 59u) { sumx += sX[j]; sumy += sY[j]; }
+        }
+        const float m = sumx * sumx + sumy * sumy;
+        if (m > bmod) { bmod = m; bx = sumx; by = sumy; bw = w; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, bmod, o), ox = __shfl_xor_sync(0xffffffffu, bx, o),
+                    oy = __shfl_xor_sync(0xffffffffu, by, o);
+        const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
+        if (om > bmod || (om == bmod && ow < bw)) { bmod = om; bx = ox; by = oy; bw = ow; }
+    }
+    __syncwarp();
+    return fast_atan2_deg(-by, bx);
+}
+
+// ---- S.patch (21 x 21 u8) -> descriptor; warp-collective
+__device__ __forceinline__ void patch_to_descriptor(DescScratch &S, int lane, int extended, float *__restrict__ dst)
+{
+    constexpr int PD = PATCH_SZ + 1;
+    const int dsize = extended ? 128 : 64;
+    float *sDX = S.buf, *sDY = S.buf + 400;
+    for (int p = lane; p < PATCH_SZ * PATCH_SZ; p += 32) {
+        const int i = p / PATCH_SZ, j = p - i * PATCH_SZ;
+        const float dw = c_DW[p];
+        const int p00 = S.patch[i * PD + j], p01 = S.patch[i * PD + j + 1];
+        const int p10 = S.patch[(i + 1) * PD + j], p11 = S.patch[(i + 1) * PD + j + 1];
+        sDX[p] = (float)(p01 - p00 + p11 - p10) * dw;
+        sDY[p] = (float)(p10 - p00 + p11 - p01) * dw;
+    }
+    __syncwarp();
+    {   // lane = (cell, half): 4 running sums each, raster order inside the 5x5 cell
+        const int cell = lane >> 1, half = lane & 1;
+        const int ci = cell >> 2, cj = cell & 3;
+        float v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+        for (int y = ci * 5; y < ci * 5 + 5; y++)
+#pragma unroll
+            for (int x5 = 0; x5 < 5; x5++) {
+                const int x = cj * 5 + x5;
+                const float tx = sDX[y * PATCH_SZ + x], ty = sDY[y * PATCH_SZ + x];
+                if (extended) {
+                    // half 0: tx sums split by sign(ty); half 1: ty sums split by sign(tx)
+                    const float u = half ? ty : tx, g = half ? tx : ty;
+                    if (g >= 0) { v0 += u; v1 += fabsf(u); } else { v2 += u; v3 += fabsf(u); }
+                } else {
+                    // 64-d: (sum tx, sum ty, sum |tx|, sum |ty|); half 0 -> (v0, v2) from tx, half 1 -> from ty
+                    const float u = half ? ty : tx;
+                    v0 += u; v1 += fabsf(u);
+                }
+            }
+        if (extended) {
+            float *d = S.vec + cell * 8 + half * 4;
+            d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v3;
+        } else {
+            float *d = S.vec + cell * 4;
+            d[half] = v0; d[2 + half] = v1;
+        }
+    }
+    __syncwarp();
+    // sum of squares: float products accumulated in double (order differences are far below float resolution)
+    double sq = 0;
+    for (int t = lane; t < dsize; t += 32) sq += (double)(S.vec[t] * S.vec[t]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float nscale = (float)(1. / (sqrt(sq) + (double)FLT_EPSILON));
+    for (int t = lane; t < dsize; t += 32) dst[t] = S.vec[t] * nscale;
+    __syncwarp();
+}
+
+// ---- INTER_AREA (cv::resize of the win x win u8 window to 21 x 21) folded over window rows arriving in order.
+// Lane dx (< 21; lanes >= 21 shadow column 20) owns output column dx: its decimation-table entries (sx1, sx2, edge taps and weights),
+// the running row accumulator `sum` and, for integer scales, the box sum.  The row table of output row dy equals lane dy's column
+// table (square window, one scale), fetched by shuffle when dy advances.
+struct AreaFold {
+    int win, iscale; bool fast, ident;
+    int sx1, sx2, nb, dxc; bool xl, xr; float axl, axm, axr, fs;
+    int dy; bool first; float sum;
+    int sy1, sy2, ya, yb; bool yl, yr; float ayl, aym, ayr;
+
+    __device__ __forceinline__ void load_dy(int d)
+    {
+        sy1 = __shfl_sync(0xffffffffu, sx1, d); sy2 = __shfl_sync(0xffffffffu, sx2, d);
+        yl = __shfl_sync(0xffffffffu, (int)xl, d) != 0; yr = __shfl_sync(0xffffffffu, (int)xr, d) != 0;
+        ayl = __shfl_sync(0xffffffffu, axl, d); aym = __shfl_sync(0xffffffffu, axm, d); ayr = __shfl_sync(0xffffffffu, axr, d);
+        ya = yl ? sy1 - 1 : sy1; yb = yr ? sy2 : sy2 - 1;
+    }
+
+    __device__ __forceinline__ void init(int w, int lane)
+    {
+        constexpr int PD = PATCH_SZ + 1;
+        win = w;
+        const double inv_scale = (double)PD / win;
+        const double scale = 1. / inv_scale;
+        iscale = __double2int_rn(scale);
+        fast = fabs(scale - iscale) < DBL_EPSILON;
+        ident = win == PD;
+        dxc = lane < PD ? lane : PD - 1;
+        dy = 0; first = true; sum = 0;
+        fs = 1.f / (float)(iscale * iscale);
+        sx1 = sx2 = nb = 0; xl = xr = false; axl = axm = axr = 0;
+        if (!ident && !fast) {
+            // column taps of this lane (decimation table entries of output column dx, in table order)
+            const double fsx1 = dxc * scale, fsx2 = fsx1 + scale, cwx = fmin(scale, win - fsx1);
+            sx1 = __double2int_ru(fsx1); sx2 = __double2int_rd(fsx2);
+            sx2 = min(sx2, win - 1); sx1 = min(sx1, sx2);
+            xl = (sx1 - fsx1 > 1e-3); xr = (fsx2 - sx2 > 1e-3);
+            axl = (float)((sx1 - fsx1) / cwx); axm = (float)(1.0 / cwx);
+            axr = (float)(fmin(fmin(fsx2 - sx2, 1.), cwx) / cwx);
+            nb = sx2 - sx1;                                   // interior taps of this lane; the warp minimum runs unpredicated
+#pragma unroll
+            for (int o = 16; o; o >>= 1) nb = min(nb, __shfl_xor_sync(0xffffffffu, nb, o));
+            load_dy(0);
+        }
+    }
+
+    __device__ __forceinline__ bool done() const { return dy >= PATCH_SZ + 1; }
+
+    // row `sy` of the window (exact floats 0..255 in shared memory); rows arrive in increasing order, each exactly once
+    __device__ __forceinline__ void row(const float *__restrict__ r, int sy, uint8_t *__restrict__ patch, int lane)
+    {
+        constexpr int PD = PATCH_SZ + 1;
+        if (dy >= PD) return;
+        if (ident) {
+            if (lane < PD) patch[sy * PD + lane] = (uint8_t)(int)r[lane];
+            dy = sy + 1;
+            return;
+        }
+        if (fast) {
+            // integer factor: exact integer box sums (<= 35^2 * 255: exact in float)
+            const float *p = r + dxc * iscale;
+            for (int xx = 0; xx < iscale; xx++) sum += p[xx];
+            if (sy == dy * iscale + iscale - 1) {
+                int out;
+                if (iscale == 2) out = (int)((sum + 2.f) * 0.25f);          // (sum + 2) >> 2
+                else out = min(max(__float2int_rn(sum * fs), 0), 255);
+                if (lane < PD) patch[dy * PD + lane] = (uint8_t)out;
+                dy++; sum = 0;
+            }
+            return;
+        }
+        if (sy < ya) return;
+        // horizontal taps of this source row, in table order
+        const float *p = r + sx1;
+        float bufv = xl ? p[-1] * axl : 0.f;
+        int t = 0;
+        for (; t + 4 <= nb; t += 4) {
+            bufv += p[t] * axm; bufv += p[t + 1] * axm; bufv += p[t + 2] * axm; bufv += p[t + 3] * axm;
+        }
+        for (; t < nb; t++) bufv += p[t] * axm;
+        for (; t < sx2 - sx1; t++) bufv += p[t] * axm;          // lanes whose column holds more taps than the warp minimum
+        if (xr) bufv += r[sx2] * axr;
+        // vertical fold: the row belongs to output row dy and, when it straddles the boundary, to dy + 1 as well
+        while (true) {
+            const float beta = (yl && sy == sy1 - 1) ? ayl : ((yr && sy == sy2) ? ayr : aym);
+            if (first) { sum = beta * bufv; first = false; } else sum += beta * bufv;
+            if (sy != yb) break;
+            if (lane < PD) patch[dy * PD + lane] = (uint8_t)min(max(round_half_even_u8(sum), 0), 255);
+            dy++; first = true;
+            if (dy >= PD) break;
+            load_dy(dy);
+            if (ya != sy) break;
+        }
+    }
+};
+
+// ---------------------------------------------------------------- K4a: reference sampler (row at a time, double precision, u8 image)
+// work_list == nullptr: every keypoint of the images [0, batch); else the items listed (flattened indices), *work_count of them.
+__global__ void __launch_bounds__(WK_WARPS * 32, 4) describe_reference_kernel(
+    const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
+    const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
+    int batch, int kp_cap, int extended, int upright, int *work_counter, int *big_flag,
+    const int *__restrict__ work_list, const int *__restrict__ work_count)
+{
+    __shared__ DescScratch s_ws[WK_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    DescScratch &S = s_ws[warp];
+    const int total = work_list ? min(*work_count, prefix[batch]) : prefix[batch];
+    const int W = cols + 1, srows = rows + 1, scols = cols + 1;
+    const int dsize = extended ? 128 : 64;
+    while (true) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(work_counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total) break;
+        if (work_list) item = work_list[item];
+        int lo = 0, hi = batch;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(prefix + mid) <= item) lo = mid; else hi = mid; }
+        const int b = lo, k = item - __ldg(prefix + lo);
+        float *kp = kp_all + ((size_t)b * kp_cap + k) * KP_STRIDE;
+        const float size = kp[KP_SIZE], cx = kp[KP_X], cy = kp[KP_Y];
+        const float s = size * 1.2f / 9.0f;
+        const int win = (int)((PATCH_SZ + 1) * s);
+        if (win > WK_MAX_WIN) { if (lane == 0) *big_flag = 1; continue; }     // warp-uniform: flag work for the CTA kernel
+        const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
+        const int32_t *I = integral + (size_t)b * srows * W;
+        const int gws = 2 * __float2int_rn(2 * s);
+        float descriptor_dir = 360.f - 90.f;
+        if (!upright) descriptor_dir = orient_keypoint(S, lane, I, W, srows, scols, cx, cy, s, gws);
+        if (lane == 0) kp[KP_ANGLE] = descriptor_dir;
+
+        const int ncols1 = cols - 1, nrows1 = rows - 1;
+        float sin_dir = 0, cos_dir = 0, chain_x = 0, chain_y = 0;
+        int ustart_x = 0, ustart_y = 0;
+        const float win_offset = -(float)(win - 1) / 2;
+        if (!upright) {
+            const float dir_rad = descriptor_dir * (float)(M_PI / 180);
+            sin_dir = -(float)sin((double)dir_rad);
+            cos_dir = (float)cos((double)dir_rad);
+            chain_x = cx + win_offset * cos_dir + win_offset * sin_dir;
+            chain_y = cy - win_offset * sin_dir + win_offset * cos_dir;
+        } else {
+            ustart_x = __float2int_rn(cx + win_offset);
+            ustart_y = __float2int_rn(cy - win_offset);
+        }
+        AreaFold F;
+        F.init(win, lane);
+        float *rowf = S.buf;
+        for (int r = 0; r < win && !F.done(); r++) {
+            if (!upright) {
+                // per-lane positions advance by 32 columns per round; all terms are exact in double (24-bit increments,
+                // |x| < 2^13), so the running sum equals the CPU's column-by-column accumulation
+                const double rx = (double)chain_x, ry = (double)chain_y;
+                double px = rx + (double)lane * (double)cos_dir, py = ry - (double)lane * (double)sin_dir;
+                const double dpx = 32.0 * (double)cos_dir, dpy = 32.0 * (double)sin_dir;
+                for (int j = lane; j < win; j += 32, px += dpx, py -= dpy)
+                    rowf[j] = (float)window_pixel(img, stride, ncols1, nrows1, px, py);
+                chain_x += sin_dir; chain_y += cos_dir;
+            } else {
+                const int x = min(max(ustart_x + r, 0), cols - 1);
+                for (int j = lane; j < win; j += 32) {
+                    const int y = min(max(ustart_y - j, 0), rows - 1);
+                    rowf[j] = (float)img[(size_t)y * stride + x];
+                }
+            }
+            __syncwarp();
+            F.row(rowf, r, S.patch, lane);
+            __syncwarp();
+        }
+        patch_to_descriptor(S, lane, extended, desc_all + ((size_t)b * kp_cap + k) * dsize);
+    }
+}
+
+// ---------------------------------------------------------------- K4b: fixed-point chunked sampler (the product path)
+// One launch per group of images sharing a stacked texture (image b at texture rows [(b - b_first) * rows, ...)).
+// Keypoints whose direction or row starts are not multiples of 2^-32 go to `fb_list` for describe_reference_kernel.
+__device__ __forceinline__ float bilinear_scaled(const float4 g, float A, float B)
+{
+    const float T = 4294967296.0f;
+    const float ia = T - A, ib = T - B;
+    const float p00 = g.w, p01 = g.z, p10 = g.x, p11 = g.y;
+    const float v = p00 * ia * ib + p01 * A * ib + p10 * ia * B + p11 * A * B;
+    return (v + 12582912.0f) - 12582912.0f;          // cvRound, ties to even, as an exact float
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(WK_WARPS * 32, MINB) describe_fixed_kernel(
+    const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
+    const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
+    int batch, int kp_cap, int extended, const cudaTextureObject_t tex, int b_first, int b_count,
+    int *work_counter, int *work_counter_large, int lpt_split, int *big_flag, int *fb_list, int *fb_count)
+{
+    __shared__ DescScratch s_ws[WK_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    DescScratch &S = s_ws[warp];
+    const int total = prefix[b_first + b_count];
+    const int item0 = prefix[b_first];
+    const int W = cols + 1, srows = rows + 1, scols = cols + 1;
+    const int dsize = extended ? 128 : 64;
+    const int ncols1 = cols - 1, nrows1 = rows - 1;
+
+    // lpt_split > 0: longest-processing-time-first in two passes over the same work list -- pass 0 describes only the windows
+    // >= lpt_split (a 600-pixel window keeps one warp busy for a long time; met late in the queue it becomes the tail of the
+    // launch), pass 1 the rest.  A skipped item costs one keypoint read.
+    int pass = lpt_split > 0 ? 0 : 1;
+    while (true) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(pass == 0 ? work_counter_large : work_counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0) + item0;
+        if (item >= total) { if (pass == 0) { pass = 1; continue; } break; }
+        int lo = b_first, hi = b_first + b_count;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(prefix + mid) <= item) lo = mid; else hi = mid; }
+        const int b = lo, k = item - __ldg(prefix + lo);
+        float *kp = kp_all + ((size_t)b * kp_cap + k) * KP_STRIDE;
+        const float size = kp[KP_SIZE], cx = kp[KP_X], cy = kp[KP_Y];
+        const float s = size * 1.2f / 9.0f;
+        const int win = (int)((PATCH_SZ + 1) * s);
+        if (lpt_split > 0 && ((win >= lpt_split) != (pass == 0))) continue;   // warp-uniform: the other pass owns this keypoint
+        if (win > WK_MAX_WIN) { if (lane == 0) *big_flag = 1; continue; }     // warp-uniform: flag work for the CTA kernel
+        const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
+        const int32_t *I = integral + (size_t)b * srows * W;
+        const int gws = 2 * __float2int_rn(2 * s);
+        const float descriptor_dir = orient_keypoint(S, lane, I, W, srows, scols, cx, cy, s, gws);
+        if (lane == 0) kp[KP_ANGLE] = descriptor_dir;
+
+        const float dir_rad = descriptor_dir * (float)(M_PI / 180);
+        const float sin_dir = -(float)sin((double)dir_rad);
+        const float cos_dir = (float)cos((double)dir_rad);
+        const float win_offset = -(float)(win - 1) / 2;
+        float chain_x = cx + win_offset * cos_dir + win_offset * sin_dir;      // start_x / start_y of the next unsampled row
+        float chain_y = cy - win_offset * sin_dir + win_offset * cos_dir;
+        const float ac = fabsf(cos_dir), as = fabsf(sin_dir);
+        // multiples of 2^-32 below 1 (warp-uniform); everything else is the reference kernel's
+        bool exact = (ac == 0.f || ac >= 0.001953125f) && ac < 1.f && (as == 0.f || as >= 0.001953125f) && as < 1.f;
+        const unsigned c32 = (unsigned)(ac * 4294967296.0f), s32 = (unsigned)(as * 4294967296.0f);
+        const bool xneg = cos_dir < 0.f;            // x decreases along a row
+        const bool yneg = sin_dir > 0.f;            // pixel_y -= sin_dir
+        const unsigned mx = xneg ? 31 - lane : lane, my = yneg ? 31 - lane : lane;
+        const int row_off = (b - b_first) * rows;
+        // every sample of the window (half diagonal + the float chain's drift, 2 px of slack) keeps its 2x2 footprint inside the image
+        const float Rw = (float)(win - 1) * 0.7072f + 2.0f;
+        const bool interior = cx - Rw >= 1.f && cx + Rw <= (float)(ncols1 - 1) && cy - Rw >= 1.f && cy + Rw <= (float)(nrows1 - 1);
+        const int kpr = (win + 31) >> 5;            // warp-rounds per window row
+        const int R = DESC_SLOTS / kpr;             // rows per chunk (R * win <= DESC_BUF)
+        AreaFold F;
+        F.init(win, lane);
+
+        for (int r0 = 0; r0 < win && exact && !F.done(); r0 += R) {
+            const int Rc = min(R, win - r0), Q = Rc * kpr;
+            // ---- slot table: lane q owns warp-round q = (row r0 + q / kpr, columns 32 * (q % kpr) ...)
+            {
+                const int myrow = lane / kpr, myk = lane - myrow * kpr;
+                float cap_x = 1.f, cap_y = 1.f;
+                for (int i = 0; i < Rc; i++) {       // the CPU's float chain, advanced by every lane alike
+                    if (i == myrow) { cap_x = chain_x; cap_y = chain_y; }
+                    chain_x += sin_dir; chain_y += cos_dir;
+                }
+                const bool ok = lane >= Q || ((cap_x == 0.f || fabsf(cap_x) >= 0.001953125f) && (cap_y == 0.f || fabsf(cap_y) >= 0.001953125f));
+                if (!__all_sync(0xffffffffu, ok)) { exact = false; break; }
+                const long long X0 = (long long)((double)cap_x * 4294967296.0);           // exact: multiples of 2^-32
+                const long long Y0 = (long long)((double)cap_y * 4294967296.0);
+                const long long kx = xneg ? -(long long)(32 * myk + 31) : (long long)(32 * myk);
+                const long long ky = yneg ? -(long long)(32 * myk + 31) : (long long)(32 * myk);
+                // + 1: tex2Dgather at (ix + 1, iy + 1) returns the footprint (ix, iy) .. (ix + 1, iy + 1); + row_off: image b of the stack
+                const unsigned long long Ux = (unsigned long long)(X0 + kx * (long long)c32 + (1LL << 32));
+                const unsigned long long Uy = (unsigned long long)(Y0 + ky * (long long)s32 + ((long long)(1 + row_off) << 32));
+                S.slot[lane] = make_uint4((unsigned)Ux, (unsigned)(Ux >> 32), (unsigned)Uy, (unsigned)(Uy >> 32));
+            }
+            __syncwarp();
+            // ---- sample the chunk: four gathers in flight per lane
+            int base = 0, kk = 0;                    // buffer offset and column block of warp-round q0
+#pragma unroll 1
+            for (int q0 = 0; q0 < Q; q0 += 4) {
+                float4 g[4]; float A[4], B[4]; unsigned oob = 0;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint4 e = S.slot[min(q0 + u, Q - 1)];
+                    const unsigned long long X = (((unsigned long long)e.y << 32) | e.x) + (unsigned long long)mx * c32;
+                    const unsigned long long Y = (((unsigned long long)e.w << 32) | e.z) + (unsigned long long)my * s32;
+                    const int ix1 = (int)(X >> 32), iy1 = (int)(Y >> 32);
+                    A[u] = __uint2float_rn((unsigned)X); B[u] = __uint2float_rn((unsigned)Y);
+                    g[u] = tex2Dgather<float4>(tex, __int2float_rn(ix1), __int2float_rn(iy1), 0);
+                    if (!interior && !((unsigned)(ix1 - 1) < (unsigned)ncols1 && (unsigned)(iy1 - 1 - row_off) < (unsigned)nrows1)) oob |= 1u << u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (q0 + u < Q) {                // warp-uniform
+                        float v = bilinear_scaled(g[u], A[u], B[u]);
+                        if (!interior && (oob >> u & 1)) {
+                            // outside the image: the CPU takes the clamped nearest pixel, cvRound(pixel) = ties to even
+                            const uint4 e = S.slot[q0 + u];
+                            const unsigned long long X = (((unsigned long long)e.y << 32) | e.x) + (unsigned long long)mx * c32;
+                            const unsigned long long Y = (((unsigned long long)e.w << 32) | e.z) + (unsigned long long)my * s32;
+                            const int ix = (int)(X >> 32) - 1, iy = (int)(Y >> 32) - 1 - row_off;
+                            const unsigned fx = (unsigned)X, fy = (unsigned)Y;
+                            int x = ix + ((fx > 0x80000000u || (fx == 0x80000000u && (ix & 1))) ? 1 : 0);
+                            int y = iy + ((fy > 0x80000000u || (fy == 0x80000000u && (iy & 1))) ? 1 : 0);
+                            x = min(max(x, 0), ncols1); y = min(max(y, 0), nrows1);
+                            v = (float)img[(size_t)y * stride + x];
+                        }
+                        const int j = kk * 32 + lane;
+                        if (j < win) S.buf[base + j] = v;
+                        if (++kk == kpr) { kk = 0; base += win; }
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- fold the chunk's rows into the patch
+            for (int i = 0; i < Rc; i++) F.row(S.buf + i * win, r0 + i, S.patch, lane);
+            __syncwarp();
+        }
+        if (!exact || !F.done()) {                   // hand over to the reference kernel (it repeats the orientation)
+            if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = item;
+            continue;
+        }
+        patch_to_descriptor(S, lane, extended, desc_all + ((size_t)b * kp_cap + k) * dsize);
+    }
+}

@@ -311,7 +311,7 @@ OPTIONS = {"describe": 0, "sort": 1, "lpt": 2, "entropy": 3}      # include/vfsm
 
 def set_option(name, value, device=0):
     """Kernel-variant switch (include/vfsms.h VFSMS_OPT_*): every value of an option gives identical results; non-default
-    values are alternative schedules kept for A/B measurement.  Also settable through VFSMS_OPTS="describe=2,sort=1"."""
+    values are alternative schedules kept for A/B measurement.  Also settable through VFSMS_OPTS="describe=0,lpt=1"."""
     check(_lib.load().vfsms_set_option(_lib.context(device), OPTIONS[name], int(value)), "vfsms_set_option")
 
 
@@ -324,6 +324,13 @@ def get_option(name, device=0):
 def last_match_fallbacks(device=0):
     n = ctypes.c_int(0)
     check(_lib.load().vfsms_last_match_fallbacks(_lib.context(device), ctypes.byref(n)), "vfsms_last_match_fallbacks")
+    return n.value
+
+
+def last_describe_handovers(device=0):
+    """Keypoints of the last SURF run that the fixed-point window sampler handed to the reference sampler."""
+    n = ctypes.c_int(0)
+    check(_lib.load().vfsms_last_describe_handovers(_lib.context(device), ctypes.byref(n)), "vfsms_last_describe_handovers")
     return n.value
 
 

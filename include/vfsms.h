@@ -80,24 +80,23 @@ int64_t vfsms_launch_count(vfsms_ctx *ctx);
  * 1 = exact fp32 SIMT kernel, 2 = like 0 with the GEMM on single CTAs (128 x 128 tiles, cta_group::1) instead of CTA pairs.
  * All produce identical results; 1 and 2 exist for verification. */
 int vfsms_set_matcher(vfsms_ctx *ctx, int mode);
-/* Kernel-variant switches.  Every variant of an option produces identical results; the non-default ones are alternative
- * schedules kept selectable for A/B measurement (bench.py --opt name=value, environment VFSMS_OPTS="name=value,...": read
- * once per vfsms_create).  Unknown options / values return VFSMS_E_ARG. */
+/* Kernel-schedule switches.  Every value of an option produces identical results; the defaults are what bench.py times and what
+ * the oracle tests run on, the others stay selectable for verification and A/B measurement (bench.py --opt name=value, environment
+ * VFSMS_OPTS="name=value,...": read once per vfsms_create).  Unknown options / values return VFSMS_E_ARG. */
 enum {
-    VFSMS_OPT_DESCRIBE_MODE = 0,  /* "describe": rotated-window sampler of the SURF descriptor.  0 = LDG, 1 (default) = one
-                                   * float texture per image, 2 = one stacked texture whose handle is a kernel parameter
-                                   * (uniform-register texture fetch, no border test for windows that lie inside the image);
-                                   * 3 = 2 with the border-free loop unrolled x4, 4 = 3 compiled for 3 CTAs per SM (80 registers),
-                                   * 5 = 2 compiled for 5 CTAs per SM (48 registers), 6 = 5 without unrolling; 7 = 2 with 32.32
-                                   * fixed-point sample coordinates in the border-free loop (no FP64), 8 = 7 for 5 CTAs per SM */
-    VFSMS_OPT_SORT_MODE = 1,      /* "sort": KeypointGreater ordering.  0 (default) = rank by counting over all staged
-                                   * candidates, 1 = one CTA per image: shared-memory bitonic sort of 64-bit keys + tie fix-up */
-    VFSMS_OPT_DESCRIBE_LPT = 2,   /* "lpt": 0 (default) = keypoints described in response order, 1 = windows of 128 px and more
-                                   * first (two passes over the work list), so that no giant window is met at the end of the launch;
-                                   * 2 / 3 = the same with the split at 64 / 256 px */
-    VFSMS_OPT_ENTROPY = 3,        /* "entropy": Huffman decoding of JPEG tiles.  0 (default) = host threads, one file each; 1 = on the
-                                   * device: self-synchronising parallel decode of 1024-bit subsequences (files with restart
-                                   * intervals keep the host stage); same coefficients, symbol for symbol */
+    VFSMS_OPT_DESCRIBE_MODE = 0,  /* "describe": rotated-window sampler of the SURF descriptor (csrc/surf_describe.cuh).
+                                   * 1 (default) = 32.32 fixed-point positions, window rows sampled in chunks through one stacked float
+                                   * texture with four gathers in flight per lane; keypoints whose direction or row starts are not
+                                   * multiples of 2^-32 are handed to sampler 0.  0 = reference sampler for every keypoint: one row at
+                                   * a time, double precision, straight from the u8 image */
+    VFSMS_OPT_SORT_MODE = 1,      /* "sort": KeypointGreater ordering.  1 (default) = 13-bit response histogram, then rank counting
+                                   * inside each candidate's own bin; 0 = rank by counting over all staged candidates */
+    VFSMS_OPT_DESCRIBE_LPT = 2,   /* "lpt": describe the large windows first (two passes over the work list), so that no giant window
+                                   * is met at the end of the launch: split at 64 px (2, default), 128 px (1), 256 px (3); 0 = keypoints
+                                   * in response order */
+    VFSMS_OPT_ENTROPY = 3,        /* "entropy": Huffman decoding of JPEG tiles.  1 (default) = on the device: self-synchronising
+                                   * parallel decode of 1024-bit subsequences (files with restart intervals take the host stage);
+                                   * 0 = host threads, one file each; same coefficients, symbol for symbol */
     VFSMS_OPT_COUNT
 };
 int vfsms_set_option(vfsms_ctx *ctx, int option, int value);
@@ -105,6 +104,8 @@ int vfsms_get_option(vfsms_ctx *ctx, int option, int *value_out);
 const char *vfsms_option_name(int option);
 /* Number of queries of the last tensor-core match that needed the exact fallback scan (synchronises the stream). */
 int vfsms_last_match_fallbacks(vfsms_ctx *ctx, int *count_out);
+/* Number of keypoints of the last SURF run that the fixed-point window sampler handed to the reference sampler (synchronises). */
+int vfsms_last_describe_handovers(vfsms_ctx *ctx, int *count_out);
 
 /* Per-stage device timing with CUDA events recorded on the launching stream (bench.py's roofline numbers).
  * Off by default.  vfsms_profile_read synchronises the stream, then returns accumulated milliseconds and call

@@ -34,7 +34,7 @@ def main():
     ap.add_argument("--overlap", type=int, default=205)
     ap.add_argument("--gray", action="store_true", help="isColorMode = False")
     ap.add_argument("--fuse", default="fadeInAndFadeOut")
-    ap.add_argument("--options", default="", help='kernel variants, e.g. "entropy=1,describe=2"')
+    ap.add_argument("--options", default="", help='kernel variants, e.g. "entropy=0,describe=0"')
     ap.add_argument("--cpu-pairs", type=int, default=2, help="pairs the host-side port is timed on (0: skip)")
     ap.add_argument("--keep", action="store_true", help="keep the temporary directory")
     a = ap.parse_args()

@@ -81,6 +81,7 @@ static inline unsigned __ballot_sync(unsigned, int pred)
     return r;
 }
 static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
+static inline int __all_sync(unsigned m, int p) { return __ballot_sync(m, !p) == 0; }
 
 // ---------------------------------------------------------------- atomics (one OS thread: plain read-modify-write)
 // (relaxed __atomic builtins: the same plain read-modify-write for one OS thread, but ThreadSanitizer knows they are atomics)
@@ -100,6 +101,7 @@ template <class T> static inline unsigned atomicInc(T *p, unsigned lim) { unsign
 // ---------------------------------------------------------------- intrinsics
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline int __float2int_rn(float v) { return (int)lrintf(v); }
+static inline float __int2float_rn(int v) { return (float)v; }
 static inline float __uint2float_rn(unsigned v) { return (float)v; }      // round to nearest even (the default FP environment)
 static inline int __float2int_rd(float v) { return (int)floorf(v); }
 static inline int __float2int_rz(float v) { return (int)v; }

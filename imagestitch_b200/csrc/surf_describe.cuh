@@ -201,22 +201,15 @@ __device__ __forceinline__ void patch_to_descriptor(DescScratch &S, int lane, in
 }
 
 // ---- INTER_AREA (cv::resize of the win x win u8 window to 21 x 21) folded over window rows arriving in order.
-// Lane dx (< 21; lanes >= 21 shadow column 20) owns output column dx: its decimation-table entries (sx1, sx2, edge taps and weights),
-// the running row accumulator `sum` and, for integer scales, the box sum.  The row table of output row dy equals lane dy's column
-// table (square window, one scale), fetched by shuffle when dy advances.
+// Lane dx (< 21; lanes >= 21 shadow column 20) owns output column dx: its decimation-table entries (sx1, n interior taps, edge taps
+// and weights), the running row accumulator `sum` and, for integer scales, the box sum.  The row table of output row dy equals lane
+// dy's column table (square window, one scale): fetched by shuffle at the start of every chunk and whenever dy advances, so that
+// only the column entries stay live while the next chunk is being sampled.
 struct AreaFold {
-    int win, iscale; bool fast, ident;
-    int sx1, sx2, nb, dxc; bool xl, xr; float axl, axm, axr, fs;
+    int win, iscale, mode;       // mode 0: general decimation tables, 1: integer scale (box sums), 2: win == 21 (copy)
+    int sx1, n, nmax, flags;     // flags: bit 0 = left edge tap, bit 1 = right edge tap
+    float axl, axm, axr;
     int dy; bool first; float sum;
-    int sy1, sy2, ya, yb; bool yl, yr; float ayl, aym, ayr;
-
-    __device__ __forceinline__ void load_dy(int d)
-    {
-        sy1 = __shfl_sync(0xffffffffu, sx1, d); sy2 = __shfl_sync(0xffffffffu, sx2, d);
-        yl = __shfl_sync(0xffffffffu, (int)xl, d) != 0; yr = __shfl_sync(0xffffffffu, (int)xr, d) != 0;
-        ayl = __shfl_sync(0xffffffffu, axl, d); aym = __shfl_sync(0xffffffffu, axm, d); ayr = __shfl_sync(0xffffffffu, axr, d);
-        ya = yl ? sy1 - 1 : sy1; yb = yr ? sy2 : sy2 - 1;
-    }
 
     __device__ __forceinline__ void init(int w, int lane)
     {
@@ -225,73 +218,85 @@ struct AreaFold {
         const double inv_scale = (double)PD / win;
         const double scale = 1. / inv_scale;
         iscale = __double2int_rn(scale);
-        fast = fabs(scale - iscale) < DBL_EPSILON;
-        ident = win == PD;
-        dxc = lane < PD ? lane : PD - 1;
+        mode = win == PD ? 2 : (fabs(scale - iscale) < DBL_EPSILON ? 1 : 0);
+        const int dxc = lane < PD ? lane : PD - 1;
         dy = 0; first = true; sum = 0;
-        fs = 1.f / (float)(iscale * iscale);
-        sx1 = sx2 = nb = 0; xl = xr = false; axl = axm = axr = 0;
-        if (!ident && !fast) {
+        sx1 = dxc * iscale; n = nmax = flags = 0; axl = axr = 0; axm = 1.f / (float)(iscale * iscale);
+        if (mode == 0) {
             // column taps of this lane (decimation table entries of output column dx, in table order)
             const double fsx1 = dxc * scale, fsx2 = fsx1 + scale, cwx = fmin(scale, win - fsx1);
-            sx1 = __double2int_ru(fsx1); sx2 = __double2int_rd(fsx2);
+            int sx2 = __double2int_rd(fsx2);
+            sx1 = __double2int_ru(fsx1);
             sx2 = min(sx2, win - 1); sx1 = min(sx1, sx2);
-            xl = (sx1 - fsx1 > 1e-3); xr = (fsx2 - sx2 > 1e-3);
+            flags = (sx1 - fsx1 > 1e-3 ? 1 : 0) | (fsx2 - sx2 > 1e-3 ? 2 : 0);
             axl = (float)((sx1 - fsx1) / cwx); axm = (float)(1.0 / cwx);
             axr = (float)(fmin(fmin(fsx2 - sx2, 1.), cwx) / cwx);
-            nb = sx2 - sx1;                                   // interior taps of this lane; the warp minimum runs unpredicated
+            n = sx2 - sx1;                                    // interior taps of this lane; the loop runs to the warp maximum, predicated
+            nmax = n;
 #pragma unroll
-            for (int o = 16; o; o >>= 1) nb = min(nb, __shfl_xor_sync(0xffffffffu, nb, o));
-            load_dy(0);
+            for (int o = 16; o; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
         }
     }
 
     __device__ __forceinline__ bool done() const { return dy >= PATCH_SZ + 1; }
 
-    // row `sy` of the window (exact floats 0..255 in shared memory); rows arrive in increasing order, each exactly once
-    __device__ __forceinline__ void row(const float *__restrict__ r, int sy, uint8_t *__restrict__ patch, int lane)
+    // rows r0 .. r0 + nrows - 1 of the window (exact floats 0..255 in shared memory, `pitch` floats apart); chunks arrive in order
+    __device__ __forceinline__ void rows(const float *__restrict__ buf, int pitch, int r0, int nrows, uint8_t *__restrict__ patch, int lane)
     {
         constexpr int PD = PATCH_SZ + 1;
-        if (dy >= PD) return;
-        if (ident) {
-            if (lane < PD) patch[sy * PD + lane] = (uint8_t)(int)r[lane];
-            dy = sy + 1;
+        if (mode == 2) {
+            for (int i = 0; i < nrows && dy < PD; i++, dy++)
+                if (lane < PD) patch[(r0 + i) * PD + lane] = (uint8_t)(int)buf[i * pitch + lane];
             return;
         }
-        if (fast) {
+        if (mode == 1) {
             // integer factor: exact integer box sums (<= 35^2 * 255: exact in float)
-            const float *p = r + dxc * iscale;
-            for (int xx = 0; xx < iscale; xx++) sum += p[xx];
-            if (sy == dy * iscale + iscale - 1) {
-                int out;
-                if (iscale == 2) out = (int)((sum + 2.f) * 0.25f);          // (sum + 2) >> 2
-                else out = min(max(__float2int_rn(sum * fs), 0), 255);
-                if (lane < PD) patch[dy * PD + lane] = (uint8_t)out;
-                dy++; sum = 0;
+            for (int i = 0; i < nrows && dy < PD; i++) {
+                const float *p = buf + i * pitch + sx1;
+                for (int xx = 0; xx < iscale; xx++) sum += p[xx];
+                if (r0 + i == dy * iscale + iscale - 1) {
+                    int out;
+                    if (iscale == 2) out = (int)((sum + 2.f) * 0.25f);          // (sum + 2) >> 2
+                    else out = min(max(__float2int_rn(sum * axm), 0), 255);
+                    if (lane < PD) patch[dy * PD + lane] = (uint8_t)out;
+                    dy++; sum = 0;
+                }
             }
             return;
         }
-        if (sy < ya) return;
-        // horizontal taps of this source row, in table order
-        const float *p = r + sx1;
-        float bufv = xl ? p[-1] * axl : 0.f;
-        int t = 0;
-        for (; t + 4 <= nb; t += 4) {
-            bufv += p[t] * axm; bufv += p[t + 1] * axm; bufv += p[t + 2] * axm; bufv += p[t + 3] * axm;
-        }
-        for (; t < nb; t++) bufv += p[t] * axm;
-        for (; t < sx2 - sx1; t++) bufv += p[t] * axm;          // lanes whose column holds more taps than the warp minimum
-        if (xr) bufv += r[sx2] * axr;
-        // vertical fold: the row belongs to output row dy and, when it straddles the boundary, to dy + 1 as well
-        while (true) {
-            const float beta = (yl && sy == sy1 - 1) ? ayl : ((yr && sy == sy2) ? ayr : aym);
-            if (first) { sum = beta * bufv; first = false; } else sum += beta * bufv;
-            if (sy != yb) break;
-            if (lane < PD) patch[dy * PD + lane] = (uint8_t)min(max(round_half_even_u8(sum), 0), 255);
-            dy++; first = true;
-            if (dy >= PD) break;
-            load_dy(dy);
-            if (ya != sy) break;
+        if (dy >= PD) return;
+        const bool xl = flags & 1, xr = flags & 2;
+        const int sx2 = sx1 + n;
+        // row table of the current output row: lane dy's column table
+        int sy1, sy2, ya, yb; bool yl, yr; float ayl, aym, ayr;
+        auto load_dy = [&](int d) {
+            sy1 = __shfl_sync(0xffffffffu, sx1, d); sy2 = sy1 + __shfl_sync(0xffffffffu, n, d);
+            const int f = __shfl_sync(0xffffffffu, flags, d);
+            yl = f & 1; yr = f & 2;
+            ayl = __shfl_sync(0xffffffffu, axl, d); aym = __shfl_sync(0xffffffffu, axm, d); ayr = __shfl_sync(0xffffffffu, axr, d);
+            ya = yl ? sy1 - 1 : sy1; yb = yr ? sy2 : sy2 - 1;
+        };
+        load_dy(dy);
+        for (int i = 0; i < nrows; i++) {
+            const int sy = r0 + i;
+            if (sy < ya) continue;
+            // horizontal taps of this source row, in table order
+            const float *p = buf + i * pitch + sx1;
+            float bufv = xl ? p[-1] * axl : 0.f;
+#pragma unroll 2
+            for (int t = 0; t < nmax; t++) if (t < n) bufv += p[t] * axm;
+            if (xr) bufv += p[n] * axr;
+            // vertical fold: the row belongs to output row dy and, when it straddles the boundary, to dy + 1 as well
+            while (true) {
+                const float beta = (yl && sy == sy1 - 1) ? ayl : ((yr && sy == sy2) ? ayr : aym);
+                if (first) { sum = beta * bufv; first = false; } else sum += beta * bufv;
+                if (sy != yb) break;
+                if (lane < PD) patch[dy * PD + lane] = (uint8_t)min(max(round_half_even_u8(sum), 0), 255);
+                dy++; first = true;
+                if (dy >= PD) return;
+                load_dy(dy);
+                if (ya != sy) break;
+            }
         }
     }
 };
@@ -366,7 +371,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) describe_reference_kernel(
                 }
             }
             __syncwarp();
-            F.row(rowf, r, S.patch, lane);
+            F.rows(rowf, 0, r, 1, S.patch, lane);
             __syncwarp();
         }
         patch_to_descriptor(S, lane, extended, desc_all + ((size_t)b * kp_cap + k) * dsize);
@@ -383,6 +388,65 @@ __device__ __forceinline__ float bilinear_scaled(const float4 g, float A, float 
     const float p00 = g.w, p01 = g.z, p10 = g.x, p11 = g.y;
     const float v = p00 * ia * ib + p01 * A * ib + p10 * ia * B + p11 * A * B;
     return (v + 12582912.0f) - 12582912.0f;          // cvRound, ties to even, as an exact float
+}
+
+// Samples the warp-rounds [0, Q4) of the chunk described by S.slot into S.buf, round q at buf[32 q + lane]: four gathers are issued
+// before the first is consumed.  mxc / myc: this lane's column offset inside a round times the per-column step, in fixed point.
+// CHECK: the window may leave the image -- such samples take the CPU's clamped nearest pixel.
+// FINE: 16.48 instead of 32.32 fixed point (directions and row starts that are multiples of 2^-48 only: |cos| or |sin| below 2^-9
+// or equal to 1, rows that start within 2^-9 of an image axis); the fraction then takes the slow 64-bit conversion.
+template <bool CHECK, bool FINE>
+__device__ __forceinline__ void sample_chunk(DescScratch &S, const cudaTextureObject_t tex, int Q4, unsigned long long mxc,
+                                             unsigned long long myc, int lane, const uint8_t *__restrict__ img, int stride,
+                                             int ncols1, int nrows1, int row_off)
+{
+    const ulonglong2 *slot = (const ulonglong2 *)S.slot;
+    float *out = S.buf + lane;
+    constexpr unsigned long long FMASK = (1ULL << 48) - 1, FHALF = 1ULL << 47;
+#pragma unroll 1
+    for (int q0 = 0; q0 < Q4; q0 += 4, slot += 4, out += 128) {
+        float4 g[4]; float A[4], B[4]; unsigned oob = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const ulonglong2 e = slot[u];
+            const unsigned long long X = e.x + mxc, Y = e.y + myc;
+            int ix1, iy1;
+            if (!FINE) {
+                ix1 = (int)(X >> 32); iy1 = (int)(Y >> 32);
+                A[u] = __uint2float_rn((unsigned)X); B[u] = __uint2float_rn((unsigned)Y);
+            } else {
+                ix1 = (int)((long long)X >> 48); iy1 = (int)((long long)Y >> 48);
+                A[u] = __ull2float_rn(X & FMASK) * 1.52587890625e-05f;      // one rounding of the 48-bit fraction, then an exact 2^-16
+                B[u] = __ull2float_rn(Y & FMASK) * 1.52587890625e-05f;
+            }
+            g[u] = tex2Dgather<float4>(tex, __int2float_rn(ix1), __int2float_rn(iy1), 0);
+            if (CHECK && !((unsigned)(ix1 - 1) < (unsigned)ncols1 && (unsigned)(iy1 - 1 - row_off) < (unsigned)nrows1)) oob |= 1u << u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            float v = bilinear_scaled(g[u], A[u], B[u]);
+            if (CHECK && (oob >> u & 1)) {
+                // outside the image: the CPU takes the clamped nearest pixel, cvRound(pixel) = ties to even
+                const ulonglong2 e = slot[u];
+                const unsigned long long X = e.x + mxc, Y = e.y + myc;
+                int ix, iy; bool upx, upy;
+                if (!FINE) {
+                    ix = (int)(X >> 32) - 1; iy = (int)(Y >> 32) - 1 - row_off;
+                    const unsigned fx = (unsigned)X, fy = (unsigned)Y;
+                    upx = fx > 0x80000000u || (fx == 0x80000000u && (ix & 1));
+                    upy = fy > 0x80000000u || (fy == 0x80000000u && (iy & 1));
+                } else {
+                    ix = (int)((long long)X >> 48) - 1; iy = (int)((long long)Y >> 48) - 1 - row_off;
+                    const unsigned long long fx = X & FMASK, fy = Y & FMASK;
+                    upx = fx > FHALF || (fx == FHALF && (ix & 1));
+                    upy = fy > FHALF || (fy == FHALF && (iy & 1));
+                }
+                const int x = min(max(ix + (upx ? 1 : 0), 0), ncols1), y = min(max(iy + (upy ? 1 : 0), 0), nrows1);
+                v = (float)img[(size_t)y * stride + x];
+            }
+            out[u * 32] = v;
+        }
+    }
 }
 
 template <int MINB>
@@ -429,89 +493,76 @@ __global__ void __launch_bounds__(WK_WARPS * 32, MINB) describe_fixed_kernel(
         const float sin_dir = -(float)sin((double)dir_rad);
         const float cos_dir = (float)cos((double)dir_rad);
         const float win_offset = -(float)(win - 1) / 2;
-        float chain_x = cx + win_offset * cos_dir + win_offset * sin_dir;      // start_x / start_y of the next unsampled row
-        float chain_y = cy - win_offset * sin_dir + win_offset * cos_dir;
         const float ac = fabsf(cos_dir), as = fabsf(sin_dir);
-        // multiples of 2^-32 below 1 (warp-uniform); everything else is the reference kernel's
-        bool exact = (ac == 0.f || ac >= 0.001953125f) && ac < 1.f && (as == 0.f || as >= 0.001953125f) && as < 1.f;
-        const unsigned c32 = (unsigned)(ac * 4294967296.0f), s32 = (unsigned)(as * 4294967296.0f);
+        // both steps multiples of 2^-32 below 1 -> 32.32 positions; multiples of 2^-48 up to 1 -> 16.48 (slower conversions, rare)
+        const bool ok32 = (ac == 0.f || ac >= 0.001953125f) && ac < 1.f && (as == 0.f || as >= 0.001953125f) && as < 1.f;
+        const bool ok48 = (ac == 0.f || ac >= 2.98023223876953125e-08f) && (as == 0.f || as >= 2.98023223876953125e-08f) &&
+                          rows < 16384 && cols < 16384;
         const bool xneg = cos_dir < 0.f;            // x decreases along a row
         const bool yneg = sin_dir > 0.f;            // pixel_y -= sin_dir
-        const unsigned mx = xneg ? 31 - lane : lane, my = yneg ? 31 - lane : lane;
         const int row_off = (b - b_first) * rows;
         // every sample of the window (half diagonal + the float chain's drift, 2 px of slack) keeps its 2x2 footprint inside the image
         const float Rw = (float)(win - 1) * 0.7072f + 2.0f;
         const bool interior = cx - Rw >= 1.f && cx + Rw <= (float)(ncols1 - 1) && cy - Rw >= 1.f && cy + Rw <= (float)(nrows1 - 1);
-        const int kpr = (win + 31) >> 5;            // warp-rounds per window row
-        const int R = DESC_SLOTS / kpr;             // rows per chunk (R * win <= DESC_BUF)
-        AreaFold F;
-        F.init(win, lane);
+        const int kpr = (win + 31) >> 5;            // warp-rounds per window row; a row occupies 32 * kpr floats of S.buf
+        const int R = DESC_SLOTS / kpr;             // rows per chunk
 
-        for (int r0 = 0; r0 < win && exact && !F.done(); r0 += R) {
-            const int Rc = min(R, win - r0), Q = Rc * kpr;
-            // ---- slot table: lane q owns warp-round q = (row r0 + q / kpr, columns 32 * (q % kpr) ...)
-            {
-                const int myrow = lane / kpr, myk = lane - myrow * kpr;
-                float cap_x = 1.f, cap_y = 1.f;
-                for (int i = 0; i < Rc; i++) {       // the CPU's float chain, advanced by every lane alike
-                    if (i == myrow) { cap_x = chain_x; cap_y = chain_y; }
-                    chain_x += sin_dir; chain_y += cos_dir;
-                }
-                const bool ok = lane >= Q || ((cap_x == 0.f || fabsf(cap_x) >= 0.001953125f) && (cap_y == 0.f || fabsf(cap_y) >= 0.001953125f));
-                if (!__all_sync(0xffffffffu, ok)) { exact = false; break; }
-                const long long X0 = (long long)((double)cap_x * 4294967296.0);           // exact: multiples of 2^-32
-                const long long Y0 = (long long)((double)cap_y * 4294967296.0);
-                const long long kx = xneg ? -(long long)(32 * myk + 31) : (long long)(32 * myk);
-                const long long ky = yneg ? -(long long)(32 * myk + 31) : (long long)(32 * myk);
-                // + 1: tex2Dgather at (ix + 1, iy + 1) returns the footprint (ix, iy) .. (ix + 1, iy + 1); + row_off: image b of the stack
-                const unsigned long long Ux = (unsigned long long)(X0 + kx * (long long)c32 + (1LL << 32));
-                const unsigned long long Uy = (unsigned long long)(Y0 + ky * (long long)s32 + ((long long)(1 + row_off) << 32));
-                S.slot[lane] = make_uint4((unsigned)Ux, (unsigned)(Ux >> 32), (unsigned)Uy, (unsigned)(Uy >> 32));
-            }
-            __syncwarp();
-            // ---- sample the chunk: four gathers in flight per lane
-            int base = 0, kk = 0;                    // buffer offset and column block of warp-round q0
-#pragma unroll 1
-            for (int q0 = 0; q0 < Q; q0 += 4) {
-                float4 g[4]; float A[4], B[4]; unsigned oob = 0;
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint4 e = S.slot[min(q0 + u, Q - 1)];
-                    const unsigned long long X = (((unsigned long long)e.y << 32) | e.x) + (unsigned long long)mx * c32;
-                    const unsigned long long Y = (((unsigned long long)e.w << 32) | e.z) + (unsigned long long)my * s32;
-                    const int ix1 = (int)(X >> 32), iy1 = (int)(Y >> 32);
-                    A[u] = __uint2float_rn((unsigned)X); B[u] = __uint2float_rn((unsigned)Y);
-                    g[u] = tex2Dgather<float4>(tex, __int2float_rn(ix1), __int2float_rn(iy1), 0);
-                    if (!interior && !((unsigned)(ix1 - 1) < (unsigned)ncols1 && (unsigned)(iy1 - 1 - row_off) < (unsigned)nrows1)) oob |= 1u << u;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (q0 + u < Q) {                // warp-uniform
-                        float v = bilinear_scaled(g[u], A[u], B[u]);
-                        if (!interior && (oob >> u & 1)) {
-                            // outside the image: the CPU takes the clamped nearest pixel, cvRound(pixel) = ties to even
-                            const uint4 e = S.slot[q0 + u];
-                            const unsigned long long X = (((unsigned long long)e.y << 32) | e.x) + (unsigned long long)mx * c32;
-                            const unsigned long long Y = (((unsigned long long)e.w << 32) | e.z) + (unsigned long long)my * s32;
-                            const int ix = (int)(X >> 32) - 1, iy = (int)(Y >> 32) - 1 - row_off;
-                            const unsigned fx = (unsigned)X, fy = (unsigned)Y;
-                            int x = ix + ((fx > 0x80000000u || (fx == 0x80000000u && (ix & 1))) ? 1 : 0);
-                            int y = iy + ((fy > 0x80000000u || (fy == 0x80000000u && (iy & 1))) ? 1 : 0);
-                            x = min(max(x, 0), ncols1); y = min(max(y, 0), nrows1);
-                            v = (float)img[(size_t)y * stride + x];
-                        }
-                        const int j = kk * 32 + lane;
-                        if (j < win) S.buf[base + j] = v;
-                        if (++kk == kpr) { kk = 0; base += win; }
+        bool described = false;
+        // attempt 0: 32.32; attempt 1: 16.48, taken when the direction needs it or a row of attempt 0 started within 2^-9 of an axis
+        for (int attempt = ok32 ? 0 : 1; attempt < 2 && !described; attempt++) {
+            const bool fine = attempt == 1;
+            if (fine && !ok48) break;
+            const double fscale = fine ? 281474976710656.0 : 4294967296.0;
+            const float tiny = fine ? 2.98023223876953125e-08f : 0.001953125f;       // row starts must be 0 or at least this (ulp >= one unit)
+            const int fbits = fine ? 48 : 32;
+            const long long cF = (long long)((double)ac * fscale), sF = (long long)((double)as * fscale);   // exact
+            const unsigned long long mxc = (unsigned long long)((xneg ? 31 - lane : lane) * cF);
+            const unsigned long long myc = (unsigned long long)((yneg ? 31 - lane : lane) * sF);
+            float chain_x = cx + win_offset * cos_dir + win_offset * sin_dir;      // start_x / start_y of the next unsampled row
+            float chain_y = cy - win_offset * sin_dir + win_offset * cos_dir;
+            AreaFold F;
+            F.init(win, lane);
+            bool bad = false;
+            for (int r0 = 0; r0 < win && !F.done(); r0 += R) {
+                const int Rc = min(R, win - r0), Q = Rc * kpr;
+                // ---- slot table: lane q owns warp-round q = (row r0 + q / kpr, columns 32 * (q % kpr) ...); lanes >= Q repeat round Q - 1
+                {
+                    const int q = min(lane, Q - 1);
+                    const int myrow = q / kpr, myk = q - myrow * kpr;
+                    float cap_x = 1.f, cap_y = 1.f;
+                    for (int i = 0; i < Rc; i++) {       // the CPU's float chain, advanced by every lane alike
+                        if (i == myrow) { cap_x = chain_x; cap_y = chain_y; }
+                        chain_x += sin_dir; chain_y += cos_dir;
                     }
+                    const bool ok = (cap_x == 0.f || fabsf(cap_x) >= tiny) && (cap_y == 0.f || fabsf(cap_y) >= tiny);
+                    if (!__all_sync(0xffffffffu, ok)) { bad = true; break; }
+                    const long long X0 = (long long)((double)cap_x * fscale);           // exact: multiples of one unit
+                    const long long Y0 = (long long)((double)cap_y * fscale);
+                    const long long kx = xneg ? -(long long)(32 * myk + 31) : (long long)(32 * myk);
+                    const long long ky = yneg ? -(long long)(32 * myk + 31) : (long long)(32 * myk);
+                    // + 1: tex2Dgather at (ix + 1, iy + 1) returns the footprint (ix, iy) .. (ix + 1, iy + 1); + row_off: image b of the stack
+                    ulonglong2 e;
+                    e.x = (unsigned long long)(X0 + kx * cF + (1LL << fbits));
+                    e.y = (unsigned long long)(Y0 + ky * sF + ((long long)(1 + row_off) << fbits));
+                    ((ulonglong2 *)S.slot)[lane] = e;
                 }
+                __syncwarp();
+                const int Q4 = (Q + 3) & ~3;
+                if (!fine) {
+                    if (interior) sample_chunk<false, false>(S, tex, Q4, mxc, myc, lane, img, stride, ncols1, nrows1, row_off);
+                    else sample_chunk<true, false>(S, tex, Q4, mxc, myc, lane, img, stride, ncols1, nrows1, row_off);
+                } else {
+                    if (interior) sample_chunk<false, true>(S, tex, Q4, mxc, myc, lane, img, stride, ncols1, nrows1, row_off);
+                    else sample_chunk<true, true>(S, tex, Q4, mxc, myc, lane, img, stride, ncols1, nrows1, row_off);
+                }
+                __syncwarp();
+                // ---- fold the chunk's rows into the patch
+                F.rows(S.buf, kpr * 32, r0, Rc, S.patch, lane);
+                __syncwarp();
             }
-            __syncwarp();
-            // ---- fold the chunk's rows into the patch
-            for (int i = 0; i < Rc; i++) F.row(S.buf + i * win, r0 + i, S.patch, lane);
-            __syncwarp();
+            described = !bad && F.done();
         }
-        if (!exact || !F.done()) {                   // hand over to the reference kernel (it repeats the orientation)
+        if (!described) {                            // hand over to the reference kernel (it repeats the orientation)
             if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = item;
             continue;
         }

@@ -102,6 +102,7 @@ template <class T> static inline unsigned atomicInc(T *p, unsigned lim) { unsign
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline int __float2int_rn(float v) { return (int)lrintf(v); }
 static inline float __int2float_rn(int v) { return (float)v; }
+static inline float __ull2float_rn(unsigned long long v) { return (float)v; }
 static inline float __uint2float_rn(unsigned v) { return (float)v; }      // round to nearest even (the default FP environment)
 static inline int __float2int_rd(float v) { return (int)floorf(v); }
 static inline int __float2int_rz(float v) { return (int)v; }

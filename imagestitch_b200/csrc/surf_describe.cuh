@@ -73,15 +73,20 @@ struct __align__(16) DescScratch {
     float buf[DESC_BUF];         // orientation: X[0..127] Y[128..255] A[256..383] (int) ; window phase: sampled rows as exact floats ;
                                  // descriptor: DX[0..399] DY[400..799]
     uint4 slot[DESC_SLOTS];      // fixed kernel: 32.32 start (x lo, x hi, y lo, y hi) of each warp-round of the current chunk
-    float vec[128];
+    float vec[168];              // descriptor bins (128) ; before that: INTER_AREA column table (21 x 8 words)
     uint8_t patch[448];
 };
 
-// ---- dominant orientation (OpenCV's 72 windows of 60 degrees over the 113 Gaussian-weighted Haar responses); warp-collective
+// ---- dominant orientation (OpenCV's 72 windows of 60 degrees over the 113 Gaussian-weighted Haar responses); warp-collective.
+// Window i = 5w holds sample j when |round(angle_j) - i| < 30 or > 330, i.e. when w lies in the circular range of 11 (12 when the
+// angle is not a multiple of 5) windows starting at angle / 5 - 5 (mod 72).  Each sample's owner turns that range into three 24-bit
+// membership words (w = 24 g + l); lane l < 24 then walks the samples ONCE, in order, adding into its windows l, l + 24, l + 48
+// under one bit test each: the CPU's summation order per window with a third of the compares.
 __device__ __forceinline__ float orient_keypoint(DescScratch &S, int lane, const int32_t *__restrict__ I, int W, int srows, int scols,
                                                  float cx, float cy, float s, int gws)
 {
-    float *sX = S.buf, *sY = S.buf + 128; int *sA = (int *)(S.buf + 256);
+    float2 *sXY = (float2 *)S.buf;                    // [128]
+    uint4 *sM = (uint4 *)(S.buf + 256);               // [128]
     const unsigned lt_mask = (1u << lane) - 1;
     const int h2 = __float2int_rn(((float)gws / 4) * 2);
     const int h4 = __float2int_rn(((float)gws / 4) * 4);
@@ -117,24 +122,42 @@ __device__ __forceinline__ float orient_keypoint(DescScratch &S, int lane, const
         const unsigned bal = __ballot_sync(0xffffffffu, have);
         if (have) {
             const int pos = nangle + __popc(bal & lt_mask);
-            sX[pos] = vX; sY[pos] = vY; sA[pos] = __float2int_rn(fast_atan2_deg(vY, vX));
+            int A = __float2int_rn(fast_atan2_deg(vY, vX));       // 0 .. 360
+            if (A >= 360) A -= 360;
+            const int a = A / 5, bq = A - 5 * a;
+            int lo = a - 5; if (lo < 0) lo += 72;
+            const unsigned M = (1u << (bq > 0 ? 12 : 11)) - 1;
+            unsigned wd[3];
+#pragma unroll
+            for (int g = 0; g < 3; g++) {
+                int sh = lo - 24 * g;
+                if (sh >= 36) sh -= 72; else if (sh < -36) sh += 72;
+                wd[g] = sh >= 0 ? ((M << min(sh, 24)) & 0xFFFFFFu) : (M >> min(-sh, 31));
+            }
+            sXY[pos] = make_float2(vX, vY);
+            sM[pos] = make_uint4(wd[0], wd[1], wd[2], 0u);
         }
         nangle += __popc(bal);
     }
     __syncwarp();
-    float bmod = 0, bx = 0, by = 0; int bw = 1 << 30;
-#pragma unroll 1
-    for (int w = lane; w < 72; w += 32) {
-        // |angle - 5w| < 30 or > 330 over integers in [-355, 360]  <=>  t, t - 360 or t + 360 in [0, 58], t = angle - 5w + 29
-        const int i29 = w * 5 - 29;
-        float sumx = 0, sumy = 0;
+    const unsigned lbit = lane < 24 ? 1u << lane : 0u;
+    float s0x = 0, s0y = 0, s1x = 0, s1y = 0, s2x = 0, s2y = 0;
 #pragma unroll 4
-        for (int j = 0; j < nangle; j++) {
-            const unsigned t = (unsigned)(sA[j] - i29);
-            if (t < 59u || t - 360u < 59u || t + 360u < 59u) { sumx += sX[j]; sumy += sY[j]; }
-        }
-        const float m = sumx * sumx + sumy * sumy;
-        if (m > bmod) { bmod = m; bx = sumx; by = sumy; bw = w; }
+    for (int j = 0; j < nangle; j++) {
+        const uint4 m = sM[j];
+        const float2 v = sXY[j];
+        if (m.x & lbit) { s0x += v.x; s0y += v.y; }
+        if (m.y & lbit) { s1x += v.x; s1y += v.y; }
+        if (m.z & lbit) { s2x += v.x; s2y += v.y; }
+    }
+    float bmod = 0, bx = 0, by = 0; int bw = 1 << 30;
+    if (lane < 24) {                                  // this lane's windows in increasing order: the first maximum wins
+        float m = s0x * s0x + s0y * s0y;
+        if (m > bmod) { bmod = m; bx = s0x; by = s0y; bw = lane; }
+        m = s1x * s1x + s1y * s1y;
+        if (m > bmod) { bmod = m; bx = s1x; by = s1y; bw = lane + 24; }
+        m = s2x * s2x + s2y * s2y;
+        if (m > bmod) { bmod = m; bx = s2x; by = s2y; bw = lane + 48; }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -200,103 +223,106 @@ __device__ __forceinline__ void patch_to_descriptor(DescScratch &S, int lane, in
     __syncwarp();
 }
 
-// ---- INTER_AREA (cv::resize of the win x win u8 window to 21 x 21) folded over window rows arriving in order.
-// Lane dx (< 21; lanes >= 21 shadow column 20) owns output column dx: its decimation-table entries (sx1, n interior taps, edge taps
-// and weights), the running row accumulator `sum` and, for integer scales, the box sum.  The row table of output row dy equals lane
-// dy's column table (square window, one scale): fetched by shuffle at the start of every chunk and whenever dy advances, so that
-// only the column entries stay live while the next chunk is being sampled.
-struct AreaFold {
-    int win, iscale, mode;       // mode 0: general decimation tables, 1: integer scale (box sums), 2: win == 21 (copy)
-    int sx1, n, nmax, flags;     // flags: bit 0 = left edge tap, bit 1 = right edge tap
-    float axl, axm, axr;
-    int dy; bool first; float sum;
+// ---- INTER_AREA (cv::resize of the win x win u8 window to 21 x 21) folded over window rows arriving in chunks, in order.
+// cv::resize's decimation table of output column c -- first interior tap sx1, n interior taps of weight axm, optional edge taps
+// sx1 - 1 (axl) and sx1 + n (axr) -- is built once per keypoint by lane c into S.vec (free until the descriptor); the row table of
+// output row dy is the same entry (square window, one scale).  Per chunk:
+//   horizontal pass: the (row, column) pairs of the chunk are spread over ALL 32 lanes; each sums its taps in table order and the row
+//       sum replaces element `column` of its row in place (a column's taps lie right of every column index written before it);
+//   vertical pass: lane dx < 21 folds the row sums of column dx into `sum` with the row weights, emitting patch rows as they complete.
+// Integer scales (OpenCV's box-sum fast path) and win == 21 use the same passes with unit weights and their own rounding at the end.
+struct __align__(16) AreaCol {                  // nf = n | flags << 16; flags: 1 = left edge tap, 2 = right edge tap
+    int sx1, nf, ya, yb;                        // ya / yb: first / last source row of output row c (the entry read as a row table)
+    float axl, axm, axr, pad;
+};
 
-    __device__ __forceinline__ void init(int w, int lane)
+struct AreaFold {
+    int iscale, mode;            // mode 0: general decimation tables, 1: integer scale (box sums), 2: win == 21 (copy)
+    int nmax, dy; float sum;
+
+    __device__ __forceinline__ void init(DescScratch &S, int win, int lane)
     {
         constexpr int PD = PATCH_SZ + 1;
-        win = w;
         const double inv_scale = (double)PD / win;
         const double scale = 1. / inv_scale;
         iscale = __double2int_rn(scale);
         mode = win == PD ? 2 : (fabs(scale - iscale) < DBL_EPSILON ? 1 : 0);
+        dy = 0; sum = 0;
         const int dxc = lane < PD ? lane : PD - 1;
-        dy = 0; first = true; sum = 0;
-        sx1 = dxc * iscale; n = nmax = flags = 0; axl = axr = 0; axm = 1.f / (float)(iscale * iscale);
+        AreaCol c;
+        c.sx1 = dxc * iscale; c.nf = iscale; c.axl = c.axr = c.pad = 0; c.axm = 1.f; c.ya = c.yb = 0;
         if (mode == 0) {
-            // column taps of this lane (decimation table entries of output column dx, in table order)
+            // decimation table entries of output column dxc, in table order
             const double fsx1 = dxc * scale, fsx2 = fsx1 + scale, cwx = fmin(scale, win - fsx1);
             int sx2 = __double2int_rd(fsx2);
-            sx1 = __double2int_ru(fsx1);
-            sx2 = min(sx2, win - 1); sx1 = min(sx1, sx2);
-            flags = (sx1 - fsx1 > 1e-3 ? 1 : 0) | (fsx2 - sx2 > 1e-3 ? 2 : 0);
-            axl = (float)((sx1 - fsx1) / cwx); axm = (float)(1.0 / cwx);
-            axr = (float)(fmin(fmin(fsx2 - sx2, 1.), cwx) / cwx);
-            n = sx2 - sx1;                                    // interior taps of this lane; the loop runs to the warp maximum, predicated
-            nmax = n;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+            c.sx1 = __double2int_ru(fsx1);
+            sx2 = min(sx2, win - 1); c.sx1 = min(c.sx1, sx2);
+            c.nf = (sx2 - c.sx1) | (c.sx1 - fsx1 > 1e-3 ? 1 << 16 : 0) | (fsx2 - sx2 > 1e-3 ? 2 << 16 : 0);
+            c.axl = (float)((c.sx1 - fsx1) / cwx); c.axm = (float)(1.0 / cwx);
+            c.axr = (float)(fmin(fmin(fsx2 - sx2, 1.), cwx) / cwx);
         }
+        c.ya = c.sx1 - ((c.nf >> 16) & 1); c.yb = c.sx1 + (c.nf & 0xffff) - 1 + ((c.nf >> 17) & 1);
+        nmax = c.nf & 0xffff;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+        if (lane < PD) ((AreaCol *)S.vec)[lane] = c;
+        __syncwarp();
     }
 
     __device__ __forceinline__ bool done() const { return dy >= PATCH_SZ + 1; }
 
-    // rows r0 .. r0 + nrows - 1 of the window (exact floats 0..255 in shared memory, `pitch` floats apart); chunks arrive in order
-    __device__ __forceinline__ void rows(const float *__restrict__ buf, int pitch, int r0, int nrows, uint8_t *__restrict__ patch, int lane)
+    // rows r0 .. r0 + nrows - 1 of the window (exact floats 0..255 in S.buf, `pitch` floats apart, overwritten); chunks arrive in order
+    __device__ __forceinline__ void rows(DescScratch &S, int pitch, int r0, int nrows, int lane)
     {
         constexpr int PD = PATCH_SZ + 1;
-        if (mode == 2) {
-            for (int i = 0; i < nrows && dy < PD; i++, dy++)
-                if (lane < PD) patch[(r0 + i) * PD + lane] = (uint8_t)(int)buf[i * pitch + lane];
-            return;
-        }
-        if (mode == 1) {
-            // integer factor: exact integer box sums (<= 35^2 * 255: exact in float)
-            for (int i = 0; i < nrows && dy < PD; i++) {
-                const float *p = buf + i * pitch + sx1;
-                for (int xx = 0; xx < iscale; xx++) sum += p[xx];
-                if (r0 + i == dy * iscale + iscale - 1) {
-                    int out;
-                    if (iscale == 2) out = (int)((sum + 2.f) * 0.25f);          // (sum + 2) >> 2
-                    else out = min(max(__float2int_rn(sum * axm), 0), 255);
-                    if (lane < PD) patch[dy * PD + lane] = (uint8_t)out;
-                    dy++; sum = 0;
-                }
-            }
-            return;
-        }
         if (dy >= PD) return;
-        const bool xl = flags & 1, xr = flags & 2;
-        const int sx2 = sx1 + n;
-        // row table of the current output row: lane dy's column table
-        int sy1, sy2, ya, yb; bool yl, yr; float ayl, aym, ayr;
-        auto load_dy = [&](int d) {
-            sy1 = __shfl_sync(0xffffffffu, sx1, d); sy2 = sy1 + __shfl_sync(0xffffffffu, n, d);
-            const int f = __shfl_sync(0xffffffffu, flags, d);
-            yl = f & 1; yr = f & 2;
-            ayl = __shfl_sync(0xffffffffu, axl, d); aym = __shfl_sync(0xffffffffu, axm, d); ayr = __shfl_sync(0xffffffffu, axr, d);
-            ya = yl ? sy1 - 1 : sy1; yb = yr ? sy2 : sy2 - 1;
-        };
-        load_dy(dy);
-        for (int i = 0; i < nrows; i++) {
-            const int sy = r0 + i;
-            if (sy < ya) continue;
-            // horizontal taps of this source row, in table order
-            const float *p = buf + i * pitch + sx1;
-            float bufv = xl ? p[-1] * axl : 0.f;
-#pragma unroll 2
-            for (int t = 0; t < nmax; t++) if (t < n) bufv += p[t] * axm;
-            if (xr) bufv += p[n] * axr;
-            // vertical fold: the row belongs to output row dy and, when it straddles the boundary, to dy + 1 as well
-            while (true) {
-                const float beta = (yl && sy == sy1 - 1) ? ayl : ((yr && sy == sy2) ? ayr : aym);
-                if (first) { sum = beta * bufv; first = false; } else sum += beta * bufv;
-                if (sy != yb) break;
-                if (lane < PD) patch[dy * PD + lane] = (uint8_t)min(max(round_half_even_u8(sum), 0), 255);
-                dy++; first = true;
-                if (dy >= PD) return;
-                load_dy(dy);
-                if (ya != sy) break;
+        const AreaCol *tab = (const AreaCol *)S.vec;
+        float *buf = S.buf;
+        // ---- horizontal pass
+        const int nitems = nrows * PD;
+        for (int id0 = 0; id0 < nitems; id0 += 32) {
+            const int id = min(id0 + lane, nitems - 1);
+            const int row = (id * 3121) >> 16, col = id - row * PD;       // id / 21 for id < 2 ^ 12
+            const AreaCol c = tab[col];
+            const int n = c.nf & 0xffff;
+            const float *p = buf + row * pitch + c.sx1;
+            float bufv = (c.nf & (1 << 16)) ? p[-1] * c.axl : 0.f;
+            // taps 0..3 straight-line (all there is for windows up to ~100 px), the rest in a loop to the warp maximum
+            if (0 < n) bufv += p[0] * c.axm;
+            if (1 < n) bufv += p[1] * c.axm;
+            if (2 < n) bufv += p[2] * c.axm;
+            if (3 < n) bufv += p[3] * c.axm;
+            if (nmax > 4) {
+#pragma unroll 4
+                for (int t = 4; t < nmax; t++) if (t < n) bufv += p[t] * c.axm;
             }
+            if (c.nf & (2 << 16)) bufv += p[n] * c.axr;
+            __syncwarp();
+            if (id0 + lane < nitems) buf[row * pitch + col] = bufv;
+        }
+        __syncwarp();
+        // ---- vertical pass (sum starts at 0: 0 + x == x, the CPU's first assignment)
+        const int rend = r0 + nrows;
+        const float *colp = buf + min(lane, PD - 1) - r0 * pitch;          // row sum of source row sy at colp[sy * pitch]
+        while (true) {
+            const AreaCol c = tab[dy];
+            int sy = max(c.ya, r0);
+            if ((c.nf & (1 << 16)) && sy == c.ya) { sum += c.axl * colp[sy * pitch]; sy++; }        // left-edge row (weight axl)
+            const bool ends = c.yb < rend, tail = ends && (c.nf & (2 << 16));
+            const int last = tail ? c.yb - 1 : min(c.yb, rend - 1);
+            for (; sy <= last; sy++) sum += c.axm * colp[sy * pitch];
+            if (tail && sy == c.yb) sum += c.axr * colp[sy * pitch];                                  // right-edge row (weight axr)
+            if (!ends) return;                                // this output row continues in the next chunk
+            int out;
+            if (mode == 0) out = min(max(round_half_even_u8(sum), 0), 255);
+            else if (mode == 2) out = (int)sum;
+            else if (iscale == 2) out = (int)((sum + 2.f) * 0.25f);          // (sum + 2) >> 2
+            else out = min(max(__float2int_rn(sum * (1.f / (float)(iscale * iscale))), 0), 255);
+            if (lane < PD) S.patch[dy * PD + lane] = (uint8_t)out;
+            dy++; sum = 0;
+            if (dy >= PD) return;
+            // (written with the whole entry loaded: `dy >= PD || tab[dy].ya >= rend` gave wrong results on the B200 with nvcc 12.9)
+            { const AreaCol cn = tab[dy]; if ((cn.sx1 - ((cn.nf >> 16) & 1)) >= rend) return; }     // the next output row starts in a later chunk
         }
     }
 };
@@ -342,8 +368,9 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) describe_reference_kernel(
         const float win_offset = -(float)(win - 1) / 2;
         if (!upright) {
             const float dir_rad = descriptor_dir * (float)(M_PI / 180);
-            sin_dir = -(float)sin((double)dir_rad);
-            cos_dir = (float)cos((double)dir_rad);
+            double sd, cd;
+            sincos((double)dir_rad, &sd, &cd);
+            sin_dir = -(float)sd; cos_dir = (float)cd;
             chain_x = cx + win_offset * cos_dir + win_offset * sin_dir;
             chain_y = cy - win_offset * sin_dir + win_offset * cos_dir;
         } else {
@@ -351,7 +378,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) describe_reference_kernel(
             ustart_y = __float2int_rn(cy - win_offset);
         }
         AreaFold F;
-        F.init(win, lane);
+        F.init(S, win, lane);
         float *rowf = S.buf;
         for (int r = 0; r < win && !F.done(); r++) {
             if (!upright) {
@@ -371,7 +398,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) describe_reference_kernel(
                 }
             }
             __syncwarp();
-            F.rows(rowf, 0, r, 1, S.patch, lane);
+            F.rows(S, 0, r, 1, lane);
             __syncwarp();
         }
         patch_to_descriptor(S, lane, extended, desc_all + ((size_t)b * kp_cap + k) * dsize);
@@ -390,63 +417,149 @@ __device__ __forceinline__ float bilinear_scaled(const float4 g, float A, float 
     return (v + 12582912.0f) - 12582912.0f;          // cvRound, ties to even, as an exact float
 }
 
-// Samples the warp-rounds [0, Q4) of the chunk described by S.slot into S.buf, round q at buf[32 q + lane]: four gathers are issued
-// before the first is consumed.  mxc / myc: this lane's column offset inside a round times the per-column step, in fixed point.
-// CHECK: the window may leave the image -- such samples take the CPU's clamped nearest pixel.
-// FINE: 16.48 instead of 32.32 fixed point (directions and row starts that are multiples of 2^-48 only: |cos| or |sin| below 2^-9
-// or equal to 1, rows that start within 2^-9 of an image axis); the fraction then takes the slow 64-bit conversion.
+// Four warp-rounds of a chunk: the gathers are issued before the first is consumed.  slot: their entries of the slot table, out: this
+// lane's element of the first round's row buffer, mxc / myc: this lane's column offset inside a round times the per-column step.
+// CHECK: some sample of these rounds may lie outside the image -- such samples take the CPU's clamped nearest pixel.
+// FINE: 16.48 instead of 32.32 fixed point; the fraction then takes the slow 64-bit conversion.
 template <bool CHECK, bool FINE>
-__device__ __forceinline__ void sample_chunk(DescScratch &S, const cudaTextureObject_t tex, int Q4, unsigned long long mxc,
+__device__ __forceinline__ void sample_rounds(const ulonglong2 *__restrict__ slot, float *__restrict__ out, const cudaTextureObject_t tex,
+                                              unsigned long long mxc, unsigned long long myc, const uint8_t *__restrict__ img, int stride,
+                                              int ncols1, int nrows1, int row_off)
+{
+    constexpr unsigned long long FMASK = (1ULL << 48) - 1, FHALF = 1ULL << 47;
+    float4 g[4]; float A[4], B[4]; unsigned oob = 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const ulonglong2 e = slot[u];
+        const unsigned long long X = e.x + mxc, Y = e.y + myc;
+        int ix1, iy1;
+        if (!FINE) {
+            ix1 = (int)(X >> 32); iy1 = (int)(Y >> 32);
+            A[u] = __uint2float_rn((unsigned)X); B[u] = __uint2float_rn((unsigned)Y);
+        } else {
+            ix1 = (int)((long long)X >> 48); iy1 = (int)((long long)Y >> 48) + row_off;
+            A[u] = __ull2float_rn(X & FMASK) * 1.52587890625e-05f;      // one rounding of the 48-bit fraction, then an exact 2^-16
+            B[u] = __ull2float_rn(Y & FMASK) * 1.52587890625e-05f;
+        }
+        g[u] = tex2Dgather<float4>(tex, __int2float_rn(ix1), __int2float_rn(iy1), 0);
+        if (CHECK && !((unsigned)(ix1 - 1) < (unsigned)ncols1 && (unsigned)(iy1 - 1 - row_off) < (unsigned)nrows1)) oob |= 1u << u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        float v = bilinear_scaled(g[u], A[u], B[u]);
+        if (CHECK && (oob >> u & 1)) {
+            // outside the image: the CPU takes the clamped nearest pixel, cvRound(pixel) = ties to even
+            const ulonglong2 e = slot[u];
+            const unsigned long long X = e.x + mxc, Y = e.y + myc;
+            int ix, iy; bool upx, upy;
+            if (!FINE) {
+                ix = (int)(X >> 32) - 1; iy = (int)(Y >> 32) - 1 - row_off;
+                const unsigned fx = (unsigned)X, fy = (unsigned)Y;
+                upx = fx > 0x80000000u || (fx == 0x80000000u && (ix & 1));
+                upy = fy > 0x80000000u || (fy == 0x80000000u && (iy & 1));
+            } else {
+                ix = (int)((long long)X >> 48) - 1; iy = (int)((long long)Y >> 48) - 1;
+                const unsigned long long fx = X & FMASK, fy = Y & FMASK;
+                upx = fx > FHALF || (fx == FHALF && (ix & 1));
+                upy = fy > FHALF || (fy == FHALF && (iy & 1));
+            }
+            const int x = min(max(ix + (upx ? 1 : 0), 0), ncols1), y = min(max(iy + (upy ? 1 : 0), 0), nrows1);
+            v = (float)img[(size_t)y * stride + x];
+        }
+        out[u * 32] = v;
+    }
+}
+
+// Samples the warp-rounds [0, Q4) of the chunk described by S.slot into S.buf, round q at buf[32 q + lane].  need: bit q set when
+// round q may hold a sample outside the image (0 for windows that lie inside it); groups of four rounds without such a bit skip the test.
+template <bool FINE>
+__device__ __forceinline__ void sample_chunk(DescScratch &S, const cudaTextureObject_t tex, int Q4, unsigned need, unsigned long long mxc,
                                              unsigned long long myc, int lane, const uint8_t *__restrict__ img, int stride,
                                              int ncols1, int nrows1, int row_off)
 {
     const ulonglong2 *slot = (const ulonglong2 *)S.slot;
     float *out = S.buf + lane;
-    constexpr unsigned long long FMASK = (1ULL << 48) - 1, FHALF = 1ULL << 47;
 #pragma unroll 1
-    for (int q0 = 0; q0 < Q4; q0 += 4, slot += 4, out += 128) {
-        float4 g[4]; float A[4], B[4]; unsigned oob = 0;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const ulonglong2 e = slot[u];
-            const unsigned long long X = e.x + mxc, Y = e.y + myc;
-            int ix1, iy1;
-            if (!FINE) {
-                ix1 = (int)(X >> 32); iy1 = (int)(Y >> 32);
-                A[u] = __uint2float_rn((unsigned)X); B[u] = __uint2float_rn((unsigned)Y);
-            } else {
-                ix1 = (int)((long long)X >> 48); iy1 = (int)((long long)Y >> 48);
-                A[u] = __ull2float_rn(X & FMASK) * 1.52587890625e-05f;      // one rounding of the 48-bit fraction, then an exact 2^-16
-                B[u] = __ull2float_rn(Y & FMASK) * 1.52587890625e-05f;
-            }
-            g[u] = tex2Dgather<float4>(tex, __int2float_rn(ix1), __int2float_rn(iy1), 0);
-            if (CHECK && !((unsigned)(ix1 - 1) < (unsigned)ncols1 && (unsigned)(iy1 - 1 - row_off) < (unsigned)nrows1)) oob |= 1u << u;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            float v = bilinear_scaled(g[u], A[u], B[u]);
-            if (CHECK && (oob >> u & 1)) {
-                // outside the image: the CPU takes the clamped nearest pixel, cvRound(pixel) = ties to even
-                const ulonglong2 e = slot[u];
-                const unsigned long long X = e.x + mxc, Y = e.y + myc;
-                int ix, iy; bool upx, upy;
-                if (!FINE) {
-                    ix = (int)(X >> 32) - 1; iy = (int)(Y >> 32) - 1 - row_off;
-                    const unsigned fx = (unsigned)X, fy = (unsigned)Y;
-                    upx = fx > 0x80000000u || (fx == 0x80000000u && (ix & 1));
-                    upy = fy > 0x80000000u || (fy == 0x80000000u && (iy & 1));
-                } else {
-                    ix = (int)((long long)X >> 48) - 1; iy = (int)((long long)Y >> 48) - 1 - row_off;
-                    const unsigned long long fx = X & FMASK, fy = Y & FMASK;
-                    upx = fx > FHALF || (fx == FHALF && (ix & 1));
-                    upy = fy > FHALF || (fy == FHALF && (iy & 1));
-                }
-                const int x = min(max(ix + (upx ? 1 : 0), 0), ncols1), y = min(max(iy + (upy ? 1 : 0), 0), nrows1);
-                v = (float)img[(size_t)y * stride + x];
-            }
-            out[u * 32] = v;
-        }
+    for (int q0 = 0; q0 < Q4; q0 += 4, slot += 4, out += 128, need >>= 4) {
+        if (need & 15u) sample_rounds<true, FINE>(slot, out, tex, mxc, myc, img, stride, ncols1, nrows1, row_off);
+        else sample_rounds<false, FINE>(slot, out, tex, mxc, myc, img, stride, ncols1, nrows1, row_off);
     }
+}
+
+// The window of one keypoint -> S.patch.  false: a row start is not a multiple of one fixed-point unit (FINE = false: the caller
+// retries in 16.48; FINE = true: the reference kernel's).  cU / sU: |cos_dir|, |sin_dir| in fixed-point units.
+template <bool FINE>
+__device__ bool window_to_patch(DescScratch &S, const cudaTextureObject_t tex, int lane, int win, float cx, float cy,
+                                                float sin_dir, float cos_dir, unsigned long long cU, unsigned long long sU, bool interior,
+                                                const uint8_t *__restrict__ img, int stride, int ncols1, int nrows1, int row_off)
+{
+    constexpr int FB = FINE ? 48 : 32;
+    const float tiny = FINE ? 2.98023223876953125e-08f : 0.001953125f;        // row starts must be 0 or at least this (ulp >= one unit)
+    const bool xneg = cos_dir < 0.f;            // x decreases along a row
+    const bool yneg = sin_dir > 0.f;            // pixel_y -= sin_dir
+    const unsigned long long mxc = (unsigned long long)(xneg ? 31 - lane : lane) * cU;
+    const unsigned long long myc = (unsigned long long)(yneg ? 31 - lane : lane) * sU;
+    const float win_offset = -(float)(win - 1) / 2;
+    float chain_x = cx + win_offset * cos_dir + win_offset * sin_dir;      // start_x / start_y of the next unsampled row
+    float chain_y = cy - win_offset * sin_dir + win_offset * cos_dir;
+    const int kpr = (win + 31) >> 5;            // warp-rounds per window row; a row occupies 32 * kpr floats of S.buf
+    const int R = DESC_SLOTS / kpr;             // rows per chunk
+    const int kinv = (65536 + kpr - 1) / kpr;   // (q * kinv) >> 16 == q / kpr for q < 32, kpr <= 24
+    AreaFold F;
+    F.init(S, win, lane);
+    for (int r0 = 0; r0 < win && !F.done(); r0 += R) {
+        const int Rc = min(R, win - r0), Q = Rc * kpr;
+        // ---- slot table: lane q owns warp-round q = (row r0 + q / kpr, columns 32 * (q % kpr) ...); lanes >= Q repeat round Q - 1
+        unsigned need = 0;
+        {
+            const int q = min(lane, Q - 1);
+            const int myrow = (q * kinv) >> 16, myk = q - myrow * kpr;
+            float cap_x = 1.f, cap_y = 1.f;
+            for (int i = 0; i < Rc; i++) {       // the CPU's float chain, advanced by every lane alike
+                if (i == myrow) { cap_x = chain_x; cap_y = chain_y; }
+                chain_x += sin_dir; chain_y += cos_dir;
+            }
+            const bool ok = (cap_x == 0.f || fabsf(cap_x) >= tiny) && (cap_y == 0.f || fabsf(cap_y) >= tiny);
+            if (!__all_sync(0xffffffffu, ok)) return false;
+            long long X0, Y0;                    // exact: the row start is a multiple of one unit
+            if (FINE) {
+                X0 = (long long)((double)cap_x * 281474976710656.0); Y0 = (long long)((double)cap_y * 281474976710656.0);
+            } else {
+                const float flx = floorf(cap_x), fly = floorf(cap_y);
+                X0 = ((long long)(int)flx << 32) | (unsigned)((cap_x - flx) * 4294967296.0f);
+                Y0 = ((long long)(int)fly << 32) | (unsigned)((cap_y - fly) * 4294967296.0f);
+            }
+            const int kx = xneg ? -(32 * myk + 31) : 32 * myk, ky = yneg ? -(32 * myk + 31) : 32 * myk;
+            // + 1: tex2Dgather at (ix + 1, iy + 1) returns the footprint (ix, iy) .. (ix + 1, iy + 1); + row_off: image b of the stack
+            // (added after the shift in 16.48, whose 16 integer bits do not hold the stack's rows)
+            ulonglong2 e;
+            if (FINE) {
+                e.x = (unsigned long long)(X0 + (long long)kx * (long long)cU + (1LL << FB));
+                e.y = (unsigned long long)(Y0 + (long long)ky * (long long)sU + (1LL << FB));
+            } else {
+                e.x = (unsigned long long)(X0 + (long long)kx * (long long)(unsigned)cU + (1LL << FB));
+                e.y = (unsigned long long)(Y0 + (long long)ky * (long long)(unsigned)sU + ((long long)(1 + row_off) << FB));
+            }
+            ((ulonglong2 *)S.slot)[lane] = e;
+            if (!interior) {
+                // a round whose two end lanes have their 2x2 footprint inside the image holds no outside sample (collinear positions)
+                const unsigned long long Xb = e.x + 31 * cU, Yb = e.y + 31 * sU;
+                const int xa = (int)((long long)e.x >> FB) - 1, xb = (int)((long long)Xb >> FB) - 1;
+                const int ya = (int)((long long)e.y >> FB) - 1 - (FINE ? 0 : row_off), yb = (int)((long long)Yb >> FB) - 1 - (FINE ? 0 : row_off);
+                const bool in = (unsigned)xa < (unsigned)ncols1 && (unsigned)xb < (unsigned)ncols1 &&
+                                (unsigned)ya < (unsigned)nrows1 && (unsigned)yb < (unsigned)nrows1;
+                need = __ballot_sync(0xffffffffu, !in);
+            }
+        }
+        __syncwarp();
+        const int Q4 = (Q + 3) & ~3;
+        sample_chunk<FINE>(S, tex, Q4, need, mxc, myc, lane, img, stride, ncols1, nrows1, row_off);
+        __syncwarp();
+        // ---- fold the chunk's rows into the patch
+        F.rows(S, kpr * 32, r0, Rc, lane);
+        __syncwarp();
+    }
+    return F.done();
 }
 
 template <int MINB>
@@ -490,78 +603,26 @@ __global__ void __launch_bounds__(WK_WARPS * 32, MINB) describe_fixed_kernel(
         if (lane == 0) kp[KP_ANGLE] = descriptor_dir;
 
         const float dir_rad = descriptor_dir * (float)(M_PI / 180);
-        const float sin_dir = -(float)sin((double)dir_rad);
-        const float cos_dir = (float)cos((double)dir_rad);
-        const float win_offset = -(float)(win - 1) / 2;
+        double sd, cd;
+        sincos((double)dir_rad, &sd, &cd);
+        const float sin_dir = -(float)sd, cos_dir = (float)cd;
         const float ac = fabsf(cos_dir), as = fabsf(sin_dir);
         // both steps multiples of 2^-32 below 1 -> 32.32 positions; multiples of 2^-48 up to 1 -> 16.48 (slower conversions, rare)
         const bool ok32 = (ac == 0.f || ac >= 0.001953125f) && ac < 1.f && (as == 0.f || as >= 0.001953125f) && as < 1.f;
         const bool ok48 = (ac == 0.f || ac >= 2.98023223876953125e-08f) && (as == 0.f || as >= 2.98023223876953125e-08f) &&
                           rows < 16384 && cols < 16384;
-        const bool xneg = cos_dir < 0.f;            // x decreases along a row
-        const bool yneg = sin_dir > 0.f;            // pixel_y -= sin_dir
         const int row_off = (b - b_first) * rows;
         // every sample of the window (half diagonal + the float chain's drift, 2 px of slack) keeps its 2x2 footprint inside the image
         const float Rw = (float)(win - 1) * 0.7072f + 2.0f;
         const bool interior = cx - Rw >= 1.f && cx + Rw <= (float)(ncols1 - 1) && cy - Rw >= 1.f && cy + Rw <= (float)(nrows1 - 1);
-        const int kpr = (win + 31) >> 5;            // warp-rounds per window row; a row occupies 32 * kpr floats of S.buf
-        const int R = DESC_SLOTS / kpr;             // rows per chunk
 
         bool described = false;
-        // attempt 0: 32.32; attempt 1: 16.48, taken when the direction needs it or a row of attempt 0 started within 2^-9 of an axis
-        for (int attempt = ok32 ? 0 : 1; attempt < 2 && !described; attempt++) {
-            const bool fine = attempt == 1;
-            if (fine && !ok48) break;
-            const double fscale = fine ? 281474976710656.0 : 4294967296.0;
-            const float tiny = fine ? 2.98023223876953125e-08f : 0.001953125f;       // row starts must be 0 or at least this (ulp >= one unit)
-            const int fbits = fine ? 48 : 32;
-            const long long cF = (long long)((double)ac * fscale), sF = (long long)((double)as * fscale);   // exact
-            const unsigned long long mxc = (unsigned long long)((xneg ? 31 - lane : lane) * cF);
-            const unsigned long long myc = (unsigned long long)((yneg ? 31 - lane : lane) * sF);
-            float chain_x = cx + win_offset * cos_dir + win_offset * sin_dir;      // start_x / start_y of the next unsampled row
-            float chain_y = cy - win_offset * sin_dir + win_offset * cos_dir;
-            AreaFold F;
-            F.init(win, lane);
-            bool bad = false;
-            for (int r0 = 0; r0 < win && !F.done(); r0 += R) {
-                const int Rc = min(R, win - r0), Q = Rc * kpr;
-                // ---- slot table: lane q owns warp-round q = (row r0 + q / kpr, columns 32 * (q % kpr) ...); lanes >= Q repeat round Q - 1
-                {
-                    const int q = min(lane, Q - 1);
-                    const int myrow = q / kpr, myk = q - myrow * kpr;
-                    float cap_x = 1.f, cap_y = 1.f;
-                    for (int i = 0; i < Rc; i++) {       // the CPU's float chain, advanced by every lane alike
-                        if (i == myrow) { cap_x = chain_x; cap_y = chain_y; }
-                        chain_x += sin_dir; chain_y += cos_dir;
-                    }
-                    const bool ok = (cap_x == 0.f || fabsf(cap_x) >= tiny) && (cap_y == 0.f || fabsf(cap_y) >= tiny);
-                    if (!__all_sync(0xffffffffu, ok)) { bad = true; break; }
-                    const long long X0 = (long long)((double)cap_x * fscale);           // exact: multiples of one unit
-                    const long long Y0 = (long long)((double)cap_y * fscale);
-                    const long long kx = xneg ? -(long long)(32 * myk + 31) : (long long)(32 * myk);
-                    const long long ky = yneg ? -(long long)(32 * myk + 31) : (long long)(32 * myk);
-                    // + 1: tex2Dgather at (ix + 1, iy + 1) returns the footprint (ix, iy) .. (ix + 1, iy + 1); + row_off: image b of the stack
-                    ulonglong2 e;
-                    e.x = (unsigned long long)(X0 + kx * cF + (1LL << fbits));
-                    e.y = (unsigned long long)(Y0 + ky * sF + ((long long)(1 + row_off) << fbits));
-                    ((ulonglong2 *)S.slot)[lane] = e;
-                }
-                __syncwarp();
-                const int Q4 = (Q + 3) & ~3;
-                if (!fine) {
-                    if (interior) sample_chunk<false, false>(S, tex, Q4, mxc, myc, lane, img, stride, ncols1, nrows1, row_off);
-                    else sample_chunk<true, false>(S, tex, Q4, mxc, myc, lane, img, stride, ncols1, nrows1, row_off);
-                } else {
-                    if (interior) sample_chunk<false, true>(S, tex, Q4, mxc, myc, lane, img, stride, ncols1, nrows1, row_off);
-                    else sample_chunk<true, true>(S, tex, Q4, mxc, myc, lane, img, stride, ncols1, nrows1, row_off);
-                }
-                __syncwarp();
-                // ---- fold the chunk's rows into the patch
-                F.rows(S.buf, kpr * 32, r0, Rc, S.patch, lane);
-                __syncwarp();
-            }
-            described = !bad && F.done();
-        }
+        if (ok32)
+            described = window_to_patch<false>(S, tex, lane, win, cx, cy, sin_dir, cos_dir, (unsigned long long)(unsigned)(ac * 4294967296.0f),
+                                               (unsigned long long)(unsigned)(as * 4294967296.0f), interior, img, stride, ncols1, nrows1, row_off);
+        if (!described && ok48)      // the direction needs the finer unit, or a row of the first attempt started within 2^-9 of an axis
+            described = window_to_patch<true>(S, tex, lane, win, cx, cy, sin_dir, cos_dir, (unsigned long long)((double)ac * 281474976710656.0),
+                                              (unsigned long long)((double)as * 281474976710656.0), interior, img, stride, ncols1, nrows1, row_off);
         if (!described) {                            // hand over to the reference kernel (it repeats the orientation)
             if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = item;
             continue;

@@ -501,14 +501,15 @@ int vfsms_tiles_download(vfsms_ctx *ctx, int first, int n, uint8_t *out)
 
 const uint8_t *vfsms_tiles_ptr(vfsms_ctx *ctx) { return ctx ? ctx->tiles.as<uint8_t>() : nullptr; }
 
-int vfsms_tiles_align(vfsms_ctx *ctx, int first, int n_pairs, int direction, int roi_len, const vfsms_surf_params *params, float ratio,
-                      int offset_evaluate, vfsms_pair_result *results)
+int vfsms_tiles_align_strided(vfsms_ctx *ctx, int first, int n_pairs, int pair_step, int direction, int roi_len,
+                              const vfsms_surf_params *params, float ratio, int offset_evaluate, vfsms_pair_result *results)
 {
     int rc;
-    if ((rc = tiles_range_ok(ctx, first, n_pairs + 1, "tiles_align"))) return rc;
+    if (pair_step < 1 || n_pairs < 1) { vfsms_set_error("tiles_align: bad arguments"); return VFSMS_E_ARG; }
+    if ((rc = tiles_range_ok(ctx, first, (n_pairs - 1) * pair_step + 2, "tiles_align"))) return rc;
     const int H = ctx->tiles_rows, W = ctx->tiles_cols;
     const int edge = (direction == 1 || direction == 3) ? H : W;
-    if (!params || !results || n_pairs < 1 || direction < 1 || direction > 4 || roi_len < 1 || roi_len > edge) {
+    if (!params || !results || direction < 1 || direction > 4 || roi_len < 1 || roi_len > edge) {
         vfsms_set_error("tiles_align: bad arguments"); return VFSMS_E_ARG;
     }
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -520,7 +521,13 @@ int vfsms_tiles_align(vfsms_ctx *ctx, int first, int n_pairs, int direction, int
     else if (direction == 2) { rows = H; cols = roi_len; A += W - roi_len; }                      // A right strip, B left strip
     else if (direction == 3) { rows = roi_len; cols = W; B += (int64_t)(H - roi_len) * W; }       // A top strip, B bottom strip
     else { rows = H; cols = roi_len; B += W - roi_len; }                                          // A left strip, B right strip
-    return align_dev_regrow(ctx, A, B, n_pairs, rows, cols, W, img, params, ratio, offset_evaluate, results, ctx->stream);
+    return align_dev_regrow(ctx, A, B, n_pairs, rows, cols, W, img * pair_step, params, ratio, offset_evaluate, results, ctx->stream);
+}
+
+int vfsms_tiles_align(vfsms_ctx *ctx, int first, int n_pairs, int direction, int roi_len, const vfsms_surf_params *params, float ratio,
+                      int offset_evaluate, vfsms_pair_result *results)
+{
+    return vfsms_tiles_align_strided(ctx, first, n_pairs, 1, direction, roi_len, params, ratio, offset_evaluate, results);
 }
 
 int vfsms_match_batch_dev(vfsms_ctx *ctx, const float *desc_a_dev, const int32_t *n_a_dev, const float *desc_b_dev,

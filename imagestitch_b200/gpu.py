@@ -257,6 +257,22 @@ def phase_correlate(roi_a, roi_b, device=0):
     return (float(out[0]), float(out[1])), float(out[2])
 
 
+def phase_correlate_dev(roi_a, roi_b, out, stream=None):
+    """phase_correlate on device-resident ROIs (torch uint8 CUDA tensors [rows, cols], equal row stride); out: float64 CUDA tensor
+    of 3 elements receiving (shift_x, shift_y, response).  Asynchronous on `stream` (default: torch's current stream)."""
+    import torch
+    L = _lib.load()
+    dev = roi_a.device.index or 0
+    ctx = _lib.context(dev)
+    assert roi_a.is_cuda and roi_b.is_cuda and roi_a.dtype == torch.uint8 and roi_a.shape == roi_b.shape and roi_a.dim() == 2
+    assert roi_a.stride(1) == 1 and roi_b.stride(1) == 1 and roi_a.stride(0) == roi_b.stride(0)
+    assert out.is_cuda and out.dtype == torch.float64 and out.numel() >= 3
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    check(L.vfsms_phase_correlate_dev(ctx, ctypes.c_void_p(roi_a.data_ptr()), ctypes.c_void_p(roi_b.data_ptr()), roi_a.shape[0],
+                                      roi_a.shape[1], roi_a.stride(0), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(st.cuda_stream)),
+          "vfsms_phase_correlate_dev")
+
+
 def overlap_sums(roi_a, roi_b, shifts, device=0):
     """Integer sums (n, Sa, Sb, Sab, Saa, Sbb) over the pixels two ROIs share under each candidate shift (dRow, dCol) --
     the scoring step of the wrap-aware phase mode (phase_wrap.resolve).  -> int64 [n, 6]."""
@@ -562,13 +578,14 @@ def tiles_download(first, n, rows, cols, device=0):
     return out
 
 
-def tiles_align(first, n_pairs, direction, roi_len, params=None, ratio=0.75, offset_evaluate=3, device=0):
-    """Candidate (direction, ROI length) of the incremental search for pairs (first+p, first+p+1), ROIs read in place
-    from the tile stack.  -> structured array like align_batch."""
+def tiles_align(first, n_pairs, direction, roi_len, params=None, ratio=0.75, offset_evaluate=3, device=0, step=1):
+    """Candidate (direction, ROI length) of the incremental search for the pairs (first + p * step, first + p * step + 1), p < n_pairs,
+    ROIs read in place from the tile stack.  -> structured array like align_batch."""
     p = params if params is not None else surf_params()
     res = np.zeros(n_pairs, PAIR_RESULT_DTYPE)
-    check(_lib.load().vfsms_tiles_align(_lib.context(device), int(first), int(n_pairs), int(direction), int(roi_len), ctypes.byref(p),
-                                        ctypes.c_float(ratio), int(offset_evaluate), res.ctypes.data_as(ctypes.c_void_p)), "vfsms_tiles_align")
+    check(_lib.load().vfsms_tiles_align_strided(_lib.context(device), int(first), int(n_pairs), int(step), int(direction), int(roi_len),
+                                                ctypes.byref(p), ctypes.c_float(ratio), int(offset_evaluate),
+                                                res.ctypes.data_as(ctypes.c_void_p)), "vfsms_tiles_align_strided")
     return res
 
 

@@ -117,6 +117,146 @@ def align_sequence_sharded(evaluate, n_pairs, direction, direct_incre, roi_ratio
     return replay(full, evaluate, direction, direct_incre, roi_ratio)
 
 
+# ---------------------------------------------------------------- batched variant: tiles stay on their owner's GPU
+# evaluate_shard() above asks for one candidate at a time -- one device call per (pair, i, direction), the latency-bound shape.
+# Here the unit of device work is a BATCH: batch_evaluate(pairs, i, direction) -> int32 [len(pairs), 4] evaluates the same
+# candidate for a list of pairs in one fused call (vfsms_tiles_align on the rank's device-resident tiles).  A shard is walked in
+# ROUNDS: the sequential search is simulated over the table filled so far, every pair stops at its first unevaluated candidate,
+# and all requests of a round are grouped by (i, direction).  Pairs behind an unresolved pair continue with the last known
+# direction -- a guess: a wrong guess only costs evaluations, the table holds pure functions of (pair, i, direction).
+# Nobody but the owner can evaluate a pair (the tiles never leave its GPU), so the replay is a loop as well: rank 0 replays, the
+# candidates it misses (a shard's first pairs, when the true carried direction differs from the shard's assumption) go back to
+# their owners as one request list, the answers are gathered again.  Collectives: all_gather of the tables (KBs) + per extra
+# round one broadcast of the request list and one all_gather of the answers.
+
+
+def _missing_candidates(table, start_pair, direction, direct_incre, roi_ratio):
+    """Sequential walk over `table` (pairs start_pair ...): -> (results, requests, end_direction).  results[k] is None for a pair
+    whose search stops at an unevaluated candidate; requests = [(pair, i, direction)] -- that candidate, one per such pair."""
+    results, requests = [], []
+    d = direction
+    for k in range(table.shape[0]):
+        ini = d
+        local = ini
+        found = None
+        pending = False
+        for i in range(1, max_i(roi_ratio)):
+            while True:
+                st = table[k, i - 1, local - 1, 0]
+                if st == UNEVALUATED:
+                    requests.append((start_pair + k, i, local)); pending = True
+                    break
+                if st:
+                    found = (True, i, local, (int(table[k, i - 1, local - 1, 1]), int(table[k, i - 1, local - 1, 2])))
+                    break
+                local = direction_increase(local, direct_incre)
+                if local == ini:
+                    break
+            if found or pending:
+                break
+        if pending:
+            results.append(None)
+            known = np.argwhere(table[k, :, :, 0] == 1)          # the request of the pairs behind it: assume this pair ends where the
+            if len(known):                                        # table already holds a success (smallest i, then direction)
+                d = int(known[0][1]) + 1
+        elif found:
+            results.append(found); d = found[2]
+        else:
+            results.append((False, 0, ini, (0, 0)))
+    return results, requests, d
+
+
+def _run_requests(batch_evaluate, table, start_pair, requests):
+    groups = {}
+    for pair, i, d in requests:
+        groups.setdefault((i, d), []).append(pair)
+    for (i, d), pairs in sorted(groups.items()):
+        res = np.asarray(batch_evaluate(pairs, i, d), np.int32).reshape(len(pairs), 4)
+        for pair, r in zip(pairs, res):
+            table[pair - start_pair, i - 1, d - 1] = r
+    return len(groups)
+
+
+def evaluate_shard_batched(batch_evaluate, start, stop, direction, direct_incre, roi_ratio, probe_step=6):
+    """Rounds of batched candidate evaluations over pairs [start, stop).  -> (table int32 [stop-start, n_i, 4, 4], device calls).
+
+    A shooting path keeps its direction for long runs, but the shard does not know it (walking blindly from `direction` tests
+    every direction on every pair: 4 x the work on a serpentine).  So, before the rounds: every probe_step-th pair is evaluated in
+    all four directions (i = 1), every other pair once, in the direction in which its nearest probe succeeded.  The rounds then
+    only fill in what the true search order also visits (the turns); speculative entries never change a result."""
+    n_i = max_i(roi_ratio) - 1
+    n = stop - start
+    table = np.full((n, n_i, 4, 4), UNEVALUATED, np.int32)
+    calls = 0
+    if n > 2 and probe_step > 0 and direct_incre != 0:
+        probes = list(range(start, stop, probe_step))
+        calls += _run_requests(batch_evaluate, table, start, [(p, 1, d) for p in probes for d in (1, 2, 3, 4)])
+        hit = {p: [d for d in (1, 2, 3, 4) if table[p - start, 0, d - 1, 0] == 1] for p in probes}
+        guesses = []
+        for k in range(start, stop):
+            if k in hit:
+                continue
+            near = sorted((p for p in probes if hit[p]), key=lambda p: (abs(p - k), p > k))
+            if near:
+                guesses.append((k, 1, hit[near[0]][0]))
+        if guesses:
+            calls += _run_requests(batch_evaluate, table, start, guesses)
+    while n > 0:
+        _, requests, _ = _missing_candidates(table, start, direction, direct_incre, roi_ratio)
+        if not requests:
+            break
+        calls += _run_requests(batch_evaluate, table, start, requests)
+    return table, calls
+
+
+def align_sequence_sharded_batched(batch_evaluate, n_pairs, direction, direct_incre, roi_ratio, rank, world_size, device=None,
+                                   probe_step=6):
+    """Contiguous pair shards, batched rounds per shard, gather, replay on the gathered table with the misses sent back to their
+    owners.  Every rank returns (results, stats): results as replay(); stats = {"device_calls", "extra_rounds", "on_demand"}."""
+    import torch
+    import torch.distributed as dist
+    ranges = partition_pairs(n_pairs, world_size)
+    s, e = ranges[rank]
+    local, calls = evaluate_shard_batched(batch_evaluate, s, e, direction, direct_incre, roi_ratio, probe_step)
+    extra_rounds = on_demand = 0
+    while True:
+        full = gather_tables(local, ranges, rank, world_size, device) if world_size > 1 else local
+        # every rank replays the same gathered table, so the request list needs no broadcast
+        results, requests, _ = _missing_candidates(full, 0, direction, direct_incre, roi_ratio)
+        if not requests:
+            break
+        extra_rounds += 1
+        on_demand += len(requests)
+        mine = [(p, i, d) for p, i, d in requests if s <= p < e]
+        if mine:
+            calls += _run_requests(batch_evaluate, local, s, mine)
+    return results, {"device_calls": calls, "extra_rounds": extra_rounds, "on_demand": on_demand}
+
+
+def tiles_batch_evaluator(first_tile, roi_lens, params=None, ratio=0.75, offset_evaluate=3, device=0):
+    """batch_evaluate(pairs, i, direction) on the context's device-resident tile stack: stack slot `pair - first_tile` holds tile
+    `pair`.  roi_lens(i, direction) -> ROI length in pixels (int(i * roiRatio * extent), ImageUtility.py:66-101).  Runs of
+    equally spaced pairs become one vfsms_tiles_align_strided call each."""
+    from . import gpu
+
+    def batch_evaluate(pairs, i, direction):
+        out = np.zeros((len(pairs), 4), np.int32)
+        k = 0
+        while k < len(pairs):                      # maximal runs of equally spaced pairs: one fused call each
+            step = pairs[k + 1] - pairs[k] if k + 1 < len(pairs) else 1
+            j = k
+            while step > 0 and j + 1 < len(pairs) and pairs[j + 1] - pairs[j] == step:
+                j += 1
+            if step <= 0:
+                step = 1
+            r = gpu.tiles_align(pairs[k] - first_tile, j - k + 1, direction, roi_lens(i, direction), params=params, ratio=ratio,
+                                offset_evaluate=offset_evaluate, device=device, step=step)
+            out[k:j + 1, 0] = r["status"]; out[k:j + 1, 1] = r["d_row"]; out[k:j + 1, 2] = r["d_col"]; out[k:j + 1, 3] = r["votes"]
+            k = j + 1
+        return out
+    return batch_evaluate
+
+
 def roi_origin_back(offset, shape_a, shape_b, i, direction, roi_ratio):
     """Add the ROI origin back (Stitcher.py:353-360)."""
     off = [int(offset[0]), int(offset[1])]
@@ -162,50 +302,49 @@ def gpu_evaluator(tiles, params=None, ratio=0.75, offset_evaluate=3, roi_ratio=0
 # gpu.mosaic_band + torch.distributed on GPUs, a NumPy renderer + gloo in the CPU tests.
 
 def rectify_offsets(origin_offsets, tile_shapes):
-    """Global offset rectification, Stitcher.getStitchByOffset's integer bookkeeping (Stitcher.py:386-431).
-    origin_offsets: [[dRow, dCol], ...] per tile, entry 0 = [0, 0]; tile_shapes: [(rows, cols), ...].
-    -> (origins int32 [n, 2], rois int32 [n, 4] (r0, c0, r1, c1; row 0 unused), (canvas_rows, canvas_cols))."""
+    """Global offset rectification: the integer bookkeeping at the head of Stitcher.getStitchByOffset (Stitcher.py:386-431) in
+    closed form.  origin_offsets: [[dRow, dCol], ...] per tile, entry 0 = [0, 0]; tile_shapes: [(rows, cols), ...].
+    -> (origins int32 [n, 2], rois int32 [n, 4] (r0, c0, r1, c1; row 0 unused), (canvas_rows, canvas_cols)).
+
+    Per axis, with P_i the running sum of the pair offsets: the reference shifts everything placed so far whenever the running
+    position would become <= 0, which amounts to  origin_i = P_i - min(0, min_j P_j).  Its `range` bookkeeping -- the extent
+    [lo_i, hi_i] of the canvas "as of tile i", later shifted like the origins -- is, in final coordinates,
+        lo_i = min(0, min_{j<=i} P_j) - min(0, min_j P_j),      hi_i = max_{j<=i}(P_j + extent_j) - min(0, min_j P_j),
+    except that a tile whose running position is <= 0 re-bases the axis: hi_i then only adds |P_i| to the previous extent
+    (the tile's own size is NOT taken into account there -- a quirk of the reference kept as is).  The ROI of tile i is its
+    rectangle clipped to the extent as of tile i - 1 (Stitcher.py:452-461).  The literal loop is restated in
+    oracle/blend_oracle.py and compared with this on random and serpentine sequences (tests/test_host_cpu.py)."""
     n = len(origin_offsets)
-    off = [[int(o[0]), int(o[1])] for o in origin_offsets]
-    range_x = [[0, 0] for _ in range(n)]
-    range_y = [[0, 0] for _ in range(n)]
-    result_row, result_col = int(tile_shapes[0][0]), int(tile_shapes[0][1])
-    range_x[0][1], range_y[0][1] = result_row, result_col
-    dx_sum = dy_sum = 0
-    for i in range(1, n):
-        h, w = int(tile_shapes[i][0]), int(tile_shapes[i][1])
-        dx_sum += off[i][0]
-        dy_sum += off[i][1]
-        if dx_sum <= 0:
-            for j in range(i):
-                off[j][0] += abs(dx_sum)
-                range_x[j][0] += abs(dx_sum)
-                range_x[j][1] += abs(dx_sum)
-            result_row += abs(dx_sum)
-            range_x[i][1] = result_row
-            dx_sum = range_x[i][0] = off[i][0] = 0
-        else:
-            off[i][0] = dx_sum
-            result_row = max(result_row, dx_sum + h)
-            range_x[i][1] = result_row
-        if dy_sum <= 0:
-            for j in range(i):
-                off[j][1] += abs(dy_sum)
-                range_y[j][0] += abs(dy_sum)
-                range_y[j][1] += abs(dy_sum)
-            result_col += abs(dy_sum)
-            range_y[i][1] = result_col
-            dy_sum = range_y[i][0] = off[i][1] = 0
-        else:
-            off[i][1] = dy_sum
-            result_col = max(result_col, dy_sum + w)
-            range_y[i][1] = result_col
+    off = np.asarray([[int(o[0]), int(o[1])] for o in origin_offsets], np.int64).reshape(n, 2)
+    ext = np.asarray([[int(t[0]), int(t[1])] for t in tile_shapes], np.int64).reshape(n, 2)
+    origins = np.zeros((n, 2), np.int64)
+    lo = np.zeros((n, 2), np.int64)
+    hi = np.zeros((n, 2), np.int64)
+    size = [0, 0]
+    for ax in range(2):
+        # walk once in the reference's own frame (origin re-based at every non-positive running position) ...
+        pos = 0                      # running position of tile i in the current frame
+        shift = 0                    # total shift applied to the frame so far
+        extent = int(ext[0, ax])     # canvas extent along this axis
+        frame_org = np.zeros(n, np.int64); frame_lo = np.zeros(n, np.int64); frame_hi = np.zeros(n, np.int64); at = np.zeros(n, np.int64)
+        frame_hi[0] = extent
+        for i in range(1, n):
+            pos += int(off[i, ax])
+            if pos <= 0:
+                shift += -pos; extent += -pos; pos = 0
+            else:
+                extent = max(extent, pos + int(ext[i, ax]))
+            frame_org[i] = pos; frame_lo[i] = 0; frame_hi[i] = extent; at[i] = shift
+        # ... then express every record in the final frame: whatever was recorded at total shift `at[i]` moves by shift - at[i]
+        origins[:, ax] = frame_org + (shift - at)
+        lo[:, ax] = frame_lo + (shift - at)
+        hi[:, ax] = frame_hi + (shift - at)
+        size[ax] = extent
     rois = np.zeros((n, 4), np.int32)
     for i in range(1, n):
-        h, w = int(tile_shapes[i][0]), int(tile_shapes[i][1])
-        rois[i] = (max(off[i][0], range_x[i - 1][0]), max(off[i][1], range_y[i - 1][0]),
-                   min(off[i][0] + h, range_x[i - 1][1]), min(off[i][1] + w, range_y[i - 1][1]))
-    return np.asarray(off, np.int32).reshape(n, 2), rois, (result_row, result_col)
+        rois[i] = (max(origins[i, 0], lo[i - 1, 0]), max(origins[i, 1], lo[i - 1, 1]),
+                   min(origins[i, 0] + ext[i, 0], hi[i - 1, 0]), min(origins[i, 1] + ext[i, 1], hi[i - 1, 1]))
+    return origins.astype(np.int32), rois, (int(size[0]), int(size[1]))
 
 
 def _intersect(a, b):

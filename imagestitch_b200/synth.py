@@ -137,3 +137,29 @@ def pair_batch_torch(seed, n_pairs, size, overlap, device, noise=2.0, canvas_hw=
                 t = t + noise * torch.randn(t.shape, generator=g, device=device)
             dst[p] = (t + 0.5).clamp(0, 255).to(torch.uint8)
     return A, B, offs
+
+
+def sequence_torch(seed, n_rows, n_cols, size, overlap, device, first=0, count=None, noise=2.0):
+    """Tiles first .. first + count - 1 of the serpentine sequence (n_rows x n_cols, shooting order) cropped from ONE synthetic canvas
+    evaluated on `device`: every rank of a sharded run generates the same canvas and crops its own run of tiles.
+    Returns (tiles [count, size, size] u8 on device, true pair offsets of the WHOLE sequence [n - 1, 2] (dRow, dCol) numpy)."""
+    import torch
+    origins, offsets = serpentine_origins(n_rows, n_cols, size, overlap, seed)
+    n = len(origins)
+    count = n - first if count is None else count
+    H = int(origins[:, 0].max()) + size + 8
+    W = int(origins[:, 1].max()) + size + 8
+    base = canvas_torch(seed, H, W, device)
+    vig = torch.from_numpy(_vignette(size, size)).to(device)
+    g = torch.Generator(device=device)
+    tiles = torch.empty((count, size, size), dtype=torch.uint8, device=device)
+    for j in range(count):
+        k = first + j
+        r, c = int(origins[k, 0]), int(origins[k, 1])
+        t = base[r:r + size, c:c + size] * vig
+        if noise > 0:
+            g.manual_seed(seed + 1000 + k)
+            t = t + noise * torch.randn(t.shape, generator=g, device=device)
+        tiles[j] = (t + 0.5).clamp(0, 255).to(torch.uint8)
+    del base
+    return tiles, offsets

@@ -300,6 +300,10 @@ const uint8_t *vfsms_tiles_ptr(vfsms_ctx *ctx);                      /* device a
  * cuts them (ImageUtility.py:66-101), read in place; results as vfsms_align_batch_host (ROI coordinates, host memory). */
 int vfsms_tiles_align(vfsms_ctx *ctx, int first, int n_pairs, int direction, int roi_len, const vfsms_surf_params *params,
                       float ratio, int offset_evaluate, vfsms_pair_result *results);
+/* The same for every pair_step-th pair: pairs (first + p * pair_step, first + p * pair_step + 1), p < n_pairs -- one fused call for
+ * the probe pairs with which a sharded run guesses the shooting direction before it walks its pairs (sharding.py). */
+int vfsms_tiles_align_strided(vfsms_ctx *ctx, int first, int n_pairs, int pair_step, int direction, int roi_len,
+                              const vfsms_surf_params *params, float ratio, int offset_evaluate, vfsms_pair_result *results);
 /* vfsms_mosaic_host with tiles first .. first + n_tiles - 1 of the stack (gray). */
 int vfsms_tiles_mosaic(vfsms_ctx *ctx, int first, int n_tiles, const int32_t *tile_origin, const int32_t *roi_rect,
                        const int32_t *pair_offset, int method, int canvas_rows, int canvas_cols, uint8_t *canvas_out);

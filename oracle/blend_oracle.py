@@ -11,6 +11,7 @@ What it follows (reference file:line, tree /root/reference):
   corner_weights        ImageFusion.getWeightsMatrix            ImageFusion.py:43-190
   fuse_fade / fuse_trig                                         ImageFusion.py:192-244, :246-293
   rectify               Stitcher.getStitchByOffset bookkeeping  Stitcher.py:386-431 (closed form, see below)
+  rectify_literal       the same, loop by loop                  Stitcher.py:386-431
   mosaic                Stitcher.getStitchByOffset paste loop   Stitcher.py:433-486
 
 Pinned (tests/test_oracle_pins.py) against tests/golden/blend_cases.npz and mosaic_case.npz, which were produced by the
@@ -178,6 +179,55 @@ def rectify(pair_offsets, tile_shape):
     rois[1:, 0:2] = np.maximum(origins[1:], lo[:-1])
     rois[1:, 2:4] = np.minimum(origins[1:] + size, hi[:-1])
     return origins, rois, (int(hi[-1, 0]), int(hi[-1, 1]))
+
+
+def rectify_literal(origin_offsets, tile_shapes):
+    """Global offset rectification, Stitcher.getStitchByOffset's integer bookkeeping, restated loop by loop (Stitcher.py:386-431:
+    the running sums, the O(n^2) shifting of everything placed so far, the per-tile `range` records) -- the checker of the
+    product's single-pass form (imagestitch_b200.sharding.rectify_offsets) and of the closed form `rectify` above.
+    origin_offsets: [[dRow, dCol], ...] per tile, entry 0 = [0, 0]; tile_shapes: [(rows, cols), ...].
+    -> (origins int32 [n, 2], rois int32 [n, 4] (r0, c0, r1, c1; row 0 unused), (canvas_rows, canvas_cols))."""
+    n = len(origin_offsets)
+    off = [[int(o[0]), int(o[1])] for o in origin_offsets]
+    range_x = [[0, 0] for _ in range(n)]
+    range_y = [[0, 0] for _ in range(n)]
+    result_row, result_col = int(tile_shapes[0][0]), int(tile_shapes[0][1])
+    range_x[0][1], range_y[0][1] = result_row, result_col
+    dx_sum = dy_sum = 0
+    for i in range(1, n):
+        h, w = int(tile_shapes[i][0]), int(tile_shapes[i][1])
+        dx_sum += off[i][0]
+        dy_sum += off[i][1]
+        if dx_sum <= 0:
+            for j in range(i):
+                off[j][0] += abs(dx_sum)
+                range_x[j][0] += abs(dx_sum)
+                range_x[j][1] += abs(dx_sum)
+            result_row += abs(dx_sum)
+            range_x[i][1] = result_row
+            dx_sum = range_x[i][0] = off[i][0] = 0
+        else:
+            off[i][0] = dx_sum
+            result_row = max(result_row, dx_sum + h)
+            range_x[i][1] = result_row
+        if dy_sum <= 0:
+            for j in range(i):
+                off[j][1] += abs(dy_sum)
+                range_y[j][0] += abs(dy_sum)
+                range_y[j][1] += abs(dy_sum)
+            result_col += abs(dy_sum)
+            range_y[i][1] = result_col
+            dy_sum = range_y[i][0] = off[i][1] = 0
+        else:
+            off[i][1] = dy_sum
+            result_col = max(result_col, dy_sum + w)
+            range_y[i][1] = result_col
+    rois = np.zeros((n, 4), np.int32)
+    for i in range(1, n):
+        h, w = int(tile_shapes[i][0]), int(tile_shapes[i][1])
+        rois[i] = (max(off[i][0], range_x[i - 1][0]), max(off[i][1], range_y[i - 1][0]),
+                   min(off[i][0] + h, range_x[i - 1][1]), min(off[i][1] + w, range_y[i - 1][1]))
+    return np.asarray(off, np.int32).reshape(n, 2), rois, (result_row, result_col)
 
 
 def paste_blend(canvas, tile, origin, roi, pair_offset, method, color, fuse):

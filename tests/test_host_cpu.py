@@ -161,6 +161,74 @@ def test_sharding_two_ranks_gloo(tmp_path):
     assert "GLOO_OK 19" in r.stdout
 
 
+def test_sharding_batched_rounds_equal_sequential():
+    """evaluate_shard_batched fills, in rounds of grouped requests, a table on which the sequential walk needs nothing else."""
+    from imagestitch_b200 import sharding as sh
+    true_dir = np.array([1] * 9 + [2] + [3] * 9 + [2] + [1] * 9 + [2] + [3] * 4)
+    n = len(true_dir)
+
+    def evaluate(pair, i, d):
+        ok = (d == true_dir[pair]) and (i >= 1 + (pair % 7 == 3))
+        spurious = (pair % 11 == 5 and d == 4 and i == 1)
+        return int(ok or spurious), 100 + pair, -pair, 9
+    calls = []
+
+    def batch_evaluate(pairs, i, d):
+        calls.append((tuple(pairs), i, d))
+        return [evaluate(p, i, d) for p in pairs]
+    for incre in (1, -1, 0):
+        seq, _ = sh.replay(sh.evaluate_shard(evaluate, 0, n, 1, incre, 0.2), evaluate, 1, incre, 0.2)
+        del calls[:]
+        table, n_calls = sh.evaluate_shard_batched(batch_evaluate, 0, n, 1, incre, 0.2)
+        out, requests, _ = sh._missing_candidates(table, 0, 1, incre, 0.2)
+        assert not requests and out == seq
+        assert n_calls == len(calls) <= 30                 # a handful of batched device calls instead of ~n single ones
+        assert all(len(set(c[0])) == len(c[0]) for c in calls)
+        on_path = int((sh.evaluate_shard(evaluate, 0, n, 1, incre, 0.2)[..., 0] != sh.UNEVALUATED).sum())
+        done = sum(len(c[0]) for c in calls)
+        assert done <= 2.2 * on_path + 8, (done, on_path)  # probes + guesses cost about as much again as the true search path
+
+
+GLOO_BATCHED_WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.environ["VFSMS_ROOT"])
+import torch.distributed as dist
+from imagestitch_b200 import sharding as sh
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+true_dir = [1] * 5 + [2] + [3] * 5 + [2] + [1] * 5 + [2] + [3] * 4          # 2 ranks: the second shard starts at a turn
+n = len(true_dir)
+ranges = sh.partition_pairs(n, world)
+lo, hi = ranges[rank]
+def evaluate(pair, i, d):
+    return int(d == true_dir[pair] and i >= 1 + (pair % 5 == 2)), 50 + pair, pair - 3, 7
+def batch_evaluate(pairs, i, d):
+    assert all(lo <= p < hi for p in pairs), (rank, pairs)          # only the owner is ever asked
+    return [evaluate(p, i, d) for p in pairs]
+seq, _ = sh.replay(sh.evaluate_shard(evaluate, 0, n, 1, 1, 0.2), evaluate, 1, 1, 0.2)
+out, stats = sh.align_sequence_sharded_batched(batch_evaluate, n, 1, 1, 0.2, rank, world)               # with direction probes
+assert out == seq, (rank, out, seq)
+out, stats = sh.align_sequence_sharded_batched(batch_evaluate, n, 1, 1, 0.2, rank, world, probe_step=0)   # blind walk from direction 1
+assert out == seq, (rank, out, seq)
+if rank == 0:
+    assert stats["extra_rounds"] >= 1 and stats["on_demand"] >= 2          # pair 11: carried direction 3, the owner assumed 1
+    print("GLOO_BATCHED_OK", len(out), stats["extra_rounds"], stats["on_demand"])
+dist.destroy_process_group()
+"""
+
+
+def test_sharding_batched_two_ranks_gloo(tmp_path):
+    """Tiles never leave their owner: misses of the replay go back to the owning rank, results equal the sequential loop."""
+    script = tmp_path / "worker_batched.py"
+    script.write_text(GLOO_BATCHED_WORKER)
+    env = dict(os.environ, VFSMS_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29543", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GLOO_BATCHED_OK 22" in r.stdout
+
+
 def test_synthetic_generator_is_seeded():
     from imagestitch_b200 import synth
     a1, b1, o1 = synth.pair(seed=9, size=256, overlap=40, direction=1)

@@ -36,7 +36,7 @@ EXPORTS = [
     "vfsms_jpeg_info", "vfsms_jpeg_luma_coefficients", "vfsms_jpeg_decode_gray_dev", "vfsms_jpeg_decode_gray_host",
     "vfsms_jpeg_component_coefficients", "vfsms_jpeg_decode_bgr_dev", "vfsms_jpeg_decode_bgr_host",
     "vfsms_tiles_reserve", "vfsms_tiles_decode_jpeg", "vfsms_tiles_upload", "vfsms_tiles_download", "vfsms_tiles_ptr",
-    "vfsms_tiles_align", "vfsms_tiles_align_strided", "vfsms_tiles_mosaic", "vfsms_set_option", "vfsms_get_option", "vfsms_option_name",
+    "vfsms_tiles_align", "vfsms_tiles_align_strided", "vfsms_tiles_align_list", "vfsms_tiles_mosaic", "vfsms_set_option", "vfsms_get_option", "vfsms_option_name",
     "vfsms_mosaic_band_host", "vfsms_overlap_sums_host", "vfsms_jpeg_encode_host", "vfsms_jpeg_encode_dev", "vfsms_jpeg_last_entropy_passes",
     "vfsms_tiles_decode_jpeg_bgr", "vfsms_tiles_upload_bgr", "vfsms_tiles_mosaic_bgr",
 ]

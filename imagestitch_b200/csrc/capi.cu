@@ -180,7 +180,7 @@ void vfsms_destroy(vfsms_ctx *ctx)
     surf_tex_destroy(ctx);
     ctx->tex_dev.release();
     SurfWorkspace &w = ctx->surf;
-    DevBuf *bufs[] = { &w.integral, &w.band_tot, &w.cand, &w.sorted, &w.kp, &w.desc, &w.descT, &w.counters, &w.prefix, &w.hist, &w.img_f32, &w.fb_list,
+    DevBuf *bufs[] = { &w.integral, &w.band_tot, &w.cand, &w.sorted, &w.kp, &w.desc, &w.descT, &w.counters, &w.prefix, &w.hist, &w.img_f32, &w.fb_list, &w.img_off_buf,
                        &ctx->match.best_idx, &ctx->match.best_dist, &ctx->match.matches, &ctx->match.n_matches,
                        &ctx->match.table_keys, &ctx->match.table_cnt, &ctx->match.table_first, &ctx->match.bf16_a,
                        &ctx->match.bf16_b, &ctx->match.cand_topk, &ctx->img_a, &ctx->img_b, &ctx->results,
@@ -522,6 +522,39 @@ int vfsms_tiles_align_strided(vfsms_ctx *ctx, int first, int n_pairs, int pair_s
     else if (direction == 3) { rows = roi_len; cols = W; B += (int64_t)(H - roi_len) * W; }       // A top strip, B bottom strip
     else { rows = H; cols = roi_len; B += W - roi_len; }                                          // A left strip, B right strip
     return align_dev_regrow(ctx, A, B, n_pairs, rows, cols, W, img * pair_step, params, ratio, offset_evaluate, results, ctx->stream);
+}
+
+int vfsms_tiles_align_list(vfsms_ctx *ctx, int n_pairs, const int32_t *first_tile, const int32_t *direction, int roi_len,
+                           const vfsms_surf_params *params, float ratio, int offset_evaluate, vfsms_pair_result *results)
+{
+    if (!ctx || !first_tile || !direction || !params || !results || n_pairs < 1) { vfsms_set_error("tiles_align_list: bad arguments"); return VFSMS_E_ARG; }
+    const int H = ctx->tiles_rows, W = ctx->tiles_cols;
+    const bool tall = direction[0] == 2 || direction[0] == 4;            // column strips (H x roi_len) vs row strips (roi_len x W)
+    const int edge = tall ? W : H;
+    if (roi_len < 1 || roi_len > edge) { vfsms_set_error("tiles_align_list: bad ROI length"); return VFSMS_E_ARG; }
+    const int64_t img = (int64_t)H * W;
+    std::vector<int64_t> off((size_t)2 * n_pairs);
+    int rc;
+    for (int p = 0; p < n_pairs; p++) {
+        const int d = direction[p];
+        if (d < 1 || d > 4 || ((d == 2 || d == 4) != tall)) { vfsms_set_error("tiles_align_list: directions of one call must share the strip shape"); return VFSMS_E_ARG; }
+        if ((rc = tiles_range_ok(ctx, first_tile[p], 2, "tiles_align_list"))) return rc;
+        int64_t a = first_tile[p] * img, b = a + img;                    // ImageUtility.py:66-101
+        if (d == 1) a += (int64_t)(H - roi_len) * W;
+        else if (d == 2) a += W - roi_len;
+        else if (d == 3) b += (int64_t)(H - roi_len) * W;
+        else b += W - roi_len;
+        off[p] = a; off[(size_t)n_pairs + p] = b;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if ((rc = ctx->surf.img_off_buf.reserve(off.size() * 8))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ctx->surf.img_off_buf.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));                         // `off` is pageable host memory
+    ctx->surf.img_off = ctx->surf.img_off_buf.as<int64_t>();
+    const uint8_t *base = ctx->tiles.as<uint8_t>();
+    rc = align_dev_regrow(ctx, base, base, n_pairs, tall ? H : roi_len, tall ? roi_len : W, W, img, params, ratio, offset_evaluate, results, ctx->stream);
+    ctx->surf.img_off = nullptr;
+    return rc;
 }
 
 int vfsms_tiles_align(vfsms_ctx *ctx, int first, int n_pairs, int direction, int roi_len, const vfsms_surf_params *params, float ratio,

@@ -117,6 +117,8 @@ struct SurfWorkspace {
     DevBuf img_f32;          // [batch][rows][pitch_f] float copy of the images * 2^-64 (texture source of the descriptor stage)
     DevBuf fb_list;          // [batch * kp_cap] int32: keypoints the fixed-point sampler hands to the reference sampler
     int pitch_f = 0;
+    DevBuf img_off_buf;      // storage of that table (vfsms_tiles_align_list)
+    const int64_t *img_off = nullptr;   // device table of per-image byte offsets from base_a for the next surf_run_batch (null: strided layout)
     int last_batch = 0;      // batch of the last surf_run_batch (the work counters sit after its per-image counters)
 };
 

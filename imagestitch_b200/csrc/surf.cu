@@ -135,8 +135,12 @@ int surf_build_plan(SurfPlan *plan, int rows, int cols, const vfsms_surf_params 
 }
 
 // ---------------------------------------------------------------- device helpers
-__device__ __forceinline__ const uint8_t *image_ptr(const uint8_t *base_a, const uint8_t *base_b, int split, int b, int64_t img_stride)
+// image b of a batch: the first `split` images lie img_stride apart from base_a, the others from base_b -- or, when the caller
+// passed a table (vfsms_tiles_align_list: arbitrary tiles of the stack, mixed strip positions), at base_a + img_off[b]
+__device__ __forceinline__ const uint8_t *image_ptr(const uint8_t *base_a, const uint8_t *base_b, int split, int b, int64_t img_stride,
+                                                    const int64_t *__restrict__ img_off = nullptr)
 {
+    if (img_off) return base_a + img_off[b];
     return b < split ? base_a + (int64_t)b * img_stride : base_b + (int64_t)(b - split) * img_stride;
 }
 
@@ -145,13 +149,14 @@ __device__ __forceinline__ const uint8_t *image_ptr(const uint8_t *base_a, const
 // sums over the band's own rows only; the band's column totals go to band_tot[b][band][cols].
 __global__ void __launch_bounds__(256) integral_band_kernel(const uint8_t *base_a, const uint8_t *base_b, int split,
                                                             int64_t img_stride, int rows, int cols, int stride,
-                                                            int32_t *integral, int32_t *band_tot, int n_bands)
+                                                            int32_t *integral, int32_t *band_tot, int n_bands,
+                                                            const int64_t *__restrict__ img_off)
 {
     extern __shared__ int32_t s_rows[];   // [INT_SUB][cols_pad]
     const int band = blockIdx.x, b = blockIdx.y;
     const int W = cols + 1;
     const int cols_pad = (min(cols, 4096) + 3) & ~3;
-    const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
+    const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride, img_off);
     int32_t *I = integral + (size_t)b * (rows + 1) * W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r0 = band * INT_BAND;
@@ -874,7 +879,7 @@ __device__ __forceinline__ int box_sum(const int32_t *__restrict__ o, int W, int
 __global__ void __launch_bounds__(DESC_THREADS) orient_describe_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
     const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
-    int batch, int kp_cap, int extended, int upright, const int *big_flag)
+    int batch, int kp_cap, int extended, int upright, const int *big_flag, const int64_t *__restrict__ img_off)
 {
     if (*big_flag == 0) return;        // no window exceeded WK_MAX_WIN (always the case for n_octaves <= 4)
     __shared__ float s_X[ORI_SAMPLES], s_Y[ORI_SAMPLES], s_ang[ORI_SAMPLES];
@@ -898,7 +903,7 @@ __global__ void __launch_bounds__(DESC_THREADS) orient_describe_kernel(
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (prefix[mid] <= item) lo = mid; else hi = mid; }
         const int b = lo, k = item - prefix[lo];
         float *kp = kp_all + ((size_t)b * kp_cap + k) * KP_STRIDE;
-        const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
+        const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride, img_off);
         const int32_t *I = integral + (size_t)b * srows * W;
         const float size = kp[KP_SIZE], cx = kp[KP_X], cy = kp[KP_Y];
         const float s = size * 1.2f / 9.0f;
@@ -1235,7 +1240,7 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
     {
     StageTimer t_int(ctx, st, VFSMS_STAGE_INTEGRAL);
     integral_band_kernel<<<dim3(n_bands, batch), 256, smem_int, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
-                                                                      ws.integral.as<int32_t>(), ws.band_tot.as<int32_t>(), n_bands);
+                                                                      ws.integral.as<int32_t>(), ws.band_tot.as<int32_t>(), n_bands, ws.img_off);
     LAUNCH_CHECK(ctx);
     if (n_bands > 1) {
         integral_fix_kernel<<<dim3(n_bands - 1, batch), 256, 0, st>>>(rows, cols, ws.integral.as<int32_t>(),
@@ -1379,7 +1384,7 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         if (n_chunks > 0 && n_chunks <= SURF_MAX_DESC_CHUNKS) {
             if ((rc = ws.img_f32.reserve((size_t)batch * rows * ws.pitch_f * 4))) return rc;
             u8_to_f32_kernel<<<dim3(std::min(ceil_div(rows * cols, 256), ctx->num_sms * 4), batch), 256, 0, st>>>(
-                base_a, base_b, split, img_stride, rows, cols, stride, ws.img_f32.as<float>(), ws.pitch_f, 5.421010862427522e-20f /* 2^-64 */);
+                base_a, base_b, split, img_stride, rows, cols, stride, ws.img_f32.as<float>(), ws.pitch_f, 5.421010862427522e-20f /* 2^-64 */, ws.img_off);
             LAUNCH_CHECK(ctx);
             std::vector<cudaTextureObject_t> ts((size_t)n_chunks);
             fixed = true;
@@ -1389,7 +1394,7 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
 #define LAUNCH_FIXED(MB) describe_fixed_kernel<MB><<<ctx->num_sms * MB, WK_WARPS * 32, 0, st>>>(                                              \
                     base_a, base_b, split, img_stride, rows, cols, stride, ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), \
                     ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, ts[c], c * per, std::min(per, batch - c * per),                   \
-                    work_counter + 4 + c, work_counter + 4 + SURF_MAX_DESC_CHUNKS + c, lpt_split, big_flag, fb_list, fb_count)
+                    work_counter + 4 + c, work_counter + 4 + SURF_MAX_DESC_CHUNKS + c, lpt_split, big_flag, fb_list, fb_count, ws.img_off)
                 static const int minb = getenv("VFSMS_DESC_MINB") ? atoi(getenv("VFSMS_DESC_MINB")) : DESC_FIXED_MINB;   // measurement aid
                 if (minb == 2) LAUNCH_FIXED(2); else if (minb == 4) LAUNCH_FIXED(4); else LAUNCH_FIXED(DESC_FIXED_MINB);
 #undef LAUNCH_FIXED
@@ -1400,11 +1405,11 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
     describe_reference_kernel<<<fixed ? ctx->num_sms : ctx->num_sms * 4, WK_WARPS * 32, 0, st>>>(
         base_a, base_b, split, img_stride, rows, cols, stride, ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(),
         ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, p->upright, work_counter, big_flag,
-        fixed ? fb_list : nullptr, fixed ? fb_count : nullptr);
+        fixed ? fb_list : nullptr, fixed ? fb_count : nullptr, ws.img_off);
     LAUNCH_CHECK(ctx);
     orient_describe_kernel<<<ctx->num_sms * 2, DESC_THREADS, 0, st>>>(base_a, base_b, split, img_stride, rows, cols, stride,
                                                                        ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(),
-                                                                       ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, p->upright, big_flag);
+                                                                       ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, p->upright, big_flag, ws.img_off);
     LAUNCH_CHECK(ctx);
     return 0;
 }

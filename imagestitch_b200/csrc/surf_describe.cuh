@@ -57,10 +57,11 @@ __device__ __forceinline__ int round_half_even_u8(float v)      // cvRound for 0
 
 // float copy of the batch's images for the texture path (pitch in floats), scaled by a power of two (2^-64 for the fixed kernel)
 __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride,
-                                                        int rows, int cols, int stride, float *dst, int pitch_f, float scale)
+                                                        int rows, int cols, int stride, float *dst, int pitch_f, float scale,
+                                                        const int64_t *__restrict__ img_off)
 {
     const int b = blockIdx.y;
-    const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
+    const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride, img_off);
     float *D = dst + (size_t)b * rows * pitch_f;
     const int total = rows * cols;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) describe_reference_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
     const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
     int batch, int kp_cap, int extended, int upright, int *work_counter, int *big_flag,
-    const int *__restrict__ work_list, const int *__restrict__ work_count)
+    const int *__restrict__ work_list, const int *__restrict__ work_count, const int64_t *__restrict__ img_off)
 {
     __shared__ DescScratch s_ws[WK_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, 4) describe_reference_kernel(
         const float s = size * 1.2f / 9.0f;
         const int win = (int)((PATCH_SZ + 1) * s);
         if (win > WK_MAX_WIN) { if (lane == 0) *big_flag = 1; continue; }     // warp-uniform: flag work for the CTA kernel
-        const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
+        const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride, img_off);
         const int32_t *I = integral + (size_t)b * srows * W;
         const int gws = 2 * __float2int_rn(2 * s);
         float descriptor_dir = 360.f - 90.f;
@@ -567,7 +568,8 @@ __global__ void __launch_bounds__(WK_WARPS * 32, MINB) describe_fixed_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
     const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
     int batch, int kp_cap, int extended, const cudaTextureObject_t tex, int b_first, int b_count,
-    int *work_counter, int *work_counter_large, int lpt_split, int *big_flag, int *fb_list, int *fb_count)
+    int *work_counter, int *work_counter_large, int lpt_split, int *big_flag, int *fb_list, int *fb_count,
+    const int64_t *__restrict__ img_off)
 {
     __shared__ DescScratch s_ws[WK_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -596,7 +598,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, MINB) describe_fixed_kernel(
         const int win = (int)((PATCH_SZ + 1) * s);
         if (lpt_split > 0 && ((win >= lpt_split) != (pass == 0))) continue;   // warp-uniform: the other pass owns this keypoint
         if (win > WK_MAX_WIN) { if (lane == 0) *big_flag = 1; continue; }     // warp-uniform: flag work for the CTA kernel
-        const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride);
+        const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride, img_off);
         const int32_t *I = integral + (size_t)b * srows * W;
         const int gws = 2 * __float2int_rn(2 * s);
         const float descriptor_dir = orient_keypoint(S, lane, I, W, srows, scols, cx, cy, s, gws);

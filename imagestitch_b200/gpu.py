@@ -589,6 +589,19 @@ def tiles_align(first, n_pairs, direction, roi_len, params=None, ratio=0.75, off
     return res
 
 
+def tiles_align_list(first_tiles, directions, roi_len, params=None, ratio=0.75, offset_evaluate=3, device=0):
+    """One fused call for an arbitrary list of candidates: pair p = stack tiles (first_tiles[p], first_tiles[p] + 1) in
+    directions[p]; all directions must cut strips of one shape (1 / 3 or 2 / 4).  -> structured array like align_batch."""
+    p = params if params is not None else surf_params()
+    ft = np.ascontiguousarray(first_tiles, np.int32); dr = np.ascontiguousarray(directions, np.int32)
+    assert ft.ndim == 1 and ft.shape == dr.shape and len(ft) > 0
+    res = np.zeros(len(ft), PAIR_RESULT_DTYPE)
+    check(_lib.load().vfsms_tiles_align_list(_lib.context(device), len(ft), ft.ctypes.data_as(ctypes.c_void_p), dr.ctypes.data_as(ctypes.c_void_p),
+                                             int(roi_len), ctypes.byref(p), ctypes.c_float(ratio), int(offset_evaluate),
+                                             res.ctypes.data_as(ctypes.c_void_p)), "vfsms_tiles_align_list")
+    return res
+
+
 def tiles_mosaic(first, n_tiles, origins, rois, pair_offsets, method, canvas_shape, device=0):
     o = np.ascontiguousarray(origins, np.int32); r = np.ascontiguousarray(rois, np.int32); po = np.ascontiguousarray(pair_offsets, np.int32)
     out = np.empty((int(canvas_shape[0]), int(canvas_shape[1])), np.uint8)

@@ -119,10 +119,10 @@ def align_sequence_sharded(evaluate, n_pairs, direction, direct_incre, roi_ratio
 
 # ---------------------------------------------------------------- batched variant: tiles stay on their owner's GPU
 # evaluate_shard() above asks for one candidate at a time -- one device call per (pair, i, direction), the latency-bound shape.
-# Here the unit of device work is a BATCH: batch_evaluate(pairs, i, direction) -> int32 [len(pairs), 4] evaluates the same
-# candidate for a list of pairs in one fused call (vfsms_tiles_align on the rank's device-resident tiles).  A shard is walked in
+# Here the unit of device work is a BATCH: batch_evaluate(pairs, i, directions) -> int32 [len(pairs), 4] evaluates candidate
+# (i, directions[k]) of pairs[k] for a whole list in one fused call (vfsms_tiles_align_list on the rank's device-resident tiles).  A shard is walked in
 # ROUNDS: the sequential search is simulated over the table filled so far, every pair stops at its first unevaluated candidate,
-# and all requests of a round are grouped by (i, direction).  Pairs behind an unresolved pair continue with the last known
+# and all requests of a round are grouped by (i, strip shape).  Pairs behind an unresolved pair continue with the last known
 # direction -- a guess: a wrong guess only costs evaluations, the table holds pure functions of (pair, i, direction).
 # Nobody but the owner can evaluate a pair (the tiles never leave its GPU), so the replay is a loop as well: rank 0 replays, the
 # candidates it misses (a shard's first pairs, when the true carried direction differs from the shard's assumption) go back to
@@ -130,9 +130,10 @@ def align_sequence_sharded(evaluate, n_pairs, direction, direct_incre, roi_ratio
 # round one broadcast of the request list and one all_gather of the answers.
 
 
-def _missing_candidates(table, start_pair, direction, direct_incre, roi_ratio):
+def _missing_candidates(table, start_pair, direction, direct_incre, roi_ratio, eager=False):
     """Sequential walk over `table` (pairs start_pair ...): -> (results, requests, end_direction).  results[k] is None for a pair
-    whose search stops at an unevaluated candidate; requests = [(pair, i, direction)] -- that candidate, one per such pair."""
+    whose search stops at an unevaluated candidate; requests = [(pair, i, direction)] -- that candidate, one per such pair
+    (eager: every unevaluated direction of that ROI size, which saves the rounds a turn of the path would otherwise take)."""
     results, requests = [], []
     d = direction
     for k in range(table.shape[0]):
@@ -145,6 +146,8 @@ def _missing_candidates(table, start_pair, direction, direct_incre, roi_ratio):
                 st = table[k, i - 1, local - 1, 0]
                 if st == UNEVALUATED:
                     requests.append((start_pair + k, i, local)); pending = True
+                    if eager and direct_incre != 0:
+                        requests += [(start_pair + k, i, dd) for dd in (1, 2, 3, 4) if dd != local and table[k, i - 1, dd - 1, 0] == UNEVALUATED]
                     break
                 if st:
                     found = (True, i, local, (int(table[k, i - 1, local - 1, 1]), int(table[k, i - 1, local - 1, 2])))
@@ -167,12 +170,14 @@ def _missing_candidates(table, start_pair, direction, direct_incre, roi_ratio):
 
 
 def _run_requests(batch_evaluate, table, start_pair, requests):
+    """One batch_evaluate call per (i, strip shape): directions 1 / 3 cut row strips, 2 / 4 column strips."""
     groups = {}
     for pair, i, d in requests:
-        groups.setdefault((i, d), []).append(pair)
-    for (i, d), pairs in sorted(groups.items()):
-        res = np.asarray(batch_evaluate(pairs, i, d), np.int32).reshape(len(pairs), 4)
-        for pair, r in zip(pairs, res):
+        groups.setdefault((i, d in (2, 4)), []).append((pair, d))
+    for (i, _), items in sorted(groups.items()):
+        pairs = [p for p, _ in items]; dirs = [d for _, d in items]
+        res = np.asarray(batch_evaluate(pairs, i, dirs), np.int32).reshape(len(pairs), 4)
+        for (pair, d), r in zip(items, res):
             table[pair - start_pair, i - 1, d - 1] = r
     return len(groups)
 
@@ -202,7 +207,7 @@ def evaluate_shard_batched(batch_evaluate, start, stop, direction, direct_incre,
         if guesses:
             calls += _run_requests(batch_evaluate, table, start, guesses)
     while n > 0:
-        _, requests, _ = _missing_candidates(table, start, direction, direct_incre, roi_ratio)
+        _, requests, _ = _missing_candidates(table, start, direction, direct_incre, roi_ratio, eager=probe_step > 0)
         if not requests:
             break
         calls += _run_requests(batch_evaluate, table, start, requests)
@@ -234,26 +239,15 @@ def align_sequence_sharded_batched(batch_evaluate, n_pairs, direction, direct_in
 
 
 def tiles_batch_evaluator(first_tile, roi_lens, params=None, ratio=0.75, offset_evaluate=3, device=0):
-    """batch_evaluate(pairs, i, direction) on the context's device-resident tile stack: stack slot `pair - first_tile` holds tile
-    `pair`.  roi_lens(i, direction) -> ROI length in pixels (int(i * roiRatio * extent), ImageUtility.py:66-101).  Runs of
-    equally spaced pairs become one vfsms_tiles_align_strided call each."""
+    """batch_evaluate(pairs, i, directions) on the context's device-resident tile stack: stack slot `pair - first_tile` holds tile
+    `pair`.  roi_lens(i, direction) -> ROI length in pixels (int(i * roiRatio * extent), ImageUtility.py:66-101).  The directions
+    of one call cut strips of one shape (sharding._run_requests groups them so)."""
     from . import gpu
 
-    def batch_evaluate(pairs, i, direction):
-        out = np.zeros((len(pairs), 4), np.int32)
-        k = 0
-        while k < len(pairs):                      # maximal runs of equally spaced pairs: one fused call each
-            step = pairs[k + 1] - pairs[k] if k + 1 < len(pairs) else 1
-            j = k
-            while step > 0 and j + 1 < len(pairs) and pairs[j + 1] - pairs[j] == step:
-                j += 1
-            if step <= 0:
-                step = 1
-            r = gpu.tiles_align(pairs[k] - first_tile, j - k + 1, direction, roi_lens(i, direction), params=params, ratio=ratio,
-                                offset_evaluate=offset_evaluate, device=device, step=step)
-            out[k:j + 1, 0] = r["status"]; out[k:j + 1, 1] = r["d_row"]; out[k:j + 1, 2] = r["d_col"]; out[k:j + 1, 3] = r["votes"]
-            k = j + 1
-        return out
+    def batch_evaluate(pairs, i, directions):
+        r = gpu.tiles_align_list([p - first_tile for p in pairs], directions, roi_lens(i, directions[0]), params=params, ratio=ratio,
+                                 offset_evaluate=offset_evaluate, device=device)
+        return np.stack([r["status"], r["d_row"], r["d_col"], r["votes"]], axis=1).astype(np.int32)
     return batch_evaluate
 
 
@@ -425,7 +419,8 @@ def _send_patches(patches, dst, device):
     for k, (rect, data) in enumerate(patches):
         head[1 + 6 * k:7 + 6 * k] = torch.tensor(list(rect) + [data.ndim, data.shape[2] if data.ndim == 3 else 1])
     n_head = torch.tensor([head.numel()], dtype=torch.int64)
-    for t in [n_head, head] + [torch.from_numpy(np.ascontiguousarray(d, np.int16)).reshape(-1) for _, d in patches]:
+    # int16 patches travel as bytes: NCCL has no 16-bit integer type
+    for t in [n_head, head] + [torch.from_numpy(np.ascontiguousarray(d, np.int16).reshape(-1).view(np.uint8)) for _, d in patches]:
         if t.numel():
             dist.send(t.to(device) if device is not None else t, dst)
 
@@ -445,7 +440,7 @@ def _recv_patches(src, device):
     for k in range(int(head[0])):
         r0, c0, r1, c1, ndim, ch = (int(v) for v in head[1 + 6 * k:7 + 6 * k])
         shape = (r1 - r0, c1 - c0) if ndim == 2 else (r1 - r0, c1 - c0, ch)
-        patches.append(((r0, c0, r1, c1), recv(int(np.prod(shape)), torch.int16).numpy().reshape(shape).copy()))
+        patches.append(((r0, c0, r1, c1), recv(2 * int(np.prod(shape)), torch.uint8).numpy().view(np.int16).reshape(shape).copy()))
     return patches
 
 

@@ -304,6 +304,11 @@ int vfsms_tiles_align(vfsms_ctx *ctx, int first, int n_pairs, int direction, int
  * the probe pairs with which a sharded run guesses the shooting direction before it walks its pairs (sharding.py). */
 int vfsms_tiles_align_strided(vfsms_ctx *ctx, int first, int n_pairs, int pair_step, int direction, int roi_len,
                               const vfsms_surf_params *params, float ratio, int offset_evaluate, vfsms_pair_result *results);
+/* The same for an arbitrary list: pair p = tiles (first_tile[p], first_tile[p] + 1) in direction[p].  All directions of one call
+ * must cut strips of one shape (1 and 3: roi_len x cols, 2 and 4: rows x roi_len).  One fused call for a whole round of the batched
+ * search of a sharded run, whatever pairs and directions it asks for (sharding.evaluate_shard_batched). */
+int vfsms_tiles_align_list(vfsms_ctx *ctx, int n_pairs, const int32_t *first_tile, const int32_t *direction, int roi_len,
+                           const vfsms_surf_params *params, float ratio, int offset_evaluate, vfsms_pair_result *results);
 /* vfsms_mosaic_host with tiles first .. first + n_tiles - 1 of the stack (gray). */
 int vfsms_tiles_mosaic(vfsms_ctx *ctx, int first, int n_tiles, const int32_t *tile_origin, const int32_t *roi_rect,
                        const int32_t *pair_offset, int method, int canvas_rows, int canvas_cols, uint8_t *canvas_out);

@@ -122,3 +122,26 @@ def test_stitcher_colour_mode_on_jpeg_tiles(tiles, tmp_path):
     assert len(results["b200"]) == len(results["cv2"]) >= 1
     for a, b in zip(results["b200"], results["cv2"]):
         assert a is not None and a.ndim == 3 and np.array_equal(a, b)
+
+
+def test_tiles_align_list_equals_per_direction_calls():
+    from imagestitch_b200 import gpu
+    """vfsms_tiles_align_list: arbitrary (pair, direction) lists in one fused call = the per-direction contiguous calls, and the
+    strided variant = every step-th pair of them (the calls a sharded run's batched search makes, sharding.py)."""
+    from imagestitch_b200 import synth
+    tiles, _ = synth.tile_sequence(31, 2, 3, size=512, overlap=64)             # 6 tiles, serpentine: directions 2, 2, 1, 4, 4
+    gpu.tiles_reserve(len(tiles), 512, 512)
+    gpu.tiles_upload(0, tiles)
+    L = int(0.2 * 512)
+    ref = {d: gpu.tiles_align(0, 5, d, L) for d in (1, 2, 3, 4)}
+    assert ref[2]["status"][[0, 1]].all() and ref[1]["status"][2] and ref[4]["status"][[3, 4]].all()
+    for dirs in ((1, 3), (2, 4)):
+        pairs = [4, 0, 2, 2, 3, 1, 0]
+        ds = [dirs[k % 2] for k in range(len(pairs))]
+        got = gpu.tiles_align_list(pairs, ds, L)
+        for k, (p, d) in enumerate(zip(pairs, ds)):
+            assert got[k] == ref[d][p], (k, p, d)
+    strided = gpu.tiles_align(0, 3, 2, L, step=2)
+    assert all(strided[k] == ref[2][2 * k] for k in range(3))
+    with pytest.raises(gpu.VfsmsError):
+        gpu.tiles_align_list([0, 1], [1, 2], L)                                  # mixed strip shapes

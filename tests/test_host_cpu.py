@@ -173,16 +173,17 @@ def test_sharding_batched_rounds_equal_sequential():
         return int(ok or spurious), 100 + pair, -pair, 9
     calls = []
 
-    def batch_evaluate(pairs, i, d):
-        calls.append((tuple(pairs), i, d))
-        return [evaluate(p, i, d) for p in pairs]
+    def batch_evaluate(pairs, i, dirs):
+        assert len({d in (2, 4) for d in dirs}) == 1         # one strip shape per device call
+        calls.append((tuple(zip(pairs, dirs)), i))
+        return [evaluate(p, i, d) for p, d in zip(pairs, dirs)]
     for incre in (1, -1, 0):
         seq, _ = sh.replay(sh.evaluate_shard(evaluate, 0, n, 1, incre, 0.2), evaluate, 1, incre, 0.2)
         del calls[:]
         table, n_calls = sh.evaluate_shard_batched(batch_evaluate, 0, n, 1, incre, 0.2)
         out, requests, _ = sh._missing_candidates(table, 0, 1, incre, 0.2)
         assert not requests and out == seq
-        assert n_calls == len(calls) <= 30                 # a handful of batched device calls instead of ~n single ones
+        assert n_calls == len(calls) <= 24                 # a handful of batched device calls instead of ~n single ones
         assert all(len(set(c[0])) == len(c[0]) for c in calls)
         on_path = int((sh.evaluate_shard(evaluate, 0, n, 1, incre, 0.2)[..., 0] != sh.UNEVALUATED).sum())
         done = sum(len(c[0]) for c in calls)
@@ -203,9 +204,9 @@ ranges = sh.partition_pairs(n, world)
 lo, hi = ranges[rank]
 def evaluate(pair, i, d):
     return int(d == true_dir[pair] and i >= 1 + (pair % 5 == 2)), 50 + pair, pair - 3, 7
-def batch_evaluate(pairs, i, d):
+def batch_evaluate(pairs, i, dirs):
     assert all(lo <= p < hi for p in pairs), (rank, pairs)          # only the owner is ever asked
-    return [evaluate(p, i, d) for p in pairs]
+    return [evaluate(p, i, d) for p, d in zip(pairs, dirs)]
 seq, _ = sh.replay(sh.evaluate_shard(evaluate, 0, n, 1, 1, 0.2), evaluate, 1, 1, 0.2)
 out, stats = sh.align_sequence_sharded_batched(batch_evaluate, n, 1, 1, 0.2, rank, world)               # with direction probes
 assert out == seq, (rank, out, seq)

@@ -153,3 +153,18 @@ def test_roi_and_vote_against_unmodified_reference():
         for order in ("first", "second"):
             for ratio in (0.2, 0.4, 0.6000000000000001):
                 assert np.array_equal(ref.getROIRegionForIncreMethod(img, d, order, ratio), ours.getROIRegionForIncreMethod(img, d, order, ratio))
+
+
+def test_cuda_path_reproduced_the_golden_vector_on_hardware():
+    """profiles/r02/dendritic_89_pairs_gpu.json is the record of scripts/golden_grid_gpu.py on a B200 (the 90 demo JPEGs cannot be
+    committed): the CUDA path -- library JPEG decode, batched incremental SURF search -- against the author's list at
+    Stitcher.py:87.  The record must agree with the committed golden list pair by pair."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rec = json.load(open(os.path.join(root, "profiles", "r02", "dendritic_89_pairs_gpu.json")))
+    golden = json.load(open(os.path.join(root, "tests", "golden", "dendritic_offsets.json")))["golden_Stitcher_py_87"]
+    assert rec["tiles"] == 90 and rec["shape"] == [1936, 2584]
+    for name, run in rec["runs"].items():
+        assert run["pairs"] == 89 and len(run["offsets"]) == 89
+        ok = sum(1 for (st, off, _), g in zip(run["offsets"], golden) if st and max(abs(off[0] - g[0]), abs(off[1] - g[1])) <= 1)
+        assert ok == run["within_1px_of_golden"] == 89, (name, ok)

@@ -21,31 +21,25 @@ class ImageFusion(Method):
         return np.asarray(imageA), np.asarray(imageB)
 
     def fuseByAverage(self, images):
-        """uint8((A + B) / 2) -- ImageFusion.py:12-21.  Inputs are taken as already zero-filled (Stitcher.py:498-504)."""
+        """uint8((A + B) / 2) on the arrays as given -- ImageFusion.py:12-21.  (The -1 -> 0 and mutual zero fill belong to
+        Stitcher.fuseImage, Stitcher.py:498-504, which goes through gpu.fuse_roi without `raw`.)"""
         a, b = self._pair(images)
-        return gpu.fuse_roi(self._filled(a), self._filled(b), "average")
+        return gpu.fuse_roi(a, b, "average", raw=True)
 
     def fuseByMaximum(self, images):
         """ImageFusion.py:23-31."""
         a, b = self._pair(images)
-        return gpu.fuse_roi(self._filled(a), self._filled(b), "maximum")
+        return gpu.fuse_roi(a, b, "maximum", raw=True)
 
     def fuseByMinimum(self, images):
         """ImageFusion.py:33-41."""
         a, b = self._pair(images)
-        return gpu.fuse_roi(self._filled(a), self._filled(b), "minimum")
-
-    @staticmethod
-    def _filled(x):
-        # the device kernel applies "-1 -> 0, mutual zero fill" itself (idempotent on already filled data)
-        return x
+        return gpu.fuse_roi(a, b, "minimum", raw=True)
 
     def getWeightsMatrix(self, images):
         """Corner-case weight matrices (weightMatA, weightMatB) float32 -- ImageFusion.py:43-190."""
         a, b = self._pair(images)
-        if np.count_nonzero(a > -1) / a.size > 0.65:
-            # the reference only calls this for sparse ROIs; force the corner path by asking the kernel for it explicitly
-            pass
+        # the reference only calls this for sparse ROIs (ImageFusion.py:209); the corner path is requested explicitly
         _, wa, wb = gpu.fuse_roi(a, b, "fadeInAndFadeOut", 0, 0, want_weights=True, force_corner=True)
         if a.ndim == 3:
             wa = np.repeat(wa[:, :, None], a.shape[2], axis=2); wb = np.repeat(wb[:, :, None], a.shape[2], axis=2)

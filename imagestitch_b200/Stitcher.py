@@ -167,11 +167,15 @@ def _load_sequence(paths, decoder="b200", keep_on_device=True, color=False):
     try:
         fill(color)
     except gpu.VfsmsError:
-        if not color:
-            raise
-        # the colour twin did not fit (3 x the gray stack): gray stack only, the mosaic then decodes the colour tiles batch by batch
+        # colour: the twin did not fit (3 x the gray stack) -> gray stack only, the mosaic then decodes the colour tiles batch by batch.
+        # gray (or the retry): no room for the stack, or a file the parser accepted turned out undecodable -> host tiles, per-file decode
         _last_sequence_has_color = False
-        fill(False)
+        try:
+            if not color:
+                raise
+            fill(False)
+        except gpu.VfsmsError:
+            return _imread_gray_many(paths, decoder), False
     host = gpu.tiles_download(0, n, rows, cols)
     return [host[j] for j in range(n)], True
 

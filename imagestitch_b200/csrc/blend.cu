@@ -183,14 +183,18 @@ __global__ void __launch_bounds__(256) blend_plan_kernel(const int16_t *__restri
     }
 }
 
-// method: VFSMS_FUSE_*.  out may alias nothing; wa_out / wb_out optional (per pixel, float32).
-__global__ void __launch_bounds__(256) blend_apply_kernel(const int16_t *__restrict__ A, int64_t a_rs, const int16_t *__restrict__ B, int64_t b_rs,
-                                                          int rows, int cols, int ch, int method, int d_row, int d_col,
+// method_flags: VFSMS_FUSE_* | 0x200 (raw: average / maximum / minimum without the -1 -> 0 and mutual zero fill of Stitcher.fuseImage --
+// the semantics of a direct ImageFusion.fuseBy* call).  out16 may be B's own memory (the mosaic blends in place): A and B carry no
+// __restrict__, and every element is read before the same thread writes it.  wa_out / wb_out optional (per pixel, float32).
+__global__ void __launch_bounds__(256) blend_apply_kernel(const int16_t *A, int64_t a_rs, const int16_t *B, int64_t b_rs,
+                                                          int rows, int cols, int ch, int method_flags, int d_row, int d_col,
                                                           const BlendPlan *__restrict__ plan, const float *__restrict__ w1, const float *__restrict__ w2,
                                                           uint8_t *out8, int64_t o_rs, int16_t *out16, int64_t o16_rs,
                                                           float *wa_out, float *wb_out)
 {
     const int64_t total = (int64_t)rows * cols;
+    const int method = method_flags & 0xff;
+    const bool raw = (method_flags & 0x200) != 0;
     const int corner = (method == VFSMS_FUSE_FADE || method == VFSMS_FUSE_TRIG) ? plan->corner : 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
@@ -239,10 +243,12 @@ __global__ void __launch_bounds__(256) blend_apply_kernel(const int16_t *__restr
                 res = (int)v;                                              // np.uint8 truncation
             } else {
                 // Stitcher.py:498-504: -1 -> 0, then mutual zero fill
-                if (a == -1) a = 0;
-                if (b == -1) b = 0;
-                if (a == 0) a = b;
-                if (b == 0) b = a;
+                if (!raw) {
+                    if (a == -1) a = 0;
+                    if (b == -1) b = 0;
+                    if (a == 0) a = b;
+                    if (b == 0) b = a;
+                }
                 if (method == VFSMS_FUSE_AVERAGE) res = (a + b) / 2;      // uint8((A + B) / 2): truncation of a non-negative value
                 else if (method == VFSMS_FUSE_MAXIMUM) res = a > b ? a : b;
                 else if (method == VFSMS_FUSE_MINIMUM) res = a < b ? a : b;
@@ -284,6 +290,7 @@ static int fuse_roi_dev(vfsms_ctx *ctx, const int16_t *A, int64_t a_rs, const in
                         float *wa_out, float *wb_out, cudaStream_t st)
 {
     const int force_corner = (method & 0x100) != 0;      // getWeightsMatrix parity hook: always take the corner path
+    const int raw = method & 0x200;                      // direct ImageFusion.fuseByAverage / Maximum / Minimum: no zero fill
     method &= 0xff;
     BlendState *bs = bstate(ctx);
     int rc;
@@ -305,7 +312,7 @@ static int fuse_roi_dev(vfsms_ctx *ctx, const int16_t *A, int64_t a_rs, const in
                                              bs->w1.as<float>(), bs->w2.as<float>(), force_corner);
         LAUNCH_CHECK(ctx);
     }
-    blend_apply_kernel<<<grid_for(ctx, n), 256, 0, st>>>(A, a_rs, B, b_rs, rows, cols, ch, method, d_row, d_col, bs->plan.as<BlendPlan>(),
+    blend_apply_kernel<<<grid_for(ctx, n), 256, 0, st>>>(A, a_rs, B, b_rs, rows, cols, ch, method | raw, d_row, d_col, bs->plan.as<BlendPlan>(),
                                                          bs->w1.as<float>(), bs->w2.as<float>(), out8, o_rs, out16, o16_rs, wa_out, wb_out);
     LAUNCH_CHECK(ctx);
     return 0;

@@ -102,9 +102,12 @@ extern "C" int vfsms_enhance_host(vfsms_ctx *ctx, const uint8_t *image, int rows
     int tiles_x = 1, tiles_y = 1, tile_w = cols, tile_h = rows;
     if (mode == 1) {
         tiles_x = tiles_y = tile_grid;
-        // OpenCV pads (REFLECT_101) to a multiple of the grid; tiles are taken over the padded size
-        const int pc = cols % tiles_x == 0 ? cols : cols + (tiles_x - cols % tiles_x);
-        const int pr = rows % tiles_y == 0 ? rows : rows + (tiles_y - rows % tiles_y);
+        // OpenCV (CLAHE_Impl::apply) pads (REFLECT_101) to a multiple of the grid and takes the tiles over the padded size.  It pads
+        // BOTH dimensions as soon as EITHER is not divisible: right = tilesX - cols % tilesX, bottom = tilesY - rows % tilesY, so an
+        // already divisible side grows by one whole tile count.
+        const bool exact = cols % tiles_x == 0 && rows % tiles_y == 0;
+        const int pc = exact ? cols : cols + (tiles_x - cols % tiles_x);
+        const int pr = exact ? rows : rows + (tiles_y - rows % tiles_y);
         tile_w = pc / tiles_x; tile_h = pr / tiles_y;
     }
     const int n_tiles = tiles_x * tiles_y, tile_total = tile_w * tile_h;

@@ -84,6 +84,28 @@ static bool build_huff(HuffTable &t, const uint8_t *bits /* 16 */, const uint8_t
     return true;
 }
 
+// Orientation tag of an APP1 Exif segment (payload `s`, `n` bytes), 0 when absent or malformed.
+static int exif_orientation(const uint8_t *s, size_t n)
+{
+    if (n < 14 || memcmp(s, "Exif\0\0", 6) != 0) return 0;
+    const uint8_t *t = s + 6; const size_t tn = n - 6;
+    const bool le = t[0] == 'I' && t[1] == 'I', be = t[0] == 'M' && t[1] == 'M';
+    if (!le && !be) return 0;
+    auto u16 = [&](size_t o) -> unsigned { return le ? (unsigned)(t[o] | (t[o + 1] << 8)) : (unsigned)((t[o] << 8) | t[o + 1]); };
+    auto u32 = [&](size_t o) -> unsigned { return le ? (unsigned)(t[o] | (t[o + 1] << 8) | (t[o + 2] << 16) | ((unsigned)t[o + 3] << 24))
+                                                     : (unsigned)(((unsigned)t[o] << 24) | (t[o + 1] << 16) | (t[o + 2] << 8) | t[o + 3]); };
+    if (u16(2) != 42) return 0;
+    const size_t ifd = u32(4);
+    if (ifd + 2 > tn) return 0;
+    const unsigned cnt = u16(ifd);
+    for (unsigned k = 0; k < cnt; k++) {
+        const size_t e = ifd + 2 + 12 * (size_t)k;
+        if (e + 12 > tn) return 0;
+        if (u16(e) == 0x0112) return (int)(u16(e + 2) == 3 ? u16(e + 8) : u32(e + 8));      // SHORT in the value field
+    }
+    return 0;
+}
+
 static int jpeg_parse(const uint8_t *d, size_t n, JpegHeader &H)
 {
     if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) { vfsms_set_error("jpeg: no SOI marker"); return VFSMS_E_UNSUPPORTED; }
@@ -140,6 +162,14 @@ static int jpeg_parse(const uint8_t *d, size_t n, JpegHeader &H)
         } else if (m == 0xC2 || m == 0xC3 || (m >= 0xC5 && m <= 0xC7) || (m >= 0xC9 && m <= 0xCB) || (m >= 0xCD && m <= 0xCF)) {
             vfsms_set_error("jpeg: SOF%d (progressive / lossless / arithmetic) is not supported", m - 0xC0);
             return VFSMS_E_UNSUPPORTED;
+        } else if (m == 0xE1) {
+            // Exif orientation (TIFF tag 0x0112 of IFD0): cv2.imdecode rotates / flips the decoded image for values 2..8 (the
+            // reference never sets IMREAD_IGNORE_ORIENTATION).  Such files are left to the caller's cv2 fallback.
+            const int orient = exif_orientation(s, sl);
+            if (orient > 1 && orient <= 8) {
+                vfsms_set_error("jpeg: Exif orientation %d (cv2.imdecode would rotate / flip the image) is not supported", orient);
+                return VFSMS_E_UNSUPPORTED;
+            }
         } else if (m == 0xEE) {
             if (sl >= 12 && memcmp(s, "Adobe", 5) == 0) adobe_transform = s[11];
         } else if (m == 0xDD) {

@@ -168,7 +168,7 @@ def _as_i16(a):
     return np.ascontiguousarray(a, np.int16)
 
 
-def fuse_roi(image_a, image_b, method, d_row=0, d_col=0, want_weights=False, force_corner=False, device=0):
+def fuse_roi(image_a, image_b, method, d_row=0, d_col=0, want_weights=False, force_corner=False, device=0, raw=False):
     """Stitcher.fuseImage for one overlap ROI.  image_*: [r, c] or [r, c, 3] integer arrays with -1 = empty.
     -> uint8 array (and the float32 weight matrices when want_weights)."""
     L = _lib.load()
@@ -181,6 +181,8 @@ def fuse_roi(image_a, image_b, method, d_row=0, d_col=0, want_weights=False, for
     m = FUSE_METHODS[method] if isinstance(method, str) else int(method)
     if force_corner:
         m |= 0x100
+    if raw:                 # average / maximum / minimum on the arrays as given (no -1 -> 0, no mutual zero fill)
+        m |= 0x200
     out = np.empty(A.shape, np.uint8)
     wa = wb = None
     if want_weights:

@@ -118,7 +118,9 @@ def test_enhancement_equals_cv2(tile_set):
     import cv2
     from imagestitch_b200 import gpu
     root, tiles, offs = tile_set
-    for img in (tiles[0], tiles[1][:103, :257], np.ascontiguousarray(tiles[2][:, 512 - 102:])):
+    # 100 x 103 / 103 x 100 / 100 x 100: one side divisible by the 5 x 5 grid, the other not (cv2 then pads BOTH), and both divisible
+    for img in (tiles[0], tiles[1][:103, :257], np.ascontiguousarray(tiles[2][:, 512 - 102:]), tiles[0][:100, :103], tiles[1][:103, :100],
+                tiles[2][:100, :100]):
         assert np.array_equal(gpu.enhance(img, clahe=False), cv2.equalizeHist(np.ascontiguousarray(img)))
         ref = cv2.createCLAHE(clipLimit=20, tileGridSize=(5, 5)).apply(np.ascontiguousarray(img))
         out = gpu.enhance(img, clahe=True, clip_limit=20, tile_size=5)

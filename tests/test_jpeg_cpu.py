@@ -115,6 +115,33 @@ def test_unsupported_and_damaged_input():
         gpu.jpeg_info(data[:30])
 
 
+def _with_exif_orientation(data, orientation, big_endian=False):
+    """Insert an APP1 Exif segment holding only the orientation tag right after SOI."""
+    import struct
+    e = ">" if big_endian else "<"
+    tiff = (b"MM" if big_endian else b"II") + struct.pack(e + "HI", 42, 8) + struct.pack(e + "H", 1) + \
+        struct.pack(e + "HHIHH", 0x0112, 3, 1, orientation, 0) + struct.pack(e + "I", 0)
+    payload = b"Exif\0\0" + tiff
+    return data[:2] + b"\xff\xe1" + struct.pack(">H", len(payload) + 2) + payload + data[2:]
+
+
+def test_exif_orientation_is_left_to_cv2():
+    """cv2.imdecode applies the Exif orientation (the reference never sets IMREAD_IGNORE_ORIENTATION): a tile tagged 2..8 comes out
+    rotated / flipped there.  The library decoder refuses such files, so that its callers take their cv2 path (Stitcher._load_sequence)."""
+    from imagestitch_b200 import gpu
+    img = _image(40, 60, 1)
+    data = _encode(img, 90)
+    for be in (False, True):
+        rot = _with_exif_orientation(data, 6, be)
+        assert cv2.imdecode(np.frombuffer(rot, np.uint8), cv2.IMREAD_GRAYSCALE).shape == (60, 40)       # cv2 rotates
+        with pytest.raises(gpu.JpegUnsupported):
+            gpu.jpeg_info(rot)
+        up = _with_exif_orientation(data, 1, be)                                                       # "top-left": nothing to do
+        assert gpu.jpeg_info(up)[:2] == (40, 60)
+        coef, _ = gpu.jpeg_luma_coefficients(up)
+        assert np.array_equal(coef, gpu.jpeg_luma_coefficients(data)[0])
+
+
 def test_damaged_files_never_crash_the_host_stage():
     """Bit flips, truncations and spliced garbage in headers and entropy data: the parser either reports unsupported / bad input or
     decodes something of the advertised geometry -- no out-of-bounds access (run under the normal allocator; a crash fails the suite)."""

@@ -177,13 +177,48 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     val = args.steps * n_sample / dt
     cores = surf.num_threads()
+    # real-cv2 context numbers on the same ROI pair through the reference's own calls (ImageUtility.py:256-302:
+    # SIFT_create().detectAndCompute + BFMatcher.knnMatch(k=2) + ratio 0.75; ORB_create(5000, 1.2, 8, 31, 0, 2, 0, 31, 20) + BFMatcher(
+    # NORM_HAMMING).match) + the vote port -- and the probe for a contrib / non-free cv2 that could run the reference's SURF itself
+    cv2_ctx = {"cv2_version": cv2.__version__}
+    try:
+        cv2.xfeatures2d.SURF_create()
+        cv2_ctx["contrib_surf_available"] = True
+    except Exception as e:                                                             # noqa: BLE001
+        cv2_ctx["contrib_surf_available"] = False
+        cv2_ctx["contrib_surf_probe"] = "%s: %s" % (type(e).__name__, str(e)[:120])
+    a, b = tiles[0]
+
+    def _vote(kA, kB, m):
+        return surf.offset_by_mode(np.float32([k.pt for k in kA]).reshape(-1, 2), np.float32([k.pt for k in kB]).reshape(-1, 2), m, 3)
+    try:
+        t0 = time.perf_counter()
+        sift = cv2.SIFT_create()
+        kA, dA = sift.detectAndCompute(a, None); kB, dB = sift.detectAndCompute(b, None)
+        raw = cv2.DescriptorMatcher_create("BruteForce").knnMatch(dA, dB, 2)
+        m = np.array([(r[0].trainIdx, r[0].queryIdx) for r in raw if len(r) == 2 and r[0].distance < r[1].distance * 0.75], np.int32).reshape(-1, 2)
+        st, o, v = _vote(kA, kB, m)
+        cv2_ctx["sift_pairs_per_s"] = 1.0 / (time.perf_counter() - t0)
+        cv2_ctx["sift_ok"] = bool(st and abs(o[0] + TILE - L - offs[0][0]) <= 1 and abs(o[1] - offs[0][1]) <= 1)
+        t0 = time.perf_counter()
+        orb = cv2.ORB_create(5000, 1.2, 8, 31, 0, 2, 0, 31, 20)
+        kA, dA = orb.detectAndCompute(a, None); kB, dB = orb.detectAndCompute(b, None)
+        mm = cv2.BFMatcher(cv2.NORM_HAMMING).match(dA, dB)
+        m = np.array([(x.trainIdx, x.queryIdx) for x in sorted(mm, key=lambda x: x.queryIdx)], np.int32).reshape(-1, 2)
+        st, o, v = _vote(kA, kB, m)
+        cv2_ctx["orb_pairs_per_s"] = 1.0 / (time.perf_counter() - t0)
+        cv2_ctx["orb_ok"] = bool(st and abs(o[0] + TILE - L - offs[0][0]) <= 1 and abs(o[1] - offs[0][1]) <= 1)
+        cv2_ctx["what"] = "one ROI pair (409x2048) of this workload, cv2 on %d threads: SIFT / ORB detect+describe, BFMatcher, vote port" % cv2.getNumThreads()
+    except Exception as e:                                                             # noqa: BLE001
+        cv2_ctx["error"] = "%s: %s" % (type(e).__name__, str(e)[:200])
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "synthetic 2048x2048 grayscale pair, SURF detect+describe+match+vote (ROI 409x2048, GPU-SURF params)",
                       "pairs_per_step": n_sample, "correct_pairs": ok, "cv2_threads": cv2.getNumThreads(), "host_cpus": host_cores()},
            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
-                            "sample": "%d pairs/step x %d steps: oracle C SURF (OpenMP %d thr) + cv2 BFMatcher knnMatch + ratio + vote port" % (n_sample, args.steps, cores)},
+                            "sample": "%d pairs/step x %d steps: oracle C SURF (OpenMP %d thr) + cv2 BFMatcher knnMatch + ratio + vote port" % (n_sample, args.steps, cores),
+                            "cv2_context": cv2_ctx},
            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 

@@ -118,8 +118,9 @@ class Method():
 
     def getOffsetByRansac(self, kpsA, kpsB, matches, offsetEvaluate=100):
         """cv2 passthrough of the self-labelled incomplete variant (ImageUtility.py:180-210); not on the hot path.
-        The reference calls cv2.getAffineTransform on all N points first, which throws for N != 3; that call is
-        dropped here, everything else is kept."""
+        The reference calls cv2.getAffineTransform on all N points first, which raises for N != 3 (and for N == 3 the
+        findHomography after it raises): the function cannot return there for any non-empty input.  That unused call is
+        dropped here, everything else is kept (tests/test_sequencing_reference_cpu.py pins both behaviours)."""
         import cv2
         if len(matches) == 0:
             return (False, [0, 0], 0)

@@ -193,3 +193,30 @@ def test_phase_incremental_search_equals_reference(monkeypatch):
         assert ref.direction == ours.direction
         n_ok += int(bool(r[0]))
     assert n_ok >= 2
+
+
+def test_get_offset_by_ransac_against_reference():
+    """Method.getOffsetByRansac (ImageUtility.py:180-210, self-labelled incomplete, not reachable from Main.py's settings).  In the
+    reference it cannot return for ANY non-empty input with the cv2 of this image: cv2.getAffineTransform on all matched points
+    raises unless there are exactly three, and with exactly three cv2.findHomography raises (it needs four).  Ours is the same
+    cv2 passthrough without the unused getAffineTransform call: same statements, same result convention, reachable from four
+    matches on.  Pinned here: the reference's behaviour, and ours on the empty / small / normal / too-few-inliers cases."""
+    import cv2
+    from oracle import reference_shims as rs
+    from imagestitch_b200.ImageUtility import Method
+    S, U, F = rs.import_reference()
+    ref, ours = U.Method(), Method()
+    rng = np.random.default_rng(4)
+    kpsB = rng.uniform(20, 400, (40, 2)).astype(np.float32)
+    kpsA = kpsB + np.float32([7.0, 153.0])                       # A = B shifted by (dx_col, dy_row) = (7, 153)
+    many = [(k, k) for k in range(40)]
+    for matches in ([(k, k) for k in (3, 11, 29)], many):
+        with pytest.raises(cv2.error):
+            ref.getOffsetByRansac(kpsA, kpsB, matches, offsetEvaluate=3)
+    assert ref.getOffsetByRansac(kpsA, kpsB, [], offsetEvaluate=3) == (False, [0, 0], 0)
+    assert ours.getOffsetByRansac(kpsA, kpsB, [], offsetEvaluate=3) == (False, [0, 0], 0)
+    st, off, H = ours.getOffsetByRansac(kpsA, kpsB, many, offsetEvaluate=10)
+    # -round(int(H)[1, 2]), -round(int(H)[0, 2]) with ptsA -> ptsB: the int() truncation of -152.99.. / -6.99.. may lose one pixel
+    assert st and abs(off[0] - 153) <= 1 and abs(off[1] - 7) <= 1
+    assert H.shape == (3, 3) and H[0, 2] == 0 and H[1, 2] == 0 and abs(H[0, 0] - 1) < 1e-3
+    assert ours.getOffsetByRansac(kpsA, kpsB, many, offsetEvaluate=1000)[0] is False

@@ -143,7 +143,7 @@ struct vfsms_ctx {
     int device = 0;
     int matcher_mode = 0;          // 0: tcgen05 candidates + exact rescoring, 1: exact SIMT kernel
     int describe_mode = 1;         // window sampler of the SURF descriptor: 0 reference (double precision, u8 image), 1 fixed-point chunked texture sampler (default)
-    int describe_lpt = 2;          // describe the large windows first (two passes over the work list): 0 off, 1 / 2 / 3 = split at 128 / 64 / 256 px
+    int describe_lpt = 1;          // describe the large windows first (two passes over the work list): 0 off, 1 / 2 / 3 = split at 128 / 64 / 256 px
     int sort_mode = 1;             // KeypointGreater ordering: 0 rank by counting over all candidates, 1 rank inside response bins (default)
     int32_t *last_fallback_count_dev = nullptr;
     cudaStream_t stream = nullptr;

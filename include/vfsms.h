@@ -92,7 +92,7 @@ enum {
     VFSMS_OPT_SORT_MODE = 1,      /* "sort": KeypointGreater ordering.  1 (default) = 13-bit response histogram, then rank counting
                                    * inside each candidate's own bin; 0 = rank by counting over all staged candidates */
     VFSMS_OPT_DESCRIBE_LPT = 2,   /* "lpt": describe the large windows first (two passes over the work list), so that no giant window
-                                   * is met at the end of the launch: split at 64 px (2, default), 128 px (1), 256 px (3); 0 = keypoints
+                                   * is met at the end of the launch: split at 128 px (1, default), 64 px (2), 256 px (3); 0 = keypoints
                                    * in response order */
     VFSMS_OPT_ENTROPY = 3,        /* "entropy": Huffman decoding of JPEG tiles.  1 (default) = on the device: self-synchronising
                                    * parallel decode of 1024-bit subsequences (files with restart intervals take the host stage);

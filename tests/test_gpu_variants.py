@@ -1,5 +1,5 @@
 """GPU: every kernel schedule selectable through vfsms_set_option (include/vfsms.h VFSMS_OPT_*) must give results IDENTICAL
-to every other one.  The defaults (describe=1: fixed-point chunked sampler, sort=1, lpt=2) are what bench.py times and what the
+to every other one.  The defaults (describe=1: fixed-point chunked sampler, sort=1, lpt=1) are what bench.py times and what the
 oracle tests of the rest of the suite run on; describe=0 is the reference sampler (double precision, u8 image)."""
 import numpy as np
 import pytest

@@ -1391,12 +1391,12 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
             for (int c = 0; c < n_chunks && fixed; c++)
                 fixed = surf_stack_texture(ctx, c * per, std::min(per, batch - c * per), rows, cols, ws.pitch_f, st, &ts[c]);
             for (int c = 0; c < n_chunks && fixed; c++) {
-#define LAUNCH_FIXED(MB) describe_fixed_kernel<MB><<<ctx->num_sms * MB, WK_WARPS * 32, 0, st>>>(                                              \
+#define LAUNCH_FIXED(MB, UU) describe_fixed_kernel<MB, UU><<<ctx->num_sms * MB, WK_WARPS * 32, 0, st>>>(                                              \
                     base_a, base_b, split, img_stride, rows, cols, stride, ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), \
                     ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, ts[c], c * per, std::min(per, batch - c * per),                   \
                     work_counter + 4 + c, work_counter + 4 + SURF_MAX_DESC_CHUNKS + c, lpt_split, big_flag, fb_list, fb_count, ws.img_off)
-                static const int minb = getenv("VFSMS_DESC_MINB") ? atoi(getenv("VFSMS_DESC_MINB")) : DESC_FIXED_MINB;   // measurement aid
-                if (minb == 2) LAUNCH_FIXED(2); else if (minb == 4) LAUNCH_FIXED(4); else LAUNCH_FIXED(DESC_FIXED_MINB);
+                // (3 CTAs per SM, 4 gathers in flight: measured against 2 / 4 CTAs and 2 / 6 / 8 gathers, profiles/r02)
+                LAUNCH_FIXED(DESC_FIXED_MINB, DESC_FIXED_U);
 #undef LAUNCH_FIXED
                 LAUNCH_CHECK(ctx);
             }

@@ -32,6 +32,7 @@
 #define DESC_BUF 1024             // floats of row storage per warp: one chunk of sampled rows (fixed kernel), one row (reference kernel)
 #define DESC_SLOTS 32             // warp-rounds per chunk
 #define DESC_FIXED_MINB 3          // CTAs per SM the fixed kernel's register budget is cut for
+#define DESC_FIXED_U 4             // gathers in flight per lane
 
 // bilinear / clamped sample of the rotated window, rounded to u8 exactly like the CPU loop (reference sampler)
 __device__ __forceinline__ int window_pixel(const uint8_t *__restrict__ img, int stride, int ncols1, int nrows1,
@@ -230,7 +231,8 @@ __device__ __forceinline__ void patch_to_descriptor(DescScratch &S, int lane, in
 // output row dy is the same entry (square window, one scale).  Per chunk:
 //   horizontal pass: the (row, column) pairs of the chunk are spread over ALL 32 lanes; each sums its taps in table order and the row
 //       sum replaces element `column` of its row in place (a column's taps lie right of every column index written before it);
-//   vertical pass: lane dx < 21 folds the row sums of column dx into `sum` with the row weights, emitting patch rows as they complete.
+//   vertical pass: lane dx < 21 folds the row sums of column dx into `sum` with the row weights, emitting patch rows as they complete
+//       (spreading the (output row, column) pairs over all lanes was measured: slower, the per-item set-up outweighs the idle lanes).
 // Integer scales (OpenCV's box-sum fast path) and win == 21 use the same passes with unit weights and their own rounding at the end.
 struct __align__(16) AreaCol {                  // nf = n | flags << 16; flags: 1 = left edge tap, 2 = right edge tap
     int sx1, nf, ya, yb;                        // ya / yb: first / last source row of output row c (the entry read as a row table)
@@ -418,19 +420,19 @@ __device__ __forceinline__ float bilinear_scaled(const float4 g, float A, float 
     return (v + 12582912.0f) - 12582912.0f;          // cvRound, ties to even, as an exact float
 }
 
-// Four warp-rounds of a chunk: the gathers are issued before the first is consumed.  slot: their entries of the slot table, out: this
+// U warp-rounds of a chunk: the U gathers are issued before the first is consumed.  slot: their entries of the slot table, out: this
 // lane's element of the first round's row buffer, mxc / myc: this lane's column offset inside a round times the per-column step.
 // CHECK: some sample of these rounds may lie outside the image -- such samples take the CPU's clamped nearest pixel.
 // FINE: 16.48 instead of 32.32 fixed point; the fraction then takes the slow 64-bit conversion.
-template <bool CHECK, bool FINE>
+template <bool CHECK, bool FINE, int U>
 __device__ __forceinline__ void sample_rounds(const ulonglong2 *__restrict__ slot, float *__restrict__ out, const cudaTextureObject_t tex,
                                               unsigned long long mxc, unsigned long long myc, const uint8_t *__restrict__ img, int stride,
                                               int ncols1, int nrows1, int row_off)
 {
     constexpr unsigned long long FMASK = (1ULL << 48) - 1, FHALF = 1ULL << 47;
-    float4 g[4]; float A[4], B[4]; unsigned oob = 0;
+    float4 g[U]; float A[U], B[U]; unsigned oob = 0;
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < U; u++) {
         const ulonglong2 e = slot[u];
         const unsigned long long X = e.x + mxc, Y = e.y + myc;
         int ix1, iy1;
@@ -446,7 +448,7 @@ __device__ __forceinline__ void sample_rounds(const ulonglong2 *__restrict__ slo
         if (CHECK && !((unsigned)(ix1 - 1) < (unsigned)ncols1 && (unsigned)(iy1 - 1 - row_off) < (unsigned)nrows1)) oob |= 1u << u;
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < U; u++) {
         float v = bilinear_scaled(g[u], A[u], B[u]);
         if (CHECK && (oob >> u & 1)) {
             // outside the image: the CPU takes the clamped nearest pixel, cvRound(pixel) = ties to even
@@ -471,9 +473,10 @@ __device__ __forceinline__ void sample_rounds(const ulonglong2 *__restrict__ slo
     }
 }
 
-// Samples the warp-rounds [0, Q4) of the chunk described by S.slot into S.buf, round q at buf[32 q + lane].  need: bit q set when
-// round q may hold a sample outside the image (0 for windows that lie inside it); groups of four rounds without such a bit skip the test.
-template <bool FINE>
+// Samples the warp-rounds [0, Q4) of the chunk described by S.slot into S.buf, round q at buf[32 q + lane] (Q4: Q rounded up to a
+// multiple of U, the padding rounds repeat the last one).  need: bit q set when round q may hold a sample outside the image (0 for
+// windows that lie inside it); groups of U rounds without such a bit skip the test.
+template <bool FINE, int U>
 __device__ __forceinline__ void sample_chunk(DescScratch &S, const cudaTextureObject_t tex, int Q4, unsigned need, unsigned long long mxc,
                                              unsigned long long myc, int lane, const uint8_t *__restrict__ img, int stride,
                                              int ncols1, int nrows1, int row_off)
@@ -481,15 +484,15 @@ __device__ __forceinline__ void sample_chunk(DescScratch &S, const cudaTextureOb
     const ulonglong2 *slot = (const ulonglong2 *)S.slot;
     float *out = S.buf + lane;
 #pragma unroll 1
-    for (int q0 = 0; q0 < Q4; q0 += 4, slot += 4, out += 128, need >>= 4) {
-        if (need & 15u) sample_rounds<true, FINE>(slot, out, tex, mxc, myc, img, stride, ncols1, nrows1, row_off);
-        else sample_rounds<false, FINE>(slot, out, tex, mxc, myc, img, stride, ncols1, nrows1, row_off);
+    for (int q0 = 0; q0 < Q4; q0 += U, slot += U, out += 32 * U, need >>= U) {
+        if (need & ((1u << U) - 1)) sample_rounds<true, FINE, U>(slot, out, tex, mxc, myc, img, stride, ncols1, nrows1, row_off);
+        else sample_rounds<false, FINE, U>(slot, out, tex, mxc, myc, img, stride, ncols1, nrows1, row_off);
     }
 }
 
 // The window of one keypoint -> S.patch.  false: a row start is not a multiple of one fixed-point unit (FINE = false: the caller
 // retries in 16.48; FINE = true: the reference kernel's).  cU / sU: |cos_dir|, |sin_dir| in fixed-point units.
-template <bool FINE>
+template <bool FINE, int U>
 __device__ bool window_to_patch(DescScratch &S, const cudaTextureObject_t tex, int lane, int win, float cx, float cy,
                                                 float sin_dir, float cos_dir, unsigned long long cU, unsigned long long sU, bool interior,
                                                 const uint8_t *__restrict__ img, int stride, int ncols1, int nrows1, int row_off)
@@ -553,8 +556,8 @@ __device__ bool window_to_patch(DescScratch &S, const cudaTextureObject_t tex, i
             }
         }
         __syncwarp();
-        const int Q4 = (Q + 3) & ~3;
-        sample_chunk<FINE>(S, tex, Q4, need, mxc, myc, lane, img, stride, ncols1, nrows1, row_off);
+        const int Q4 = (Q + U - 1) / U * U;
+        sample_chunk<FINE, U>(S, tex, Q4, need, mxc, myc, lane, img, stride, ncols1, nrows1, row_off);
         __syncwarp();
         // ---- fold the chunk's rows into the patch
         F.rows(S, kpr * 32, r0, Rc, lane);
@@ -563,7 +566,7 @@ __device__ bool window_to_patch(DescScratch &S, const cudaTextureObject_t tex, i
     return F.done();
 }
 
-template <int MINB>
+template <int MINB, int U>
 __global__ void __launch_bounds__(WK_WARPS * 32, MINB) describe_fixed_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
     const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
@@ -620,10 +623,10 @@ __global__ void __launch_bounds__(WK_WARPS * 32, MINB) describe_fixed_kernel(
 
         bool described = false;
         if (ok32)
-            described = window_to_patch<false>(S, tex, lane, win, cx, cy, sin_dir, cos_dir, (unsigned long long)(unsigned)(ac * 4294967296.0f),
+            described = window_to_patch<false, U>(S, tex, lane, win, cx, cy, sin_dir, cos_dir, (unsigned long long)(unsigned)(ac * 4294967296.0f),
                                                (unsigned long long)(unsigned)(as * 4294967296.0f), interior, img, stride, ncols1, nrows1, row_off);
         if (!described && ok48)      // the direction needs the finer unit, or a row of the first attempt started within 2^-9 of an axis
-            described = window_to_patch<true>(S, tex, lane, win, cx, cy, sin_dir, cos_dir, (unsigned long long)((double)ac * 281474976710656.0),
+            described = window_to_patch<true, 2>(S, tex, lane, win, cx, cy, sin_dir, cos_dir, (unsigned long long)((double)ac * 281474976710656.0),
                                               (unsigned long long)((double)as * 281474976710656.0), interior, img, stride, ncols1, nrows1, row_off);
         if (!described) {                            // hand over to the reference kernel (it repeats the orientation)
             if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = item;

@@ -27,8 +27,13 @@
 #define ORI_SAMPLES 113
 #define MAX_WIN 2048
 
-#define HT_X 64          // Hessian tile (samples)
+#define HT_X 64          // Hessian tile (samples) of every octave but 1
 #define HT_Y 16
+#define HT1_X 32         // octave 1: its staged footprint (step 2) is 4 x larger per sample; 32 x 16 keeps 3 CTAs on an SM instead of 2
+                         // (measured per 32-pair step: 64 x 16 1.46 ms, 32 x 16 1.36 ms, 32 x 8 1.59 ms)
+#define HT1_Y 16
+__host__ __device__ constexpr int ht_x(int o) { return o == 1 ? HT1_X : HT_X; }
+__host__ __device__ constexpr int ht_y(int o) { return o == 1 ? HT1_Y : HT_Y; }
 #define HT_THREADS 256
 #define INT_BAND 32      // integral band height
 #define INT_SUB 8        // rows staged per sub-step (one warp per row)
@@ -120,11 +125,11 @@ int surf_build_plan(SurfPlan *plan, int rows, int cols, const vfsms_surf_params 
                 off_max = std::max(off_max, -L.margin * step + L.size);
             }
             plan->stage_off_min[o] = off_min;
-            plan->stage_rows[o] = (HT_Y + 1) * step + (off_max - off_min) + 1;
-            plan->stage_cols[o] = (HT_X + 1) * step + (off_max - off_min) + 1;
+            plan->stage_rows[o] = (ht_y(o) + 1) * step + (off_max - off_min) + 1;
+            plan->stage_cols[o] = (ht_x(o) + 1) * step + (off_max - off_min) + 1;
         }
         // NMS positions exist only inside [margin_min, l - margin_min): skip tiles that cannot hold a maximum
-        int tx = ceil_div(lcols > 0 ? lcols : 1, HT_X), ty = ceil_div(lrows > 0 ? lrows : 1, HT_Y);
+        int tx = ceil_div(lcols > 0 ? lcols : 1, ht_x(o)), ty = ceil_div(lrows > 0 ? lrows : 1, ht_y(o));
         if (lrows < 3 || lcols < 3) { tx = 0; ty = 0; }
         plan->tiles_x[o] = tx;
         plan->tile_begin[o] = tiles;
@@ -356,19 +361,15 @@ template <int OCT, int L>
 __device__ __forceinline__ void det_layer_fixed(const SurfPlan &plan, const int32_t *s_int, float *s_det, int i0, int j0, int r_base, int c_base)
 {
     using T = HessFixed<OCT, L>;
-    constexpr int step = 1 << OCT, SW = HT_X + 2, SH = HT_Y + 2, RW = T::pitch;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int step = 1 << OCT, SW = ht_x(OCT) + 2, SH = ht_y(OCT) + 2, RW = T::pitch;
     const int ni = plan.layer[OCT][L].samples_i, nj = plan.layer[OCT][L].samples_j;
-    for (int ly = warp; ly < SH; ly += HT_THREADS / 32) {
-        const int si = i0 + ly - T::margin;
-        const bool row_ok = si >= 0 && si < ni;
-        const int32_t *row = s_int + (si * step - r_base) * RW - c_base;
-        for (int lx = lane; lx < SW; lx += 32) {
-            const int sj = j0 + lx - T::margin;
-            float det = 0.f;
-            if (row_ok && sj >= 0 && sj < nj) det = det_fixed<OCT, L>(row + sj * step);
-            s_det[(L * SH + ly) * SW + lx] = det;
-        }
+    // the haloed tile flattened over the CTA: (66 x 18 samples as rows per warp and columns per lane left a third of the lane slots idle)
+    for (int idx = threadIdx.x; idx < SH * SW; idx += HT_THREADS) {
+        const int ly = idx / SW, lx = idx - ly * SW;
+        const int si = i0 + ly - T::margin, sj = j0 + lx - T::margin;
+        float det = 0.f;
+        if (si >= 0 && si < ni && sj >= 0 && sj < nj) det = det_fixed<OCT, L>(s_int + (si * step - r_base) * RW - c_base + sj * step);
+        s_det[L * SH * SW + idx] = det;
     }
 }
 
@@ -390,10 +391,10 @@ __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_co
     const int W = plan.cols + 1;
     const int32_t *I = integral + (size_t)b * (plan.rows + 1) * W;
     const int nl = plan.n_layers;
-    constexpr int SW = HT_X + 2, SH = HT_Y + 2;
-    float *s_det = s_dyn;                                   // [n_layers][HT_Y+2][HT_X+2]
+    constexpr int TX = ht_x(OCT), TY = ht_y(OCT), SW = TX + 2, SH = TY + 2;
+    float *s_det = s_dyn;                                   // [n_layers][TY+2][TX+2]
     int32_t *s_int = (int32_t *)(s_dyn + nl * SW * SH);     // [stage_rows][stage_cols] (STAGE only)
-    const int i0 = tile_y * HT_Y - 1, j0 = tile_x * HT_X - 1;   // layer coords of the smem origin
+    const int i0 = tile_y * TY - 1, j0 = tile_x * TX - 1;   // layer coords of the smem origin
     const int RW = plan.stage_cols[o];
     const int r_base = i0 * step + plan.stage_off_min[o], c_base = j0 * step + plan.stage_off_min[o];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -417,10 +418,10 @@ __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_co
         det_layer_fixed<OCT < 2 ? OCT : 0, 3>(plan, s_int, s_det, i0, j0, r_base, c_base);
         det_layer_fixed<OCT < 2 ? OCT : 0, 4>(plan, s_int, s_det, i0, j0, r_base, c_base);
     } else
-    for (int ly = warp; ly < SH; ly += HT_THREADS / 32) {
-        const int li = i0 + ly;
-        for (int lx = lane; lx < SW; lx += 32) {
-            const int lj = j0 + lx;
+    for (int idx = threadIdx.x; idx < SH * SW; idx += HT_THREADS) {           // the haloed tile flattened over the CTA
+        const int ly = idx / SW, lx = idx - ly * SW;
+        const int li = i0 + ly, lj = j0 + lx;
+        {
 #pragma unroll
             for (int l = 0; l < VFSMS_MAX_LAYERS_PER_OCTAVE; l++) {
                 if (l < nl) {
@@ -443,9 +444,9 @@ __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_co
     __syncthreads();
 
     // phase 2: 3x3x3 non-maximum suppression on the middle layers, interpolation, candidate push
-    for (int idx = threadIdx.x; idx < HT_X * HT_Y; idx += HT_THREADS) {
-        const int ty = idx / HT_X, tx = idx - ty * HT_X;
-        const int li = tile_y * HT_Y + ty, lj = tile_x * HT_X + tx;
+    for (int idx = threadIdx.x; idx < TX * TY; idx += HT_THREADS) {
+        const int ty = idx / TX, tx = idx - ty * TX;
+        const int li = tile_y * TY + ty, lj = tile_x * TX + tx;
         if (li >= lrows || lj >= lcols) continue;
         for (int l = 1; l < nl - 1; l++) {
             const float *c1 = s_det + (l * SH + ty + 1) * SW + tx + 1;
@@ -1251,12 +1252,12 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
     const int total_tiles = plan.tile_begin[plan.n_octaves];
     if (total_tiles > 0) {
         StageTimer t_h(ctx, st, VFSMS_STAGE_HESSIAN);
-        const size_t smem_det = (size_t)plan.n_layers * (HT_X + 2) * (HT_Y + 2) * 4;
+        auto smem_det_of = [&](int o) { return (size_t)plan.n_layers * (ht_x(o) + 2) * (ht_y(o) + 2) * 4; };
         // octaves whose integral footprint fits in shared memory next to the det tile (two CTAs per SM)
         int o_split = 0;
         static const bool no_stage = getenv("VFSMS_HESSIAN_UNSTAGED") != nullptr;     // debugging aid
         while (!no_stage && o_split < plan.n_octaves &&
-               smem_det + (size_t)plan.stage_rows[o_split] * plan.stage_cols[o_split] * 4 <= 110 * 1024) o_split++;
+               smem_det_of(o_split) + (size_t)plan.stage_rows[o_split] * plan.stage_cols[o_split] * 4 <= 110 * 1024) o_split++;
         if (o_split > 2) o_split = 2;                  // staged kernels are instantiated for octaves 0 and 1
         // corner offsets combined with the pitch each octave's kernel reads from
         for (int o = 0; o < plan.n_octaves; o++) {
@@ -1300,7 +1301,7 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
             const int nt = plan.tile_begin[o + 1] - plan.tile_begin[o];
             if (nt <= 0) continue;
             const bool staged = o < o_split;
-            const size_t sm = smem_det + (staged ? (size_t)plan.stage_rows[o] * plan.stage_cols[o] * 4 : 0);
+            const size_t sm = smem_det_of(o) + (staged ? (size_t)plan.stage_rows[o] * plan.stage_cols[o] * 4 : 0);
             const dim3 grid(nt, batch);
 #define HL(S, O) hessian_nms_kernel<S, O><<<grid, HT_THREADS, sm, st>>>(plan, ws.integral.as<int32_t>(), ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap)
             switch (o) {
@@ -1391,12 +1392,15 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
             for (int c = 0; c < n_chunks && fixed; c++)
                 fixed = surf_stack_texture(ctx, c * per, std::min(per, batch - c * per), rows, cols, ws.pitch_f, st, &ts[c]);
             for (int c = 0; c < n_chunks && fixed; c++) {
-#define LAUNCH_FIXED(MB, UU) describe_fixed_kernel<MB, UU><<<ctx->num_sms * MB, WK_WARPS * 32, 0, st>>>(                                              \
+#define LAUNCH_FIXED(MB, UU, NW) describe_fixed_kernel<MB, UU, NW><<<ctx->num_sms * MB, NW * 32, 0, st>>>(                                              \
                     base_a, base_b, split, img_stride, rows, cols, stride, ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), \
                     ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, ts[c], c * per, std::min(per, batch - c * per),                   \
                     work_counter + 4 + c, work_counter + 4 + SURF_MAX_DESC_CHUNKS + c, lpt_split, big_flag, fb_list, fb_count, ws.img_off)
                 // (3 CTAs per SM, 4 gathers in flight: measured against 2 / 4 CTAs and 2 / 6 / 8 gathers, profiles/r02)
-                LAUNCH_FIXED(DESC_FIXED_MINB, DESC_FIXED_U);
+                {
+                    // (8 warps per CTA, 3 CTAs per SM: 4-warp CTAs at 6 / 7 per SM and 2-warp CTAs at 14 measured no better)
+                    LAUNCH_FIXED(DESC_FIXED_MINB, DESC_FIXED_U, WK_WARPS);
+                }
 #undef LAUNCH_FIXED
                 LAUNCH_CHECK(ctx);
             }

@@ -566,15 +566,15 @@ __device__ bool window_to_patch(DescScratch &S, const cudaTextureObject_t tex, i
     return F.done();
 }
 
-template <int MINB, int U>
-__global__ void __launch_bounds__(WK_WARPS * 32, MINB) describe_fixed_kernel(
+template <int MINB, int U, int NW>
+__global__ void __launch_bounds__(NW * 32, MINB) describe_fixed_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
     const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
     int batch, int kp_cap, int extended, const cudaTextureObject_t tex, int b_first, int b_count,
     int *work_counter, int *work_counter_large, int lpt_split, int *big_flag, int *fb_list, int *fb_count,
     const int64_t *__restrict__ img_off)
 {
-    __shared__ DescScratch s_ws[WK_WARPS];
+    __shared__ DescScratch s_ws[NW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     DescScratch &S = s_ws[warp];
     const int total = prefix[b_first + b_count];

@@ -53,29 +53,37 @@ __device__ __forceinline__ bool px_nonempty(const int16_t *p, int ch)
     return (int)p[0] + (int)p[1] + (int)p[2] != -3;
 }
 
-// A: rows x cols x ch int16 with row stride a_rs (elements).
+// A: rows x cols x ch int16 with row stride a_rs (elements).  grid (ceil(cols / 256), ceil(rows / STATS_ROWS)): a thread walks
+// STATS_ROWS rows of ONE column (coalesced across the warp), so the first / last non-empty row of the column costs one atomic per
+// thread instead of two per pixel (a 2048^2 corner ROI made 8 M contended atomics).
+#define STATS_ROWS 32
 __global__ void __launch_bounds__(256) blend_stats_kernel(const int16_t *__restrict__ A, int64_t a_rs, int rows, int cols, int ch,
                                                           BlendPlan *plan, int *col_top, int *col_bot)
 {
     long long cv = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-    const int64_t total = (int64_t)rows * cols;
     const int hr = rows / 2, hc = cols / 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
-        const int16_t *p = A + r * a_rs + (int64_t)c * ch;
-        int pos = 0, valid = 0;
-        for (int k = 0; k < ch; k++) { pos += p[k] > 0; valid += p[k] > -1; }
-        cv += valid;
-        if (r < hr) { if (c < hc) q0 += pos; else q3 += pos; }
-        else { if (c < hc) q1 += pos; else q2 += pos; }
-        if (px_nonempty(p, ch)) { atomicMin(&col_top[c], r); atomicMax(&col_bot[c], r); }
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r_begin = blockIdx.y * STATS_ROWS, r_end = min(rows, r_begin + STATS_ROWS);
+    if (c < cols) {
+        int top = rows, bot = -1;
+#pragma unroll 8
+        for (int r = r_begin; r < r_end; r++) {
+            const int16_t *p = A + r * a_rs + (int64_t)c * ch;
+            int pos = 0, valid = 0;
+            for (int k = 0; k < ch; k++) { pos += p[k] > 0; valid += p[k] > -1; }
+            cv += valid;
+            if (r < hr) { if (c < hc) q0 += pos; else q3 += pos; }
+            else { if (c < hc) q1 += pos; else q2 += pos; }
+            if (px_nonempty(p, ch)) { top = min(top, r); bot = r; }
+        }
+        if (bot >= 0) { atomicMin(&col_top[c], top); atomicMax(&col_bot[c], bot); }
     }
     for (int o = 16; o; o >>= 1) {
         cv += __shfl_xor_sync(0xffffffffu, cv, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
         q1 += __shfl_xor_sync(0xffffffffu, q1, o); q2 += __shfl_xor_sync(0xffffffffu, q2, o);
         q3 += __shfl_xor_sync(0xffffffffu, q3, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if ((threadIdx.x & 31) == 0 && (cv | q0 | q1 | q2 | q3)) {
         atomicAdd((unsigned long long *)&plan->count_valid, (unsigned long long)cv);
         atomicAdd((unsigned long long *)&plan->quad[0], (unsigned long long)q0);
         atomicAdd((unsigned long long *)&plan->quad[1], (unsigned long long)q1);
@@ -95,49 +103,50 @@ __global__ void __launch_bounds__(256) blend_plan_kernel(const int16_t *__restri
                                                          BlendPlan *plan, const int *__restrict__ col_top, const int *__restrict__ col_bot,
                                                          float *w1, float *w2, int force_corner)
 {
-    __shared__ int s_ri_start, s_ri, s_ci_start, s_ci, s_index, s_corner;
+    __shared__ int s_ri_start, s_ri, s_ci_start, s_ci, s_index, s_corner, s_red[8];
     const int row = rows, col = cols;
+    // block-wide max of v (v >= -1; the scans below look for the first hit in ascending order as a max of -index)
+    auto block_max = [&](int v) {
+        for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        int m = s_red[0];
+        for (int k = 1; k < (int)(blockDim.x >> 5); k++) m = max(m, s_red[k]);
+        return m;
+    };
     if (threadIdx.x == 0) {
         const double ratio = (double)plan->count_valid / ((double)rows * cols * ch);
-        int corner = force_corner || !(ratio > 0.65);
         int index = 0;
         { long long best = plan->quad[0]; for (int k = 1; k < 4; k++) if (plan->quad[k] < best) { best = plan->quad[k]; index = k; } }
-        int rowIndex = 0, colIndex = 0;
-        if (corner) {
-            if (index == 2) {                                         // ImageFusion.py:63-90
-                for (int j = 1; j < col; j++) {
-                    const int c = col - j;
-                    if (col_bot[c] >= 0) rowIndex = col_bot[c] + 1;
-                    if (rowIndex != 0) break;
-                }
-                const int16_t *rp = A + py_index(rowIndex, row) * a_rs;
-                for (int i = col - 1; i >= 0; i--) if (px_nonempty(rp + (int64_t)i * ch, ch)) { colIndex = i + 1; break; }
-            } else if (index == 3) {                                  // ImageFusion.py:92-120
-                for (int j = 1; j < col; j++) {
-                    const int c = col - j;
-                    if (col_top[c] < row) rowIndex = col_top[c] - 1;
-                    if (rowIndex != 0) break;
-                }
-                const int16_t *rp = A + py_index(rowIndex, row) * a_rs;
-                for (int i = col - 1; i >= 0; i--) if (px_nonempty(rp + (int64_t)i * ch, ch)) { colIndex = i + 1; break; }
-            } else if (index == 0) {                                  // ImageFusion.py:122-152
-                for (int j = 0; j < col; j++) {
-                    if (col_top[j] < row) rowIndex = col_top[j] - 1;
-                    if (rowIndex != 0) break;
-                }
-                const int16_t *rp = A + py_index(rowIndex, row) * a_rs;
-                for (int i = 0; i < col; i++) if (px_nonempty(rp + (int64_t)i * ch, ch)) { colIndex = i - 1; break; }
-            } else {                                                  // index == 1, ImageFusion.py:154-186
-                for (int j = 0; j < col; j++) {
-                    if (col_bot[j] >= 0) rowIndex = col_bot[j] + 1;
-                    if (rowIndex != 0) break;
-                }
-                const int16_t *rp = A + py_index(rowIndex, row) * a_rs;
-                for (int i = 0; i < col; i++) if (px_nonempty(rp + (int64_t)i * ch, ch)) { colIndex = i - 1; break; }
-            }
+        s_corner = force_corner || !(ratio > 0.65);
+        s_index = index;
+    }
+    __syncthreads();
+    const int corner = s_corner, idx = s_index;
+    int rowIndex = 0, colIndex = 0;
+    if (corner) {
+        // The reference scans the columns for the first one with data (ImageFusion.py:63-90 / 92-120 / 122-152 / 154-186): cases 2, 3
+        // from the right (columns col-1 .. 1), cases 0, 1 from the left; cases 2, 1 take rowIndex = last non-empty row + 1, cases
+        // 3, 0 take first non-empty row - 1 and KEEP SCANNING when that is 0 (first row == 1).  The whole CTA looks for that column.
+        const bool from_right = idx == 2 || idx == 3, use_bot = idx == 2 || idx == 1;
+        int best = -0x7fffffff;
+        for (int c = threadIdx.x + (from_right ? 1 : 0); c < col; c += blockDim.x) {
+            const bool ok = use_bot ? col_bot[c] >= 0 : (col_top[c] < row && col_top[c] != 1);
+            if (ok) best = max(best, from_right ? c : -c);
         }
-        plan->corner = corner; plan->index = index; plan->row_index = rowIndex; plan->col_index = colIndex;
-        s_corner = corner; s_index = index;
+        best = block_max(best);
+        if (best != -0x7fffffff) { const int c = from_right ? best : -best; rowIndex = use_bot ? col_bot[c] + 1 : col_top[c] - 1; }
+        // then the row rowIndex (python indexing) for its last (cases 2, 3) / first (cases 0, 1) non-empty pixel
+        const int16_t *rp = A + py_index(rowIndex, row) * a_rs;
+        best = -0x7fffffff;
+        for (int i = threadIdx.x; i < col; i += blockDim.x)
+            if (px_nonempty(rp + (int64_t)i * ch, ch)) best = max(best, from_right ? i : -i);
+        best = block_max(best);
+        if (best != -0x7fffffff) colIndex = from_right ? best + 1 : -best - 1;
+    }
+    if (threadIdx.x == 0) {
+        plan->corner = corner; plan->index = idx; plan->row_index = rowIndex; plan->col_index = colIndex;
         s_ri_start = rowIndex; s_ci_start = colIndex;
         // "if rowIndex == 0: rowIndex = 1" happens inside the assignment loops (first iteration), ImageFusion.py:85-90 etc.
         s_ri = rowIndex == 0 ? 1 : rowIndex;
@@ -306,7 +315,8 @@ static int fuse_roi_dev(vfsms_ctx *ctx, const int16_t *A, int64_t a_rs, const in
         fill_i32_kernel<<<grid_for(ctx, cols), 256, 0, st>>>(bs->col_top.as<int>(), cols, rows);     // "none" = rows
         LAUNCH_CHECK(ctx);
         CUDA_TRY(cudaMemsetAsync(bs->col_bot.p, 0xff, (size_t)cols * 4, st));                        // "none" = -1
-        blend_stats_kernel<<<grid_for(ctx, n), 256, 0, st>>>(A, a_rs, rows, cols, ch, bs->plan.as<BlendPlan>(), bs->col_top.as<int>(), bs->col_bot.as<int>());
+        blend_stats_kernel<<<dim3(ceil_div(cols, 256), ceil_div(rows, STATS_ROWS)), 256, 0, st>>>(A, a_rs, rows, cols, ch, bs->plan.as<BlendPlan>(),
+                                                                                                     bs->col_top.as<int>(), bs->col_bot.as<int>());
         LAUNCH_CHECK(ctx);
         blend_plan_kernel<<<1, 256, 0, st>>>(A, a_rs, rows, cols, ch, bs->plan.as<BlendPlan>(), bs->col_top.as<int>(), bs->col_bot.as<int>(),
                                              bs->w1.as<float>(), bs->w2.as<float>(), force_corner);

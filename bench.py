@@ -514,7 +514,7 @@ def main():
     ap.add_argument("--batches", type=int, default=3, help="distinct input batches rotated through (L2 hygiene)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the c4 / phase / mosaic blocks (profiling runs)")
-    ap.add_argument("--matcher", default=None, choices=["tc", "tc_1sm", "simt"], help="override the descriptor matcher kernel")
+    ap.add_argument("--matcher", default=None, choices=["tc", "tc_1sm", "simt", "tc_bf16x3", "tc_f16x2", "tc_f16x1"], help="override the descriptor matcher kernel")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="kernel-schedule switch (include/vfsms.h VFSMS_OPT_*, e.g. describe=0, lpt=1); identical results, A/B timing.  Without it the "
                          "bench times the library's default schedule, the one the oracle tests run on")

@@ -32,7 +32,7 @@ EXPORTS = [
     "vfsms_orb_detect_and_describe", "vfsms_offset_by_mode", "vfsms_align_batch_host", "vfsms_align_batch_dev",
     "vfsms_match_batch_dev", "vfsms_phase_correlate_host", "vfsms_phase_correlate_dev", "vfsms_fuse_roi_host",
     "vfsms_mosaic_host", "vfsms_profile_enable", "vfsms_profile_read", "vfsms_stage_name",
-    "vfsms_set_matcher", "vfsms_last_match_fallbacks", "vfsms_last_describe_handovers", "vfsms_enhance_host",
+    "vfsms_set_matcher", "vfsms_last_match_fallbacks", "vfsms_last_match_bound_violations", "vfsms_last_describe_handovers", "vfsms_enhance_host",
     "vfsms_jpeg_info", "vfsms_jpeg_luma_coefficients", "vfsms_jpeg_decode_gray_dev", "vfsms_jpeg_decode_gray_host",
     "vfsms_jpeg_component_coefficients", "vfsms_jpeg_decode_bgr_dev", "vfsms_jpeg_decode_bgr_host",
     "vfsms_tiles_reserve", "vfsms_tiles_decode_jpeg", "vfsms_tiles_upload", "vfsms_tiles_download", "vfsms_tiles_ptr",
@@ -89,6 +89,7 @@ def load():
     L.vfsms_jpeg_encode_dev.argtypes = [vp, vp, i32, i32, i32, i64, i32, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), vp]
     L.vfsms_set_matcher.argtypes = [vp, i32]
     L.vfsms_last_match_fallbacks.argtypes = [vp, ctypes.POINTER(i32)]
+    L.vfsms_last_match_bound_violations.argtypes = [vp, ctypes.POINTER(i32)]
     L.vfsms_last_describe_handovers.argtypes = [vp, ctypes.POINTER(i32)]
     L.vfsms_set_option.argtypes = [vp, i32, i32]
     L.vfsms_get_option.argtypes = [vp, i32, ctypes.POINTER(i32)]

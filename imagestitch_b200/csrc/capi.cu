@@ -57,8 +57,9 @@ int vfsms_profile_read(vfsms_ctx *ctx, float *ms_out, int32_t *calls_out, int re
 
 int vfsms_set_matcher(vfsms_ctx *ctx, int mode)
 {
-    if (!ctx || mode < 0 || mode > 2) { vfsms_set_error("vfsms_set_matcher: bad arguments"); return VFSMS_E_ARG; }
-    ctx->matcher_mode = mode;
+    if (!ctx || mode < 0 || mode > 5) { vfsms_set_error("vfsms_set_matcher: bad arguments"); return VFSMS_E_ARG; }
+    ctx->matcher_mode = mode >= 3 ? 0 : mode;
+    ctx->match_terms = mode >= 3 ? 6 - mode : MATCH_TERMS_DEFAULT;      // 3 -> split-bf16, 4 -> fp16 two terms, 5 -> fp16 one term
     return 0;
 }
 static const char *const k_option_names[VFSMS_OPT_COUNT] = { "describe", "sort", "lpt", "entropy" };
@@ -119,6 +120,16 @@ int vfsms_last_match_fallbacks(vfsms_ctx *ctx, int *count_out)
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(count_out, ctx->last_fallback_count_dev, 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int vfsms_last_match_bound_violations(vfsms_ctx *ctx, int *count_out)
+{
+    if (!ctx || !count_out) return VFSMS_E_ARG;
+    *count_out = 0;
+    if (!ctx->last_fallback_count_dev) return 0;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(count_out, ctx->last_fallback_count_dev + 1, 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -261,8 +272,13 @@ int vfsms_match_descriptors(vfsms_ctx *ctx, const float *desc_a, int n_a, const 
         if ((rc = match_hamming_batch(ctx, ctx->scratch0.as<float>(), cn, 0, ctx->scratch1.as<float>(), cn + 1, 0, 1, cap, dim, 0, 0,
                                       mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(), st))) return rc;
     } else if (ctx->matcher_mode != 1 && dim % 32 == 0 && dim <= 128) {
-        if ((rc = match_tc_batch(ctx, ctx->scratch0.as<float>(), cn, 0, ctx->scratch1.as<float>(), cn + 1, 0, 1, cap, dim,
-                                 mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(), st))) return rc;
+        // descriptors of unknown scale (SIFT: values up to 255) take the split-bf16 operands: fp16 has no range for them
+        const int terms_saved = ctx->match_terms;
+        if (feature_type != 2) ctx->match_terms = 3;
+        rc = match_tc_batch(ctx, ctx->scratch0.as<float>(), cn, 0, ctx->scratch1.as<float>(), cn + 1, 0, 1, cap, dim,
+                            mw.best_idx.as<int32_t>(), mw.best_dist.as<float>(), st);
+        ctx->match_terms = terms_saved;
+        if (rc) return rc;
     } else {
         float *AT = ctx->scratch2.as<float>(), *BT = AT + (size_t)cap * dim;
         CUDA_TRY(cudaMemsetAsync(AT, 0, (size_t)cap * dim * 4 * 2, st));

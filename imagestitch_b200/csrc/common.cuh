@@ -134,6 +134,7 @@ struct MatchWorkspace {
 
 struct ProfPending { int stage; cudaEvent_t a, b; };
 
+#define MATCH_TERMS_DEFAULT 1
 struct vfsms_ctx {
     bool prof = false;
     std::vector<ProfPending> prof_pending;
@@ -141,7 +142,8 @@ struct vfsms_ctx {
     float prof_ms[VFSMS_STAGE_COUNT] = {0};
     int32_t prof_calls[VFSMS_STAGE_COUNT] = {0};
     int device = 0;
-    int matcher_mode = 0;          // 0: tcgen05 candidates + exact rescoring, 1: exact SIMT kernel
+    int matcher_mode = 0;          // 0: tcgen05 candidates + exact rescoring, 1: exact SIMT kernel, 2: 0 on single CTAs
+    int match_terms = MATCH_TERMS_DEFAULT;   // operand scheme of the tcgen05 matcher: 3 split-bf16, 2 fp16 + query split, 1 fp16
     int describe_mode = 1;         // window sampler of the SURF descriptor: 0 reference (double precision, u8 image), 1 fixed-point chunked texture sampler (default)
     int describe_lpt = 1;          // describe the large windows first (two passes over the work list): 0 off, 1 / 2 / 3 = split at 128 / 64 / 256 px
     int sort_mode = 1;             // KeypointGreater ordering: 0 rank by counting over all candidates, 1 rank inside response bins (default)

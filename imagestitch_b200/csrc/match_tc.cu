@@ -18,11 +18,12 @@
 //   3. rescore_kernel         exact fp32 distances (serial k order, no FMA: the CPU value) of the candidates, best two by
 //                             (distance, index), plus a guard: if the second best exact score is not separated from the
 //                             worst kept candidate by more than the split-bf16 error bound, the query is flagged ...
-//   4. fallback_exact_kernel  ... and rescanned exactly against every train row.  Results are therefore identical to the
+//   4. fallback_scan_kernel   ... and rescanned exactly against every train row (all flagged queries of a pair together).  Results are therefore identical to the
 //                             exact SIMT kernel (match.cu) by construction, not by luck.
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <float.h>
 
 #define TC_M 128
@@ -129,50 +130,87 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr)
     return d;
 }
 
-// instruction descriptor: D = f32, A = B = bf16, both K-major, N = 128, M = 128
-__device__ __forceinline__ uint32_t make_idesc()
+// instruction descriptor: D = f32, both operands K-major, N = 128, M = 128; `fmt` = TC_FMT_BF16 or TC_FMT_F16 (A and B format fields)
+#define TC_FMT_BF16 ((1u << 7) | (1u << 10))
+#define TC_FMT_F16 0u
+__device__ __forceinline__ uint32_t make_idesc(uint32_t fmt)
 {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    return (1u << 4) | fmt | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 }
 
-// ---------------------------------------------------------------- 1. split-bf16 operand rows
+// ---------------------------------------------------------------- 1. split operand rows
 // grid (ceil(cap/8), images), 256 threads: one warp per row.  side 0 = query layout, 1 = train layout.
+// terms 3: split-bf16 rows (header);  terms 2 / 1: fp16 rows
+//     query  [ a_hi | a_lo | 1, 1, 0 ... ]      resp.  [ a_hi | 1, 1, 0 ... ]
+//     train  [ B    | B    | nb_hi, nb_lo ... ] resp.  [ B    | nb_hi, nb_lo ... ]        B = fp16(-2 b)
+// `used` = terms * dim + 16 columns take part in the product; the row is padded to kprime (a multiple of 64) with zeros.
+// fp16 has no room for large values: a row whose squared norm exceeds TC_F16_NORM_MAX (or is not finite) raises the pair's
+// overflow flag and rescore_kernel hands every query of that pair to the exact rescan.
+#define TC_F16_NORM_MAX 1e4f
+#define TC_F16_PAD_NORM 60000.f      // fp16-representable, above every score a pair without the overflow flag can produce
 __global__ void __launch_bounds__(256) prep_split_kernel(const float *__restrict__ desc, const int32_t *n_ptr, int n_stride,
-                                                         int cap, int dim, int kprime, int side, int img0,
-                                                         __nv_bfloat16 *out, float *norms)
+                                                         int cap, int dim, int kprime, int terms, int side, int img0,
+                                                         uint16_t *out, float *norms, float *errs, int32_t *ovf)
 {
     const int b = blockIdx.y;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= cap) return;
     const int n = n_ptr[(size_t)(img0 + b) * n_stride];
     const float *src = desc + ((size_t)(img0 + b) * cap + row) * dim;
-    __nv_bfloat16 *dst = out + ((size_t)b * cap + row) * kprime;
+    uint16_t *dst = out + ((size_t)b * cap + row) * kprime;
     const bool valid = row < n;
-    float nrm = 0.f;
+    const bool f16 = terms < 3;
+    float nrm = 0.f, er = 0.f;      // er: squared norm of what the stored operand row lost (fp16 schemes; both differences are exact)
     for (int k = lane; k < dim; k += 32) {
         const float v = valid ? src[k] : 0.f;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
         nrm += v * v;
-        if (side == 0) { dst[k] = hi; dst[dim + k] = hi; dst[2 * dim + k] = lo; }
-        else {
-            const __nv_bfloat16 mhi = __float2bfloat16_rn(-2.f * __bfloat162float(hi)), mlo = __float2bfloat16_rn(-2.f * __bfloat162float(lo));
-            dst[k] = mhi; dst[dim + k] = mlo; dst[2 * dim + k] = mhi;
+        if (f16) {
+            if (side == 0) {
+                const __half hi = __float2half_rn(v);
+                float e = v - __half2float(hi);
+                dst[k] = __half_as_ushort(hi);
+                if (terms == 2) {
+                    const __half lo = __float2half_rn(e);
+                    dst[dim + k] = __half_as_ushort(lo);
+                    e -= __half2float(lo);
+                }
+                er += e * e;
+            } else {
+                const __half m = __float2half_rn(-2.f * v);
+                const float e = __half2float(m) + 2.f * v;
+                dst[k] = __half_as_ushort(m);
+                if (terms == 2) dst[dim + k] = __half_as_ushort(m);
+                er += e * e;
+            }
+        } else {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+            if (side == 0) { dst[k] = __bfloat16_as_ushort(hi); dst[dim + k] = __bfloat16_as_ushort(hi); dst[2 * dim + k] = __bfloat16_as_ushort(lo); }
+            else {
+                const uint16_t mhi = __bfloat16_as_ushort(__float2bfloat16_rn(-2.f * __bfloat162float(hi)));
+                const uint16_t mlo = __bfloat16_as_ushort(__float2bfloat16_rn(-2.f * __bfloat162float(lo)));
+                dst[k] = mhi; dst[dim + k] = mlo; dst[2 * dim + k] = mhi;
+            }
         }
     }
-    for (int o = 16; o; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
-    for (int k = 3 * dim + lane; k < kprime; k += 32) {
+    for (int o = 16; o; o >>= 1) { nrm += __shfl_xor_sync(0xffffffffu, nrm, o); er += __shfl_xor_sync(0xffffffffu, er, o); }
+    if (f16 && valid && lane == 0 && !(nrm <= TC_F16_NORM_MAX)) ovf[b] = 1;
+    for (int k = terms * dim + lane; k < kprime; k += 32) {
         float v = 0.f;
-        const int e = k - 3 * dim;
+        const int e = k - terms * dim;
         if (side == 0) v = (e < 2) ? 1.f : 0.f;
-        else {
-            const float nb = valid ? nrm : 1e30f;       // padding train rows can never be selected
+        else if (f16) {
+            const float nb = valid ? fminf(nrm, TC_F16_NORM_MAX) : TC_F16_PAD_NORM;       // padding train rows can never be selected
+            const float hi = __half2float(__float2half_rn(nb));
+            v = e == 0 ? hi : (e == 1 ? (valid ? nb - hi : 0.f) : 0.f);
+        } else {
+            const float nb = valid ? nrm : 1e30f;
             const float hi = __bfloat162float(__float2bfloat16_rn(nb));
             v = e == 0 ? hi : (e == 1 ? (valid ? nb - hi : 0.f) : 0.f);
         }
-        dst[k] = __float2bfloat16_rn(v);
+        dst[k] = f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
     }
-    if (lane == 0) norms[(size_t)b * cap + row] = valid ? nrm : 0.f;
+    if (lane == 0) { norms[(size_t)b * cap + row] = valid ? nrm : 0.f; errs[(size_t)b * cap + row] = valid ? er : 0.f; }
 }
 
 // ---------------------------------------------------------------- 2. the GEMM + running top-K
@@ -199,12 +237,34 @@ __device__ __forceinline__ void top4_merge4(float (&m)[4], float a, float b, flo
     cmpx(c0, c2); cmpx(c1, c3); cmpx(c0, c1); cmpx(c2, c3);
     m[0] = c0; m[1] = c1; m[2] = c2; m[3] = c3;
 }
-__device__ __forceinline__ void tile_top4(const uint32_t (&v)[32], int col_base, float (&l)[4])
+__device__ __forceinline__ float fmin3(float a, float b, float c)
 {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));      // FMNMX3
+    return r;
+}
+// Four scores at a time.  Once a row has seen a few hundred train columns almost no score can still enter its list
+// (chance ~4/n per column), so the merge network runs only when some lane of the warp has a score below `thr`, the
+// smaller of the tile list's and the item list's fourth key: 2 FMNMX(3) + FSETP + VOTE + BRA per skipped group instead
+// of 22 FMNMX + 4 LOP3.  A skipped score is >= thr >= the final fourth key, which is all the rescoring guard relies on.
+// The eight votes of a 32-column block are taken together against the threshold at its start (a stale threshold only
+// lets a few more groups through): one min -> compare -> vote latency per block instead of one per group.
+__device__ __forceinline__ void tile_top4(const uint32_t (&v)[32], int col_base, float (&l)[4], float &thr)
+{
+    bool hit[8];
 #pragma unroll
-    for (int j = 0; j < 32; j += 4)
-        top4_merge4(l, __uint_as_float((v[j] & TC_KEY_MASK) | (uint32_t)(col_base + j)), __uint_as_float((v[j + 1] & TC_KEY_MASK) | (uint32_t)(col_base + j + 1)),
-                    __uint_as_float((v[j + 2] & TC_KEY_MASK) | (uint32_t)(col_base + j + 2)), __uint_as_float((v[j + 3] & TC_KEY_MASK) | (uint32_t)(col_base + j + 3)));
+    for (int j = 0; j < 32; j += 4) {
+        const float m = fminf(fmin3(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2])), __uint_as_float(v[j + 3]));
+        hit[j >> 2] = __any_sync(0xffffffffu, m < thr);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        if (hit[j >> 2]) {
+            top4_merge4(l, __uint_as_float((v[j] & TC_KEY_MASK) | (uint32_t)(col_base + j)), __uint_as_float((v[j + 1] & TC_KEY_MASK) | (uint32_t)(col_base + j + 1)),
+                        __uint_as_float((v[j + 2] & TC_KEY_MASK) | (uint32_t)(col_base + j + 2)), __uint_as_float((v[j + 3] & TC_KEY_MASK) | (uint32_t)(col_base + j + 3)));
+            thr = fminf(thr, l[3]);
+        }
+    }
 }
 // the item-wide list carries the train tile of every key beside it; a tile's four keys enter here (ascending, so the
 // loop stops at the first that no lane can use)
@@ -233,8 +293,9 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint64_t *acc_empt
     __syncwarp();
     if (lane == 0) mbar_arrive(acc_empty);
     float l[4] = { FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX };
-    tile_top4(v0, 0, l);
-    tile_top4(v1, 32, l);
+    float thr = r[3];
+    tile_top4(v0, 0, l, thr);
+    tile_top4(v1, 32, l, thr);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         if (!__any_sync(0xffffffffu, l[k] < r[3])) break;
@@ -262,7 +323,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap tmap_b,
                                                                  const int32_t *__restrict__ n_a_ptr, int n_a_stride,
                                                                  const int32_t *__restrict__ n_b_ptr, int n_b_stride,
-                                                                 int n_pairs, int cap, int kblocks, int n_splits,
+                                                                 int n_pairs, int cap, int kblocks, int last_steps, uint32_t fmt, int n_splits,
                                                                  float *cand_score, int32_t *cand_idx)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -323,7 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const __grid_co
     } else if (warp == TC_WARP_MMA) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc();
+            const uint32_t idesc = make_idesc(fmt);
             const uint64_t a_desc0 = make_sw128_desc(smem_u32(sA)), b_desc0 = make_sw128_desc(smem_u32(sB));
             uint32_t stage = 0, sphase = 0, a_phase = 0, acc = 0, acc_phase = 0;
             TCT_DECL;
@@ -341,9 +402,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) match_tc_kernel(const __grid_co
                         tc_fence_after();
                         const uint64_t a_desc = a_desc0 + (uint64_t)(kb * (TC_M * 128 >> 4));
                         const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (TC_N * 128 >> 4));
+                        const int steps = kb == kblocks - 1 ? last_steps : TC_KB / 16;       // the last k-block may be partly used
 #pragma unroll
                         for (int k = 0; k < TC_KB / 16; k++)      // +32 B per 16-element k step = +2 in the (addr >> 4) field
-                            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                            if (k < steps) umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
                         umma_commit(&sh->b_empty[stage]);            // frees the smem stage when these MMAs are done
                         if (++stage == TC_STAGES) { stage = 0; sphase ^= 1; }
                     }
@@ -413,9 +475,12 @@ __device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *m
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
 }
+// Hands an accumulator buffer back to the leader's MMA thread.  No generic-memory data travels with this signal (the
+// TMEM reads are ordered by tcgen05.wait::ld + tcgen05.fence), so the default CTA-scope release is enough; the
+// .release.cluster form put a cluster-scope MEMBAR (~900 cycles, 20 % of the epilogue warps' time in ncu) in front of it.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr)
 {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
@@ -441,7 +506,7 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 match_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const int32_t *__restrict__ n_a_ptr, int n_a_stride, const int32_t *__restrict__ n_b_ptr, int n_b_stride,
-                     int n_pairs, int cap, int kblocks, int n_splits, float *cand_score, int32_t *cand_idx)
+                     int n_pairs, int cap, int kblocks, int last_steps, uint32_t fmt, int n_splits, float *cand_score, int32_t *cand_idx)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -508,8 +573,8 @@ match_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     } else if (warp == TC_WARP_MMA) {
         // ===================== MMA issuer: one thread of the leader CTA drives both tensor cores =====================
         if (lane == 0 && leader) {
-            // D = f32, A = B = bf16, K-major, N = 256, M = 256 (128 rows per CTA)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC2_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            // D = f32, A and B in `fmt`, K-major, N = 256, M = 256 (128 rows per CTA)
+            const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(TC2_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
             const uint64_t a_desc0 = make_sw128_desc(smem_u32(sA)), b_desc0 = make_sw128_desc(smem_u32(sB));
             uint32_t stage = 0, sphase = 0, a_phase = 0, acc = 0, acc_phase = 0;
             for (int item = cluster_id; item < items; item += n_clusters) {
@@ -526,9 +591,10 @@ match_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         tc_fence_after();
                         const uint64_t a_desc = a_desc0 + (uint64_t)(kb * (TC_M * 128 >> 4));
                         const uint64_t b_desc = b_desc0 + (uint64_t)(stage * ((TC2_N / 2) * 128 >> 4));
+                        const int steps = kb == kblocks - 1 ? last_steps : TC_KB / 16;
 #pragma unroll
                         for (int k = 0; k < TC_KB / 16; k++)
-                            umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                            if (k < steps) umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
                         umma_commit_pair(&sh->b_empty[stage]);
                         if (++stage == TC_STAGES) { stage = 0; sphase ^= 1; }
                     }
@@ -554,16 +620,23 @@ match_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * TC2_N + grp * (TC2_N / 2);
                 const uint32_t acc_empty_leader = mapa_u32(smem_u32(&sh->acc_empty[acc]), 0);
                 float l[4] = { FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX };
+                float thr = r[3];
                 uint32_t v0[32], v1[32];
+                // TMEM drains at 16 B/clk per sub-partition (256 cycles per x32 load): the next 32 columns are in flight
+                // while the previous 32 go through the selection
                 tmem_ld32_issue(taddr, v0); tmem_ld32_issue(taddr + 32, v1);
                 tmem_ld_wait();
-                tile_top4(v0, 0, l); tile_top4(v1, 32, l);
-                tmem_ld32_issue(taddr + 64, v0); tmem_ld32_issue(taddr + 96, v1);
+                tile_top4(v0, 0, l, thr);
+                tmem_ld32_issue(taddr + 64, v0);
+                tile_top4(v1, 32, l, thr);
+                tmem_ld_wait();
+                tmem_ld32_issue(taddr + 96, v1);
+                tile_top4(v0, 64, l, thr);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(acc_empty_leader);            // scores are in registers: hand the buffer back
-                tile_top4(v0, 64, l); tile_top4(v1, 96, l);
+                tile_top4(v1, 96, l, thr);
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     if (!__any_sync(0xffffffffu, l[k] < r[3])) break;
@@ -586,15 +659,21 @@ match_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 // ---------------------------------------------------------------- 3. exact rescoring + guard
 // one warp per query.  desc_*: fp32 row-major [img][cap][dim] (the original descriptors).
 // G lanes per query (G = candidates per query rounded up to a power of two), 32 / G queries per warp.
+// (squared distance, train index) as one ordered 64-bit key: distances are >= 0, so their bit patterns order like the values,
+// and equal distances order by index -- the matcher's tie rule.
+__device__ __forceinline__ unsigned long long fb_pack(float d, int t) { return ((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)t; }
 template <int G>
 __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ desc_a, const float *__restrict__ desc_b,
                                                       int64_t pair_stride_a, int64_t pair_stride_b,
                                                       const int32_t *__restrict__ n_a_ptr, int n_a_stride,
                                                       const int32_t *__restrict__ n_b_ptr, int n_b_stride,
                                                       const float *__restrict__ norm_a, const float *__restrict__ norm_b_max,
+                                                      const float *__restrict__ err_a, const float *__restrict__ err_b_max,
                                                       const float *__restrict__ cand_score, const int32_t *__restrict__ cand_idx,
-                                                      int cap, int dim, int n_splits, int32_t *best_idx, float *best_dist,
-                                                      int32_t *fallback_list, int32_t *fallback_count)
+                                                      int cap, int dim, int n_splits, int terms, const int32_t *__restrict__ ovf,
+                                                      int32_t *best_idx, float *best_dist,
+                                                      int32_t *fallback_list, int32_t *fallback_count, int32_t *pair_count,
+                                                      unsigned long long *fb_slots)
 {
     constexpr int QPW = 32 / G;
     const int p = blockIdx.y;
@@ -610,6 +689,45 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
         const size_t o = ((size_t)p * cap + q) * nc + gl;
         t = cand_idx[o]; approx = cand_score[o];
         if (t >= nB || approx > 1e29f) t = -1;      // a padding column (or an unfilled slot): not a candidate, but its key still bounds the list
+    }
+    // |GEMM score - exact score| <= E_gemm (DESIGN.md "matcher error bound"):
+    //   terms 3 (split-bf16): dropped lo*lo and second-order split errors 3*2^-18 |a||b| (x2 for the -2 scale), fp32
+    //     accumulation of K' <= 448 exact products with a worst case truncating adder 448*2^-23 (2|a||b| + |b|^2), norm
+    //     split 2^-17 |b|^2.
+    //   terms 2 / 1 (fp16): the stored query row is a + eps, the stored train row -2b + eta; prep_split_kernel measured
+    //     |eps|^2 of this query (err_a) and max |eta|^2 over the pair's train rows (err_b_max) exactly, subnormal rounding
+    //     included, so by Cauchy-Schwarz the products are off by at most |a||eta| + 2|eps||b| + |eps||eta|; fp32
+    //     accumulation of `used` exact products <= used*2^-23 (2|a||b| + |b|^2); norm: fp32 sum + fp16 split <= 1.1e-6 |b|^2.
+    // On top of that a key differs from its score by the column bits (2^-16 |key|), the fp32 rescoring from the real
+    // distance by 128*2^-24 d^2, and the fp32 |a|^2 from the real one by < 1e-6 |a|^2: tail(|key|, d^2).
+    const float na = live ? norm_a[(size_t)p * cap + q] : 0.f;
+    const float bmax = norm_b_max[p];
+    const float ab = sqrtf(na) * sqrtf(bmax);
+    float E_gemm;
+    if (terms == 3) E_gemm = 1.4e-4f * ab + 7e-5f * bmax;
+    else {
+        const float ea = sqrtf(live ? err_a[(size_t)p * cap + q] : 0.f), eb = sqrtf(err_b_max[p]);
+        E_gemm = 1.001f * (sqrtf(na) * eb + 2.f * ea * sqrtf(bmax) + ea * eb) + 1.01f * (float)(terms * dim + 16) * 1.1920929e-7f * (2.f * ab + bmax)
+               + 1.1e-6f * bmax + 3e-8f;
+    }
+#define TC_TAIL(key, dd) (1.6e-5f * fabsf(key) + 8e-6f * (dd) + 1e-6f * na + 1e-7f)
+    // Only candidates whose key is within reach of the second smallest key can be one of the best two: a candidate further
+    // than 2 E_gemm + the key / rescoring slack above it has a larger fp32 distance than both of the two smallest keys'
+    // rows, and its train row is not fetched (typically 2 - 3 of the 8 candidates are).
+    {
+        const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u) << (lane / G * G));
+        const float kv = t >= 0 ? approx : FLT_MAX;
+        float k1 = kv;
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1) k1 = fminf(k1, __shfl_xor_sync(0xffffffffu, k1, o));
+        const unsigned holders = __ballot_sync(0xffffffffu, kv == k1) & gmask;
+        float k2 = (lane == __ffs(holders) - 1) ? FLT_MAX : kv;
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1) k2 = fminf(k2, __shfl_xor_sync(0xffffffffu, k2, o));
+        const float D = na + bmax + 2.f * ab;
+        if (t >= 0 && k2 < 1e29f && approx > k2 + 2.f * E_gemm + 1.6e-5f * (fabsf(approx) + fabsf(k2) + D) + 1e-6f) t = -1;
+    }
+    {
         if (t >= 0) {
             const float4 *a4 = (const float4 *)a, *b4 = (const float4 *)(B + (size_t)t * dim);     // dim % 4 == 0, rows 16-byte aligned
             float s = 0.f;
@@ -643,122 +761,145 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
         const float od = __shfl_xor_sync(0xffffffffu, d1, o); const int ot = __shfl_xor_sync(0xffffffffu, t1, o);
         if (ot >= 0 && (t1 < 0 || od < d1 || (od == d1 && ot < t1))) { d1 = od; t1 = ot; }
     }
+    // every rescored candidate checks the bound it relies on; tests read the counter (fallback_count[1]) and expect 0
+    if (t >= 0 && !(fabsf(approx - (d - na)) <= E_gemm + TC_TAIL(approx, d)) && !ovf[p]) atomicAdd(fallback_count + 1, 1);
     if (live && gl == 0) {
-        const float na = norm_a[(size_t)p * cap + q];
-        const float bmax = norm_b_max[p];
-        // |approx key - exact score| <= E.  Terms (DESIGN.md "matcher error bound"): dropped lo*lo and second-order split
-        // errors 3*2^-18 |a||b| (x2 for the -2 scale), fp32 accumulation of K' = 448 exact bf16 products, worst case
-        // truncating adder 448*2^-23 (2|a||b| + |b|^2), norm split 2^-17 |b|^2, fp32 rescoring 128*2^-24 d^2, and the
-        // column bits in the epilogue's keys, 2^-16 |score| <= 2^-16 (|b|^2 + 2|a||b|).
-        const float ab = sqrtf(na) * sqrtf(bmax);
-        const float E = 1.4e-4f * ab + 7e-5f * bmax + 1e-5f * (na + bmax + 2.f * ab) + 1.6e-5f * (bmax + 2.f * ab) + 1e-7f;
-        bool ok = true;
+        bool ok = !ovf[p];
         if (nB >= 2) {
             if (t1 < 0) ok = false;
-            else if (worst < FLT_MAX && !((d1 - na) < worst - E)) ok = false;
+            // no train row outside the lists can reach the second best: its key is >= worst, so its fp32 distance is
+            // > d1 whenever d1 - |a|^2 stays below worst by the GEMM bound and the tail at (worst, d1)
+            else if (worst < FLT_MAX && !((d1 - na) < worst - (E_gemm + TC_TAIL(worst, d1)))) ok = false;
         } else if (nB == 1 && t0 < 0) ok = false;
         const size_t o = ((size_t)p * cap + q) * 2;
         best_idx[o] = t0; best_idx[o + 1] = t1;
         best_dist[o] = t0 >= 0 ? sqrtf(d0) : FLT_MAX; best_dist[o + 1] = t1 >= 0 ? sqrtf(d1) : FLT_MAX;
-        if (!ok) { const int slot = atomicAdd(fallback_count, 1); fallback_list[slot] = p * cap + q; }
+        if (!ok) {
+            // flagged: joins its pair's rescan list, seeded with the candidates' best two so the scan only touches memory for
+            // train rows that beat them
+            atomicAdd(fallback_count, 1);
+            const size_t slot = (size_t)p * cap + atomicAdd(pair_count + p, 1);
+            fallback_list[slot] = q;
+            fb_slots[2 * slot] = t0 >= 0 ? fb_pack(d0, t0) : ~0ull;
+            fb_slots[2 * slot + 1] = t1 >= 0 ? fb_pack(d1, t1) : ~0ull;
+        }
     }
 }
 
-// per pair: max ||b||^2
-__global__ void norm_max_kernel(const float *__restrict__ norms_b, const int32_t *n_b_ptr, int n_b_stride, int cap, float *out)
+// per pair: max ||b||^2 and max squared operand rounding error over the train rows
+__global__ void norm_max_kernel(const float *__restrict__ norms_b, const float *__restrict__ errs_b, const int32_t *n_b_ptr, int n_b_stride,
+                                int cap, float *out, float *err_out)
 {
-    __shared__ float s[32];
+    __shared__ float s[32], se[32];
     const int p = blockIdx.x;
     const int n = n_b_ptr[(size_t)p * n_b_stride];
-    float m = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, norms_b[(size_t)p * cap + i]);
-    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    float m = 0.f, e = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { m = fmaxf(m, norms_b[(size_t)p * cap + i]); e = fmaxf(e, errs_b[(size_t)p * cap + i]); }
+    for (int o = 16; o; o >>= 1) { m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); e = fmaxf(e, __shfl_xor_sync(0xffffffffu, e, o)); }
+    if ((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5] = m; se[threadIdx.x >> 5] = e; }
     __syncthreads();
-    if (threadIdx.x == 0) { for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, s[w]); out[p] = m; }
-}
-
-// ---------------------------------------------------------------- 4. exact fallback for flagged queries (one CTA each)
-__device__ __forceinline__ void top2_merge(float &d0, int &t0, float &d1, int &t1, float e0, int u0, float e1, int u1)
-{
-    float c[4] = { d0, d1, e0, e1 }; int ci[4] = { t0, t1, u0, u1 };
-    float b0 = FLT_MAX, b1 = FLT_MAX; int i0 = -1, i1 = -1;
-#pragma unroll
-    for (int z = 0; z < 4; z++) {
-        if (ci[z] < 0) continue;
-        if (i0 < 0 || c[z] < b0 || (c[z] == b0 && ci[z] < i0)) { b1 = b0; i1 = i0; b0 = c[z]; i0 = ci[z]; }
-        else if (i1 < 0 || c[z] < b1 || (c[z] == b1 && ci[z] < i1)) { b1 = c[z]; i1 = ci[z]; }
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) { m = fmaxf(m, s[w]); e = fmaxf(e, se[w]); }
+        out[p] = m; err_out[p] = e;
     }
-    d0 = b0; t0 = i0; d1 = b1; t1 = i1;
 }
 
-#define FB_THREADS 512
-#define FB_ROWS 4
-__global__ void __launch_bounds__(FB_THREADS) fallback_exact_kernel(const float *__restrict__ desc_a, const float *__restrict__ desc_b,
-                                                             int64_t pair_stride_a, int64_t pair_stride_b,
-                                                             const int32_t *__restrict__ n_b_ptr, int n_b_stride, int cap, int dim,
-                                                             const int32_t *__restrict__ fallback_list, const int32_t *__restrict__ fallback_count,
-                                                             int32_t *best_idx, float *best_dist)
+// ---------------------------------------------------------------- 4. exact rescan of the flagged queries
+// grid (slices of train rows, pairs), 256 threads = 256 train rows at a time.  The flagged queries of a pair are taken
+// FB_Q at a time into shared memory and every train row of the slice is read ONCE for all of them (one CTA per query
+// streamed the whole train set per query: 4.3 MB of L2 traffic each, 0.3 - 0.6 ms for a few hundred queries).  Distances
+// are the serial-k, FMA-free sums of rescore_kernel, so a candidate row met again gives the seed's exact key and is skipped.
+// A row whose key beats the query's current second best enters the two-slot list with two atomicMin: slot 0 keeps the
+// minimum, every key that loses there (the new one, or the one it displaced) is offered to slot 1 -- the minimum of all
+// keys except the overall minimum, in any arrival order.
+#define FB_Q 8
+// the rows of one slice against the first QN queries in shared memory
+template <int QN>
+__device__ __forceinline__ void fb_scan_rows(const float *__restrict__ B, int dim, int t_begin, int t_end, const float4 (*s_a)[32],
+                                             const unsigned long long *s_seed0, unsigned long long *s_k1, unsigned long long *slots)
 {
-    __shared__ float s_a[128];
-    __shared__ float s_d[FB_THREADS / 32][2];
-    __shared__ int s_t[FB_THREADS / 32][2];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int total = *fallback_count;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int pq = fallback_list[w];
-        const int p = pq / cap, q = pq - p * cap;
-        const int nB = n_b_ptr[(size_t)p * n_b_stride];
-        const float *a = desc_a + p * pair_stride_a + (size_t)q * dim;
-        const float *B = desc_b + p * pair_stride_b;
-        __syncthreads();
-        for (int k = threadIdx.x; k < dim; k += blockDim.x) s_a[k] = a[k];
-        __syncthreads();
-        float d0 = FLT_MAX, d1 = FLT_MAX; int t0 = -1, t1 = -1;
-        // FB_ROWS train rows in flight per thread: the scan is L2-latency bound (few CTAs run), not bandwidth bound
-        for (int tb = threadIdx.x; tb < nB; tb += FB_ROWS * FB_THREADS) {
-            const float4 *b4[FB_ROWS]; float s[FB_ROWS];
+    const int d4 = dim / 4;
+    for (int t = t_begin + threadIdx.x; t < t_end; t += blockDim.x) {
+        const float4 *b4 = (const float4 *)(B + (size_t)t * dim);     // dim % 4 == 0, rows 16-byte aligned
+        float s[QN];
 #pragma unroll
-            for (int r = 0; r < FB_ROWS; r++) {
-                const int t = min(tb + r * FB_THREADS, nB - 1);              // clamped rows are computed and discarded
-                b4[r] = (const float4 *)(B + (size_t)t * dim); s[r] = 0.f;   // dim % 4 == 0, rows 16-byte aligned
-            }
-#pragma unroll 4
-            for (int k4 = 0; k4 < dim / 4; k4++) {
-                float4 bv[FB_ROWS];
+        for (int q = 0; q < QN; q++) s[q] = 0.f;
+#pragma unroll 2
+        for (int k4 = 0; k4 < d4; k4++) {
+            const float4 bv = __ldg(b4 + k4);
 #pragma unroll
-                for (int r = 0; r < FB_ROWS; r++) bv[r] = __ldg(b4[r] + k4);
-                const float a0 = s_a[4 * k4], a1 = s_a[4 * k4 + 1], a2 = s_a[4 * k4 + 2], a3 = s_a[4 * k4 + 3];
-#pragma unroll
-                for (int r = 0; r < FB_ROWS; r++) {                          // serial k order per row: the CPU value
-                    float df = a0 - bv[r].x; s[r] += df * df;
-                    df = a1 - bv[r].y; s[r] += df * df;
-                    df = a2 - bv[r].z; s[r] += df * df;
-                    df = a3 - bv[r].w; s[r] += df * df;
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < FB_ROWS; r++) {                              // ascending t: ties keep the lower train index
-                const int t = tb + r * FB_THREADS;
-                if (t < nB) {
-                    if (s[r] < d0) { d1 = d0; t1 = t0; d0 = s[r]; t0 = t; }
-                    else if (s[r] < d1) { d1 = s[r]; t1 = t; }
-                }
+            for (int q = 0; q < QN; q++) {                              // serial k order per (query, row): the CPU value
+                const float4 av = s_a[q][k4];
+                float df = av.x - bv.x; s[q] += df * df;
+                df = av.y - bv.y; s[q] += df * df;
+                df = av.z - bv.z; s[q] += df * df;
+                df = av.w - bv.w; s[q] += df * df;
             }
         }
-        for (int o = 16; o; o >>= 1) {
-            const float e0 = __shfl_xor_sync(0xffffffffu, d0, o), e1 = __shfl_xor_sync(0xffffffffu, d1, o);
-            const int u0 = __shfl_xor_sync(0xffffffffu, t0, o), u1 = __shfl_xor_sync(0xffffffffu, t1, o);
-            top2_merge(d0, t0, d1, t1, e0, u0, e1, u1);
+#pragma unroll
+        for (int q = 0; q < QN; q++) {
+            const unsigned long long key = fb_pack(s[q], t);
+            if (key < s_k1[q] && key != s_seed0[q]) {
+                unsigned long long *sl = slots + 2 * q;
+                const unsigned long long old = atomicMin(sl, key);
+                const unsigned long long now1 = min(atomicMin(sl + 1, max(old, key)), max(old, key));
+                s_k1[q] = now1;                                          // a looser value written late only costs a few more atomics
+            }
         }
-        if (lane == 0) { s_d[warp][0] = d0; s_d[warp][1] = d1; s_t[warp][0] = t0; s_t[warp][1] = t1; }
+    }
+}
+
+__global__ void __launch_bounds__(256) fallback_scan_kernel(const float *__restrict__ desc_a, const float *__restrict__ desc_b,
+                                                            int64_t pair_stride_a, int64_t pair_stride_b,
+                                                            const int32_t *__restrict__ n_b_ptr, int n_b_stride, int cap, int dim,
+                                                            const int32_t *__restrict__ pair_count, const int32_t *__restrict__ pair_list,
+                                                            unsigned long long *fb_slots)
+{
+    __shared__ float4 s_a[FB_Q][32];                       // dim <= 128
+    __shared__ unsigned long long s_seed0[FB_Q], s_k1[FB_Q];
+    const int p = blockIdx.y;
+    const int F = pair_count[p];
+    if (F == 0) return;
+    const int nB = n_b_ptr[(size_t)p * n_b_stride];
+    const int per = ((nB + gridDim.x - 1) / gridDim.x + 255) & ~255;          // whole passes of the CTA's 256 threads
+    const int t_begin = blockIdx.x * per, t_end = min(nB, t_begin + per);
+    if (t_begin >= t_end) return;
+    const float *A = desc_a + p * pair_stride_a, *B = desc_b + p * pair_stride_b;
+    const int d4 = dim / 4;
+    for (int g = 0; g < F; g += FB_Q) {
+        const int Q = min(FB_Q, F - g);
+        const size_t slot0 = (size_t)p * cap + g;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int z = 1; z < FB_THREADS / 32; z++) top2_merge(d0, t0, d1, t1, s_d[z][0], s_t[z][0], s_d[z][1], s_t[z][1]);
-            const size_t o = ((size_t)p * cap + q) * 2;
-            best_idx[o] = t0; best_idx[o + 1] = t1;
-            best_dist[o] = t0 >= 0 ? sqrtf(d0) : FLT_MAX; best_dist[o + 1] = t1 >= 0 ? sqrtf(d1) : FLT_MAX;
+        for (int i = threadIdx.x; i < FB_Q * d4; i += blockDim.x) {
+            const int qi = i / d4, kk = i - qi * d4;
+            s_a[qi][kk] = qi < Q ? ((const float4 *)(A + (size_t)pair_list[slot0 + qi] * dim))[kk] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        if (threadIdx.x < FB_Q) {                          // unused query slots: key 0, nothing is smaller
+            s_seed0[threadIdx.x] = (int)threadIdx.x < Q ? fb_slots[2 * (slot0 + threadIdx.x)] : 0ull;
+            s_k1[threadIdx.x] = (int)threadIdx.x < Q ? fb_slots[2 * (slot0 + threadIdx.x) + 1] : 0ull;
+        }
+        __syncthreads();
+        if (Q > 4) fb_scan_rows<8>(B, dim, t_begin, t_end, s_a, s_seed0, s_k1, fb_slots + 2 * slot0);
+        else if (Q > 2) fb_scan_rows<4>(B, dim, t_begin, t_end, s_a, s_seed0, s_k1, fb_slots + 2 * slot0);
+        else if (Q > 1) fb_scan_rows<2>(B, dim, t_begin, t_end, s_a, s_seed0, s_k1, fb_slots + 2 * slot0);
+        else fb_scan_rows<1>(B, dim, t_begin, t_end, s_a, s_seed0, s_k1, fb_slots + 2 * slot0);
+    }
+}
+
+// one thread per flagged query: the two-slot list -> the matcher's output format
+__global__ void fallback_store_kernel(const int32_t *__restrict__ pair_count, const int32_t *__restrict__ pair_list,
+                                      const unsigned long long *__restrict__ fb_slots, int cap, int32_t *best_idx, float *best_dist)
+{
+    const int p = blockIdx.y;
+    const int F = pair_count[p];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F; i += gridDim.x * blockDim.x) {
+        const size_t slot = (size_t)p * cap + i;
+        const unsigned long long k0 = fb_slots[2 * slot], k1 = fb_slots[2 * slot + 1];
+        const size_t o = ((size_t)p * cap + pair_list[slot]) * 2;
+        best_idx[o] = k0 == ~0ull ? -1 : (int32_t)(uint32_t)k0;
+        best_idx[o + 1] = k1 == ~0ull ? -1 : (int32_t)(uint32_t)k1;
+        best_dist[o] = k0 == ~0ull ? FLT_MAX : sqrtf(__uint_as_float((uint32_t)(k0 >> 32)));
+        best_dist[o + 1] = k1 == ~0ull ? FLT_MAX : sqrtf(__uint_as_float((uint32_t)(k1 >> 32)));
     }
 }
 
@@ -779,7 +920,7 @@ static PFN_encodeTiled get_encode()
     return fn;
 }
 
-static int make_tmap(CUtensorMap *map, void *base, int kprime, long long rows, int box_rows = TC_M)
+static int make_tmap(CUtensorMap *map, void *base, int kprime, long long rows, bool f16, int box_rows = TC_M)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) { vfsms_set_error("cuTensorMapEncodeTiled not available"); return VFSMS_E_CUDA; }
@@ -787,7 +928,7 @@ static int make_tmap(CUtensorMap *map, void *base, int kprime, long long rows, i
     cuuint64_t strides[1] = { (cuuint64_t)kprime * 2 };
     cuuint32_t box[2] = { TC_KB, (cuuint32_t)box_rows };
     cuuint32_t estr[2] = { 1, 1 };
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { vfsms_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return VFSMS_E_CUDA; }
     return 0;
@@ -800,7 +941,13 @@ int match_tc_batch(vfsms_ctx *ctx, const float *desc_a, const int32_t *n_a, int 
 {
     if (cap % TC_M || dim % 32 || dim > 128) { vfsms_set_error("match_tc: cap %% 128 == 0 and dim in {32,64,96,128} required"); return VFSMS_E_ARG; }
     MatchWorkspace &mw = ctx->match;
-    const int kprime = 3 * dim + 64, kblocks = kprime / TC_KB;
+    // operand scheme (vfsms_set_matcher): 3 = split-bf16, 2 = fp16 with the query split in two, 1 = plain fp16
+    const int terms = ctx->match_terms;
+    const bool f16 = terms < 3;
+    const int used = terms * dim + 16;                                  // columns that take part in the product
+    const int kblocks = ceil_div(used, TC_KB), kprime = kblocks * TC_KB;
+    const int last_steps = (used - (kblocks - 1) * TC_KB) / 16;         // MMA k-steps of the last k-block
+    const uint32_t fmt = f16 ? TC_FMT_F16 : TC_FMT_BF16;
     const int m_tiles = cap / TC_M;
     int n_splits = 1;
     while (n_pairs * m_tiles * n_splits < 2 * ctx->num_sms && n_splits * TC_EPI_GROUPS * TC_TOPK < 32) n_splits *= 2;
@@ -810,25 +957,31 @@ int match_tc_batch(vfsms_ctx *ctx, const float *desc_a, const int32_t *n_a, int 
     if ((rc = mw.bf16_b.reserve(rows * kprime * 2))) return rc;
     // cand buffer: scores | idx | norms_a | norms_b | bmax | fallback_count | fallback_list
     const size_t n_cand = rows * n_splits * TC_EPI_GROUPS * TC_TOPK;
-    const size_t bytes = n_cand * 8 + rows * 8 + (size_t)n_pairs * 4 + 16 + rows * 4;
+    const int np4 = (n_pairs + 3) & ~3;                                 // keeps the float4 scratch below 16-byte aligned
+    const size_t bytes = n_cand * 8 + rows * 16 + (size_t)np4 * 16 + 16 + rows * 16 + rows * 4;
     if ((rc = mw.cand_topk.reserve(bytes))) return rc;
     float *cand_score = mw.cand_topk.as<float>();
     int32_t *cand_idx = (int32_t *)(cand_score + n_cand);
-    float *norm_a = (float *)(cand_idx + n_cand), *norm_b = norm_a + rows, *bmax = norm_b + rows;
-    int32_t *fb_count = (int32_t *)(bmax + n_pairs), *fb_list = fb_count + 4;
+    float *norm_a = (float *)(cand_idx + n_cand), *norm_b = norm_a + rows, *err_a = norm_b + rows, *err_b = err_a + rows;
+    float *bmax = err_b + rows, *ebmax = bmax + np4;
+    int32_t *ovf = (int32_t *)(ebmax + np4);
+    int32_t *pair_count = ovf + np4;                                    // flagged queries per pair
+    int32_t *fb_count = pair_count + np4;                               // fb_count[0] rescans, [1] error-bound violations
+    unsigned long long *fb_slots = (unsigned long long *)(fb_count + 4);    // 8-byte aligned: rows % 128 == 0, np4 % 4 == 0
+    int32_t *fb_list = (int32_t *)(fb_slots + 2 * rows);                // [pair][cap] query indices
 
     StageTimer tt(ctx, st, VFSMS_STAGE_MATCH_TC);
-    prep_split_kernel<<<dim3(ceil_div(cap, 8), n_pairs), 256, 0, st>>>(desc_a, n_a, n_a_stride, cap, dim, kprime, 0, 0, mw.bf16_a.as<__nv_bfloat16>(), norm_a);
+    CUDA_TRY(cudaMemsetAsync(ovf, 0, (size_t)np4 * 8 + 16, st));
+    prep_split_kernel<<<dim3(ceil_div(cap, 8), n_pairs), 256, 0, st>>>(desc_a, n_a, n_a_stride, cap, dim, kprime, terms, 0, 0, mw.bf16_a.as<uint16_t>(), norm_a, err_a, ovf);
     LAUNCH_CHECK(ctx);
-    prep_split_kernel<<<dim3(ceil_div(cap, 8), n_pairs), 256, 0, st>>>(desc_b, n_b, n_b_stride, cap, dim, kprime, 1, 0, mw.bf16_b.as<__nv_bfloat16>(), norm_b);
+    prep_split_kernel<<<dim3(ceil_div(cap, 8), n_pairs), 256, 0, st>>>(desc_b, n_b, n_b_stride, cap, dim, kprime, terms, 1, 0, mw.bf16_b.as<uint16_t>(), norm_b, err_b, ovf);
     LAUNCH_CHECK(ctx);
-    norm_max_kernel<<<n_pairs, 256, 0, st>>>(norm_b, n_b, n_b_stride, cap, bmax);
+    norm_max_kernel<<<n_pairs, 256, 0, st>>>(norm_b, err_b, n_b, n_b_stride, cap, bmax, ebmax);
     LAUNCH_CHECK(ctx);
-    CUDA_TRY(cudaMemsetAsync(fb_count, 0, 16, st));
 
     CUtensorMap ta, tb;
-    if ((rc = make_tmap(&ta, mw.bf16_a.p, kprime, (long long)rows))) return rc;
-    if ((rc = make_tmap(&tb, mw.bf16_b.p, kprime, (long long)rows))) return rc;
+    if ((rc = make_tmap(&ta, mw.bf16_a.p, kprime, (long long)rows, f16))) return rc;
+    if ((rc = make_tmap(&tb, mw.bf16_b.p, kprime, (long long)rows, f16))) return rc;
     const size_t smem = (size_t)(TC_MAX_KBLOCKS * TC_M + TC_STAGES * TC_N) * 128 + sizeof(TcShared) + 1024;
     static bool attr = false;
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
@@ -840,12 +993,12 @@ int match_tc_batch(vfsms_ctx *ctx, const float *desc_a, const int32_t *n_a, int 
         const int citems = n_pairs * ((m_tiles + 1) / 2) * n_splits;
         int clusters = ctx->num_sms / 2;
         if (citems < clusters) clusters = citems;
-        match_tc_pair_kernel<<<clusters * 2, TC_THREADS, smem, st>>>(ta, tb, n_a, n_a_stride, n_b, n_b_stride, n_pairs, cap, kblocks, n_splits,
+        match_tc_pair_kernel<<<clusters * 2, TC_THREADS, smem, st>>>(ta, tb, n_a, n_a_stride, n_b, n_b_stride, n_pairs, cap, kblocks, last_steps, fmt, n_splits,
                                                                   cand_score, cand_idx);
         LAUNCH_CHECK(ctx);
     } else {
         const int grid = items < ctx->num_sms ? items : ctx->num_sms;
-        match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(ta, tb, n_a, n_a_stride, n_b, n_b_stride, n_pairs, cap, kblocks, n_splits, cand_score, cand_idx);
+        match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(ta, tb, n_a, n_a_stride, n_b, n_b_stride, n_pairs, cap, kblocks, last_steps, fmt, n_splits, cand_score, cand_idx);
         LAUNCH_CHECK(ctx);
 #ifdef TC_TIMING
         {
@@ -861,13 +1014,19 @@ int match_tc_batch(vfsms_ctx *ctx, const float *desc_a, const int32_t *n_a, int 
     {
         const int nc = n_splits * TC_EPI_GROUPS * TC_TOPK;
 #define RESCORE(G) rescore_kernel<G><<<dim3(ceil_div(cap, 8 * (32 / G)), n_pairs), 256, 0, st>>>(desc_a, desc_b, (int64_t)cap * dim, (int64_t)cap * dim, \
-            n_a, n_a_stride, n_b, n_b_stride, norm_a, bmax, cand_score, cand_idx, cap, dim, n_splits, best_idx, best_dist, fb_list, fb_count)
+            n_a, n_a_stride, n_b, n_b_stride, norm_a, bmax, err_a, ebmax, cand_score, cand_idx, cap, dim, n_splits, terms, ovf, best_idx, best_dist, fb_list, fb_count, pair_count, fb_slots)
         if (nc <= 8) RESCORE(8); else if (nc <= 16) RESCORE(16); else RESCORE(32);
 #undef RESCORE
         LAUNCH_CHECK(ctx);
     }
-    fallback_exact_kernel<<<ctx->num_sms * 2, FB_THREADS, 0, st>>>(desc_a, desc_b, (int64_t)cap * dim, (int64_t)cap * dim, n_b, n_b_stride, cap, dim,
-                                                            fb_list, fb_count, best_idx, best_dist);
+    {
+        int slices = 4 * ctx->num_sms / n_pairs;
+        slices = slices < 1 ? 1 : (slices > 64 ? 64 : slices);
+        fallback_scan_kernel<<<dim3(slices, n_pairs), 256, 0, st>>>(desc_a, desc_b, (int64_t)cap * dim, (int64_t)cap * dim, n_b, n_b_stride, cap, dim,
+                                                                    pair_count, fb_list, fb_slots);
+        LAUNCH_CHECK(ctx);
+        fallback_store_kernel<<<dim3(1, n_pairs), 256, 0, st>>>(pair_count, fb_list, fb_slots, cap, best_idx, best_dist);
+    }
     LAUNCH_CHECK(ctx);
     ctx->last_fallback_count_dev = fb_count;
     return 0;

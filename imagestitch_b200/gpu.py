@@ -318,10 +318,14 @@ def enhance(image, clahe=False, clip_limit=20, tile_size=5, device=0):
     return out
 
 
+MATCHERS = {"tc": 0, "simt": 1, "tc_1sm": 2, "tc_bf16x3": 3, "tc_f16x2": 4, "tc_f16x1": 5}      # include/vfsms.h vfsms_set_matcher
+
+
 def set_matcher(mode, device=0):
-    """'tc' (default): tcgen05 candidates (CTA pairs) + exact rescoring; 'tc_1sm': the same on single CTAs;
-    'simt': exact fp32 SIMT kernel.  Identical results."""
-    check(_lib.load().vfsms_set_matcher(_lib.context(device), {"tc": 0, "simt": 1, "tc_1sm": 2}[mode]), "vfsms_set_matcher")
+    """'tc' (default): tcgen05 candidates (CTA pairs, fp16 operands = 'tc_f16x1') + exact rescoring;
+    'tc_1sm': the same on single CTAs; 'simt': exact fp32 SIMT kernel; 'tc_bf16x3' / 'tc_f16x2' / 'tc_f16x1': 'tc' with
+    split-bf16 (3 terms) / fp16 + query split (2 terms) / plain fp16 (1 term) operands.  Identical results."""
+    check(_lib.load().vfsms_set_matcher(_lib.context(device), MATCHERS[mode]), "vfsms_set_matcher")
 
 
 OPTIONS = {"describe": 0, "sort": 1, "lpt": 2, "entropy": 3}      # include/vfsms.h VFSMS_OPT_*
@@ -342,6 +346,13 @@ def get_option(name, device=0):
 def last_match_fallbacks(device=0):
     n = ctypes.c_int(0)
     check(_lib.load().vfsms_last_match_fallbacks(_lib.context(device), ctypes.byref(n)), "vfsms_last_match_fallbacks")
+    return n.value
+
+
+def last_match_bound_violations(device=0):
+    """Rescored candidates of the last tensor-core match whose GEMM score broke the guard's error bound (expected: 0)."""
+    n = ctypes.c_int(0)
+    check(_lib.load().vfsms_last_match_bound_violations(_lib.context(device), ctypes.byref(n)), "vfsms_last_match_bound_violations")
     return n.value
 
 

@@ -76,9 +76,15 @@ void *vfsms_stream(vfsms_ctx *ctx);           /* the context's cudaStream_t */
 /* number of kernel launches this context has issued since creation (bench.py's gpu_launches) */
 int64_t vfsms_launch_count(vfsms_ctx *ctx);
 
-/* Matcher selection: 0 (default) = tcgen05 split-bf16 GEMM candidates + exact fp32 rescoring (+ exact fallback),
- * 1 = exact fp32 SIMT kernel, 2 = like 0 with the GEMM on single CTAs (128 x 128 tiles, cta_group::1) instead of CTA pairs.
- * All produce identical results; 1 and 2 exist for verification. */
+/* Matcher selection.  All modes produce identical results (candidates from a tcgen05 GEMM on reduced-precision operands,
+ * exact fp32 rescoring, and an exact rescan of every query whose candidates the operand error bound cannot separate):
+ *   0 (default) = CTA pairs (cta_group::2, 256 x 256 tiles) with the default operand scheme (plain fp16, mode 5),
+ *   1 = exact fp32 SIMT kernel, no tensor cores (verification),
+ *   2 = like 0 on single CTAs (128 x 128 tiles, cta_group::1) (verification),
+ *   3 / 4 / 5 = like 0 with split-bf16 operands (3 product terms, K' = 3D + 16) / fp16 with the query split
+ *               (2 terms, K' = 2D + 16) / plain fp16 (1 term, K' = D + 16).
+ * The fp16 schemes need squared descriptor norms <= 1e4 (SURF descriptors are unit vectors); a pair that breaks this is
+ * rescanned exactly, and vfsms_match uses the bf16 scheme for featureType 1 (SIFT) descriptors. */
 int vfsms_set_matcher(vfsms_ctx *ctx, int mode);
 /* Kernel-schedule switches.  Every value of an option produces identical results; the defaults are what bench.py times and what
  * the oracle tests run on, the others stay selectable for verification and A/B measurement (bench.py --opt name=value, environment
@@ -104,6 +110,9 @@ int vfsms_get_option(vfsms_ctx *ctx, int option, int *value_out);
 const char *vfsms_option_name(int option);
 /* Number of queries of the last tensor-core match that needed the exact fallback scan (synchronises the stream). */
 int vfsms_last_match_fallbacks(vfsms_ctx *ctx, int *count_out);
+/* Number of rescored candidates of the last tensor-core match whose GEMM score was further from the exact score than the
+ * error bound the guard relies on; 0 unless the bound is wrong (synchronises the stream). */
+int vfsms_last_match_bound_violations(vfsms_ctx *ctx, int *count_out);
 /* Number of keypoints of the last SURF run that the fixed-point window sampler handed to the reference sampler (synchronises). */
 int vfsms_last_describe_handovers(vfsms_ctx *ctx, int *count_out);
 

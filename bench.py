@@ -5,7 +5,8 @@ A "step" = one pass of the hot path (2 x ROI SURF detect+describe -> kNN(2) matc
 body of Stitcher.calculateOffsetForFeatureSearchIncre succeeding at i=1 in the starting direction, roiRatio 0.2,
 GPU-SURF parameters of ImageUtility.py:23-28) over a batch of synthetic tile pairs.
   value : whole-job pairs/s with tiles resident in HBM (device timing, max over ranks)
-  e2e   : same metric through the public host API (gpu.align_batch: pinned host ROIs -> H2D -> kernels -> D2H)
+  e2e   : same metric through the public host API (gpu.align_batches: pinned host ROIs -> H2D -> kernels -> D2H, the copy of
+          batch k+1 in flight while batch k runs; gpu.align_batch, one blocking call per batch, is timed beside it)
   --impl reference : the CPU port of the same path (oracle SURF on all host cores + cv2 BFMatcher + vote port)
 """
 import argparse
@@ -602,25 +603,38 @@ def main():
             nkp.append((r[p, 4], r[p, 5])); nmatch.append(r[p, 6])
     nkp = np.array(nkp, np.float64); mean_na, mean_nb = nkp[:, 0].mean(), nkp[:, 1].mean()
 
-    # ---- e2e: public host API with pinned host ROIs (H2D + kernels + D2H inside the timed region)
+    # ---- e2e: public host API with pinned host ROIs (H2D + kernels + D2H inside the timed region).  gpu.align_batches is
+    # the streaming form of gpu.align_batch: the copy of batch k+1 is in flight while batch k's kernels run (two input slots);
+    # every step's ROIs cross PCIe and every step's results come back inside the timed region.  Two distinct pinned
+    # batches alternate so that no upload could be skipped.  The one-call-per-batch form is timed beside it (e2e_sync).
     A0, B0, offs0 = batches[0]
-    hostA = torch.empty((P, L, TILE), dtype=torch.uint8).pin_memory(); hostB = torch.empty_like(hostA).pin_memory()
-    hostA.copy_(A0[:, TILE - L:, :]); hostB.copy_(B0[:, :L, :])
+    A1, B1, offs1 = batches[1 % NB]
+    hostA = torch.empty((2, P, L, TILE), dtype=torch.uint8).pin_memory(); hostB = torch.empty_like(hostA).pin_memory()
+    hostA[0].copy_(A0[:, TILE - L:, :]); hostB[0].copy_(B0[:, :L, :])
+    hostA[1].copy_(A1[:, TILE - L:, :]); hostB[1].copy_(B1[:, :L, :])
     nA, nB_ = hostA.numpy(), hostB.numpy()
-    for _ in range(2):
-        gpu.align_batch(nA, nB_, params=params, device=local)
+    e2e_steps = max(4, args.steps // 2)
+    for _ in gpu.align_batches(((nA[k & 1], nB_[k & 1]) for k in range(3)), params=params, device=local):
+        pass
     if world > 1:
         dist.barrier()
+    torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    e2e_steps = max(3, args.steps // 2)
-    for _ in range(e2e_steps):
-        res_host = gpu.align_batch(nA, nB_, params=params, device=local)
+    res_steps = list(gpu.align_batches(((nA[k & 1], nB_[k & 1]) for k in range(e2e_steps)), params=params, device=local))
     torch.cuda.synchronize(dev)
     dt_e2e = time.perf_counter() - t0
     te = torch.tensor([dt_e2e], device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * P * e2e_steps / float(te.item())
+    res_host = res_steps[0]
+    t0 = time.perf_counter()
+    for k in range(3):
+        res_sync = gpu.align_batch(nA[k & 1], nB_[k & 1], params=params, device=local)
+    torch.cuda.synchronize(dev)
+    e2e_sync_val = world * P * 3 / (time.perf_counter() - t0)
+    e2e_same = bool(all(np.array_equal(res_steps[k], res_steps[k & 1]) for k in range(e2e_steps)) and np.array_equal(res_sync, res_steps[0]))
+    nA, nB_ = nA[0], nB_[0]                # the first batch's ROIs serve the probes and the CPU baseline below
     e2e_ok = int(sum(int(r["status"] == 1 and abs(r["d_row"] + TILE - L - offs0[p, 0]) <= 1) for p, r in enumerate(res_host)))
 
     # ---- the other named configurations (auxiliary blocks; every rank takes part in the sharded ones)
@@ -749,7 +763,8 @@ def main():
                       "e2e_correct_pairs": "%d/%d" % (e2e_ok, P), "kernel_variants": variants},
            "clocks": clk, "gpu_launches": int(launches),
            "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * P * L * TILE), "d2h_bytes_per_step": int(P * 32),
-                   "steps": e2e_steps},
+                   "steps": e2e_steps, "api": "gpu.align_batches (vfsms_align_batch_upload / _run, two input slots)",
+                   "one_call_per_batch_pairs_per_s": e2e_sync_val, "streamed_results_equal_one_call_results": e2e_same},
            "roofline": roof, "stages_ms_per_step": stage_ms, "matcher": matcher, "surf_keypoints_per_s": surf_kps}
     if c4:
         out["c4"] = c4

@@ -198,6 +198,8 @@ void vfsms_destroy(vfsms_ctx *ctx)
                        &ctx->scratch0, &ctx->scratch1, &ctx->scratch2, &ctx->scratch3 };
     for (DevBuf *b : bufs) b->release();
     ctx->pinned_in.release(); ctx->pinned_out.release();
+    for (auto &sl : ctx->slots) { sl.a.release(); sl.b.release(); if (sl.uploaded) cudaEventDestroy(sl.uploaded); }
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     ctx->jpeg_pinned.release(); ctx->jpeg_coef.release(); ctx->jpeg_out.release(); ctx->jpeg_planes.release(); ctx->tiles.release(); ctx->tiles_bgr.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -422,6 +424,47 @@ int vfsms_align_batch_host(vfsms_ctx *ctx, const uint8_t *rois_a, const uint8_t 
     }
     return align_dev_regrow(ctx, ctx->img_a.as<uint8_t>(), ctx->img_b.as<uint8_t>(), n_pairs, rows, cols, cols, (int64_t)img_bytes, params, ratio,
                             offset_evaluate, results, st);
+}
+
+int vfsms_align_batch_upload(vfsms_ctx *ctx, int slot, const uint8_t *rois_a, const uint8_t *rois_b, int n_pairs,
+                             int rows, int cols, int stride, int64_t pair_stride)
+{
+    if (!ctx || slot < 0 || slot > 1 || !rois_a || !rois_b || n_pairs < 1 || rows < 1 || cols < 1) { vfsms_set_error("align_batch_upload: bad arguments"); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    vfsms_ctx::UploadSlot &s = ctx->slots[slot];
+    if (!s.uploaded) CUDA_TRY(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
+    int rc;
+    const size_t img_bytes = (size_t)rows * cols;
+    // a slot is written again only after vfsms_align_batch_run of its previous batch returned (that call synchronises)
+    if ((rc = s.a.reserve(img_bytes * n_pairs))) return rc;
+    if ((rc = s.b.reserve(img_bytes * n_pairs))) return rc;
+    if (stride == cols && pair_stride == (int64_t)img_bytes) {
+        CUDA_TRY(cudaMemcpyAsync(s.a.p, rois_a, img_bytes * n_pairs, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CUDA_TRY(cudaMemcpyAsync(s.b.p, rois_b, img_bytes * n_pairs, cudaMemcpyHostToDevice, ctx->copy_stream));
+    } else {
+        for (int p = 0; p < n_pairs; p++) {
+            CUDA_TRY(cudaMemcpy2DAsync(s.a.as<uint8_t>() + p * img_bytes, cols, rois_a + p * pair_stride, stride, cols, rows, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CUDA_TRY(cudaMemcpy2DAsync(s.b.as<uint8_t>() + p * img_bytes, cols, rois_b + p * pair_stride, stride, cols, rows, cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
+    }
+    CUDA_TRY(cudaEventRecord(s.uploaded, ctx->copy_stream));
+    s.n_pairs = n_pairs; s.rows = rows; s.cols = cols;
+    return 0;
+}
+
+int vfsms_align_batch_run(vfsms_ctx *ctx, int slot, const vfsms_surf_params *params, float ratio, int offset_evaluate,
+                          vfsms_pair_result *results)
+{
+    if (!ctx || slot < 0 || slot > 1 || !params || !results) { vfsms_set_error("align_batch_run: bad arguments"); return VFSMS_E_ARG; }
+    vfsms_ctx::UploadSlot &s = ctx->slots[slot];
+    if (!s.uploaded || s.n_pairs < 1) { vfsms_set_error("align_batch_run: slot %d holds no uploaded batch", slot); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, s.uploaded, 0));
+    const int n_pairs = s.n_pairs;
+    s.n_pairs = 0;                      // consumed: a second run needs a new upload
+    return align_dev_regrow(ctx, s.a.as<uint8_t>(), s.b.as<uint8_t>(), n_pairs, s.rows, s.cols, s.cols, (int64_t)s.rows * s.cols, params, ratio,
+                            offset_evaluate, results, ctx->stream);
 }
 
 /* ---------------------------------------------------------------- device-resident tile stack */

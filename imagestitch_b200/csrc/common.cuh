@@ -154,6 +154,10 @@ struct vfsms_ctx {
     SurfWorkspace surf;
     MatchWorkspace match;
     DevBuf img_a, img_b;      // staged ROIs (host variants)
+    // double-buffered input slots of vfsms_align_batch_upload / _run: the copy of the next batch runs on copy_stream
+    // while the kernels of the current one run on `stream`
+    struct UploadSlot { DevBuf a, b; cudaEvent_t uploaded = nullptr; int n_pairs = 0, rows = 0, cols = 0; } slots[2];
+    cudaStream_t copy_stream = nullptr;
     DevBuf results;           // vfsms_pair_result[pairs]
     DevBuf scratch0, scratch1, scratch2, scratch3;
     HostBuf pinned_in, pinned_out;

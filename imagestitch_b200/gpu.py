@@ -118,6 +118,52 @@ def align_batch(rois_a, rois_b, params=None, ratio=0.75, offset_evaluate=3, devi
     return res
 
 
+def _roi_stack(rois_a, rois_b):
+    A = np.asarray(rois_a)
+    B = np.asarray(rois_b)
+    if A.ndim == 2:
+        A = A[None]; B = B[None]
+    if A.dtype != np.uint8 or B.dtype != np.uint8 or A.shape != B.shape or A.ndim != 3:
+        raise TypeError("rois must be uint8 arrays of identical shape [P, h, w]")
+    if A.strides[2] != 1 or A.strides[1] < A.shape[2] or A.strides[0] < 0:
+        A = np.ascontiguousarray(A)
+    if B.strides != A.strides:
+        A = np.ascontiguousarray(A); B = np.ascontiguousarray(B)
+    return A, B
+
+
+def align_batches(batches, params=None, ratio=0.75, offset_evaluate=3, device=0, **kw):
+    """align_batch over a stream of batches, double-buffered: `batches` yields (rois_a, rois_b) host arrays [P, h, w]; the
+    generator yields one structured result array per batch, in order.  The host -> device copy of batch k+1 is enqueued
+    (vfsms_align_batch_upload, asynchronous when the arrays are in pinned memory) before batch k runs, so it overlaps
+    batch k's kernels; results are the same as calling align_batch on every batch."""
+    L = _lib.load()
+    ctx = _lib.context(device)
+    p = params if params is not None else surf_params(**kw)
+
+    def upload(slot, ab):
+        A, B = _roi_stack(*ab)
+        P, h, w = A.shape
+        check(L.vfsms_align_batch_upload(ctx, slot, _vp(A), _vp(B), P, h, w, A.strides[1], A.strides[0] if P > 1 else h * A.strides[1]),
+              "vfsms_align_batch_upload")
+        return slot, P, A, B                    # the arrays stay referenced until their batch has run
+
+    def run(job):
+        slot, P = job[0], job[1]
+        res = np.zeros(P, PAIR_RESULT_DTYPE)
+        check(L.vfsms_align_batch_run(ctx, slot, ctypes.byref(p), float(ratio), int(offset_evaluate), _vp(res)), "vfsms_align_batch_run")
+        return res
+
+    pending = None
+    for k, ab in enumerate(batches):
+        job = upload(k & 1, ab)
+        if pending is not None:
+            yield run(pending)
+        pending = job
+    if pending is not None:
+        yield run(pending)
+
+
 def align_batch_dev(rois_a, rois_b, results, params=None, ratio=0.75, offset_evaluate=3, stream=None):
     """Device-resident variant: rois_* are contiguous torch uint8 CUDA tensors [P, h, w]; results is a torch int32
     CUDA tensor [P, 8].  Asynchronous on `stream` (a torch.cuda.Stream) or the current torch stream."""

@@ -173,6 +173,15 @@ int vfsms_align_batch_dev(vfsms_ctx *ctx, const uint8_t *rois_a_dev, const uint8
                           int rows, int cols, int stride, int64_t pair_stride,
                           const vfsms_surf_params *params, float ratio, int offset_evaluate,
                           vfsms_pair_result *results_dev, void *stream);
+/* Double-buffered form of vfsms_align_batch_host for a stream of batches.  _upload enqueues the host -> device copy of one
+ * batch into input slot 0 or 1 on the context's copy stream and returns at once (pinned host memory makes the copy
+ * asynchronous; the buffers must stay valid until the matching _run returned).  _run waits for that slot's copy, aligns the
+ * batch exactly like vfsms_align_batch_host and returns the results.  Uploading batch k+1 into the other slot before running
+ * batch k hides its copy behind batch k's kernels.  A slot may be uploaded again once its _run has returned. */
+int vfsms_align_batch_upload(vfsms_ctx *ctx, int slot, const uint8_t *rois_a, const uint8_t *rois_b, int n_pairs,
+                             int rows, int cols, int stride, int64_t pair_stride);
+int vfsms_align_batch_run(vfsms_ctx *ctx, int slot, const vfsms_surf_params *params, float ratio, int offset_evaluate,
+                          vfsms_pair_result *results);
 
 /* Matcher on device-resident descriptors (bench / profiling hook for the BF matcher, ImageUtility.py:278-309):
  * exact fp32 kNN(2)+ratio for n_pairs descriptor sets laid out [pair][cap][dim], counts per pair on device. */

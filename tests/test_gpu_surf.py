@@ -136,3 +136,34 @@ def test_align_batch_matches_stagewise(gpu, synth_pair_rois):
         assert bool(r["status"]) == st and [int(r["d_row"]), int(r["d_col"])] == off
         assert int(r["votes"]) == votes
     assert abs(off[0] - true_off[0]) <= 1 and abs(off[1] - true_off[1]) <= 1
+
+
+def test_align_batches_stream_equals_one_call_per_batch(gpu):
+    """The double-buffered form (vfsms_align_batch_upload / _run): batches of different content, pair count and ROI
+    shape, pinned and pageable host memory -- every batch's results equal gpu.align_batch on that batch."""
+    import torch
+    from imagestitch_b200 import synth
+    batches = []
+    for k, (P, size, overlap) in enumerate([(3, 384, 96), (2, 384, 96), (1, 320, 80), (4, 384, 128), (3, 384, 96)]):
+        A = np.empty((P, overlap, size), np.uint8); B = np.empty_like(A)
+        for p in range(P):
+            a, b, _ = synth.pair(seed=100 + 10 * k + p, size=size, overlap=overlap, direction=1)
+            A[p] = a[size - overlap:]; B[p] = b[:overlap]
+        if k % 2 == 0 and torch.cuda.is_available():      # pinned: the upload really is asynchronous
+            tA = torch.from_numpy(A).pin_memory(); tB = torch.from_numpy(B).pin_memory()
+            A, B = tA.numpy(), tB.numpy()
+            batches.append((A, B, tA, tB))
+        else:
+            batches.append((A, B))
+    streamed = list(gpu.align_batches((b[0], b[1]) for b in batches))
+    assert len(streamed) == len(batches)
+    for b, got in zip(batches, streamed):
+        want = gpu.align_batch(b[0], b[1])
+        assert np.array_equal(got, want)
+    # a run without an upload is an error, not stale data
+    from imagestitch_b200 import _lib
+    import ctypes
+    res = np.zeros(1, gpu.PAIR_RESULT_DTYPE)
+    p = gpu.surf_params()
+    rc = _lib.load().vfsms_align_batch_run(_lib.context(0), 0, ctypes.byref(p), 0.75, 3, res.ctypes.data_as(ctypes.c_void_p))
+    assert rc != 0 and b"no uploaded batch" in _lib.load().vfsms_last_error()

@@ -373,6 +373,92 @@ __device__ __forceinline__ void det_layer_fixed(const SurfPlan &plan, const int3
     }
 }
 
+// phase 2b of hessian_nms_kernel for one in-layer maximum (tile sample idx of layer l): the 26-neighbour test against the
+// layers below and above, sub-sample interpolation (Brown & Lowe step of the CPU code), laplacian sign, candidate push.
+template <int OCT>
+__device__ __forceinline__ void nms_finish(const SurfPlan &plan, const int32_t *__restrict__ I, int W, const float *s_det, int SW, int SH,
+                                           int tile_j0, int tile_i0, int TX, int idx, int l, int b, float *cand, int32_t *counters, int cand_cap)
+{
+    constexpr int o = OCT, step = 1 << OCT;
+    const int ty = idx / TX, tx = idx - ty * TX;
+    const int li = tile_i0 + ty, lj = tile_j0 + tx;
+    const SurfLayer &L = plan.layer[o][l];
+    const float *c1 = s_det + (l * SH + ty + 1) * SW + tx + 1;
+    const float val0 = c1[0];
+    const float *c0 = c1 - SH * SW, *c2 = c1 + SH * SW;
+    float N9[3][9];
+    const float *cs[3] = { c0, c1, c2 };
+    bool is_max = true;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const float *c = cs[q];
+        N9[q][0] = c[-SW - 1]; N9[q][1] = c[-SW]; N9[q][2] = c[-SW + 1];
+        N9[q][3] = c[-1];      N9[q][4] = c[0];   N9[q][5] = c[1];
+        N9[q][6] = c[SW - 1];  N9[q][7] = c[SW];  N9[q][8] = c[SW + 1];
+    }
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+#pragma unroll
+        for (int k = 0; k < 9; k++)
+            if (!(q == 1 && k == 4)) is_max = is_max && (val0 > N9[q][k]);
+    if (!is_max) return;
+    const int size = L.size;
+    const int sum_i = step * (li - (size / 2) / step), sum_j = step * (lj - (size / 2) / step);
+    float py = sum_i + (size - 1) * 0.5f, px = sum_j + (size - 1) * 0.5f, psz = (float)size;
+    const int ds = size - plan.layer[o][l - 1].size;
+    float bb[3] = { -(N9[1][5] - N9[1][3]) / 2, -(N9[1][7] - N9[1][1]) / 2, -(N9[2][4] - N9[0][4]) / 2 };
+    float A[3][3];
+    A[0][0] = N9[1][3] - 2 * N9[1][4] + N9[1][5];
+    A[0][1] = (N9[1][8] - N9[1][6] - N9[1][2] + N9[1][0]) / 4;
+    A[0][2] = (N9[2][5] - N9[2][3] - N9[0][5] + N9[0][3]) / 4;
+    A[1][0] = A[0][1];
+    A[1][1] = N9[1][1] - 2 * N9[1][4] + N9[1][7];
+    A[1][2] = (N9[2][7] - N9[2][1] - N9[0][7] + N9[0][1]) / 4;
+    A[2][0] = A[0][2]; A[2][1] = A[1][2];
+    A[2][2] = N9[0][4] - 2 * N9[1][4] + N9[2][4];
+    float x[3];
+    solve3(A, bb, x);
+    const bool ok = (x[0] != 0 || x[1] != 0 || x[2] != 0) && fabsf(x[0]) <= 1 && fabsf(x[1]) <= 1 && fabsf(x[2]) <= 1;
+    if (!ok) return;
+    px += x[0] * step;
+    py += x[1] * step;
+    psz = (float)__float2int_rn(psz + x[2] * ds);
+    // laplacian sign: recompute trace at the maximum (rare path)
+    // laplacian sign from trace = dxx + dyy, recomputed box by box from the global integral
+    const int32_t *org = I + (size_t)((li - L.margin) * step) * W + (lj - L.margin) * step;
+    double tdx = 0, tdy = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const HaarBox &fx = L.dx[k], &fy = L.dy[k];
+        const int vx = __ldg(org + fx.y1 * W + fx.x1) + __ldg(org + fx.y2 * W + fx.x2) - __ldg(org + fx.y2 * W + fx.x1) - __ldg(org + fx.y1 * W + fx.x2);
+        const int vy = __ldg(org + fy.y1 * W + fy.x1) + __ldg(org + fy.y2 * W + fy.x2) - __ldg(org + fy.y2 * W + fy.x1) - __ldg(org + fy.y1 * W + fy.x2);
+        tdx += (double)((float)vx * fx.w); tdy += (double)((float)vy * fy.w);
+    }
+    const float trace = (float)tdx + (float)tdy;
+    const int slot = atomicAdd(&counters[b * 4 + 0], 1);
+    if (slot < cand_cap) {
+        float4 *dst = (float4 *)(cand + ((size_t)b * cand_cap + slot) * KP_STRIDE);
+        dst[0] = make_float4(px, py, psz, -1.f);
+        dst[1] = make_float4(val0, (float)o, (float)((trace > 0) - (trace < 0)), 0.f);
+    }
+}
+
+// 4-byte global -> shared copy
+__device__ __forceinline__ void stage_copy4(int32_t *dst, const int32_t *src)
+{
+#ifdef __CUDACC__
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#else
+    *dst = *src;        // CPU emulation build (tests/cuda_emu)
+#endif
+}
+__device__ __forceinline__ void stage_copy_wait()
+{
+#ifdef __CUDACC__
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 // STAGE = true: the integral footprint of the tile (all layers of the octave) is copied to shared memory once and the
 // 32 corner reads per sample-layer become LDS (octaves whose footprint fits: 0 and 1); false: reads go to L1/L2.
 // One launch per octave (OCT is a template parameter, see hessian_responses).
@@ -393,19 +479,27 @@ __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_co
     const int nl = plan.n_layers;
     constexpr int TX = ht_x(OCT), TY = ht_y(OCT), SW = TX + 2, SH = TY + 2;
     float *s_det = s_dyn;                                   // [n_layers][TY+2][TX+2]
-    int32_t *s_int = (int32_t *)(s_dyn + nl * SW * SH);     // [stage_rows][stage_cols] (STAGE only)
+    int *s_list = (int *)(s_dyn + nl * SW * SH);            // [0] entry count, [4 ..) queue of in-layer maxima (phase 2)
+    int32_t *s_int = (int32_t *)(s_list + 4 + TX * TY);     // [stage_rows][stage_cols] (STAGE only)
     const int i0 = tile_y * TY - 1, j0 = tile_x * TX - 1;   // layer coords of the smem origin
     const int RW = plan.stage_cols[o];
     const int r_base = i0 * step + plan.stage_off_min[o], c_base = j0 * step + plan.stage_off_min[o];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    if (threadIdx.x == 0) s_list[0] = 0;
     if (STAGE) {
+        // global -> shared without a register round trip (cp.async, 4 bytes: the integral rows have an odd pitch); the
+        // load -> store dependency of the plain copy was 18 % of this kernel's stall samples.  Tiles whose footprint lies
+        // inside the image skip the coordinate clamps.
         const int RH = plan.stage_rows[o];
+        const bool inside = r_base >= 0 && r_base + RH - 1 <= plan.rows && c_base >= 0 && c_base + RW - 1 <= plan.cols;
         for (int rr = warp; rr < RH; rr += HT_THREADS / 32) {           // one warp per footprint row: no index division
             const int32_t *src = I + (size_t)min(max(r_base + rr, 0), plan.rows) * W;
             int32_t *dst = s_int + rr * RW;
-            for (int cc = lane; cc < RW; cc += 32) dst[cc] = __ldg(src + min(max(c_base + cc, 0), plan.cols));
+            if (inside) for (int cc = lane; cc < RW; cc += 32) stage_copy4(dst + cc, src + c_base + cc);
+            else for (int cc = lane; cc < RW; cc += 32) stage_copy4(dst + cc, src + min(max(c_base + cc, 0), plan.cols));
         }
+        stage_copy_wait();
         __syncthreads();
     }
 
@@ -443,75 +537,31 @@ __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_co
     }
     __syncthreads();
 
-    // phase 2: 3x3x3 non-maximum suppression on the middle layers, interpolation, candidate push
+    // phase 2a: threshold and 3x3 maximum inside the own layer.  A warp runs the whole neighbourhood test as soon as one
+    // lane needs it, so the cheap in-layer test runs here and the few survivors (in-layer maxima above the threshold) are
+    // queued; phase 2b gives every queued sample its own lane for the two neighbour layers, the interpolation and the push.
     for (int idx = threadIdx.x; idx < TX * TY; idx += HT_THREADS) {
         const int ty = idx / TX, tx = idx - ty * TX;
         const int li = tile_y * TY + ty, lj = tile_x * TX + tx;
         if (li >= lrows || lj >= lcols) continue;
         for (int l = 1; l < nl - 1; l++) {
-            const float *c1 = s_det + (l * SH + ty + 1) * SW + tx + 1;
-            const float val0 = c1[0];
+            const float *c = s_det + (l * SH + ty + 1) * SW + tx + 1;
+            const float val0 = c[0];
             if (!(val0 > plan.threshold)) continue;                      // cheapest test first: most samples stop here
-            const SurfLayer &L = plan.layer[o][l];
             const int margin = (plan.layer[o][l + 1].size / 2) / step + 1;
             if (li < margin || li >= lrows - margin || lj < margin || lj >= lcols - margin) continue;
-            const float *c0 = c1 - SH * SW, *c2 = c1 + SH * SW;
-            float N9[3][9];
-            const float *cs[3] = { c0, c1, c2 };
-            bool is_max = true;
-#pragma unroll
-            for (int q = 0; q < 3; q++) {
-                const float *c = cs[q];
-                N9[q][0] = c[-SW - 1]; N9[q][1] = c[-SW]; N9[q][2] = c[-SW + 1];
-                N9[q][3] = c[-1];      N9[q][4] = c[0];   N9[q][5] = c[1];
-                N9[q][6] = c[SW - 1];  N9[q][7] = c[SW];  N9[q][8] = c[SW + 1];
-            }
-#pragma unroll
-            for (int q = 0; q < 3; q++)
-#pragma unroll
-                for (int k = 0; k < 9; k++)
-                    if (!(q == 1 && k == 4)) is_max = is_max && (val0 > N9[q][k]);
-            if (!is_max) continue;
-            const int size = L.size;
-            const int sum_i = step * (li - (size / 2) / step), sum_j = step * (lj - (size / 2) / step);
-            float py = sum_i + (size - 1) * 0.5f, px = sum_j + (size - 1) * 0.5f, psz = (float)size;
-            const int ds = size - plan.layer[o][l - 1].size;
-            float bb[3] = { -(N9[1][5] - N9[1][3]) / 2, -(N9[1][7] - N9[1][1]) / 2, -(N9[2][4] - N9[0][4]) / 2 };
-            float A[3][3];
-            A[0][0] = N9[1][3] - 2 * N9[1][4] + N9[1][5];
-            A[0][1] = (N9[1][8] - N9[1][6] - N9[1][2] + N9[1][0]) / 4;
-            A[0][2] = (N9[2][5] - N9[2][3] - N9[0][5] + N9[0][3]) / 4;
-            A[1][0] = A[0][1];
-            A[1][1] = N9[1][1] - 2 * N9[1][4] + N9[1][7];
-            A[1][2] = (N9[2][7] - N9[2][1] - N9[0][7] + N9[0][1]) / 4;
-            A[2][0] = A[0][2]; A[2][1] = A[1][2];
-            A[2][2] = N9[0][4] - 2 * N9[1][4] + N9[2][4];
-            float x[3];
-            solve3(A, bb, x);
-            const bool ok = (x[0] != 0 || x[1] != 0 || x[2] != 0) && fabsf(x[0]) <= 1 && fabsf(x[1]) <= 1 && fabsf(x[2]) <= 1;
-            if (!ok) continue;
-            px += x[0] * step;
-            py += x[1] * step;
-            psz = (float)__float2int_rn(psz + x[2] * ds);
-            // laplacian sign: recompute trace at the maximum (rare path)
-            // laplacian sign from trace = dxx + dyy, recomputed box by box from the global integral
-            const int32_t *org = I + (size_t)((li - L.margin) * step) * W + (lj - L.margin) * step;
-            double tdx = 0, tdy = 0;
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const HaarBox &fx = L.dx[k], &fy = L.dy[k];
-                const int vx = __ldg(org + fx.y1 * W + fx.x1) + __ldg(org + fx.y2 * W + fx.x2) - __ldg(org + fx.y2 * W + fx.x1) - __ldg(org + fx.y1 * W + fx.x2);
-                const int vy = __ldg(org + fy.y1 * W + fy.x1) + __ldg(org + fy.y2 * W + fy.x2) - __ldg(org + fy.y2 * W + fy.x1) - __ldg(org + fy.y1 * W + fy.x2);
-                tdx += (double)((float)vx * fx.w); tdy += (double)((float)vy * fy.w);
-            }
-            const float trace = (float)tdx + (float)tdy;
-            const int slot = atomicAdd(&counters[b * 4 + 0], 1);
-            if (slot < cand_cap) {
-                float4 *dst = (float4 *)(cand + ((size_t)b * cand_cap + slot) * KP_STRIDE);
-                dst[0] = make_float4(px, py, psz, -1.f);
-                dst[1] = make_float4(val0, (float)o, (float)((trace > 0) - (trace < 0)), 0.f);
-            }
+            if (!(val0 > c[-SW - 1] && val0 > c[-SW] && val0 > c[-SW + 1] && val0 > c[-1] && val0 > c[1] &&
+                  val0 > c[SW - 1] && val0 > c[SW] && val0 > c[SW + 1])) continue;
+            const int slot = atomicAdd(s_list, 1);
+            if (slot < TX * TY) s_list[4 + slot] = idx | (l << 16);
+            else nms_finish<OCT>(plan, I, W, s_det, SW, SH, tile_x * TX, tile_y * TY, TX, idx, l, b, cand, counters, cand_cap);    // queue full
         }
+    }
+    __syncthreads();
+    const int n_list = min(s_list[0], TX * TY);
+    for (int e = threadIdx.x; e < n_list; e += HT_THREADS) {
+        const int v = s_list[4 + e];
+        nms_finish<OCT>(plan, I, W, s_det, SW, SH, tile_x * TX, tile_y * TY, TX, v & 0xffff, v >> 16, b, cand, counters, cand_cap);
     }
 }
 
@@ -1252,7 +1302,8 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
     const int total_tiles = plan.tile_begin[plan.n_octaves];
     if (total_tiles > 0) {
         StageTimer t_h(ctx, st, VFSMS_STAGE_HESSIAN);
-        auto smem_det_of = [&](int o) { return (size_t)plan.n_layers * (ht_x(o) + 2) * (ht_y(o) + 2) * 4; };
+        // det planes of every layer over the haloed tile + the queue of in-layer maxima (count + one entry per tile sample)
+        auto smem_det_of = [&](int o) { return (size_t)plan.n_layers * (ht_x(o) + 2) * (ht_y(o) + 2) * 4 + (size_t)(4 + ht_x(o) * ht_y(o)) * 4; };
         // octaves whose integral footprint fits in shared memory next to the det tile (two CTAs per SM)
         int o_split = 0;
         static const bool no_stage = getenv("VFSMS_HESSIAN_UNSTAGED") != nullptr;     // debugging aid

@@ -316,11 +316,25 @@ __device__ __forceinline__ void hessian_responses(Ptr o, const SurfLayer &L, flo
 
 #include "hessian_tables.inc"
 
+// Shared-memory address of box corner k relative to the sample origin.  Octave 0: plain [row][col] footprint.  Octave 1
+// samples every second column, so the footprint is staged as two column-parity planes [parity][row][col / 2] and the lanes
+// of a warp (consecutive samples) read consecutive words instead of every second one (2-way bank conflict on all 32 reads).
+template <int OCT, int L>
+struct HessAddr {
+    using F = HessFixed<OCT, L>;
+    static constexpr bool deint = OCT == 1;
+    static __host__ __device__ constexpr int off(int k)
+    {
+        return deint ? (F::dx(k) & 1) * F::plane + F::dy(k) * F::pitch2 + (F::dx(k) >> 1) : F::dy(k) * F::pitch + F::dx(k);
+    }
+    static __host__ __device__ constexpr float w(int k) { return F::w(k); }
+};
+
 // det of one sample for the default layer structure: every corner offset and weight is an immediate
 template <int OCT, int L>
 __device__ __forceinline__ float det_fixed(const int32_t *o)
 {
-    using T = HessFixed<OCT, L>;
+    using T = HessAddr<OCT, L>;
     float dx, dy, dxy;
     {
         const int t0 = o[T::off(0)], t1 = o[T::off(1)], t2 = o[T::off(2)], t3 = o[T::off(3)];
@@ -368,7 +382,10 @@ __device__ __forceinline__ void det_layer_fixed(const SurfPlan &plan, const int3
         const int ly = idx / SW, lx = idx - ly * SW;
         const int si = i0 + ly - T::margin, sj = j0 + lx - T::margin;
         float det = 0.f;
-        if (si >= 0 && si < ni && sj >= 0 && sj < nj) det = det_fixed<OCT, L>(s_int + (si * step - r_base) * RW - c_base + sj * step);
+        if (si >= 0 && si < ni && sj >= 0 && sj < nj) {
+            if constexpr (HessAddr<OCT, L>::deint) det = det_fixed<OCT, L>(s_int + (si * step - r_base) * T::pitch2 + sj - (c_base >> 1));   // c_base is even
+            else det = det_fixed<OCT, L>(s_int + (si * step - r_base) * RW - c_base + sj * step);
+        }
         s_det[L * SH * SW + idx] = det;
     }
 }
@@ -496,7 +513,12 @@ __global__ void __launch_bounds__(HT_THREADS) hessian_nms_kernel(const __grid_co
         for (int rr = warp; rr < RH; rr += HT_THREADS / 32) {           // one warp per footprint row: no index division
             const int32_t *src = I + (size_t)min(max(r_base + rr, 0), plan.rows) * W;
             int32_t *dst = s_int + rr * RW;
-            if (inside) for (int cc = lane; cc < RW; cc += 32) stage_copy4(dst + cc, src + c_base + cc);
+            if constexpr (FIXED && OCT == 1) {              // column-parity planes (HessAddr)
+                using F = HessFixed<1, 0>;
+                dst = s_int + rr * F::pitch2;
+                for (int cc = lane; cc < RW; cc += 32)
+                    stage_copy4(dst + (cc & 1) * F::plane + (cc >> 1), src + (inside ? c_base + cc : min(max(c_base + cc, 0), plan.cols)));
+            } else if (inside) for (int cc = lane; cc < RW; cc += 32) stage_copy4(dst + cc, src + c_base + cc);
             else for (int cc = lane; cc < RW; cc += 32) stage_copy4(dst + cc, src + min(max(c_base + cc, 0), plan.cols));
         }
         stage_copy_wait();
@@ -1337,7 +1359,8 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         static const bool no_fixed = getenv("VFSMS_HESSIAN_GENERIC") != nullptr;           // debugging aid
         auto check_fixed = [&](int o, int l, int size, int margin, int pitch, int (*off)(int), float (*w)(int)) {
             const SurfLayer &L = plan.layer[o][l];
-            bool ok = L.size == size && L.margin == margin && plan.stage_cols[o] == pitch;
+            bool ok = L.size == size && L.margin == margin && plan.stage_cols[o] == pitch && plan.stage_rows[o] == HessFixed<0, 0>::rows * (o == 0) + HessFixed<1, 0>::rows * (o == 1) &&
+                      (plan.stage_off_min[o] & 1) == 0;
             for (int k = 0; ok && k < 32; k++) ok = L.off[k] == off(k);
             const float pw[10] = { L.dx[0].w, L.dx[1].w, L.dx[2].w, L.dy[0].w, L.dy[1].w, L.dy[2].w, L.dxy[0].w, L.dxy[1].w, L.dxy[2].w, L.dxy[3].w };
             for (int k = 0; ok && k < 10; k++) { const float wk = w(k); ok = memcmp(&pw[k], &wk, 4) == 0; }
@@ -1352,7 +1375,8 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
             const int nt = plan.tile_begin[o + 1] - plan.tile_begin[o];
             if (nt <= 0) continue;
             const bool staged = o < o_split;
-            const size_t sm = smem_det_of(o) + (staged ? (size_t)plan.stage_rows[o] * plan.stage_cols[o] * 4 : 0);
+            size_t sm = smem_det_of(o) + (staged ? (size_t)plan.stage_rows[o] * plan.stage_cols[o] * 4 : 0);
+            if (o == 1 && staged && fixed_ok[1]) sm = smem_det_of(1) + (size_t)2 * HessFixed<1, 0>::plane * 4;      // two column-parity planes
             const dim3 grid(nt, batch);
 #define HL(S, O) hessian_nms_kernel<S, O><<<grid, HT_THREADS, sm, st>>>(plan, ws.integral.as<int32_t>(), ws.cand.as<float>(), ws.counters.as<int32_t>(), ws.cand_cap)
             switch (o) {

@@ -702,7 +702,10 @@ def main():
         matcher = {"stage_ms": stage_ms["match_tc"], "algorithmic_tflops": fl / tm / 1e12, "frac_of_bf16_sustained": fl / tm / 1e12 / peaks["bf16_tflops_sustained"],
                    "gbs": (4 * D * (mean_na + mean_nb) + 16 * mean_na) * P / tm / 1e9,
                    "kernel": args.matcher or "tc", "exact_rescans_last_step": gpu.last_match_fallbacks(local), "queries_per_step": int(mean_na * P),
-                   "note": "stage = split + tcgen05 GEMM + exact rescoring + fallback; the GEMM executes 3.5x the algorithmic FLOPs (3-term split-bf16 + norm columns)"}
+                   "error_bound_violations_last_step": gpu.last_match_bound_violations(local),
+                   "executed_over_algorithmic_flops": {"tc_bf16x3": (3 * D + 16) / D, "tc_f16x2": (2 * D + 16) / D}.get(args.matcher, (D + 16) / D) if args.matcher not in ("simt",) else 1.0,
+                   "note": "stage = operand rows + tcgen05 GEMM with top-4 epilogue + exact fp32 rescoring + exact rescan of flagged queries; "
+                           "default operands: fp16 rows of K' = D + 16 columns (the norm columns ride in a 16-column k-step)"}
     surf_kps = (mean_na + mean_nb) * P * world / (sum(stage_ms.get(k, 0) for k in ("integral", "hessian_nms", "rank_sort", "validate_compact", "orient_describe")) * 1e-3)
 
     # ---- CPU baseline on a bounded sample of the same workload (rank 0, N = 1 only)

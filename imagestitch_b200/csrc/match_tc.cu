@@ -2,24 +2,27 @@
 //
 // Replaces the O(nA*nB*D) part of Method.matchDescriptors (ImageUtility.py:278-309, BF L2 kNN(2)).
 //
-//   1. prep_split_kernel      fp32 descriptors -> bf16 rows of K' = 3D + 64 columns:
-//                               query  row: [ a_hi | a_hi | a_lo | 1, 1, 0 ... ]
-//                               train  row: [-2b_hi|-2b_lo|-2b_hi| nb_hi, nb_lo, 0 ... ]     (nb = ||b||^2)
-//                             so that  <query row, train row> = ||b||^2 - 2 a.b  up to ~2^-17 relative error
-//                             (3-term split-bf16 product; the hi*hi + hi*lo + lo*hi terms of (a_hi+a_lo).(b_hi+b_lo)).
+//   1. prep_split_kernel      fp32 descriptors -> 16-bit operand rows whose product is  ||b||^2 - 2 a.b  (nb = ||b||^2):
+//                               fp16 x1 (default)  query [ a | 1, 1, 0 ... ]               train [ -2b | nb_hi, nb_lo, 0 ... ]
+//                               fp16 x2            query [ a_hi | a_lo | 1, 1 ... ]        train [ -2b | -2b | nb ... ]
+//                               bf16 x3            query [ a_hi | a_hi | a_lo | 1, 1 ... ] train [ -2b_hi | -2b_lo | -2b_hi | nb ... ]
+//                             K' = terms * D + 16 columns take part (only the used 16-column steps of the last k-block are
+//                             issued).  The kernel also measures the rounding error norms of the rows it writes.
 //   2. match_tc_pair_kernel   persistent warp-specialised GEMM on CTA pairs (the default): TMA (SWIZZLE_128B) -> smem ->
-//                             tcgen05.mma.cta_group::2 (256 x 256 x 16 per step, kind::f16, bf16 in / fp32 accumulate in TMEM,
-//                             two accumulator buffers) -> epilogue warps read TMEM with tcgen05.ld and keep a running top-4
-//                             of (score | column) keys per query row and column half, branch-free.  Each CTA's 128 x K'
-//                             query tile stays resident in shared memory while its half of every train tile streams through
-//                             a 7-stage mbarrier ring.  Nothing but 8 candidates per query is written to HBM.
+//                             tcgen05.mma.cta_group::2 (256 x 256 x 16 per step, kind::f16, fp32 accumulate in TMEM, two
+//                             accumulator buffers) -> epilogue warps read TMEM with tcgen05.ld and keep a running top-4 of
+//                             (score | column) keys per query row and column half; the merge network runs only for groups
+//                             of four scores in which some row of the warp can still improve.  Each CTA's 128 x K' query
+//                             tile stays resident in shared memory while its half of every train tile streams through a
+//                             7-stage mbarrier ring.  Nothing but 8 candidates per query is written to HBM.
 //      match_tc_kernel        the same on single CTAs (128 x 128 tiles, cta_group::1); kept for verification and as the
 //                             subject of the -DTC_TIMING probes that located the shared-memory operand bottleneck.
-//   3. rescore_kernel         exact fp32 distances (serial k order, no FMA: the CPU value) of the candidates, best two by
-//                             (distance, index), plus a guard: if the second best exact score is not separated from the
-//                             worst kept candidate by more than the split-bf16 error bound, the query is flagged ...
-//   4. fallback_scan_kernel   ... and rescanned exactly against every train row (all flagged queries of a pair together).  Results are therefore identical to the
-//                             exact SIMT kernel (match.cu) by construction, not by luck.
+//   3. rescore_kernel         exact fp32 distances (serial k order, no FMA: the CPU value) of the candidates that can be
+//                             one of the best two, best two by (distance, index), plus a guard: if the second best exact
+//                             score is not separated from the worst kept key by more than the operand error bound, the
+//                             query is flagged ...
+//   4. fallback_scan_kernel   ... and rescanned exactly against every train row, all flagged queries of a pair together.
+//                             Results are therefore identical to the exact SIMT kernel (match.cu) by construction, not by luck.
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>

@@ -418,6 +418,10 @@ int vfsms_align_batch_host(vfsms_ctx *ctx, const uint8_t *rois_a, const uint8_t 
     const size_t img_bytes = (size_t)rows * cols;
     if ((rc = ctx->img_a.reserve(img_bytes * n_pairs))) return rc;
     if ((rc = ctx->img_b.reserve(img_bytes * n_pairs))) return rc;
+    if (stride == cols && pair_stride == (int64_t)img_bytes) {          // packed ROIs: one copy per side
+        CUDA_TRY(cudaMemcpyAsync(ctx->img_a.p, rois_a, img_bytes * n_pairs, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ctx->img_b.p, rois_b, img_bytes * n_pairs, cudaMemcpyHostToDevice, st));
+    } else
     for (int p = 0; p < n_pairs; p++) {
         CUDA_TRY(cudaMemcpy2DAsync(ctx->img_a.as<uint8_t>() + p * img_bytes, cols, rois_a + p * pair_stride, stride, cols, rows, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpy2DAsync(ctx->img_b.as<uint8_t>() + p * img_bytes, cols, rois_b + p * pair_stride, stride, cols, rows, cudaMemcpyHostToDevice, st));

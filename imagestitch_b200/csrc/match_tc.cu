@@ -34,7 +34,9 @@
 #define TC_KB 64                 // bf16 elements per k-block = 128 bytes = one swizzle row
 #define TC_STAGES 7
 #define TC_TOPK 4
-#define TC_EPI_GROUPS 2          // epilogue warpgroups; group g scans columns [g*64, g*64+64) of every tile
+#ifndef TC_EPI_GROUPS
+#define TC_EPI_GROUPS 2          // epilogue warpgroups; group g scans its 1 / TC_EPI_GROUPS share of the columns of every tile.
+#endif                           // 4 (16 epilogue warps, 16 candidates per query) measured slower: GEMM 1.07 vs 0.95 ms, rescoring 0.22 vs 0.13 ms
 #define TC_MAX_KBLOCKS 7         // K' <= 448  (D <= 128)
 #define TC_THREADS (128 + 128 * TC_EPI_GROUPS)
 // Warp roles.  The schedulers favour the HIGHEST warp id of a sub-partition, so the two latency-critical single-thread
@@ -287,10 +289,10 @@ __device__ __forceinline__ void running_insert(float s, int tile, float (&r)[4],
 // the scores are in registers.
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint64_t *acc_empty, int lane, int tile, float (&r)[4], int (&t)[4])
 {
-    static_assert(TC_TOPK == 4 && TC_N / TC_EPI_GROUPS == 64, "epilogue is written for top-4 over 64-column half tiles");
+    static_assert(TC_TOPK == 4 && (TC_N / TC_EPI_GROUPS == 64 || TC_N / TC_EPI_GROUPS == 32), "epilogue is written for top-4 over 64- or 32-column shares");
     uint32_t v0[32], v1[32];
     tmem_ld32_issue(taddr, v0);
-    tmem_ld32_issue(taddr + 32, v1);
+    if (TC_N / TC_EPI_GROUPS == 64) tmem_ld32_issue(taddr + 32, v1);
     tmem_ld_wait();
     tc_fence_before();
     __syncwarp();
@@ -298,7 +300,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint64_t *acc_empt
     float l[4] = { FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX };
     float thr = r[3];
     tile_top4(v0, 0, l, thr);
-    tile_top4(v1, 32, l, thr);
+    if (TC_N / TC_EPI_GROUPS == 64) tile_top4(v1, 32, l, thr);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         if (!__any_sync(0xffffffffu, l[k] < r[3])) break;
@@ -620,26 +622,36 @@ match_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             for (int nt = nt0; nt < nt1; nt++) {
                 mbar_wait(&sh->acc_full[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * TC2_N + grp * (TC2_N / 2);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * TC2_N + grp * (TC2_N / TC_EPI_GROUPS);
                 const uint32_t acc_empty_leader = mapa_u32(smem_u32(&sh->acc_empty[acc]), 0);
                 float l[4] = { FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX };
                 float thr = r[3];
                 uint32_t v0[32], v1[32];
-                // TMEM drains at 16 B/clk per sub-partition (256 cycles per x32 load): the next 32 columns are in flight
-                // while the previous 32 go through the selection
-                tmem_ld32_issue(taddr, v0); tmem_ld32_issue(taddr + 32, v1);
-                tmem_ld_wait();
-                tile_top4(v0, 0, l, thr);
-                tmem_ld32_issue(taddr + 64, v0);
-                tile_top4(v1, 32, l, thr);
-                tmem_ld_wait();
-                tmem_ld32_issue(taddr + 96, v1);
-                tile_top4(v0, 64, l, thr);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(acc_empty_leader);            // scores are in registers: hand the buffer back
-                tile_top4(v1, 96, l, thr);
+                if constexpr (TC2_N / TC_EPI_GROUPS == 128) {
+                    // TMEM drains at 16 B/clk per sub-partition (256 cycles per x32 load): the next 32 columns are in flight
+                    // while the previous 32 go through the selection
+                    tmem_ld32_issue(taddr, v0); tmem_ld32_issue(taddr + 32, v1);
+                    tmem_ld_wait();
+                    tile_top4(v0, 0, l, thr);
+                    tmem_ld32_issue(taddr + 64, v0);
+                    tile_top4(v1, 32, l, thr);
+                    tmem_ld_wait();
+                    tmem_ld32_issue(taddr + 96, v1);
+                    tile_top4(v0, 64, l, thr);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(acc_empty_leader);            // scores are in registers: hand the buffer back
+                    tile_top4(v1, 96, l, thr);
+                } else {
+                    static_assert(TC2_N / TC_EPI_GROUPS == 64, "two or four column groups");
+                    tmem_ld32_issue(taddr, v0); tmem_ld32_issue(taddr + 32, v1);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(acc_empty_leader);        // scores are in registers: hand the buffer back
+                    tile_top4(v0, 0, l, thr); tile_top4(v1, 32, l, thr);
+                }
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     if (!__any_sync(0xffffffffu, l[k] < r[3])) break;

@@ -627,6 +627,7 @@ match_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 float l[4] = { FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX };
                 float thr = r[3];
                 uint32_t v0[32], v1[32];
+                static_assert(TC2_N / TC_EPI_GROUPS == 128 || TC2_N / TC_EPI_GROUPS == 64, "two or four column groups");
                 if constexpr (TC2_N / TC_EPI_GROUPS == 128) {
                     // TMEM drains at 16 B/clk per sub-partition (256 cycles per x32 load): the next 32 columns are in flight
                     // while the previous 32 go through the selection
@@ -644,7 +645,6 @@ match_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     if (lane == 0) mbar_arrive_cluster(acc_empty_leader);            // scores are in registers: hand the buffer back
                     tile_top4(v1, 96, l, thr);
                 } else {
-                    static_assert(TC2_N / TC_EPI_GROUPS == 64, "two or four column groups");
                     tmem_ld32_issue(taddr, v0); tmem_ld32_issue(taddr + 32, v1);
                     tmem_ld_wait();
                     tc_fence_before();

@@ -63,7 +63,7 @@ int vfsms_set_matcher(vfsms_ctx *ctx, int mode)
     return 0;
 }
 static const char *const k_option_names[VFSMS_OPT_COUNT] = { "describe", "sort", "lpt", "entropy" };
-static const int k_option_max[VFSMS_OPT_COUNT] = { 8, 1, 3, 1 };
+static const int k_option_max[VFSMS_OPT_COUNT] = { 3, 1, 3, 1 };
 static int *option_slot(vfsms_ctx *ctx, int option)
 {
     switch (option) {

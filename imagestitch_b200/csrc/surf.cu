@@ -1182,8 +1182,8 @@ __global__ void __launch_bounds__(DESC_THREADS) orient_describe_kernel(
 
 // ---------------------------------------------------------------- host: texture objects over the float copy of the images
 // Pitch-2D float textures (point sampled, clamped, used only through tex2Dgather).  Cached by (ptr, shape, pitch).
-struct TexKey { const void *p; int rows, cols, stride; bool operator<(const TexKey &o) const {
-    return std::tie(p, rows, cols, stride) < std::tie(o.p, o.rows, o.cols, o.stride); } };   // stride: pitch in floats
+struct TexKey { const void *p; int rows, cols, stride, linear; bool operator<(const TexKey &o) const {
+    return std::tie(p, rows, cols, stride, linear) < std::tie(o.p, o.rows, o.cols, o.stride, o.linear); } };   // stride: pitch in floats
 struct TexCache { std::map<TexKey, cudaTextureObject_t> m; int align = 512, pitch_align = 32; bool init = false; };
 
 void surf_tex_destroy(vfsms_ctx *ctx)
@@ -1197,12 +1197,13 @@ void surf_tex_destroy(vfsms_ctx *ctx)
 
 // One texture over `n_img` consecutive images of the float copy, starting at image `b0` (image b at texture rows
 // [(b - b0) * rows, ...)).  Cached by (pointer, shape).
-static bool surf_stack_texture(vfsms_ctx *ctx, int b0, int n_img, int rows, int cols, int pitch_f, cudaStream_t st, cudaTextureObject_t *out)
+static bool surf_stack_texture(vfsms_ctx *ctx, int b0, int n_img, int rows, int cols, int pitch_f, cudaStream_t st, cudaTextureObject_t *out,
+                               bool linear = false)
 {
     if (!ctx->tex_cache) ctx->tex_cache = new TexCache();
     TexCache *tc = (TexCache *)ctx->tex_cache;
     const float *p = ctx->surf.img_f32.as<float>() + (size_t)b0 * rows * pitch_f;
-    TexKey key{p, n_img * rows, cols, pitch_f};
+    TexKey key{p, n_img * rows, cols, pitch_f, linear ? 1 : 0};
     auto it = tc->m.find(key);
     if (it == tc->m.end()) {
         if (tc->m.size() > 8192) {
@@ -1217,7 +1218,7 @@ static bool surf_stack_texture(vfsms_ctx *ctx, int b0, int n_img, int rows, int 
         rd.res.pitch2D.width = cols; rd.res.pitch2D.height = (size_t)n_img * rows; rd.res.pitch2D.pitchInBytes = (size_t)pitch_f * 4;
         cudaTextureDesc td; memset(&td, 0, sizeof(td));
         td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-        td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+        td.filterMode = linear ? cudaFilterModeLinear : cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
         cudaTextureObject_t t = 0;
         if (cudaCreateTextureObject(&t, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); return false; }
         it = tc->m.emplace(key, t).first;
@@ -1450,7 +1451,10 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
     // describe = 1 (default): fixed-point chunked sampler over a float copy of the images scaled by 2^-64, read through one stacked
     // texture per group of images whose rows fit the 2-D linear texture height limit; one launch per group with its own queues.
     // Keypoints it hands over (and everything when describe = 0, upright, or no texture) go through the reference sampler.
+    // describe = 2 / 3: tolerance modes -- same kernel structure, window pixels from fp32 lerps on a gather / from the texture
+    // unit's bilinear filter (NOT bit-exact; surf_describe.cuh).
     bool fixed = false;
+    const int tol = ctx->describe_mode >= 2 ? ctx->describe_mode - 1 : 0;      // 1: fp32 lerps on a gather, 2: texture-unit filter
     if (ctx->describe_mode >= 1 && !p->upright) {
         int max_h = 0;
         if (cudaDeviceGetAttribute(&max_h, cudaDevAttrMaxTexture2DLinearHeight, ctx->device) != cudaSuccess) { cudaGetLastError(); max_h = 0; }
@@ -1460,21 +1464,24 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         if (n_chunks > 0 && n_chunks <= SURF_MAX_DESC_CHUNKS) {
             if ((rc = ws.img_f32.reserve((size_t)batch * rows * ws.pitch_f * 4))) return rc;
             u8_to_f32_kernel<<<dim3(std::min(ceil_div(rows * cols, 256), ctx->num_sms * 4), batch), 256, 0, st>>>(
-                base_a, base_b, split, img_stride, rows, cols, stride, ws.img_f32.as<float>(), ws.pitch_f, 5.421010862427522e-20f /* 2^-64 */, ws.img_off);
+                base_a, base_b, split, img_stride, rows, cols, stride, ws.img_f32.as<float>(), ws.pitch_f,
+                tol ? 1.0f : 5.421010862427522e-20f /* 2^-64 */, ws.img_off);
             LAUNCH_CHECK(ctx);
             std::vector<cudaTextureObject_t> ts((size_t)n_chunks);
             fixed = true;
             for (int c = 0; c < n_chunks && fixed; c++)
-                fixed = surf_stack_texture(ctx, c * per, std::min(per, batch - c * per), rows, cols, ws.pitch_f, st, &ts[c]);
+                fixed = surf_stack_texture(ctx, c * per, std::min(per, batch - c * per), rows, cols, ws.pitch_f, st, &ts[c], tol == 2);
             for (int c = 0; c < n_chunks && fixed; c++) {
-#define LAUNCH_FIXED(MB, UU, NW) describe_fixed_kernel<MB, UU, NW><<<ctx->num_sms * MB, NW * 32, 0, st>>>(                                              \
+#define LAUNCH_FIXED(MB, UU, NW, TT) describe_fixed_kernel<MB, UU, NW, TT><<<ctx->num_sms * MB, NW * 32, 0, st>>>(                                            \
                     base_a, base_b, split, img_stride, rows, cols, stride, ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), \
                     ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, ts[c], c * per, std::min(per, batch - c * per),                   \
                     work_counter + 4 + c, work_counter + 4 + SURF_MAX_DESC_CHUNKS + c, lpt_split, big_flag, fb_list, fb_count, ws.img_off)
                 // (3 CTAs per SM, 4 gathers in flight: measured against 2 / 4 CTAs and 2 / 6 / 8 gathers, profiles/r02)
                 {
                     // (8 warps per CTA, 3 CTAs per SM: 4-warp CTAs at 6 / 7 per SM and 2-warp CTAs at 14 measured no better)
-                    LAUNCH_FIXED(DESC_FIXED_MINB, DESC_FIXED_U, WK_WARPS);
+                    if (tol == 1) LAUNCH_FIXED(DESC_FIXED_MINB, DESC_FIXED_U, WK_WARPS, 1);
+                    else if (tol == 2) LAUNCH_FIXED(DESC_FIXED_MINB, DESC_FIXED_U, WK_WARPS, 2);      // (8 in flight, 4 or 2 CTAs per SM: no faster -- the fp32 filter rate of the texture unit is the limit)
+                    else LAUNCH_FIXED(DESC_FIXED_MINB, DESC_FIXED_U, WK_WARPS, 0);
                 }
 #undef LAUNCH_FIXED
                 LAUNCH_CHECK(ctx);

@@ -490,9 +490,55 @@ __device__ __forceinline__ void sample_chunk(DescScratch &S, const cudaTextureOb
     }
 }
 
+// ---- tolerance modes (option describe = 2 / 3; NOT bit-exact, DESIGN.md "tolerance modes"), both at float positions:
+// TOL = 1 (describe = 2): the 2x2 footprint through a gather, fp32 weights, three fused lerps -- the real bilinear value to a few
+//   1e-6 of a grey level, so a window pixel differs from the CPU's only when its value sits that close to a .5 boundary;
+// TOL = 2 (describe = 3): the texture unit's own bilinear filter (one TEX; the unit interpolates with 8-bit weights).  slot: float2 position of lane 0 of every warp-round, texel-centre convention, image b's rows
+// included; mxf / myf: this lane's offset along the window row.  Everything after the window pixel (rounding to u8, INTER_AREA,
+// gradients, bins, normalisation) is the exact path's code.
+template <bool CHECK, int U, int TOL>
+__device__ __forceinline__ void sample_rounds_tol(const float2 *__restrict__ slot, float *__restrict__ out, const cudaTextureObject_t tex,
+                                                  float mxf, float myf, const uint8_t *__restrict__ img, int stride, int ncols1, int nrows1,
+                                                  int row_off)
+{
+    float t[U], xs[U], ys[U];
+    float4 g[U]; float fa[U], fb[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const float2 e = slot[u];
+        xs[u] = e.x + mxf; ys[u] = e.y + myf;
+        if (TOL == 2) t[u] = tex2D<float>(tex, xs[u], ys[u]);          // the texture unit's filter: 8-bit weights
+        else {
+            // fp32 weights, fused lerps: the footprint through a gather, no emulation of the CPU's operation order
+            const float fx = floorf(xs[u] - 0.5f), fy = floorf(ys[u] - 0.5f);
+            fa[u] = (xs[u] - 0.5f) - fx; fb[u] = (ys[u] - 0.5f) - fy;
+            g[u] = tex2Dgather<float4>(tex, fx + 1.0f, fy + 1.0f, 0);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (TOL != 2) {
+            const float p00 = g[u].w, p01 = g[u].z, p10 = g[u].x, p11 = g[u].y;
+            const float top = __fmaf_rn(fa[u], p01 - p00, p00), bot = __fmaf_rn(fa[u], p11 - p10, p10);
+            t[u] = __fmaf_rn(fb[u], bot - top, top);
+        }
+        float v = (t[u] + 12582912.0f) - 12582912.0f;          // cvRound, ties to even
+        if (CHECK) {
+            const float px = xs[u] - 0.5f, py = ys[u] - 0.5f - (float)row_off;
+            const int ix = (int)floorf(px), iy = (int)floorf(py);
+            if (!((unsigned)ix < (unsigned)ncols1 && (unsigned)iy < (unsigned)nrows1)) {
+                // outside the image: the CPU takes the clamped nearest pixel
+                const int x = min(max(__float2int_rn(px), 0), ncols1), y = min(max(__float2int_rn(py), 0), nrows1);
+                v = (float)img[(size_t)y * stride + x];
+            }
+        }
+        out[u * 32] = v;
+    }
+}
+
 // The window of one keypoint -> S.patch.  false: a row start is not a multiple of one fixed-point unit (FINE = false: the caller
 // retries in 16.48; FINE = true: the reference kernel's).  cU / sU: |cos_dir|, |sin_dir| in fixed-point units.
-template <bool FINE, int U>
+template <bool FINE, int U, int TOL = 0>
 __device__ bool window_to_patch(DescScratch &S, const cudaTextureObject_t tex, int lane, int win, float cx, float cy,
                                                 float sin_dir, float cos_dir, unsigned long long cU, unsigned long long sU, bool interior,
                                                 const uint8_t *__restrict__ img, int stride, int ncols1, int nrows1, int row_off)
@@ -523,6 +569,20 @@ __device__ bool window_to_patch(DescScratch &S, const cudaTextureObject_t tex, i
                 if (i == myrow) { cap_x = chain_x; cap_y = chain_y; }
                 chain_x += sin_dir; chain_y += cos_dir;
             }
+            if constexpr (TOL) {
+                const float c0 = (float)(32 * myk);
+                float2 e;
+                e.x = cap_x + c0 * cos_dir + 0.5f;
+                e.y = cap_y - c0 * sin_dir + 0.5f + (float)row_off;
+                ((float2 *)S.slot)[lane] = e;
+                if (!interior) {
+                    const int xa = (int)floorf(e.x - 0.5f), xb = (int)floorf(e.x - 0.5f + 31.f * cos_dir);
+                    const int ya = (int)floorf(e.y - 0.5f) - row_off, yb = (int)floorf(e.y - 0.5f - 31.f * sin_dir) - row_off;
+                    const bool in = (unsigned)xa < (unsigned)ncols1 && (unsigned)xb < (unsigned)ncols1 &&
+                                    (unsigned)ya < (unsigned)nrows1 && (unsigned)yb < (unsigned)nrows1;
+                    need = __ballot_sync(0xffffffffu, !in);
+                }
+            } else {
             const bool ok = (cap_x == 0.f || fabsf(cap_x) >= tiny) && (cap_y == 0.f || fabsf(cap_y) >= tiny);
             if (!__all_sync(0xffffffffu, ok)) return false;
             long long X0, Y0;                    // exact: the row start is a multiple of one unit
@@ -554,9 +614,20 @@ __device__ bool window_to_patch(DescScratch &S, const cudaTextureObject_t tex, i
                                 (unsigned)ya < (unsigned)nrows1 && (unsigned)yb < (unsigned)nrows1;
                 need = __ballot_sync(0xffffffffu, !in);
             }
+            }
         }
         __syncwarp();
         const int Q4 = (Q + U - 1) / U * U;
+        if constexpr (TOL) {
+            const float mxf = (float)lane * cos_dir, myf = -(float)lane * sin_dir;
+            const float2 *slot = (const float2 *)S.slot;
+            float *out = S.buf + lane;
+#pragma unroll 1
+            for (int q0 = 0; q0 < Q4; q0 += U, slot += U, out += 32 * U, need >>= U) {
+                if (need & ((1u << U) - 1)) sample_rounds_tol<true, U, TOL>(slot, out, tex, mxf, myf, img, stride, ncols1, nrows1, row_off);
+                else sample_rounds_tol<false, U, TOL>(slot, out, tex, mxf, myf, img, stride, ncols1, nrows1, row_off);
+            }
+        } else
         sample_chunk<FINE, U>(S, tex, Q4, need, mxc, myc, lane, img, stride, ncols1, nrows1, row_off);
         __syncwarp();
         // ---- fold the chunk's rows into the patch
@@ -566,7 +637,7 @@ __device__ bool window_to_patch(DescScratch &S, const cudaTextureObject_t tex, i
     return F.done();
 }
 
-template <int MINB, int U, int NW>
+template <int MINB, int U, int NW, int TOL = 0>
 __global__ void __launch_bounds__(NW * 32, MINB) describe_fixed_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
     const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
@@ -622,7 +693,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) describe_fixed_kernel(
         const bool interior = cx - Rw >= 1.f && cx + Rw <= (float)(ncols1 - 1) && cy - Rw >= 1.f && cy + Rw <= (float)(nrows1 - 1);
 
         bool described = false;
-        if (ok32)
+        if constexpr (TOL)
+            described = window_to_patch<false, U, TOL>(S, tex, lane, win, cx, cy, sin_dir, cos_dir, 0ULL, 0ULL, interior, img, stride, ncols1, nrows1, row_off);
+        else if (ok32)
             described = window_to_patch<false, U>(S, tex, lane, win, cx, cy, sin_dir, cos_dir, (unsigned long long)(unsigned)(ac * 4294967296.0f),
                                                (unsigned long long)(unsigned)(as * 4294967296.0f), interior, img, stride, ncols1, nrows1, row_off);
         if (!described && ok48)      // the direction needs the finer unit, or a row of the first attempt started within 2^-9 of an axis

@@ -378,8 +378,9 @@ OPTIONS = {"describe": 0, "sort": 1, "lpt": 2, "entropy": 3}      # include/vfsm
 
 
 def set_option(name, value, device=0):
-    """Kernel-variant switch (include/vfsms.h VFSMS_OPT_*): every value of an option gives identical results; non-default
-    values are alternative schedules kept for A/B measurement.  Also settable through VFSMS_OPTS="describe=0,lpt=1"."""
+    """Kernel-variant switch (include/vfsms.h VFSMS_OPT_*): every value of an option gives identical results (except the two
+    tolerance modes describe=2 / 3, whose stated tolerances include/vfsms.h lists); non-default values are alternative
+    schedules kept for A/B measurement.  Also settable through VFSMS_OPTS="describe=0,lpt=1"."""
     check(_lib.load().vfsms_set_option(_lib.context(device), OPTIONS[name], int(value)), "vfsms_set_option")
 
 

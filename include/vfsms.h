@@ -94,7 +94,12 @@ enum {
                                    * 1 (default) = 32.32 fixed-point positions, window rows sampled in chunks through one stacked float
                                    * texture with four gathers in flight per lane; keypoints whose direction or row starts are not
                                    * multiples of 2^-32 are handed to sampler 0.  0 = reference sampler for every keypoint: one row at
-                                   * a time, double precision, straight from the u8 image */
+                                   * a time, double precision, straight from the u8 image.  Values 0 and 1 give bit-identical results.
+                                   * 2 and 3 are TOLERANCE modes (keypoints identical, descriptors not): 2 = float positions, fp32
+                                   * lerps on the gathered footprint (95 % of the descriptors identical, max |diff| 0.06, mean 1e-6;
+                                   * -5 % describe time); 3 = the texture unit's own bilinear filter with its 8-bit weights (max |diff|
+                                   * 0.15, mean 2e-4, >= 97 % of the matches identical, offsets identical on every fixture; -12 %).
+                                   * tests/test_gpu_variants.py asserts these tolerances; DESIGN.md 12 */
     VFSMS_OPT_SORT_MODE = 1,      /* "sort": KeypointGreater ordering.  1 (default) = 13-bit response histogram, then rank counting
                                    * inside each candidate's own bin; 0 = rank by counting over all staged candidates */
     VFSMS_OPT_DESCRIBE_LPT = 2,   /* "lpt": describe the large windows first (two passes over the work list), so that no giant window

@@ -316,7 +316,7 @@ cudaError_t cudaFuncSetAttribute(const void *, enum cudaFuncAttribute, int) { re
 cudaError_t cudaCreateTextureObject(cudaTextureObject_t *obj, const struct cudaResourceDesc *res, const struct cudaTextureDesc *td,
                                     const struct cudaResourceViewDesc *)
 {
-    if (res->resType != cudaResourceTypePitch2D || td->filterMode != cudaFilterModePoint || td->normalizedCoords ||
+    if (res->resType != cudaResourceTypePitch2D || td->normalizedCoords ||
         td->addressMode[0] != cudaAddressModeClamp || td->addressMode[1] != cudaAddressModeClamp || td->readMode != cudaReadModeElementType)
         return cudaErrorNotSupported;
     emu::Tex *t = new emu::Tex;

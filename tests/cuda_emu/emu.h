@@ -102,6 +102,7 @@ template <class T> static inline unsigned atomicInc(T *p, unsigned lim) { unsign
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline int __float2int_rn(float v) { return (int)lrintf(v); }
 static inline float __int2float_rn(int v) { return (float)v; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __ull2float_rn(unsigned long long v) { return (float)v; }
 static inline float __uint2float_rn(unsigned v) { return (float)v; }      // round to nearest even (the default FP environment)
 static inline int __float2int_rd(float v) { return (int)floorf(v); }
@@ -175,6 +176,17 @@ template <> inline float4 tex2Dgather<float4>(cudaTextureObject_t obj, float x, 
     const emu::Tex *t = (const emu::Tex *)(uintptr_t)obj;
     const int i0 = (int)floorf(x - 0.5f), j0 = (int)floorf(y - 0.5f);
     return make_float4(emu_texel_any(t, i0, j0 + 1), emu_texel_any(t, i0 + 1, j0 + 1), emu_texel_any(t, i0 + 1, j0), emu_texel_any(t, i0, j0));
+}
+// bilinear filtering as the texture unit does it: 8 fractional bits for the weights (CUDA programming guide, "linear filtering")
+template <class T> static inline T tex2D(cudaTextureObject_t obj, float x, float y);
+template <> inline float tex2D<float>(cudaTextureObject_t obj, float x, float y)
+{
+    const emu::Tex *t = (const emu::Tex *)(uintptr_t)obj;
+    const float xb = x - 0.5f, yb = y - 0.5f;
+    const int i0 = (int)floorf(xb), j0 = (int)floorf(yb);
+    const float a = floorf((xb - (float)i0) * 256.0f + 0.5f) / 256.0f, b = floorf((yb - (float)j0) * 256.0f + 0.5f) / 256.0f;
+    return (1 - a) * (1 - b) * emu_texel_any(t, i0, j0) + a * (1 - b) * emu_texel_any(t, i0 + 1, j0) +
+           (1 - a) * b * emu_texel_any(t, i0, j0 + 1) + a * b * emu_texel_any(t, i0 + 1, j0 + 1);
 }
 template <> inline uchar4 tex2Dgather<uchar4>(cudaTextureObject_t obj, float x, float y, int)
 {

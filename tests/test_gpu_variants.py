@@ -99,3 +99,45 @@ def test_describe_large_windows_first_identical(gpu, synth_pair_rois):
             assert np.array_equal(k0, k2) and np.array_equal(d0, d2)
         assert len(k0) > 1000 and (np.floor(21 * k0[:, 2] * np.float32(1.2) / 9) >= 128).sum() > 5
         assert np.array_equal(k0, k1) and np.array_equal(d0, d1)
+
+
+# ---- tolerance modes (describe = 2, 3): NOT bit-exact; the stated tolerances of DESIGN.md "tolerance modes" are asserted here.
+# mode -> (largest |component difference| of any unit-norm descriptor, mean |component difference|, share of the exact path's
+#          matches (same query, same train) the mode reproduces)
+TOLERANCES = {2: (0.06, 5e-5, 0.995), 3: (0.15, 2e-3, 0.97)}
+
+
+def _match_set(m):
+    return set(map(tuple, np.asarray(m).reshape(-1, 2).tolist()))
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("extended", [True, False])
+def test_describe_tolerance_modes_within_stated_tolerance(gpu, synth_pair_rois, extended, mode):
+    """describe = 2 blends the gathered 2x2 footprint with fp32 lerps at float positions, describe = 3 takes the window pixels
+    from the texture unit's bilinear filter.  Keypoints (position, size, response, orientation) stay identical -- detection
+    and orientation do not use the sampler; descriptors, match lists and offsets stay within the stated tolerances."""
+    roiA, roiB, true_off = synth_pair_rois
+    tol_max, tol_mean, tol_share = TOLERANCES[mode]
+    outs = {}
+    for md in (1, mode):
+        gpu.set_option("describe", md)
+        kA, dA = gpu.surf_detect_and_describe(roiA, extended=extended, keypoints_ratio=0.01)
+        kB, dB = gpu.surf_detect_and_describe(roiB, extended=extended, keypoints_ratio=0.01)
+        m = gpu.match_descriptors(dA, dB, 2, 0.75)
+        st, off, votes = gpu.offset_by_mode(kA, kB, m, 3)
+        outs[md] = (kA, dA, kB, dB, m, st, off, votes)
+    e, t = outs[1], outs[mode]
+    assert np.array_equal(e[0], t[0]) and np.array_equal(e[2], t[2])                 # keypoints identical
+    for de, dt in ((e[1], t[1]), (e[3], t[3])):
+        diff = np.abs(de - dt)
+        assert diff.max() <= tol_max, diff.max()
+        assert diff.mean() <= tol_mean, diff.mean()
+        assert np.allclose(np.linalg.norm(dt, axis=1), 1.0, atol=1e-5)
+    me, mt = _match_set(e[4]), _match_set(t[4])
+    assert len(me & mt) >= tol_share * len(me), (len(me), len(mt), len(me & mt))
+    assert e[5] and t[5] and e[6] == t[6]                                            # same status, identical offset
+    assert abs(t[6][0] - true_off[0]) <= 1 and abs(t[6][1] - true_off[1]) <= 1
+    print("describe=%d: max |d desc| %.2e mean %.2e identical descriptors %.1f %%, matches %d / %d common %d, votes %d / %d" % (
+        mode, max(np.abs(e[1] - t[1]).max(), np.abs(e[3] - t[3]).max()), np.abs(e[1] - t[1]).mean(),
+        100.0 * (np.abs(e[1] - t[1]).max(axis=1) == 0).mean(), len(me), len(mt), len(me & mt), e[7], t[7]))

@@ -40,7 +40,7 @@ def main():
     roiA, roiB = np.ascontiguousarray(A[384 - 76:, :]), np.ascontiguousarray(B[:76, :])
 
     def surf():
-        for mode in (1, 2, 0, 7):
+        for mode in (1, 2, 3, 0):
             gpu.set_option("describe", mode)
             gpu.surf_detect_and_describe(roiA, hessian_threshold=100.0, extended=True, keypoints_ratio=0.01)
         gpu.set_option("describe", 1)

@@ -1259,13 +1259,13 @@ int surf_reserve(vfsms_ctx *ctx, int batch, int rows, int cols, const vfsms_surf
     if ((rc = ws.sorted.reserve((size_t)batch * cand_cap * KP_STRIDE * 4))) return rc;
     if ((rc = ws.kp.reserve((size_t)batch * kp_cap * KP_STRIDE * 4))) return rc;
     if ((rc = ws.desc.reserve((size_t)batch * kp_cap * dim * 4))) return rc;
-    if ((rc = ws.counters.reserve((size_t)batch * 16 + 16 + 8 * SURF_MAX_DESC_CHUNKS))) return rc;   // + work counters (two per launch group)
+    if ((rc = ws.counters.reserve((size_t)batch * 16 + 32 + 8 * SURF_MAX_DESC_CHUNKS))) return rc;   // + work counters (two per launch group, cooperative pass)
     if ((rc = ws.prefix.reserve((size_t)(batch + 1) * 4))) return rc;
     if ((rc = ws.descT.reserve((size_t)batch * kp_cap * dim * 4))) return rc;
     if ((rc = ws.hist.reserve((size_t)batch * (3 * RB_BINS + 1) * 4))) return rc;     // sort mode 0 uses [RH_BINS + 1] per image
     ws.pitch_f = (cols + 31) & ~31;
     if (!p->upright && (rc = ws.img_f32.reserve((size_t)batch * rows * ws.pitch_f * 4))) return rc;
-    if ((rc = ws.fb_list.reserve((size_t)batch * kp_cap * 4))) return rc;      // keypoints handed from the fixed-point sampler to the reference one
+    if ((rc = ws.fb_list.reserve((size_t)batch * kp_cap * 8))) return rc;      // keypoints handed from the fixed-point sampler to the reference one | giant windows of the cooperative pass
     ws.max_features = max_features;
     ws.batch = batch; ws.rows = rows; ws.cols = cols; ws.cand_cap = cand_cap; ws.kp_cap = kp_cap; ws.dim = dim;
     return 0;
@@ -1282,7 +1282,7 @@ int surf_grow(vfsms_ctx *ctx, int grow_cand, int grow_kp)
         if ((rc = ws.kp.reserve((size_t)ws.batch * ws.kp_cap * KP_STRIDE * 4))) return rc;
         if ((rc = ws.desc.reserve((size_t)ws.batch * ws.kp_cap * ws.dim * 4))) return rc;
         if ((rc = ws.descT.reserve((size_t)ws.batch * ws.kp_cap * ws.dim * 4))) return rc;
-        if ((rc = ws.fb_list.reserve((size_t)ws.batch * ws.kp_cap * 4))) return rc;
+        if ((rc = ws.fb_list.reserve((size_t)ws.batch * ws.kp_cap * 8))) return rc;
     }
     if ((rc = ws.cand.reserve((size_t)ws.batch * ws.cand_cap * KP_STRIDE * 4))) return rc;
     if ((rc = ws.sorted.reserve((size_t)ws.batch * ws.cand_cap * KP_STRIDE * 4))) return rc;
@@ -1309,7 +1309,7 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
         CUDA_TRY(cudaFuncSetAttribute(integral_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_done = true;
     }
-    CUDA_TRY(cudaMemsetAsync(ws.counters.p, 0, (size_t)batch * 16 + 16 + 8 * SURF_MAX_DESC_CHUNKS, st));
+    CUDA_TRY(cudaMemsetAsync(ws.counters.p, 0, (size_t)batch * 16 + 32 + 8 * SURF_MAX_DESC_CHUNKS, st));
     ws.last_batch = batch;
     {
     StageTimer t_int(ctx, st, VFSMS_STAGE_INTEGRAL);
@@ -1472,6 +1472,23 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
             for (int c = 0; c < n_chunks && fixed; c++)
                 fixed = surf_stack_texture(ctx, c * per, std::min(per, batch - c * per), rows, cols, ws.pitch_f, st, &ts[c], tol == 2);
             for (int c = 0; c < n_chunks && fixed; c++) {
+                // Small batches: one giant window (up to 768 px, 6 * 10^5 samples) on one warp is the whole tail of the launch
+                // (3 ms of a 3.5 ms single-pair call); the CTA's eight warps share such windows (surf_describe.cuh).
+                static const int coop_split_v = getenv("VFSMS_COOP_SPLIT") ? atoi(getenv("VFSMS_COOP_SPLIT")) : DESC_COOP_SPLIT;       // tuning aids
+                static const int coop_batch_v = getenv("VFSMS_COOP_BATCH") ? atoi(getenv("VFSMS_COOP_BATCH")) : DESC_COOP_MAX_BATCH;
+                const bool coop = n_chunks == 1 && batch <= coop_batch_v;
+                int *coop_list = fb_list + (size_t)batch * ws.kp_cap, *coop_count = work_counter + 3,
+                    *coop_counter = work_counter + 4 + 2 * SURF_MAX_DESC_CHUNKS;
+                if (coop) {
+                    describe_giants_kernel<<<std::min(ceil_div(batch * ws.kp_cap, 256), ctx->num_sms * 2), 256, 0, st>>>(
+                        ws.kp.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap, coop_split_v, coop_list, coop_count);
+                    LAUNCH_CHECK(ctx);
+                }
+#define LAUNCH_COOP(MB, UU, NW, TT) describe_fixed_kernel<MB, UU, NW, TT, true><<<ctx->num_sms * MB, NW * 32, 0, st>>>(                                  \
+                    base_a, base_b, split, img_stride, rows, cols, stride, ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), \
+                    ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, ts[c], c * per, std::min(per, batch - c * per),                   \
+                    work_counter + 4 + c, work_counter + 4 + SURF_MAX_DESC_CHUNKS + c, lpt_split, big_flag, fb_list, fb_count, ws.img_off,   \
+                    coop_split_v, coop_list, coop_count, coop_counter)
 #define LAUNCH_FIXED(MB, UU, NW, TT) describe_fixed_kernel<MB, UU, NW, TT><<<ctx->num_sms * MB, NW * 32, 0, st>>>(                                            \
                     base_a, base_b, split, img_stride, rows, cols, stride, ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), \
                     ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, ts[c], c * per, std::min(per, batch - c * per),                   \
@@ -1479,11 +1496,13 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
                 // (3 CTAs per SM, 4 gathers in flight: measured against 2 / 4 CTAs and 2 / 6 / 8 gathers, profiles/r02)
                 {
                     // (8 warps per CTA, 3 CTAs per SM: 4-warp CTAs at 6 / 7 per SM and 2-warp CTAs at 14 measured no better)
-                    if (tol == 1) LAUNCH_FIXED(DESC_FIXED_MINB, DESC_FIXED_U, WK_WARPS, 1);
+                    if (coop && tol == 0) LAUNCH_COOP(DESC_FIXED_MINB, DESC_FIXED_U, WK_WARPS, 0);
+                    else if (tol == 1) LAUNCH_FIXED(DESC_FIXED_MINB, DESC_FIXED_U, WK_WARPS, 1);
                     else if (tol == 2) LAUNCH_FIXED(DESC_FIXED_MINB, DESC_FIXED_U, WK_WARPS, 2);      // (8 in flight, 4 or 2 CTAs per SM: no faster -- the fp32 filter rate of the texture unit is the limit)
                     else LAUNCH_FIXED(DESC_FIXED_MINB, DESC_FIXED_U, WK_WARPS, 0);
                 }
 #undef LAUNCH_FIXED
+#undef LAUNCH_COOP
                 LAUNCH_CHECK(ctx);
             }
         }

@@ -33,6 +33,8 @@
 #define DESC_SLOTS 32             // warp-rounds per chunk
 #define DESC_FIXED_MINB 3          // CTAs per SM the fixed kernel's register budget is cut for
 #define DESC_FIXED_U 4             // gathers in flight per lane
+#define DESC_COOP_SPLIT 320        // windows at least this wide are shared by the warps of a CTA ...
+#define DESC_COOP_MAX_BATCH 24     // ... in batches of at most this many images (larger batches fill the GPU without it)
 
 // bilinear / clamped sample of the rotated window, rounded to u8 exactly like the CPU loop (reference sampler)
 __device__ __forceinline__ int window_pixel(const uint8_t *__restrict__ img, int stride, int ncols1, int nrows1,
@@ -242,6 +244,19 @@ struct __align__(16) AreaCol {                  // nf = n | flags << 16; flags: 
 struct AreaFold {
     int iscale, mode;            // mode 0: general decimation tables, 1: integer scale (box sums), 2: win == 21 (copy)
     int nmax, dy; float sum;
+    int dy_end; uint8_t *patch;  // output rows [dy at init, dy_end) go to patch[row * 21 + col] (default: all 21 rows into S.patch)
+
+    // The output rows [dy_begin, dy_end) only: their source rows start at first_row() (call after init), every output row is
+    // still summed over its own source rows in order, so several warps can fold disjoint row ranges of one window exactly.
+    __device__ __forceinline__ void restrict_rows(const DescScratch &S, int dy_begin, int dy_stop, uint8_t *out)
+    {
+        dy = dy_begin; dy_end = dy_stop; patch = out;
+    }
+    __device__ __forceinline__ int first_row(const DescScratch &S) const
+    {
+        const AreaCol c = ((const AreaCol *)S.vec)[dy];
+        return c.sx1 - ((c.nf >> 16) & 1);
+    }
 
     __device__ __forceinline__ void init(DescScratch &S, int win, int lane)
     {
@@ -250,7 +265,7 @@ struct AreaFold {
         const double scale = 1. / inv_scale;
         iscale = __double2int_rn(scale);
         mode = win == PD ? 2 : (fabs(scale - iscale) < DBL_EPSILON ? 1 : 0);
-        dy = 0; sum = 0;
+        dy = 0; sum = 0; dy_end = PD; patch = S.patch;
         const int dxc = lane < PD ? lane : PD - 1;
         AreaCol c;
         c.sx1 = dxc * iscale; c.nf = iscale; c.axl = c.axr = c.pad = 0; c.axm = 1.f; c.ya = c.yb = 0;
@@ -272,13 +287,13 @@ struct AreaFold {
         __syncwarp();
     }
 
-    __device__ __forceinline__ bool done() const { return dy >= PATCH_SZ + 1; }
+    __device__ __forceinline__ bool done() const { return dy >= dy_end; }
 
     // rows r0 .. r0 + nrows - 1 of the window (exact floats 0..255 in S.buf, `pitch` floats apart, overwritten); chunks arrive in order
     __device__ __forceinline__ void rows(DescScratch &S, int pitch, int r0, int nrows, int lane)
     {
         constexpr int PD = PATCH_SZ + 1;
-        if (dy >= PD) return;
+        if (dy >= dy_end) return;
         const AreaCol *tab = (const AreaCol *)S.vec;
         float *buf = S.buf;
         // ---- horizontal pass
@@ -321,9 +336,9 @@ struct AreaFold {
             else if (mode == 2) out = (int)sum;
             else if (iscale == 2) out = (int)((sum + 2.f) * 0.25f);          // (sum + 2) >> 2
             else out = min(max(__float2int_rn(sum * (1.f / (float)(iscale * iscale))), 0), 255);
-            if (lane < PD) S.patch[dy * PD + lane] = (uint8_t)out;
+            if (lane < PD) patch[dy * PD + lane] = (uint8_t)out;
             dy++; sum = 0;
-            if (dy >= PD) return;
+            if (dy >= dy_end) return;
             // (written with the whole entry loaded: `dy >= PD || tab[dy].ya >= rend` gave wrong results on the B200 with nvcc 12.9)
             { const AreaCol cn = tab[dy]; if ((cn.sx1 - ((cn.nf >> 16) & 1)) >= rend) return; }     // the next output row starts in a later chunk
         }
@@ -541,7 +556,8 @@ __device__ __forceinline__ void sample_rounds_tol(const float2 *__restrict__ slo
 template <bool FINE, int U, int TOL = 0>
 __device__ bool window_to_patch(DescScratch &S, const cudaTextureObject_t tex, int lane, int win, float cx, float cy,
                                                 float sin_dir, float cos_dir, unsigned long long cU, unsigned long long sU, bool interior,
-                                                const uint8_t *__restrict__ img, int stride, int ncols1, int nrows1, int row_off)
+                                                const uint8_t *__restrict__ img, int stride, int ncols1, int nrows1, int row_off,
+                                                int dy_begin = 0, int dy_stop = PATCH_SZ + 1, uint8_t *patch_out = nullptr)
 {
     constexpr int FB = FINE ? 48 : 32;
     const float tiny = FINE ? 2.98023223876953125e-08f : 0.001953125f;        // row starts must be 0 or at least this (ulp >= one unit)
@@ -557,7 +573,13 @@ __device__ bool window_to_patch(DescScratch &S, const cudaTextureObject_t tex, i
     const int kinv = (65536 + kpr - 1) / kpr;   // (q * kinv) >> 16 == q / kpr for q < 32, kpr <= 24
     AreaFold F;
     F.init(S, win, lane);
-    for (int r0 = 0; r0 < win && !F.done(); r0 += R) {
+    int r_first = 0;
+    if (patch_out) {                             // a share of the output rows (cooperative pass): skip to their first source row
+        F.restrict_rows(S, dy_begin, dy_stop, patch_out);
+        r_first = F.first_row(S);
+        for (int i = 0; i < r_first; i++) { chain_x += sin_dir; chain_y += cos_dir; }      // the CPU's float chain up to that row
+    }
+    for (int r0 = r_first; r0 < win && !F.done(); r0 += R) {
         const int Rc = min(R, win - r0), Q = Rc * kpr;
         // ---- slot table: lane q owns warp-round q = (row r0 + q / kpr, columns 32 * (q % kpr) ...); lanes >= Q repeat round Q - 1
         unsigned need = 0;
@@ -637,13 +659,32 @@ __device__ bool window_to_patch(DescScratch &S, const cudaTextureObject_t tex, i
     return F.done();
 }
 
-template <int MINB, int U, int NW, int TOL = 0>
+// Work list of the cooperative pass: the keypoints whose window is at least coop_split pixels wide (and that the warp kernel can
+// hold at all).  Small batches only: there a single giant window on a single warp is the whole tail of the launch.
+__global__ void __launch_bounds__(256) describe_giants_kernel(const float *__restrict__ kp_all, const int32_t *__restrict__ prefix, int batch,
+                                                              int kp_cap, int coop_split, int *coop_list, int *coop_count)
+{
+    const int total = prefix[batch];
+    for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < total; item += gridDim.x * blockDim.x) {
+        int lo = 0, hi = batch;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(prefix + mid) <= item) lo = mid; else hi = mid; }
+        const float size = kp_all[((size_t)lo * kp_cap + (item - __ldg(prefix + lo))) * KP_STRIDE + KP_SIZE];
+        const int win = (int)((PATCH_SZ + 1) * (size * 1.2f / 9.0f));
+        if (win >= coop_split && win <= WK_MAX_WIN) coop_list[atomicAdd(coop_count, 1)] = item;
+    }
+}
+
+// coop_split > 0 (COOP instances, single launch group): before the per-warp passes the CTA's warps share every window of at least
+// coop_split pixels -- each warp samples and folds its share of the 21 output rows (AreaFold::restrict_rows), warp 0 turns the
+// assembled patch into the descriptor.  Same arithmetic per output row, so the descriptor is the per-warp path's.
+template <int MINB, int U, int NW, int TOL = 0, bool COOP = false>
 __global__ void __launch_bounds__(NW * 32, MINB) describe_fixed_kernel(
     const uint8_t *base_a, const uint8_t *base_b, int split, int64_t img_stride, int rows, int cols, int stride,
     const int32_t *__restrict__ integral, float *kp_all, float *desc_all, const int32_t *__restrict__ prefix,
     int batch, int kp_cap, int extended, const cudaTextureObject_t tex, int b_first, int b_count,
     int *work_counter, int *work_counter_large, int lpt_split, int *big_flag, int *fb_list, int *fb_count,
-    const int64_t *__restrict__ img_off)
+    const int64_t *__restrict__ img_off, int coop_split = 0, const int *coop_list = nullptr, const int *coop_count = nullptr,
+    int *coop_counter = nullptr)
 {
     __shared__ DescScratch s_ws[NW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -653,6 +694,69 @@ __global__ void __launch_bounds__(NW * 32, MINB) describe_fixed_kernel(
     const int W = cols + 1, srows = rows + 1, scols = cols + 1;
     const int dsize = extended ? 128 : 64;
     const int ncols1 = cols - 1, nrows1 = rows - 1;
+
+    if constexpr (COOP) {
+        constexpr int PD = PATCH_SZ + 1;
+        __shared__ int s_item, s_fail, s_fail_fine;
+        __shared__ uint8_t s_patch[PD * PD + 7];
+        const int n_coop = *coop_count;
+        while (true) {
+            if (threadIdx.x == 0) { s_item = atomicAdd(coop_counter, 1); s_fail = 0; s_fail_fine = 0; }
+            __syncthreads();
+            const int ci = s_item;
+            if (ci >= n_coop) break;                           // CTA-uniform
+            const int item = coop_list[ci];
+            int lo = b_first, hi = b_first + b_count;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(prefix + mid) <= item) lo = mid; else hi = mid; }
+            const int b = lo, k = item - __ldg(prefix + lo);
+            float *kp = kp_all + ((size_t)b * kp_cap + k) * KP_STRIDE;
+            const float size = kp[KP_SIZE], cx = kp[KP_X], cy = kp[KP_Y];
+            const float s = size * 1.2f / 9.0f;
+            const int win = (int)((PATCH_SZ + 1) * s);
+            const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride, img_off);
+            const int32_t *I = integral + (size_t)b * srows * W;
+            const int gws = 2 * __float2int_rn(2 * s);
+            // every warp repeats the orientation (a few thousand instructions against the > 10^5 of its share of the window)
+            const float descriptor_dir = orient_keypoint(S, lane, I, W, srows, scols, cx, cy, s, gws);
+            const float dir_rad = descriptor_dir * (float)(M_PI / 180);
+            double sd, cd;
+            sincos((double)dir_rad, &sd, &cd);
+            const float sin_dir = -(float)sd, cos_dir = (float)cd;
+            const float ac = fabsf(cos_dir), as = fabsf(sin_dir);
+            const bool ok32 = (ac == 0.f || ac >= 0.001953125f) && ac < 1.f && (as == 0.f || as >= 0.001953125f) && as < 1.f;
+            const int row_off = (b - b_first) * rows;
+            const float Rw = (float)(win - 1) * 0.7072f + 2.0f;
+            const bool interior = cx - Rw >= 1.f && cx + Rw <= (float)(ncols1 - 1) && cy - Rw >= 1.f && cy + Rw <= (float)(nrows1 - 1);
+            const int dy0 = warp * PD / NW, dy1 = (warp + 1) * PD / NW;
+            bool mine = TOL != 0 || ok32;
+            if (mine)
+                mine = window_to_patch<false, U, TOL>(S, tex, lane, win, cx, cy, sin_dir, cos_dir, (unsigned long long)(unsigned)(ac * 4294967296.0f),
+                                                      (unsigned long long)(unsigned)(as * 4294967296.0f), interior, img, stride, ncols1, nrows1, row_off,
+                                                      dy0, dy1, s_patch);
+            if (!mine && lane == 0) s_fail = 1;
+            __syncthreads();
+            if (TOL == 0 && s_fail) {                          // CTA-uniform: some share needs the finer unit -> all shares again in 16.48
+                const bool ok48 = (ac == 0.f || ac >= 2.98023223876953125e-08f) && (as == 0.f || as >= 2.98023223876953125e-08f) &&
+                                  rows < 16384 && cols < 16384;
+                mine = ok48 && window_to_patch<true, 2>(S, tex, lane, win, cx, cy, sin_dir, cos_dir, (unsigned long long)((double)ac * 281474976710656.0),
+                                                        (unsigned long long)((double)as * 281474976710656.0), interior, img, stride, ncols1, nrows1,
+                                                        row_off, dy0, dy1, s_patch);
+                if (!mine && lane == 0) s_fail_fine = 1;
+                __syncthreads();
+            }
+            if (warp == 0) {
+                if (s_fail && (TOL != 0 || s_fail_fine)) {     // neither unit fits: the reference kernel takes the keypoint
+                    if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = item;
+                } else {
+                    if (lane == 0) kp[KP_ANGLE] = descriptor_dir;
+                    for (int i = lane; i < PD * PD; i += 32) S.patch[i] = s_patch[i];
+                    __syncwarp();
+                    patch_to_descriptor(S, lane, extended, desc_all + ((size_t)b * kp_cap + k) * dsize);
+                }
+            }
+            __syncthreads();                                   // s_patch / s_item are reused by the next window
+        }
+    }
 
     // lpt_split > 0: longest-processing-time-first in two passes over the same work list -- pass 0 describes only the windows
     // >= lpt_split (a 600-pixel window keeps one warp busy for a long time; met late in the queue it becomes the tail of the
@@ -672,6 +776,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) describe_fixed_kernel(
         const int win = (int)((PATCH_SZ + 1) * s);
         if (lpt_split > 0 && ((win >= lpt_split) != (pass == 0))) continue;   // warp-uniform: the other pass owns this keypoint
         if (win > WK_MAX_WIN) { if (lane == 0) *big_flag = 1; continue; }     // warp-uniform: flag work for the CTA kernel
+        if (COOP && win >= coop_split) continue;                              // described by the cooperative pass above
         const uint8_t *img = image_ptr(base_a, base_b, split, b, img_stride, img_off);
         const int32_t *I = integral + (size_t)b * srows * W;
         const int gws = 2 * __float2int_rn(2 * s);

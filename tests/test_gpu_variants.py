@@ -141,3 +141,23 @@ def test_describe_tolerance_modes_within_stated_tolerance(gpu, synth_pair_rois, 
     print("describe=%d: max |d desc| %.2e mean %.2e identical descriptors %.1f %%, matches %d / %d common %d, votes %d / %d" % (
         mode, max(np.abs(e[1] - t[1]).max(), np.abs(e[3] - t[3]).max()), np.abs(e[1] - t[1]).mean(),
         100.0 * (np.abs(e[1] - t[1]).max(axis=1) == 0).mean(), len(me), len(mt), len(me & mt), e[7], t[7]))
+
+
+def test_describe_cooperative_giant_windows(gpu):
+    """Small batches describe windows of >= 320 px with the warps of a CTA sharing the 21 output rows (surf_describe.cuh,
+    cooperative pass) -- same descriptors as the reference sampler and the oracle.  The 1024 x 409 strip holds keypoints of the
+    top octave (sizes up to ~200 -> windows up to ~560 px) crossing every border."""
+    from imagestitch_b200 import synth
+    from oracle import surf
+    A, _, _ = synth.pair(seed=11, size=1024, overlap=110, direction=1)
+    img = np.ascontiguousarray(A[:409])
+    gpu.set_option("describe", 1)
+    k1, d1 = gpu.surf_detect_and_describe(img, extended=True, keypoints_ratio=0.0, hessian_threshold=100.0)
+    win = (21 * (k1[:, 2] * 1.2 / 9.0)).astype(int)
+    assert (win >= 320).sum() >= 3, int((win >= 320).sum())          # the pass has work
+    gpu.set_option("describe", 0)
+    k0, d0 = gpu.surf_detect_and_describe(img, extended=True, keypoints_ratio=0.0, hessian_threshold=100.0)
+    assert np.array_equal(k1, k0) and np.array_equal(d1, d0)
+    ko, do = surf.detect_and_compute(img, 100.0, 4, 3, True, False, 0)
+    big = win >= 320
+    assert np.array_equal(d1[big], do[big]) and np.array_equal(k1[big][:, :4], ko[big][:, :4])

@@ -10,6 +10,9 @@
 // Two kernels:
 //   describe_fixed_kernel      the product path.  Window positions in 32.32 fixed point (exact, see below), rows sampled in CHUNKS
 //                              of up to 32 warp-rounds whose texture gathers are issued four at a time, INTER_AREA folded row by row.
+//                              Small batches add a cooperative pass: the eight warps of a CTA share each window of >= 320 px by
+//                              output rows (describe_giants_kernel lists them).  Options describe = 2 / 3 swap the window pixel
+//                              for a tolerance-mode sampler (NOT bit-exact; sample_rounds_tol).
 //   describe_reference_kernel  row-at-a-time sampler in double precision straight from the u8 image (no texture, no exactness
 //                              preconditions).  Describes what the fixed kernel hands over (a work list: degenerate directions,
 //                              sub-2^-9 row starts), everything when vfsms_set_option("describe", 0), and upright keypoints.

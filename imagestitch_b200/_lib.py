@@ -32,7 +32,7 @@ EXPORTS = [
     "vfsms_orb_detect_and_describe", "vfsms_offset_by_mode", "vfsms_align_batch_host", "vfsms_align_batch_dev",
     "vfsms_match_batch_dev", "vfsms_phase_correlate_host", "vfsms_phase_correlate_dev", "vfsms_fuse_roi_host",
     "vfsms_mosaic_host", "vfsms_profile_enable", "vfsms_profile_read", "vfsms_stage_name",
-    "vfsms_set_matcher", "vfsms_last_match_fallbacks", "vfsms_last_match_bound_violations", "vfsms_align_batch_upload", "vfsms_align_batch_run", "vfsms_last_describe_handovers", "vfsms_enhance_host",
+    "vfsms_set_matcher", "vfsms_last_match_fallbacks", "vfsms_last_match_bound_violations", "vfsms_align_batch_upload", "vfsms_align_batch_run", "vfsms_tiles_attach", "vfsms_last_describe_handovers", "vfsms_enhance_host",
     "vfsms_jpeg_info", "vfsms_jpeg_luma_coefficients", "vfsms_jpeg_decode_gray_dev", "vfsms_jpeg_decode_gray_host",
     "vfsms_jpeg_component_coefficients", "vfsms_jpeg_decode_bgr_dev", "vfsms_jpeg_decode_bgr_host",
     "vfsms_tiles_reserve", "vfsms_tiles_decode_jpeg", "vfsms_tiles_upload", "vfsms_tiles_download", "vfsms_tiles_ptr",
@@ -78,6 +78,7 @@ def load():
     L.vfsms_offset_by_mode.argtypes = [vp, vp, i32, vp, i32, i32, vp, i32, i32, ctypes.POINTER(PairResult)]
     L.vfsms_align_batch_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, ctypes.POINTER(SurfParams), f32, i32, vp]
     L.vfsms_align_batch_dev.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, ctypes.POINTER(SurfParams), f32, i32, vp, vp]
+    L.vfsms_tiles_attach.argtypes = [vp, vp]
     L.vfsms_align_batch_upload.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, i64]
     L.vfsms_align_batch_run.argtypes = [vp, i32, ctypes.POINTER(SurfParams), f32, i32, vp]
     L.vfsms_match_batch_dev.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp]
@@ -116,14 +117,16 @@ def check(rc, what=""):
 _contexts = {}
 
 
-def context(device=0):
-    """One vfsms_ctx per (process, device)."""
-    if device not in _contexts:
+def context(device=0, lane=0):
+    """One vfsms_ctx per (process, device); lane > 0: an extra context of that device (own stream and workspaces) for calls that
+    should overlap with lane 0's, e.g. the second strip shape of a search round (gpu.tiles_attach)."""
+    key = device if lane == 0 else (device, lane)
+    if key not in _contexts:
         L = load()
         h = ctypes.c_void_p()
         check(L.vfsms_create(device, ctypes.byref(h)), "vfsms_create")
-        _contexts[device] = h
-    return _contexts[device]
+        _contexts[key] = h
+    return _contexts[key]
 
 
 def destroy_contexts():

@@ -200,6 +200,7 @@ void vfsms_destroy(vfsms_ctx *ctx)
     ctx->pinned_in.release(); ctx->pinned_out.release();
     for (auto &sl : ctx->slots) { sl.a.release(); sl.b.release(); if (sl.uploaded) cudaEventDestroy(sl.uploaded); }
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->tiles_borrowed) { ctx->tiles.p = nullptr; ctx->tiles.bytes = 0; }
     ctx->jpeg_pinned.release(); ctx->jpeg_coef.release(); ctx->jpeg_out.release(); ctx->jpeg_planes.release(); ctx->tiles.release(); ctx->tiles_bgr.release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -477,9 +478,22 @@ int vfsms_tiles_reserve(vfsms_ctx *ctx, int n_tiles, int rows, int cols)
     if (!ctx || n_tiles < 1 || rows < 1 || cols < 1) { vfsms_set_error("tiles_reserve: bad arguments"); return VFSMS_E_ARG; }
     CUDA_TRY(cudaSetDevice(ctx->device));
     int rc;
+    if (ctx->tiles_borrowed) { ctx->tiles.p = nullptr; ctx->tiles.bytes = 0; ctx->tiles_borrowed = false; }     // drop the alias, own a stack again
     if ((rc = ctx->tiles.reserve((size_t)n_tiles * rows * cols))) return rc;
     ctx->tiles_n = n_tiles; ctx->tiles_rows = rows; ctx->tiles_cols = cols;
     ctx->tiles_has_bgr.assign((size_t)n_tiles, 0);   // a new reservation starts without colour tiles
+    return 0;
+}
+
+int vfsms_tiles_attach(vfsms_ctx *ctx, vfsms_ctx *owner)
+{
+    if (!ctx || !owner || ctx == owner || !owner->tiles.p || ctx->device != owner->device) { vfsms_set_error("tiles_attach: bad arguments"); return VFSMS_E_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(owner->stream));          // uploads / decodes into the stack have landed
+    if (!ctx->tiles_borrowed) ctx->tiles.release();
+    ctx->tiles.p = owner->tiles.p; ctx->tiles.bytes = owner->tiles.bytes; ctx->tiles_borrowed = true;
+    ctx->tiles_n = owner->tiles_n; ctx->tiles_rows = owner->tiles_rows; ctx->tiles_cols = owner->tiles_cols;
+    ctx->tiles_has_bgr.assign((size_t)ctx->tiles_n, 0);
     return 0;
 }
 

@@ -165,6 +165,7 @@ struct vfsms_ctx {
     DevBuf jpeg_coef, jpeg_out, jpeg_planes;
     DevBuf tiles;              // device-resident tile stack [tiles_n][tiles_rows][tiles_cols] u8 (vfsms_tiles_*)
     int tiles_n = 0, tiles_rows = 0, tiles_cols = 0;
+    bool tiles_borrowed = false;   // `tiles` aliases another context's stack (vfsms_tiles_attach): never freed or resized here
     DevBuf tiles_bgr;          // colour twin of the stack [tiles_n][tiles_rows][tiles_cols][3] (BGR), allocated on first use
     std::vector<uint8_t> tiles_has_bgr;   // per slot: the colour twin holds this tile
     void *tex_cache = nullptr;     // texture objects over caller images (surf.cu)

@@ -649,14 +649,21 @@ def tiles_align(first, n_pairs, direction, roi_len, params=None, ratio=0.75, off
     return res
 
 
-def tiles_align_list(first_tiles, directions, roi_len, params=None, ratio=0.75, offset_evaluate=3, device=0):
+def tiles_attach(lane=1, device=0):
+    """Give the extra context `lane` of this device read access to lane 0's tile stack (vfsms_tiles_attach).  Call again after
+    lane 0 re-reserves its stack."""
+    check(_lib.load().vfsms_tiles_attach(_lib.context(device, lane), _lib.context(device)), "vfsms_tiles_attach")
+
+
+def tiles_align_list(first_tiles, directions, roi_len, params=None, ratio=0.75, offset_evaluate=3, device=0, lane=0):
     """One fused call for an arbitrary list of candidates: pair p = stack tiles (first_tiles[p], first_tiles[p] + 1) in
-    directions[p]; all directions must cut strips of one shape (1 / 3 or 2 / 4).  -> structured array like align_batch."""
+    directions[p]; all directions must cut strips of one shape (1 / 3 or 2 / 4).  -> structured array like align_batch.
+    lane: the context that runs the call (lane > 0 after tiles_attach(lane))."""
     p = params if params is not None else surf_params()
     ft = np.ascontiguousarray(first_tiles, np.int32); dr = np.ascontiguousarray(directions, np.int32)
     assert ft.ndim == 1 and ft.shape == dr.shape and len(ft) > 0
     res = np.zeros(len(ft), PAIR_RESULT_DTYPE)
-    check(_lib.load().vfsms_tiles_align_list(_lib.context(device), len(ft), ft.ctypes.data_as(ctypes.c_void_p), dr.ctypes.data_as(ctypes.c_void_p),
+    check(_lib.load().vfsms_tiles_align_list(_lib.context(device, lane), len(ft), ft.ctypes.data_as(ctypes.c_void_p), dr.ctypes.data_as(ctypes.c_void_p),
                                              int(roi_len), ctypes.byref(p), ctypes.c_float(ratio), int(offset_evaluate),
                                              res.ctypes.data_as(ctypes.c_void_p)), "vfsms_tiles_align_list")
     return res

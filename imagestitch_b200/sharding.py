@@ -174,9 +174,13 @@ def _run_requests(batch_evaluate, table, start_pair, requests):
     groups = {}
     for pair, i, d in requests:
         groups.setdefault((i, d in (2, 4)), []).append((pair, d))
-    for (i, _), items in sorted(groups.items()):
-        pairs = [p for p, _ in items]; dirs = [d for _, d in items]
-        res = np.asarray(batch_evaluate(pairs, i, dirs), np.int32).reshape(len(pairs), 4)
+    order = sorted(groups.items())
+    calls = [([p for p, _ in items], i, [d for _, d in items]) for (i, _), items in order]
+    # an evaluator with .many runs the groups of a round side by side (two strip shapes = two contexts on the GPU)
+    many = getattr(batch_evaluate, "many", None)
+    results = many(calls) if many is not None and len(calls) > 1 else [batch_evaluate(*c) for c in calls]
+    for ((i, _), items), res in zip(order, results):
+        res = np.asarray(res, np.int32).reshape(len(items), 4)
         for (pair, d), r in zip(items, res):
             table[pair - start_pair, i - 1, d - 1] = r
     return len(groups)
@@ -238,16 +242,42 @@ def align_sequence_sharded_batched(batch_evaluate, n_pairs, direction, direct_in
     return results, {"device_calls": calls, "extra_rounds": extra_rounds, "on_demand": on_demand}
 
 
-def tiles_batch_evaluator(first_tile, roi_lens, params=None, ratio=0.75, offset_evaluate=3, device=0):
+def tiles_batch_evaluator(first_tile, roi_lens, params=None, ratio=0.75, offset_evaluate=3, device=0, lanes=2):
     """batch_evaluate(pairs, i, directions) on the context's device-resident tile stack: stack slot `pair - first_tile` holds tile
     `pair`.  roi_lens(i, direction) -> ROI length in pixels (int(i * roiRatio * extent), ImageUtility.py:66-101).  The directions
-    of one call cut strips of one shape (sharding._run_requests groups them so)."""
+    of one call cut strips of one shape (sharding._run_requests groups them so).
+    lanes = 2: batch_evaluate.many(calls) runs the calls of one round on two contexts of the device from two host threads (the
+    second context borrows the stack, gpu.tiles_attach), so the row-strip and the column-strip candidates overlap on the GPU;
+    the results are those of running the calls one after the other."""
     from . import gpu
 
-    def batch_evaluate(pairs, i, directions):
+    def batch_evaluate(pairs, i, directions, lane=0):
         r = gpu.tiles_align_list([p - first_tile for p in pairs], directions, roi_lens(i, directions[0]), params=params, ratio=ratio,
-                                 offset_evaluate=offset_evaluate, device=device)
+                                 offset_evaluate=offset_evaluate, device=device, lane=lane)
         return np.stack([r["status"], r["d_row"], r["d_col"], r["votes"]], axis=1).astype(np.int32)
+
+    if lanes > 1:
+        import threading
+
+        def many(calls):
+            gpu.tiles_attach(1, device=device)      # every round: the stack may have been re-reserved since (a few microseconds)
+            out = [None] * len(calls)
+            errors = []
+
+            def work(lane):
+                try:
+                    for k in range(lane, len(calls), 2):
+                        out[k] = batch_evaluate(*calls[k], lane=lane)
+                except BaseException as e:          # re-raised on the calling thread
+                    errors.append(e)
+            t = threading.Thread(target=work, args=(1,))
+            t.start()
+            work(0)
+            t.join()
+            if errors:
+                raise errors[0]
+            return out
+        batch_evaluate.many = many
     return batch_evaluate
 
 

@@ -314,6 +314,11 @@ int vfsms_jpeg_encode_dev(vfsms_ctx *ctx, const uint8_t *img_dev, int rows, int 
  * appendix/myGpuFeatures.cpp:70).  Here the gray tiles of a sequence (all rows x cols) are decoded / uploaded ONCE into a
  * context-owned stack in HBM; alignment reads its ROI strips in place and the gray mosaic pastes from it. */
 int vfsms_tiles_reserve(vfsms_ctx *ctx, int n_tiles, int rows, int cols);
+/* A second context of the same device reads (never writes) the owner's gray stack: two contexts = two streams and two
+ * workspaces, so two vfsms_tiles_align* calls issued from two host threads overlap on the GPU (the row-strip and the
+ * column-strip candidates of one search round, sharding._run_requests).  The owner must outlive the borrower's use and must
+ * not re-reserve meanwhile; uploads / decodes go through the owner only.  Synchronises the owner's stream. */
+int vfsms_tiles_attach(vfsms_ctx *ctx, vfsms_ctx *owner);
 int vfsms_tiles_decode_jpeg(vfsms_ctx *ctx, int first, int n, const uint8_t *const *data, const size_t *sizes);   /* as vfsms_jpeg_decode_gray_dev */
 int vfsms_tiles_upload(vfsms_ctx *ctx, int first, int n, const uint8_t *tiles /* n x rows x cols, host */);
 int vfsms_tiles_download(vfsms_ctx *ctx, int first, int n, uint8_t *out /* n x rows x cols, host */);

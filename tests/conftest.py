@@ -20,9 +20,9 @@ if EMU:
     _vfsms_lib.SO_PATH = build_emu.build()
     _real_context = _vfsms_lib.context
 
-    def _emu_context(device=0):
-        fresh = device not in _vfsms_lib._contexts
-        h = _real_context(device)
+    def _emu_context(device=0, lane=0):
+        fresh = (device if lane == 0 else (device, lane)) not in _vfsms_lib._contexts
+        h = _real_context(device, lane)
         if fresh:       # match_tc.cu (tcgen05 inline PTX) is not emulated: the exact SIMT matcher, whatever a test selects
             L = _vfsms_lib.load()
             set_matcher = L.vfsms_set_matcher
@@ -41,7 +41,8 @@ def pytest_configure(config):
 
 
 # under emulation: no tcgen05 / TMA (inline PTX), no torch CUDA tensors, and the full-size cases would take hours
-_EMU_SKIP = ("test_gpu_match_tc.py", "test_gpu_fullsize.py", "test_decode_into_device_tile_stack", "test_describe_stacked_texture_row_limit_groups")
+_EMU_SKIP = ("test_gpu_match_tc.py", "test_gpu_fullsize.py", "test_decode_into_device_tile_stack", "test_describe_stacked_texture_row_limit_groups",
+             "test_two_contexts_run_a_round_side_by_side")      # the emulation runs one launch at a time: no second host thread
 
 
 # gpu tests of code that has not run on the B200 yet would be listed here (node-id substrings): they are ordered after everything

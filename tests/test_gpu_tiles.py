@@ -145,3 +145,43 @@ def test_tiles_align_list_equals_per_direction_calls():
     assert all(strided[k] == ref[2][2 * k] for k in range(3))
     with pytest.raises(gpu.VfsmsError):
         gpu.tiles_align_list([0, 1], [1, 2], L)                                  # mixed strip shapes
+
+
+def _small_stack():
+    from imagestitch_b200 import gpu, synth
+    tiles, _ = synth.tile_sequence(31, 2, 3, size=512, overlap=64)
+    tiles = np.stack(tiles)
+    gpu.tiles_reserve(len(tiles), 512, 512)
+    gpu.tiles_upload(0, tiles)
+
+
+_CALLS = [([0, 1, 3], 1, [1, 3, 1]), ([0, 1, 3, 4], 1, [2, 4, 2, 4]), ([2], 2, [1]), ([2, 3], 2, [4, 2])]
+
+
+def test_second_context_borrows_the_stack():
+    """vfsms_tiles_attach: a second context of the device reads lane 0's stack and gives lane 0's results."""
+    from imagestitch_b200 import gpu, sharding
+    _small_stack()
+    ev = sharding.tiles_batch_evaluator(0, lambda i, d: int(i * 0.2 * 512), lanes=1)
+    gpu.tiles_attach(1)
+    for c in _CALLS:
+        assert np.array_equal(ev(*c, lane=1), ev(*c))
+    _small_stack()                      # lane 0 re-reserves: attach again, same answers
+    gpu.tiles_attach(1)
+    assert np.array_equal(ev(*_CALLS[1], lane=1), ev(*_CALLS[1]))
+
+
+def test_two_contexts_run_a_round_side_by_side():
+    """The two strip shapes of a search round run from two host threads on two contexts
+    (sharding.tiles_batch_evaluator(...).many) and give the results of running them one after the other."""
+    from imagestitch_b200 import sharding
+    _small_stack()
+    ev = sharding.tiles_batch_evaluator(0, lambda i, d: int(i * 0.2 * 512), lanes=2)
+    for _ in range(3):
+        for c, got in zip(_CALLS, ev.many(_CALLS)):
+            assert np.array_equal(got, ev(*c))
+    # a sharded search through _run_requests uses .many for rounds with two shapes: same table as a one-lane evaluator
+    ev1 = sharding.tiles_batch_evaluator(0, lambda i, d: int(i * 0.2 * 512), lanes=1)
+    t2, _ = sharding.evaluate_shard_batched(ev, 0, 5, 1, 1, 0.2)
+    t1, _ = sharding.evaluate_shard_batched(ev1, 0, 5, 1, 1, 0.2)
+    assert np.array_equal(t1, t2)

@@ -155,6 +155,9 @@ def test_align_batches_stream_equals_one_call_per_batch(gpu):
             batches.append((A, B, tA, tB))
         else:
             batches.append((A, B))
+    assert list(gpu.align_batches(iter(()))) == []                       # nothing in, nothing out
+    one = list(gpu.align_batches([(batches[1][0], batches[1][1])]))      # a single batch: upload, run
+    assert len(one) == 1 and np.array_equal(one[0], gpu.align_batch(batches[1][0], batches[1][1]))
     streamed = list(gpu.align_batches((b[0], b[1]) for b in batches))
     assert len(streamed) == len(batches)
     for b, got in zip(batches, streamed):

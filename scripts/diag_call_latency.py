@@ -1,3 +1,6 @@
+"""Per-call cost of vfsms_tiles_align_list for small batches on one B200 (what a round of the sharded search costs):
+wall time per call and the describe / Hessian / matcher stage times for 1, 4, 8, 12 and 16 ROI pairs.
+  gpurun -- python scripts/diag_call_latency.py"""
 import time, sys
 import numpy as np, torch
 sys.path.insert(0, "/root/repo")

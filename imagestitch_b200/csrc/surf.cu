@@ -1475,18 +1475,19 @@ int surf_run_batch(vfsms_ctx *ctx, const uint8_t *base_a, const uint8_t *base_b,
                 // Small batches: one giant window (up to 768 px, 6 * 10^5 samples) on one warp is the whole tail of the launch
                 // (3 ms of a 3.5 ms single-pair call); the CTA's eight warps share such windows (surf_describe.cuh).
                 const bool coop = n_chunks == 1 && batch <= DESC_COOP_MAX_BATCH;
+                const int coop_split = batch <= 4 ? DESC_COOP_SPLIT_TINY : DESC_COOP_SPLIT;       // one or two pairs: share more windows
                 int *coop_list = fb_list + (size_t)batch * ws.kp_cap, *coop_count = work_counter + 3,
                     *coop_counter = work_counter + 4 + 2 * SURF_MAX_DESC_CHUNKS;
                 if (coop) {
                     describe_giants_kernel<<<std::min(ceil_div(batch * ws.kp_cap, 256), ctx->num_sms * 2), 256, 0, st>>>(
-                        ws.kp.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap, DESC_COOP_SPLIT, coop_list, coop_count);
+                        ws.kp.as<float>(), ws.prefix.as<int32_t>(), batch, ws.kp_cap, coop_split, coop_list, coop_count);
                     LAUNCH_CHECK(ctx);
                 }
 #define LAUNCH_COOP(MB, UU, NW, TT) describe_fixed_kernel<MB, UU, NW, TT, true><<<ctx->num_sms * MB, NW * 32, 0, st>>>(                                  \
                     base_a, base_b, split, img_stride, rows, cols, stride, ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), \
                     ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, ts[c], c * per, std::min(per, batch - c * per),                   \
                     work_counter + 4 + c, work_counter + 4 + SURF_MAX_DESC_CHUNKS + c, lpt_split, big_flag, fb_list, fb_count, ws.img_off,   \
-                    DESC_COOP_SPLIT, coop_list, coop_count, coop_counter)
+                    coop_split, coop_list, coop_count, coop_counter)
 #define LAUNCH_FIXED(MB, UU, NW, TT) describe_fixed_kernel<MB, UU, NW, TT><<<ctx->num_sms * MB, NW * 32, 0, st>>>(                                            \
                     base_a, base_b, split, img_stride, rows, cols, stride, ws.integral.as<int32_t>(), ws.kp.as<float>(), ws.desc.as<float>(), \
                     ws.prefix.as<int32_t>(), batch, ws.kp_cap, p->extended, ts[c], c * per, std::min(per, batch - c * per),                   \

@@ -38,6 +38,7 @@
 #define DESC_FIXED_U 4             // gathers in flight per lane
 #define DESC_COOP_SPLIT 320        // windows at least this wide are shared by the warps of a CTA ...
 #define DESC_COOP_MAX_BATCH 24     // ... in batches of at most this many images (larger batches fill the GPU without it)
+#define DESC_COOP_SPLIT_TINY 240   // threshold for batches of up to four images (measured: 1.53 vs 1.73 ms for a single pair)
 
 // bilinear / clamped sample of the rotated window, rounded to u8 exactly like the CPU loop (reference sampler)
 __device__ __forceinline__ int window_pixel(const uint8_t *__restrict__ img, int stride, int ncols1, int nrows1,

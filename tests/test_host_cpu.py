@@ -230,6 +230,60 @@ def test_sharding_batched_two_ranks_gloo(tmp_path):
     assert "GLOO_BATCHED_OK 22" in r.stdout
 
 
+GLOO_BATCHED_WORKER_4 = r"""
+import os, sys, threading
+import numpy as np
+sys.path.insert(0, os.environ["VFSMS_ROOT"])
+import torch.distributed as dist
+from imagestitch_b200 import sharding as sh
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# a 6 x 7 serpentine: runs of 6 pairs along a row (directions 2 / 4 alternating), one pair down (direction 1) at every row end
+true_dir = []
+for r in range(6):
+    true_dir += [2 if r % 2 == 0 else 4] * 6 + [1]
+true_dir = true_dir[:-1]
+n = len(true_dir)
+ranges = sh.partition_pairs(n, world)
+lo, hi = ranges[rank]
+def evaluate(pair, i, d):
+    return int(d == true_dir[pair] and i >= 1 + (pair % 7 == 3)), 50 + pair, pair - 3, 7
+threads_seen = set()
+def batch_evaluate(pairs, i, dirs):
+    assert all(lo <= p < hi for p in pairs), (rank, pairs)
+    assert len({d in (2, 4) for d in dirs}) == 1                     # one strip shape per call
+    threads_seen.add(threading.get_ident())
+    return [evaluate(p, i, d) for p, d in zip(pairs, dirs)]
+def many(calls):                                                     # the two-lane form of tiles_batch_evaluator, on host threads
+    out = [None] * len(calls)
+    def work(lane):
+        for k in range(lane, len(calls), 2):
+            out[k] = batch_evaluate(*calls[k])
+    t = threading.Thread(target=work, args=(1,)); t.start(); work(0); t.join()
+    return out
+batch_evaluate.many = many
+seq, _ = sh.replay(sh.evaluate_shard(evaluate, 0, n, 1, 1, 0.2), evaluate, 1, 1, 0.2)
+out, stats = sh.align_sequence_sharded_batched(batch_evaluate, n, 1, 1, 0.2, rank, world)
+assert out == seq, (rank, out, seq)
+assert len(threads_seen) == 2, threads_seen                          # rounds with both shapes really ran on two threads
+if rank == 0:
+    print("GLOO_BATCHED4_OK", len(out), world, stats["device_calls"])
+dist.destroy_process_group()
+"""
+
+
+def test_sharding_batched_four_ranks_two_lanes_gloo(tmp_path):
+    """Four shards of a serpentine, every round's two strip shapes evaluated side by side (batch_evaluate.many): the gathered
+    replay equals the sequential loop."""
+    script = tmp_path / "worker_batched4.py"
+    script.write_text(GLOO_BATCHED_WORKER_4)
+    env = dict(os.environ, VFSMS_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+                        "--master-port", "29545", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GLOO_BATCHED4_OK 41 4" in r.stdout
+
+
 def test_synthetic_generator_is_seeded():
     from imagestitch_b200 import synth
     a1, b1, o1 = synth.pair(seed=9, size=256, overlap=40, direction=1)
